@@ -1,0 +1,243 @@
+"""ORACLE (test infrastructure, never on the product path).
+
+LAMMPS-free CPU restatement of the reference pair style `PairNequIPAllegro<false>`
+(`pair_style allegro`), function by function, against the LAMMPS stand-in of
+oracle/lmp_harness.py.  Each method cites the reference lines it follows
+(/root/reference/pair_nequip_allegro.cpp).  The model call goes through torch.jit exactly
+as `call()` does (cpp:409-430): load with the five metadata keys (cpp:214-222), eval,
+freeze when not frozen (cpp:228-232), fusion strategy DYNAMIC/10 (cpp:259-263), TF32 flags
+from metadata (cpp:267-270).
+
+PARITY STATUS: the glue (coeff / preprocess / compute store) follows the reference source
+line by line and is pinned by the known-answer edge counts of SURVEY.md section 4 and by the
+real reference sources compiled into oracle/_ref (see oracle/Makefile); the network behind
+`forward` is this repo's own TorchScript model (oracle/allegro_torch.py) because the
+reference's model graph lives in un-vendored packages -- parity unpinned for that part.
+"""
+import os
+from typing import Dict, List, Optional
+
+import numpy as np
+import torch
+
+from .lmp_harness import NEIGHMASK, Atoms, NeighList
+
+
+class RefPairAllegro:
+    def __init__(self, debug_mode: bool = False):
+        # cpp:66-125 (constructor): restartinfo=0, manybody_flag=1, device = CPU here
+        self.restartinfo = 0
+        self.manybody_flag = 1
+        self.debug_mode = debug_mode
+        self.device = torch.device("cpu")
+        self.allocated = False
+        self.custom_output_names: List[str] = []
+        self.custom_output: Dict[str, torch.Tensor] = {}
+        self.eng_vdwl = 0.0
+        self.virial = np.zeros(6)
+        self.eatom = None
+        self.debug_lines: List[str] = []
+
+    # cpp:168-172
+    def settings(self, args: List[str]):
+        if len(args) > 0:
+            raise RuntimeError("Illegal pair_style command, too many arguments")
+
+    # cpp:174-330
+    def coeff(self, args: List[str], ntypes: int):
+        self.ntypes = ntypes
+        self.setflag = np.zeros((ntypes + 1, ntypes + 1), dtype=np.int32)
+        self.cutoff_matrix = np.zeros((ntypes, ntypes))
+        self.allocated = True
+        if len(args) != 3 + ntypes:
+            raise RuntimeError("Incorrect args for pair coefficients, should be * * <model>.nequip.pth/pt2 <type1> <type2> ... <typen>")
+        if args[0] != "*" or args[1] != "*":
+            raise RuntimeError("Incorrect args for pair coefficients")
+        self.model_path = args[2]
+        if self.model_path.endswith(".nequip.pth"):
+            self.use_aot = False
+        elif self.model_path.endswith(".nequip.pt2"):
+            self.use_aot = True
+            raise RuntimeError("AOT Inductor compiled model (`.nequip.pt2` extension) found but pair style not compiled with `NEQUIP_AOT_COMPILE`")
+        else:
+            raise RuntimeError("Only accepts model paths with extension `.nequip.pth` or `.nequip.pt2`, but found" + self.model_path)
+        metadata = {"r_max": "", "per_edge_type_cutoff": "", "type_names": "", "num_types": "", "allow_tf32": ""}
+        self.model = torch.jit.load(self.model_path, map_location=self.device, _extra_files=metadata)
+        self.model.eval()
+        if hasattr(self.model, "training"):
+            self.model = torch.jit.freeze(self.model)
+        metadata = {k: (v.decode() if isinstance(v, bytes) else v) for k, v in metadata.items()}
+        self.metadata = metadata
+        torch.jit.set_fusion_strategy([("DYNAMIC", 10)])
+        allow_tf32 = bool(int(metadata["allow_tf32"]))
+        torch.backends.cuda.matmul.allow_tf32 = allow_tf32
+        torch.backends.cudnn.allow_tf32 = allow_tf32
+        self.cutoff = float(metadata["r_max"])
+        self.type_mapper = [-1] * ntypes
+        num_model_types = int(float(metadata["num_types"]))
+        names = metadata["type_names"].split()
+        for i in range(num_model_types):
+            ele = names[i]
+            for itype in range(1, ntypes + 1):
+                if ele == args[itype + 3 - 1]:
+                    self.type_mapper[itype - 1] = i
+        for i in range(1, ntypes + 1):
+            for j in range(i, ntypes + 1):
+                if self.type_mapper[i - 1] >= 0 and self.type_mapper[j - 1] >= 0:
+                    self.setflag[i][j] = 1
+        if metadata["per_edge_type_cutoff"] != "":
+            vals = [float(v) for v in metadata["per_edge_type_cutoff"].split()]
+            reverse_type_mapper = [-1] * num_model_types
+            for i in range(ntypes):
+                reverse_type_mapper[self.type_mapper[i]] = i
+            k = 0
+            for i in range(num_model_types):
+                for j in range(num_model_types):
+                    cutij = vals[k]
+                    k += 1
+                    if reverse_type_mapper[i] >= 0 and reverse_type_mapper[j] >= 0:
+                        self.cutoff_matrix[reverse_type_mapper[i]][reverse_type_mapper[j]] = cutij
+        else:
+            self.cutoff_matrix[:, :] = self.cutoff
+
+    # cpp:137-156
+    def init_style(self, newton_pair: int = 1, tag_enable: int = 1):
+        if tag_enable == 0:
+            raise RuntimeError("Pair style Allegro requires atom IDs")
+        if newton_pair == 0:
+            raise RuntimeError("Pair style allegro requires newton pair on")
+
+    def init_one(self, i: int, j: int) -> float:
+        return self.cutoff
+
+    # cpp:457-650, Allegro branches, literal loops (small cases only)
+    def preprocess_loops(self, atom: Atoms, lst: NeighList):
+        x, tag, type_ = atom.x, atom.tag, atom.type
+        nlocal = atom.nlocal
+        inum = lst.inum
+        assert inum == nlocal
+        ntotal = inum + lst.gnum
+        ilist = lst.ilist
+        nedges = 0
+        neigh_per_atom = [0] * nlocal
+        for ii in range(nlocal):
+            i = ilist[ii]
+            jlist = lst.firstneigh(i)
+            for jj in range(lst.numneigh[i]):
+                j = int(jlist[jj]) & NEIGHMASK
+                dx = x[i][0] - x[j][0]
+                dy = x[i][1] - x[j][1]
+                dz = x[i][2] - x[j][2]
+                rsq = dx * dx + dy * dy + dz * dz
+                cutij = self.cutoff_matrix[type_[i] - 1][type_[j] - 1]
+                if rsq <= cutij * cutij:
+                    neigh_per_atom[ii] += 1
+                    nedges += 1
+        cumsum = [0] * nlocal
+        for ii in range(1, nlocal):
+            cumsum[ii] = cumsum[ii - 1] + neigh_per_atom[ii - 1]
+        pos = np.zeros((ntotal, 3))
+        edges = np.zeros((2, nedges), dtype=np.int64)
+        ij2type = np.zeros(ntotal, dtype=np.int64)
+        self.debug_lines = ["Allegro edges: i j rij"]
+        for ii in range(ntotal):
+            i = ilist[ii]
+            itag, itype = tag[i], type_[i]
+            pos[i] = x[i]
+            ij2type[i] = self.type_mapper[itype - 1]
+            if ii >= nlocal:
+                continue
+            jlist = lst.firstneigh(i)
+            edge_counter = cumsum[ii]
+            for jj in range(lst.numneigh[i]):
+                j = int(jlist[jj]) & NEIGHMASK
+                jtag, jtype = tag[j], type_[j]
+                dx = x[i][0] - x[j][0]
+                dy = x[i][1] - x[j][1]
+                dz = x[i][2] - x[j][2]
+                rsq = dx * dx + dy * dy + dz * dz
+                cutij = self.cutoff_matrix[itype - 1][jtype - 1]
+                if rsq > cutij * cutij:
+                    continue
+                edges[0][edge_counter] = i
+                edges[1][edge_counter] = j
+                if self.debug_mode:
+                    self.debug_lines.append("%d %d %.10g" % (itag - 1, jtag - 1, np.sqrt(rsq)))
+                edge_counter += 1
+        self.debug_lines.append("end Allegro edges")
+        return {"pos": torch.from_numpy(pos), "edge_index": torch.from_numpy(edges),
+                "atom_types": torch.from_numpy(ij2type)}
+
+    # same semantics, vectorised (identical output incl. edge order; used at larger sizes)
+    def preprocess(self, atom: Atoms, lst: NeighList):
+        x, type_ = atom.x, atom.type
+        nlocal = atom.nlocal
+        ntotal = lst.inum + lst.gnum
+        ilist = lst.ilist
+        ii_of = np.repeat(np.arange(nlocal), lst.numneigh[ilist[:nlocal]])
+        i = ilist[ii_of].astype(np.int64)
+        # rows in ilist order, each row in jlist order
+        if np.array_equal(ilist[:nlocal], np.arange(nlocal)) and lst.first[0] == 0 and \
+                np.array_equal(lst.first[1:nlocal], np.cumsum(lst.numneigh[:nlocal])[:-1]):
+            j = lst.neigh_flat[:len(i)].astype(np.int64) & NEIGHMASK
+        else:
+            j = np.concatenate([lst.firstneigh(k) for k in ilist[:nlocal]]).astype(np.int64) & NEIGHMASK
+        dx = x[i, 0] - x[j, 0]
+        dy = x[i, 1] - x[j, 1]
+        dz = x[i, 2] - x[j, 2]
+        rsq = dx * dx + dy * dy + dz * dz
+        cutij = self.cutoff_matrix[type_[i] - 1, type_[j] - 1]
+        keep = rsq <= cutij * cutij
+        edges = np.stack([i[keep], j[keep]])
+        pos = np.zeros((ntotal, 3))
+        ij2type = np.zeros(ntotal, dtype=np.int64)
+        idx = ilist[:ntotal]
+        pos[idx] = x[idx]
+        ij2type[idx] = np.asarray(self.type_mapper, dtype=np.int64)[type_[idx] - 1]
+        if self.debug_mode:
+            self.debug_lines = ["Allegro edges: i j rij"] + [
+                "%d %d %.10g" % (atom.tag[a] - 1, atom.tag[b] - 1, np.sqrt(r))
+                for a, b, r in zip(i[keep], j[keep], rsq[keep])] + ["end Allegro edges"]
+        return {"pos": torch.from_numpy(pos), "edge_index": torch.from_numpy(edges),
+                "atom_types": torch.from_numpy(ij2type)}
+
+    # cpp:409-430
+    def call(self, inp: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
+        return dict(self.model(inp))
+
+    # cpp:333-407
+    def compute(self, atom: Atoms, lst: NeighList, eflag: int = 1, vflag: int = 1, eflag_atom: int = 1,
+                vflag_atom: int = 0, loops: bool = False):
+        f = atom.f
+        inum = lst.inum
+        if inum == 0:
+            return
+        ntotal = inum + lst.gnum
+        ilist = lst.ilist
+        inp = self.preprocess_loops(atom, lst) if loops else self.preprocess(atom, lst)
+        self.last_input = inp
+        out = self.call(inp)
+        forces = out["forces"].detach().cpu().numpy()
+        atomic_energies = out["atomic_energy"].detach().cpu().numpy()
+        self.eng_vdwl = 0.0
+        if eflag_atom:
+            self.eatom = np.zeros(len(atom.x))
+        idx = ilist[:ntotal]
+        f[idx] += forces[idx]
+        if eflag_atom:
+            self.eatom[ilist[:inum]] = atomic_energies[ilist[:inum], 0]
+        self.eng_vdwl = float(atomic_energies[ilist[:inum], 0].sum())
+        if vflag:
+            v = out["virial"].detach().cpu().numpy()
+            self.virial[:] = [v[0][0][0], v[0][1][1], v[0][2][2], v[0][0][1], v[0][0][2], v[0][1][2]]
+        if vflag_atom:
+            raise RuntimeError("Pair styles nequip and allegro do not support per-atom virial")
+        for name in self.custom_output_names:
+            if name not in out:
+                raise RuntimeError("missing " + name)
+            self.custom_output[name] = out[name].detach()
+        self.last_output = {k: v.detach() for k, v in out.items()}
+
+    # cpp:681-684
+    def add_custom_output(self, name: str):
+        self.custom_output_names.append(name)
