@@ -1,0 +1,151 @@
+/* allegro_b200.h -- C-ABI of the B200-native Allegro force evaluation.
+ *
+ * Drop-in boundary for the hot path of mir-group/pair_allegro: everything the reference
+ * does between `PairNequIPAllegro<false>::compute()` entering and leaving
+ * (pair_nequip_allegro.cpp:333-407: preprocess() :457-650, call() :409-454 i.e. the whole
+ * libtorch model execution, and the output store :358-393) and its Kokkos twin
+ * (pair_nequip_allegro_kokkos.cpp:87-353) happens behind these entry points, in hand-written
+ * sm_100a CUDA kernels.  No C++ types, no libtorch, no exceptions cross this boundary.
+ *
+ * Conventions
+ *   - every function returns 0 on success or a negative ALG_E* code; the message is
+ *     available through alg_last_error() (never throws; the host pair style converts to
+ *     LAMMPS error->all / error->one, cf. pair_nequip_allegro.cpp:87,115,139,149,186,394).
+ *   - the caller owns every pointer it passes; the handle owns all device scratch (grown
+ *     geometrically, never per-step cudaMalloc in steady state); pointers returned by
+ *     alg_get_* stay valid until the next alg_compute_* / alg_destroy on that handle.
+ *   - one handle = one CUDA device = one caller thread (one LAMMPS rank), all work on one
+ *     stream.  alg_compute_host is synchronous; alg_compute_device is stream-ordered except
+ *     for the scalar outputs (see below).
+ *   - dtypes at the boundary are LAMMPS': double x/f/energies/virial
+ *     (pair_nequip_allegro.h:73-75), 32-bit int indices; int64 only in alg_get_edges
+ *     (the reference's edge_index tensor, pair_nequip_allegro.cpp:526-527).
+ */
+#ifndef ALLEGRO_B200_H
+#define ALLEGRO_B200_H
+
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define ALG_API __attribute__((visibility("default")))
+#else
+#define ALG_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct alg_handle alg_handle;
+
+enum {
+  ALG_OK = 0,
+  ALG_EINVAL = -1,   /* bad argument / unsupported model hyper-parameters */
+  ALG_EIO = -2,      /* weight file missing or malformed */
+  ALG_ECUDA = -3,    /* CUDA runtime error (no device, out of memory, launch failure) */
+  ALG_ESTATE = -4,   /* call order violated (e.g. compute before set_type_map) */
+  ALG_ENOTFOUND = -5 /* unknown output / option name */
+};
+
+/* Replaces the model load in coeff(): torch::jit::load(model_path, device, metadata)
+ * (pair_nequip_allegro.cpp:213-232) / AOTIModelPackageLoader (:238).  `weight_path` is the
+ * `.alg` file written by the offline exporter (python -m pair_allegro_b200.export).
+ * `cuda_device` is the device index chosen by the pair style (node-local rank,
+ * pair_nequip_allegro.cpp:91-120).  There is no CPU fallback: without a usable device this
+ * returns ALG_ECUDA. */
+ALG_API int alg_create(const char* weight_path, int cuda_device, alg_handle** out);
+ALG_API void alg_destroy(alg_handle* h);
+
+/* message of the last failing call on `h`; with h == NULL: of the last failing alg_create. */
+ALG_API const char* alg_last_error(const alg_handle* h);
+
+/* The five metadata keys the reference reads from the model file
+ * (pair_nequip_allegro.cpp:214-220, used at :267-328).  `type_names` is space separated;
+ * `per_edge_type_cutoff` is num_types x num_types row-major [centre][neighbour] in MODEL type
+ * order, or NULL when the model has a single r_max.  Any out pointer may be NULL. */
+ALG_API int alg_metadata(const alg_handle* h, double* r_max, int* num_types, const char** type_names,
+                 const double** per_edge_type_cutoff, int* allow_tf32);
+
+/* Replaces the tail of coeff() (pair_nequip_allegro.cpp:274-328; Kokkos copy
+ * pair_nequip_allegro_kokkos.cpp:365-386): `lammps_type_to_model[t-1]` = model type index of
+ * LAMMPS type t (type_mapper, -1 = unmapped), `cutoff_matrix` = ntypes x ntypes row-major,
+ * indexed [centre LAMMPS type-1][neighbour LAMMPS type-1] (may be asymmetric). */
+ALG_API int alg_set_type_map(alg_handle* h, int ntypes, const int* lammps_type_to_model,
+                     const double* cutoff_matrix);
+
+/* Options (string key/value, all optional):
+ *   "filter"       "le" (default; host path rsq <= cut^2, pair_nequip_allegro.cpp:507,599)
+ *                  | "lt" (Kokkos path rsq < cut^2, pair_nequip_allegro_kokkos.cpp:189)
+ *   "chunk_edges"  edges processed per pipeline pass (activation buffers are sized by this)
+ *   "keep_edges"   "1": materialise the int64 [2,E] edge_index for alg_get_edges
+ *   "debug"        "1": keep per-edge gradients / intermediates for alg_get_output */
+ALG_API int alg_set_option(alg_handle* h, const char* key, const char* value);
+
+/* Host-pointer force evaluation: replaces the body of PairNequIPAllegro<false>::compute()
+ * (pair_nequip_allegro.cpp:333-407).
+ *   nlocal, nghost : atom->nlocal (== list->inum, :470) and list->gnum (:344)
+ *   x              : atom->x, [nlocal+nghost][3] contiguous doubles
+ *   type           : atom->type, 1-based LAMMPS types, [nlocal+nghost]
+ *   ilist,numneigh,firstneigh : the FULL neighbour list of the local atoms (:340-350,476-480);
+ *                    numneigh/firstneigh are indexed by atom index i = ilist[ii];
+ *                    neighbour entries are masked with NEIGHMASK (:496)
+ *   eflag_atom     : write eatom[i] (assigned, locals only, :378) when non-zero and eatom != NULL
+ *   vflag_global   : write virial6 (assigned, LAMMPS order xx,yy,zz,xy,xz,yz, :387-392)
+ *   f              : atom->f, [nlocal+nghost][3]; model forces are ADDED for local AND ghost
+ *                    atoms (newton on, :370-377); LAMMPS reverse-communicates afterwards
+ *   eng            : eng_vdwl = sum of LOCAL atomic energies (:379)
+ * nlocal == 0 is a valid no-op (:341). */
+ALG_API int alg_compute_host(alg_handle* h, int nlocal, int nghost, const double* x, const int* type,
+                     const int* ilist, const int* numneigh, int* const* firstneigh,
+                     int eflag_atom, int vflag_global,
+                     double* f, double* eatom, double* eng, double* virial6);
+
+/* Device-pointer force evaluation: replaces PairAllegroKokkos<false>::compute()
+ * (pair_nequip_allegro_kokkos.cpp:87-353).  All d_* pointers are device memory on the
+ * handle's device.  Neighbours are the Kokkos 2-D view d_neighbors(i,jj) addressed as
+ * d_neighbors[i*stride_i + jj*stride_jj] (:126,176).  d_f is accumulated in place (:308-310),
+ * d_eatom (may be NULL) assigned for locals (:311-313).  `eng` and `virial6` are HOST
+ * pointers written before return (the call synchronises the stream once for them, like
+ * the reference's parallel_reduce result :318 and virial .cpu() :329); pass NULL for both
+ * to keep the call fully asynchronous.  `stream` is a cudaStream_t (0 = legacy default). */
+ALG_API int alg_compute_device(alg_handle* h, int nlocal, int nghost, const double* d_x, const int* d_type,
+                       const int* d_ilist, const int* d_numneigh, const int* d_neighbors,
+                       int64_t stride_i, int64_t stride_jj,
+                       int eflag_atom, int vflag_global,
+                       double* d_f, double* d_eatom, double* eng, double* virial6, void* stream);
+
+/* The edge list of the last compute in the reference's tensor layout
+ * (edge_index int64 [2][E], row 0 = centre atom index, row 1 = neighbour atom index with
+ * ghost indices kept; pair_nequip_allegro.cpp:601-602).  Host memory.  Requires option
+ * keep_edges=1 before the compute.  This is the parity hook for the reference's debug
+ * dump "Allegro edges: i j rij" (:562-565,620-633). */
+ALG_API int alg_get_edges(alg_handle* h, const int64_t** edge_index, int64_t* nedges);
+
+/* Named outputs of the last compute (host memory, doubles) -- the hook `compute allegro`
+ * / `compute allegro/atom` use (compute/compute_allegro.cpp:113-116,148-150 read
+ * pair->custom_output[name]).  Always available: "atomic_energy" [ntot] (ghost rows =
+ * per-type shift, as the model returns them), "forces" [ntot*3], "virial" [9],
+ * "edge_energy" [E] (needs debug=1).  With debug=1 single-chunk runs also expose
+ * intermediates for parity tests ("x0","x1","gamma0","edge_grad",...). */
+ALG_API int alg_get_output(alg_handle* h, const char* name, const double** ptr, int64_t* n);
+
+/* Per-phase device time of the last compute in milliseconds (CUDA events on the handle's
+ * stream): [0] edge build, [1] network forward+backward, [2] finalize/store. */
+ALG_API int alg_get_timings(alg_handle* h, double* ms3);
+
+/* Ghost halo helpers for spatial-domain multi-GPU runs (replace LAMMPS
+ * comm->forward_comm / reverse_comm pack/unpack for x and f; the transport between ranks is
+ * NCCL and lives in the caller).  Device pointers; stream-ordered.
+ *   pack:        buf[k][0..2] = x[list[k]][0..2] + shift[0..2]
+ *   unpack_add:  f[list[k]][0..2] += buf[k][0..2]        (list entries must be unique) */
+ALG_API int alg_halo_pack(const double* d_x, const int* d_list, int n, const double shift[3], double* d_buf,
+                  void* stream);
+ALG_API int alg_halo_unpack_add(double* d_f, const int* d_list, int n, const double* d_buf, void* stream);
+
+/* library / build identification, e.g. "allegro_b200 0.1.0 sm_100a" */
+ALG_API const char* alg_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ALLEGRO_B200_H */

@@ -1,0 +1,189 @@
+"""ctypes binding of the C-ABI (include/allegro_b200.h).
+
+This is the reference-side binding a maintainer would write for a Python driver; the LAMMPS
+pair style (src/pair_allegro_b200.cpp) binds the same symbols from C++.  There is NO fallback:
+if the shared library is missing or no CUDA device is usable, an exception is raised.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "liballegro_b200.so")
+
+EXPORTS = ["alg_create", "alg_destroy", "alg_last_error", "alg_metadata", "alg_set_type_map", "alg_set_option",
+           "alg_compute_host", "alg_compute_device", "alg_get_edges", "alg_get_output", "alg_get_timings",
+           "alg_halo_pack", "alg_halo_unpack_add", "alg_version"]
+
+_lib = None
+
+
+class AllegroError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("allegro_b200 error %d: %s" % (code, msg))
+        self.code = code
+
+
+def load_library(path=None):
+    """dlopen liballegro_b200.so and declare prototypes.  Raises if the library is absent."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    p = path or LIB_PATH
+    if not os.path.exists(p):
+        raise FileNotFoundError(
+            "%s not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(or `make -C pair_allegro_b200/csrc`); there is no CPU fallback" % p)
+    lib = C.CDLL(p)
+    vp, ip, dp = C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_double)
+    lib.alg_create.argtypes = [C.c_char_p, C.c_int, C.POINTER(vp)]
+    lib.alg_create.restype = C.c_int
+    lib.alg_destroy.argtypes = [vp]
+    lib.alg_destroy.restype = None
+    lib.alg_last_error.argtypes = [vp]
+    lib.alg_last_error.restype = C.c_char_p
+    lib.alg_metadata.argtypes = [vp, dp, ip, C.POINTER(C.c_char_p), C.POINTER(dp), ip]
+    lib.alg_metadata.restype = C.c_int
+    lib.alg_set_type_map.argtypes = [vp, C.c_int, ip, dp]
+    lib.alg_set_type_map.restype = C.c_int
+    lib.alg_set_option.argtypes = [vp, C.c_char_p, C.c_char_p]
+    lib.alg_set_option.restype = C.c_int
+    lib.alg_compute_host.argtypes = [vp, C.c_int, C.c_int, dp, ip, ip, ip, C.POINTER(ip), C.c_int, C.c_int, dp, dp, dp, dp]
+    lib.alg_compute_host.restype = C.c_int
+    lib.alg_compute_device.argtypes = [vp, C.c_int, C.c_int, vp, vp, vp, vp, vp, C.c_int64, C.c_int64, C.c_int, C.c_int,
+                                       vp, vp, dp, dp, vp]
+    lib.alg_compute_device.restype = C.c_int
+    lib.alg_get_edges.argtypes = [vp, C.POINTER(C.POINTER(C.c_int64)), C.POINTER(C.c_int64)]
+    lib.alg_get_edges.restype = C.c_int
+    lib.alg_get_output.argtypes = [vp, C.c_char_p, C.POINTER(dp), C.POINTER(C.c_int64)]
+    lib.alg_get_output.restype = C.c_int
+    lib.alg_get_timings.argtypes = [vp, dp]
+    lib.alg_get_timings.restype = C.c_int
+    lib.alg_halo_pack.argtypes = [vp, vp, C.c_int, dp, vp, vp]
+    lib.alg_halo_pack.restype = C.c_int
+    lib.alg_halo_unpack_add.argtypes = [vp, vp, C.c_int, vp, vp]
+    lib.alg_halo_unpack_add.restype = C.c_int
+    lib.alg_version.argtypes = []
+    lib.alg_version.restype = C.c_char_p
+    if path is None:
+        _lib = lib
+    return lib
+
+
+def _dptr(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def _iptr(a):
+    return a.ctypes.data_as(C.POINTER(C.c_int))
+
+
+class Handle:
+    """thin RAII wrapper over alg_handle*"""
+
+    def __init__(self, weight_path, device=0):
+        self.lib = load_library()
+        self.h = C.c_void_p()
+        rc = self.lib.alg_create(os.fsencode(weight_path), int(device), C.byref(self.h))
+        if rc != 0:
+            msg = self.lib.alg_last_error(None).decode()
+            self.h = None
+            raise AllegroError(rc, msg)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.alg_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != 0:
+            raise AllegroError(rc, self.lib.alg_last_error(self.h).decode())
+
+    def metadata(self):
+        r = C.c_double()
+        n = C.c_int()
+        names = C.c_char_p()
+        pc = C.POINTER(C.c_double)()
+        tf = C.c_int()
+        self._check(self.lib.alg_metadata(self.h, C.byref(r), C.byref(n), C.byref(names), C.byref(pc), C.byref(tf)))
+        T = n.value
+        cut = None
+        if pc:
+            cut = np.array([pc[i] for i in range(T * T)]).reshape(T, T)
+        return dict(r_max=r.value, num_types=T, type_names=names.value.decode().split(), per_edge_type_cutoff=cut,
+                    allow_tf32=bool(tf.value))
+
+    def set_type_map(self, type_mapper, cutoff_matrix):
+        tm = np.ascontiguousarray(type_mapper, dtype=np.int32)
+        cm = np.ascontiguousarray(cutoff_matrix, dtype=np.float64)
+        assert cm.shape == (len(tm), len(tm))
+        self._check(self.lib.alg_set_type_map(self.h, len(tm), _iptr(tm), _dptr(cm)))
+
+    def set_option(self, key, value):
+        self._check(self.lib.alg_set_option(self.h, key.encode(), str(value).encode()))
+
+    def compute_host(self, x, type_, ilist, numneigh, neigh_flat, first, nlocal, nghost, f, eatom=None, vflag=True):
+        """x [ntot,3] f64, type_ [ntot] i32, list given as flat neighbours + per-atom offsets
+        (converted here into the int** firstneigh LAMMPS passes).  f is accumulated in place.
+        returns (eng_vdwl, virial6)"""
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        type_ = np.ascontiguousarray(type_, dtype=np.int32)
+        ilist = np.ascontiguousarray(ilist, dtype=np.int32)
+        numneigh = np.ascontiguousarray(numneigh, dtype=np.int32)
+        neigh_flat = np.ascontiguousarray(neigh_flat, dtype=np.int32)
+        assert f.dtype == np.float64 and f.flags.c_contiguous and f.shape == x.shape
+        base = neigh_flat.ctypes.data if neigh_flat.size else 0
+        ptrs = (base + np.asarray(first, dtype=np.int64) * 4).astype(np.uint64)
+        ptrs = np.ascontiguousarray(ptrs)
+        eng = C.c_double()
+        vir = np.zeros(6)
+        self._check(self.lib.alg_compute_host(
+            self.h, int(nlocal), int(nghost), _dptr(x), _iptr(type_), _iptr(ilist), _iptr(numneigh),
+            ptrs.ctypes.data_as(C.POINTER(C.POINTER(C.c_int))), 1 if eatom is not None else 0, 1 if vflag else 0,
+            _dptr(f), _dptr(eatom) if eatom is not None else None, C.byref(eng), _dptr(vir)))
+        self._keep = (x, type_, ilist, numneigh, neigh_flat, ptrs)
+        return eng.value, vir
+
+    def compute_device(self, nlocal, nghost, d_x, d_type, d_ilist, d_numneigh, d_neighbors, stride_i, stride_jj,
+                       d_f, d_eatom=0, want_scalars=True, vflag=True, stream=0):
+        """all d_* are raw device addresses (ints).  returns (eng, virial6) or (None, None)."""
+        eng = C.c_double()
+        vir = np.zeros(6)
+        self._check(self.lib.alg_compute_device(
+            self.h, int(nlocal), int(nghost), d_x, d_type, d_ilist, d_numneigh, d_neighbors, int(stride_i), int(stride_jj),
+            1 if d_eatom else 0, 1 if vflag else 0, d_f, d_eatom or None,
+            C.byref(eng) if want_scalars else None, _dptr(vir) if want_scalars else None, stream or None))
+        return (eng.value, vir) if want_scalars else (None, None)
+
+    def get_edges(self):
+        p = C.POINTER(C.c_int64)()
+        n = C.c_int64()
+        self._check(self.lib.alg_get_edges(self.h, C.byref(p), C.byref(n)))
+        E = n.value
+        if E == 0:
+            return np.zeros((2, 0), dtype=np.int64)
+        return np.ctypeslib.as_array(p, shape=(2 * E,)).reshape(2, E).copy()
+
+    def get_output(self, name):
+        p = C.POINTER(C.c_double)()
+        n = C.c_int64()
+        self._check(self.lib.alg_get_output(self.h, name.encode(), C.byref(p), C.byref(n)))
+        if n.value == 0:
+            return np.zeros(0)
+        return np.ctypeslib.as_array(p, shape=(n.value,)).copy()
+
+    def timings(self):
+        t = np.zeros(3)
+        self._check(self.lib.alg_get_timings(self.h, _dptr(t)))
+        return t
+
+
+def version():
+    return load_library().alg_version().decode()

@@ -1,0 +1,859 @@
+// C-ABI of the Allegro B200 engine (include/allegro_b200.h): weight loader, device scratch
+// management, edge-list build from the LAMMPS full neighbour list, chunked pipeline
+// orchestration, output store.  Replaces /root/reference/pair_nequip_allegro.cpp:333-650
+// (compute/preprocess/call) and pair_nequip_allegro_kokkos.cpp:87-353.  No libtorch, no CPU
+// fallback: every failure surfaces as an error code.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <sstream>
+#include <string>
+#include <vector>
+
+#include <cub/device/device_scan.cuh>
+
+#include "../../include/allegro_b200.h"
+#include "alg_pipeline.cuh"
+
+namespace alg {
+const Pipeline* get_pipeline(int L) {
+  switch (L) {
+    case 1: return get_pipeline_L1();
+    case 2: return get_pipeline_L2();
+    case 3: return get_pipeline_L3();
+  }
+  return nullptr;
+}
+}  // namespace alg
+
+using namespace alg;
+
+#define NEIGHMASK 0x1FFFFFFF
+
+static std::string g_create_error;
+
+// ------------------------------------------------------------------------------------------
+// device buffer that only grows (geometric), never shrinks
+// ------------------------------------------------------------------------------------------
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t ensure(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    size_t want = std::max(bytes, cap + cap / 2);
+    want = (want + 255) / 256 * 256;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e != cudaSuccess) { cap = 0; p = nullptr; return e; }
+    cap = want;
+    return cudaSuccess;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+  template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+struct PinBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t ensure(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    size_t want = std::max(bytes, cap + cap / 2);
+    cudaError_t e = cudaMallocHost(&p, want);
+    if (e != cudaSuccess) { cap = 0; p = nullptr; return e; }
+    cap = want;
+    return cudaSuccess;
+  }
+  void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+  template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct HostTensor { std::string dtype; std::vector<long> dims; std::vector<char> data; size_t count() const { size_t n = 1; for (long d : dims) n *= d; return n; } };
+
+struct alg_handle {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  // model
+  std::map<std::string, std::string> header;
+  std::map<std::string, HostTensor> tensors;
+  int L = 0, nl = 0, T = 0, B = 0;
+  double r_max = 0, avg_n = 1, p = 6;
+  std::string type_names;
+  std::vector<double> per_edge_cut;   // T*T or empty
+  std::vector<double> cut_table;      // T*T (model types)
+  std::vector<double> scales, shifts;
+  int allow_tf32 = 0;
+  DevBuf weights;
+  ModelW mw{};
+  const Pipeline* pipe = nullptr;
+  PipelineInfo pinfo{};
+  // type map
+  int ntypes = 0;
+  DevBuf d_tmap, d_cutsq, d_scale, d_shift;
+  bool have_map = false;
+  // options
+  bool filter_le = true, keep_edges = false, debug = false;
+  long chunk_edges = 1 << 20;
+  // per-step scratch
+  DevBuf d_x, d_type, d_ilist, d_numneigh, d_cand, d_first, d_cnt, d_rowptr, d_scan_tmp;
+  DevBuf d_mtype, d_edge_j, d_edge_c, d_rvec, d_esum, d_facc, d_vacc, d_forces, d_eall, d_red, d_edge_index, d_edge_energy, d_edge_grad, d_eatom_out;
+  DevBuf c_X[3], c_W0, c_V[3], c_dX, c_dV[2], c_dY, c_du, c_gamma[3], c_dgamma[3], c_carry, c_ecarry;
+  PinBuf h_stage, h_rowptr, h_out, h_first;
+  // results
+  int last_nlocal = 0, last_ntot = 0;
+  long last_E = 0;
+  std::vector<int64_t> edges_host;
+  std::map<std::string, std::vector<double>> outputs;
+  double timings[3] = {0, 0, 0};
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  // debug bookkeeping of the last single-chunk run
+  int dbg_ntiles = 0, dbg_c0 = 0, dbg_ncent = 0;
+};
+
+#define CK(call)                                                                                      \
+  do {                                                                                                \
+    cudaError_t _e = (call);                                                                          \
+    if (_e != cudaSuccess) {                                                                          \
+      h->err = std::string("CUDA error: ") + cudaGetErrorString(_e) + " at " + __FILE__ + ":" + std::to_string(__LINE__) + " (" #call ")"; \
+      return ALG_ECUDA;                                                                               \
+    }                                                                                                 \
+  } while (0)
+
+static int fail(alg_handle* h, int code, const std::string& msg) { h->err = msg; return code; }
+
+// ------------------------------------------------------------------------------------------
+// .alg reader (format: pair_allegro_b200/export.py)
+// ------------------------------------------------------------------------------------------
+static bool read_alg(const char* path, alg_handle* h, std::string& err) {
+  FILE* f = fopen(path, "rb");
+  if (!f) { err = std::string("cannot open weight file ") + path; return false; }
+  fseek(f, 0, SEEK_END);
+  long sz = ftell(f);
+  fseek(f, 0, SEEK_SET);
+  std::vector<char> raw(sz);
+  if (sz <= 0 || fread(raw.data(), 1, sz, f) != (size_t)sz) { fclose(f); err = "short read on weight file"; return false; }
+  fclose(f);
+  std::string all(raw.data(), std::min<long>(sz, 1 << 20));
+  size_t endp = all.find("\nend\n");
+  if (all.compare(0, 9, "ALGB200 1") != 0 || endp == std::string::npos) { err = std::string(path) + " is not an ALGB200 version-1 weight file"; return false; }
+  std::istringstream in(all.substr(0, endp + 1));
+  std::string line;
+  long data_offset = -1;
+  std::getline(in, line);
+  while (std::getline(in, line)) {
+    if (line.empty()) continue;
+    size_t sp = line.find(' ');
+    std::string key = line.substr(0, sp), val = sp == std::string::npos ? "" : line.substr(sp + 1);
+    if (key == "data_offset") { data_offset = atol(val.c_str()); continue; }
+    if (key == "tensor") {
+      std::istringstream ts(val);
+      std::string name, dt; int nd;
+      ts >> name >> dt >> nd;
+      HostTensor t; t.dtype = dt;
+      for (int i = 0; i < nd; ++i) { long d; ts >> d; t.dims.push_back(d); }
+      long off, nb; ts >> off >> nb;
+      if (data_offset < 0 || data_offset + off + nb > sz) { err = "tensor " + name + " out of file bounds"; return false; }
+      t.data.assign(raw.begin() + data_offset + off, raw.begin() + data_offset + off + nb);
+      h->tensors[name] = std::move(t);
+    } else {
+      h->header[key] = val;
+    }
+  }
+  return true;
+}
+
+static const float* tf32(alg_handle* h, const std::string& name, long d0, long d1, std::string& err) {
+  auto it = h->tensors.find(name);
+  if (it == h->tensors.end()) { err = "weight file misses tensor " + name; return nullptr; }
+  const HostTensor& t = it->second;
+  long n = 1; for (long d : t.dims) n *= d;
+  if (t.dtype != "f32" || n != d0 * d1) {
+    err = "tensor " + name + " has unexpected shape/dtype (expected " + std::to_string(d0) + "x" + std::to_string(d1) + " f32)";
+    return nullptr;
+  }
+  return reinterpret_cast<const float*>(t.data.data());
+}
+
+// ------------------------------------------------------------------------------------------
+// edge build kernels (K1): LAMMPS full list -> centre-sorted CSR, same filter and same
+// (ilist, jlist) order as the reference host loop (pair_nequip_allegro.cpp:488-512, 566-629)
+// ------------------------------------------------------------------------------------------
+struct NeighAcc {
+  const int* base;
+  const long long* first;   // flat mode: offset of centre slot ii
+  const int* cnt;           // flat: per slot ii ; 2-D: per atom i (numneigh)
+  long long stride_i, stride_jj;
+  int flat;
+};
+
+__device__ __forceinline__ double rsq_nofma(const double* __restrict__ x, int i, int j, double& dx, double& dy, double& dz) {
+  dx = x[3 * (size_t)i + 0] - x[3 * (size_t)j + 0];
+  dy = x[3 * (size_t)i + 1] - x[3 * (size_t)j + 1];
+  dz = x[3 * (size_t)i + 2] - x[3 * (size_t)j + 2];
+  // same rounding as the reference's `dx*dx + dy*dy + dz*dz` compiled without contraction
+  return __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+}
+
+template <bool FILL>
+__global__ void k_edges(int nlocal, const double* __restrict__ x, const int* __restrict__ type, const int* __restrict__ ilist,
+                        NeighAcc acc, const double* __restrict__ cutsq, int ntypes, int filter_le,
+                        int* __restrict__ cnt_out, const int* __restrict__ rowptr, const int* __restrict__ tmap,
+                        int* __restrict__ edge_j, int* __restrict__ edge_c, float4* __restrict__ rvec) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= nlocal) return;
+  const int ii = warp;
+  const int i = ilist[ii];
+  const int ti = type[i] - 1;
+  int n; const int* ptr; long long st;
+  if (acc.flat) { n = acc.cnt[ii]; ptr = acc.base + acc.first[ii]; st = 1; }
+  else { n = acc.cnt[i]; ptr = acc.base + (long long)i * acc.stride_i; st = acc.stride_jj; }
+  int total = 0;
+  int base = FILL ? rowptr[ii] : 0;
+  const int zi = FILL ? tmap[ti] : 0;
+  for (int j0 = 0; j0 < n; j0 += 32) {
+    const int jj = j0 + lane;
+    bool keep = false;
+    int j = 0; double dx = 0, dy = 0, dz = 0;
+    if (jj < n) {
+      j = ptr[(long long)jj * st] & NEIGHMASK;
+      const double rsq = rsq_nofma(x, i, j, dx, dy, dz);
+      const double c2 = cutsq[ti * ntypes + (type[j] - 1)];
+      keep = filter_le ? (rsq <= c2) : (rsq < c2);
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, keep);
+    if (FILL) {
+      if (keep) {
+        const int pos = base + __popc(m & ((1u << lane) - 1u));
+        edge_j[pos] = j;
+        edge_c[pos] = ii;
+        const int zj = tmap[type[j] - 1];
+        rvec[pos] = make_float4((float)(-dx), (float)(-dy), (float)(-dz), __int_as_float(zi | (zj << 8)));
+      }
+      base += __popc(m);
+    } else {
+      total += __popc(m);
+    }
+  }
+  if (!FILL && lane == 0) cnt_out[ii] = total;
+}
+
+__global__ void k_edge_index(long E, const int* __restrict__ edge_j, const int* __restrict__ edge_c, const int* __restrict__ ilist,
+                             long long* __restrict__ out) {
+  const long e = blockIdx.x * (long)blockDim.x + threadIdx.x;
+  if (e >= E) return;
+  out[e] = ilist[edge_c[e]];
+  out[E + e] = edge_j[e];
+}
+
+__global__ void k_mtype(int ntot, const int* __restrict__ type, const int* __restrict__ tmap, int* __restrict__ mtype) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < ntot) mtype[i] = tmap[type[i] - 1];
+}
+
+// finalize: fixed-point accumulators -> model forces (double), optionally f += ; per-atom energies
+__global__ void k_forces(int ntot, const unsigned long long* __restrict__ facc, double* __restrict__ forces, double* __restrict__ f_inout) {
+  const long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
+  if (i >= 3L * ntot) return;
+  const double v = (double)(long long)facc[i] * FIX_INV;
+  forces[i] = v;
+  if (f_inout) f_inout[i] += v;
+}
+__global__ void k_eall_ghost(int ntot, const int* __restrict__ mtype, const double* __restrict__ shift, double* __restrict__ eall) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < ntot) { const int z = mtype[i]; eall[i] = z >= 0 ? shift[z] : 0.0; }
+}
+// one block-partial per 1024 centres, fixed reduction tree -> deterministic
+__global__ void k_eall_local(int nlocal, const int* __restrict__ ilist, const int* __restrict__ mtype, const double* __restrict__ esum,
+                             const double* __restrict__ scale, const double* __restrict__ shift, double inv_sqrt_n,
+                             double* __restrict__ eall, double* __restrict__ eatom, double* __restrict__ partial) {
+  __shared__ double red[256];
+  double acc = 0.0;
+  for (int q = 0; q < 4; ++q) {
+    const int ii = blockIdx.x * 1024 + q * 256 + threadIdx.x;
+    if (ii < nlocal) {
+      const int i = ilist[ii];
+      const int z = mtype[i];
+      const double e = z >= 0 ? scale[z] * (inv_sqrt_n * esum[ii]) + shift[z] : 0.0;
+      eall[i] = e;
+      if (eatom) eatom[i] = e;
+      acc += e;
+    }
+  }
+  red[threadIdx.x] = acc;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if (threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) partial[blockIdx.x] = red[0];
+}
+__global__ void k_final_scalars(int nblocks, const double* __restrict__ partial, const unsigned long long* __restrict__ vacc, double* __restrict__ out7) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    double e = 0.0;
+    for (int b = 0; b < nblocks; ++b) e += partial[b];
+    out7[0] = e;
+    for (int q = 0; q < 6; ++q) out7[1 + q] = (double)(long long)vacc[q] / VIR_SCALE;
+  }
+}
+
+__global__ void k_halo_pack(const double* __restrict__ x, const int* __restrict__ list, int n, double sx, double sy, double sz, double* __restrict__ buf) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  const int i = list[k];
+  buf[3 * (size_t)k + 0] = x[3 * (size_t)i + 0] + sx;
+  buf[3 * (size_t)k + 1] = x[3 * (size_t)i + 1] + sy;
+  buf[3 * (size_t)k + 2] = x[3 * (size_t)i + 2] + sz;
+}
+__global__ void k_halo_unpack_add(double* __restrict__ f, const int* __restrict__ list, int n, const double* __restrict__ buf) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  const int i = list[k];
+  f[3 * (size_t)i + 0] += buf[3 * (size_t)k + 0];
+  f[3 * (size_t)i + 1] += buf[3 * (size_t)k + 1];
+  f[3 * (size_t)i + 2] += buf[3 * (size_t)k + 2];
+}
+
+// ------------------------------------------------------------------------------------------
+// model setup
+// ------------------------------------------------------------------------------------------
+static int setup_model(alg_handle* h) {
+  auto& hd = h->header;
+  auto geti = [&](const char* k, int def) { auto it = hd.find(k); return it == hd.end() ? def : atoi(it->second.c_str()); };
+  auto getd = [&](const char* k, double def) { auto it = hd.find(k); return it == hd.end() ? def : atof(it->second.c_str()); };
+  for (const char* k : {"r_max", "type_names", "num_types", "allow_tf32", "l_max", "num_layers", "num_bessels"})
+    if (!hd.count(k)) return fail(h, ALG_EIO, std::string("weight file header misses key ") + k);
+  h->L = geti("l_max", 0); h->nl = geti("num_layers", 0); h->T = geti("num_types", 0); h->B = geti("num_bessels", 0);
+  h->r_max = getd("r_max", 0); h->avg_n = getd("avg_num_neighbors", 1.0); h->p = getd("polynomial_cutoff_p", 6.0);
+  h->allow_tf32 = geti("allow_tf32", 0);
+  h->type_names = hd["type_names"];
+  if (h->L < 1 || h->L > 3) return fail(h, ALG_EINVAL, "unsupported l_max (supported: 1..3)");
+  if (h->nl < 1 || h->nl > 3) return fail(h, ALG_EINVAL, "unsupported num_layers (supported: 1..3)");
+  if (h->T < 1 || h->T > MAXT) return fail(h, ALG_EINVAL, "unsupported num_types (supported: 1..8)");
+  if (h->B < 1 || h->B > MAXB) return fail(h, ALG_EINVAL, "unsupported num_bessels (supported: 1..16)");
+  if (geti("num_scalar_features", 0) != S || geti("num_tensor_features", 0) != U || geti("mlp_width", 0) != H ||
+      geti("mlp_depth", 0) != 2 || geti("readout_width", 0) != R)
+    return fail(h, ALG_EINVAL, "unsupported widths: this build supports num_scalar_features=64, num_tensor_features=32, "
+                               "mlp 2x64, readout 1x32");
+  {
+    std::istringstream ss(hd.count("per_edge_type_cutoff") ? hd["per_edge_type_cutoff"] : "");
+    double v;
+    while (ss >> v) h->per_edge_cut.push_back(v);
+    if (!h->per_edge_cut.empty() && (int)h->per_edge_cut.size() != h->T * h->T)
+      return fail(h, ALG_EIO, "per_edge_type_cutoff must hold num_types^2 values");
+  }
+  h->pipe = get_pipeline(h->L);
+  h->pinfo = h->pipe->info(h->nl);
+  const int L = h->L, T = h->T, B = h->B, ENVW = (L + 1) * U, SIN = S + ENVW;
+  std::string err;
+  // gather all fp32 matrices (+ transposes) into one device blob
+  struct Item { const float* src; long k, n; bool transpose; size_t off; };
+  std::vector<Item> items;
+  size_t total = 0;
+  auto add = [&](const std::string& name, long k, long n, bool tr) -> long {
+    const float* p = tf32(h, name, k, n, err);
+    if (!p) return -1;
+    items.push_back({p, k, n, tr, total});
+    long idx = (long)items.size() - 1;
+    total += ((size_t)k * n + 63) / 64 * 64;
+    return idx;
+  };
+  std::vector<std::pair<const float**, long>> fix;   // pointers to patch after upload
+  ModelW& mw = h->mw;
+  auto both = [&](const std::string& name, long k, long n, const float** w, const float** wt) -> bool {
+    long a = add(name, k, n, false); if (a < 0) return false;
+    long b = add(name, k, n, true); if (b < 0) return false;
+    fix.push_back({w, a}); fix.push_back({wt, b});
+    return true;
+  };
+  bool ok = true;
+  ok = ok && both("twobody.w0", 2 * T + B, H, &mw.two.w[0], &mw.two.wt[0]);
+  ok = ok && both("twobody.w1", H, H, &mw.two.w[1], &mw.two.wt[1]);
+  ok = ok && both("twobody.w2", H, S, &mw.two.w[2], &mw.two.wt[2]);
+  ok = ok && both("embed_linear", S, ENVW, &mw.emb, &mw.emb_t);
+  static const char* kinds[4][3] = {{"", "", ""}, {"A", "", ""}, {"B", "A", ""}, {"C", "D", "A"}};
+  (void)kinds;
+  for (int k = 0; k < h->nl && ok; ++k) {
+    const std::string pre = "layer" + std::to_string(k) + ".";
+    ok = ok && both(pre + "env_linear", S, ENVW, &mw.layer[k].env, &mw.layer[k].env_t);
+    auto it = h->tensors.find(pre + "omega");
+    if (it == h->tensors.end() || it->second.dims.size() != 2 || it->second.dims[1] != U) { err = "bad tensor " + pre + "omega"; ok = false; break; }
+    long a = add(pre + "omega", it->second.dims[0], U, false); if (a < 0) { ok = false; break; }
+    fix.push_back({&mw.layer[k].omega, a});
+    ok = ok && both(pre + "mlp.w0", SIN, H, &mw.layer[k].mlp.w[0], &mw.layer[k].mlp.wt[0]);
+    ok = ok && both(pre + "mlp.w1", H, H, &mw.layer[k].mlp.w[1], &mw.layer[k].mlp.wt[1]);
+    ok = ok && both(pre + "mlp.w2", H, S, &mw.layer[k].mlp.w[2], &mw.layer[k].mlp.wt[2]);
+    const float* al = tf32(h, pre + "alpha", 1, 1, err);
+    if (!al) { ok = false; break; }
+    const double alpha = al[0];
+    mw.layer[k].a = (float)(1.0 / std::sqrt(1.0 + alpha * alpha));
+    mw.layer[k].b = (float)(alpha / std::sqrt(1.0 + alpha * alpha));
+  }
+  if (ok) {
+    ok = ok && both("readout.w0", S, R, &mw.ro0, &mw.ro0_t);
+    long a = add("readout.w1", R, 1, false); if (a < 0) ok = false; else fix.push_back({&mw.ro1, a});
+  }
+  if (!ok) return fail(h, ALG_EIO, err);
+  std::vector<float> blob(total, 0.f);
+  for (const Item& it : items) {
+    float* dst = blob.data() + it.off;
+    if (!it.transpose) memcpy(dst, it.src, sizeof(float) * it.k * it.n);
+    else for (long r = 0; r < it.k; ++r) for (long c = 0; c < it.n; ++c) dst[c * it.k + r] = it.src[r * it.n + c];
+  }
+  CK(h->weights.ensure(total * sizeof(float)));
+  CK(cudaMemcpy(h->weights.p, blob.data(), total * sizeof(float), cudaMemcpyHostToDevice));
+  for (auto& fx : fix) *fx.first = h->weights.as<float>() + items[fx.second].off;
+  // scalars
+  auto getf64 = [&](const char* name, long n, std::vector<double>& out) -> bool {
+    auto it = h->tensors.find(name);
+    if (it == h->tensors.end() || it->second.dtype != "f64" || (long)it->second.count() != n) { err = std::string("bad tensor ") + name; return false; }
+    out.assign(reinterpret_cast<const double*>(it->second.data.data()), reinterpret_cast<const double*>(it->second.data.data()) + n);
+    return true;
+  };
+  if (!getf64("scales", T, h->scales) || !getf64("shifts", T, h->shifts) || !getf64("cutoff_table", (long)T * T, h->cut_table))
+    return fail(h, ALG_EIO, err);
+  const double inv = 1.0 / std::sqrt(h->avg_n);
+  for (int i = 0; i < MAXT * MAXT; ++i) mw.rc[i] = (float)h->r_max;
+  for (int i = 0; i < T; ++i) for (int j = 0; j < T; ++j) mw.rc[i * MAXT + j] = (float)h->cut_table[i * T + j];
+  for (int i = 0; i < MAXT; ++i) mw.gscale[i] = i < T ? (float)(inv * h->scales[i]) : 0.f;
+  mw.T = T; mw.B = B; mw.nl = h->nl; mw.p = (float)h->p; mw.inv_sqrt_n = (float)inv;
+  CK(h->d_scale.ensure(sizeof(double) * MAXT));
+  CK(h->d_shift.ensure(sizeof(double) * MAXT));
+  CK(cudaMemcpy(h->d_scale.p, h->scales.data(), sizeof(double) * T, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(h->d_shift.p, h->shifts.data(), sizeof(double) * T, cudaMemcpyHostToDevice));
+  CK(h->pipe->init());
+  h->tensors.clear();
+  return ALG_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// C-ABI
+// ------------------------------------------------------------------------------------------
+extern "C" const char* alg_version(void) { return "allegro_b200 0.1.0 sm_100a"; }
+
+extern "C" const char* alg_last_error(const alg_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+extern "C" int alg_create(const char* weight_path, int cuda_device, alg_handle** out) {
+  if (!out || !weight_path) { g_create_error = "alg_create: null argument"; return ALG_EINVAL; }
+  *out = nullptr;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    g_create_error = std::string("no CUDA device available (") + cudaGetErrorString(e) + "); this library has no CPU fallback";
+    return ALG_ECUDA;
+  }
+  if (cuda_device < 0 || cuda_device >= ndev) { g_create_error = "alg_create: cuda_device out of range"; return ALG_EINVAL; }
+  alg_handle* h = new alg_handle();
+  h->device = cuda_device;
+  std::string err;
+  if (!read_alg(weight_path, h, err)) { g_create_error = err; delete h; return ALG_EIO; }
+  int rc = ALG_OK;
+  if ((e = cudaSetDevice(cuda_device)) != cudaSuccess || (e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess) {
+    g_create_error = std::string("CUDA error: ") + cudaGetErrorString(e); delete h; return ALG_ECUDA;
+  }
+  for (int i = 0; i < 4; ++i) cudaEventCreate(&h->ev[i]);
+  rc = setup_model(h);
+  if (rc != ALG_OK) { g_create_error = h->err; alg_destroy(h); return rc; }
+  *out = h;
+  return ALG_OK;
+}
+
+extern "C" void alg_destroy(alg_handle* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  DevBuf* bufs[] = {&h->weights, &h->d_tmap, &h->d_cutsq, &h->d_scale, &h->d_shift, &h->d_x, &h->d_type, &h->d_ilist, &h->d_numneigh,
+                    &h->d_cand, &h->d_first, &h->d_cnt, &h->d_rowptr, &h->d_scan_tmp, &h->d_mtype, &h->d_edge_j, &h->d_edge_c, &h->d_rvec,
+                    &h->d_esum, &h->d_facc, &h->d_vacc, &h->d_forces, &h->d_eall, &h->d_red, &h->d_edge_index, &h->d_edge_energy,
+                    &h->d_edge_grad, &h->d_eatom_out, &h->c_W0, &h->c_dX, &h->c_dY, &h->c_du, &h->c_carry, &h->c_ecarry,
+                    &h->c_X[0], &h->c_X[1], &h->c_X[2], &h->c_V[0], &h->c_V[1], &h->c_V[2], &h->c_dV[0], &h->c_dV[1],
+                    &h->c_gamma[0], &h->c_gamma[1], &h->c_gamma[2], &h->c_dgamma[0], &h->c_dgamma[1], &h->c_dgamma[2]};
+  for (DevBuf* b : bufs) b->release();
+  h->h_stage.release(); h->h_rowptr.release(); h->h_out.release(); h->h_first.release();
+  for (int i = 0; i < 4; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+}
+
+extern "C" int alg_metadata(const alg_handle* h, double* r_max, int* num_types, const char** type_names,
+                            const double** per_edge_type_cutoff, int* allow_tf32) {
+  if (!h) return ALG_EINVAL;
+  if (r_max) *r_max = h->r_max;
+  if (num_types) *num_types = h->T;
+  if (type_names) *type_names = h->type_names.c_str();
+  if (per_edge_type_cutoff) *per_edge_type_cutoff = h->per_edge_cut.empty() ? nullptr : h->per_edge_cut.data();
+  if (allow_tf32) *allow_tf32 = h->allow_tf32;
+  return ALG_OK;
+}
+
+extern "C" int alg_set_type_map(alg_handle* h, int ntypes, const int* map, const double* cutoff_matrix) {
+  if (!h) return ALG_EINVAL;
+  if (ntypes < 1 || !map || !cutoff_matrix) return fail(h, ALG_EINVAL, "alg_set_type_map: bad arguments");
+  for (int i = 0; i < ntypes; ++i)
+    if (map[i] < -1 || map[i] >= h->T) return fail(h, ALG_EINVAL, "alg_set_type_map: model type index out of range");
+  CK(cudaSetDevice(h->device));
+  std::vector<double> c2((size_t)ntypes * ntypes);
+  for (size_t i = 0; i < c2.size(); ++i) c2[i] = cutoff_matrix[i] * cutoff_matrix[i];   // cutij*cutij, cpp:507
+  CK(h->d_tmap.ensure(sizeof(int) * ntypes));
+  CK(h->d_cutsq.ensure(sizeof(double) * c2.size()));
+  CK(cudaMemcpy(h->d_tmap.p, map, sizeof(int) * ntypes, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(h->d_cutsq.p, c2.data(), sizeof(double) * c2.size(), cudaMemcpyHostToDevice));
+  h->ntypes = ntypes;
+  h->have_map = true;
+  return ALG_OK;
+}
+
+extern "C" int alg_set_option(alg_handle* h, const char* key, const char* value) {
+  if (!h || !key || !value) return ALG_EINVAL;
+  const std::string k(key), v(value);
+  if (k == "filter") {
+    if (v == "le") h->filter_le = true; else if (v == "lt") h->filter_le = false; else return fail(h, ALG_EINVAL, "filter must be le or lt");
+  } else if (k == "chunk_edges") {
+    long c = atol(value);
+    if (c < 4096) return fail(h, ALG_EINVAL, "chunk_edges must be >= 4096");
+    h->chunk_edges = c;
+  } else if (k == "keep_edges") h->keep_edges = v == "1";
+  else if (k == "debug") h->debug = v == "1";
+  else return fail(h, ALG_ENOTFOUND, "unknown option " + k);
+  return ALG_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// the step
+// ------------------------------------------------------------------------------------------
+static int ensure_chunk_buffers(alg_handle* h, long max_tiles, long max_centres) {
+  const PipelineInfo& pi = h->pinfo;
+  const size_t TM = pi.TM;
+  for (int k = 0; k < h->nl; ++k) CK(h->c_X[k].ensure(sizeof(float) * max_tiles * S * TM));
+  CK(h->c_W0.ensure(sizeof(float) * max_tiles * pi.ENVW * TM));
+  for (int k = 1; k < h->nl; ++k) CK(h->c_V[k].ensure(sizeof(float) * max_tiles * U * pi.vdim[k] * TM));
+  CK(h->c_dX.ensure(sizeof(float) * max_tiles * S * TM));
+  if (h->nl > 1) for (int q = 0; q < 2; ++q) CK(h->c_dV[q].ensure(sizeof(float) * max_tiles * U * pi.dvdim * TM));
+  CK(h->c_dY.ensure(sizeof(float) * max_tiles * pi.NSH * TM));
+  CK(h->c_du.ensure(sizeof(float) * max_tiles * TM));
+  for (int k = 0; k < h->nl; ++k) {
+    CK(h->c_gamma[k].ensure(sizeof(float) * max_centres * pi.F));
+    CK(h->c_dgamma[k].ensure(sizeof(float) * max_centres * pi.F));
+  }
+  CK(h->c_carry.ensure(sizeof(float) * max_tiles * pi.F));
+  CK(h->c_ecarry.ensure(sizeof(double) * max_tiles));
+  return ALG_OK;
+}
+
+static void detile(const std::vector<float>& raw, int ntiles, int rows, int TM, long E, std::vector<double>& out) {
+  out.assign((size_t)E * rows, 0.0);
+  for (long e = 0; e < E; ++e) {
+    const long t = e / TM, m = e % TM;
+    for (int r = 0; r < rows; ++r) out[(size_t)e * rows + r] = raw[((size_t)t * rows + r) * TM + m];
+  }
+}
+
+// d_x/d_type/d_ilist are device pointers; acc describes the device-resident neighbour list.
+static int run_step(alg_handle* h, int nlocal, int nghost, const double* d_x, const int* d_type, const int* d_ilist, NeighAcc acc,
+                    int eflag_atom, int vflag_global, double* d_f_inout, double* d_eatom, double* eng, double* virial6) {
+  cudaStream_t st = h->stream;
+  const int ntot = nlocal + nghost;
+  const PipelineInfo& pi = h->pinfo;
+  const int TM = pi.TM;
+  h->last_nlocal = nlocal; h->last_ntot = ntot; h->last_E = 0;
+  h->outputs.clear();
+  CK(cudaEventRecord(h->ev[0], st));
+  // ---- K1: count, scan, fill
+  CK(h->d_cnt.ensure(sizeof(int) * (nlocal + 1)));
+  CK(h->d_rowptr.ensure(sizeof(int) * (nlocal + 1)));
+  CK(h->d_mtype.ensure(sizeof(int) * ntot));
+  const int wblocks = (int)(((long)nlocal * 32 + 255) / 256);
+  k_mtype<<<(ntot + 255) / 256, 256, 0, st>>>(ntot, d_type, h->d_tmap.as<int>(), h->d_mtype.as<int>());
+  k_edges<false><<<wblocks, 256, 0, st>>>(nlocal, d_x, d_type, d_ilist, acc, h->d_cutsq.as<double>(), h->ntypes, h->filter_le ? 1 : 0,
+                                          h->d_cnt.as<int>(), nullptr, nullptr, nullptr, nullptr, nullptr);
+  CK(cudaMemsetAsync(h->d_cnt.as<int>() + nlocal, 0, sizeof(int), st));
+  size_t tmp_bytes = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, h->d_cnt.as<int>(), h->d_rowptr.as<int>(), nlocal + 1, st);
+  CK(h->d_scan_tmp.ensure(tmp_bytes));
+  CK(cub::DeviceScan::ExclusiveSum(h->d_scan_tmp.p, tmp_bytes, h->d_cnt.as<int>(), h->d_rowptr.as<int>(), nlocal + 1, st));
+  CK(h->h_rowptr.ensure(sizeof(int) * (nlocal + 1)));
+  CK(cudaMemcpyAsync(h->h_rowptr.p, h->d_rowptr.p, sizeof(int) * (nlocal + 1), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  const int* rowptr = h->h_rowptr.as<int>();
+  const long E = rowptr[nlocal];
+  h->last_E = E;
+  CK(h->d_edge_j.ensure(sizeof(int) * std::max<long>(E, 1)));
+  CK(h->d_edge_c.ensure(sizeof(int) * std::max<long>(E, 1)));
+  CK(h->d_rvec.ensure(sizeof(float4) * std::max<long>(E, 1)));
+  k_edges<true><<<wblocks, 256, 0, st>>>(nlocal, d_x, d_type, d_ilist, acc, h->d_cutsq.as<double>(), h->ntypes, h->filter_le ? 1 : 0,
+                                         nullptr, h->d_rowptr.as<int>(), h->d_tmap.as<int>(), h->d_edge_j.as<int>(), h->d_edge_c.as<int>(),
+                                         h->d_rvec.as<float4>());
+  if (h->keep_edges) {
+    CK(h->d_edge_index.ensure(sizeof(long long) * 2 * std::max<long>(E, 1)));
+    if (E > 0) k_edge_index<<<(unsigned)((E + 255) / 256), 256, 0, st>>>(E, h->d_edge_j.as<int>(), h->d_edge_c.as<int>(), d_ilist, h->d_edge_index.as<long long>());
+  }
+  CK(cudaGetLastError());
+  CK(cudaEventRecord(h->ev[1], st));
+  // ---- per-step accumulators
+  CK(h->d_esum.ensure(sizeof(double) * nlocal));
+  CK(h->d_facc.ensure(sizeof(unsigned long long) * 3 * ntot));
+  CK(h->d_vacc.ensure(sizeof(unsigned long long) * 8));
+  CK(cudaMemsetAsync(h->d_esum.p, 0, sizeof(double) * nlocal, st));
+  CK(cudaMemsetAsync(h->d_facc.p, 0, sizeof(unsigned long long) * 3 * ntot, st));
+  CK(cudaMemsetAsync(h->d_vacc.p, 0, sizeof(unsigned long long) * 8, st));
+  if (h->debug) {
+    CK(h->d_edge_energy.ensure(sizeof(float) * std::max<long>(E, 1)));
+    CK(h->d_edge_grad.ensure(sizeof(float) * 3 * std::max<long>(E, 1)));
+  }
+  // ---- chunk plan (centre aligned)
+  struct Chunk { int c0, c1, e0, e1; };
+  std::vector<Chunk> chunks;
+  const long CE = std::max<long>(h->chunk_edges, TM);
+  const long CC = CE;   // centres per chunk bound
+  long max_tiles = 1, max_cent = 1;
+  for (int c0 = 0; c0 < nlocal;) {
+    // largest c1 with rowptr[c1]-rowptr[c0] <= CE and c1-c0 <= CC
+    const long lim = (long)rowptr[c0] + CE;
+    int c1 = (int)(std::upper_bound(rowptr + c0, rowptr + nlocal + 1, (int)std::min<long>(lim, 0x7fffffff)) - rowptr) - 1;
+    if (c1 - c0 > CC) c1 = c0 + (int)CC;
+    if (c1 <= c0) {
+      if ((long)rowptr[c0 + 1] - rowptr[c0] > CE)
+        return fail(h, ALG_EINVAL, "a single atom has more neighbours than chunk_edges; raise option chunk_edges");
+      c1 = c0 + 1;
+    }
+    if (rowptr[c1] > rowptr[c0]) {
+      chunks.push_back({c0, c1, rowptr[c0], rowptr[c1]});
+      max_tiles = std::max<long>(max_tiles, ((long)rowptr[c1] - rowptr[c0] + TM - 1) / TM);
+      max_cent = std::max<long>(max_cent, c1 - c0);
+    }
+    c0 = c1;
+  }
+  int rc = ensure_chunk_buffers(h, max_tiles, max_cent);
+  if (rc != ALG_OK) return rc;
+  ChunkArgs a{};
+  a.rvec = h->d_rvec.as<float4>(); a.edge_j = h->d_edge_j.as<int>(); a.edge_c = h->d_edge_c.as<int>();
+  a.rowptr = h->d_rowptr.as<int>(); a.ilist = d_ilist;
+  for (int k = 0; k < 3; ++k) { a.X[k] = h->c_X[k].as<float>(); a.V[k] = h->c_V[k].as<float>(); a.gamma[k] = h->c_gamma[k].as<float>(); a.dgamma[k] = h->c_dgamma[k].as<float>(); }
+  a.W0 = h->c_W0.as<float>(); a.dX = h->c_dX.as<float>(); a.dV[0] = h->c_dV[0].as<float>(); a.dV[1] = h->c_dV[1].as<float>();
+  a.dY = h->c_dY.as<float>(); a.du = h->c_du.as<float>(); a.carry = h->c_carry.as<float>(); a.ecarry = h->c_ecarry.as<double>();
+  a.esum = h->d_esum.as<double>();
+  a.edge_energy = h->debug ? h->d_edge_energy.as<float>() : nullptr;
+  a.edge_grad = h->debug ? h->d_edge_grad.as<float>() : nullptr;
+  a.facc = h->d_facc.as<unsigned long long>();
+  a.vacc = h->d_vacc.as<unsigned long long>();
+  for (const Chunk& c : chunks) {
+    a.e0 = c.e0; a.e1 = c.e1; a.c0 = c.c0;
+    const int ntiles = (c.e1 - c.e0 + TM - 1) / TM;
+    CK(h->pipe->run_chunk(a, h->mw, ntiles, st));
+  }
+  CK(cudaEventRecord(h->ev[2], st));
+  // ---- finalize
+  CK(h->d_forces.ensure(sizeof(double) * 3 * ntot));
+  CK(h->d_eall.ensure(sizeof(double) * ntot));
+  const int eblocks = (nlocal + 1023) / 1024;
+  CK(h->d_red.ensure(sizeof(double) * (eblocks + 8)));
+  k_forces<<<(unsigned)((3L * ntot + 255) / 256), 256, 0, st>>>(ntot, h->d_facc.as<unsigned long long>(), h->d_forces.as<double>(), d_f_inout);
+  k_eall_ghost<<<(ntot + 255) / 256, 256, 0, st>>>(ntot, h->d_mtype.as<int>(), h->d_shift.as<double>(), h->d_eall.as<double>());
+  k_eall_local<<<eblocks, 256, 0, st>>>(nlocal, d_ilist, h->d_mtype.as<int>(), h->d_esum.as<double>(), h->d_scale.as<double>(),
+                                        h->d_shift.as<double>(), 1.0 / std::sqrt(h->avg_n), h->d_eall.as<double>(),
+                                        eflag_atom ? d_eatom : nullptr, h->d_red.as<double>() + 8);
+  k_final_scalars<<<1, 32, 0, st>>>(eblocks, h->d_red.as<double>() + 8, h->d_vacc.as<unsigned long long>(), h->d_red.as<double>());
+  CK(cudaGetLastError());
+  CK(cudaEventRecord(h->ev[3], st));
+  if (eng || virial6) {
+    CK(h->h_out.ensure(sizeof(double) * 8));
+    CK(cudaMemcpyAsync(h->h_out.p, h->d_red.p, sizeof(double) * 7, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    const double* o = h->h_out.as<double>();
+    if (eng) *eng = o[0];
+    if (virial6 && vflag_global) for (int q = 0; q < 6; ++q) virial6[q] = o[1 + q];
+    float ms;
+    for (int q = 0; q < 3; ++q) { cudaEventElapsedTime(&ms, h->ev[q], h->ev[q + 1]); h->timings[q] = ms; }
+  }
+  h->dbg_ntiles = chunks.size() == 1 ? (chunks[0].e1 - chunks[0].e0 + TM - 1) / TM : 0;
+  h->dbg_c0 = chunks.size() == 1 ? chunks[0].c0 : 0;
+  h->dbg_ncent = chunks.size() == 1 ? chunks[0].c1 - chunks[0].c0 : 0;
+  return ALG_OK;
+}
+
+extern "C" int alg_compute_host(alg_handle* h, int nlocal, int nghost, const double* x, const int* type, const int* ilist,
+                                const int* numneigh, int* const* firstneigh, int eflag_atom, int vflag_global,
+                                double* f, double* eatom, double* eng, double* virial6) {
+  if (!h) return ALG_EINVAL;
+  if (!h->have_map) return fail(h, ALG_ESTATE, "alg_compute_host called before alg_set_type_map");
+  if (nlocal < 0 || nghost < 0) return fail(h, ALG_EINVAL, "negative atom count");
+  if (eng) *eng = 0.0;
+  if (nlocal == 0) return ALG_OK;                   // empty domain: silent no-op (cpp:341)
+  if (!x || !type || !ilist || !numneigh || !firstneigh || !f) return fail(h, ALG_EINVAL, "alg_compute_host: null pointer");
+  CK(cudaSetDevice(h->device));
+  cudaStream_t st = h->stream;
+  const int ntot = nlocal + nghost;
+  // flatten the paged LAMMPS list (ilist order, jlist order) into pinned staging
+  CK(h->h_first.ensure(sizeof(long long) * (nlocal + 1) + sizeof(int) * nlocal));
+  long long* first = h->h_first.as<long long>();
+  int* cnt = reinterpret_cast<int*>(first + nlocal + 1);
+  long long tot = 0;
+  for (int ii = 0; ii < nlocal; ++ii) { first[ii] = tot; cnt[ii] = numneigh[ilist[ii]]; tot += cnt[ii]; }
+  first[nlocal] = tot;
+  CK(h->h_stage.ensure(sizeof(int) * std::max<long long>(tot, 1)));
+  int* stage = h->h_stage.as<int>();
+#pragma omp parallel for schedule(static)
+  for (int ii = 0; ii < nlocal; ++ii) memcpy(stage + first[ii], firstneigh[ilist[ii]], sizeof(int) * cnt[ii]);
+  CK(h->d_x.ensure(sizeof(double) * 3 * ntot));
+  CK(h->d_type.ensure(sizeof(int) * ntot));
+  CK(h->d_ilist.ensure(sizeof(int) * nlocal));
+  CK(h->d_cand.ensure(sizeof(int) * std::max<long long>(tot, 1)));
+  CK(h->d_first.ensure(sizeof(long long) * (nlocal + 1)));
+  CK(h->d_numneigh.ensure(sizeof(int) * nlocal));
+  CK(cudaMemcpyAsync(h->d_x.p, x, sizeof(double) * 3 * ntot, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(h->d_type.p, type, sizeof(int) * ntot, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(h->d_ilist.p, ilist, sizeof(int) * nlocal, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(h->d_cand.p, stage, sizeof(int) * tot, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(h->d_first.p, first, sizeof(long long) * (nlocal + 1), cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(h->d_numneigh.p, cnt, sizeof(int) * nlocal, cudaMemcpyHostToDevice, st));
+  NeighAcc acc{h->d_cand.as<int>(), h->d_first.as<long long>(), h->d_numneigh.as<int>(), 0, 0, 1};
+  if (eflag_atom && eatom) CK(h->d_eatom_out.ensure(sizeof(double) * ntot));
+  double eng_l = 0.0, vir_l[6] = {0, 0, 0, 0, 0, 0};
+  int rc = run_step(h, nlocal, nghost, h->d_x.as<double>(), h->d_type.as<int>(), h->d_ilist.as<int>(), acc, eflag_atom && eatom ? 1 : 0,
+                    1, nullptr, (eflag_atom && eatom) ? h->d_eatom_out.as<double>() : nullptr, &eng_l, vir_l);
+  if (rc != ALG_OK) return rc;
+  // store: f += forces for ALL atoms incl. ghosts (cpp:370-377), eatom for locals (cpp:378)
+  auto& fo = h->outputs["forces"];
+  fo.resize((size_t)3 * ntot);
+  CK(cudaMemcpyAsync(fo.data(), h->d_forces.p, sizeof(double) * 3 * ntot, cudaMemcpyDeviceToHost, st));
+  auto& eo = h->outputs["atomic_energy"];
+  eo.resize(ntot);
+  CK(cudaMemcpyAsync(eo.data(), h->d_eall.p, sizeof(double) * ntot, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+#pragma omp parallel for schedule(static)
+  for (long i = 0; i < 3L * ntot; ++i) f[i] += fo[i];
+  if (eflag_atom && eatom)
+    for (int ii = 0; ii < nlocal; ++ii) eatom[ilist[ii]] = eo[ilist[ii]];
+  if (eng) *eng = eng_l;
+  if (vflag_global && virial6) for (int q = 0; q < 6; ++q) virial6[q] = vir_l[q];
+  auto& vo = h->outputs["virial"];
+  vo = {vir_l[0], vir_l[3], vir_l[4], vir_l[3], vir_l[1], vir_l[5], vir_l[4], vir_l[5], vir_l[2]};
+  return ALG_OK;
+}
+
+extern "C" int alg_compute_device(alg_handle* h, int nlocal, int nghost, const double* d_x, const int* d_type, const int* d_ilist,
+                                  const int* d_numneigh, const int* d_neighbors, int64_t stride_i, int64_t stride_jj,
+                                  int eflag_atom, int vflag_global, double* d_f, double* d_eatom, double* eng, double* virial6,
+                                  void* stream) {
+  if (!h) return ALG_EINVAL;
+  if (!h->have_map) return fail(h, ALG_ESTATE, "alg_compute_device called before alg_set_type_map");
+  if (eng) *eng = 0.0;
+  if (nlocal == 0) return ALG_OK;
+  if (!d_x || !d_type || !d_ilist || !d_numneigh || !d_neighbors || !d_f) return fail(h, ALG_EINVAL, "alg_compute_device: null pointer");
+  CK(cudaSetDevice(h->device));
+  // order our stream after the caller's stream and vice versa
+  cudaStream_t cs = reinterpret_cast<cudaStream_t>(stream);
+  cudaEvent_t evt;
+  CK(cudaEventCreateWithFlags(&evt, cudaEventDisableTiming));
+  CK(cudaEventRecord(evt, cs));
+  CK(cudaStreamWaitEvent(h->stream, evt, 0));
+  NeighAcc acc{d_neighbors, nullptr, d_numneigh, (long long)stride_i, (long long)stride_jj, 0};
+  int rc = run_step(h, nlocal, nghost, d_x, d_type, d_ilist, acc, eflag_atom && d_eatom ? 1 : 0, vflag_global, d_f, d_eatom, eng, virial6);
+  cudaEventRecord(evt, h->stream);
+  cudaStreamWaitEvent(cs, evt, 0);
+  cudaEventDestroy(evt);
+  return rc;
+}
+
+extern "C" int alg_get_edges(alg_handle* h, const int64_t** edge_index, int64_t* nedges) {
+  if (!h || !edge_index || !nedges) return ALG_EINVAL;
+  if (!h->keep_edges) return fail(h, ALG_ESTATE, "alg_get_edges needs option keep_edges=1 before the compute");
+  CK(cudaSetDevice(h->device));
+  const long E = h->last_E;
+  h->edges_host.resize((size_t)2 * E);
+  if (E > 0) {
+    CK(cudaMemcpyAsync(h->edges_host.data(), h->d_edge_index.p, sizeof(int64_t) * 2 * E, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+  }
+  *edge_index = h->edges_host.data();
+  *nedges = E;
+  return ALG_OK;
+}
+
+extern "C" int alg_get_output(alg_handle* h, const char* name, const double** ptr, int64_t* n) {
+  if (!h || !name || !ptr || !n) return ALG_EINVAL;
+  CK(cudaSetDevice(h->device));
+  const std::string key(name);
+  auto it = h->outputs.find(key);
+  if (it == h->outputs.end()) {
+    cudaStream_t st = h->stream;
+    const long E = h->last_E;
+    const int ntot = h->last_ntot;
+    const PipelineInfo& pi = h->pinfo;
+    auto fetchf = [&](const void* dptr, size_t count, std::vector<float>& out) -> cudaError_t {
+      out.resize(count);
+      cudaError_t e = cudaMemcpyAsync(out.data(), dptr, sizeof(float) * count, cudaMemcpyDeviceToHost, st);
+      if (e != cudaSuccess) return e;
+      return cudaStreamSynchronize(st);
+    };
+    std::vector<float> raw;
+    std::vector<double> out;
+    if (key == "forces" || key == "atomic_energy") {
+      const bool fo = key == "forces";
+      out.resize(fo ? (size_t)3 * ntot : (size_t)ntot);
+      CK(cudaMemcpyAsync(out.data(), fo ? h->d_forces.p : h->d_eall.p, sizeof(double) * out.size(), cudaMemcpyDeviceToHost, st));
+      CK(cudaStreamSynchronize(st));
+    } else if (!h->debug) {
+      return fail(h, ALG_ENOTFOUND, "output '" + key + "' not available (intermediates need option debug=1)");
+    } else if (key == "edge_energy") {
+      CK(fetchf(h->d_edge_energy.p, E, raw)); out.assign(raw.begin(), raw.end());
+    } else if (key == "edge_grad") {
+      CK(fetchf(h->d_edge_grad.p, 3 * E, raw)); out.assign(raw.begin(), raw.end());
+    } else if (key == "edge_vec") {
+      CK(fetchf(h->d_rvec.p, 4 * E, raw));
+      out.resize((size_t)3 * E);
+      for (long e = 0; e < E; ++e) for (int q = 0; q < 3; ++q) out[3 * e + q] = raw[4 * e + q];
+    } else if (h->dbg_ntiles == 0) {
+      return fail(h, ALG_ENOTFOUND, "intermediate outputs need a single-chunk run (raise chunk_edges)");
+    } else if (key.size() == 2 && key[0] == 'x' && key[1] >= '0' && key[1] < '0' + h->nl) {
+      CK(fetchf(h->c_X[key[1] - '0'].p, (size_t)h->dbg_ntiles * S * pi.TM, raw));
+      detile(raw, h->dbg_ntiles, S, pi.TM, E, out);
+    } else if (key == "dx0") {
+      CK(fetchf(h->c_dX.p, (size_t)h->dbg_ntiles * S * pi.TM, raw));
+      detile(raw, h->dbg_ntiles, S, pi.TM, E, out);
+    } else if (key == "du") {
+      CK(fetchf(h->c_du.p, (size_t)h->dbg_ntiles * pi.TM, raw));
+      detile(raw, h->dbg_ntiles, 1, pi.TM, E, out);
+    } else if (key.size() == 2 && key[0] == 'V' && key[1] >= '1' && key[1] < '0' + h->nl) {
+      const int k = key[1] - '0';
+      CK(fetchf(h->c_V[k].p, (size_t)h->dbg_ntiles * U * pi.vdim[k] * pi.TM, raw));
+      detile(raw, h->dbg_ntiles, U * pi.vdim[k], pi.TM, E, out);      // [E][u][comp]
+    } else if ((key.rfind("gamma", 0) == 0 && key.size() == 6) || (key.rfind("dgamma", 0) == 0 && key.size() == 7)) {
+      const bool d = key[0] == 'd';
+      const int k = key.back() - '0';
+      if (k < 0 || k >= h->nl) return fail(h, ALG_ENOTFOUND, "no such layer");
+      CK(fetchf(d ? h->c_dgamma[k].p : h->c_gamma[k].p, (size_t)h->dbg_ncent * pi.F, raw));
+      out.assign(raw.begin(), raw.end());                              // [centre][lm][u]
+    } else {
+      return fail(h, ALG_ENOTFOUND, "unknown output '" + key + "'");
+    }
+    it = h->outputs.emplace(key, std::move(out)).first;
+  }
+  *ptr = it->second.data();
+  *n = (int64_t)it->second.size();
+  return ALG_OK;
+}
+
+extern "C" int alg_get_timings(alg_handle* h, double* ms3) {
+  if (!h || !ms3) return ALG_EINVAL;
+  for (int q = 0; q < 3; ++q) ms3[q] = h->timings[q];
+  return ALG_OK;
+}
+
+extern "C" int alg_halo_pack(const double* d_x, const int* d_list, int n, const double shift[3], double* d_buf, void* stream) {
+  if (n <= 0) return ALG_OK;
+  if (!d_x || !d_list || !d_buf || !shift) return ALG_EINVAL;
+  k_halo_pack<<<(n + 255) / 256, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(d_x, d_list, n, shift[0], shift[1], shift[2], d_buf);
+  return cudaGetLastError() == cudaSuccess ? ALG_OK : ALG_ECUDA;
+}
+extern "C" int alg_halo_unpack_add(double* d_f, const int* d_list, int n, const double* d_buf, void* stream) {
+  if (n <= 0) return ALG_OK;
+  if (!d_f || !d_list || !d_buf) return ALG_EINVAL;
+  k_halo_unpack_add<<<(n + 255) / 256, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(d_f, d_list, n, d_buf);
+  return cudaGetLastError() == cudaSuccess ? ALG_OK : ALG_ECUDA;
+}

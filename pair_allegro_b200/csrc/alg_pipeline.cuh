@@ -1,0 +1,103 @@
+// Per-l_max pipeline instantiation: one translation unit per L (alg_inst_L{1,2,3}.cu) so the
+// unrolled tensor-product code compiles in parallel.
+#pragma once
+#include "allegro_kernels.cuh"
+
+namespace alg {
+
+struct PipelineInfo {
+  int L, TM, NSH, ENVW, F;
+  int vdim[3];        // components per channel of V^k (k = 1..nl-1), index by k
+  int dvdim;          // max over vdim
+  size_t smem_bytes;
+};
+
+struct Pipeline {
+  PipelineInfo (*info)(int nl);
+  cudaError_t (*init)();                                                       // opt-in shared memory
+  cudaError_t (*run_chunk)(const ChunkArgs& a, const ModelW& w, int ntiles, cudaStream_t st);
+};
+
+const Pipeline* get_pipeline(int L);
+
+#ifdef ALG_PIPELINE_IMPL
+template <int L> PipelineInfo info_impl(int nl) {
+  using D = Dims<L>;
+  PipelineInfo p{};
+  p.L = L; p.TM = D::TM; p.NSH = D::NSH; p.ENVW = D::ENVW; p.F = D::F;
+  p.vdim[0] = D::NSH; p.vdim[1] = p.vdim[2] = 0;
+  if (nl == 2) p.vdim[1] = tpgen::TP<L, 'B'>::DOUT;
+  if (nl == 3) { p.vdim[1] = tpgen::TP<L, 'C'>::DOUT; p.vdim[2] = tpgen::TP<L, 'D'>::DOUT; }
+  p.dvdim = p.vdim[1] > p.vdim[2] ? p.vdim[1] : p.vdim[2];
+  p.smem_bytes = Smem<L>::BYTES;
+  return p;
+}
+
+template <int L> cudaError_t init_impl() {
+  const int b = (int)Smem<L>::BYTES;
+  cudaError_t e;
+#define ALG_SET(kern) \
+  if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, b)) != cudaSuccess) return e;
+  ALG_SET((k_f0<L>));
+  ALG_SET((k_fk<L, 'B', true>));
+  ALG_SET((k_fk<L, 'C', true>));
+  ALG_SET((k_fk<L, 'D', false>));
+  ALG_SET((k_t<L, true>));
+  ALG_SET((k_t<L, false>));
+  ALG_SET((k_bk<L, 'B', true>));
+  ALG_SET((k_bk<L, 'C', true>));
+  ALG_SET((k_bk<L, 'D', false>));
+  ALG_SET((k_b0<L>));
+#undef ALG_SET
+  return cudaSuccess;
+}
+
+template <int L> cudaError_t run_chunk_impl(const ChunkArgs& a, const ModelW& w, int ntiles, cudaStream_t st) {
+  using D = Dims<L>;
+  constexpr int TM = D::TM;
+  const size_t sm = Smem<L>::BYTES;
+  const dim3 g(ntiles), b(NT);
+  auto fix = [&](float* out) { k_fixup<TM><<<g, 128, 0, st>>>(a.edge_c, a.rowptr, a.e0, a.e1, a.c0, ntiles, D::F, out, a.carry); };
+  k_f0<L><<<g, b, sm, st>>>(a, w);
+  fix(a.gamma[0]);
+  const int nl = w.nl;
+  if (nl == 1) {
+    k_t<L, true><<<g, b, sm, st>>>(a, w, 0);
+  } else if (nl == 2) {
+    k_fk<L, 'B', true><<<g, b, sm, st>>>(a, w, 0);
+    fix(a.gamma[1]);
+    k_t<L, false><<<g, b, sm, st>>>(a, w, 1);
+  } else {
+    k_fk<L, 'C', true><<<g, b, sm, st>>>(a, w, 0);
+    fix(a.gamma[1]);
+    k_fk<L, 'D', false><<<g, b, sm, st>>>(a, w, 1);
+    fix(a.gamma[2]);
+    k_t<L, false><<<g, b, sm, st>>>(a, w, 2);
+  }
+  fix(a.dgamma[nl - 1]);
+  k_fixup_e<TM><<<(ntiles + 127) / 128, 128, 0, st>>>(a.edge_c, a.rowptr, a.e0, a.e1, ntiles, a.esum, a.ecarry);
+  if (nl == 2) {
+    k_bk<L, 'B', true><<<g, b, sm, st>>>(a, w, 0);
+    fix(a.dgamma[0]);
+  } else if (nl == 3) {
+    k_bk<L, 'D', false><<<g, b, sm, st>>>(a, w, 1);
+    fix(a.dgamma[1]);
+    k_bk<L, 'C', true><<<g, b, sm, st>>>(a, w, 0);
+    fix(a.dgamma[0]);
+  }
+  k_b0<L><<<g, b, sm, st>>>(a, w);
+  return cudaGetLastError();
+}
+
+#define ALG_DEFINE_PIPELINE(L)                                                             \
+  const Pipeline* get_pipeline_L##L() {                                                    \
+    static const Pipeline p = {&info_impl<L>, &init_impl<L>, &run_chunk_impl<L>};          \
+    return &p;                                                                             \
+  }
+#endif
+
+const Pipeline* get_pipeline_L1();
+const Pipeline* get_pipeline_L2();
+const Pipeline* get_pipeline_L3();
+
+}  // namespace alg

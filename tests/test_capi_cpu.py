@@ -1,0 +1,97 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library builds, loads and exports every
+symbol include/allegro_b200.h declares; without a GPU it fails LOUDLY (no CPU fallback); the
+host-side pair-style mirror keeps the reference's argument/error behaviour."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+from helpers import alg_path
+
+
+def test_header_symbols_exported(ensure_built):
+    from pair_allegro_b200 import capi
+    hdr = open(os.path.join(ROOT, "include", "allegro_b200.h")).read()
+    declared = sorted(set(re.findall(r"ALG_API[^;]*?\b(alg_[a-z_0-9]+)\s*\(", hdr)))
+    assert declared, "no prototypes found in the header"
+    lib = ctypes.CDLL(ensure_built)
+    for sym in declared:
+        assert hasattr(lib, sym), "library does not export " + sym
+    assert sorted(capi.EXPORTS) == declared
+    assert b"sm_100a" in capi.load_library().alg_version()
+
+
+def test_library_has_sm100a_code(ensure_built):
+    """the shipped binary carries sm_100a SASS (not PTX-only, not another arch)"""
+    import subprocess
+    out = subprocess.run(["cuobjdump", "-lelf", ensure_built], capture_output=True, text=True).stdout
+    assert "sm_100a" in out, out
+
+
+def test_no_cpu_fallback(ensure_built):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from pair_allegro_b200 import capi
+    with pytest.raises(capi.AllegroError) as ei:
+        capi.Handle(alg_path("Cu_r5"), 0)
+    assert ei.value.code == -3 and "no CPU fallback" in str(ei.value)
+
+
+def test_create_rejects_bad_file(ensure_built, tmp_path):
+    """argument validation happens before any device work only for null args; a malformed file on a
+    GPU-less box still reports the missing device first -- both are loud errors"""
+    from pair_allegro_b200 import capi
+    p = tmp_path / "bad.alg"
+    p.write_bytes(b"not a weight file")
+    with pytest.raises(capi.AllegroError):
+        capi.Handle(str(p), 0)
+
+
+def test_pair_style_argument_errors():
+    """same messages / conditions as pair_nequip_allegro.cpp:171,185-192,205"""
+    from pair_allegro_b200.pair import PairAllegroB200
+    p = PairAllegroB200()
+    with pytest.raises(RuntimeError, match="too many arguments"):
+        p.settings(["x"])
+    with pytest.raises(RuntimeError, match="Incorrect args for pair coefficients"):
+        p.coeff(["*", "*", "m.alg"], 2)                     # missing type names
+    with pytest.raises(RuntimeError, match="Incorrect args for pair coefficients"):
+        p.coeff(["1", "*", "m.alg", "Cu"], 1)
+    with pytest.raises(RuntimeError, match="Only accepts model paths"):
+        p.coeff(["*", "*", "model.pt", "Cu"], 1)
+    with pytest.raises(RuntimeError, match="requires newton pair on"):
+        p.init_style(newton_pair=0)
+    with pytest.raises(RuntimeError, match="requires atom IDs"):
+        p.init_style(tag_enable=0)
+
+
+def test_alg_roundtrip_and_metadata():
+    from pair_allegro_b200.export import read_alg
+    hdr, ten = read_alg(alg_path("Cu2AgO4_r5"))
+    assert hdr["type_names"] == "Ag Cu O" and hdr["num_types"] == "3" and hdr["allow_tf32"] == "0"
+    assert len(hdr["per_edge_type_cutoff"].split()) == 9
+    assert ten["twobody.w0"].shape == (2 * 3 + 8, 64)
+    assert ten["layer0.mlp.w0"].shape == (64 + 4 * 32, 64)
+    assert ten["scales"].dtype == np.float64
+
+
+def test_generated_tables_are_current():
+    """tp_gen.cuh / allegro_tables.json are what tools/gen_tables.py generates (structure check)"""
+    import importlib.util
+    import json
+    spec = importlib.util.spec_from_file_location("gen_tables", os.path.join(ROOT, "tools", "gen_tables.py"))
+    gt = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gt)
+    t = gt.build_tables()
+    old = json.load(open(os.path.join(ROOT, "tables", "allegro_tables.json")))
+    for L in ("1", "2", "3"):
+        for k in "ABCD":
+            a, b = t["L"][L]["kinds"][k], old["L"][L]["kinds"][k]
+            assert a["n_paths"] == b["n_paths"] and a["din"] == b["din"] and a["dout"] == b["dout"]
+            for pa, pb in zip(a["paths"], b["paths"]):
+                assert [q[:3] for q in pa["nz"]] == [q[:3] for q in pb["nz"]]
+                np.testing.assert_allclose([q[3] for q in pa["nz"]], [q[3] for q in pb["nz"]], atol=1e-12)
