@@ -78,7 +78,8 @@ ALG_API int alg_set_type_map(alg_handle* h, int ntypes, const int* lammps_type_t
  *                  | "lt" (Kokkos path rsq < cut^2, pair_nequip_allegro_kokkos.cpp:189)
  *   "chunk_edges"  edges processed per pipeline pass (activation buffers are sized by this)
  *   "keep_edges"   "1": materialise the int64 [2,E] edge_index for alg_get_edges
- *   "debug"        "1": keep per-edge gradients / intermediates for alg_get_output */
+ *   "debug"        "1": keep per-edge gradients / intermediates for alg_get_output
+ *   "profile"      "1": time every pipeline kernel with CUDA events (alg_get_stats) */
 ALG_API int alg_set_option(alg_handle* h, const char* key, const char* value);
 
 /* Host-pointer force evaluation: replaces the body of PairNequIPAllegro<false>::compute()
@@ -133,12 +134,17 @@ ALG_API int alg_get_output(alg_handle* h, const char* name, const double** ptr, 
  * stream): [0] edge build, [1] network forward+backward, [2] finalize/store. */
 ALG_API int alg_get_timings(alg_handle* h, double* ms3);
 
+/* Counters of the last compute (doubles): what = "step" -> [own kernel launches, edges, chunks,
+ * tiles]; with option profile=1 also "kernel_ms" / "kernel_launches" -> per kernel family
+ * [F0, FK, T, BK, B0, fixup] summed CUDA-event durations (ms) and launch counts. */
+ALG_API int alg_get_stats(alg_handle* h, const char* what, double* out, int n);
+
 /* Ghost halo helpers for spatial-domain multi-GPU runs (replace LAMMPS
  * comm->forward_comm / reverse_comm pack/unpack for x and f; the transport between ranks is
  * NCCL and lives in the caller).  Device pointers; stream-ordered.
- *   pack:        buf[k][0..2] = x[list[k]][0..2] + shift[0..2]
- *   unpack_add:  f[list[k]][0..2] += buf[k][0..2]        (list entries must be unique) */
-ALG_API int alg_halo_pack(const double* d_x, const int* d_list, int n, const double shift[3], double* d_buf,
+ *   pack:        buf[k][0..2] = x[list[k]][0..2] + shift[k][0..2]   (d_shift may be NULL)
+ *   unpack_add:  f[list[k]][0..2] += buf[k][0..2]        (atomic; list entries may repeat) */
+ALG_API int alg_halo_pack(const double* d_x, const int* d_list, int n, const double* d_shift, double* d_buf,
                   void* stream);
 ALG_API int alg_halo_unpack_add(double* d_f, const int* d_list, int n, const double* d_buf, void* stream);
 

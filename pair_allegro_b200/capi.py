@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "liballegro_b200.so")
 
 EXPORTS = ["alg_create", "alg_destroy", "alg_last_error", "alg_metadata", "alg_set_type_map", "alg_set_option",
-           "alg_compute_host", "alg_compute_device", "alg_get_edges", "alg_get_output", "alg_get_timings",
+           "alg_compute_host", "alg_compute_device", "alg_get_edges", "alg_get_output", "alg_get_timings", "alg_get_stats",
            "alg_halo_pack", "alg_halo_unpack_add", "alg_version"]
 
 _lib = None
@@ -60,7 +60,9 @@ def load_library(path=None):
     lib.alg_get_output.restype = C.c_int
     lib.alg_get_timings.argtypes = [vp, dp]
     lib.alg_get_timings.restype = C.c_int
-    lib.alg_halo_pack.argtypes = [vp, vp, C.c_int, dp, vp, vp]
+    lib.alg_get_stats.argtypes = [vp, C.c_char_p, dp, C.c_int]
+    lib.alg_get_stats.restype = C.c_int
+    lib.alg_halo_pack.argtypes = [vp, vp, C.c_int, vp, vp, vp]
     lib.alg_halo_pack.restype = C.c_int
     lib.alg_halo_unpack_add.argtypes = [vp, vp, C.c_int, vp, vp]
     lib.alg_halo_unpack_add.restype = C.c_int
@@ -179,10 +181,18 @@ class Handle:
             return np.zeros(0)
         return np.ctypeslib.as_array(p, shape=(n.value,)).copy()
 
+    def stats(self, what, n):
+        t = np.zeros(n)
+        self._check(self.lib.alg_get_stats(self.h, what.encode(), _dptr(t), n))
+        return t
+
     def timings(self):
         t = np.zeros(3)
         self._check(self.lib.alg_get_timings(self.h, _dptr(t)))
         return t
+
+
+KERNEL_FAMILIES = ["F0", "FK", "T", "BK", "B0", "fixup"]
 
 
 def version():

@@ -110,6 +110,10 @@ struct alg_handle {
   std::vector<int64_t> edges_host;
   std::map<std::string, std::vector<double>> outputs;
   double timings[3] = {0, 0, 0};
+  Prof prof;
+  double kernel_ms[KID_COUNT] = {0, 0, 0, 0, 0, 0};
+  double kernel_n[KID_COUNT] = {0, 0, 0, 0, 0, 0};
+  double step_stats[4] = {0, 0, 0, 0};   // launches of own kernels, edges, chunks, tiles
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   // debug bookkeeping of the last single-chunk run
   int dbg_ntiles = 0, dbg_c0 = 0, dbg_ncent = 0;
@@ -302,21 +306,21 @@ __global__ void k_final_scalars(int nblocks, const double* __restrict__ partial,
   }
 }
 
-__global__ void k_halo_pack(const double* __restrict__ x, const int* __restrict__ list, int n, double sx, double sy, double sz, double* __restrict__ buf) {
+__global__ void k_halo_pack(const double* __restrict__ x, const int* __restrict__ list, int n, const double* __restrict__ shift, double* __restrict__ buf) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= n) return;
   const int i = list[k];
-  buf[3 * (size_t)k + 0] = x[3 * (size_t)i + 0] + sx;
-  buf[3 * (size_t)k + 1] = x[3 * (size_t)i + 1] + sy;
-  buf[3 * (size_t)k + 2] = x[3 * (size_t)i + 2] + sz;
+  buf[3 * (size_t)k + 0] = x[3 * (size_t)i + 0] + (shift ? shift[3 * (size_t)k + 0] : 0.0);
+  buf[3 * (size_t)k + 1] = x[3 * (size_t)i + 1] + (shift ? shift[3 * (size_t)k + 1] : 0.0);
+  buf[3 * (size_t)k + 2] = x[3 * (size_t)i + 2] + (shift ? shift[3 * (size_t)k + 2] : 0.0);
 }
 __global__ void k_halo_unpack_add(double* __restrict__ f, const int* __restrict__ list, int n, const double* __restrict__ buf) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= n) return;
   const int i = list[k];
-  f[3 * (size_t)i + 0] += buf[3 * (size_t)k + 0];
-  f[3 * (size_t)i + 1] += buf[3 * (size_t)k + 1];
-  f[3 * (size_t)i + 2] += buf[3 * (size_t)k + 2];
+  atomicAdd(f + 3 * (size_t)i + 0, buf[3 * (size_t)k + 0]);   // list entries may repeat (several images of one atom)
+  atomicAdd(f + 3 * (size_t)i + 1, buf[3 * (size_t)k + 1]);
+  atomicAdd(f + 3 * (size_t)i + 2, buf[3 * (size_t)k + 2]);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -519,6 +523,7 @@ extern "C" int alg_set_option(alg_handle* h, const char* key, const char* value)
     h->chunk_edges = c;
   } else if (k == "keep_edges") h->keep_edges = v == "1";
   else if (k == "debug") h->debug = v == "1";
+  else if (k == "profile") h->prof.on = v == "1";
   else return fail(h, ALG_ENOTFOUND, "unknown option " + k);
   return ALG_OK;
 }
@@ -641,11 +646,17 @@ static int run_step(alg_handle* h, int nlocal, int nghost, const double* d_x, co
   a.edge_grad = h->debug ? h->d_edge_grad.as<float>() : nullptr;
   a.facc = h->d_facc.as<unsigned long long>();
   a.vacc = h->d_vacc.as<unsigned long long>();
+  h->prof.reset();
+  long tiles_total = 0;
   for (const Chunk& c : chunks) {
     a.e0 = c.e0; a.e1 = c.e1; a.c0 = c.c0;
     const int ntiles = (c.e1 - c.e0 + TM - 1) / TM;
-    CK(h->pipe->run_chunk(a, h->mw, ntiles, st));
+    tiles_total += ntiles;
+    CK(h->pipe->run_chunk(a, h->mw, ntiles, st, &h->prof));
   }
+  // own kernels outside the chunk pipeline: k_mtype, k_edges x2, [k_edge_index], 4 finalize kernels
+  h->step_stats[0] = (double)h->prof.launches + 3 + (h->keep_edges && E > 0 ? 1 : 0) + 4;
+  h->step_stats[1] = (double)E; h->step_stats[2] = (double)chunks.size(); h->step_stats[3] = (double)tiles_total;
   CK(cudaEventRecord(h->ev[2], st));
   // ---- finalize
   CK(h->d_forces.ensure(sizeof(double) * 3 * ntot));
@@ -669,6 +680,13 @@ static int run_step(alg_handle* h, int nlocal, int nghost, const double* d_x, co
     if (virial6 && vflag_global) for (int q = 0; q < 6; ++q) virial6[q] = o[1 + q];
     float ms;
     for (int q = 0; q < 3; ++q) { cudaEventElapsedTime(&ms, h->ev[q], h->ev[q + 1]); h->timings[q] = ms; }
+    if (h->prof.on) {
+      for (int q = 0; q < KID_COUNT; ++q) { h->kernel_ms[q] = 0; h->kernel_n[q] = 0; }
+      for (size_t r = 0; r < h->prof.ids.size(); ++r) {
+        cudaEventElapsedTime(&ms, h->prof.ev[2 * r], h->prof.ev[2 * r + 1]);
+        h->kernel_ms[h->prof.ids[r]] += ms; h->kernel_n[h->prof.ids[r]] += 1;
+      }
+    }
   }
   h->dbg_ntiles = chunks.size() == 1 ? (chunks[0].e1 - chunks[0].e0 + TM - 1) / TM : 0;
   h->dbg_c0 = chunks.size() == 1 ? chunks[0].c0 : 0;
@@ -845,10 +863,22 @@ extern "C" int alg_get_timings(alg_handle* h, double* ms3) {
   return ALG_OK;
 }
 
-extern "C" int alg_halo_pack(const double* d_x, const int* d_list, int n, const double shift[3], double* d_buf, void* stream) {
+extern "C" int alg_get_stats(alg_handle* h, const char* what, double* out, int n) {
+  if (!h || !what || !out) return ALG_EINVAL;
+  const std::string k(what);
+  const double* src = nullptr; int m = 0;
+  if (k == "kernel_ms") { src = h->kernel_ms; m = KID_COUNT; }
+  else if (k == "kernel_launches") { src = h->kernel_n; m = KID_COUNT; }
+  else if (k == "step") { src = h->step_stats; m = 4; }
+  else return fail(h, ALG_ENOTFOUND, "unknown stats group " + k);
+  for (int i = 0; i < n && i < m; ++i) out[i] = src[i];
+  return ALG_OK;
+}
+
+extern "C" int alg_halo_pack(const double* d_x, const int* d_list, int n, const double* d_shift, double* d_buf, void* stream) {
   if (n <= 0) return ALG_OK;
-  if (!d_x || !d_list || !d_buf || !shift) return ALG_EINVAL;
-  k_halo_pack<<<(n + 255) / 256, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(d_x, d_list, n, shift[0], shift[1], shift[2], d_buf);
+  if (!d_x || !d_list || !d_buf) return ALG_EINVAL;
+  k_halo_pack<<<(n + 255) / 256, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(d_x, d_list, n, d_shift, d_buf);
   return cudaGetLastError() == cudaSuccess ? ALG_OK : ALG_ECUDA;
 }
 extern "C" int alg_halo_unpack_add(double* d_f, const int* d_list, int n, const double* d_buf, void* stream) {

@@ -25,7 +25,8 @@ constexpr double FIX_INV = 1.0 / 4294967296.0;
 constexpr double VIR_SCALE = 16777216.0;            // 2^24 fixed point for the virial
 
 template <int L> struct Dims {
-  static constexpr int TM = (L == 3) ? 64 : 128;   // edges per tile
+  static constexpr int TM = 64;                     // edges per tile (2 CTAs/SM for L <= 2)
+  static constexpr int MINB = (L == 3) ? 1 : 2;     // resident CTAs per SM targeted by __launch_bounds__
   static constexpr int NSH = (L + 1) * (L + 1);
   static constexpr int NL = L + 1;
   static constexpr int ENVW = NL * U;               // env / embed linear width, column = l*U+u
@@ -135,14 +136,44 @@ __device__ __forceinline__ void gemm_tile(const float* __restrict__ A_s, int K, 
       for (int j = 0; j < 4; ++j) acc[q][i][j] = 0.f;
   const float* wp = W + col0 + ng * 4;
   const float* ap = A_s + mg * 4;
-#pragma unroll 4
-  for (int k = 0; k < K; ++k) {
+  constexpr int KB = 8;   // weight rows prefetched one block ahead (hides L2 latency of the weight stream)
+  const int nkb = K / KB;
+  float4 wn[KB];
+  if (nkb > 0) {
+#pragma unroll
+    for (int kk = 0; kk < KB; ++kk) wn[kk] = __ldg(reinterpret_cast<const float4*>(wp + (size_t)kk * ldw));
+  }
+#pragma unroll 1
+  for (int kb = 0; kb < nkb; ++kb) {
+    float4 wc[KB];
+#pragma unroll
+    for (int kk = 0; kk < KB; ++kk) wc[kk] = wn[kk];
+    if (kb + 1 < nkb) {
+#pragma unroll
+      for (int kk = 0; kk < KB; ++kk) wn[kk] = __ldg(reinterpret_cast<const float4*>(wp + (size_t)((kb + 1) * KB + kk) * ldw));
+    }
+#pragma unroll
+    for (int kk = 0; kk < KB; ++kk) {
+      const int k = kb * KB + kk;
+      const float w[4] = {wc[kk].x, wc[kk].y, wc[kk].z, wc[kk].w};
+#pragma unroll
+      for (int q = 0; q < C::Q; ++q) {
+        const float4 a4 = *reinterpret_cast<const float4*>(ap + k * TM + q * (C::MG * 4));
+        const float a[4] = {a4.x, a4.y, a4.z, a4.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[q][i][j] = fmaf(a[i], w[j], acc[q][i][j]);
+      }
+    }
+  }
+  for (int k = nkb * KB; k < K; ++k) {   // K tail (num_bessels not a multiple of 8)
     const float4 w4 = __ldg(reinterpret_cast<const float4*>(wp + (size_t)k * ldw));
+    const float w[4] = {w4.x, w4.y, w4.z, w4.w};
 #pragma unroll
     for (int q = 0; q < C::Q; ++q) {
       const float4 a4 = *reinterpret_cast<const float4*>(ap + k * TM + q * (C::MG * 4));
       const float a[4] = {a4.x, a4.y, a4.z, a4.w};
-      const float w[4] = {w4.x, w4.y, w4.z, w4.w};
 #pragma unroll
       for (int i = 0; i < 4; ++i)
 #pragma unroll

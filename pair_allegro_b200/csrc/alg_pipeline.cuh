@@ -1,6 +1,8 @@
 // Per-l_max pipeline instantiation: one translation unit per L (alg_inst_L{1,2,3}.cu) so the
 // unrolled tensor-product code compiles in parallel.
 #pragma once
+#include <vector>
+
 #include "allegro_kernels.cuh"
 
 namespace alg {
@@ -12,10 +14,33 @@ struct PipelineInfo {
   size_t smem_bytes;
 };
 
+// optional per-kernel CUDA-event timing (option profile=1) and launch counting
+enum { KID_F0 = 0, KID_FK = 1, KID_T = 2, KID_BK = 3, KID_B0 = 4, KID_FIXUP = 5, KID_COUNT = 6 };
+struct Prof {
+  bool on = false;
+  std::vector<cudaEvent_t> ev;
+  std::vector<int> ids;
+  size_t used = 0;
+  long launches = 0;
+  void begin(int id, cudaStream_t st) {
+    ++launches;
+    if (!on) return;
+    while (ev.size() < used + 2) { cudaEvent_t e; cudaEventCreate(&e); ev.push_back(e); }
+    cudaEventRecord(ev[used], st);
+    ids.push_back(id);
+  }
+  void end(cudaStream_t st) {
+    if (!on) return;
+    cudaEventRecord(ev[used + 1], st);
+    used += 2;
+  }
+  void reset() { used = 0; ids.clear(); launches = 0; }
+};
+
 struct Pipeline {
   PipelineInfo (*info)(int nl);
   cudaError_t (*init)();                                                       // opt-in shared memory
-  cudaError_t (*run_chunk)(const ChunkArgs& a, const ModelW& w, int ntiles, cudaStream_t st);
+  cudaError_t (*run_chunk)(const ChunkArgs& a, const ModelW& w, int ntiles, cudaStream_t st, Prof* prof);
 };
 
 const Pipeline* get_pipeline(int L);
@@ -52,40 +77,44 @@ template <int L> cudaError_t init_impl() {
   return cudaSuccess;
 }
 
-template <int L> cudaError_t run_chunk_impl(const ChunkArgs& a, const ModelW& w, int ntiles, cudaStream_t st) {
+template <int L> cudaError_t run_chunk_impl(const ChunkArgs& a, const ModelW& w, int ntiles, cudaStream_t st, Prof* pf) {
   using D = Dims<L>;
   constexpr int TM = D::TM;
   const size_t sm = Smem<L>::BYTES;
   const dim3 g(ntiles), b(NT);
-  auto fix = [&](float* out) { k_fixup<TM><<<g, 128, 0, st>>>(a.edge_c, a.rowptr, a.e0, a.e1, a.c0, ntiles, D::F, out, a.carry); };
-  k_f0<L><<<g, b, sm, st>>>(a, w);
+#define ALG_RUN(kid, ...) do { pf->begin(kid, st); __VA_ARGS__; pf->end(st); } while (0)
+  auto fix = [&](float* out) {
+    ALG_RUN(KID_FIXUP, (k_fixup<TM><<<g, 128, 0, st>>>(a.edge_c, a.rowptr, a.e0, a.e1, a.c0, ntiles, D::F, out, a.carry)));
+  };
+  ALG_RUN(KID_F0, (k_f0<L><<<g, b, sm, st>>>(a, w)));
   fix(a.gamma[0]);
   const int nl = w.nl;
   if (nl == 1) {
-    k_t<L, true><<<g, b, sm, st>>>(a, w, 0);
+    ALG_RUN(KID_T, (k_t<L, true><<<g, b, sm, st>>>(a, w, 0)));
   } else if (nl == 2) {
-    k_fk<L, 'B', true><<<g, b, sm, st>>>(a, w, 0);
+    ALG_RUN(KID_FK, (k_fk<L, 'B', true><<<g, b, sm, st>>>(a, w, 0)));
     fix(a.gamma[1]);
-    k_t<L, false><<<g, b, sm, st>>>(a, w, 1);
+    ALG_RUN(KID_T, (k_t<L, false><<<g, b, sm, st>>>(a, w, 1)));
   } else {
-    k_fk<L, 'C', true><<<g, b, sm, st>>>(a, w, 0);
+    ALG_RUN(KID_FK, (k_fk<L, 'C', true><<<g, b, sm, st>>>(a, w, 0)));
     fix(a.gamma[1]);
-    k_fk<L, 'D', false><<<g, b, sm, st>>>(a, w, 1);
+    ALG_RUN(KID_FK, (k_fk<L, 'D', false><<<g, b, sm, st>>>(a, w, 1)));
     fix(a.gamma[2]);
-    k_t<L, false><<<g, b, sm, st>>>(a, w, 2);
+    ALG_RUN(KID_T, (k_t<L, false><<<g, b, sm, st>>>(a, w, 2)));
   }
   fix(a.dgamma[nl - 1]);
-  k_fixup_e<TM><<<(ntiles + 127) / 128, 128, 0, st>>>(a.edge_c, a.rowptr, a.e0, a.e1, ntiles, a.esum, a.ecarry);
+  ALG_RUN(KID_FIXUP, (k_fixup_e<TM><<<(ntiles + 127) / 128, 128, 0, st>>>(a.edge_c, a.rowptr, a.e0, a.e1, ntiles, a.esum, a.ecarry)));
   if (nl == 2) {
-    k_bk<L, 'B', true><<<g, b, sm, st>>>(a, w, 0);
+    ALG_RUN(KID_BK, (k_bk<L, 'B', true><<<g, b, sm, st>>>(a, w, 0)));
     fix(a.dgamma[0]);
   } else if (nl == 3) {
-    k_bk<L, 'D', false><<<g, b, sm, st>>>(a, w, 1);
+    ALG_RUN(KID_BK, (k_bk<L, 'D', false><<<g, b, sm, st>>>(a, w, 1)));
     fix(a.dgamma[1]);
-    k_bk<L, 'C', true><<<g, b, sm, st>>>(a, w, 0);
+    ALG_RUN(KID_BK, (k_bk<L, 'C', true><<<g, b, sm, st>>>(a, w, 0)));
     fix(a.dgamma[0]);
   }
-  k_b0<L><<<g, b, sm, st>>>(a, w);
+  ALG_RUN(KID_B0, (k_b0<L><<<g, b, sm, st>>>(a, w)));
+#undef ALG_RUN
   return cudaGetLastError();
 }
 

@@ -89,7 +89,7 @@ template <int L> __device__ __forceinline__ void env_sum(const ChunkArgs& a, con
 // F0
 // ============================================================================================
 template <int L>
-__global__ void __launch_bounds__(NT, 1) k_f0(const __grid_constant__ ChunkArgs a, const __grid_constant__ ModelW w) {
+__global__ void __launch_bounds__(NT, Dims<L>::MINB) k_f0(const __grid_constant__ ChunkArgs a, const __grid_constant__ ModelW w) {
   using D = Dims<L>; using SM = Smem<L>; constexpr int TM = D::TM;
   extern __shared__ __align__(16) float sm[];
   const int t = threadIdx.x, tile = blockIdx.x;
@@ -163,7 +163,7 @@ __device__ __forceinline__ void load_vin(const ChunkArgs& a, int tile, int k, in
 // FK: layer k forward (k < nl-1)
 // ============================================================================================
 template <int L, char KIND, bool FIRST>
-__global__ void __launch_bounds__(NT, 1) k_fk(const __grid_constant__ ChunkArgs a, const __grid_constant__ ModelW w, const int k) {
+__global__ void __launch_bounds__(NT, Dims<L>::MINB) k_fk(const __grid_constant__ ChunkArgs a, const __grid_constant__ ModelW w, const int k) {
   using D = Dims<L>; using SM = Smem<L>; using TP = tpgen::TP<L, KIND>; constexpr int TM = D::TM;
   extern __shared__ __align__(16) float sm[];
   const int t = threadIdx.x, tile = blockIdx.x;
@@ -401,7 +401,7 @@ __device__ __forceinline__ void phase2(const ChunkArgs& a, const ModelW& w, int 
 // T: last layer (kind 'A') forward + readout + backward phase 1
 // ============================================================================================
 template <int L, bool FIRST>
-__global__ void __launch_bounds__(NT, 1) k_t(const __grid_constant__ ChunkArgs a, const __grid_constant__ ModelW w, const int k) {
+__global__ void __launch_bounds__(NT, Dims<L>::MINB) k_t(const __grid_constant__ ChunkArgs a, const __grid_constant__ ModelW w, const int k) {
   using D = Dims<L>; using SM = Smem<L>; using TP = tpgen::TP<L, 'A'>; constexpr int TM = D::TM;
   extern __shared__ __align__(16) float sm[];
   const int t = threadIdx.x, tile = blockIdx.x;
@@ -506,7 +506,7 @@ __global__ void __launch_bounds__(NT, 1) k_t(const __grid_constant__ ChunkArgs a
 // BK: backward of layer k (k < nl-1): phase 2 of layer k+1, then phase 1 of layer k
 // ============================================================================================
 template <int L, char KIND, bool FIRST>
-__global__ void __launch_bounds__(NT, 1) k_bk(const __grid_constant__ ChunkArgs a, const __grid_constant__ ModelW w, const int k) {
+__global__ void __launch_bounds__(NT, Dims<L>::MINB) k_bk(const __grid_constant__ ChunkArgs a, const __grid_constant__ ModelW w, const int k) {
   using D = Dims<L>; using SM = Smem<L>; using TP = tpgen::TP<L, KIND>; constexpr int TM = D::TM;
   extern __shared__ __align__(16) float sm[];
   const int t = threadIdx.x, tile = blockIdx.x;
@@ -575,7 +575,7 @@ __global__ void __launch_bounds__(NT, 1) k_bk(const __grid_constant__ ChunkArgs 
 // B0: phase 2 of layer 0, embed / two-body / geometry backward, force + virial accumulation
 // ============================================================================================
 template <int L>
-__global__ void __launch_bounds__(NT, 1) k_b0(const __grid_constant__ ChunkArgs a, const __grid_constant__ ModelW w) {
+__global__ void __launch_bounds__(NT, Dims<L>::MINB) k_b0(const __grid_constant__ ChunkArgs a, const __grid_constant__ ModelW w) {
   using D = Dims<L>; using SM = Smem<L>; constexpr int TM = D::TM;
   extern __shared__ __align__(16) float sm[];
   const int t = threadIdx.x, tile = blockIdx.x;
