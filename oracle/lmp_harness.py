@@ -282,3 +282,83 @@ def decompose(pos, types, cell, pbc, nranks, rcomm):
                          nghost=len(x) - len(mine), ntypes=ntypes,
                          owner_rank=np.concatenate(orank), owner_index=np.concatenate(oidx)))
     return out, rank_of, local_index
+
+
+def decompose_rank(pos, types, cell, pbc, nranks, rank, rcomm):
+    """One rank's view of the brick decomposition plus its halo plan.
+
+    Ghosts are ordered by (owner rank, image shift id, owner local index) so that the ghosts
+    owned by one peer form a contiguous slice (forward comm can receive straight into x, reverse
+    comm can send straight out of f) and so that the owner can reproduce the order on its own.
+    Returns (atoms, plan) with plan = dict(
+        recv_slices[s] = (start, stop) ghost index range owned by rank s (absent if empty),
+        send_index[s]  = local atom indices this rank ships to rank s (in s's ghost order),
+        send_shift[s]  = [n,3] shift to add to x when packing for rank s)."""
+    L = np.diag(cell).astype(np.float64)
+    assert np.allclose(cell, np.diag(L)), "brick decomposition: orthogonal boxes only"
+    pos = np.asarray(pos, dtype=np.float64).copy()
+    for k in range(3):
+        if pbc[k]:
+            pos[:, k] -= np.floor(pos[:, k] / L[k]) * L[k]
+    grid = np.array(proc_grid(nranks))
+    sub = L / grid
+    cidx = np.minimum((pos / sub).astype(np.int64), grid - 1)
+    rank_of = (cidx[:, 0] * grid[1] + cidx[:, 1]) * grid[2] + cidx[:, 2]
+    mine = np.nonzero(rank_of == rank)[0]
+    counts = np.bincount(rank_of, minlength=nranks)
+    # local index of every atom on its owner = rank within the owner's (stable, global-order) list
+    order = np.argsort(rank_of, kind="stable")
+    starts = np.concatenate([[0], np.cumsum(counts)])
+    local_index = np.empty(len(pos), dtype=np.int64)
+    local_index[order] = np.arange(len(pos)) - starts[rank_of[order]]
+    shifts = [(a, b, c) for a in ((-1, 0, 1) if pbc[0] else (0,)) for b in ((-1, 0, 1) if pbc[1] else (0,))
+              for c in ((-1, 0, 1) if pbc[2] else (0,))]
+    assert np.all(sub >= rcomm), "sub-domain thinner than the ghost cutoff"
+
+    def brick(r):
+        c = np.array([r // (grid[1] * grid[2]), (r // grid[2]) % grid[1], r % grid[2]])
+        return c * sub, (c + 1) * sub
+
+    lo, hi = brick(rank)
+    # --- my ghosts
+    g_idx, g_shift, g_sid = [], [], []
+    for sid, sh in enumerate(shifts):
+        shv = np.array(sh) * L
+        p2 = pos + shv
+        keep = np.all((p2 >= lo - rcomm) & (p2 < hi + rcomm), axis=1)
+        if sh == (0, 0, 0):
+            keep &= rank_of != rank
+        idx = np.nonzero(keep)[0]
+        g_idx.append(idx); g_shift.append(np.tile(shv, (len(idx), 1))); g_sid.append(np.full(len(idx), sid))
+    g_idx = np.concatenate(g_idx); g_shift = np.concatenate(g_shift); g_sid = np.concatenate(g_sid)
+    o = np.lexsort((local_index[g_idx], g_sid, rank_of[g_idx]))
+    g_idx, g_shift = g_idx[o], g_shift[o]
+    x = np.concatenate([pos[mine], pos[g_idx] + g_shift])
+    atoms = Atoms(x=x, type=np.concatenate([types[mine], types[g_idx]]).astype(np.int32),
+                  tag=np.concatenate([mine, g_idx]).astype(np.int64) + 1, nlocal=len(mine), nghost=len(g_idx),
+                  ntypes=int(types.max()), owner_rank=np.concatenate([np.full(len(mine), rank), rank_of[g_idx]]),
+                  owner_index=np.concatenate([np.arange(len(mine)), local_index[g_idx]]))
+    plan = dict(recv_slices={}, send_index={}, send_shift={})
+    gowner = rank_of[g_idx]
+    for s in range(nranks):
+        w = np.nonzero(gowner == s)[0]
+        if len(w):
+            plan["recv_slices"][s] = (len(mine) + int(w[0]), len(mine) + int(w[-1]) + 1)
+    # --- what I ship to each peer s: my atoms inside s's extended brick, (shift id, local index) order
+    mypos = pos[mine]
+    for s in range(nranks):
+        slo, shi = brick(s)
+        si, ss = [], []
+        for sh in shifts:
+            if s == rank and sh == (0, 0, 0):
+                continue
+            shv = np.array(sh) * L
+            p2 = mypos + shv
+            keep = np.all((p2 >= slo - rcomm) & (p2 < shi + rcomm), axis=1)
+            idx = np.nonzero(keep)[0]
+            si.append(idx); ss.append(np.tile(shv, (len(idx), 1)))
+        si = np.concatenate(si); ss = np.concatenate(ss)
+        if len(si):
+            plan["send_index"][s] = si.astype(np.int32)
+            plan["send_shift"][s] = ss
+    return atoms, plan

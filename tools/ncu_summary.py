@@ -1,0 +1,71 @@
+#!/usr/bin/env python
+"""Summarise ncu output for profiles/:
+   python tools/ncu_summary.py launches <launches.csv> <out.md>     (gpu__time_duration list)
+   python tools/ncu_summary.py full <report.ncu-rep> <out.md>       (--set full capture)"""
+import csv
+import subprocess
+import sys
+from collections import OrderedDict
+
+KEYS = ["gpu__time_duration.sum", "launch__grid_size", "launch__registers_per_thread", "launch__occupancy_limit_shared_mem",
+        "launch__occupancy_limit_registers", "sm__warps_active.avg.pct_of_peak_sustained_active",
+        "smsp__issue_active.avg.pct_of_peak_sustained_active", "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_tensor.sum", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
+        "sm__throughput.avg.pct_of_peak_sustained_elapsed", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
+        "dram__bytes_read.sum", "dram__bytes_write.sum", "lts__t_sector_hit_rate.pct", "l1tex__t_sector_hit_rate.pct",
+        "smsp__inst_executed.sum", "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio",
+        "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum"]
+
+
+def short(name):
+    n = name.replace("void ", "").replace("alg::", "")
+    return n.split("(")[0]
+
+
+def launches(path, out):
+    rows = [r for r in csv.reader(open(path)) if len(r) > 10]
+    h = rows[0]
+    ki, vi, ui = h.index("Kernel Name"), h.index("Metric Value"), h.index("Metric Unit")
+    agg = OrderedDict()
+    for r in rows[1:]:
+        v = float(r[vi].replace(",", ""))
+        if r[ui] == "ns":
+            v /= 1e3
+        elif r[ui] == "ms":
+            v *= 1e3
+        elif r[ui] in ("s", "second"):
+            v *= 1e6
+        k = short(r[ki])
+        a = agg.setdefault(k, [0, 0.0])
+        a[0] += 1
+        a[1] += v
+    tot = sum(a[1] for a in agg.values())
+    with open(out, "w") as f:
+        f.write("# ncu launch list summary (%s): %d launches, %.1f us total (cold-cache, serialised: compare SHARES)\n\n" % (path, len(rows) - 1, tot))
+        f.write("| kernel | launches | total us | share | avg us |\n|---|---:|---:|---:|---:|\n")
+        for k, (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+            f.write("| %s | %d | %.1f | %.1f%% | %.1f |\n" % (k, n, t, 100 * t / tot, t / n))
+
+
+def full(path, out):
+    raw = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(raw.splitlines()))
+    h, units, data = rows[0], rows[1], rows[2:]
+    ki = h.index("Kernel Name")
+    with open(out, "w") as f:
+        f.write("# ncu --set full summary of %s (one column per captured launch)\n\n" % path)
+        f.write("| metric | unit | " + " | ".join(short(r[ki]) for r in data) + " |\n")
+        f.write("|---|---|" + "---:|" * len(data) + "\n")
+        for k in KEYS:
+            if k in h:
+                i = h.index(k)
+                f.write("| %s | %s | " % (k, units[i]) + " | ".join(r[i] for r in data) + " |\n")
+
+
+if __name__ == "__main__":
+    {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2], sys.argv[3])
