@@ -95,3 +95,26 @@ def test_generated_tables_are_current():
             for pa, pb in zip(a["paths"], b["paths"]):
                 assert [q[:3] for q in pa["nz"]] == [q[:3] for q in pb["nz"]]
                 np.testing.assert_allclose([q[3] for q in pa["nz"]], [q[3] for q in pb["nz"]], atol=1e-12)
+
+
+def test_cpp_pair_style_error_paths_cpu(ensure_built):
+    """the C++ pair style (src/pair_allegro_b200.cpp) under the lmpshim harness: LAMMPS-style
+    errors surface as exceptions with the reference's messages; without a GPU coeff() fails loudly"""
+    import torch
+    from helpers import load_golden
+    from lmpshim import driver
+    if not os.path.exists(driver.OURS_LIB):
+        import __graft_entry__ as g
+        g.build()
+    atom, lst, z = load_golden("Cu_r5")
+    lmp = driver.ShimLammps(driver.OURS_LIB, atom, lst)
+    with pytest.raises(driver.ShimError, match="too many arguments"):
+        lmp.pair_style(["x"])
+    with pytest.raises(driver.ShimError, match="Incorrect args for pair coefficients"):
+        lmp.pair_coeff(["*", "*", alg_path("Cu_r5")])
+    with pytest.raises(driver.ShimError, match="Only accepts model paths"):
+        lmp.pair_coeff(["*", "*", "model.pt", "Cu"])
+    if not torch.cuda.is_available():
+        with pytest.raises(driver.ShimError, match="no CPU fallback"):
+            lmp.pair_coeff(["*", "*", alg_path("Cu_r5"), "Cu"])
+    assert lmp.flags()["restartinfo"] == 0 and lmp.flags()["manybody_flag"] == 1
