@@ -1,0 +1,182 @@
+// Debug / unit-test entry points of the C-ABI library (not part of the force path).
+//   alg_debug_umma_gemm : C[128][N] = A^T W on the tcgen05 tensor cores (kind::tf32, 1 or 3
+//   passes), operands staged exactly the way the pipeline kernels stage them (umma.cuh).
+#include <cstdio>
+#include <vector>
+
+#include "../../include/allegro_b200.h"
+#include <cuda_bf16.h>
+
+#include "umma.cuh"
+
+extern "C" ALG_API int alg_debug_umma_gemm2(const float* A, const float* W, float* C, int K, int N, int passes, int variant, float* dump128);
+
+namespace {
+using umma::opk_idx;
+using umma::make_desc_k_sw128;
+__global__ void __launch_bounds__(256, 1) k_umma_test(const float* __restrict__ A, const float* __restrict__ W, float* __restrict__ C,
+                                                      int K, int N, int passes, int variant, float* __restrict__ dump) {
+  extern __shared__ __align__(1024) float sm_raw[];
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_base_s;
+  const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+  float* sm = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(sm_raw) + 1023) & ~uintptr_t(1023));
+  float* A_hi = sm;
+  float* A_lo = A_hi + 128 * K;
+  float* W_hi = A_lo + 128 * K;
+  float* W_lo = W_hi + N * K;
+  const bool kmajor = true;
+  const bool bf16ns = variant & 2;
+  if (variant & 4) {   // TMEM store/load round trip only
+    if (warp == 0) umma::tmem_alloc(&tmem_base_s, 128);
+    umma::fence_before_sync();
+    __syncthreads();
+    umma::fence_after_sync();
+    const uint32_t tm = tmem_base_s;
+    const int q = warp & 3, half = warp >> 2;
+    const int m = q * 32 + lane;
+    for (int c0 = half * 64; c0 < (half + 1) * 64; c0 += 16) {
+      uint32_t r[16];
+      for (int i = 0; i < 16; ++i) r[i] = __float_as_uint((float)(m * 1000 + c0 + i));
+      asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%16], {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15};"
+                   ::"r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+                     "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(tm + ((uint32_t)(q * 32) << 16) + (uint32_t)c0) : "memory");
+    }
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    umma::fence_before_sync();
+    __syncthreads();
+    umma::fence_after_sync();
+    for (int c0 = half * 64; c0 < (half + 1) * 64; c0 += 16) {
+      float v[16];
+      umma::tmem_ld16(tm + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+      for (int i = 0; i < 16; ++i) dump[(size_t)m * 128 + c0 + i] = v[i];
+    }
+    umma::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) umma::tmem_dealloc(tm, 128);
+    return;
+  }
+  if (bf16ns) {
+    // bf16, K-major, no swizzle: core matrix = 8 rows x 16 B; LBO (K dir) = 128 B, SBO (row-group dir) = K/8*128 B
+    __nv_bfloat16* Ab = reinterpret_cast<__nv_bfloat16*>(A_hi);
+    __nv_bfloat16* Wb = reinterpret_cast<__nv_bfloat16*>(W_hi);
+    for (int i = t; i < 128 * K; i += 256) {
+      const int k = i / 128, m = i % 128;
+      Ab[(m / 8) * (K * 8) + (k / 8) * 64 + (m % 8) * 8 + (k % 8)] = __float2bfloat16(A[i]);
+    }
+    for (int i = t; i < N * K; i += 256) {
+      const int k = i / N, n = i % N;
+      Wb[(n / 8) * (K * 8) + (k / 8) * 64 + (n % 8) * 8 + (k % 8)] = __float2bfloat16(W[i]);
+    }
+  } else
+  for (int i = t; i < 128 * K; i += 256) {
+    const int k = i / 128, m = i % 128;
+    const float a = A[i];
+    const int o = opk_idx(m, k, 128);
+    A_hi[o] = a;
+    A_lo[o] = umma::tf32_lo(a);
+  }
+  if (!bf16ns)
+  for (int i = t; i < N * K; i += 256) {
+    const int k = i / N, n = i % N;
+    const float w = W[i];
+    const int o = opk_idx(n, k, N);
+    W_hi[o] = w;
+    W_lo[o] = umma::tf32_lo(w);
+  }
+  if (warp == 0) umma::tmem_alloc(&tmem_base_s, 128);
+  if (t == 0) umma::mbar_init(&bar, 1);
+  umma::fence_async_smem();
+  umma::fence_before_sync();
+  __syncthreads();
+  umma::fence_after_sync();
+  const uint32_t tmem = tmem_base_s;
+  if (t == 0 && (variant & 8)) printf("smem_raw %x sm %x A_hi %x W_hi %x tmem %x bar %x\n", umma::smem_u32(sm_raw), umma::smem_u32(sm), umma::smem_u32(A_hi), umma::smem_u32(W_hi), tmem, umma::smem_u32(&bar));
+  if (t == 0 && bf16ns) {
+    // kind::f16: A=B=BF16 (format 1), D=F32, K-major both, M=128
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((128u >> 4) << 24);
+    uint32_t acc = 0;
+    for (int ks = 0; ks < K / 16; ++ks) {
+      auto mk = [&](const void* p) {
+        uint64_t d = 0;
+        d |= (uint64_t)((umma::smem_u32(p) >> 4) & 0x3FFF);
+        d |= (uint64_t)((128u >> 4) & 0x3FFF) << 16;                       // LBO: next core matrix along K
+        d |= (uint64_t)((((uint32_t)K / 8u * 128u) >> 4) & 0x3FFF) << 32;   // SBO: next 8-row group
+        d |= (uint64_t)1 << 46;
+        return d;
+      };
+      const uint64_t da = mk(reinterpret_cast<const char*>(A_hi) + ks * 256);
+      const uint64_t db = mk(reinterpret_cast<const char*>(W_hi) + ks * 256);
+      asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                   ::"r"(tmem), "l"(da), "l"(db), "r"(idesc), "r"(acc) : "memory");
+      acc = 1;
+    }
+    umma::mma_commit(&bar);
+  } else
+  if (t == 0) {
+    uint32_t idesc = umma::make_idesc_tf32(N);
+    uint32_t acc = 0;
+    for (int p = 0; p < passes; ++p) {
+      const float* Ap = (passes == 3 && p == 0) ? A_lo : A_hi;
+      const float* Wp = (passes == 3 && p == 1) ? W_lo : W_hi;
+      for (int kg = 0; kg < K / 8; ++kg) {
+        uint64_t da, db;
+        da = make_desc_k_sw128(Ap + (kg >> 2) * (128 * 32) + (kg & 3) * 8);
+        db = make_desc_k_sw128(Wp + (kg >> 2) * (N * 32) + (kg & 3) * 8);
+        umma::mma_tf32(tmem, da, db, idesc, acc);
+        acc = 1;
+      }
+    }
+    umma::mma_commit(&bar);
+  }
+  umma::mbar_wait(&bar, 0);
+  umma::fence_after_sync();
+  {
+    const int q = warp & 3, half = warp >> 2;
+    const int m = q * 32 + lane;
+    for (int c0 = half * (N / 2); c0 < (half + 1) * (N / 2); c0 += 16) {
+      float v[16];
+      umma::tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+      for (int i = 0; i < 16; ++i) C[(size_t)m * N + c0 + i] = v[i];
+    }
+    if (dump) {   // all 128 allocated columns of every lane
+      for (int c0 = half * 64; c0 < (half + 1) * 64; c0 += 16) {
+        float v[16];
+        umma::tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+        for (int i = 0; i < 16; ++i) dump[(size_t)m * 128 + c0 + i] = v[i];
+      }
+    }
+  }
+  umma::fence_before_sync();
+  __syncthreads();
+  if (warp == 0) umma::tmem_dealloc(tmem, 128);
+}
+}  // namespace
+
+extern "C" ALG_API int alg_debug_umma_gemm(const float* A, const float* W, float* C, int K, int N, int passes) {
+  return alg_debug_umma_gemm2(A, W, C, K, N, passes, 0, nullptr);
+}
+
+extern "C" ALG_API int alg_debug_umma_gemm2(const float* A, const float* W, float* C, int K, int N, int passes, int variant, float* dump128) {
+  if (!A || !W || !C || K % 32 || N % 32 || N > 128 || K < 32 || (passes != 1 && passes != 3)) return ALG_EINVAL;
+  if (K % 32) return ALG_EINVAL;
+  if ((variant & 2) && K % 16) return ALG_EINVAL;
+  const size_t smem = sizeof(float) * 2 * (size_t)(128 + N) * K + 2048;
+  if (smem > 227 * 1024) return ALG_EINVAL;
+  float *dA, *dW, *dC;
+  if (cudaMalloc(&dA, sizeof(float) * 128 * K) != cudaSuccess) return ALG_ECUDA;
+  cudaMalloc(&dW, sizeof(float) * N * K);
+  cudaMalloc(&dC, sizeof(float) * 128 * N);
+  cudaMemcpy(dA, A, sizeof(float) * 128 * K, cudaMemcpyHostToDevice);
+  cudaMemcpy(dW, W, sizeof(float) * N * K, cudaMemcpyHostToDevice);
+  cudaFuncSetAttribute(k_umma_test, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  float* dD = nullptr;
+  if (dump128) { cudaMalloc(&dD, sizeof(float) * 128 * 128); cudaMemset(dD, 0, sizeof(float) * 128 * 128); }
+  k_umma_test<<<1, 256, smem>>>(dA, dW, dC, K, N, passes, variant, dD);
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e == cudaSuccess) cudaMemcpy(C, dC, sizeof(float) * 128 * N, cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess && dump128) cudaMemcpy(dump128, dD, sizeof(float) * 128 * 128, cudaMemcpyDeviceToHost);
+  cudaFree(dA); cudaFree(dW); cudaFree(dC); if (dD) cudaFree(dD);
+  if (e != cudaSuccess) { fprintf(stderr, "alg_debug_umma_gemm: %s\n", cudaGetErrorString(e)); return ALG_ECUDA; }
+  return ALG_OK;
+}
