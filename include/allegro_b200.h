@@ -79,7 +79,10 @@ ALG_API int alg_set_type_map(alg_handle* h, int ntypes, const int* lammps_type_t
  *   "chunk_edges"  edges processed per pipeline pass (activation buffers are sized by this)
  *   "keep_edges"   "1": materialise the int64 [2,E] edge_index for alg_get_edges
  *   "debug"        "1": keep per-edge gradients / intermediates for alg_get_output
- *   "profile"      "1": time every pipeline kernel with CUDA events (alg_get_stats) */
+ *   "profile"      "1": time every pipeline kernel with CUDA events (alg_get_stats)
+ *   "gemm"         "tc": dense contractions on the tcgen05 tensor cores (l_max = 1) | "ffma": FP32 pipe
+ *   "precision"    "strict": fp32-level accuracy (3xTF32 split on the tensor cores) | "tf32": one
+ *                  TF32 pass (fast mode, ~1e-3 relative accuracy; tensor-core path only) */
 ALG_API int alg_set_option(alg_handle* h, const char* key, const char* value);
 
 /* Host-pointer force evaluation: replaces the body of PairNequIPAllegro<false>::compute()

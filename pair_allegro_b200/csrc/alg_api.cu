@@ -27,6 +27,7 @@ const Pipeline* get_pipeline(int L) {
   }
   return nullptr;
 }
+const Pipeline* get_pipeline_tc(int L) { return L == 1 ? get_pipeline_tc_L1() : nullptr; }
 }  // namespace alg
 
 using namespace alg;
@@ -88,10 +89,14 @@ struct alg_handle {
   std::vector<double> cut_table;      // T*T (model types)
   std::vector<double> scales, shifts;
   int allow_tf32 = 0;
-  DevBuf weights;
+  DevBuf weights, tc_weights;
   ModelW mw{};
-  const Pipeline* pipe = nullptr;
+  TcW tcw{};
+  const Pipeline* pipe = nullptr;        // active pipeline
   PipelineInfo pinfo{};
+  const Pipeline* pipe_ffma = nullptr;
+  const Pipeline* pipe_tc = nullptr;
+  bool use_tc = false;
   // type map
   int ntypes = 0;
   DevBuf d_tmap, d_cutsq, d_scale, d_shift;
@@ -430,7 +435,70 @@ static int setup_model(alg_handle* h) {
   CK(h->d_shift.ensure(sizeof(double) * MAXT));
   CK(cudaMemcpy(h->d_scale.p, h->scales.data(), sizeof(double) * T, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(h->d_shift.p, h->shifts.data(), sizeof(double) * T, cudaMemcpyHostToDevice));
+  h->pipe_ffma = h->pipe;
   CK(h->pipe->init());
+  // ---- tensor-core path: pre-swizzled K-major hi/lo weight images (umma.cuh), one per GEMM
+  h->pipe_tc = get_pipeline_tc(h->L);
+  if (h->pipe_tc) {
+    struct Img { TcMat* dst; int N, K; std::vector<float> hi, lo; size_t off; };
+    std::vector<Img> imgs;
+    auto T_ = [&](const std::string& name) { return reinterpret_cast<const float*>(h->tensors.at(name).data.data()); };
+    auto make = [&](TcMat* dst, int N, int K, auto&& f /*(n,k)->float*/) {
+      Img im; im.dst = dst; im.N = N; im.K = K; im.hi.assign((size_t)N * K, 0.f); im.lo.assign((size_t)N * K, 0.f);
+      for (int n = 0; n < N; ++n)
+        for (int k = 0; k < K; ++k) {
+          const float v = f(n, k);
+          const float vh = umma::tf32_hi(v);
+          const int o = umma::opk_idx(n, k, N);
+          im.hi[o] = vh; im.lo[o] = v - vh;
+        }
+      imgs.push_back(std::move(im));
+    };
+    const float* t0 = T_("twobody.w0"); const float* t1 = T_("twobody.w1"); const float* t2 = T_("twobody.w2");
+    const float* emb = T_("embed_linear"); const float* r0 = T_("readout.w0");
+    const float* env0 = T_("layer0.env_linear");
+    TcW& tw = h->tcw;
+    make(&tw.two0, H, 32, [&](int n, int k) { return k < B ? t0[(size_t)(2 * T + k) * H + n] : 0.f; });
+    make(&tw.two1, H, H, [&](int n, int k) { return t1[(size_t)k * H + n]; });
+    make(&tw.two2, S, H, [&](int n, int k) { return t2[(size_t)k * S + n]; });
+    make(&tw.embenv, 2 * ENVW, S, [&](int n, int k) { return n < ENVW ? emb[(size_t)k * ENVW + n] : env0[(size_t)k * ENVW + n - ENVW]; });
+    make(&tw.two2_b, H, S, [&](int n, int k) { return t2[(size_t)n * S + k]; });
+    make(&tw.two1_b, H, H, [&](int n, int k) { return t1[(size_t)n * H + k]; });
+    make(&tw.two0_b, 32, H, [&](int n, int k) { return n < B ? t0[(size_t)(2 * T + n) * H + k] : 0.f; });
+    make(&tw.envemb_b, S, 2 * ENVW, [&](int n, int k) { return k < ENVW ? env0[(size_t)n * ENVW + k] : emb[(size_t)n * ENVW + k - ENVW]; });
+    make(&tw.ro0, R, S, [&](int n, int k) { return r0[(size_t)k * R + n]; });
+    make(&tw.ro0_b, S, R, [&](int n, int k) { return r0[(size_t)n * R + k]; });
+    for (int kk = 0; kk < h->nl; ++kk) {
+      const std::string pre = "layer" + std::to_string(kk) + ".";
+      const float* m0 = T_(pre + "mlp.w0"); const float* m1 = T_(pre + "mlp.w1"); const float* m2 = T_(pre + "mlp.w2");
+      const float* env = T_(pre + "env_linear");
+      TcLayerW& tl = tw.layer[kk];
+      make(&tl.m0, H, SIN, [&](int n, int k) { return m0[(size_t)k * H + n]; });
+      make(&tl.m1, H, H, [&](int n, int k) { return m1[(size_t)k * H + n]; });
+      make(&tl.m2, S, H, [&](int n, int k) { return m2[(size_t)k * S + n]; });
+      make(&tl.env, ENVW, S, [&](int n, int k) { return env[(size_t)k * ENVW + n]; });
+      make(&tl.m2_b, H, S, [&](int n, int k) { return m2[(size_t)n * S + k]; });
+      make(&tl.m1_b, H, H, [&](int n, int k) { return m1[(size_t)n * H + k]; });
+      make(&tl.m0_b, SIN, H, [&](int n, int k) { return m0[(size_t)n * H + k]; });
+      make(&tl.env_b, S, ENVW, [&](int n, int k) { return env[(size_t)n * ENVW + k]; });
+    }
+    size_t tot = 0;
+    for (Img& im : imgs) { im.off = tot; tot += 2 * (((size_t)im.N * im.K + 255) / 256 * 256); }
+    std::vector<float> tb(tot, 0.f);
+    for (Img& im : imgs) {
+      memcpy(tb.data() + im.off, im.hi.data(), sizeof(float) * im.hi.size());
+      memcpy(tb.data() + im.off + ((size_t)im.N * im.K + 255) / 256 * 256, im.lo.data(), sizeof(float) * im.lo.size());
+    }
+    CK(h->tc_weights.ensure(tot * sizeof(float)));
+    CK(cudaMemcpy(h->tc_weights.p, tb.data(), tot * sizeof(float), cudaMemcpyHostToDevice));
+    for (Img& im : imgs) {
+      im.dst->hi = h->tc_weights.as<float>() + im.off;
+      im.dst->lo = im.dst->hi + ((size_t)im.N * im.K + 255) / 256 * 256;
+      im.dst->N = im.N; im.dst->K = im.K;
+    }
+    tw.passes = 3;
+    CK(h->pipe_tc->init());
+  }
   h->tensors.clear();
   return ALG_OK;
 }
@@ -474,7 +542,7 @@ extern "C" void alg_destroy(alg_handle* h) {
   DevBuf* bufs[] = {&h->weights, &h->d_tmap, &h->d_cutsq, &h->d_scale, &h->d_shift, &h->d_x, &h->d_type, &h->d_ilist, &h->d_numneigh,
                     &h->d_cand, &h->d_first, &h->d_cnt, &h->d_rowptr, &h->d_scan_tmp, &h->d_mtype, &h->d_edge_j, &h->d_edge_c, &h->d_rvec,
                     &h->d_esum, &h->d_facc, &h->d_vacc, &h->d_forces, &h->d_eall, &h->d_red, &h->d_edge_index, &h->d_edge_energy,
-                    &h->d_edge_grad, &h->d_eatom_out, &h->c_W0, &h->c_dX, &h->c_dY, &h->c_du, &h->c_carry, &h->c_ecarry,
+                    &h->d_edge_grad, &h->d_eatom_out, &h->tc_weights, &h->c_W0, &h->c_dX, &h->c_dY, &h->c_du, &h->c_carry, &h->c_ecarry,
                     &h->c_X[0], &h->c_X[1], &h->c_X[2], &h->c_V[0], &h->c_V[1], &h->c_V[2], &h->c_dV[0], &h->c_dV[1],
                     &h->c_gamma[0], &h->c_gamma[1], &h->c_gamma[2], &h->c_dgamma[0], &h->c_dgamma[1], &h->c_dgamma[2]};
   for (DevBuf* b : bufs) b->release();
@@ -524,6 +592,16 @@ extern "C" int alg_set_option(alg_handle* h, const char* key, const char* value)
   } else if (k == "keep_edges") h->keep_edges = v == "1";
   else if (k == "debug") h->debug = v == "1";
   else if (k == "profile") h->prof.on = v == "1";
+  else if (k == "gemm") {
+    if (v == "ffma") { h->use_tc = false; h->pipe = h->pipe_ffma; }
+    else if (v == "tc") {
+      if (!h->pipe_tc) return fail(h, ALG_EINVAL, "gemm=tc: the tensor-core pipeline of this build supports l_max = 1 only");
+      h->use_tc = true; h->pipe = h->pipe_tc;
+    } else return fail(h, ALG_EINVAL, "gemm must be ffma or tc");
+    h->pinfo = h->pipe->info(h->nl);
+  } else if (k == "precision") {
+    if (v == "strict") h->tcw.passes = 3; else if (v == "tf32") h->tcw.passes = 1; else return fail(h, ALG_EINVAL, "precision must be strict or tf32");
+  }
   else return fail(h, ALG_ENOTFOUND, "unknown option " + k);
   return ALG_OK;
 }
@@ -652,7 +730,7 @@ static int run_step(alg_handle* h, int nlocal, int nghost, const double* d_x, co
     a.e0 = c.e0; a.e1 = c.e1; a.c0 = c.c0;
     const int ntiles = (c.e1 - c.e0 + TM - 1) / TM;
     tiles_total += ntiles;
-    CK(h->pipe->run_chunk(a, h->mw, ntiles, st, &h->prof));
+    CK(h->pipe->run_chunk(a, h->mw, &h->tcw, ntiles, st, &h->prof));
   }
   // own kernels outside the chunk pipeline: k_mtype, k_edges x2, [k_edge_index], 4 finalize kernels
   h->step_stats[0] = (double)h->prof.launches + 3 + (h->keep_edges && E > 0 ? 1 : 0) + 4;

@@ -73,7 +73,7 @@ __global__ void __launch_bounds__(256, 1) k_umma_test(const float* __restrict__ 
     const int k = i / 128, m = i % 128;
     const float a = A[i];
     const int o = opk_idx(m, k, 128);
-    A_hi[o] = a;
+    A_hi[o] = umma::tf32_hi(a);
     A_lo[o] = umma::tf32_lo(a);
   }
   if (!bf16ns)
@@ -81,7 +81,7 @@ __global__ void __launch_bounds__(256, 1) k_umma_test(const float* __restrict__ 
     const int k = i / N, n = i % N;
     const float w = W[i];
     const int o = opk_idx(n, k, N);
-    W_hi[o] = w;
+    W_hi[o] = umma::tf32_hi(w);
     W_lo[o] = umma::tf32_lo(w);
   }
   if (warp == 0) umma::tmem_alloc(&tmem_base_s, 128);

@@ -4,6 +4,7 @@
 #include <vector>
 
 #include "allegro_kernels.cuh"
+#include "allegro_kernels_tc.cuh"
 
 namespace alg {
 
@@ -40,7 +41,7 @@ struct Prof {
 struct Pipeline {
   PipelineInfo (*info)(int nl);
   cudaError_t (*init)();                                                       // opt-in shared memory
-  cudaError_t (*run_chunk)(const ChunkArgs& a, const ModelW& w, int ntiles, cudaStream_t st, Prof* prof);
+  cudaError_t (*run_chunk)(const ChunkArgs& a, const ModelW& w, const TcW* tw, int ntiles, cudaStream_t st, Prof* prof);
 };
 
 const Pipeline* get_pipeline(int L);
@@ -77,7 +78,7 @@ template <int L> cudaError_t init_impl() {
   return cudaSuccess;
 }
 
-template <int L> cudaError_t run_chunk_impl(const ChunkArgs& a, const ModelW& w, int ntiles, cudaStream_t st, Prof* pf) {
+template <int L> cudaError_t run_chunk_impl(const ChunkArgs& a, const ModelW& w, const TcW*, int ntiles, cudaStream_t st, Prof* pf) {
   using D = Dims<L>;
   constexpr int TM = D::TM;
   const size_t sm = Smem<L>::BYTES;
@@ -118,6 +119,78 @@ template <int L> cudaError_t run_chunk_impl(const ChunkArgs& a, const ModelW& w,
   return cudaGetLastError();
 }
 
+// ---- tensor-core pipeline (l_max = 1) ------------------------------------------------------
+template <int L> PipelineInfo info_tc_impl(int nl) {
+  PipelineInfo p = info_impl<L>(nl);
+  p.TM = DimsTC<L>::TM;
+  p.smem_bytes = SmemTC<L>::BYTES;
+  return p;
+}
+template <int L> cudaError_t init_tc_impl() {
+  const int b = (int)SmemTC<L>::BYTES;
+  cudaError_t e;
+#define ALG_SET(kern) \
+  if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, b)) != cudaSuccess) return e;
+  ALG_SET((k_f0_tc<L>));
+  ALG_SET((k_fk_tc<L, 'B', true>));
+  ALG_SET((k_fk_tc<L, 'C', true>));
+  ALG_SET((k_fk_tc<L, 'D', false>));
+  ALG_SET((k_t_tc<L, true>));
+  ALG_SET((k_t_tc<L, false>));
+  ALG_SET((k_bk_tc<L, 'B', true>));
+  ALG_SET((k_bk_tc<L, 'C', true>));
+  ALG_SET((k_bk_tc<L, 'D', false>));
+  ALG_SET((k_b0_tc<L>));
+#undef ALG_SET
+  return cudaSuccess;
+}
+template <int L> cudaError_t run_chunk_tc_impl(const ChunkArgs& a, const ModelW& w, const TcW* twp, int ntiles, cudaStream_t st, Prof* pf) {
+  using D = DimsTC<L>;
+  constexpr int TM = D::TM;
+  const size_t sm = SmemTC<L>::BYTES;
+  const dim3 g(ntiles), b(NT);
+  const TcW& tw = *twp;
+#define ALG_RUN(kid, ...) do { pf->begin(kid, st); __VA_ARGS__; pf->end(st); } while (0)
+  auto fix = [&](float* out) {
+    ALG_RUN(KID_FIXUP, (k_fixup<TM><<<g, 128, 0, st>>>(a.edge_c, a.rowptr, a.e0, a.e1, a.c0, ntiles, D::F, out, a.carry)));
+  };
+  ALG_RUN(KID_F0, (k_f0_tc<L><<<g, b, sm, st>>>(a, w, tw)));
+  fix(a.gamma[0]);
+  const int nl = w.nl;
+  if (nl == 1) {
+    ALG_RUN(KID_T, (k_t_tc<L, true><<<g, b, sm, st>>>(a, w, tw, 0)));
+  } else if (nl == 2) {
+    ALG_RUN(KID_FK, (k_fk_tc<L, 'B', true><<<g, b, sm, st>>>(a, w, tw, 0)));
+    fix(a.gamma[1]);
+    ALG_RUN(KID_T, (k_t_tc<L, false><<<g, b, sm, st>>>(a, w, tw, 1)));
+  } else {
+    ALG_RUN(KID_FK, (k_fk_tc<L, 'C', true><<<g, b, sm, st>>>(a, w, tw, 0)));
+    fix(a.gamma[1]);
+    ALG_RUN(KID_FK, (k_fk_tc<L, 'D', false><<<g, b, sm, st>>>(a, w, tw, 1)));
+    fix(a.gamma[2]);
+    ALG_RUN(KID_T, (k_t_tc<L, false><<<g, b, sm, st>>>(a, w, tw, 2)));
+  }
+  fix(a.dgamma[nl - 1]);
+  ALG_RUN(KID_FIXUP, (k_fixup_e<TM><<<(ntiles + 127) / 128, 128, 0, st>>>(a.edge_c, a.rowptr, a.e0, a.e1, ntiles, a.esum, a.ecarry)));
+  if (nl == 2) {
+    ALG_RUN(KID_BK, (k_bk_tc<L, 'B', true><<<g, b, sm, st>>>(a, w, tw, 0)));
+    fix(a.dgamma[0]);
+  } else if (nl == 3) {
+    ALG_RUN(KID_BK, (k_bk_tc<L, 'D', false><<<g, b, sm, st>>>(a, w, tw, 1)));
+    fix(a.dgamma[1]);
+    ALG_RUN(KID_BK, (k_bk_tc<L, 'C', true><<<g, b, sm, st>>>(a, w, tw, 0)));
+    fix(a.dgamma[0]);
+  }
+  ALG_RUN(KID_B0, (k_b0_tc<L><<<g, b, sm, st>>>(a, w, tw)));
+#undef ALG_RUN
+  return cudaGetLastError();
+}
+#define ALG_DEFINE_PIPELINE_TC(L)                                                                  \
+  const Pipeline* get_pipeline_tc_L##L() {                                                         \
+    static const Pipeline p = {&info_tc_impl<L>, &init_tc_impl<L>, &run_chunk_tc_impl<L>};         \
+    return &p;                                                                                     \
+  }
+
 #define ALG_DEFINE_PIPELINE(L)                                                             \
   const Pipeline* get_pipeline_L##L() {                                                    \
     static const Pipeline p = {&info_impl<L>, &init_impl<L>, &run_chunk_impl<L>};          \
@@ -128,5 +201,6 @@ template <int L> cudaError_t run_chunk_impl(const ChunkArgs& a, const ModelW& w,
 const Pipeline* get_pipeline_L1();
 const Pipeline* get_pipeline_L2();
 const Pipeline* get_pipeline_L3();
+const Pipeline* get_pipeline_tc_L1();
 
 }  // namespace alg

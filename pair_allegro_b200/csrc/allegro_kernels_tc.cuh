@@ -1,0 +1,926 @@
+// Tensor-core (tcgen05) variant of the five fused edge-tile kernels, l_max = 1.
+//
+// Same staging and the same HBM buffers as allegro_kernels.cuh (F0 / FK / T / BK / B0, kernel
+// boundaries at the per-centre environment sums), but every dense contraction runs on the
+// 5th-generation tensor cores:
+//   * tile = 128 edges = the M dimension of one tcgen05.mma (cta_group::1), 256 threads;
+//     thread (m = t%128, half = t/128) owns edge row m and one half of the output columns in
+//     every epilogue (TMEM lane m is readable by warps w with w%4 == m/32);
+//   * A operands (activations) are written by their producer thread straight into the K-major
+//     SWIZZLE_128B shared-memory layout of umma.cuh, B operands (weights) are pre-swizzled on
+//     the host and fetched by one TMA bulk copy (cp.async.bulk) per GEMM, overlapped with the
+//     previous epilogue;
+//   * accumulators live in TMEM; in the backward kernels the pre-activations z1, z2 and the
+//     pre-envelope MLP output m STAY in TMEM between the forward recompute and the backward
+//     GEMMs (no shared-memory copies, act'(z) re-evaluated from TMEM);
+//   * strict mode = 3xTF32 (a = hi + lo split of both operands, lo*hi + hi*lo + hi*hi
+//     accumulated in fp32): error ~5e-7, i.e. fp32-level (tests/test_gpu_umma.py);
+//     fast mode = single TF32 pass.
+#pragma once
+#include "alg_common.cuh"
+#include "tp_gen.cuh"
+#include "umma.cuh"
+
+namespace alg {
+
+struct TcMat { const float* hi; const float* lo; int N, K; };   // smem image: K/32 panels x N rows x 32 floats
+struct TcLayerW { TcMat m0, m1, m2, env, m2_b, m1_b, m0_b, env_b; };
+struct TcW {
+  TcMat two0, two1, two2, embenv, two2_b, two1_b, two0_b, envemb_b, ro0, ro0_b;
+  TcLayerW layer[3];
+  int passes;     // 3 = strict (3xTF32), 1 = fast (TF32)
+};
+
+template <int L> struct DimsTC {
+  static constexpr int TM = 128;
+  static constexpr int NSH = (L + 1) * (L + 1);
+  static constexpr int NL = L + 1;
+  static constexpr int ENVW = NL * U;
+  static constexpr int SIN = S + NL * U;
+  static constexpr int F = NSH * U;
+  static constexpr int CPH = NT / TM;      // 2
+  static constexpr int CPT = U / CPH;      // 16
+  static constexpr int WS = ENVW + 1;
+  static constexpr int CHU = (L == 1) ? 32 : 16;
+  static constexpr int FC = NSH * CHU;
+  static constexpr int DGS = FC + 1;
+};
+
+template <int L> struct SmemTC {
+  using D = DimsTC<L>;
+  static constexpr int TM = 128;
+  static constexpr int OPF = TM * 128;                 // operand capacity: K <= 128
+  static constexpr int WBF = 8192;                     // weight image capacity: N*K <= 8192
+  static constexpr int oOPH = 0;
+  static constexpr int oOPL = oOPH + OPF;
+  static constexpr int oWBH = oOPL + OPF;
+  static constexpr int oWBL = oWBH + WBF;
+  static constexpr int oY = oWBL + WBF;
+  static constexpr int oDY = oY + D::NSH * TM;
+  static constexpr int oU = oDY + D::NSH * TM;
+  static constexpr int oC = oU + TM;                   // int
+  static constexpr int oZZ = oC + TM;                  // int
+  static constexpr int oE = oZZ + TM;                  // 4*TM floats: per-half partials, E_e, du partial
+  static constexpr int oBAR = oE + 4 * TM;             // 2 mbarriers + tmem pointer (8 floats)
+  static constexpr int TOTAL = oBAR + 8;
+  static constexpr size_t BYTES = (size_t)TOTAL * sizeof(float) + 1024;   // + alignment slack
+  static_assert(L == 1, "tensor-core pipeline: shared-memory plan is sized for l_max = 1");
+  static_assert(D::SIN <= 128 && 2 * D::ENVW <= 128, "operand K capacity");
+  static_assert(D::WS * TM <= OPF && D::DGS * TM <= 2 * OPF, "staging buffers alias the operand regions");
+};
+
+struct TcCtx {
+  float* sm;
+  uint32_t tmem;
+  uint64_t* mbar;
+  uint64_t* wbar;
+  uint32_t mph, wph;
+  int passes;
+  int m, half, q;
+};
+
+template <int L> __device__ __forceinline__ TcCtx tc_begin(float* sm_raw, const TcW& tw) {
+  using SM = SmemTC<L>;
+  TcCtx c;
+  c.sm = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(sm_raw) + 1023) & ~uintptr_t(1023));
+  c.mbar = reinterpret_cast<uint64_t*>(c.sm + SM::oBAR);
+  c.wbar = c.mbar + 1;
+  uint32_t* tptr = reinterpret_cast<uint32_t*>(c.mbar + 2);
+  const int t = threadIdx.x;
+  if ((t >> 5) == 0) umma::tmem_alloc(tptr, 512);
+  if (t == 0) { umma::mbar_init(c.mbar, 1); umma::mbar_init(c.wbar, 1); }
+  umma::fence_async_smem();
+  umma::fence_before_sync();
+  __syncthreads();
+  umma::fence_after_sync();
+  c.tmem = *tptr;
+  c.mph = c.wph = 0;
+  c.passes = tw.passes;
+  c.m = t & 127; c.half = t >> 7; c.q = (t >> 5) & 3;
+  return c;
+}
+__device__ __forceinline__ void tc_end(TcCtx& c) {
+  umma::fence_before_sync();
+  __syncthreads();
+  if ((threadIdx.x >> 5) == 0) umma::tmem_dealloc(c.tmem, 512);
+}
+
+// thread 0: fetch the next GEMM's weight image(s) with TMA bulk copies (call after the previous MMA completed)
+template <int L> __device__ __forceinline__ void tc_load_w(TcCtx& c, const TcMat& w) {
+  using SM = SmemTC<L>;
+  if (threadIdx.x == 0) {
+    const uint32_t bytes = (uint32_t)(w.N * w.K) * 4u;
+    umma::mbar_expect_tx(c.wbar, c.passes == 3 ? 2 * bytes : bytes);
+    umma::bulk_g2s(c.sm + SM::oWBH, w.hi, bytes, c.wbar);
+    if (c.passes == 3) umma::bulk_g2s(c.sm + SM::oWBL, w.lo, bytes, c.wbar);
+  }
+}
+
+// all threads: operands are written -> thread 0 issues the MMAs -> everybody waits for completion
+template <int L> __device__ __forceinline__ void tc_mma(TcCtx& c, int K, int N, uint32_t dcol) {
+  using SM = SmemTC<L>;
+  umma::fence_async_smem();
+  umma::fence_before_sync();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    umma::fence_after_sync();
+    umma::mbar_wait(c.wbar, c.wph);
+    const float* Ah = c.sm + SM::oOPH; const float* Al = c.sm + SM::oOPL;
+    const float* Wh = c.sm + SM::oWBH; const float* Wl = c.sm + SM::oWBL;
+    const uint32_t idesc = umma::make_idesc_tf32(N);
+    uint32_t acc = 0;
+    for (int p = 0; p < c.passes; ++p) {
+      const float* Ap = (c.passes == 3 && p == 0) ? Al : Ah;       // lo*hi, hi*lo, hi*hi
+      const float* Wp = (c.passes == 3 && p == 1) ? Wl : Wh;
+      for (int ks = 0; ks < K / 8; ++ks) {
+        const uint64_t da = umma::make_desc_k_sw128(Ap + (ks >> 2) * (128 * 32) + (ks & 3) * 8);
+        const uint64_t db = umma::make_desc_k_sw128(Wp + (ks >> 2) * (N * 32) + (ks & 3) * 8);
+        umma::mma_tf32(c.tmem + dcol, da, db, idesc, acc);
+        acc = 1;
+      }
+    }
+    umma::mma_commit(c.mbar);
+  }
+  c.wph ^= 1;
+  umma::mbar_wait(c.mbar, c.mph);
+  c.mph ^= 1;
+  umma::fence_after_sync();
+}
+
+// this thread's row m, 16 columns starting at absolute TMEM column col
+__device__ __forceinline__ void tc_ld16(const TcCtx& c, uint32_t col, float* v) {
+  umma::tmem_ld16(c.tmem + ((uint32_t)(c.q * 32) << 16) + col, v);
+}
+// write 4 consecutive k (k4 % 4 == 0) of row m into the A operand (hi [+ lo])
+template <int L> __device__ __forceinline__ void op_put4(const TcCtx& c, int k4, float a, float b, float d, float e) {
+  using SM = SmemTC<L>;
+  const int o = umma::opk_idx(c.m, k4, 128);
+  const float ah = umma::tf32_hi(a), bh = umma::tf32_hi(b), dh = umma::tf32_hi(d), eh = umma::tf32_hi(e);
+  *reinterpret_cast<float4*>(c.sm + SM::oOPH + o) = make_float4(ah, bh, dh, eh);
+  if (c.passes == 3) *reinterpret_cast<float4*>(c.sm + SM::oOPL + o) = make_float4(a - ah, b - bh, d - dh, e - eh);
+}
+template <int L> __device__ __forceinline__ void op_put1(const TcCtx& c, int row, int k, float a) {
+  using SM = SmemTC<L>;
+  const int o = umma::opk_idx(row, k, 128);
+  const float ah = umma::tf32_hi(a);
+  c.sm[SM::oOPH + o] = ah;
+  if (c.passes == 3) c.sm[SM::oOPL + o] = a - ah;
+}
+// epilogue over this thread's half of NC columns: fn(n, v0..v3) for 4 consecutive columns n..n+3
+template <class Fn> __device__ __forceinline__ void tc_epi(const TcCtx& c, uint32_t dcol, int NC, Fn fn) {
+  const int w = NC / 2;
+  for (int c0 = c.half * w; c0 < (c.half + 1) * w; c0 += 16) {
+    float v[16];
+    tc_ld16(c, dcol + c0, v);
+#pragma unroll
+    for (int i = 0; i < 16; i += 4) fn(c0 + i, v[i], v[i + 1], v[i + 2], v[i + 3]);
+  }
+}
+// load a 64-row tile-SoA array (x^k, dX) of this tile into operand columns [0,64)
+template <int L> __device__ __forceinline__ void op_load_rows64(const TcCtx& c, const float* __restrict__ g /*tile base [64][128]*/) {
+  for (int n = c.half * 32; n < c.half * 32 + 32; n += 4)
+    op_put4<L>(c, n, g[(n + 0) * 128 + c.m], g[(n + 1) * 128 + c.m], g[(n + 2) * 128 + c.m], g[(n + 3) * 128 + c.m]);
+}
+
+// geometry of row m (both halves compute, half 0 publishes Y_s, u_s, c_s, zz_s)
+template <int L> __device__ __forceinline__ Geom tc_geom(const ChunkArgs& a, const ModelW& w, const TcCtx& c, int es, int nvalid) {
+  using D = DimsTC<L>; using SM = SmemTC<L>; constexpr int TM = 128;
+  const int e = es + min(c.m, nvalid - 1);
+  const float4 rv = a.rvec[e];
+  Geom g;
+  const int zz = __float_as_int(rv.w);
+  g.zi = zz & 255; g.zj = zz >> 8;
+  g.r = sqrtf(rv.x * rv.x + rv.y * rv.y + rv.z * rv.z);
+  g.x = rv.x / g.r; g.y = rv.y / g.r; g.z = rv.z / g.r;
+  g.rc = w.rc[g.zi * MAXT + g.zj];
+  float dudx;
+  poly_cutoff(g.r / g.rc, w.p, g.u, dudx);
+  g.dudr = dudx / g.rc;
+  if (c.half == 0) {
+    float Y[D::NSH];
+    sph_harm<L>(g.x, g.y, g.z, Y);
+#pragma unroll
+    for (int k = 0; k < D::NSH; ++k) c.sm[SM::oY + k * TM + c.m] = Y[k];
+    c.sm[SM::oU + c.m] = g.u;
+    reinterpret_cast<int*>(c.sm + SM::oC)[c.m] = a.edge_c[e];
+    reinterpret_cast<int*>(c.sm + SM::oZZ)[c.m] = zz;
+  }
+  return g;
+}
+
+// env-weight GEMM output (TMEM columns [dcol, dcol+ENVW)) -> W_s (edge-major, stride WS) in the OPL region
+template <int L> __device__ __forceinline__ void tc_env_to_ws(const TcCtx& c, uint32_t dcol) {
+  using D = DimsTC<L>; using SM = SmemTC<L>;
+  float* W_s = c.sm + SM::oOPL;
+  tc_epi(c, dcol, D::ENVW, [&](int n, float v0, float v1, float v2, float v3) {
+    float* p = W_s + c.m * D::WS + n;
+    p[0] = v0; p[1] = v1; p[2] = v2; p[3] = v3;
+  });
+}
+template <int L> __device__ __forceinline__ void tc_env_sum(const ChunkArgs& a, const ModelW& w, const TcCtx& c, int tile, int es, int nvalid,
+                                                             float* __restrict__ gamma) {
+  using D = DimsTC<L>; using SM = SmemTC<L>; constexpr int TM = 128;
+  const float* W_s = c.sm + SM::oOPL;
+  const float* Y_s = c.sm + SM::oY;
+  const int* c_s = reinterpret_cast<const int*>(c.sm + SM::oC);
+  segsum_tile<D::F>(c_s, nvalid, es, a.rowptr, w.inv_sqrt_n, gamma, a.c0, a.carry + (size_t)tile * D::F,
+                    [&](int e, int f) { const int lm = f / U, u = f % U; return W_s[e * D::WS + lsel(lm) * U + u] * Y_s[lm * TM + e]; });
+}
+
+template <int L, bool FIRST, int DIN>
+__device__ __forceinline__ void tc_load_vin(const ChunkArgs& a, int tile, int k, int e, int u, const float* Y_s, float* Vin) {
+  using D = DimsTC<L>; constexpr int TM = 128;
+  if (FIRST) {
+    const float* W0g = a.W0 + (size_t)tile * D::ENVW * TM;
+#pragma unroll
+    for (int l = 0; l <= L; ++l) {
+      const float wv = W0g[(l * U + u) * TM + e];
+#pragma unroll
+      for (int lm = l * l; lm < (l + 1) * (l + 1); ++lm) Vin[lm] = wv * Y_s[lm * TM + e];
+    }
+  } else {
+    const float* Vg = a.V[k] + ((size_t)tile * U + u) * DIN * TM;
+#pragma unroll
+    for (int cc = 0; cc < DIN; ++cc) Vin[cc] = Vg[cc * TM + e];
+  }
+}
+
+// ============================================================================================
+// F0
+// ============================================================================================
+template <int L>
+__global__ void __launch_bounds__(NT, 1) k_f0_tc(const __grid_constant__ ChunkArgs a, const __grid_constant__ ModelW w, const __grid_constant__ TcW tw) {
+  using D = DimsTC<L>; using SM = SmemTC<L>; constexpr int TM = 128;
+  extern __shared__ __align__(1024) float sm_raw[];
+  TcCtx c = tc_begin<L>(sm_raw, tw);
+  const int tile = blockIdx.x;
+  const int es = a.e0 + tile * TM;
+  const int nvalid = min(TM, a.e1 - es);
+  tc_load_w<L>(c, tw.two0);
+  const Geom g = tc_geom<L>(a, w, c, es, nvalid);
+  {  // Bessel*u -> operand columns [0,32) (zero padded beyond num_bessels)
+    const float pref = sqrtf(2.0f / g.rc);
+    const float xr = g.r / g.rc;
+    for (int k4 = c.half * 16; k4 < c.half * 16 + 16; k4 += 4) {
+      float b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int n = k4 + i;
+        b[i] = n < w.B ? pref * sinf((float)(n + 1) * (3.14159265358979323846f * xr)) / g.r * g.u : 0.f;
+      }
+      op_put4<L>(c, k4, b[0], b[1], b[2], b[3]);
+    }
+  }
+  tc_mma<L>(c, 32, 64, 0);
+  tc_load_w<L>(c, tw.two1);
+  {
+    const float* w0 = w.two.w[0];
+    const float* wi = w0 + g.zi * H; const float* wj = w0 + (w.T + g.zj) * H;
+    tc_epi(c, 0, 64, [&](int n, float v0, float v1, float v2, float v3) {
+      op_put4<L>(c, n, silu_act(v0 + __ldg(wi + n) + __ldg(wj + n)), silu_act(v1 + __ldg(wi + n + 1) + __ldg(wj + n + 1)),
+                 silu_act(v2 + __ldg(wi + n + 2) + __ldg(wj + n + 2)), silu_act(v3 + __ldg(wi + n + 3) + __ldg(wj + n + 3)));
+    });
+  }
+  tc_mma<L>(c, 64, 64, 64);
+  tc_load_w<L>(c, tw.two2);
+  tc_epi(c, 64, 64, [&](int n, float v0, float v1, float v2, float v3) { op_put4<L>(c, n, silu_act(v0), silu_act(v1), silu_act(v2), silu_act(v3)); });
+  tc_mma<L>(c, 64, 64, 0);
+  tc_load_w<L>(c, tw.embenv);
+  {
+    float* X0g = a.X[0] + (size_t)tile * S * TM;
+    tc_epi(c, 0, 64, [&](int n, float v0, float v1, float v2, float v3) {
+      v0 *= g.u; v1 *= g.u; v2 *= g.u; v3 *= g.u;
+      op_put4<L>(c, n, v0, v1, v2, v3);
+      X0g[(n + 0) * TM + c.m] = v0; X0g[(n + 1) * TM + c.m] = v1; X0g[(n + 2) * TM + c.m] = v2; X0g[(n + 3) * TM + c.m] = v3;
+    });
+  }
+  tc_mma<L>(c, 64, 2 * D::ENVW, 128);            // [embed | env_0] in one GEMM
+  {
+    float* W0g = a.W0 + (size_t)tile * D::ENVW * TM;
+    tc_epi(c, 128, D::ENVW, [&](int n, float v0, float v1, float v2, float v3) {
+      W0g[(n + 0) * TM + c.m] = v0; W0g[(n + 1) * TM + c.m] = v1; W0g[(n + 2) * TM + c.m] = v2; W0g[(n + 3) * TM + c.m] = v3;
+    });
+    tc_env_to_ws<L>(c, 128 + D::ENVW);
+  }
+  __syncthreads();
+  tc_env_sum<L>(a, w, c, tile, es, nvalid, a.gamma[0]);
+  tc_end(c);
+}
+
+// ============================================================================================
+// FK
+// ============================================================================================
+template <int L, char KIND, bool FIRST>
+__global__ void __launch_bounds__(NT, 1) k_fk_tc(const __grid_constant__ ChunkArgs a, const __grid_constant__ ModelW w, const __grid_constant__ TcW tw, const int k) {
+  using D = DimsTC<L>; using SM = SmemTC<L>; using TP = tpgen::TP<L, KIND>; constexpr int TM = 128;
+  extern __shared__ __align__(1024) float sm_raw[];
+  TcCtx c = tc_begin<L>(sm_raw, tw);
+  const int tile = blockIdx.x;
+  const int es = a.e0 + tile * TM;
+  const int nvalid = min(TM, a.e1 - es);
+  const LayerW& lw = w.layer[k];
+  const TcLayerW& tl = tw.layer[k];
+  tc_load_w<L>(c, tl.m0);
+  const Geom g = tc_geom<L>(a, w, c, es, nvalid);
+  const float* Xg = a.X[k] + (size_t)tile * S * TM;
+  op_load_rows64<L>(c, Xg);
+  __syncthreads();
+  {  // tensor product: s -> operand columns S.., V^{k+1} -> global
+    const float* Y_s = c.sm + SM::oY;
+    const int* c_s = reinterpret_cast<const int*>(c.sm + SM::oC);
+    const int e = c.m, uh = c.half;
+    const float* gam = a.gamma[k] + (size_t)(c_s[e] - a.c0) * D::F;
+    float* Vng = a.V[k + 1] + (size_t)tile * U * TP::DOUT * TM;
+#pragma unroll 1
+    for (int i = 0; i < D::CPT; ++i) {
+      const int u = uh + D::CPH * i;
+      float Vin[TP::DIN], G[D::NSH], Vout[TP::DOUT], s[TP::N0];
+      tc_load_vin<L, FIRST, TP::DIN>(a, tile, k, e, u, Y_s, Vin);
+#pragma unroll
+      for (int lm = 0; lm < D::NSH; ++lm) G[lm] = gam[lm * U + u];
+      TP::template fwd<U>(Vin, G, lw.omega + u, Vout, s);
+#pragma unroll
+      for (int q = 0; q < TP::N0; ++q) op_put1<L>(c, e, S + q * U + u, s[q]);
+#pragma unroll
+      for (int cc = 0; cc < TP::DOUT; ++cc) Vng[(u * TP::DOUT + cc) * TM + e] = Vout[cc];
+    }
+  }
+  tc_mma<L>(c, D::SIN, 64, 0);
+  tc_load_w<L>(c, tl.m1);
+  tc_epi(c, 0, 64, [&](int n, float v0, float v1, float v2, float v3) { op_put4<L>(c, n, silu_act(v0), silu_act(v1), silu_act(v2), silu_act(v3)); });
+  tc_mma<L>(c, 64, 64, 64);
+  tc_load_w<L>(c, tl.m2);
+  tc_epi(c, 64, 64, [&](int n, float v0, float v1, float v2, float v3) { op_put4<L>(c, n, silu_act(v0), silu_act(v1), silu_act(v2), silu_act(v3)); });
+  tc_mma<L>(c, 64, 64, 0);
+  tc_load_w<L>(c, tw.layer[k + 1].env);
+  {
+    float* Xng = a.X[k + 1] + (size_t)tile * S * TM;
+    tc_epi(c, 0, 64, [&](int n, float v0, float v1, float v2, float v3) {
+      const float x0 = lw.a * Xg[(n + 0) * TM + c.m] + lw.b * v0 * g.u, x1 = lw.a * Xg[(n + 1) * TM + c.m] + lw.b * v1 * g.u;
+      const float x2 = lw.a * Xg[(n + 2) * TM + c.m] + lw.b * v2 * g.u, x3 = lw.a * Xg[(n + 3) * TM + c.m] + lw.b * v3 * g.u;
+      op_put4<L>(c, n, x0, x1, x2, x3);
+      Xng[(n + 0) * TM + c.m] = x0; Xng[(n + 1) * TM + c.m] = x1; Xng[(n + 2) * TM + c.m] = x2; Xng[(n + 3) * TM + c.m] = x3;
+    });
+  }
+  tc_mma<L>(c, 64, D::ENVW, 128);
+  tc_env_to_ws<L>(c, 128);
+  __syncthreads();
+  tc_env_sum<L>(a, w, c, tile, es, nvalid, a.gamma[k + 1]);
+  tc_end(c);
+}
+
+// ============================================================================================
+// shared backward pieces.  TMEM column map: z1 [0,64)  z2 [64,128)  m [128,192)  scratch [192,...)
+// ============================================================================================
+constexpr uint32_t TC_Z1 = 0, TC_Z2 = 64, TC_M = 128, TC_SCR = 192;
+
+// forward (re)compute of an MLP whose first-layer operand (K0 columns) is already in place;
+// leaves z1, z2, m in TMEM.  Weight image of layer 0 must already be requested (tc_load_w).
+template <int L, class Bias>
+__device__ __forceinline__ void tc_mlp_fwd_keep(TcCtx& c, int K0, const TcMat& w1, const TcMat& w2, const TcMat& next, Bias bias) {
+  tc_mma<L>(c, K0, 64, TC_Z1);
+  tc_load_w<L>(c, w1);
+  tc_epi(c, TC_Z1, 64, [&](int n, float v0, float v1, float v2, float v3) {
+    op_put4<L>(c, n, silu_act(v0 + bias(n)), silu_act(v1 + bias(n + 1)), silu_act(v2 + bias(n + 2)), silu_act(v3 + bias(n + 3)));
+  });
+  tc_mma<L>(c, 64, 64, TC_Z2);
+  tc_load_w<L>(c, w2);
+  tc_epi(c, TC_Z2, 64, [&](int n, float v0, float v1, float v2, float v3) { op_put4<L>(c, n, silu_act(v0), silu_act(v1), silu_act(v2), silu_act(v3)); });
+  tc_mma<L>(c, 64, 64, TC_M);
+  tc_load_w<L>(c, next);
+}
+
+// given dm (operand columns [0,64)) : dz2 = (dm W2^T) * act'(z2) ; dz1 = (dz2 W1^T) * act'(z1 + bias) -> operand [0,64)
+// the weight image w2_b must already be requested; requests `next` at the end.
+template <int L, class Bias>
+__device__ __forceinline__ void tc_mlp_bwd_hidden(TcCtx& c, const TcMat& w1_b, const TcMat& next, Bias bias) {
+  tc_mma<L>(c, 64, 64, TC_SCR);
+  tc_load_w<L>(c, w1_b);
+  for (int c0 = c.half * 32; c0 < c.half * 32 + 32; c0 += 16) {
+    float v[16], z[16];
+    tc_ld16(c, TC_SCR + c0, v);
+    tc_ld16(c, TC_Z2 + c0, z);
+#pragma unroll
+    for (int i = 0; i < 16; i += 4) {
+      float d0, d1, d2, d3;
+      silu_act(z[i], d0); silu_act(z[i + 1], d1); silu_act(z[i + 2], d2); silu_act(z[i + 3], d3);
+      op_put4<L>(c, c0 + i, v[i] * d0, v[i + 1] * d1, v[i + 2] * d2, v[i + 3] * d3);
+    }
+  }
+  tc_mma<L>(c, 64, 64, TC_SCR);
+  tc_load_w<L>(c, next);
+  for (int c0 = c.half * 32; c0 < c.half * 32 + 32; c0 += 16) {
+    float v[16], z[16];
+    tc_ld16(c, TC_SCR + c0, v);
+    tc_ld16(c, TC_Z1 + c0, z);
+#pragma unroll
+    for (int i = 0; i < 16; i += 4) {
+      float d0, d1, d2, d3;
+      silu_act(z[i] + bias(c0 + i), d0); silu_act(z[i + 1] + bias(c0 + i + 1), d1);
+      silu_act(z[i + 2] + bias(c0 + i + 2), d2); silu_act(z[i + 3] + bias(c0 + i + 3), d3);
+      op_put4<L>(c, c0 + i, v[i] * d0, v[i + 1] * d1, v[i + 2] * d2, v[i + 3] * d3);
+    }
+  }
+}
+
+struct NoBias { __device__ __forceinline__ float operator()(int) const { return 0.f; } };
+
+// tensor-product backward (all channels, passes of CHU), dG segmented sum -> dgamma_out.
+// ds is read from DS_s (= WBH region, [q*U+u][128]); dG staged in the OPH/OPL regions.
+template <int L, char KIND, bool FIRST, bool HAS_DVOUT>
+__device__ __forceinline__ void tc_tp_backward(const ChunkArgs& a, const LayerW& lw, const TcCtx& c, int tile, int k, int es, int nvalid,
+                                               const float* __restrict__ dVnext, float* __restrict__ dVprev,
+                                               float* __restrict__ dgamma_out, float* dYp) {
+  using D = DimsTC<L>; using SM = SmemTC<L>; using TP = tpgen::TP<L, KIND>; constexpr int TM = 128;
+  const int t = threadIdx.x;
+  const float* DS_s = c.sm + SM::oWBH;
+  float* DG = c.sm + SM::oOPH;
+  const float* Y_s = c.sm + SM::oY;
+  const int* c_s = reinterpret_cast<const int*>(c.sm + SM::oC);
+  const int e = c.m, uh = c.half;
+  const float* gam = a.gamma[k] + (size_t)(c_s[e] - a.c0) * D::F;
+  float* W0g = a.W0 + (size_t)tile * D::ENVW * TM;
+  if (FIRST) {
+#pragma unroll
+    for (int lm = 0; lm < D::NSH; ++lm) dYp[lm] = 0.f;
+  }
+#pragma unroll 1
+  for (int pass = 0; pass < U / D::CHU; ++pass) {
+#pragma unroll 1
+    for (int ul = uh; ul < D::CHU; ul += D::CPH) {
+      const int u = pass * D::CHU + ul;
+      float Vin[TP::DIN], G[D::NSH], dVout[TP::DOUT], ds[TP::N0], dVin[TP::DIN], dG[D::NSH];
+      tc_load_vin<L, FIRST, TP::DIN>(a, tile, k, e, u, Y_s, Vin);
+#pragma unroll
+      for (int lm = 0; lm < D::NSH; ++lm) G[lm] = gam[lm * U + u];
+      if (HAS_DVOUT) {
+        const float* dVg = dVnext + ((size_t)tile * U + u) * TP::DOUT * TM;
+#pragma unroll
+        for (int cc = 0; cc < TP::DOUT; ++cc) dVout[cc] = dVg[cc * TM + e];
+      }
+#pragma unroll
+      for (int q = 0; q < TP::N0; ++q) ds[q] = DS_s[(q * U + u) * TM + e];
+      TP::template bwd<U>(Vin, G, lw.omega + u, dVout, ds, dVin, dG);
+      if (FIRST) {
+#pragma unroll
+        for (int l = 0; l <= L; ++l) {
+          const float wv = W0g[(l * U + u) * TM + e];
+          float dw = 0.f;
+#pragma unroll
+          for (int lm = l * l; lm < (l + 1) * (l + 1); ++lm) { dw += dVin[lm] * Y_s[lm * TM + e]; dYp[lm] += dVin[lm] * wv; }
+          W0g[(l * U + u) * TM + e] = dw;
+        }
+      } else {
+        float* dVp = dVprev + ((size_t)tile * U + u) * TP::DIN * TM;
+#pragma unroll
+        for (int cc = 0; cc < TP::DIN; ++cc) dVp[cc * TM + e] = dVin[cc];
+      }
+#pragma unroll
+      for (int lm = 0; lm < D::NSH; ++lm) DG[e * D::DGS + lm * D::CHU + ul] = dG[lm];
+    }
+    __syncthreads();
+    {
+      const int cfirst = c_s[0];
+      const bool contin = a.rowptr[cfirst] < es;
+      float* carry = a.carry + (size_t)tile * D::F;
+      for (int f = t; f < D::FC; f += NT) {
+        const int lm = f / D::CHU, ul = f % D::CHU;
+        const int fg = lm * U + pass * D::CHU + ul;
+        int cur = cfirst; bool first = true; float acc = 0.f;
+        for (int ee = 0; ee < nvalid; ++ee) {
+          const int cc = c_s[ee];
+          if (cc != cur) {
+            if (first && contin) carry[fg] = acc; else dgamma_out[(size_t)(cur - a.c0) * D::F + fg] = acc;
+            cur = cc; acc = 0.f; first = false;
+          }
+          acc += DG[ee * D::DGS + f];
+        }
+        if (first && contin) carry[fg] = acc; else dgamma_out[(size_t)(cur - a.c0) * D::F + fg] = acc;
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// dY partials of the two channel halves -> global dY (+ optional extra per-row values held by half 0)
+template <int L, bool ASSIGN>
+__device__ __forceinline__ void tc_dy_store(const ChunkArgs& a, const TcCtx& c, int tile, const float* dYp, bool have) {
+  using D = DimsTC<L>; using SM = SmemTC<L>; constexpr int TM = 128;
+  float* P = c.sm + SM::oOPH;     // [2][NSH][128]
+  if (have) {
+#pragma unroll
+    for (int lm = 0; lm < D::NSH; ++lm) P[(c.half * D::NSH + lm) * TM + c.m] = dYp[lm];
+  }
+  __syncthreads();
+  float* dYg = a.dY + (size_t)tile * D::NSH * TM;
+  const float* DY_s = c.sm + SM::oDY;
+  for (int i = threadIdx.x; i < D::NSH * TM; i += NT) {
+    float v = DY_s[i];
+    if (have) v += P[i] + P[D::NSH * TM + i];
+    if (ASSIGN) dYg[i] = v; else dYg[i] += v;
+  }
+  __syncthreads();
+}
+
+// phase 2 of layer kk: x^kk must be in operand columns [0,64) and tl.env requested.
+//   w = env(x) (TMEM) ; dGamma gather -> dw (operand [0,ENVW)), dY partial (-> DY_s) ; dX(global) += dw env^T
+//   `extra` (FIRST layer in B0): additional operand columns [ENVW, 2*ENVW) = dw0 and the stacked weight image.
+template <int L>
+__device__ __forceinline__ void tc_phase2(const ChunkArgs& a, const ModelW& w, TcCtx& c, int kk, int tile, const TcMat& back, bool with_dw0) {
+  using D = DimsTC<L>; using SM = SmemTC<L>; constexpr int TM = 128;
+  tc_mma<L>(c, 64, D::ENVW, TC_SCR);
+  tc_load_w<L>(c, back);
+  const float* Y_s = c.sm + SM::oY;
+  const int* c_s = reinterpret_cast<const int*>(c.sm + SM::oC);
+  float* DY_s = c.sm + SM::oDY;
+  {
+    // thread (m, half): env columns of its half: columns n = l*U+u with u in [16*half, 16*half+16) for every l
+    const float* dgam = a.dgamma[kk] + (size_t)(c_s[c.m] - a.c0) * D::F;
+    float dYp[D::NSH];
+#pragma unroll
+    for (int lm = 0; lm < D::NSH; ++lm) dYp[lm] = 0.f;
+#pragma unroll
+    for (int l = 0; l <= L; ++l) {
+      float wv[16];
+      tc_ld16(c, TC_SCR + l * U + c.half * 16, wv);
+      float dw[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const int u = c.half * 16 + i;
+        float acc = 0.f;
+#pragma unroll
+        for (int lm = l * l; lm < (l + 1) * (l + 1); ++lm) {
+          const float dg = dgam[lm * U + u] * w.inv_sqrt_n;
+          acc += dg * Y_s[lm * TM + c.m];
+          dYp[lm] += dg * wv[i];
+        }
+        dw[i] = acc;
+      }
+#pragma unroll
+      for (int i = 0; i < 16; i += 4) op_put4<L>(c, l * U + c.half * 16 + i, dw[i], dw[i + 1], dw[i + 2], dw[i + 3]);
+    }
+    // combine the two halves' dY partials: half 1 publishes, half 0 adds
+    if (c.half == 1) {
+#pragma unroll
+      for (int lm = 0; lm < D::NSH; ++lm) DY_s[lm * TM + c.m] = dYp[lm];
+    }
+    __syncthreads();
+    if (c.half == 0) {
+#pragma unroll
+      for (int lm = 0; lm < D::NSH; ++lm) DY_s[lm * TM + c.m] += dYp[lm];
+    }
+  }
+  if (with_dw0) {   // operand columns [ENVW, 2*ENVW) = dw0 (stored in the W0 buffer by the layer-0 TP backward)
+    const float* W0g = a.W0 + (size_t)tile * D::ENVW * TM;
+    for (int n = c.half * (D::ENVW / 2); n < (c.half + 1) * (D::ENVW / 2); n += 4)
+      op_put4<L>(c, D::ENVW + n, W0g[(n + 0) * TM + c.m], W0g[(n + 1) * TM + c.m], W0g[(n + 2) * TM + c.m], W0g[(n + 3) * TM + c.m]);
+  }
+  tc_mma<L>(c, with_dw0 ? 2 * D::ENVW : D::ENVW, 64, TC_SCR);
+}
+
+// ============================================================================================
+// T
+// ============================================================================================
+template <int L, bool FIRST>
+__global__ void __launch_bounds__(NT, 1) k_t_tc(const __grid_constant__ ChunkArgs a, const __grid_constant__ ModelW w, const __grid_constant__ TcW tw, const int k) {
+  using D = DimsTC<L>; using SM = SmemTC<L>; using TP = tpgen::TP<L, 'A'>; constexpr int TM = 128;
+  extern __shared__ __align__(1024) float sm_raw[];
+  TcCtx c = tc_begin<L>(sm_raw, tw);
+  const int tile = blockIdx.x;
+  const int es = a.e0 + tile * TM;
+  const int nvalid = min(TM, a.e1 - es);
+  const LayerW& lw = w.layer[k];
+  const TcLayerW& tl = tw.layer[k];
+  tc_load_w<L>(c, tl.m0);
+  const Geom g = tc_geom<L>(a, w, c, es, nvalid);
+  const float* Xg = a.X[k] + (size_t)tile * S * TM;
+  op_load_rows64<L>(c, Xg);
+  __syncthreads();
+  const float* Y_s = c.sm + SM::oY;
+  const int* c_s = reinterpret_cast<const int*>(c.sm + SM::oC);
+  {
+    const int e = c.m, uh = c.half;
+    const float* gam = a.gamma[k] + (size_t)(c_s[e] - a.c0) * D::F;
+#pragma unroll 1
+    for (int i = 0; i < D::CPT; ++i) {
+      const int u = uh + D::CPH * i;
+      float Vin[TP::DIN], G[D::NSH], s[TP::N0];
+      tc_load_vin<L, FIRST, TP::DIN>(a, tile, k, e, u, Y_s, Vin);
+#pragma unroll
+      for (int lm = 0; lm < D::NSH; ++lm) G[lm] = gam[lm * U + u];
+      TP::template fwd<U>(Vin, G, lw.omega + u, nullptr, s);
+#pragma unroll
+      for (int q = 0; q < TP::N0; ++q) op_put1<L>(c, e, S + q * U + u, s[q]);
+    }
+  }
+  tc_mlp_fwd_keep<L>(c, D::SIN, tl.m1, tl.m2, tw.ro0, NoBias());
+  // x^n = a x^{n-1} + b m u -> operand [0,64)
+  tc_epi(c, TC_M, 64, [&](int n, float v0, float v1, float v2, float v3) {
+    op_put4<L>(c, n, lw.a * Xg[(n + 0) * TM + c.m] + lw.b * v0 * g.u, lw.a * Xg[(n + 1) * TM + c.m] + lw.b * v1 * g.u,
+               lw.a * Xg[(n + 2) * TM + c.m] + lw.b * v2 * g.u, lw.a * Xg[(n + 3) * TM + c.m] + lw.b * v3 * g.u);
+  });
+  tc_mma<L>(c, 64, R, TC_SCR);                       // readout hidden
+  tc_load_w<L>(c, tw.ro0_b);
+  float* e_s = c.sm + SM::oE;
+  {
+    const float ge = w.gscale[g.zi];
+    float v[16];
+    tc_ld16(c, TC_SCR + c.half * 16, v);
+    float ee = 0.f, dz[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const float wq = __ldg(w.ro1 + c.half * 16 + i);
+      float d;
+      const float r = silu_act(v[i], d);
+      ee += wq * r;
+      dz[i] = ge * wq * d;
+    }
+#pragma unroll
+    for (int i = 0; i < 16; i += 4) op_put4<L>(c, c.half * 16 + i, dz[i], dz[i + 1], dz[i + 2], dz[i + 3]);
+    e_s[c.half * TM + c.m] = ee;
+  }
+  tc_mma<L>(c, R, 64, TC_SCR);                       // dx^n = dz ro0^T   (barrier inside orders e_s)
+  tc_load_w<L>(c, tl.m2_b);
+  if (c.half == 0) {
+    const float ee = e_s[c.m] + e_s[TM + c.m];
+    e_s[2 * TM + c.m] = ee;                          // final E_e (read by thread 0 after the barrier below)
+    if (c.m < nvalid && a.edge_energy) a.edge_energy[es + c.m] = ee;
+  }
+  float* dXg = a.dX + (size_t)tile * S * TM;
+  {
+    float dup = 0.f;
+    for (int c0 = c.half * 32; c0 < c.half * 32 + 32; c0 += 16) {
+      float v[16], mv[16];
+      tc_ld16(c, TC_SCR + c0, v);
+      tc_ld16(c, TC_M + c0, mv);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        dXg[(c0 + i) * TM + c.m] = lw.a * v[i];
+        v[i] *= lw.b;                 // dxt
+        dup += v[i] * mv[i];
+        v[i] *= g.u;                  // dm
+      }
+#pragma unroll
+      for (int i = 0; i < 16; i += 4) op_put4<L>(c, c0 + i, v[i], v[i + 1], v[i + 2], v[i + 3]);
+    }
+    if (c.half == 1) e_s[3 * TM + c.m] = dup;
+    __syncthreads();
+    if (c.half == 0) a.du[(size_t)tile * TM + c.m] = dup + e_s[3 * TM + c.m];
+  }
+  if (threadIdx.x == 0) {  // E_i raw sums (double), deterministic edge order
+    const int cfirst = c_s[0];
+    const bool contin = a.rowptr[cfirst] < es;
+    int cur = cfirst; bool first = true; double acc = 0.0;
+    for (int e = 0; e < nvalid; ++e) {
+      const int cc = c_s[e];
+      if (cc != cur) {
+        if (first && contin) a.ecarry[tile] = acc; else a.esum[cur] = acc;
+        cur = cc; acc = 0.0; first = false;
+      }
+      acc += (double)e_s[2 * TM + e];
+    }
+    if (first && contin) a.ecarry[tile] = acc; else a.esum[cur] = acc;
+  }
+  tc_mlp_bwd_hidden<L>(c, tl.m1_b, tl.m0_b, NoBias());
+  tc_mma<L>(c, 64, D::SIN, TC_SCR);                  // dIN
+  {
+    float* DS_s = c.sm + SM::oWBH;                   // weights no longer needed
+    tc_epi(c, TC_SCR, D::SIN, [&](int n, float v0, float v1, float v2, float v3) {
+      if (n < S) {
+        dXg[(n + 0) * TM + c.m] += v0; dXg[(n + 1) * TM + c.m] += v1; dXg[(n + 2) * TM + c.m] += v2; dXg[(n + 3) * TM + c.m] += v3;
+      } else {
+        DS_s[(n - S + 0) * TM + c.m] = v0; DS_s[(n - S + 1) * TM + c.m] = v1; DS_s[(n - S + 2) * TM + c.m] = v2; DS_s[(n - S + 3) * TM + c.m] = v3;
+      }
+    });
+  }
+  __syncthreads();
+  float dYp[D::NSH];
+  tc_tp_backward<L, 'A', FIRST, false>(a, lw, c, tile, k, es, nvalid, nullptr, FIRST ? nullptr : a.dV[k & 1], a.dgamma[k], dYp);
+  for (int i = threadIdx.x; i < D::NSH * TM; i += NT) c.sm[SM::oDY + i] = 0.f;
+  __syncthreads();
+  tc_dy_store<L, true>(a, c, tile, dYp, FIRST);
+  tc_end(c);
+}
+
+// ============================================================================================
+// BK
+// ============================================================================================
+template <int L, char KIND, bool FIRST>
+__global__ void __launch_bounds__(NT, 1) k_bk_tc(const __grid_constant__ ChunkArgs a, const __grid_constant__ ModelW w, const __grid_constant__ TcW tw, const int k) {
+  using D = DimsTC<L>; using SM = SmemTC<L>; using TP = tpgen::TP<L, KIND>; constexpr int TM = 128;
+  extern __shared__ __align__(1024) float sm_raw[];
+  TcCtx c = tc_begin<L>(sm_raw, tw);
+  const int tile = blockIdx.x;
+  const int es = a.e0 + tile * TM;
+  const int nvalid = min(TM, a.e1 - es);
+  const LayerW& lw = w.layer[k];
+  const TcLayerW& tl = tw.layer[k];
+  tc_load_w<L>(c, tw.layer[k + 1].env);
+  const Geom g = tc_geom<L>(a, w, c, es, nvalid);
+  op_load_rows64<L>(c, a.X[k + 1] + (size_t)tile * S * TM);
+  __syncthreads();
+  float* dXg = a.dX + (size_t)tile * S * TM;
+  tc_phase2<L>(a, w, c, k + 1, tile, tw.layer[k + 1].env_b, false);
+  tc_load_w<L>(c, tl.m0);
+  // dX += (dw env^T): keep the complete dx^{k+1} of this thread's columns in registers? -> write back to global
+  tc_epi(c, TC_SCR, 64, [&](int n, float v0, float v1, float v2, float v3) {
+    dXg[(n + 0) * TM + c.m] += v0; dXg[(n + 1) * TM + c.m] += v1; dXg[(n + 2) * TM + c.m] += v2; dXg[(n + 3) * TM + c.m] += v3;
+  });
+  // ---- recompute layer k forward
+  const float* Xg = a.X[k] + (size_t)tile * S * TM;
+  op_load_rows64<L>(c, Xg);
+  const float* Y_s = c.sm + SM::oY;
+  const int* c_s = reinterpret_cast<const int*>(c.sm + SM::oC);
+  {
+    const int e = c.m, uh = c.half;
+    const float* gam = a.gamma[k] + (size_t)(c_s[e] - a.c0) * D::F;
+#pragma unroll 1
+    for (int i = 0; i < D::CPT; ++i) {
+      const int u = uh + D::CPH * i;
+      float Vin[TP::DIN], G[D::NSH], s[TP::N0];
+      tc_load_vin<L, FIRST, TP::DIN>(a, tile, k, e, u, Y_s, Vin);
+#pragma unroll
+      for (int lm = 0; lm < D::NSH; ++lm) G[lm] = gam[lm * U + u];
+      tpgen::TP<L, 'A'>::template fwd<U>(Vin, G, nullptr, nullptr, s);
+#pragma unroll
+      for (int q = 0; q < TP::N0; ++q) op_put1<L>(c, e, S + q * U + u, s[q]);
+    }
+  }
+  tc_mlp_fwd_keep<L>(c, D::SIN, tl.m1, tl.m2, tl.m2_b, NoBias());
+  {
+    float dup = 0.f;
+    for (int c0 = c.half * 32; c0 < c.half * 32 + 32; c0 += 16) {
+      float mv[16], v[16];
+      tc_ld16(c, TC_M + c0, mv);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const float dxn = dXg[(c0 + i) * TM + c.m];
+        dXg[(c0 + i) * TM + c.m] = lw.a * dxn;
+        const float dxt = lw.b * dxn;
+        dup += dxt * mv[i];
+        v[i] = dxt * g.u;
+      }
+#pragma unroll
+      for (int i = 0; i < 16; i += 4) op_put4<L>(c, c0 + i, v[i], v[i + 1], v[i + 2], v[i + 3]);
+    }
+    float* e_s = c.sm + SM::oE;
+    if (c.half == 1) e_s[c.m] = dup;
+    __syncthreads();
+    if (c.half == 0) a.du[(size_t)tile * TM + c.m] += dup + e_s[c.m];
+  }
+  tc_mlp_bwd_hidden<L>(c, tl.m1_b, tl.m0_b, NoBias());
+  tc_mma<L>(c, 64, D::SIN, TC_SCR);
+  {
+    float* DS_s = c.sm + SM::oWBH;
+    tc_epi(c, TC_SCR, D::SIN, [&](int n, float v0, float v1, float v2, float v3) {
+      if (n < S) {
+        dXg[(n + 0) * TM + c.m] += v0; dXg[(n + 1) * TM + c.m] += v1; dXg[(n + 2) * TM + c.m] += v2; dXg[(n + 3) * TM + c.m] += v3;
+      } else {
+        DS_s[(n - S + 0) * TM + c.m] = v0; DS_s[(n - S + 1) * TM + c.m] = v1; DS_s[(n - S + 2) * TM + c.m] = v2; DS_s[(n - S + 3) * TM + c.m] = v3;
+      }
+    });
+  }
+  __syncthreads();
+  float dYp[D::NSH];
+  tc_tp_backward<L, KIND, FIRST, true>(a, lw, c, tile, k, es, nvalid, a.dV[(k + 1) & 1], FIRST ? nullptr : a.dV[k & 1], a.dgamma[k], dYp);
+  tc_dy_store<L, false>(a, c, tile, dYp, FIRST);
+  tc_end(c);
+}
+
+// ============================================================================================
+// B0
+// ============================================================================================
+template <int L>
+__global__ void __launch_bounds__(NT, 1) k_b0_tc(const __grid_constant__ ChunkArgs a, const __grid_constant__ ModelW w, const __grid_constant__ TcW tw) {
+  using D = DimsTC<L>; using SM = SmemTC<L>; constexpr int TM = 128;
+  extern __shared__ __align__(1024) float sm_raw[];
+  TcCtx c = tc_begin<L>(sm_raw, tw);
+  const int tile = blockIdx.x;
+  const int es = a.e0 + tile * TM;
+  const int nvalid = min(TM, a.e1 - es);
+  tc_load_w<L>(c, tw.layer[0].env);
+  const Geom g = tc_geom<L>(a, w, c, es, nvalid);
+  op_load_rows64<L>(c, a.X[0] + (size_t)tile * S * TM);
+  __syncthreads();
+  float* dXg = a.dX + (size_t)tile * S * TM;
+  tc_phase2<L>(a, w, c, 0, tile, tw.envemb_b, true);     // dx0 += dw env0^T + dw0 emb^T  (one GEMM, K = 2*ENVW)
+  tc_load_w<L>(c, tw.two0);
+  float dx0[32];                                         // complete dx^0 of this thread's 32 columns
+  for (int c0 = 0; c0 < 32; c0 += 16) {
+    float v[16];
+    tc_ld16(c, TC_SCR + c.half * 32 + c0, v);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) dx0[c0 + i] = v[i] + dXg[(c.half * 32 + c0 + i) * TM + c.m];
+  }
+  // ---- recompute the two-body MLP (Bessel operand), keep z1, z2, m0 in TMEM
+  float bes[MAXB], dbes[MAXB];
+  {
+    const float pref = sqrtf(2.0f / g.rc);
+    const float xr = g.r / g.rc;
+#pragma unroll
+    for (int n = 0; n < MAXB; ++n) {
+      if (n < w.B) {
+        const float kn = (float)(n + 1) * 3.14159265358979323846f;
+        float sn, cs;
+        sincosf(kn * xr, &sn, &cs);
+        bes[n] = pref * sn / g.r;
+        dbes[n] = pref * (kn / g.rc * cs / g.r - sn / (g.r * g.r));
+      } else { bes[n] = 0.f; dbes[n] = 0.f; }
+    }
+    for (int k4 = c.half * 16; k4 < c.half * 16 + 16; k4 += 4) {
+      float b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) b[i] = (k4 + i) < MAXB ? bes[(k4 + i) & (MAXB - 1)] * g.u : 0.f;
+      op_put4<L>(c, k4, b[0], b[1], b[2], b[3]);
+    }
+  }
+  const float* w0 = w.two.w[0];
+  const float* wi = w0 + g.zi * H; const float* wj = w0 + (w.T + g.zj) * H;
+  auto bias = [&](int n) { return __ldg(wi + n) + __ldg(wj + n); };
+  tc_mlp_fwd_keep<L>(c, 32, tw.two1, tw.two2, tw.two2_b, bias);
+  float du_tot;
+  {
+    float dup = 0.f;
+    for (int c0 = 0; c0 < 32; c0 += 16) {
+      float mv[16], v[16];
+      tc_ld16(c, TC_M + c.half * 32 + c0, mv);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) { dup += dx0[c0 + i] * mv[i]; v[i] = dx0[c0 + i] * g.u; }
+#pragma unroll
+      for (int i = 0; i < 16; i += 4) op_put4<L>(c, c.half * 32 + c0 + i, v[i], v[i + 1], v[i + 2], v[i + 3]);
+    }
+    float* e_s = c.sm + SM::oE;
+    e_s[c.half * TM + c.m] = dup;
+    __syncthreads();
+    du_tot = e_s[c.m] + e_s[TM + c.m] + a.du[(size_t)tile * TM + c.m];
+  }
+  tc_mlp_bwd_hidden<L>(c, tw.two1_b, tw.two0_b, bias);
+  tc_mma<L>(c, 64, 32, TC_SCR);                          // d(bessel*u) = dz1 W0[bessel rows]^T  (N padded to 32)
+  float gx = 0.f, gy = 0.f, gz = 0.f;
+  float* G3 = c.sm + SM::oOPH;                           // [3][128] g components ; virial rows after
+  float* VR = G3 + 3 * TM;                               // [6][128]
+  if (c.half == 0) {
+    float v[16];
+    tc_ld16(c, TC_SCR, v);
+    float dr = du_tot * g.dudr;
+#pragma unroll
+    for (int n = 0; n < MAXB; ++n) dr += v[n] * (dbes[n] * g.u + bes[n] * g.dudr);
+    float dYt[D::NSH];
+    const float* dYg = a.dY + (size_t)tile * D::NSH * TM;
+    const float* DY_s = c.sm + SM::oDY;
+#pragma unroll
+    for (int lm = 0; lm < D::NSH; ++lm) dYt[lm] = dYg[lm * TM + c.m] + DY_s[lm * TM + c.m];
+    float qx, qy, qz;
+    sph_harm_vjp<L>(g.x, g.y, g.z, dYt, qx, qy, qz);
+    const float nq = g.x * qx + g.y * qy + g.z * qz;
+    const float ir = 1.0f / g.r;
+    gx = dr * g.x + (qx - g.x * nq) * ir;
+    gy = dr * g.y + (qy - g.y * nq) * ir;
+    gz = dr * g.z + (qz - g.z * nq) * ir;
+    if (c.m >= nvalid) { gx = gy = gz = 0.f; }
+  }
+  __syncthreads();                                       // all TMEM / operand reads done before G3/VR overwrite OPH
+  if (c.half == 0) {
+    const int t = c.m;
+    G3[0 * TM + t] = gx; G3[1 * TM + t] = gy; G3[2 * TM + t] = gz;
+    if (t < nvalid) {
+      const int e = es + t;
+      if (a.edge_grad) { a.edge_grad[3 * (size_t)e + 0] = gx; a.edge_grad[3 * (size_t)e + 1] = gy; a.edge_grad[3 * (size_t)e + 2] = gz; }
+      const int j = a.edge_j[e];
+      atomicAdd(a.facc + 3 * (size_t)j + 0, (unsigned long long)__double2ll_rn(-(double)gx * FIX_SCALE));
+      atomicAdd(a.facc + 3 * (size_t)j + 1, (unsigned long long)__double2ll_rn(-(double)gy * FIX_SCALE));
+      atomicAdd(a.facc + 3 * (size_t)j + 2, (unsigned long long)__double2ll_rn(-(double)gz * FIX_SCALE));
+      const float rx = g.x * g.r, ry = g.y * g.r, rz = g.z * g.r;
+      VR[0 * TM + t] = -rx * gx; VR[1 * TM + t] = -ry * gy; VR[2 * TM + t] = -rz * gz;
+      VR[3 * TM + t] = -0.5f * (rx * gy + ry * gx); VR[4 * TM + t] = -0.5f * (rx * gz + rz * gx); VR[5 * TM + t] = -0.5f * (ry * gz + rz * gy);
+    } else {
+#pragma unroll
+      for (int q = 0; q < 6; ++q) VR[q * TM + t] = 0.f;
+    }
+  }
+  __syncthreads();
+  {
+    const int t = threadIdx.x;
+    const int* c_s = reinterpret_cast<const int*>(c.sm + SM::oC);
+    if (t < 3) {
+      int cur = c_s[0]; double acc = 0.0;
+      for (int e = 0; e < nvalid; ++e) {
+        const int cc = c_s[e];
+        if (cc != cur) {
+          atomicAdd(a.facc + 3 * (size_t)a.ilist[cur] + t, (unsigned long long)__double2ll_rn(acc * FIX_SCALE));
+          cur = cc; acc = 0.0;
+        }
+        acc += (double)G3[t * TM + e];
+      }
+      atomicAdd(a.facc + 3 * (size_t)a.ilist[cur] + t, (unsigned long long)__double2ll_rn(acc * FIX_SCALE));
+    } else if (t >= 32 && t < 38 && a.vacc) {
+      const int q = t - 32;
+      double acc = 0.0;
+      for (int e = 0; e < nvalid; ++e) acc += (double)VR[q * TM + e];
+      atomicAdd(a.vacc + q, (unsigned long long)__double2ll_rn(acc * VIR_SCALE));
+    }
+  }
+  tc_end(c);
+}
+
+}  // namespace alg

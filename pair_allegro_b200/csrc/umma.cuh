@@ -16,6 +16,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <string.h>
 
 namespace umma {
 
@@ -107,7 +108,15 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
-// split for 3xTF32: hi is what the tensor core sees (low 13 mantissa bits ignored), lo the rest
-__device__ __forceinline__ float tf32_lo(float a) { return a - __uint_as_float(__float_as_uint(a) & 0xFFFFE000u); }
+// split for 3xTF32: hi = a rounded to TF32 (round-to-nearest on the magnitude, so the residual is
+// signed and the split is unbiased), lo = a - hi (exact in fp32; the tensor core keeps its top 11 bits)
+__host__ __device__ __forceinline__ float tf32_hi(float a) {
+#ifdef __CUDA_ARCH__
+  return __uint_as_float((__float_as_uint(a) + 0x1000u) & 0xFFFFE000u);
+#else
+  uint32_t b; memcpy(&b, &a, 4); b = (b + 0x1000u) & 0xFFFFE000u; float r; memcpy(&r, &b, 4); return r;
+#endif
+}
+__host__ __device__ __forceinline__ float tf32_lo(float a) { return a - tf32_hi(a); }
 
 }  // namespace umma
