@@ -456,16 +456,15 @@ static int setup_model(alg_handle* h) {
     };
     const float* t0 = T_("twobody.w0"); const float* t1 = T_("twobody.w1"); const float* t2 = T_("twobody.w2");
     const float* emb = T_("embed_linear"); const float* r0 = T_("readout.w0");
-    const float* env0 = T_("layer0.env_linear");
     TcW& tw = h->tcw;
     make(&tw.two0, H, 32, [&](int n, int k) { return k < B ? t0[(size_t)(2 * T + k) * H + n] : 0.f; });
     make(&tw.two1, H, H, [&](int n, int k) { return t1[(size_t)k * H + n]; });
     make(&tw.two2, S, H, [&](int n, int k) { return t2[(size_t)k * S + n]; });
-    make(&tw.embenv, 2 * ENVW, S, [&](int n, int k) { return n < ENVW ? emb[(size_t)k * ENVW + n] : env0[(size_t)k * ENVW + n - ENVW]; });
+    make(&tw.emb, ENVW, S, [&](int n, int k) { return emb[(size_t)k * ENVW + n]; });
     make(&tw.two2_b, H, S, [&](int n, int k) { return t2[(size_t)n * S + k]; });
     make(&tw.two1_b, H, H, [&](int n, int k) { return t1[(size_t)n * H + k]; });
     make(&tw.two0_b, 32, H, [&](int n, int k) { return n < B ? t0[(size_t)(2 * T + n) * H + k] : 0.f; });
-    make(&tw.envemb_b, S, 2 * ENVW, [&](int n, int k) { return k < ENVW ? env0[(size_t)n * ENVW + k] : emb[(size_t)n * ENVW + k - ENVW]; });
+    make(&tw.emb_b, S, ENVW, [&](int n, int k) { return emb[(size_t)n * ENVW + k]; });
     make(&tw.ro0, R, S, [&](int n, int k) { return r0[(size_t)k * R + n]; });
     make(&tw.ro0_b, S, R, [&](int n, int k) { return r0[(size_t)n * R + k]; });
     for (int kk = 0; kk < h->nl; ++kk) {
@@ -473,13 +472,15 @@ static int setup_model(alg_handle* h) {
       const float* m0 = T_(pre + "mlp.w0"); const float* m1 = T_(pre + "mlp.w1"); const float* m2 = T_(pre + "mlp.w2");
       const float* env = T_(pre + "env_linear");
       TcLayerW& tl = tw.layer[kk];
-      make(&tl.m0, H, SIN, [&](int n, int k) { return m0[(size_t)k * H + n]; });
+      make(&tl.m0x, H, S, [&](int n, int k) { return m0[(size_t)k * H + n]; });
+      make(&tl.m0s, H, SIN - S, [&](int n, int k) { return m0[(size_t)(S + k) * H + n]; });
       make(&tl.m1, H, H, [&](int n, int k) { return m1[(size_t)k * H + n]; });
       make(&tl.m2, S, H, [&](int n, int k) { return m2[(size_t)k * S + n]; });
       make(&tl.env, ENVW, S, [&](int n, int k) { return env[(size_t)k * ENVW + n]; });
       make(&tl.m2_b, H, S, [&](int n, int k) { return m2[(size_t)n * S + k]; });
       make(&tl.m1_b, H, H, [&](int n, int k) { return m1[(size_t)n * H + k]; });
-      make(&tl.m0_b, SIN, H, [&](int n, int k) { return m0[(size_t)n * H + k]; });
+      make(&tl.m0_bx, S, H, [&](int n, int k) { return m0[(size_t)n * H + k]; });
+      make(&tl.m0_bs, SIN - S, H, [&](int n, int k) { return m0[(size_t)(S + n) * H + k]; });
       make(&tl.env_b, S, ENVW, [&](int n, int k) { return env[(size_t)n * ENVW + k]; });
     }
     size_t tot = 0;

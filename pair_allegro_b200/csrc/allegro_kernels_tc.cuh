@@ -24,9 +24,11 @@
 namespace alg {
 
 struct TcMat { const float* hi; const float* lo; int N, K; };   // smem image: K/32 panels x N rows x 32 floats
-struct TcLayerW { TcMat m0, m1, m2, env, m2_b, m1_b, m0_b, env_b; };
+// every image is one MMA block: N <= 64 rows, K <= 64 columns (16 KB) so that a CTA needs only
+// ~104 KB of shared memory and two CTAs share an SM (their phases overlap)
+struct TcLayerW { TcMat m0x, m0s, m1, m2, env, m2_b, m1_b, m0_bx, m0_bs, env_b; };
 struct TcW {
-  TcMat two0, two1, two2, embenv, two2_b, two1_b, two0_b, envemb_b, ro0, ro0_b;
+  TcMat two0, two1, two2, emb, two2_b, two1_b, two0_b, emb_b, ro0, ro0_b;
   TcLayerW layer[3];
   int passes;     // 3 = strict (3xTF32), 1 = fast (TF32)
 };
@@ -41,7 +43,7 @@ template <int L> struct DimsTC {
   static constexpr int CPH = NT / TM;      // 2
   static constexpr int CPT = U / CPH;      // 16
   static constexpr int WS = ENVW + 1;
-  static constexpr int CHU = (L == 1) ? 32 : 16;
+  static constexpr int CHU = 16;
   static constexpr int FC = NSH * CHU;
   static constexpr int DGS = FC + 1;
 };
@@ -49,8 +51,8 @@ template <int L> struct DimsTC {
 template <int L> struct SmemTC {
   using D = DimsTC<L>;
   static constexpr int TM = 128;
-  static constexpr int OPF = TM * 128;                 // operand capacity: K <= 128
-  static constexpr int WBF = 8192;                     // weight image capacity: N*K <= 8192
+  static constexpr int OPF = TM * 64;                  // operand capacity: K <= 64
+  static constexpr int WBF = 4096;                     // weight block capacity: N*K <= 64*64
   static constexpr int oOPH = 0;
   static constexpr int oOPL = oOPH + OPF;
   static constexpr int oWBH = oOPL + OPF;
@@ -65,8 +67,9 @@ template <int L> struct SmemTC {
   static constexpr int TOTAL = oBAR + 8;
   static constexpr size_t BYTES = (size_t)TOTAL * sizeof(float) + 1024;   // + alignment slack
   static_assert(L == 1, "tensor-core pipeline: shared-memory plan is sized for l_max = 1");
-  static_assert(D::SIN <= 128 && 2 * D::ENVW <= 128, "operand K capacity");
-  static_assert(D::WS * TM <= OPF && D::DGS * TM <= 2 * OPF, "staging buffers alias the operand regions");
+  static_assert(D::ENVW == 64 && D::SIN == 128, "block plan below assumes l_max = 1 widths");
+  static_assert(D::WS * TM <= OPF + 2 * WBF && D::DGS * TM <= 2 * OPF, "staging buffers alias the operand / weight regions");
+  static_assert(BYTES <= 113 * 1024, "two CTAs per SM");
 };
 
 struct TcCtx {
@@ -87,7 +90,7 @@ template <int L> __device__ __forceinline__ TcCtx tc_begin(float* sm_raw, const 
   c.wbar = c.mbar + 1;
   uint32_t* tptr = reinterpret_cast<uint32_t*>(c.mbar + 2);
   const int t = threadIdx.x;
-  if ((t >> 5) == 0) umma::tmem_alloc(tptr, 512);
+  if ((t >> 5) == 0) umma::tmem_alloc(tptr, 256);
   if (t == 0) { umma::mbar_init(c.mbar, 1); umma::mbar_init(c.wbar, 1); }
   umma::fence_async_smem();
   umma::fence_before_sync();
@@ -102,7 +105,7 @@ template <int L> __device__ __forceinline__ TcCtx tc_begin(float* sm_raw, const 
 __device__ __forceinline__ void tc_end(TcCtx& c) {
   umma::fence_before_sync();
   __syncthreads();
-  if ((threadIdx.x >> 5) == 0) umma::tmem_dealloc(c.tmem, 512);
+  if ((threadIdx.x >> 5) == 0) umma::tmem_dealloc(c.tmem, 256);
 }
 
 // thread 0: fetch the next GEMM's weight image(s) with TMA bulk copies (call after the previous MMA completed)
@@ -117,7 +120,7 @@ template <int L> __device__ __forceinline__ void tc_load_w(TcCtx& c, const TcMat
 }
 
 // all threads: operands are written -> thread 0 issues the MMAs -> everybody waits for completion
-template <int L> __device__ __forceinline__ void tc_mma(TcCtx& c, int K, int N, uint32_t dcol) {
+template <int L> __device__ __forceinline__ void tc_mma(TcCtx& c, int K, int N, uint32_t dcol, uint32_t accumulate = 0) {
   using SM = SmemTC<L>;
   umma::fence_async_smem();
   umma::fence_before_sync();
@@ -128,7 +131,7 @@ template <int L> __device__ __forceinline__ void tc_mma(TcCtx& c, int K, int N, 
     const float* Ah = c.sm + SM::oOPH; const float* Al = c.sm + SM::oOPL;
     const float* Wh = c.sm + SM::oWBH; const float* Wl = c.sm + SM::oWBL;
     const uint32_t idesc = umma::make_idesc_tf32(N);
-    uint32_t acc = 0;
+    uint32_t acc = accumulate;
     for (int p = 0; p < c.passes; ++p) {
       const float* Ap = (c.passes == 3 && p == 0) ? Al : Ah;       // lo*hi, hi*lo, hi*hi
       const float* Wp = (c.passes == 3 && p == 1) ? Wl : Wh;
@@ -227,6 +230,9 @@ template <int L> __device__ __forceinline__ void tc_env_sum(const ChunkArgs& a, 
                     [&](int e, int f) { const int lm = f / U, u = f % U; return W_s[e * D::WS + lsel(lm) * U + u] * Y_s[lm * TM + e]; });
 }
 
+// s-part operand column of (scalar path q, channel u): K index inside the 64-wide "s" block
+__device__ __forceinline__ int s_col(int q, int u) { return q * U + u; }
+
 template <int L, bool FIRST, int DIN>
 __device__ __forceinline__ void tc_load_vin(const ChunkArgs& a, int tile, int k, int e, int u, const float* Y_s, float* Vin) {
   using D = DimsTC<L>; constexpr int TM = 128;
@@ -246,140 +252,162 @@ __device__ __forceinline__ void tc_load_vin(const ChunkArgs& a, int tile, int k,
 }
 
 // ============================================================================================
-// F0
+// tensor product drivers: thread (edge e = m, channel phase uh = half), channels u = uh + 2 i,
+// processed in batches of TB channels with all global loads of a batch issued before any use
 // ============================================================================================
-template <int L>
-__global__ void __launch_bounds__(NT, 1) k_f0_tc(const __grid_constant__ ChunkArgs a, const __grid_constant__ ModelW w, const __grid_constant__ TcW tw) {
-  using D = DimsTC<L>; using SM = SmemTC<L>; constexpr int TM = 128;
-  extern __shared__ __align__(1024) float sm_raw[];
-  TcCtx c = tc_begin<L>(sm_raw, tw);
-  const int tile = blockIdx.x;
-  const int es = a.e0 + tile * TM;
-  const int nvalid = min(TM, a.e1 - es);
-  tc_load_w<L>(c, tw.two0);
-  const Geom g = tc_geom<L>(a, w, c, es, nvalid);
-  {  // Bessel*u -> operand columns [0,32) (zero padded beyond num_bessels)
-    const float pref = sqrtf(2.0f / g.rc);
-    const float xr = g.r / g.rc;
-    for (int k4 = c.half * 16; k4 < c.half * 16 + 16; k4 += 4) {
-      float b[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int n = k4 + i;
-        b[i] = n < w.B ? pref * sinf((float)(n + 1) * (3.14159265358979323846f * xr)) / g.r * g.u : 0.f;
-      }
-      op_put4<L>(c, k4, b[0], b[1], b[2], b[3]);
-    }
-  }
-  tc_mma<L>(c, 32, 64, 0);
-  tc_load_w<L>(c, tw.two1);
-  {
-    const float* w0 = w.two.w[0];
-    const float* wi = w0 + g.zi * H; const float* wj = w0 + (w.T + g.zj) * H;
-    tc_epi(c, 0, 64, [&](int n, float v0, float v1, float v2, float v3) {
-      op_put4<L>(c, n, silu_act(v0 + __ldg(wi + n) + __ldg(wj + n)), silu_act(v1 + __ldg(wi + n + 1) + __ldg(wj + n + 1)),
-                 silu_act(v2 + __ldg(wi + n + 2) + __ldg(wj + n + 2)), silu_act(v3 + __ldg(wi + n + 3) + __ldg(wj + n + 3)));
-    });
-  }
-  tc_mma<L>(c, 64, 64, 64);
-  tc_load_w<L>(c, tw.two2);
-  tc_epi(c, 64, 64, [&](int n, float v0, float v1, float v2, float v3) { op_put4<L>(c, n, silu_act(v0), silu_act(v1), silu_act(v2), silu_act(v3)); });
-  tc_mma<L>(c, 64, 64, 0);
-  tc_load_w<L>(c, tw.embenv);
-  {
-    float* X0g = a.X[0] + (size_t)tile * S * TM;
-    tc_epi(c, 0, 64, [&](int n, float v0, float v1, float v2, float v3) {
-      v0 *= g.u; v1 *= g.u; v2 *= g.u; v3 *= g.u;
-      op_put4<L>(c, n, v0, v1, v2, v3);
-      X0g[(n + 0) * TM + c.m] = v0; X0g[(n + 1) * TM + c.m] = v1; X0g[(n + 2) * TM + c.m] = v2; X0g[(n + 3) * TM + c.m] = v3;
-    });
-  }
-  tc_mma<L>(c, 64, 2 * D::ENVW, 128);            // [embed | env_0] in one GEMM
-  {
-    float* W0g = a.W0 + (size_t)tile * D::ENVW * TM;
-    tc_epi(c, 128, D::ENVW, [&](int n, float v0, float v1, float v2, float v3) {
-      W0g[(n + 0) * TM + c.m] = v0; W0g[(n + 1) * TM + c.m] = v1; W0g[(n + 2) * TM + c.m] = v2; W0g[(n + 3) * TM + c.m] = v3;
-    });
-    tc_env_to_ws<L>(c, 128 + D::ENVW);
-  }
-  __syncthreads();
-  tc_env_sum<L>(a, w, c, tile, es, nvalid, a.gamma[0]);
-  tc_end(c);
-}
+constexpr int TB = 4;
 
-// ============================================================================================
-// FK
-// ============================================================================================
-template <int L, char KIND, bool FIRST>
-__global__ void __launch_bounds__(NT, 1) k_fk_tc(const __grid_constant__ ChunkArgs a, const __grid_constant__ ModelW w, const __grid_constant__ TcW tw, const int k) {
-  using D = DimsTC<L>; using SM = SmemTC<L>; using TP = tpgen::TP<L, KIND>; constexpr int TM = 128;
-  extern __shared__ __align__(1024) float sm_raw[];
-  TcCtx c = tc_begin<L>(sm_raw, tw);
-  const int tile = blockIdx.x;
-  const int es = a.e0 + tile * TM;
-  const int nvalid = min(TM, a.e1 - es);
-  const LayerW& lw = w.layer[k];
-  const TcLayerW& tl = tw.layer[k];
-  tc_load_w<L>(c, tl.m0);
-  const Geom g = tc_geom<L>(a, w, c, es, nvalid);
-  const float* Xg = a.X[k] + (size_t)tile * S * TM;
-  op_load_rows64<L>(c, Xg);
-  __syncthreads();
-  {  // tensor product: s -> operand columns S.., V^{k+1} -> global
-    const float* Y_s = c.sm + SM::oY;
-    const int* c_s = reinterpret_cast<const int*>(c.sm + SM::oC);
-    const int e = c.m, uh = c.half;
-    const float* gam = a.gamma[k] + (size_t)(c_s[e] - a.c0) * D::F;
-    float* Vng = a.V[k + 1] + (size_t)tile * U * TP::DOUT * TM;
+// forward: s -> operand columns [0, N0*U) (the "s" K-block); optionally V^{k+1} -> global
+template <int L, char KIND, bool FIRST, bool WANT_V>
+__device__ __forceinline__ void tc_tp_forward(const ChunkArgs& a, const LayerW& lw, const TcCtx& c, int tile, int k) {
+  using D = DimsTC<L>; using SM = SmemTC<L>; using TP = tpgen::TP<L, KIND>; using TPA = tpgen::TP<L, 'A'>; constexpr int TM = 128;
+  const float* Y_s = c.sm + SM::oY;
+  const int* c_s = reinterpret_cast<const int*>(c.sm + SM::oC);
+  const int e = c.m, uh = c.half;
+  const float* gam = a.gamma[k] + (size_t)(c_s[e] - a.c0) * D::F;
+  float* Vng = WANT_V ? a.V[k + 1] + (size_t)tile * U * TP::DOUT * TM : nullptr;
 #pragma unroll 1
-    for (int i = 0; i < D::CPT; ++i) {
-      const int u = uh + D::CPH * i;
-      float Vin[TP::DIN], G[D::NSH], Vout[TP::DOUT], s[TP::N0];
-      tc_load_vin<L, FIRST, TP::DIN>(a, tile, k, e, u, Y_s, Vin);
+  for (int i0 = 0; i0 < D::CPT; i0 += TB) {
+    float Vin[TB][TP::DIN], G[TB][D::NSH];
 #pragma unroll
-      for (int lm = 0; lm < D::NSH; ++lm) G[lm] = gam[lm * U + u];
-      TP::template fwd<U>(Vin, G, lw.omega + u, Vout, s);
+    for (int b = 0; b < TB; ++b) {
+      const int u = uh + D::CPH * (i0 + b);
+      tc_load_vin<L, FIRST, TP::DIN>(a, tile, k, e, u, Y_s, Vin[b]);
 #pragma unroll
-      for (int q = 0; q < TP::N0; ++q) op_put1<L>(c, e, S + q * U + u, s[q]);
+      for (int lm = 0; lm < D::NSH; ++lm) G[b][lm] = gam[lm * U + u];
+    }
 #pragma unroll
-      for (int cc = 0; cc < TP::DOUT; ++cc) Vng[(u * TP::DOUT + cc) * TM + e] = Vout[cc];
+    for (int b = 0; b < TB; ++b) {
+      const int u = uh + D::CPH * (i0 + b);
+      float Vout[TP::DOUT], s[TP::N0];
+      if (WANT_V) TP::template fwd<U>(Vin[b], G[b], lw.omega + u, Vout, s);
+      else TPA::template fwd<U>(Vin[b], G[b], nullptr, nullptr, s);     // scalar paths only (same order in every kind)
+#pragma unroll
+      for (int q = 0; q < TP::N0; ++q) op_put1<L>(c, e, s_col(q, u), s[q]);
+      if (WANT_V) {
+#pragma unroll
+        for (int cc = 0; cc < TP::DOUT; ++cc) Vng[(u * TP::DOUT + cc) * TM + e] = Vout[cc];
+      }
     }
   }
-  tc_mma<L>(c, D::SIN, 64, 0);
-  tc_load_w<L>(c, tl.m1);
-  tc_epi(c, 0, 64, [&](int n, float v0, float v1, float v2, float v3) { op_put4<L>(c, n, silu_act(v0), silu_act(v1), silu_act(v2), silu_act(v3)); });
-  tc_mma<L>(c, 64, 64, 64);
-  tc_load_w<L>(c, tl.m2);
-  tc_epi(c, 64, 64, [&](int n, float v0, float v1, float v2, float v3) { op_put4<L>(c, n, silu_act(v0), silu_act(v1), silu_act(v2), silu_act(v3)); });
-  tc_mma<L>(c, 64, 64, 0);
-  tc_load_w<L>(c, tw.layer[k + 1].env);
-  {
-    float* Xng = a.X[k + 1] + (size_t)tile * S * TM;
-    tc_epi(c, 0, 64, [&](int n, float v0, float v1, float v2, float v3) {
-      const float x0 = lw.a * Xg[(n + 0) * TM + c.m] + lw.b * v0 * g.u, x1 = lw.a * Xg[(n + 1) * TM + c.m] + lw.b * v1 * g.u;
-      const float x2 = lw.a * Xg[(n + 2) * TM + c.m] + lw.b * v2 * g.u, x3 = lw.a * Xg[(n + 3) * TM + c.m] + lw.b * v3 * g.u;
-      op_put4<L>(c, n, x0, x1, x2, x3);
-      Xng[(n + 0) * TM + c.m] = x0; Xng[(n + 1) * TM + c.m] = x1; Xng[(n + 2) * TM + c.m] = x2; Xng[(n + 3) * TM + c.m] = x3;
-    });
-  }
-  tc_mma<L>(c, 64, D::ENVW, 128);
-  tc_env_to_ws<L>(c, 128);
-  __syncthreads();
-  tc_env_sum<L>(a, w, c, tile, es, nvalid, a.gamma[k + 1]);
-  tc_end(c);
 }
 
-// ============================================================================================
-// shared backward pieces.  TMEM column map: z1 [0,64)  z2 [64,128)  m [128,192)  scratch [192,...)
-// ============================================================================================
-constexpr uint32_t TC_Z1 = 0, TC_Z2 = 64, TC_M = 128, TC_SCR = 192;
+// backward over all channels in passes of CHU, dG segmented sum -> dgamma_out.
+// ds is read from DS_s (= WBH.. region, [q*U+u][128]); dG staged in the OPH/OPL regions.
+template <int L, char KIND, bool FIRST, bool HAS_DVOUT>
+__device__ __forceinline__ void tc_tp_backward(const ChunkArgs& a, const LayerW& lw, const TcCtx& c, int tile, int k, int es, int nvalid,
+                                               const float* __restrict__ dVnext, float* __restrict__ dVprev,
+                                               float* __restrict__ dgamma_out, float* dYp) {
+  using D = DimsTC<L>; using SM = SmemTC<L>; using TP = tpgen::TP<L, KIND>; constexpr int TM = 128;
+  const int t = threadIdx.x;
+  const float* DS_s = c.sm + SM::oWBH;
+  float* DG = c.sm + SM::oOPH;
+  const float* Y_s = c.sm + SM::oY;
+  const int* c_s = reinterpret_cast<const int*>(c.sm + SM::oC);
+  const int e = c.m, uh = c.half;
+  const float* gam = a.gamma[k] + (size_t)(c_s[e] - a.c0) * D::F;
+  float* W0g = a.W0 + (size_t)tile * D::ENVW * TM;
+  if (FIRST) {
+#pragma unroll
+    for (int lm = 0; lm < D::NSH; ++lm) dYp[lm] = 0.f;
+  }
+  static_assert(D::CHU / D::CPH % TB == 0, "batching");
+#pragma unroll 1
+  for (int pass = 0; pass < U / D::CHU; ++pass) {
+#pragma unroll 1
+    for (int j0 = 0; j0 < D::CHU / D::CPH; j0 += TB) {
+      float Vin[TB][TP::DIN], G[TB][D::NSH], dVout[TB][TP::DOUT], ds[TB][TP::N0];
+#pragma unroll
+      for (int b = 0; b < TB; ++b) {
+        const int ul = uh + D::CPH * (j0 + b);
+        const int u = pass * D::CHU + ul;
+        tc_load_vin<L, FIRST, TP::DIN>(a, tile, k, e, u, Y_s, Vin[b]);
+#pragma unroll
+        for (int lm = 0; lm < D::NSH; ++lm) G[b][lm] = gam[lm * U + u];
+        if (HAS_DVOUT) {
+          const float* dVg = dVnext + ((size_t)tile * U + u) * TP::DOUT * TM;
+#pragma unroll
+          for (int cc = 0; cc < TP::DOUT; ++cc) dVout[b][cc] = dVg[cc * TM + e];
+        }
+#pragma unroll
+        for (int q = 0; q < TP::N0; ++q) ds[b][q] = DS_s[s_col(q, u) * TM + e];
+      }
+#pragma unroll
+      for (int b = 0; b < TB; ++b) {
+        const int ul = uh + D::CPH * (j0 + b);
+        const int u = pass * D::CHU + ul;
+        float dVin[TP::DIN], dG[D::NSH];
+        TP::template bwd<U>(Vin[b], G[b], lw.omega + u, dVout[b], ds[b], dVin, dG);
+        if (FIRST) {
+#pragma unroll
+          for (int l = 0; l <= L; ++l) {
+            const float wv = W0g[(l * U + u) * TM + e];
+            float dw = 0.f;
+#pragma unroll
+            for (int lm = l * l; lm < (l + 1) * (l + 1); ++lm) { dw += dVin[lm] * Y_s[lm * TM + e]; dYp[lm] += dVin[lm] * wv; }
+            W0g[(l * U + u) * TM + e] = dw;      // in place: w0 -> dw0
+          }
+        } else {
+          float* dVp = dVprev + ((size_t)tile * U + u) * TP::DIN * TM;
+#pragma unroll
+          for (int cc = 0; cc < TP::DIN; ++cc) dVp[cc * TM + e] = dVin[cc];
+        }
+#pragma unroll
+        for (int lm = 0; lm < D::NSH; ++lm) DG[e * D::DGS + lm * D::CHU + ul] = dG[lm];
+      }
+    }
+    __syncthreads();
+    {
+      const int cfirst = c_s[0];
+      const bool contin = a.rowptr[cfirst] < es;
+      float* carry = a.carry + (size_t)tile * D::F;
+      for (int f = t; f < D::FC; f += NT) {
+        const int lm = f / D::CHU, ul = f % D::CHU;
+        const int fg = lm * U + pass * D::CHU + ul;
+        int cur = cfirst; bool first = true; float acc = 0.f;
+        for (int ee = 0; ee < nvalid; ++ee) {
+          const int cc = c_s[ee];
+          if (cc != cur) {
+            if (first && contin) carry[fg] = acc; else dgamma_out[(size_t)(cur - a.c0) * D::F + fg] = acc;
+            cur = cc; acc = 0.f; first = false;
+          }
+          acc += DG[ee * D::DGS + f];
+        }
+        if (first && contin) carry[fg] = acc; else dgamma_out[(size_t)(cur - a.c0) * D::F + fg] = acc;
+      }
+    }
+    __syncthreads();
+  }
+}
 
-// forward (re)compute of an MLP whose first-layer operand (K0 columns) is already in place;
-// leaves z1, z2, m in TMEM.  Weight image of layer 0 must already be requested (tc_load_w).
+// dY: DY_s (phase-2 part, smem) + the two channel-halves' partials (FIRST layers) -> global dY
+template <int L, bool ASSIGN>
+__device__ __forceinline__ void tc_dy_store(const ChunkArgs& a, const TcCtx& c, int tile, const float* dYp, bool have) {
+  using D = DimsTC<L>; using SM = SmemTC<L>; constexpr int TM = 128;
+  float* P = c.sm + SM::oOPH;     // [2][NSH][128]
+  if (have) {
+#pragma unroll
+    for (int lm = 0; lm < D::NSH; ++lm) P[(c.half * D::NSH + lm) * TM + c.m] = dYp[lm];
+  }
+  __syncthreads();
+  float* dYg = a.dY + (size_t)tile * D::NSH * TM;
+  const float* DY_s = c.sm + SM::oDY;
+  for (int i = threadIdx.x; i < D::NSH * TM; i += NT) {
+    float v = DY_s[i];
+    if (have) v += P[i] + P[D::NSH * TM + i];
+    if (ASSIGN) dYg[i] = v; else dYg[i] += v;
+  }
+  __syncthreads();
+}
+
+// TMEM column map (256 columns per CTA): z1 [0,64)  z2 [64,128)  m [128,192)  scratch [192,256)
+constexpr uint32_t TC_Z1 = 0, TC_Z2 = 64, TC_M = 128, TC_SCR = 192;
+struct NoBias { __device__ __forceinline__ float operator()(int) const { return 0.f; } };
+
+// hidden layers of an MLP whose layer-0 pre-activation z1 is complete in TMEM (w1 requested):
+// leaves z2 and m (pre-envelope output) in TMEM, requests `next`
 template <int L, class Bias>
-__device__ __forceinline__ void tc_mlp_fwd_keep(TcCtx& c, int K0, const TcMat& w1, const TcMat& w2, const TcMat& next, Bias bias) {
-  tc_mma<L>(c, K0, 64, TC_Z1);
-  tc_load_w<L>(c, w1);
+__device__ __forceinline__ void tc_mlp_hidden_fwd(TcCtx& c, const TcMat& w2, const TcMat& next, Bias bias) {
   tc_epi(c, TC_Z1, 64, [&](int n, float v0, float v1, float v2, float v3) {
     op_put4<L>(c, n, silu_act(v0 + bias(n)), silu_act(v1 + bias(n + 1)), silu_act(v2 + bias(n + 2)), silu_act(v3 + bias(n + 3)));
   });
@@ -390,8 +418,7 @@ __device__ __forceinline__ void tc_mlp_fwd_keep(TcCtx& c, int K0, const TcMat& w
   tc_load_w<L>(c, next);
 }
 
-// given dm (operand columns [0,64)) : dz2 = (dm W2^T) * act'(z2) ; dz1 = (dz2 W1^T) * act'(z1 + bias) -> operand [0,64)
-// the weight image w2_b must already be requested; requests `next` at the end.
+// dm in operand [0,64), w2_b requested: dz2 = (dm W2^T) act'(z2); dz1 = (dz2 W1^T) act'(z1+bias) -> operand; requests `next`
 template <int L, class Bias>
 __device__ __forceinline__ void tc_mlp_bwd_hidden(TcCtx& c, const TcMat& w1_b, const TcMat& next, Bias bias) {
   tc_mma<L>(c, 64, 64, TC_SCR);
@@ -423,167 +450,140 @@ __device__ __forceinline__ void tc_mlp_bwd_hidden(TcCtx& c, const TcMat& w1_b, c
   }
 }
 
-struct NoBias { __device__ __forceinline__ float operator()(int) const { return 0.f; } };
-
-// tensor-product backward (all channels, passes of CHU), dG segmented sum -> dgamma_out.
-// ds is read from DS_s (= WBH region, [q*U+u][128]); dG staged in the OPH/OPL regions.
-template <int L, char KIND, bool FIRST, bool HAS_DVOUT>
-__device__ __forceinline__ void tc_tp_backward(const ChunkArgs& a, const LayerW& lw, const TcCtx& c, int tile, int k, int es, int nvalid,
-                                               const float* __restrict__ dVnext, float* __restrict__ dVprev,
-                                               float* __restrict__ dgamma_out, float* dYp) {
-  using D = DimsTC<L>; using SM = SmemTC<L>; using TP = tpgen::TP<L, KIND>; constexpr int TM = 128;
-  const int t = threadIdx.x;
-  const float* DS_s = c.sm + SM::oWBH;
-  float* DG = c.sm + SM::oOPH;
-  const float* Y_s = c.sm + SM::oY;
-  const int* c_s = reinterpret_cast<const int*>(c.sm + SM::oC);
-  const int e = c.m, uh = c.half;
-  const float* gam = a.gamma[k] + (size_t)(c_s[e] - a.c0) * D::F;
-  float* W0g = a.W0 + (size_t)tile * D::ENVW * TM;
-  if (FIRST) {
-#pragma unroll
-    for (int lm = 0; lm < D::NSH; ++lm) dYp[lm] = 0.f;
-  }
-#pragma unroll 1
-  for (int pass = 0; pass < U / D::CHU; ++pass) {
-#pragma unroll 1
-    for (int ul = uh; ul < D::CHU; ul += D::CPH) {
-      const int u = pass * D::CHU + ul;
-      float Vin[TP::DIN], G[D::NSH], dVout[TP::DOUT], ds[TP::N0], dVin[TP::DIN], dG[D::NSH];
-      tc_load_vin<L, FIRST, TP::DIN>(a, tile, k, e, u, Y_s, Vin);
-#pragma unroll
-      for (int lm = 0; lm < D::NSH; ++lm) G[lm] = gam[lm * U + u];
-      if (HAS_DVOUT) {
-        const float* dVg = dVnext + ((size_t)tile * U + u) * TP::DOUT * TM;
-#pragma unroll
-        for (int cc = 0; cc < TP::DOUT; ++cc) dVout[cc] = dVg[cc * TM + e];
-      }
-#pragma unroll
-      for (int q = 0; q < TP::N0; ++q) ds[q] = DS_s[(q * U + u) * TM + e];
-      TP::template bwd<U>(Vin, G, lw.omega + u, dVout, ds, dVin, dG);
-      if (FIRST) {
-#pragma unroll
-        for (int l = 0; l <= L; ++l) {
-          const float wv = W0g[(l * U + u) * TM + e];
-          float dw = 0.f;
-#pragma unroll
-          for (int lm = l * l; lm < (l + 1) * (l + 1); ++lm) { dw += dVin[lm] * Y_s[lm * TM + e]; dYp[lm] += dVin[lm] * wv; }
-          W0g[(l * U + u) * TM + e] = dw;
-        }
-      } else {
-        float* dVp = dVprev + ((size_t)tile * U + u) * TP::DIN * TM;
-#pragma unroll
-        for (int cc = 0; cc < TP::DIN; ++cc) dVp[cc * TM + e] = dVin[cc];
-      }
-#pragma unroll
-      for (int lm = 0; lm < D::NSH; ++lm) DG[e * D::DGS + lm * D::CHU + ul] = dG[lm];
-    }
-    __syncthreads();
-    {
-      const int cfirst = c_s[0];
-      const bool contin = a.rowptr[cfirst] < es;
-      float* carry = a.carry + (size_t)tile * D::F;
-      for (int f = t; f < D::FC; f += NT) {
-        const int lm = f / D::CHU, ul = f % D::CHU;
-        const int fg = lm * U + pass * D::CHU + ul;
-        int cur = cfirst; bool first = true; float acc = 0.f;
-        for (int ee = 0; ee < nvalid; ++ee) {
-          const int cc = c_s[ee];
-          if (cc != cur) {
-            if (first && contin) carry[fg] = acc; else dgamma_out[(size_t)(cur - a.c0) * D::F + fg] = acc;
-            cur = cc; acc = 0.f; first = false;
-          }
-          acc += DG[ee * D::DGS + f];
-        }
-        if (first && contin) carry[fg] = acc; else dgamma_out[(size_t)(cur - a.c0) * D::F + fg] = acc;
-      }
-    }
-    __syncthreads();
-  }
-}
-
-// dY partials of the two channel halves -> global dY (+ optional extra per-row values held by half 0)
-template <int L, bool ASSIGN>
-__device__ __forceinline__ void tc_dy_store(const ChunkArgs& a, const TcCtx& c, int tile, const float* dYp, bool have) {
-  using D = DimsTC<L>; using SM = SmemTC<L>; constexpr int TM = 128;
-  float* P = c.sm + SM::oOPH;     // [2][NSH][128]
-  if (have) {
-#pragma unroll
-    for (int lm = 0; lm < D::NSH; ++lm) P[(c.half * D::NSH + lm) * TM + c.m] = dYp[lm];
-  }
-  __syncthreads();
-  float* dYg = a.dY + (size_t)tile * D::NSH * TM;
-  const float* DY_s = c.sm + SM::oDY;
-  for (int i = threadIdx.x; i < D::NSH * TM; i += NT) {
-    float v = DY_s[i];
-    if (have) v += P[i] + P[D::NSH * TM + i];
-    if (ASSIGN) dYg[i] = v; else dYg[i] += v;
-  }
-  __syncthreads();
-}
-
-// phase 2 of layer kk: x^kk must be in operand columns [0,64) and tl.env requested.
-//   w = env(x) (TMEM) ; dGamma gather -> dw (operand [0,ENVW)), dY partial (-> DY_s) ; dX(global) += dw env^T
-//   `extra` (FIRST layer in B0): additional operand columns [ENVW, 2*ENVW) = dw0 and the stacked weight image.
+// dz1 in operand, m0_bx requested: dX(global) += dz1 W0x^T ; ds = dz1 W0s^T -> DS_s (weight region)
 template <int L>
-__device__ __forceinline__ void tc_phase2(const ChunkArgs& a, const ModelW& w, TcCtx& c, int kk, int tile, const TcMat& back, bool with_dw0) {
+__device__ __forceinline__ void tc_din(TcCtx& c, const TcLayerW& tl, float* __restrict__ dXg) {
+  using SM = SmemTC<L>; constexpr int TM = 128;
+  tc_mma<L>(c, 64, 64, TC_SCR);
+  tc_load_w<L>(c, tl.m0_bs);
+  tc_epi(c, TC_SCR, 64, [&](int n, float v0, float v1, float v2, float v3) {
+    dXg[(n + 0) * TM + c.m] += v0; dXg[(n + 1) * TM + c.m] += v1; dXg[(n + 2) * TM + c.m] += v2; dXg[(n + 3) * TM + c.m] += v3;
+  });
+  tc_mma<L>(c, 64, 64, TC_SCR);                       // same operand (dz1), second weight block
+  float* DS_s = c.sm + SM::oWBH;                       // the weight region is free now
+  tc_epi(c, TC_SCR, 64, [&](int n, float v0, float v1, float v2, float v3) {
+    DS_s[(n + 0) * TM + c.m] = v0; DS_s[(n + 1) * TM + c.m] = v1; DS_s[(n + 2) * TM + c.m] = v2; DS_s[(n + 3) * TM + c.m] = v3;
+  });
+  __syncthreads();
+}
+
+// phase 2 of layer kk.  In: x^kk in operand [0,64), weight block env_kk requested.
+// Out: dw (operand [0,64)), DY_s = d/dY of the environment sum; requests `next`.
+template <int L>
+__device__ __forceinline__ void tc_phase2(const ChunkArgs& a, const ModelW& w, TcCtx& c, int kk, const TcMat& next) {
   using D = DimsTC<L>; using SM = SmemTC<L>; constexpr int TM = 128;
   tc_mma<L>(c, 64, D::ENVW, TC_SCR);
-  tc_load_w<L>(c, back);
+  tc_load_w<L>(c, next);
   const float* Y_s = c.sm + SM::oY;
   const int* c_s = reinterpret_cast<const int*>(c.sm + SM::oC);
   float* DY_s = c.sm + SM::oDY;
-  {
-    // thread (m, half): env columns of its half: columns n = l*U+u with u in [16*half, 16*half+16) for every l
-    const float* dgam = a.dgamma[kk] + (size_t)(c_s[c.m] - a.c0) * D::F;
-    float dYp[D::NSH];
+  const float* dgam = a.dgamma[kk] + (size_t)(c_s[c.m] - a.c0) * D::F;
+  float dYp[D::NSH];
 #pragma unroll
-    for (int lm = 0; lm < D::NSH; ++lm) dYp[lm] = 0.f;
+  for (int lm = 0; lm < D::NSH; ++lm) dYp[lm] = 0.f;
 #pragma unroll
-    for (int l = 0; l <= L; ++l) {
-      float wv[16];
-      tc_ld16(c, TC_SCR + l * U + c.half * 16, wv);
-      float dw[16];
+  for (int l = 0; l <= L; ++l) {
+    float wv[16], dw[16];
+    tc_ld16(c, TC_SCR + l * U + c.half * 16, wv);
 #pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        const int u = c.half * 16 + i;
-        float acc = 0.f;
+    for (int i = 0; i < 16; ++i) {
+      const int u = c.half * 16 + i;
+      float acc = 0.f;
 #pragma unroll
-        for (int lm = l * l; lm < (l + 1) * (l + 1); ++lm) {
-          const float dg = dgam[lm * U + u] * w.inv_sqrt_n;
-          acc += dg * Y_s[lm * TM + c.m];
-          dYp[lm] += dg * wv[i];
-        }
-        dw[i] = acc;
+      for (int lm = l * l; lm < (l + 1) * (l + 1); ++lm) {
+        const float dg = dgam[lm * U + u] * w.inv_sqrt_n;
+        acc += dg * Y_s[lm * TM + c.m];
+        dYp[lm] += dg * wv[i];
       }
-#pragma unroll
-      for (int i = 0; i < 16; i += 4) op_put4<L>(c, l * U + c.half * 16 + i, dw[i], dw[i + 1], dw[i + 2], dw[i + 3]);
+      dw[i] = acc;
     }
-    // combine the two halves' dY partials: half 1 publishes, half 0 adds
-    if (c.half == 1) {
 #pragma unroll
-      for (int lm = 0; lm < D::NSH; ++lm) DY_s[lm * TM + c.m] = dYp[lm];
-    }
-    __syncthreads();
-    if (c.half == 0) {
-#pragma unroll
-      for (int lm = 0; lm < D::NSH; ++lm) DY_s[lm * TM + c.m] += dYp[lm];
-    }
+    for (int i = 0; i < 16; i += 4) op_put4<L>(c, l * U + c.half * 16 + i, dw[i], dw[i + 1], dw[i + 2], dw[i + 3]);
   }
-  if (with_dw0) {   // operand columns [ENVW, 2*ENVW) = dw0 (stored in the W0 buffer by the layer-0 TP backward)
-    const float* W0g = a.W0 + (size_t)tile * D::ENVW * TM;
-    for (int n = c.half * (D::ENVW / 2); n < (c.half + 1) * (D::ENVW / 2); n += 4)
-      op_put4<L>(c, D::ENVW + n, W0g[(n + 0) * TM + c.m], W0g[(n + 1) * TM + c.m], W0g[(n + 2) * TM + c.m], W0g[(n + 3) * TM + c.m]);
+  if (c.half == 1) {
+#pragma unroll
+    for (int lm = 0; lm < D::NSH; ++lm) DY_s[lm * TM + c.m] = dYp[lm];
   }
-  tc_mma<L>(c, with_dw0 ? 2 * D::ENVW : D::ENVW, 64, TC_SCR);
+  __syncthreads();
+  if (c.half == 0) {
+#pragma unroll
+    for (int lm = 0; lm < D::NSH; ++lm) DY_s[lm * TM + c.m] += dYp[lm];
+  }
 }
 
 // ============================================================================================
-// T
+// F0
 // ============================================================================================
-template <int L, bool FIRST>
-__global__ void __launch_bounds__(NT, 1) k_t_tc(const __grid_constant__ ChunkArgs a, const __grid_constant__ ModelW w, const __grid_constant__ TcW tw, const int k) {
-  using D = DimsTC<L>; using SM = SmemTC<L>; using TP = tpgen::TP<L, 'A'>; constexpr int TM = 128;
+template <int L>
+__global__ void __launch_bounds__(NT, 2) k_f0_tc(const __grid_constant__ ChunkArgs a, const __grid_constant__ ModelW w, const __grid_constant__ TcW tw) {
+  using D = DimsTC<L>; using SM = SmemTC<L>; constexpr int TM = 128;
+  extern __shared__ __align__(1024) float sm_raw[];
+  TcCtx c = tc_begin<L>(sm_raw, tw);
+  const int tile = blockIdx.x;
+  const int es = a.e0 + tile * TM;
+  const int nvalid = min(TM, a.e1 - es);
+  tc_load_w<L>(c, tw.two0);
+  const Geom g = tc_geom<L>(a, w, c, es, nvalid);
+  {  // Bessel*u -> operand columns [0,32) (zero padded beyond num_bessels)
+    const float pref = sqrtf(2.0f / g.rc);
+    const float xr = g.r / g.rc;
+    for (int k4 = c.half * 16; k4 < c.half * 16 + 16; k4 += 4) {
+      float b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int n = k4 + i;
+        b[i] = n < w.B ? pref * sinf((float)(n + 1) * (3.14159265358979323846f * xr)) / g.r * g.u : 0.f;
+      }
+      op_put4<L>(c, k4, b[0], b[1], b[2], b[3]);
+    }
+  }
+  tc_mma<L>(c, 32, 64, TC_Z1);
+  tc_load_w<L>(c, tw.two1);
+  const float* w0 = w.two.w[0];
+  const float* wi = w0 + g.zi * H; const float* wj = w0 + (w.T + g.zj) * H;
+  tc_mlp_hidden_fwd<L>(c, tw.two2, tw.emb, [&](int n) { return __ldg(wi + n) + __ldg(wj + n); });
+  {
+    float* X0g = a.X[0] + (size_t)tile * S * TM;
+    tc_epi(c, TC_M, 64, [&](int n, float v0, float v1, float v2, float v3) {
+      v0 *= g.u; v1 *= g.u; v2 *= g.u; v3 *= g.u;
+      op_put4<L>(c, n, v0, v1, v2, v3);
+      X0g[(n + 0) * TM + c.m] = v0; X0g[(n + 1) * TM + c.m] = v1; X0g[(n + 2) * TM + c.m] = v2; X0g[(n + 3) * TM + c.m] = v3;
+    });
+  }
+  tc_mma<L>(c, 64, D::ENVW, TC_SCR);                 // embed linear
+  tc_load_w<L>(c, tw.layer[0].env);
+  {
+    float* W0g = a.W0 + (size_t)tile * D::ENVW * TM;
+    tc_epi(c, TC_SCR, D::ENVW, [&](int n, float v0, float v1, float v2, float v3) {
+      W0g[(n + 0) * TM + c.m] = v0; W0g[(n + 1) * TM + c.m] = v1; W0g[(n + 2) * TM + c.m] = v2; W0g[(n + 3) * TM + c.m] = v3;
+    });
+  }
+  tc_mma<L>(c, 64, D::ENVW, TC_SCR);                 // env linear of layer 0 (same operand x^0)
+  tc_env_to_ws<L>(c, TC_SCR);
+  __syncthreads();
+  tc_env_sum<L>(a, w, c, tile, es, nvalid, a.gamma[0]);
+  tc_end(c);
+}
+
+// layer-0 GEMM of a latent MLP: z1 = [x || s] W0 as two accumulating K-blocks (s first, then x)
+// in: weight block m0s requested, geometry published.  out: z1 in TMEM, m1 requested.
+template <int L, char KIND, bool FIRST, bool WANT_V>
+__device__ __forceinline__ void tc_latent_z1(const ChunkArgs& a, const LayerW& lw, const TcLayerW& tl, TcCtx& c, int tile, int k,
+                                             const float* __restrict__ Xg) {
+  tc_tp_forward<L, KIND, FIRST, WANT_V>(a, lw, c, tile, k);
+  tc_mma<L>(c, 64, 64, TC_Z1, 0);
+  tc_load_w<L>(c, tl.m0x);
+  op_load_rows64<L>(c, Xg);
+  tc_mma<L>(c, 64, 64, TC_Z1, 1);
+  tc_load_w<L>(c, tl.m1);
+}
+
+// ============================================================================================
+// FK
+// ============================================================================================
+template <int L, char KIND, bool FIRST>
+__global__ void __launch_bounds__(NT, 2) k_fk_tc(const __grid_constant__ ChunkArgs a, const __grid_constant__ ModelW w, const __grid_constant__ TcW tw, const int k) {
+  using D = DimsTC<L>; using SM = SmemTC<L>; constexpr int TM = 128;
   extern __shared__ __align__(1024) float sm_raw[];
   TcCtx c = tc_begin<L>(sm_raw, tw);
   const int tile = blockIdx.x;
@@ -591,31 +591,49 @@ __global__ void __launch_bounds__(NT, 1) k_t_tc(const __grid_constant__ ChunkArg
   const int nvalid = min(TM, a.e1 - es);
   const LayerW& lw = w.layer[k];
   const TcLayerW& tl = tw.layer[k];
-  tc_load_w<L>(c, tl.m0);
+  tc_load_w<L>(c, tl.m0s);
   const Geom g = tc_geom<L>(a, w, c, es, nvalid);
   const float* Xg = a.X[k] + (size_t)tile * S * TM;
-  op_load_rows64<L>(c, Xg);
   __syncthreads();
-  const float* Y_s = c.sm + SM::oY;
-  const int* c_s = reinterpret_cast<const int*>(c.sm + SM::oC);
+  tc_latent_z1<L, KIND, FIRST, true>(a, lw, tl, c, tile, k, Xg);
+  tc_mlp_hidden_fwd<L>(c, tl.m2, tw.layer[k + 1].env, NoBias());
   {
-    const int e = c.m, uh = c.half;
-    const float* gam = a.gamma[k] + (size_t)(c_s[e] - a.c0) * D::F;
-#pragma unroll 1
-    for (int i = 0; i < D::CPT; ++i) {
-      const int u = uh + D::CPH * i;
-      float Vin[TP::DIN], G[D::NSH], s[TP::N0];
-      tc_load_vin<L, FIRST, TP::DIN>(a, tile, k, e, u, Y_s, Vin);
-#pragma unroll
-      for (int lm = 0; lm < D::NSH; ++lm) G[lm] = gam[lm * U + u];
-      TP::template fwd<U>(Vin, G, lw.omega + u, nullptr, s);
-#pragma unroll
-      for (int q = 0; q < TP::N0; ++q) op_put1<L>(c, e, S + q * U + u, s[q]);
-    }
+    float* Xng = a.X[k + 1] + (size_t)tile * S * TM;
+    tc_epi(c, TC_M, 64, [&](int n, float v0, float v1, float v2, float v3) {
+      const float x0 = lw.a * Xg[(n + 0) * TM + c.m] + lw.b * v0 * g.u, x1 = lw.a * Xg[(n + 1) * TM + c.m] + lw.b * v1 * g.u;
+      const float x2 = lw.a * Xg[(n + 2) * TM + c.m] + lw.b * v2 * g.u, x3 = lw.a * Xg[(n + 3) * TM + c.m] + lw.b * v3 * g.u;
+      op_put4<L>(c, n, x0, x1, x2, x3);
+      Xng[(n + 0) * TM + c.m] = x0; Xng[(n + 1) * TM + c.m] = x1; Xng[(n + 2) * TM + c.m] = x2; Xng[(n + 3) * TM + c.m] = x3;
+    });
   }
-  tc_mlp_fwd_keep<L>(c, D::SIN, tl.m1, tl.m2, tw.ro0, NoBias());
-  // x^n = a x^{n-1} + b m u -> operand [0,64)
-  tc_epi(c, TC_M, 64, [&](int n, float v0, float v1, float v2, float v3) {
+  tc_mma<L>(c, 64, D::ENVW, TC_SCR);
+  tc_env_to_ws<L>(c, TC_SCR);
+  __syncthreads();
+  tc_env_sum<L>(a, w, c, tile, es, nvalid, a.gamma[k + 1]);
+  tc_end(c);
+}
+
+// ============================================================================================
+// T
+// ============================================================================================
+template <int L, bool FIRST>
+__global__ void __launch_bounds__(NT, 2) k_t_tc(const __grid_constant__ ChunkArgs a, const __grid_constant__ ModelW w, const __grid_constant__ TcW tw, const int k) {
+  using D = DimsTC<L>; using SM = SmemTC<L>; constexpr int TM = 128;
+  extern __shared__ __align__(1024) float sm_raw[];
+  TcCtx c = tc_begin<L>(sm_raw, tw);
+  const int tile = blockIdx.x;
+  const int es = a.e0 + tile * TM;
+  const int nvalid = min(TM, a.e1 - es);
+  const LayerW& lw = w.layer[k];
+  const TcLayerW& tl = tw.layer[k];
+  tc_load_w<L>(c, tl.m0s);
+  const Geom g = tc_geom<L>(a, w, c, es, nvalid);
+  const float* Xg = a.X[k] + (size_t)tile * S * TM;
+  __syncthreads();
+  const int* c_s = reinterpret_cast<const int*>(c.sm + SM::oC);
+  tc_latent_z1<L, 'A', FIRST, false>(a, lw, tl, c, tile, k, Xg);
+  tc_mlp_hidden_fwd<L>(c, tl.m2, tw.ro0, NoBias());
+  tc_epi(c, TC_M, 64, [&](int n, float v0, float v1, float v2, float v3) {        // x^n -> operand
     op_put4<L>(c, n, lw.a * Xg[(n + 0) * TM + c.m] + lw.b * v0 * g.u, lw.a * Xg[(n + 1) * TM + c.m] + lw.b * v1 * g.u,
                lw.a * Xg[(n + 2) * TM + c.m] + lw.b * v2 * g.u, lw.a * Xg[(n + 3) * TM + c.m] + lw.b * v3 * g.u);
   });
@@ -639,11 +657,11 @@ __global__ void __launch_bounds__(NT, 1) k_t_tc(const __grid_constant__ ChunkArg
     for (int i = 0; i < 16; i += 4) op_put4<L>(c, c.half * 16 + i, dz[i], dz[i + 1], dz[i + 2], dz[i + 3]);
     e_s[c.half * TM + c.m] = ee;
   }
-  tc_mma<L>(c, R, 64, TC_SCR);                       // dx^n = dz ro0^T   (barrier inside orders e_s)
+  tc_mma<L>(c, R, 64, TC_SCR);                       // dx^n = dz ro0^T   (the barrier inside orders e_s)
   tc_load_w<L>(c, tl.m2_b);
   if (c.half == 0) {
     const float ee = e_s[c.m] + e_s[TM + c.m];
-    e_s[2 * TM + c.m] = ee;                          // final E_e (read by thread 0 after the barrier below)
+    e_s[2 * TM + c.m] = ee;                          // final E_e (read after the next barrier)
     if (c.m < nvalid && a.edge_energy) a.edge_energy[es + c.m] = ee;
   }
   float* dXg = a.dX + (size_t)tile * S * TM;
@@ -667,7 +685,7 @@ __global__ void __launch_bounds__(NT, 1) k_t_tc(const __grid_constant__ ChunkArg
     __syncthreads();
     if (c.half == 0) a.du[(size_t)tile * TM + c.m] = dup + e_s[3 * TM + c.m];
   }
-  if (threadIdx.x == 0) {  // E_i raw sums (double), deterministic edge order
+  if (threadIdx.x == NT - 1) {  // E_i raw sums (double), deterministic edge order (not the MMA-issuing thread)
     const int cfirst = c_s[0];
     const bool contin = a.rowptr[cfirst] < es;
     int cur = cfirst; bool first = true; double acc = 0.0;
@@ -681,19 +699,8 @@ __global__ void __launch_bounds__(NT, 1) k_t_tc(const __grid_constant__ ChunkArg
     }
     if (first && contin) a.ecarry[tile] = acc; else a.esum[cur] = acc;
   }
-  tc_mlp_bwd_hidden<L>(c, tl.m1_b, tl.m0_b, NoBias());
-  tc_mma<L>(c, 64, D::SIN, TC_SCR);                  // dIN
-  {
-    float* DS_s = c.sm + SM::oWBH;                   // weights no longer needed
-    tc_epi(c, TC_SCR, D::SIN, [&](int n, float v0, float v1, float v2, float v3) {
-      if (n < S) {
-        dXg[(n + 0) * TM + c.m] += v0; dXg[(n + 1) * TM + c.m] += v1; dXg[(n + 2) * TM + c.m] += v2; dXg[(n + 3) * TM + c.m] += v3;
-      } else {
-        DS_s[(n - S + 0) * TM + c.m] = v0; DS_s[(n - S + 1) * TM + c.m] = v1; DS_s[(n - S + 2) * TM + c.m] = v2; DS_s[(n - S + 3) * TM + c.m] = v3;
-      }
-    });
-  }
-  __syncthreads();
+  tc_mlp_bwd_hidden<L>(c, tl.m1_b, tl.m0_bx, NoBias());
+  tc_din<L>(c, tl, dXg);
   float dYp[D::NSH];
   tc_tp_backward<L, 'A', FIRST, false>(a, lw, c, tile, k, es, nvalid, nullptr, FIRST ? nullptr : a.dV[k & 1], a.dgamma[k], dYp);
   for (int i = threadIdx.x; i < D::NSH * TM; i += NT) c.sm[SM::oDY + i] = 0.f;
@@ -706,8 +713,8 @@ __global__ void __launch_bounds__(NT, 1) k_t_tc(const __grid_constant__ ChunkArg
 // BK
 // ============================================================================================
 template <int L, char KIND, bool FIRST>
-__global__ void __launch_bounds__(NT, 1) k_bk_tc(const __grid_constant__ ChunkArgs a, const __grid_constant__ ModelW w, const __grid_constant__ TcW tw, const int k) {
-  using D = DimsTC<L>; using SM = SmemTC<L>; using TP = tpgen::TP<L, KIND>; constexpr int TM = 128;
+__global__ void __launch_bounds__(NT, 2) k_bk_tc(const __grid_constant__ ChunkArgs a, const __grid_constant__ ModelW w, const __grid_constant__ TcW tw, const int k) {
+  using D = DimsTC<L>; using SM = SmemTC<L>; constexpr int TM = 128;
   extern __shared__ __align__(1024) float sm_raw[];
   TcCtx c = tc_begin<L>(sm_raw, tw);
   const int tile = blockIdx.x;
@@ -720,33 +727,16 @@ __global__ void __launch_bounds__(NT, 1) k_bk_tc(const __grid_constant__ ChunkAr
   op_load_rows64<L>(c, a.X[k + 1] + (size_t)tile * S * TM);
   __syncthreads();
   float* dXg = a.dX + (size_t)tile * S * TM;
-  tc_phase2<L>(a, w, c, k + 1, tile, tw.layer[k + 1].env_b, false);
-  tc_load_w<L>(c, tl.m0);
-  // dX += (dw env^T): keep the complete dx^{k+1} of this thread's columns in registers? -> write back to global
-  tc_epi(c, TC_SCR, 64, [&](int n, float v0, float v1, float v2, float v3) {
+  tc_phase2<L>(a, w, c, k + 1, tw.layer[k + 1].env_b);
+  tc_mma<L>(c, D::ENVW, 64, TC_SCR);                  // dw env^T
+  tc_load_w<L>(c, tl.m0s);
+  tc_epi(c, TC_SCR, 64, [&](int n, float v0, float v1, float v2, float v3) {   // dX now holds the complete dx^{k+1}
     dXg[(n + 0) * TM + c.m] += v0; dXg[(n + 1) * TM + c.m] += v1; dXg[(n + 2) * TM + c.m] += v2; dXg[(n + 3) * TM + c.m] += v3;
   });
-  // ---- recompute layer k forward
+  // ---- recompute layer k forward (z1, z2, m stay in TMEM)
   const float* Xg = a.X[k] + (size_t)tile * S * TM;
-  op_load_rows64<L>(c, Xg);
-  const float* Y_s = c.sm + SM::oY;
-  const int* c_s = reinterpret_cast<const int*>(c.sm + SM::oC);
-  {
-    const int e = c.m, uh = c.half;
-    const float* gam = a.gamma[k] + (size_t)(c_s[e] - a.c0) * D::F;
-#pragma unroll 1
-    for (int i = 0; i < D::CPT; ++i) {
-      const int u = uh + D::CPH * i;
-      float Vin[TP::DIN], G[D::NSH], s[TP::N0];
-      tc_load_vin<L, FIRST, TP::DIN>(a, tile, k, e, u, Y_s, Vin);
-#pragma unroll
-      for (int lm = 0; lm < D::NSH; ++lm) G[lm] = gam[lm * U + u];
-      tpgen::TP<L, 'A'>::template fwd<U>(Vin, G, nullptr, nullptr, s);
-#pragma unroll
-      for (int q = 0; q < TP::N0; ++q) op_put1<L>(c, e, S + q * U + u, s[q]);
-    }
-  }
-  tc_mlp_fwd_keep<L>(c, D::SIN, tl.m1, tl.m2, tl.m2_b, NoBias());
+  tc_latent_z1<L, KIND, FIRST, false>(a, lw, tl, c, tile, k, Xg);
+  tc_mlp_hidden_fwd<L>(c, tl.m2, tl.m2_b, NoBias());
   {
     float dup = 0.f;
     for (int c0 = c.half * 32; c0 < c.half * 32 + 32; c0 += 16) {
@@ -768,19 +758,8 @@ __global__ void __launch_bounds__(NT, 1) k_bk_tc(const __grid_constant__ ChunkAr
     __syncthreads();
     if (c.half == 0) a.du[(size_t)tile * TM + c.m] += dup + e_s[c.m];
   }
-  tc_mlp_bwd_hidden<L>(c, tl.m1_b, tl.m0_b, NoBias());
-  tc_mma<L>(c, 64, D::SIN, TC_SCR);
-  {
-    float* DS_s = c.sm + SM::oWBH;
-    tc_epi(c, TC_SCR, D::SIN, [&](int n, float v0, float v1, float v2, float v3) {
-      if (n < S) {
-        dXg[(n + 0) * TM + c.m] += v0; dXg[(n + 1) * TM + c.m] += v1; dXg[(n + 2) * TM + c.m] += v2; dXg[(n + 3) * TM + c.m] += v3;
-      } else {
-        DS_s[(n - S + 0) * TM + c.m] = v0; DS_s[(n - S + 1) * TM + c.m] = v1; DS_s[(n - S + 2) * TM + c.m] = v2; DS_s[(n - S + 3) * TM + c.m] = v3;
-      }
-    });
-  }
-  __syncthreads();
+  tc_mlp_bwd_hidden<L>(c, tl.m1_b, tl.m0_bx, NoBias());
+  tc_din<L>(c, tl, dXg);
   float dYp[D::NSH];
   tc_tp_backward<L, KIND, FIRST, true>(a, lw, c, tile, k, es, nvalid, a.dV[(k + 1) & 1], FIRST ? nullptr : a.dV[k & 1], a.dgamma[k], dYp);
   tc_dy_store<L, false>(a, c, tile, dYp, FIRST);
@@ -791,28 +770,16 @@ __global__ void __launch_bounds__(NT, 1) k_bk_tc(const __grid_constant__ ChunkAr
 // B0
 // ============================================================================================
 template <int L>
-__global__ void __launch_bounds__(NT, 1) k_b0_tc(const __grid_constant__ ChunkArgs a, const __grid_constant__ ModelW w, const __grid_constant__ TcW tw) {
+__global__ void __launch_bounds__(NT, 2) k_b0_tc(const __grid_constant__ ChunkArgs a, const __grid_constant__ ModelW w, const __grid_constant__ TcW tw) {
   using D = DimsTC<L>; using SM = SmemTC<L>; constexpr int TM = 128;
   extern __shared__ __align__(1024) float sm_raw[];
   TcCtx c = tc_begin<L>(sm_raw, tw);
   const int tile = blockIdx.x;
   const int es = a.e0 + tile * TM;
   const int nvalid = min(TM, a.e1 - es);
-  tc_load_w<L>(c, tw.layer[0].env);
-  const Geom g = tc_geom<L>(a, w, c, es, nvalid);
-  op_load_rows64<L>(c, a.X[0] + (size_t)tile * S * TM);
-  __syncthreads();
-  float* dXg = a.dX + (size_t)tile * S * TM;
-  tc_phase2<L>(a, w, c, 0, tile, tw.envemb_b, true);     // dx0 += dw env0^T + dw0 emb^T  (one GEMM, K = 2*ENVW)
   tc_load_w<L>(c, tw.two0);
-  float dx0[32];                                         // complete dx^0 of this thread's 32 columns
-  for (int c0 = 0; c0 < 32; c0 += 16) {
-    float v[16];
-    tc_ld16(c, TC_SCR + c.half * 32 + c0, v);
-#pragma unroll
-    for (int i = 0; i < 16; ++i) dx0[c0 + i] = v[i] + dXg[(c.half * 32 + c0 + i) * TM + c.m];
-  }
-  // ---- recompute the two-body MLP (Bessel operand), keep z1, z2, m0 in TMEM
+  const Geom g = tc_geom<L>(a, w, c, es, nvalid);
+  // ---- recompute the two-body MLP first: z1, z2, m0 stay in TMEM
   float bes[MAXB], dbes[MAXB];
   {
     const float pref = sqrtf(2.0f / g.rc);
@@ -827,27 +794,46 @@ __global__ void __launch_bounds__(NT, 1) k_b0_tc(const __grid_constant__ ChunkAr
         dbes[n] = pref * (kn / g.rc * cs / g.r - sn / (g.r * g.r));
       } else { bes[n] = 0.f; dbes[n] = 0.f; }
     }
-    for (int k4 = c.half * 16; k4 < c.half * 16 + 16; k4 += 4) {
-      float b[4];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) b[i] = (k4 + i) < MAXB ? bes[(k4 + i) & (MAXB - 1)] * g.u : 0.f;
-      op_put4<L>(c, k4, b[0], b[1], b[2], b[3]);
+    for (int k4 = 0; k4 < 16; k4 += 4) {
+      if (c.half == 0) op_put4<L>(c, k4, bes[k4] * g.u, bes[k4 + 1] * g.u, bes[k4 + 2] * g.u, bes[k4 + 3] * g.u);
+      else op_put4<L>(c, 16 + k4, 0.f, 0.f, 0.f, 0.f);
     }
   }
+  tc_mma<L>(c, 32, 64, TC_Z1);
+  tc_load_w<L>(c, tw.two1);
   const float* w0 = w.two.w[0];
   const float* wi = w0 + g.zi * H; const float* wj = w0 + (w.T + g.zj) * H;
   auto bias = [&](int n) { return __ldg(wi + n) + __ldg(wj + n); };
-  tc_mlp_fwd_keep<L>(c, 32, tw.two1, tw.two2, tw.two2_b, bias);
+  tc_mlp_hidden_fwd<L>(c, tw.two2, tw.layer[0].env, bias);
+  // ---- phase 2 of layer 0 and the embed backward: dx0 = dX + dw env0^T + dw0 emb^T
+  op_load_rows64<L>(c, a.X[0] + (size_t)tile * S * TM);
+  tc_phase2<L>(a, w, c, 0, tw.layer[0].env_b);
+  tc_mma<L>(c, D::ENVW, 64, TC_SCR, 0);
+  tc_load_w<L>(c, tw.emb_b);
+  {
+    const float* W0g = a.W0 + (size_t)tile * D::ENVW * TM;    // dw0 (written by the layer-0 TP backward)
+    for (int n = c.half * 32; n < c.half * 32 + 32; n += 4)
+      op_put4<L>(c, n, W0g[(n + 0) * TM + c.m], W0g[(n + 1) * TM + c.m], W0g[(n + 2) * TM + c.m], W0g[(n + 3) * TM + c.m]);
+  }
+  tc_mma<L>(c, D::ENVW, 64, TC_SCR, 1);
+  tc_load_w<L>(c, tw.two2_b);
+  const float* dXg = a.dX + (size_t)tile * S * TM;
   float du_tot;
   {
     float dup = 0.f;
-    for (int c0 = 0; c0 < 32; c0 += 16) {
-      float mv[16], v[16];
-      tc_ld16(c, TC_M + c.half * 32 + c0, mv);
+    for (int c0 = c.half * 32; c0 < c.half * 32 + 32; c0 += 16) {
+      float v[16], mv[16];
+      tc_ld16(c, TC_SCR + c0, v);
+      tc_ld16(c, TC_M + c0, mv);
 #pragma unroll
-      for (int i = 0; i < 16; ++i) { dup += dx0[c0 + i] * mv[i]; v[i] = dx0[c0 + i] * g.u; }
+      for (int i = 0; i < 16; ++i) {
+        const float dx0 = v[i] + dXg[(c0 + i) * TM + c.m];
+        dup += dx0 * mv[i];
+        v[i] = dx0 * g.u;
+      }
 #pragma unroll
-      for (int i = 0; i < 16; i += 4) op_put4<L>(c, c.half * 32 + c0 + i, v[i], v[i + 1], v[i + 2], v[i + 3]);
+      for (int i = 0; i < 16; i += 4) op_put4<L>(c, c0 + i, v[i], v[i + 1], v[i + 2], v[i + 3]);
     }
     float* e_s = c.sm + SM::oE;
     e_s[c.half * TM + c.m] = dup;
@@ -879,7 +865,7 @@ __global__ void __launch_bounds__(NT, 1) k_b0_tc(const __grid_constant__ ChunkAr
     gz = dr * g.z + (qz - g.z * nq) * ir;
     if (c.m >= nvalid) { gx = gy = gz = 0.f; }
   }
-  __syncthreads();                                       // all TMEM / operand reads done before G3/VR overwrite OPH
+  __syncthreads();                                       // operand reads (MMA) are complete; reuse OPH
   if (c.half == 0) {
     const int t = c.m;
     G3[0 * TM + t] = gx; G3[1 * TM + t] = gy; G3[2 * TM + t] = gz;
@@ -902,19 +888,20 @@ __global__ void __launch_bounds__(NT, 1) k_b0_tc(const __grid_constant__ ChunkAr
   {
     const int t = threadIdx.x;
     const int* c_s = reinterpret_cast<const int*>(c.sm + SM::oC);
-    if (t < 3) {
+    if (t >= 128 && t < 131) {
+      const int q = t - 128;
       int cur = c_s[0]; double acc = 0.0;
       for (int e = 0; e < nvalid; ++e) {
         const int cc = c_s[e];
         if (cc != cur) {
-          atomicAdd(a.facc + 3 * (size_t)a.ilist[cur] + t, (unsigned long long)__double2ll_rn(acc * FIX_SCALE));
+          atomicAdd(a.facc + 3 * (size_t)a.ilist[cur] + q, (unsigned long long)__double2ll_rn(acc * FIX_SCALE));
           cur = cc; acc = 0.0;
         }
-        acc += (double)G3[t * TM + e];
+        acc += (double)G3[q * TM + e];
       }
-      atomicAdd(a.facc + 3 * (size_t)a.ilist[cur] + t, (unsigned long long)__double2ll_rn(acc * FIX_SCALE));
-    } else if (t >= 32 && t < 38 && a.vacc) {
-      const int q = t - 32;
+      atomicAdd(a.facc + 3 * (size_t)a.ilist[cur] + q, (unsigned long long)__double2ll_rn(acc * FIX_SCALE));
+    } else if (t >= 160 && t < 166 && a.vacc) {
+      const int q = t - 160;
       double acc = 0.0;
       for (int e = 0; e < nvalid; ++e) acc += (double)VR[q * TM + e];
       atomicAdd(a.vacc + q, (unsigned long long)__double2ll_rn(acc * VIR_SCALE));

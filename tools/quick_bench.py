@@ -19,6 +19,8 @@ def main():
     L = int(sys.argv[2]) if len(sys.argv) > 2 else 1
     nl = int(sys.argv[3]) if len(sys.argv) > 3 else 2
     chunk = sys.argv[4] if len(sys.argv) > 4 else "1048576"
+    gemm = sys.argv[5] if len(sys.argv) > 5 else "ffma"
+    prec = sys.argv[6] if len(sys.argv) > 6 else "strict"
     pos, types, cell = H.fcc_box(ncell)
     t0 = time.time()
     atoms = H.make_single_rank(types, pos, cell, [True] * 3, 6.0)
@@ -31,6 +33,10 @@ def main():
     pair = PairAllegroB200(device=0, debug_mode=False)
     pair.coeff(["*", "*", "/tmp/qb/m.alg", "Ag"], 1)
     pair.handle.set_option("chunk_edges", chunk)
+    pair.handle.set_option("gemm", gemm)
+    if gemm == "tc":
+        pair.handle.set_option("precision", prec)
+    pair.handle.set_option("profile", "1")
     for it in range(4):
         atoms.f[:] = 0
         t0 = time.time()
@@ -39,6 +45,7 @@ def main():
         tm = pair.handle.timings()
         print("iter %d: wall %.1f ms  device: edges %.2f ms, network %.2f ms, finalize %.2f ms  -> %.3f Matom-steps/s (device)  eng %.6f" %
               (it, dt * 1e3, tm[0], tm[1], tm[2], atoms.nlocal / (tm.sum() * 1e-3) / 1e6, pair.eng_vdwl))
+    print("kernel ms:", dict(zip(["F0", "FK", "T", "BK", "B0", "fixup"], np.round(pair.handle.stats("kernel_ms", 6), 2))))
 
 
 if __name__ == "__main__":
