@@ -336,6 +336,9 @@ def run_ours(args):
     h = pair.handle
     if args.chunk_edges:
         h.set_option("chunk_edges", str(args.chunk_edges))
+    h.set_option("gemm", args.gemm)           # tc: tcgen05 tensor cores (default for l_max=1) | ffma: FP32 pipe
+    if args.gemm == "tc":
+        h.set_option("precision", args.precision)
     lib = capi.load_library()
 
     # ---- device-resident inputs (the Kokkos-style entry: alg_compute_device)
@@ -428,10 +431,16 @@ def run_ours(args):
         except Exception:
             pass
     sm_clock = (clocks.get("sm_mhz") or 1965.0) * 1e6
-    roofline = {"bound": "tensor", "kernel": "k_" + dom_name.lower(), "achieved": achieved, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
+    if args.gemm == "tc":
+        note = ("dense contractions on tcgen05 (kind::tf32, TMEM accumulators, TMA-fed weights); precision=%s -> %d TF32 MMA pass(es) per GEMM, "
+                "i.e. executed tensor flops = %dx the algorithmic GEMM flops; peak quoted is the measured dense bf16 figure (TF32 dense peak is half of it)"
+                % (args.precision, 3 if args.precision == "strict" else 1, 3 if args.precision == "strict" else 1))
+    else:
+        note = ("FP32-pipe path (gemm=ffma): fp32 pipe peak at the sampled clock = %.1f TFLOP/s, frac_of_fp32_pipe = %.3f"
+                % (148 * 128 * 2 * sm_clock / 1e12, achieved / (148 * 128 * 2 * sm_clock / 1e12)))
+    roofline = {"bound": "tensor", "kernel": "k_" + dom_name.lower() + ("_tc" if args.gemm == "tc" else ""), "achieved": achieved, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
                 "frac": achieved / peaks["bf16_sustained"], "traffic": traffic, "peak_source": peaks["source"] + " bf16 sustained (MEASURED_PEAKS.json)" if peaks["source"] == "measured" else "fallback (B200_PROFILING.md)",
-                "note": "strict-fp32 path runs on the FP32 FMA pipe (no fp32 tensor-core mode exists); fp32 pipe peak at the sampled clock = %.1f TFLOP/s, frac_of_fp32_pipe = %.3f"
-                        % (148 * 128 * 2 * sm_clock / 1e12, achieved / (148 * 128 * 2 * sm_clock / 1e12)),
+                "note": note,
                 "launch_ms": dur * 1e3, "launches_per_step": float(kn[dom]),
                 "kernel_ms_per_step": {names[i]: float(kms[i]) for i in range(6)},
                 "algorithmic_flops_per_edge": {k: float(v) for k, v in fam.items()}}
@@ -488,7 +497,7 @@ def run_ours(args):
                                        % (NCELL, nl, E), "domains": grid, "atoms_total": total_atoms, "ghosts_rank0": ng,
                            "l2_policy": "inputs larger than L2 (neighbour list + per-edge state >> 126 MB); no explicit flush",
                            "halo": "NCCL p2p forward x / reverse f every step" if world > 1 else "self-image halo on device every step",
-                           "chunk_edges": int(args.chunk_edges or 1 << 20)},
+                           "chunk_edges": int(args.chunk_edges or 1 << 20), "gemm": args.gemm, "precision": args.precision},
                 "clocks": clocks, "gpu_launches": launches_per_step * K,
                 "e2e": {"value": e2e_val, "unit": "Matom-steps/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                         "ms_per_step": ms_e2e / K, "neigh_upload_every": NEIGH_EVERY},
@@ -508,6 +517,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--chunk-edges", type=int, default=0)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--gemm", default="tc", choices=["tc", "ffma"])
+    ap.add_argument("--precision", default="strict", choices=["strict", "tf32"], help="strict = 3xTF32 (fp32-level), tf32 = fast mode")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

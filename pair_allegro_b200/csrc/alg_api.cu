@@ -499,6 +499,8 @@ static int setup_model(alg_handle* h) {
     }
     tw.passes = 3;
     CK(h->pipe_tc->init());
+    // default: tensor-core pipeline in strict (3xTF32) mode whenever the model is supported
+    h->use_tc = true; h->pipe = h->pipe_tc; h->pinfo = h->pipe->info(h->nl);
   }
   h->tensors.clear();
   return ALG_OK;
