@@ -497,7 +497,7 @@ def run_ours(args):
                                        % (NCELL, nl, E), "domains": grid, "atoms_total": total_atoms, "ghosts_rank0": ng,
                            "l2_policy": "inputs larger than L2 (neighbour list + per-edge state >> 126 MB); no explicit flush",
                            "halo": "NCCL p2p forward x / reverse f every step" if world > 1 else "self-image halo on device every step",
-                           "chunk_edges": int(args.chunk_edges or 1 << 20), "gemm": args.gemm, "precision": args.precision},
+                           "chunk_edges": int(args.chunk_edges or 1 << 21), "gemm": args.gemm, "precision": args.precision},
                 "clocks": clocks, "gpu_launches": launches_per_step * K,
                 "e2e": {"value": e2e_val, "unit": "Matom-steps/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                         "ms_per_step": ms_e2e / K, "neigh_upload_every": NEIGH_EVERY},

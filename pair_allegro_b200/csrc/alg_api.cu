@@ -103,7 +103,7 @@ struct alg_handle {
   bool have_map = false;
   // options
   bool filter_le = true, keep_edges = false, debug = false;
-  long chunk_edges = 1 << 20;
+  long chunk_edges = 1 << 21;
   // per-step scratch
   DevBuf d_x, d_type, d_ilist, d_numneigh, d_cand, d_first, d_cnt, d_rowptr, d_scan_tmp;
   DevBuf d_mtype, d_edge_j, d_edge_c, d_rvec, d_esum, d_facc, d_vacc, d_forces, d_eall, d_red, d_edge_index, d_edge_energy, d_edge_grad, d_eatom_out;

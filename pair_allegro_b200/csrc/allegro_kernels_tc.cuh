@@ -63,13 +63,23 @@ template <int L> struct SmemTC {
   static constexpr int oC = oU + TM;                   // int
   static constexpr int oZZ = oC + TM;                  // int
   static constexpr int oE = oZZ + TM;                  // 4*TM floats: per-half partials, E_e, du partial
-  static constexpr int oBAR = oE + 4 * TM;             // 2 mbarriers + tmem pointer (8 floats)
+  static constexpr int GSROWS = 16;                    // staged per-centre rows (Gamma / dGamma) of the tile's centres
+  static constexpr int oGS = oE + 4 * TM;
+  static constexpr int oBAR = oGS + GSROWS * D::F;     // 2 mbarriers + tmem pointer (8 floats)
   static constexpr int TOTAL = oBAR + 8;
   static constexpr size_t BYTES = (size_t)TOTAL * sizeof(float) + 1024;   // + alignment slack
   static_assert(L == 1, "tensor-core pipeline: shared-memory plan is sized for l_max = 1");
   static_assert(D::ENVW == 64 && D::SIN == 128, "block plan below assumes l_max = 1 widths");
   static_assert(D::WS * TM <= OPF + 2 * WBF && D::DGS * TM <= 2 * OPF, "staging buffers alias the operand / weight regions");
   static_assert(BYTES <= 113 * 1024, "two CTAs per SM");
+};
+
+// per-centre rows (Gamma_k or dGamma_k) of the centres touched by this tile: staged in shared memory
+// when the tile spans <= GSROWS consecutive centre slots (the normal case), else read from global
+struct RowSrc {
+  const float* base;   // staged: smem row of centre cmin ; else global row of centre c0
+  int c_origin;        // cmin or c0
+  __device__ __forceinline__ const float* row(int centre, int F) const { return base + (size_t)(centre - c_origin) * F; }
 };
 
 struct TcCtx {
@@ -132,12 +142,17 @@ template <int L> __device__ __forceinline__ void tc_mma(TcCtx& c, int K, int N, 
     const float* Wh = c.sm + SM::oWBH; const float* Wl = c.sm + SM::oWBL;
     const uint32_t idesc = umma::make_idesc_tf32(N);
     uint32_t acc = accumulate;
+    const uint64_t dAh = umma::make_desc_k_sw128(Ah), dAl = umma::make_desc_k_sw128(Al);
+    const uint64_t dWh = umma::make_desc_k_sw128(Wh), dWl = umma::make_desc_k_sw128(Wl);
+    const uint32_t wpan = (uint32_t)(N * 32 * 4) >> 4;             // weight panel stride in 16-byte units
     for (int p = 0; p < c.passes; ++p) {
-      const float* Ap = (c.passes == 3 && p == 0) ? Al : Ah;       // lo*hi, hi*lo, hi*hi
-      const float* Wp = (c.passes == 3 && p == 1) ? Wl : Wh;
+      const uint64_t da0 = (c.passes == 3 && p == 0) ? dAl : dAh;  // lo*hi, hi*lo, hi*hi
+      const uint64_t db0 = (c.passes == 3 && p == 1) ? dWl : dWh;
+#pragma unroll 4
       for (int ks = 0; ks < K / 8; ++ks) {
-        const uint64_t da = umma::make_desc_k_sw128(Ap + (ks >> 2) * (128 * 32) + (ks & 3) * 8);
-        const uint64_t db = umma::make_desc_k_sw128(Wp + (ks >> 2) * (N * 32) + (ks & 3) * 8);
+        // start-address field is in 16-byte units: panel stride 128*32*4 B = 1024 units, 8 k = 32 B = 2 units
+        const uint64_t da = da0 + (uint64_t)((ks >> 2) * 1024 + (ks & 3) * 2);
+        const uint64_t db = db0 + (uint64_t)((ks >> 2) * wpan + (ks & 3) * 2);
         umma::mma_tf32(c.tmem + dcol, da, db, idesc, acc);
         acc = 1;
       }
@@ -153,6 +168,16 @@ template <int L> __device__ __forceinline__ void tc_mma(TcCtx& c, int K, int N, 
 // this thread's row m, 16 columns starting at absolute TMEM column col
 __device__ __forceinline__ void tc_ld16(const TcCtx& c, uint32_t col, float* v) {
   umma::tmem_ld16(c.tmem + ((uint32_t)(c.q * 32) << 16) + col, v);
+}
+// two 16-column loads from different TMEM regions in flight together
+__device__ __forceinline__ void tc_ld16x2(const TcCtx& c, uint32_t colA, float* a, uint32_t colB, float* b) {
+  uint32_t ra[16], rb[16];
+  const uint32_t base = c.tmem + ((uint32_t)(c.q * 32) << 16);
+  umma::tmem_ld16_nowait(base + colA, ra);
+  umma::tmem_ld16_nowait(base + colB, rb);
+  umma::tmem_ld_wait();
+#pragma unroll
+  for (int i = 0; i < 16; ++i) { a[i] = __uint_as_float(ra[i]); b[i] = __uint_as_float(rb[i]); }
 }
 // write 4 consecutive k (k4 % 4 == 0) of row m into the A operand (hi [+ lo])
 template <int L> __device__ __forceinline__ void op_put4(const TcCtx& c, int k4, float a, float b, float d, float e) {
@@ -171,18 +196,37 @@ template <int L> __device__ __forceinline__ void op_put1(const TcCtx& c, int row
 }
 // epilogue over this thread's half of NC columns: fn(n, v0..v3) for 4 consecutive columns n..n+3
 template <class Fn> __device__ __forceinline__ void tc_epi(const TcCtx& c, uint32_t dcol, int NC, Fn fn) {
-  const int w = NC / 2;
-  for (int c0 = c.half * w; c0 < (c.half + 1) * w; c0 += 16) {
-    float v[16];
-    tc_ld16(c, dcol + c0, v);
+  // every epilogue of this pipeline covers 64 columns: this thread's half = 32 columns, one TMEM load
+  const int c0 = c.half * 32;
+  float v[32];
+  umma::tmem_ld32(c.tmem + ((uint32_t)(c.q * 32) << 16) + dcol + c0, v);
 #pragma unroll
-    for (int i = 0; i < 16; i += 4) fn(c0 + i, v[i], v[i + 1], v[i + 2], v[i + 3]);
-  }
+  for (int i = 0; i < 32; i += 4) fn(c0 + i, v[i], v[i + 1], v[i + 2], v[i + 3]);
+  (void)NC;
 }
 // load a 64-row tile-SoA array (x^k, dX) of this tile into operand columns [0,64)
 template <int L> __device__ __forceinline__ void op_load_rows64(const TcCtx& c, const float* __restrict__ g /*tile base [64][128]*/) {
   for (int n = c.half * 32; n < c.half * 32 + 32; n += 4)
     op_put4<L>(c, n, g[(n + 0) * 128 + c.m], g[(n + 1) * 128 + c.m], g[(n + 2) * 128 + c.m], g[(n + 3) * 128 + c.m]);
+}
+
+// all threads; c_s must be published.  Ends with a barrier.
+template <int L> __device__ __forceinline__ RowSrc tc_stage_rows(const TcCtx& c, const float* __restrict__ gbase, int c0, int nvalid) {
+  using D = DimsTC<L>; using SM = SmemTC<L>;
+  const int* c_s = reinterpret_cast<const int*>(c.sm + SM::oC);
+  const int cmin = c_s[0];
+  const int span = c_s[nvalid - 1] - cmin + 1;
+  RowSrc r;
+  if (span <= SM::GSROWS) {
+    float* GS = c.sm + SM::oGS;
+    const float4* src = reinterpret_cast<const float4*>(gbase + (size_t)(cmin - c0) * D::F);
+    for (int i = threadIdx.x; i < span * D::F / 4; i += NT) reinterpret_cast<float4*>(GS)[i] = src[i];
+    r.base = GS; r.c_origin = cmin;
+  } else {
+    r.base = gbase; r.c_origin = c0;
+  }
+  __syncthreads();
+  return r;
 }
 
 // geometry of row m (both halves compute, half 0 publishes Y_s, u_s, c_s, zz_s)
@@ -259,12 +303,12 @@ constexpr int TB = 4;
 
 // forward: s -> operand columns [0, N0*U) (the "s" K-block); optionally V^{k+1} -> global
 template <int L, char KIND, bool FIRST, bool WANT_V>
-__device__ __forceinline__ void tc_tp_forward(const ChunkArgs& a, const LayerW& lw, const TcCtx& c, int tile, int k) {
+__device__ __forceinline__ void tc_tp_forward(const ChunkArgs& a, const LayerW& lw, const TcCtx& c, int tile, int k, const RowSrc& gsrc) {
   using D = DimsTC<L>; using SM = SmemTC<L>; using TP = tpgen::TP<L, KIND>; using TPA = tpgen::TP<L, 'A'>; constexpr int TM = 128;
   const float* Y_s = c.sm + SM::oY;
   const int* c_s = reinterpret_cast<const int*>(c.sm + SM::oC);
   const int e = c.m, uh = c.half;
-  const float* gam = a.gamma[k] + (size_t)(c_s[e] - a.c0) * D::F;
+  const float* gam = gsrc.row(c_s[e], D::F);
   float* Vng = WANT_V ? a.V[k + 1] + (size_t)tile * U * TP::DOUT * TM : nullptr;
 #pragma unroll 1
   for (int i0 = 0; i0 < D::CPT; i0 += TB) {
@@ -297,7 +341,7 @@ __device__ __forceinline__ void tc_tp_forward(const ChunkArgs& a, const LayerW& 
 template <int L, char KIND, bool FIRST, bool HAS_DVOUT>
 __device__ __forceinline__ void tc_tp_backward(const ChunkArgs& a, const LayerW& lw, const TcCtx& c, int tile, int k, int es, int nvalid,
                                                const float* __restrict__ dVnext, float* __restrict__ dVprev,
-                                               float* __restrict__ dgamma_out, float* dYp) {
+                                               float* __restrict__ dgamma_out, float* dYp, const RowSrc& gsrc) {
   using D = DimsTC<L>; using SM = SmemTC<L>; using TP = tpgen::TP<L, KIND>; constexpr int TM = 128;
   const int t = threadIdx.x;
   const float* DS_s = c.sm + SM::oWBH;
@@ -305,7 +349,7 @@ __device__ __forceinline__ void tc_tp_backward(const ChunkArgs& a, const LayerW&
   const float* Y_s = c.sm + SM::oY;
   const int* c_s = reinterpret_cast<const int*>(c.sm + SM::oC);
   const int e = c.m, uh = c.half;
-  const float* gam = a.gamma[k] + (size_t)(c_s[e] - a.c0) * D::F;
+  const float* gam = gsrc.row(c_s[e], D::F);
   float* W0g = a.W0 + (size_t)tile * D::ENVW * TM;
   if (FIRST) {
 #pragma unroll
@@ -425,8 +469,7 @@ __device__ __forceinline__ void tc_mlp_bwd_hidden(TcCtx& c, const TcMat& w1_b, c
   tc_load_w<L>(c, w1_b);
   for (int c0 = c.half * 32; c0 < c.half * 32 + 32; c0 += 16) {
     float v[16], z[16];
-    tc_ld16(c, TC_SCR + c0, v);
-    tc_ld16(c, TC_Z2 + c0, z);
+    tc_ld16x2(c, TC_SCR + c0, v, TC_Z2 + c0, z);
 #pragma unroll
     for (int i = 0; i < 16; i += 4) {
       float d0, d1, d2, d3;
@@ -438,8 +481,7 @@ __device__ __forceinline__ void tc_mlp_bwd_hidden(TcCtx& c, const TcMat& w1_b, c
   tc_load_w<L>(c, next);
   for (int c0 = c.half * 32; c0 < c.half * 32 + 32; c0 += 16) {
     float v[16], z[16];
-    tc_ld16(c, TC_SCR + c0, v);
-    tc_ld16(c, TC_Z1 + c0, z);
+    tc_ld16x2(c, TC_SCR + c0, v, TC_Z1 + c0, z);
 #pragma unroll
     for (int i = 0; i < 16; i += 4) {
       float d0, d1, d2, d3;
@@ -470,14 +512,14 @@ __device__ __forceinline__ void tc_din(TcCtx& c, const TcLayerW& tl, float* __re
 // phase 2 of layer kk.  In: x^kk in operand [0,64), weight block env_kk requested.
 // Out: dw (operand [0,64)), DY_s = d/dY of the environment sum; requests `next`.
 template <int L>
-__device__ __forceinline__ void tc_phase2(const ChunkArgs& a, const ModelW& w, TcCtx& c, int kk, const TcMat& next) {
+__device__ __forceinline__ void tc_phase2(const ChunkArgs& a, const ModelW& w, TcCtx& c, int kk, const TcMat& next, const RowSrc& dsrc) {
   using D = DimsTC<L>; using SM = SmemTC<L>; constexpr int TM = 128;
   tc_mma<L>(c, 64, D::ENVW, TC_SCR);
   tc_load_w<L>(c, next);
   const float* Y_s = c.sm + SM::oY;
   const int* c_s = reinterpret_cast<const int*>(c.sm + SM::oC);
   float* DY_s = c.sm + SM::oDY;
-  const float* dgam = a.dgamma[kk] + (size_t)(c_s[c.m] - a.c0) * D::F;
+  const float* dgam = dsrc.row(c_s[c.m], D::F);
   float dYp[D::NSH];
 #pragma unroll
   for (int lm = 0; lm < D::NSH; ++lm) dYp[lm] = 0.f;
@@ -569,8 +611,8 @@ __global__ void __launch_bounds__(NT, 2) k_f0_tc(const __grid_constant__ ChunkAr
 // in: weight block m0s requested, geometry published.  out: z1 in TMEM, m1 requested.
 template <int L, char KIND, bool FIRST, bool WANT_V>
 __device__ __forceinline__ void tc_latent_z1(const ChunkArgs& a, const LayerW& lw, const TcLayerW& tl, TcCtx& c, int tile, int k,
-                                             const float* __restrict__ Xg) {
-  tc_tp_forward<L, KIND, FIRST, WANT_V>(a, lw, c, tile, k);
+                                             const float* __restrict__ Xg, const RowSrc& gsrc) {
+  tc_tp_forward<L, KIND, FIRST, WANT_V>(a, lw, c, tile, k, gsrc);
   tc_mma<L>(c, 64, 64, TC_Z1, 0);
   tc_load_w<L>(c, tl.m0x);
   op_load_rows64<L>(c, Xg);
@@ -595,7 +637,8 @@ __global__ void __launch_bounds__(NT, 2) k_fk_tc(const __grid_constant__ ChunkAr
   const Geom g = tc_geom<L>(a, w, c, es, nvalid);
   const float* Xg = a.X[k] + (size_t)tile * S * TM;
   __syncthreads();
-  tc_latent_z1<L, KIND, FIRST, true>(a, lw, tl, c, tile, k, Xg);
+  const RowSrc gsrc = tc_stage_rows<L>(c, a.gamma[k], a.c0, nvalid);
+  tc_latent_z1<L, KIND, FIRST, true>(a, lw, tl, c, tile, k, Xg, gsrc);
   tc_mlp_hidden_fwd<L>(c, tl.m2, tw.layer[k + 1].env, NoBias());
   {
     float* Xng = a.X[k + 1] + (size_t)tile * S * TM;
@@ -631,7 +674,8 @@ __global__ void __launch_bounds__(NT, 2) k_t_tc(const __grid_constant__ ChunkArg
   const float* Xg = a.X[k] + (size_t)tile * S * TM;
   __syncthreads();
   const int* c_s = reinterpret_cast<const int*>(c.sm + SM::oC);
-  tc_latent_z1<L, 'A', FIRST, false>(a, lw, tl, c, tile, k, Xg);
+  const RowSrc gsrc = tc_stage_rows<L>(c, a.gamma[k], a.c0, nvalid);
+  tc_latent_z1<L, 'A', FIRST, false>(a, lw, tl, c, tile, k, Xg, gsrc);
   tc_mlp_hidden_fwd<L>(c, tl.m2, tw.ro0, NoBias());
   tc_epi(c, TC_M, 64, [&](int n, float v0, float v1, float v2, float v3) {        // x^n -> operand
     op_put4<L>(c, n, lw.a * Xg[(n + 0) * TM + c.m] + lw.b * v0 * g.u, lw.a * Xg[(n + 1) * TM + c.m] + lw.b * v1 * g.u,
@@ -669,8 +713,7 @@ __global__ void __launch_bounds__(NT, 2) k_t_tc(const __grid_constant__ ChunkArg
     float dup = 0.f;
     for (int c0 = c.half * 32; c0 < c.half * 32 + 32; c0 += 16) {
       float v[16], mv[16];
-      tc_ld16(c, TC_SCR + c0, v);
-      tc_ld16(c, TC_M + c0, mv);
+      tc_ld16x2(c, TC_SCR + c0, v, TC_M + c0, mv);
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
         dXg[(c0 + i) * TM + c.m] = lw.a * v[i];
@@ -702,7 +745,7 @@ __global__ void __launch_bounds__(NT, 2) k_t_tc(const __grid_constant__ ChunkArg
   tc_mlp_bwd_hidden<L>(c, tl.m1_b, tl.m0_bx, NoBias());
   tc_din<L>(c, tl, dXg);
   float dYp[D::NSH];
-  tc_tp_backward<L, 'A', FIRST, false>(a, lw, c, tile, k, es, nvalid, nullptr, FIRST ? nullptr : a.dV[k & 1], a.dgamma[k], dYp);
+  tc_tp_backward<L, 'A', FIRST, false>(a, lw, c, tile, k, es, nvalid, nullptr, FIRST ? nullptr : a.dV[k & 1], a.dgamma[k], dYp, gsrc);
   for (int i = threadIdx.x; i < D::NSH * TM; i += NT) c.sm[SM::oDY + i] = 0.f;
   __syncthreads();
   tc_dy_store<L, true>(a, c, tile, dYp, FIRST);
@@ -727,7 +770,8 @@ __global__ void __launch_bounds__(NT, 2) k_bk_tc(const __grid_constant__ ChunkAr
   op_load_rows64<L>(c, a.X[k + 1] + (size_t)tile * S * TM);
   __syncthreads();
   float* dXg = a.dX + (size_t)tile * S * TM;
-  tc_phase2<L>(a, w, c, k + 1, tw.layer[k + 1].env_b);
+  const RowSrc dsrc = tc_stage_rows<L>(c, a.dgamma[k + 1], a.c0, nvalid);
+  tc_phase2<L>(a, w, c, k + 1, tw.layer[k + 1].env_b, dsrc);
   tc_mma<L>(c, D::ENVW, 64, TC_SCR);                  // dw env^T
   tc_load_w<L>(c, tl.m0s);
   tc_epi(c, TC_SCR, 64, [&](int n, float v0, float v1, float v2, float v3) {   // dX now holds the complete dx^{k+1}
@@ -735,7 +779,8 @@ __global__ void __launch_bounds__(NT, 2) k_bk_tc(const __grid_constant__ ChunkAr
   });
   // ---- recompute layer k forward (z1, z2, m stay in TMEM)
   const float* Xg = a.X[k] + (size_t)tile * S * TM;
-  tc_latent_z1<L, KIND, FIRST, false>(a, lw, tl, c, tile, k, Xg);
+  const RowSrc gsrc = tc_stage_rows<L>(c, a.gamma[k], a.c0, nvalid);    // dGamma rows are consumed (barrier inside tc_mma)
+  tc_latent_z1<L, KIND, FIRST, false>(a, lw, tl, c, tile, k, Xg, gsrc);
   tc_mlp_hidden_fwd<L>(c, tl.m2, tl.m2_b, NoBias());
   {
     float dup = 0.f;
@@ -761,7 +806,7 @@ __global__ void __launch_bounds__(NT, 2) k_bk_tc(const __grid_constant__ ChunkAr
   tc_mlp_bwd_hidden<L>(c, tl.m1_b, tl.m0_bx, NoBias());
   tc_din<L>(c, tl, dXg);
   float dYp[D::NSH];
-  tc_tp_backward<L, KIND, FIRST, true>(a, lw, c, tile, k, es, nvalid, a.dV[(k + 1) & 1], FIRST ? nullptr : a.dV[k & 1], a.dgamma[k], dYp);
+  tc_tp_backward<L, KIND, FIRST, true>(a, lw, c, tile, k, es, nvalid, a.dV[(k + 1) & 1], FIRST ? nullptr : a.dV[k & 1], a.dgamma[k], dYp, gsrc);
   tc_dy_store<L, false>(a, c, tile, dYp, FIRST);
   tc_end(c);
 }
@@ -808,7 +853,8 @@ __global__ void __launch_bounds__(NT, 2) k_b0_tc(const __grid_constant__ ChunkAr
   tc_mlp_hidden_fwd<L>(c, tw.two2, tw.layer[0].env, bias);
   // ---- phase 2 of layer 0 and the embed backward: dx0 = dX + dw env0^T + dw0 emb^T
   op_load_rows64<L>(c, a.X[0] + (size_t)tile * S * TM);
-  tc_phase2<L>(a, w, c, 0, tw.layer[0].env_b);
+  const RowSrc dsrc = tc_stage_rows<L>(c, a.dgamma[0], a.c0, nvalid);
+  tc_phase2<L>(a, w, c, 0, tw.layer[0].env_b, dsrc);
   tc_mma<L>(c, D::ENVW, 64, TC_SCR, 0);
   tc_load_w<L>(c, tw.emb_b);
   {
@@ -824,8 +870,7 @@ __global__ void __launch_bounds__(NT, 2) k_b0_tc(const __grid_constant__ ChunkAr
     float dup = 0.f;
     for (int c0 = c.half * 32; c0 < c.half * 32 + 32; c0 += 16) {
       float v[16], mv[16];
-      tc_ld16(c, TC_SCR + c0, v);
-      tc_ld16(c, TC_M + c0, mv);
+      tc_ld16x2(c, TC_SCR + c0, v, TC_M + c0, mv);
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
         const float dx0 = v[i] + dXg[(c0 + i) * TM + c.m];
