@@ -107,7 +107,7 @@ struct alg_handle {
   // per-step scratch
   DevBuf d_x, d_type, d_ilist, d_numneigh, d_cand, d_first, d_cnt, d_rowptr, d_scan_tmp;
   DevBuf d_mtype, d_edge_j, d_edge_c, d_rvec, d_esum, d_facc, d_vacc, d_forces, d_eall, d_red, d_edge_index, d_edge_energy, d_edge_grad, d_eatom_out;
-  DevBuf c_X[3], c_W0, c_V[3], c_dX, c_dV[2], c_dY, c_du, c_gamma[3], c_dgamma[3], c_carry, c_ecarry;
+  DevBuf d_tstamp, c_X[3], c_W0, c_V[3], c_dX, c_dV[2], c_dY, c_du, c_gamma[3], c_dgamma[3], c_carry, c_ecarry;
   PinBuf h_stage, h_rowptr, h_out, h_first;
   // results
   int last_nlocal = 0, last_ntot = 0;
@@ -545,7 +545,7 @@ extern "C" void alg_destroy(alg_handle* h) {
   DevBuf* bufs[] = {&h->weights, &h->d_tmap, &h->d_cutsq, &h->d_scale, &h->d_shift, &h->d_x, &h->d_type, &h->d_ilist, &h->d_numneigh,
                     &h->d_cand, &h->d_first, &h->d_cnt, &h->d_rowptr, &h->d_scan_tmp, &h->d_mtype, &h->d_edge_j, &h->d_edge_c, &h->d_rvec,
                     &h->d_esum, &h->d_facc, &h->d_vacc, &h->d_forces, &h->d_eall, &h->d_red, &h->d_edge_index, &h->d_edge_energy,
-                    &h->d_edge_grad, &h->d_eatom_out, &h->tc_weights, &h->c_W0, &h->c_dX, &h->c_dY, &h->c_du, &h->c_carry, &h->c_ecarry,
+                    &h->d_edge_grad, &h->d_eatom_out, &h->tc_weights, &h->d_tstamp, &h->c_W0, &h->c_dX, &h->c_dY, &h->c_du, &h->c_carry, &h->c_ecarry,
                     &h->c_X[0], &h->c_X[1], &h->c_X[2], &h->c_V[0], &h->c_V[1], &h->c_V[2], &h->c_dV[0], &h->c_dV[1],
                     &h->c_gamma[0], &h->c_gamma[1], &h->c_gamma[2], &h->c_dgamma[0], &h->c_dgamma[1], &h->c_dgamma[2]};
   for (DevBuf* b : bufs) b->release();
@@ -727,6 +727,12 @@ static int run_step(alg_handle* h, int nlocal, int nghost, const double* d_x, co
   a.edge_grad = h->debug ? h->d_edge_grad.as<float>() : nullptr;
   a.facc = h->d_facc.as<unsigned long long>();
   a.vacc = h->d_vacc.as<unsigned long long>();
+  a.tstamp = nullptr;
+  if (h->debug) {
+    CK(h->d_tstamp.ensure(sizeof(long long) * 5 * 32));
+    CK(cudaMemsetAsync(h->d_tstamp.p, 0, sizeof(long long) * 5 * 32, st));
+    a.tstamp = h->d_tstamp.as<long long>();
+  }
   h->prof.reset();
   long tiles_total = 0;
   for (const Chunk& c : chunks) {
@@ -903,6 +909,11 @@ extern "C" int alg_get_output(alg_handle* h, const char* name, const double** pt
       CK(fetchf(h->d_edge_energy.p, E, raw)); out.assign(raw.begin(), raw.end());
     } else if (key == "edge_grad") {
       CK(fetchf(h->d_edge_grad.p, 3 * E, raw)); out.assign(raw.begin(), raw.end());
+    } else if (key == "tstamp") {
+      std::vector<long long> ts(5 * 32);
+      CK(cudaMemcpyAsync(ts.data(), h->d_tstamp.p, sizeof(long long) * ts.size(), cudaMemcpyDeviceToHost, st));
+      CK(cudaStreamSynchronize(st));
+      out.assign(ts.begin(), ts.end());
     } else if (key == "edge_vec") {
       CK(fetchf(h->d_rvec.p, 4 * E, raw));
       out.resize((size_t)3 * E);

@@ -94,12 +94,16 @@ struct ChunkArgs {
   float* edge_grad;     // [E][3] or nullptr (debug)
   unsigned long long* facc;   // [ntot][3] fixed-point force accumulators
   unsigned long long* vacc;   // [6] fixed-point virial accumulators
+  long long* tstamp;          // debug: [5 kernels][32] clock64() marks of one CTA, or nullptr
 };
+// phase time stamps of CTA 148 (a CTA of the second wave half, steady state) -- debug only
+#define ALG_TS(a, kern, i) do { if ((a).tstamp && blockIdx.x == 148 && threadIdx.x == 0) (a).tstamp[(kern) * 32 + (i)] = clock64(); } while (0)
 
 // ------------------------------------------------------------------------------------------
 // sigmoid via the SFU: ex2.approx (2 ulp) + rcp.approx (1 ulp); absolute error of s <~ 2e-7,
 // far inside the strict fp32 tolerance (checked per stage by tests/test_gpu_parity.py::test_intermediates)
-__device__ __forceinline__ float sigmoid_fast(float z) { return __frcp_rn(1.0f + __expf(-z)); }
+__device__ __forceinline__ float rcp_approx(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float sigmoid_fast(float z) { return rcp_approx(1.0f + __expf(-z)); }
 __device__ __forceinline__ float silu_act(float z, float& d) {
   const float s = sigmoid_fast(z);
   d = ACT_C * s * (1.0f + z * (1.0f - s));
@@ -282,6 +286,58 @@ __device__ __forceinline__ void segsum_tile(const int* __restrict__ c_s, int nva
       acc += val(e, f);
     }
     if (first && contin) carry[f] = acc * scale; else out[(size_t)(cur - c0) * NF + f] = acc * scale;
+  }
+}
+
+
+// ------------------------------------------------------------------------------------------
+// Segment table of a tile: seg[0..nseg] = first tile-local edge of every centre run
+// (seg[nseg] = nvalid), built in parallel by the first TM threads (ballot + prefix).
+// Shared scratch: seg[TM + 1] ints, then nseg, then up to 8 per-warp counts.
+// Must be called by ALL threads of the CTA (contains barriers); c_s must be visible.
+template <int TM>
+__device__ __forceinline__ void seg_build(const int* __restrict__ c_s, int nvalid, int* __restrict__ seg) {
+  int* nseg_p = seg + TM + 1;
+  int* wcnt = seg + TM + 2;
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  bool flag = false;
+  unsigned m = 0;
+  if (t < TM) {
+    flag = t < nvalid && (t == 0 || c_s[t] != c_s[t - 1]);
+    m = __ballot_sync(0xffffffffu, flag);
+    if (lane == 0) wcnt[warp] = __popc(m);
+  }
+  __syncthreads();
+  if (t < TM) {
+    int base = 0;
+    for (int w2 = 0; w2 < warp; ++w2) base += wcnt[w2];
+    if (flag) seg[base + __popc(m & ((1u << lane) - 1u))] = t;
+    if (t == TM - 1) {
+      const int total = base + __popc(m);
+      *nseg_p = total;
+      seg[total] = nvalid;
+    }
+  }
+  __syncthreads();
+}
+
+// Deterministic segmented sum with the segment table: work item (feature f, segment s) is one
+// thread that adds the segment's edges in order (no per-edge branch, unrolled loads).
+//   put(centre_slot, f, is_first_segment_of_tile, value)
+template <int NF, int TM, class Val, class Put>
+__device__ __forceinline__ void segsum_items(const int* __restrict__ c_s, const int* __restrict__ seg, Val val, Put put) {
+  const int nseg = seg[TM + 1];
+  for (int w = threadIdx.x; w < NF * nseg; w += NT) {
+    const int f = w % NF, sgm = w / NF;
+    const int e0 = seg[sgm], e1 = seg[sgm + 1];
+    float acc = 0.f;
+    int e = e0;
+    for (; e + 4 <= e1; e += 4) {
+      const float v0 = val(e, f), v1 = val(e + 1, f), v2 = val(e + 2, f), v3 = val(e + 3, f);
+      acc += v0; acc += v1; acc += v2; acc += v3;
+    }
+    for (; e < e1; ++e) acc += val(e, f);
+    put(c_s[e0], f, sgm == 0, acc);
   }
 }
 

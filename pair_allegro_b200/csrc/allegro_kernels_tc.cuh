@@ -63,9 +63,10 @@ template <int L> struct SmemTC {
   static constexpr int oC = oU + TM;                   // int
   static constexpr int oZZ = oC + TM;                  // int
   static constexpr int oE = oZZ + TM;                  // 4*TM floats: per-half partials, E_e, du partial
-  static constexpr int GSROWS = 16;                    // staged per-centre rows (Gamma / dGamma) of the tile's centres
+  static constexpr int GSROWS = 12;                    // staged per-centre rows (Gamma / dGamma) of the tile's centres
   static constexpr int oGS = oE + 4 * TM;
-  static constexpr int oBAR = oGS + GSROWS * D::F;     // 2 mbarriers + tmem pointer (8 floats)
+  static constexpr int oSEG = oGS + GSROWS * D::F;     // int: segment table seg[TM+1], nseg, warp counts (TM + 16 ints)
+  static constexpr int oBAR = oSEG + TM + 16;          // 2 mbarriers + tmem pointer (8 floats)
   static constexpr int TOTAL = oBAR + 8;
   static constexpr size_t BYTES = (size_t)TOTAL * sizeof(float) + 1024;   // + alignment slack
   static_assert(L == 1, "tensor-core pipeline: shared-memory plan is sized for l_max = 1");
@@ -206,8 +207,18 @@ template <class Fn> __device__ __forceinline__ void tc_epi(const TcCtx& c, uint3
 }
 // load a 64-row tile-SoA array (x^k, dX) of this tile into operand columns [0,64)
 template <int L> __device__ __forceinline__ void op_load_rows64(const TcCtx& c, const float* __restrict__ g /*tile base [64][128]*/) {
-  for (int n = c.half * 32; n < c.half * 32 + 32; n += 4)
-    op_put4<L>(c, n, g[(n + 0) * 128 + c.m], g[(n + 1) * 128 + c.m], g[(n + 2) * 128 + c.m], g[(n + 3) * 128 + c.m]);
+  float v[32];
+  const float* gp = g + (c.half * 32) * 128 + c.m;
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __ldg(gp + i * 128);      // all loads in flight before the first use
+#pragma unroll
+  for (int i = 0; i < 32; i += 4) op_put4<L>(c, c.half * 32 + i, v[i], v[i + 1], v[i + 2], v[i + 3]);
+}
+// this thread's 32 values (its column half) of a 64-row tile-SoA array, all loads issued together
+__device__ __forceinline__ void ld_rows32(const TcCtx& c, const float* __restrict__ g, float* v) {
+  const float* gp = g + (c.half * 32) * 128 + c.m;
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = gp[i * 128];
 }
 
 // all threads; c_s must be published.  Ends with a barrier.
@@ -270,8 +281,15 @@ template <int L> __device__ __forceinline__ void tc_env_sum(const ChunkArgs& a, 
   const float* W_s = c.sm + SM::oOPL;
   const float* Y_s = c.sm + SM::oY;
   const int* c_s = reinterpret_cast<const int*>(c.sm + SM::oC);
-  segsum_tile<D::F>(c_s, nvalid, es, a.rowptr, w.inv_sqrt_n, gamma, a.c0, a.carry + (size_t)tile * D::F,
-                    [&](int e, int f) { const int lm = f / U, u = f % U; return W_s[e * D::WS + lsel(lm) * U + u] * Y_s[lm * TM + e]; });
+  const int* seg = reinterpret_cast<const int*>(c.sm + SM::oSEG);
+  const bool contin = a.rowptr[c_s[0]] < es;
+  float* carry = a.carry + (size_t)tile * D::F;
+  const float sc = w.inv_sqrt_n;
+  segsum_items<D::F, TM>(c_s, seg,
+      [&](int e, int f) { const int lm = f / U, u = f % U; return W_s[e * D::WS + lsel(lm) * U + u] * Y_s[lm * TM + e]; },
+      [&](int centre, int f, bool first, float v) {
+        if (first && contin) carry[f] = v * sc; else gamma[(size_t)(centre - a.c0) * D::F + f] = v * sc;
+      });
 }
 
 // s-part operand column of (scalar path q, channel u): K index inside the 64-wide "s" block
@@ -402,26 +420,20 @@ __device__ __forceinline__ void tc_tp_backward(const ChunkArgs& a, const LayerW&
     }
     __syncthreads();
     {
-      const int cfirst = c_s[0];
-      const bool contin = a.rowptr[cfirst] < es;
+      const int* seg = reinterpret_cast<const int*>(c.sm + SM::oSEG);
+      const bool contin = a.rowptr[c_s[0]] < es;
       float* carry = a.carry + (size_t)tile * D::F;
-      for (int f = t; f < D::FC; f += NT) {
-        const int lm = f / D::CHU, ul = f % D::CHU;
-        const int fg = lm * U + pass * D::CHU + ul;
-        int cur = cfirst; bool first = true; float acc = 0.f;
-        for (int ee = 0; ee < nvalid; ++ee) {
-          const int cc = c_s[ee];
-          if (cc != cur) {
-            if (first && contin) carry[fg] = acc; else dgamma_out[(size_t)(cur - a.c0) * D::F + fg] = acc;
-            cur = cc; acc = 0.f; first = false;
-          }
-          acc += DG[ee * D::DGS + f];
-        }
-        if (first && contin) carry[fg] = acc; else dgamma_out[(size_t)(cur - a.c0) * D::F + fg] = acc;
-      }
+      segsum_items<D::FC, TM>(c_s, seg,
+          [&](int ee, int f) { return DG[ee * D::DGS + f]; },
+          [&](int centre, int f, bool first, float v) {
+            const int lm = f / D::CHU, ul = f % D::CHU;
+            const int fg = lm * U + pass * D::CHU + ul;
+            if (first && contin) carry[fg] = v; else dgamma_out[(size_t)(centre - a.c0) * D::F + fg] = v;
+          });
     }
     __syncthreads();
   }
+  (void)t; (void)nvalid;
 }
 
 // dY: DY_s (phase-2 part, smem) + the two channel-halves' partials (FIRST layers) -> global dY
@@ -464,9 +476,13 @@ __device__ __forceinline__ void tc_mlp_hidden_fwd(TcCtx& c, const TcMat& w2, con
 
 // dm in operand [0,64), w2_b requested: dz2 = (dm W2^T) act'(z2); dz1 = (dz2 W1^T) act'(z1+bias) -> operand; requests `next`
 template <int L, class Bias>
-__device__ __forceinline__ void tc_mlp_bwd_hidden(TcCtx& c, const TcMat& w1_b, const TcMat& next, Bias bias) {
+__device__ __forceinline__ void tc_mlp_bwd_hidden(TcCtx& c, const TcMat& w1_b, const TcMat& next, Bias bias, long long* ts = nullptr) {
+  if (ts && blockIdx.x == 148 && threadIdx.x == 0) ts[20] = clock64();
   tc_mma<L>(c, 64, 64, TC_SCR);
+  if (ts && blockIdx.x == 148 && threadIdx.x == 0) ts[21] = clock64();
   tc_load_w<L>(c, w1_b);
+  if (ts && blockIdx.x == 148 && threadIdx.x == 0) ts[24] = clock64();
+  if (ts && blockIdx.x == 148 && threadIdx.x == 200) ts[26] = clock64();
   for (int c0 = c.half * 32; c0 < c.half * 32 + 32; c0 += 16) {
     float v[16], z[16];
     tc_ld16x2(c, TC_SCR + c0, v, TC_Z2 + c0, z);
@@ -477,7 +493,10 @@ __device__ __forceinline__ void tc_mlp_bwd_hidden(TcCtx& c, const TcMat& w1_b, c
       op_put4<L>(c, c0 + i, v[i] * d0, v[i + 1] * d1, v[i + 2] * d2, v[i + 3] * d3);
     }
   }
+  if (ts && blockIdx.x == 148 && threadIdx.x == 0) ts[22] = clock64();
+  if (ts && blockIdx.x == 148 && threadIdx.x == 200) ts[27] = clock64();
   tc_mma<L>(c, 64, 64, TC_SCR);
+  if (ts && blockIdx.x == 148 && threadIdx.x == 0) ts[23] = clock64();
   tc_load_w<L>(c, next);
   for (int c0 = c.half * 32; c0 < c.half * 32 + 32; c0 += 16) {
     float v[16], z[16];
@@ -496,10 +515,14 @@ __device__ __forceinline__ void tc_mlp_bwd_hidden(TcCtx& c, const TcMat& w1_b, c
 template <int L>
 __device__ __forceinline__ void tc_din(TcCtx& c, const TcLayerW& tl, float* __restrict__ dXg) {
   using SM = SmemTC<L>; constexpr int TM = 128;
+  float dp[32];
+  ld_rows32(c, dXg, dp);                              // in flight during the MMA
   tc_mma<L>(c, 64, 64, TC_SCR);
   tc_load_w<L>(c, tl.m0_bs);
   tc_epi(c, TC_SCR, 64, [&](int n, float v0, float v1, float v2, float v3) {
-    dXg[(n + 0) * TM + c.m] += v0; dXg[(n + 1) * TM + c.m] += v1; dXg[(n + 2) * TM + c.m] += v2; dXg[(n + 3) * TM + c.m] += v3;
+    const int j = n - c.half * 32;
+    dXg[(n + 0) * TM + c.m] = dp[j] + v0; dXg[(n + 1) * TM + c.m] = dp[j + 1] + v1;
+    dXg[(n + 2) * TM + c.m] = dp[j + 2] + v2; dXg[(n + 3) * TM + c.m] = dp[j + 3] + v3;
   });
   tc_mma<L>(c, 64, 64, TC_SCR);                       // same operand (dz1), second weight block
   float* DS_s = c.sm + SM::oWBH;                       // the weight region is free now
@@ -566,6 +589,8 @@ __global__ void __launch_bounds__(NT, 2) k_f0_tc(const __grid_constant__ ChunkAr
   const int nvalid = min(TM, a.e1 - es);
   tc_load_w<L>(c, tw.two0);
   const Geom g = tc_geom<L>(a, w, c, es, nvalid);
+  __syncthreads();
+  seg_build<TM>(reinterpret_cast<const int*>(c.sm + SM::oC), nvalid, reinterpret_cast<int*>(c.sm + SM::oSEG));
   {  // Bessel*u -> operand columns [0,32) (zero padded beyond num_bessels)
     const float pref = sqrtf(2.0f / g.rc);
     const float xr = g.r / g.rc;
@@ -613,10 +638,14 @@ template <int L, char KIND, bool FIRST, bool WANT_V>
 __device__ __forceinline__ void tc_latent_z1(const ChunkArgs& a, const LayerW& lw, const TcLayerW& tl, TcCtx& c, int tile, int k,
                                              const float* __restrict__ Xg, const RowSrc& gsrc) {
   tc_tp_forward<L, KIND, FIRST, WANT_V>(a, lw, c, tile, k, gsrc);
+  ALG_TS(a, 2, 16);
   tc_mma<L>(c, 64, 64, TC_Z1, 0);
+  ALG_TS(a, 2, 17);
   tc_load_w<L>(c, tl.m0x);
   op_load_rows64<L>(c, Xg);
+  ALG_TS(a, 2, 18);
   tc_mma<L>(c, 64, 64, TC_Z1, 1);
+  ALG_TS(a, 2, 19);
   tc_load_w<L>(c, tl.m1);
 }
 
@@ -637,14 +666,18 @@ __global__ void __launch_bounds__(NT, 2) k_fk_tc(const __grid_constant__ ChunkAr
   const Geom g = tc_geom<L>(a, w, c, es, nvalid);
   const float* Xg = a.X[k] + (size_t)tile * S * TM;
   __syncthreads();
+  seg_build<TM>(reinterpret_cast<const int*>(c.sm + SM::oC), nvalid, reinterpret_cast<int*>(c.sm + SM::oSEG));
   const RowSrc gsrc = tc_stage_rows<L>(c, a.gamma[k], a.c0, nvalid);
   tc_latent_z1<L, KIND, FIRST, true>(a, lw, tl, c, tile, k, Xg, gsrc);
   tc_mlp_hidden_fwd<L>(c, tl.m2, tw.layer[k + 1].env, NoBias());
   {
     float* Xng = a.X[k + 1] + (size_t)tile * S * TM;
+    float xp[32];
+    ld_rows32(c, Xg, xp);
     tc_epi(c, TC_M, 64, [&](int n, float v0, float v1, float v2, float v3) {
-      const float x0 = lw.a * Xg[(n + 0) * TM + c.m] + lw.b * v0 * g.u, x1 = lw.a * Xg[(n + 1) * TM + c.m] + lw.b * v1 * g.u;
-      const float x2 = lw.a * Xg[(n + 2) * TM + c.m] + lw.b * v2 * g.u, x3 = lw.a * Xg[(n + 3) * TM + c.m] + lw.b * v3 * g.u;
+      const int j = n - c.half * 32;
+      const float x0 = lw.a * xp[j] + lw.b * v0 * g.u, x1 = lw.a * xp[j + 1] + lw.b * v1 * g.u;
+      const float x2 = lw.a * xp[j + 2] + lw.b * v2 * g.u, x3 = lw.a * xp[j + 3] + lw.b * v3 * g.u;
       op_put4<L>(c, n, x0, x1, x2, x3);
       Xng[(n + 0) * TM + c.m] = x0; Xng[(n + 1) * TM + c.m] = x1; Xng[(n + 2) * TM + c.m] = x2; Xng[(n + 3) * TM + c.m] = x3;
     });
@@ -669,19 +702,32 @@ __global__ void __launch_bounds__(NT, 2) k_t_tc(const __grid_constant__ ChunkArg
   const int nvalid = min(TM, a.e1 - es);
   const LayerW& lw = w.layer[k];
   const TcLayerW& tl = tw.layer[k];
+  ALG_TS(a, 2, 0);
   tc_load_w<L>(c, tl.m0s);
   const Geom g = tc_geom<L>(a, w, c, es, nvalid);
   const float* Xg = a.X[k] + (size_t)tile * S * TM;
   __syncthreads();
+  seg_build<TM>(reinterpret_cast<const int*>(c.sm + SM::oC), nvalid, reinterpret_cast<int*>(c.sm + SM::oSEG));
+  ALG_TS(a, 2, 1);
   const int* c_s = reinterpret_cast<const int*>(c.sm + SM::oC);
   const RowSrc gsrc = tc_stage_rows<L>(c, a.gamma[k], a.c0, nvalid);
+  ALG_TS(a, 2, 2);
   tc_latent_z1<L, 'A', FIRST, false>(a, lw, tl, c, tile, k, Xg, gsrc);
+  ALG_TS(a, 2, 3);
   tc_mlp_hidden_fwd<L>(c, tl.m2, tw.ro0, NoBias());
-  tc_epi(c, TC_M, 64, [&](int n, float v0, float v1, float v2, float v3) {        // x^n -> operand
-    op_put4<L>(c, n, lw.a * Xg[(n + 0) * TM + c.m] + lw.b * v0 * g.u, lw.a * Xg[(n + 1) * TM + c.m] + lw.b * v1 * g.u,
-               lw.a * Xg[(n + 2) * TM + c.m] + lw.b * v2 * g.u, lw.a * Xg[(n + 3) * TM + c.m] + lw.b * v3 * g.u);
-  });
+  ALG_TS(a, 2, 4);
+  {
+    float xp[32];
+    ld_rows32(c, Xg, xp);
+    tc_epi(c, TC_M, 64, [&](int n, float v0, float v1, float v2, float v3) {        // x^n -> operand
+      const int j = n - c.half * 32;
+      op_put4<L>(c, n, lw.a * xp[j] + lw.b * v0 * g.u, lw.a * xp[j + 1] + lw.b * v1 * g.u,
+                 lw.a * xp[j + 2] + lw.b * v2 * g.u, lw.a * xp[j + 3] + lw.b * v3 * g.u);
+    });
+  }
+  ALG_TS(a, 2, 5);
   tc_mma<L>(c, 64, R, TC_SCR);                       // readout hidden
+  ALG_TS(a, 2, 6);
   tc_load_w<L>(c, tw.ro0_b);
   float* e_s = c.sm + SM::oE;
   {
@@ -701,7 +747,9 @@ __global__ void __launch_bounds__(NT, 2) k_t_tc(const __grid_constant__ ChunkArg
     for (int i = 0; i < 16; i += 4) op_put4<L>(c, c.half * 16 + i, dz[i], dz[i + 1], dz[i + 2], dz[i + 3]);
     e_s[c.half * TM + c.m] = ee;
   }
+  ALG_TS(a, 2, 7);
   tc_mma<L>(c, R, 64, TC_SCR);                       // dx^n = dz ro0^T   (the barrier inside orders e_s)
+  ALG_TS(a, 2, 8);
   tc_load_w<L>(c, tl.m2_b);
   if (c.half == 0) {
     const float ee = e_s[c.m] + e_s[TM + c.m];
@@ -728,28 +776,30 @@ __global__ void __launch_bounds__(NT, 2) k_t_tc(const __grid_constant__ ChunkArg
     __syncthreads();
     if (c.half == 0) a.du[(size_t)tile * TM + c.m] = dup + e_s[3 * TM + c.m];
   }
-  if (threadIdx.x == NT - 1) {  // E_i raw sums (double), deterministic edge order (not the MMA-issuing thread)
-    const int cfirst = c_s[0];
-    const bool contin = a.rowptr[cfirst] < es;
-    int cur = cfirst; bool first = true; double acc = 0.0;
-    for (int e = 0; e < nvalid; ++e) {
-      const int cc = c_s[e];
-      if (cc != cur) {
-        if (first && contin) a.ecarry[tile] = acc; else a.esum[cur] = acc;
-        cur = cc; acc = 0.0; first = false;
-      }
-      acc += (double)e_s[2 * TM + e];
+  {  // E_i raw sums (double): one thread per centre run, edges in order (deterministic)
+    const int* seg = reinterpret_cast<const int*>(c.sm + SM::oSEG);
+    const int nseg = seg[TM + 1];
+    const bool contin = a.rowptr[c_s[0]] < es;
+    for (int sgm = NT - 1 - threadIdx.x; sgm < nseg; sgm += NT) {     // highest threads first: not the MMA-issuing thread
+      double acc = 0.0;
+      for (int e = seg[sgm]; e < seg[sgm + 1]; ++e) acc += (double)e_s[2 * TM + e];
+      if (sgm == 0 && contin) a.ecarry[tile] = acc; else a.esum[c_s[seg[sgm]]] = acc;
     }
-    if (first && contin) a.ecarry[tile] = acc; else a.esum[cur] = acc;
   }
-  tc_mlp_bwd_hidden<L>(c, tl.m1_b, tl.m0_bx, NoBias());
+  ALG_TS(a, 2, 9);
+  tc_mlp_bwd_hidden<L>(c, tl.m1_b, tl.m0_bx, NoBias(), a.tstamp ? a.tstamp + 64 : nullptr);
+  ALG_TS(a, 2, 10);
   tc_din<L>(c, tl, dXg);
+  ALG_TS(a, 2, 11);
   float dYp[D::NSH];
   tc_tp_backward<L, 'A', FIRST, false>(a, lw, c, tile, k, es, nvalid, nullptr, FIRST ? nullptr : a.dV[k & 1], a.dgamma[k], dYp, gsrc);
+  ALG_TS(a, 2, 12);
   for (int i = threadIdx.x; i < D::NSH * TM; i += NT) c.sm[SM::oDY + i] = 0.f;
   __syncthreads();
   tc_dy_store<L, true>(a, c, tile, dYp, FIRST);
+  ALG_TS(a, 2, 13);
   tc_end(c);
+  ALG_TS(a, 2, 14);
 }
 
 // ============================================================================================
@@ -769,13 +819,17 @@ __global__ void __launch_bounds__(NT, 2) k_bk_tc(const __grid_constant__ ChunkAr
   const Geom g = tc_geom<L>(a, w, c, es, nvalid);
   op_load_rows64<L>(c, a.X[k + 1] + (size_t)tile * S * TM);
   __syncthreads();
+  seg_build<TM>(reinterpret_cast<const int*>(c.sm + SM::oC), nvalid, reinterpret_cast<int*>(c.sm + SM::oSEG));
   float* dXg = a.dX + (size_t)tile * S * TM;
   const RowSrc dsrc = tc_stage_rows<L>(c, a.dgamma[k + 1], a.c0, nvalid);
   tc_phase2<L>(a, w, c, k + 1, tw.layer[k + 1].env_b, dsrc);
+  float dxn[32];                                      // complete dx^{k+1} of this thread's 32 columns (kept in registers)
+  ld_rows32(c, dXg, dxn);
   tc_mma<L>(c, D::ENVW, 64, TC_SCR);                  // dw env^T
   tc_load_w<L>(c, tl.m0s);
-  tc_epi(c, TC_SCR, 64, [&](int n, float v0, float v1, float v2, float v3) {   // dX now holds the complete dx^{k+1}
-    dXg[(n + 0) * TM + c.m] += v0; dXg[(n + 1) * TM + c.m] += v1; dXg[(n + 2) * TM + c.m] += v2; dXg[(n + 3) * TM + c.m] += v3;
+  tc_epi(c, TC_SCR, 64, [&](int n, float v0, float v1, float v2, float v3) {
+    const int j = n - c.half * 32;
+    dxn[j] += v0; dxn[j + 1] += v1; dxn[j + 2] += v2; dxn[j + 3] += v3;
   });
   // ---- recompute layer k forward (z1, z2, m stay in TMEM)
   const float* Xg = a.X[k] + (size_t)tile * S * TM;
@@ -789,9 +843,9 @@ __global__ void __launch_bounds__(NT, 2) k_bk_tc(const __grid_constant__ ChunkAr
       tc_ld16(c, TC_M + c0, mv);
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
-        const float dxn = dXg[(c0 + i) * TM + c.m];
-        dXg[(c0 + i) * TM + c.m] = lw.a * dxn;
-        const float dxt = lw.b * dxn;
+        const float dx1 = dxn[c0 - c.half * 32 + i];
+        dXg[(c0 + i) * TM + c.m] = lw.a * dx1;
+        const float dxt = lw.b * dx1;
         dup += dxt * mv[i];
         v[i] = dxt * g.u;
       }
@@ -824,6 +878,8 @@ __global__ void __launch_bounds__(NT, 2) k_b0_tc(const __grid_constant__ ChunkAr
   const int nvalid = min(TM, a.e1 - es);
   tc_load_w<L>(c, tw.two0);
   const Geom g = tc_geom<L>(a, w, c, es, nvalid);
+  __syncthreads();
+  seg_build<TM>(reinterpret_cast<const int*>(c.sm + SM::oC), nvalid, reinterpret_cast<int*>(c.sm + SM::oSEG));
   // ---- recompute the two-body MLP first: z1, z2, m0 stay in TMEM
   float bes[MAXB], dbes[MAXB];
   {
@@ -858,9 +914,7 @@ __global__ void __launch_bounds__(NT, 2) k_b0_tc(const __grid_constant__ ChunkAr
   tc_mma<L>(c, D::ENVW, 64, TC_SCR, 0);
   tc_load_w<L>(c, tw.emb_b);
   {
-    const float* W0g = a.W0 + (size_t)tile * D::ENVW * TM;    // dw0 (written by the layer-0 TP backward)
-    for (int n = c.half * 32; n < c.half * 32 + 32; n += 4)
-      op_put4<L>(c, n, W0g[(n + 0) * TM + c.m], W0g[(n + 1) * TM + c.m], W0g[(n + 2) * TM + c.m], W0g[(n + 3) * TM + c.m]);
+    op_load_rows64<L>(c, a.W0 + (size_t)tile * D::ENVW * TM);   // dw0 (written by the layer-0 TP backward)
   }
   tc_mma<L>(c, D::ENVW, 64, TC_SCR, 1);
   tc_load_w<L>(c, tw.two2_b);
@@ -868,12 +922,14 @@ __global__ void __launch_bounds__(NT, 2) k_b0_tc(const __grid_constant__ ChunkAr
   float du_tot;
   {
     float dup = 0.f;
+    float dp[32];
+    ld_rows32(c, dXg, dp);
     for (int c0 = c.half * 32; c0 < c.half * 32 + 32; c0 += 16) {
       float v[16], mv[16];
       tc_ld16x2(c, TC_SCR + c0, v, TC_M + c0, mv);
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
-        const float dx0 = v[i] + dXg[(c0 + i) * TM + c.m];
+        const float dx0 = v[i] + dp[c0 - c.half * 32 + i];
         dup += dx0 * mv[i];
         v[i] = dx0 * g.u;
       }
@@ -933,23 +989,25 @@ __global__ void __launch_bounds__(NT, 2) k_b0_tc(const __grid_constant__ ChunkAr
   {
     const int t = threadIdx.x;
     const int* c_s = reinterpret_cast<const int*>(c.sm + SM::oC);
-    if (t >= 128 && t < 131) {
-      const int q = t - 128;
-      int cur = c_s[0]; double acc = 0.0;
-      for (int e = 0; e < nvalid; ++e) {
-        const int cc = c_s[e];
-        if (cc != cur) {
-          atomicAdd(a.facc + 3 * (size_t)a.ilist[cur] + q, (unsigned long long)__double2ll_rn(acc * FIX_SCALE));
-          cur = cc; acc = 0.0;
-        }
-        acc += (double)G3[q * TM + e];
-      }
-      atomicAdd(a.facc + 3 * (size_t)a.ilist[cur] + q, (unsigned long long)__double2ll_rn(acc * FIX_SCALE));
-    } else if (t >= 160 && t < 166 && a.vacc) {
-      const int q = t - 160;
+    const int* seg = reinterpret_cast<const int*>(c.sm + SM::oSEG);
+    const int nseg = seg[TM + 1];
+    // F_i += sum of g_e over each centre run (fixed order), one atomic per (centre, component)
+    for (int w2 = t; w2 < 3 * nseg; w2 += NT) {
+      const int q = w2 % 3, sgm = w2 / 3;
       double acc = 0.0;
-      for (int e = 0; e < nvalid; ++e) acc += (double)VR[q * TM + e];
-      atomicAdd(a.vacc + q, (unsigned long long)__double2ll_rn(acc * VIR_SCALE));
+      for (int e = seg[sgm]; e < seg[sgm + 1]; ++e) acc += (double)G3[q * TM + e];
+      atomicAdd(a.facc + 3 * (size_t)a.ilist[c_s[seg[sgm]]] + q, (unsigned long long)__double2ll_rn(acc * FIX_SCALE));
+    }
+    // virial: exact integer (fixed-point) warp reduction, one atomic per warp and component
+    if (a.vacc && t >= 128) {
+      const int e = t - 128;
+#pragma unroll
+      for (int q = 0; q < 6; ++q) {
+        long long v = __double2ll_rn((double)VR[q * TM + e] * VIR_SCALE);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if ((t & 31) == 0) atomicAdd(a.vacc + q, (unsigned long long)v);
+      }
     }
   }
   tc_end(c);

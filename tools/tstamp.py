@@ -1,0 +1,37 @@
+#!/usr/bin/env python
+"""phase timing of one steady-state CTA of k_t_tc (clock64 marks, debug=1)"""
+import os, sys
+import numpy as np
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import allegro_torch as AT
+from oracle import lmp_harness as H
+from pair_allegro_b200.export import export_alg
+from pair_allegro_b200.pair import PairAllegroB200
+pos, types, cell = H.fcc_box(24)
+atoms = H.make_single_rank(types, pos, cell, [True] * 3, 6.0)
+lst = H.build_full_list(atoms, 6.0)
+cfg = AT.default_config(type_names=["Ag"], r_max=5.0, l_max=1, num_layers=2, avg_num_neighbors=28.0, seed=2)
+os.makedirs("/tmp/qb", exist_ok=True)
+AT.save_torchscript(cfg, "/tmp/qb/m.nequip.pth"); export_alg("/tmp/qb/m.nequip.pth", "/tmp/qb/m.alg")
+pair = PairAllegroB200(device=0, debug_mode=False)
+pair.coeff(["*", "*", "/tmp/qb/m.alg", "Ag"], 1)
+pair.handle.set_option("debug", "1")
+for _ in range(2):
+    atoms.f[:] = 0
+    pair.compute(atoms, lst)
+ts = pair.handle.get_output("tstamp").reshape(5, 32)
+t = ts[2]
+names = {1: "geom+sync", 2: "stage rows", 16: " tp fwd", 17: " mma s-block", 18: " load x rows", 19: " mma x-block", 4: "hidden fwd (2 epi + 2 mma)",
+         5: "x^n epilogue", 6: "mma readout", 7: "readout epi", 8: "mma dx", 9: "dx epi + du + E loop", 10: "bwd hidden (2 mma + 2 epi)", 11: "dIN (2 mma + 2 epi)",
+         12: "tp backward (+segsum)", 13: "dy store", 14: "tc_end"}
+order = [1, 2, 16, 17, 18, 19, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14]
+prev = t[0]
+print("k_t_tc CTA 148: total %d cycles" % (t[14] - t[0]))
+for i in order:
+    print("  %-32s %7d" % (names[i], t[i] - prev))
+    prev = t[i]
+
+b = ts[2]
+print("bwd hidden detail (T kernel): mma1 %d  epi1 %d  mma2 %d  epi2(to mark10) %d" % (b[21]-b[20], b[22]-b[21], b[23]-b[22], t[10]-b[23]))
+print("thread0: tc_load_w %d  epi-loop %d ; thread200: epi-loop %d (start offset vs t0 %d)" % (b[24]-b[21], b[22]-b[24], b[27]-b[26], b[26]-b[21]))
