@@ -27,7 +27,8 @@ template <int L> struct Smem {
   static constexpr int oDY = oY + D::NSH * TM;
   static constexpr int oU = oDY + D::NSH * TM;
   static constexpr int oMisc = oU + TM;            // 3 rows: c_s (int), zz_s (int), e_s (float)
-  static constexpr int oIN = oMisc + 3 * TM;
+  static constexpr int oSeg = oMisc + 3 * TM;      // 2 rows (int): segment table seg[TM+1], nseg, warp counts
+  static constexpr int oIN = oSeg + 2 * TM;
   static constexpr int oA = oIN + D::SIN * TM;
   static constexpr int oB = oA + 64 * TM;
   static constexpr int oPAD = oB + 64 * TM;
@@ -81,8 +82,20 @@ template <int L> __device__ __forceinline__ void env_sum(const ChunkArgs& a, con
   const float* W_s = sm + SM::oA;
   const float* Y_s = sm + SM::oY;
   const int* c_s = reinterpret_cast<const int*>(sm + SM::oMisc);
-  segsum_tile<D::F>(c_s, nvalid, es, a.rowptr, w.inv_sqrt_n, gamma, a.c0, a.carry + (size_t)tile * D::F,
-                    [&](int e, int f) { const int lm = f / U, u = f % U; return W_s[e * D::WS + lsel(lm) * U + u] * Y_s[lm * TM + e]; });
+  const int* seg = reinterpret_cast<const int*>(sm + SM::oSeg);
+  const bool contin = a.rowptr[c_s[0]] < es;
+  float* carry = a.carry + (size_t)tile * D::F;
+  const float sc = w.inv_sqrt_n;
+  segsum_items<D::F, TM>(c_s, seg,
+      [&](int e, int f) { const int lm = f / U, u = f % U; return W_s[e * D::WS + lsel(lm) * U + u] * Y_s[lm * TM + e]; },
+      [&](int centre, int f, bool first, float v) {
+        if (first && contin) carry[f] = v * sc; else gamma[(size_t)(centre - a.c0) * D::F + f] = v * sc;
+      });
+  (void)nvalid;
+}
+template <int L> __device__ __forceinline__ void seg_setup(float* sm, int nvalid) {
+  using SM = Smem<L>;
+  seg_build<Dims<L>::TM>(reinterpret_cast<const int*>(sm + SM::oMisc), nvalid, reinterpret_cast<int*>(sm + SM::oSeg));
 }
 
 // ============================================================================================
@@ -108,6 +121,7 @@ __global__ void __launch_bounds__(NT, Dims<L>::MINB) k_f0(const __grid_constant_
     }
   }
   __syncthreads();
+  seg_setup<L>(sm, nvalid);
   {  // two-body MLP layer 0: one-hot rows are added in the epilogue
     const float* w0 = w.two.w[0];
     const int T = w.T;
@@ -176,6 +190,7 @@ __global__ void __launch_bounds__(NT, Dims<L>::MINB) k_fk(const __grid_constant_
   load_rows<TM>(IN, a.X[k] + (size_t)tile * S * TM, S);
   if (t < TM) edge_geom<L>(a, w, es, nvalid, sm);
   __syncthreads();
+  seg_setup<L>(sm, nvalid);
   {  // tensor product: s -> IN rows S.., V^{k+1} -> global
     const int e = t % TM, uh = t / TM;
     const float* gam = a.gamma[k] + (size_t)(c_s[e] - a.c0) * D::F;
@@ -303,26 +318,20 @@ __device__ __forceinline__ void tp_backward(const ChunkArgs& a, const LayerW& lw
     }
     __syncthreads();
     {  // segmented sum of this pass's features: local f = lm*CHU+ul -> global lm*U + pass*CHU+ul
-      const int cfirst = c_s[0];
-      const bool contin = a.rowptr[cfirst] < es;
+      const int* seg = reinterpret_cast<const int*>(sm + SM::oSeg);
+      const bool contin = a.rowptr[c_s[0]] < es;
       float* carry = a.carry + (size_t)tile * D::F;
-      for (int f = t; f < D::FC; f += NT) {
-        const int lm = f / D::CHU, ul = f % D::CHU;
-        const int fg = lm * U + pass * D::CHU + ul;
-        int cur = cfirst; bool first = true; float acc = 0.f;
-        for (int ee = 0; ee < nvalid; ++ee) {
-          const int c = c_s[ee];
-          if (c != cur) {
-            if (first && contin) carry[fg] = acc; else dgamma_out[(size_t)(cur - a.c0) * D::F + fg] = acc;
-            cur = c; acc = 0.f; first = false;
-          }
-          acc += DG[ee * D::DGS + f];
-        }
-        if (first && contin) carry[fg] = acc; else dgamma_out[(size_t)(cur - a.c0) * D::F + fg] = acc;
-      }
+      segsum_items<D::FC, TM>(c_s, seg,
+          [&](int ee, int f) { return DG[ee * D::DGS + f]; },
+          [&](int centre, int f, bool first, float v) {
+            const int lm = f / D::CHU, ul = f % D::CHU;
+            const int fg = lm * U + pass * D::CHU + ul;
+            if (first && contin) carry[fg] = v; else dgamma_out[(size_t)(centre - a.c0) * D::F + fg] = v;
+          });
     }
     __syncthreads();
   }
+  (void)t; (void)nvalid;
 }
 
 // reduce per-thread dY partials (CPH phases per edge) through region D and add to global dY
@@ -416,6 +425,7 @@ __global__ void __launch_bounds__(NT, Dims<L>::MINB) k_t(const __grid_constant__
   load_rows<TM>(IN, a.X[k] + (size_t)tile * S * TM, S);
   if (t < TM) edge_geom<L>(a, w, es, nvalid, sm);
   __syncthreads();
+  seg_setup<L>(sm, nvalid);
   {  // scalar tensor-product outputs s -> IN rows S..
     const int e = t % TM, uh = t / TM;
     const float* gam = a.gamma[k] + (size_t)(c_s[e] - a.c0) * D::F;
@@ -456,19 +466,15 @@ __global__ void __launch_bounds__(NT, Dims<L>::MINB) k_t(const __grid_constant__
     if (t < nvalid && a.edge_energy) a.edge_energy[es + t] = ee;
   }
   __syncthreads();
-  if (t == 0) {  // E_i raw sums (double), deterministic edge order
-    const int cfirst = c_s[0];
-    const bool contin = a.rowptr[cfirst] < es;
-    int cur = cfirst; bool first = true; double acc = 0.0;
-    for (int e = 0; e < nvalid; ++e) {
-      const int c = c_s[e];
-      if (c != cur) {
-        if (first && contin) a.ecarry[tile] = acc; else a.esum[cur] = acc;
-        cur = c; acc = 0.0; first = false;
-      }
-      acc += (double)e_s[e];
+  {  // E_i raw sums (double): one thread per centre run, edges in order (deterministic)
+    const int* seg = reinterpret_cast<const int*>(sm + SM::oSeg);
+    const int nseg = seg[TM + 1];
+    const bool contin = a.rowptr[c_s[0]] < es;
+    for (int sgm = t; sgm < nseg; sgm += NT) {
+      double acc = 0.0;
+      for (int e = seg[sgm]; e < seg[sgm + 1]; ++e) acc += (double)e_s[e];
+      if (sgm == 0 && contin) a.ecarry[tile] = acc; else a.esum[c_s[seg[sgm]]] = acc;
     }
-    if (first && contin) a.ecarry[tile] = acc; else a.esum[cur] = acc;
   }
   // dx^n = ro0^T dz ; then residual / envelope split (fused epilogue)
   float* dXg = a.dX + (size_t)tile * S * TM;
@@ -519,6 +525,7 @@ __global__ void __launch_bounds__(NT, Dims<L>::MINB) k_bk(const __grid_constant_
   load_rows<TM>(C, a.X[k + 1] + (size_t)tile * S * TM, S);
   if (t < TM) edge_geom<L>(a, w, es, nvalid, sm);
   __syncthreads();
+  seg_setup<L>(sm, nvalid);
   phase2<L>(a, w, k + 1, tile, sm);                  // dX(global) now holds the complete dx^{k+1}
   // ---- phase 1 of layer k: recompute forward
   load_rows<TM>(IN, a.X[k] + (size_t)tile * S * TM, S);
@@ -589,6 +596,7 @@ __global__ void __launch_bounds__(NT, Dims<L>::MINB) k_b0(const __grid_constant_
   Geom g;
   if (t < TM) g = edge_geom<L>(a, w, es, nvalid, sm);
   __syncthreads();
+  seg_setup<L>(sm, nvalid);
   phase2<L>(a, w, 0, tile, sm);
   // dx0 += emb^T dw0
   float* dXg = a.dX + (size_t)tile * S * TM;
@@ -668,22 +676,27 @@ __global__ void __launch_bounds__(NT, Dims<L>::MINB) k_b0(const __grid_constant_
     }
   }
   __syncthreads();
-  if (t < 3) {  // F_i += sum of g_e over the centre's edges in this tile (fixed order), one atomic per centre
-    int cur = c_s[0]; double acc = 0.0;
-    for (int e = 0; e < nvalid; ++e) {
-      const int c = c_s[e];
-      if (c != cur) {
-        atomicAdd(a.facc + 3 * (size_t)a.ilist[cur] + t, (unsigned long long)__double2ll_rn(acc * FIX_SCALE));
-        cur = c; acc = 0.0;
-      }
-      acc += (double)A[t * TM + e];
+  {
+    const int* seg = reinterpret_cast<const int*>(sm + SM::oSeg);
+    const int nseg = seg[TM + 1];
+    // F_i += sum of g_e over each centre run (fixed order), one atomic per (centre, component)
+    for (int w2 = t; w2 < 3 * nseg; w2 += NT) {
+      const int q = w2 % 3, sgm = w2 / 3;
+      double acc = 0.0;
+      for (int e = seg[sgm]; e < seg[sgm + 1]; ++e) acc += (double)A[q * TM + e];
+      atomicAdd(a.facc + 3 * (size_t)a.ilist[c_s[seg[sgm]]] + q, (unsigned long long)__double2ll_rn(acc * FIX_SCALE));
     }
-    atomicAdd(a.facc + 3 * (size_t)a.ilist[cur] + t, (unsigned long long)__double2ll_rn(acc * FIX_SCALE));
-  } else if (t >= 32 && t < 38 && a.vacc) {
-    const int q = t - 32;
-    double acc = 0.0;
-    for (int e = 0; e < nvalid; ++e) acc += (double)Dd[q * TM + e];
-    atomicAdd(a.vacc + q, (unsigned long long)__double2ll_rn(acc * VIR_SCALE));
+    // virial: exact integer (fixed-point) warp reduction, one atomic per warp and component
+    if (a.vacc && t >= NT - TM) {
+      const int e = t - (NT - TM);
+#pragma unroll
+      for (int q = 0; q < 6; ++q) {
+        long long v = __double2ll_rn((double)Dd[q * TM + e] * VIR_SCALE);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if ((t & 31) == 0) atomicAdd(a.vacc + q, (unsigned long long)v);
+      }
+    }
   }
 }
 

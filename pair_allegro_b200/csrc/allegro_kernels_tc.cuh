@@ -133,30 +133,38 @@ template <int L> __device__ __forceinline__ void tc_load_w(TcCtx& c, const TcMat
 // all threads: operands are written -> thread 0 issues the MMAs -> everybody waits for completion
 template <int L> __device__ __forceinline__ void tc_mma(TcCtx& c, int K, int N, uint32_t dcol, uint32_t accumulate = 0) {
   using SM = SmemTC<L>;
+  const bool issuer = threadIdx.x == 0;
+  uint64_t dAh = 0, dAl = 0, dWh = 0, dWl = 0;
+  if (issuer) {   // everything that does not depend on the other threads happens before the barrier
+    umma::mbar_wait(c.wbar, c.wph);                  // weight block landed (requested one epilogue ago)
+    dAh = umma::make_desc_k_sw128(c.sm + SM::oOPH); dAl = umma::make_desc_k_sw128(c.sm + SM::oOPL);
+    dWh = umma::make_desc_k_sw128(c.sm + SM::oWBH); dWl = umma::make_desc_k_sw128(c.sm + SM::oWBL);
+  }
   umma::fence_async_smem();
   umma::fence_before_sync();
   __syncthreads();
-  if (threadIdx.x == 0) {
+  if (issuer) {
     umma::fence_after_sync();
-    umma::mbar_wait(c.wbar, c.wph);
-    const float* Ah = c.sm + SM::oOPH; const float* Al = c.sm + SM::oOPL;
-    const float* Wh = c.sm + SM::oWBH; const float* Wl = c.sm + SM::oWBL;
     const uint32_t idesc = umma::make_idesc_tf32(N);
-    uint32_t acc = accumulate;
-    const uint64_t dAh = umma::make_desc_k_sw128(Ah), dAl = umma::make_desc_k_sw128(Al);
-    const uint64_t dWh = umma::make_desc_k_sw128(Wh), dWl = umma::make_desc_k_sw128(Wl);
     const uint32_t wpan = (uint32_t)(N * 32 * 4) >> 4;             // weight panel stride in 16-byte units
+    const uint32_t td = c.tmem + dcol;
+    uint32_t acc = accumulate;
+#pragma unroll 1
     for (int p = 0; p < c.passes; ++p) {
       const uint64_t da0 = (c.passes == 3 && p == 0) ? dAl : dAh;  // lo*hi, hi*lo, hi*hi
       const uint64_t db0 = (c.passes == 3 && p == 1) ? dWl : dWh;
-#pragma unroll 4
-      for (int ks = 0; ks < K / 8; ++ks) {
-        // start-address field is in 16-byte units: panel stride 128*32*4 B = 1024 units, 8 k = 32 B = 2 units
-        const uint64_t da = da0 + (uint64_t)((ks >> 2) * 1024 + (ks & 3) * 2);
-        const uint64_t db = db0 + (uint64_t)((ks >> 2) * wpan + (ks & 3) * 2);
-        umma::mma_tf32(c.tmem + dcol, da, db, idesc, acc);
-        acc = 1;
+      // start-address field is in 16-byte units: operand panel = 128*32*4 B = 1024 units, 8 k = 32 B = 2 units
+      umma::mma_tf32(td, da0, db0, idesc, acc);
+      umma::mma_tf32(td, da0 + 2, db0 + 2, idesc, 1);
+      umma::mma_tf32(td, da0 + 4, db0 + 4, idesc, 1);
+      umma::mma_tf32(td, da0 + 6, db0 + 6, idesc, 1);
+      if (K > 32) {
+        umma::mma_tf32(td, da0 + 1024, db0 + wpan, idesc, 1);
+        umma::mma_tf32(td, da0 + 1026, db0 + wpan + 2, idesc, 1);
+        umma::mma_tf32(td, da0 + 1028, db0 + wpan + 4, idesc, 1);
+        umma::mma_tf32(td, da0 + 1030, db0 + wpan + 6, idesc, 1);
       }
+      acc = 1;
     }
     umma::mma_commit(c.mbar);
   }
