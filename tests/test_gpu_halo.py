@@ -1,0 +1,70 @@
+"""Device-resident ghost halo: the C-ABI pack/unpack kernels plus
+alg_compute_device reproduce what LAMMPS forward_comm / reverse_comm do around the pair style:
+ghost x = owner x + image shift before the call, ghost f folded back onto the owners after it."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import alg_path, load_golden
+from test_gpu_parity import F_ATOL, make_pair
+
+pytestmark = pytest.mark.gpu
+
+
+def test_halo_pack_unpack_and_device_step(ensure_built):
+    from oracle import lmp_harness as H
+    from pair_allegro_b200 import capi
+    lib = capi.load_library()
+    name = "CuPd_r5"
+    atom, lst, z = load_golden(name)
+    nl, ng = atom.nlocal, atom.nghost
+    ntot = nl + ng
+    dev = torch.device("cuda:0")
+    owner = atom.owner[nl:].astype(np.int32)
+    shift = atom.x[nl:] - atom.x[owner]
+    d_x = torch.from_numpy(atom.x).to(dev)
+    d_x[nl:] = float("nan")                                   # ghosts must come from the halo
+    d_idx = torch.from_numpy(owner).to(dev)
+    d_shift = torch.from_numpy(np.ascontiguousarray(shift)).to(dev)
+    st = torch.cuda.current_stream().cuda_stream
+    # forward: pack straight into the ghost slice of x
+    assert lib.alg_halo_pack(d_x.data_ptr(), d_idx.data_ptr(), ng, d_shift.data_ptr(), d_x[nl:].data_ptr(), st) == 0
+    torch.cuda.synchronize()
+    assert np.array_equal(d_x.cpu().numpy(), atom.x)          # bit-exact ghost positions
+    # compute on device pointers
+    pair = make_pair(name, z, atom)
+    maxn = int(lst.numneigh.max())
+    nb = np.zeros((nl, maxn), dtype=np.int32)
+    for i in range(nl):
+        nb[i, :lst.numneigh[i]] = lst.firstneigh(i)
+    d_nb = torch.from_numpy(nb).to(dev)
+    d_num = torch.from_numpy(lst.numneigh[:nl].copy()).to(dev)
+    d_type = torch.from_numpy(atom.type).to(dev)
+    d_ilist = torch.arange(nl, dtype=torch.int32, device=dev)
+    d_f = torch.zeros(ntot, 3, dtype=torch.float64, device=dev)
+    pair.handle.compute_device(nl, ng, d_x.data_ptr(), d_type.data_ptr(), d_ilist.data_ptr(), d_num.data_ptr(), d_nb.data_ptr(),
+                               maxn, 1, d_f.data_ptr(), 0, want_scalars=True, stream=st)
+    # reverse: ghost forces -> owners (several images of one atom: list entries repeat)
+    assert lib.alg_halo_unpack_add(d_f.data_ptr(), d_idx.data_ptr(), ng, d_f[nl:].data_ptr(), st) == 0
+    torch.cuda.synchronize()
+    f_loc = d_f[:nl].cpu().numpy()
+    ref = H.reverse_comm_single_rank(atom, z["f"])
+    assert np.abs(f_loc - ref).max() < F_ATOL
+    assert np.abs(f_loc.sum(0)).max() < 1e-4                  # momentum conservation after the reverse halo
+
+
+def test_stats_and_timings(ensure_built):
+    name = "CuPd_r5"
+    atom, lst, z = load_golden(name)
+    pair = make_pair(name, z, atom, profile="1", chunk_edges="4096")
+    pair.compute(atom, lst)
+    h = pair.handle
+    st = h.stats("step", 4)
+    assert int(st[1]) == z["edge_index"].shape[1] and st[2] >= 2 and st[0] > 10      # edges, chunks, own launches
+    kms = h.stats("kernel_ms", 6)
+    kn = h.stats("kernel_launches", 6)
+    assert kms[:5].min() > 0 and kn[0] == st[2]               # one F0 launch per chunk
+    t = h.timings()
+    assert t.min() >= 0 and t[1] > 0
