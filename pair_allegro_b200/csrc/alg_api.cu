@@ -27,7 +27,7 @@ const Pipeline* get_pipeline(int L) {
   }
   return nullptr;
 }
-const Pipeline* get_pipeline_tc(int L) { return L == 1 ? get_pipeline_tc_L1() : nullptr; }
+const Pipeline* get_pipeline_tc(int L) { return L == 1 ? get_pipeline_tc_L1() : (L == 2 ? get_pipeline_tc_L2() : nullptr); }
 }  // namespace alg
 
 using namespace alg;
@@ -460,11 +460,15 @@ static int setup_model(alg_handle* h) {
     make(&tw.two0, H, 32, [&](int n, int k) { return k < B ? t0[(size_t)(2 * T + k) * H + n] : 0.f; });
     make(&tw.two1, H, H, [&](int n, int k) { return t1[(size_t)k * H + n]; });
     make(&tw.two2, S, H, [&](int n, int k) { return t2[(size_t)k * S + n]; });
-    make(&tw.emb, ENVW, S, [&](int n, int k) { return emb[(size_t)k * ENVW + n]; });
+    const int NBK = (ENVW + 63) / 64;                    // blocks of the l-indexed width
+    auto bwid = [&](int b) { return std::min(64, ENVW - 64 * b); };
+    for (int b = 0; b < NBK; ++b)
+      make(&tw.emb[b], bwid(b), S, [&](int n, int k) { return emb[(size_t)k * ENVW + 64 * b + n]; });
     make(&tw.two2_b, H, S, [&](int n, int k) { return t2[(size_t)n * S + k]; });
     make(&tw.two1_b, H, H, [&](int n, int k) { return t1[(size_t)n * H + k]; });
     make(&tw.two0_b, 32, H, [&](int n, int k) { return n < B ? t0[(size_t)(2 * T + n) * H + k] : 0.f; });
-    make(&tw.emb_b, S, ENVW, [&](int n, int k) { return emb[(size_t)n * ENVW + k]; });
+    for (int b = 0; b < NBK; ++b)
+      make(&tw.emb_b[b], S, bwid(b), [&](int n, int k) { return emb[(size_t)n * ENVW + 64 * b + k]; });
     make(&tw.ro0, R, S, [&](int n, int k) { return r0[(size_t)k * R + n]; });
     make(&tw.ro0_b, S, R, [&](int n, int k) { return r0[(size_t)n * R + k]; });
     for (int kk = 0; kk < h->nl; ++kk) {
@@ -473,15 +477,19 @@ static int setup_model(alg_handle* h) {
       const float* env = T_(pre + "env_linear");
       TcLayerW& tl = tw.layer[kk];
       make(&tl.m0x, H, S, [&](int n, int k) { return m0[(size_t)k * H + n]; });
-      make(&tl.m0s, H, SIN - S, [&](int n, int k) { return m0[(size_t)(S + k) * H + n]; });
+      for (int b = 0; b < NBK; ++b)
+        make(&tl.m0s[b], H, bwid(b), [&](int n, int k) { return m0[(size_t)(S + 64 * b + k) * H + n]; });
       make(&tl.m1, H, H, [&](int n, int k) { return m1[(size_t)k * H + n]; });
       make(&tl.m2, S, H, [&](int n, int k) { return m2[(size_t)k * S + n]; });
-      make(&tl.env, ENVW, S, [&](int n, int k) { return env[(size_t)k * ENVW + n]; });
+      for (int b = 0; b < NBK; ++b)
+        make(&tl.env[b], bwid(b), S, [&](int n, int k) { return env[(size_t)k * ENVW + 64 * b + n]; });
       make(&tl.m2_b, H, S, [&](int n, int k) { return m2[(size_t)n * S + k]; });
       make(&tl.m1_b, H, H, [&](int n, int k) { return m1[(size_t)n * H + k]; });
       make(&tl.m0_bx, S, H, [&](int n, int k) { return m0[(size_t)n * H + k]; });
-      make(&tl.m0_bs, SIN - S, H, [&](int n, int k) { return m0[(size_t)(S + n) * H + k]; });
-      make(&tl.env_b, S, ENVW, [&](int n, int k) { return env[(size_t)n * ENVW + k]; });
+      for (int b = 0; b < NBK; ++b)
+        make(&tl.m0_bs[b], bwid(b), H, [&](int n, int k) { return m0[(size_t)(S + 64 * b + n) * H + k]; });
+      for (int b = 0; b < NBK; ++b)
+        make(&tl.env_b[b], S, bwid(b), [&](int n, int k) { return env[(size_t)n * ENVW + 64 * b + k]; });
     }
     size_t tot = 0;
     for (Img& im : imgs) { im.off = tot; tot += 2 * (((size_t)im.N * im.K + 255) / 256 * 256); }
@@ -598,7 +606,7 @@ extern "C" int alg_set_option(alg_handle* h, const char* key, const char* value)
   else if (k == "gemm") {
     if (v == "ffma") { h->use_tc = false; h->pipe = h->pipe_ffma; }
     else if (v == "tc") {
-      if (!h->pipe_tc) return fail(h, ALG_EINVAL, "gemm=tc: the tensor-core pipeline of this build supports l_max = 1 only");
+      if (!h->pipe_tc) return fail(h, ALG_EINVAL, "gemm=tc: the tensor-core pipeline of this build supports l_max = 1, 2");
       h->use_tc = true; h->pipe = h->pipe_tc;
     } else return fail(h, ALG_EINVAL, "gemm must be ffma or tc");
     h->pinfo = h->pipe->info(h->nl);

@@ -1,6 +1,7 @@
-// Allegro B200 pipeline instantiation for l_max = 2
+// Allegro B200 pipeline instantiation for l_max = 2 (FP32-pipe path and tensor-core path)
 #define ALG_PIPELINE_IMPL
 #include "alg_pipeline.cuh"
 namespace alg {
 ALG_DEFINE_PIPELINE(2)
+ALG_DEFINE_PIPELINE_TC(2)
 }

@@ -26,9 +26,11 @@ namespace alg {
 struct TcMat { const float* hi; const float* lo; int N, K; };   // smem image: K/32 panels x N rows x 32 floats
 // every image is one MMA block: N <= 64 rows, K <= 64 columns (16 KB) so that a CTA needs only
 // ~104 KB of shared memory and two CTAs share an SM (their phases overlap)
-struct TcLayerW { TcMat m0x, m0s, m1, m2, env, m2_b, m1_b, m0_bx, m0_bs, env_b; };
+// matrices whose l-indexed dimension (width 32*(l_max+1)) exceeds 64 are split into blocks b = 0,1:
+// block b covers l in [2b, 2b+2) i.e. columns [64b, 64b + BW(b))
+struct TcLayerW { TcMat m0x, m0s[2], m1, m2, env[2], m2_b, m1_b, m0_bx, m0_bs[2], env_b[2]; };
 struct TcW {
-  TcMat two0, two1, two2, emb, two2_b, two1_b, two0_b, emb_b, ro0, ro0_b;
+  TcMat two0, two1, two2, emb[2], two2_b, two1_b, two0_b, emb_b[2], ro0, ro0_b;
   TcLayerW layer[3];
   int passes;     // 3 = strict (3xTF32), 1 = fast (TF32)
 };
@@ -42,10 +44,14 @@ template <int L> struct DimsTC {
   static constexpr int F = NSH * U;
   static constexpr int CPH = NT / TM;      // 2
   static constexpr int CPT = U / CPH;      // 16
-  static constexpr int WS = ENVW + 1;
-  static constexpr int CHU = 16;
+  static constexpr int NB = (NL + 1) / 2;               // 64-wide blocks of the l-indexed width
+  static constexpr int WS = 64 + 1;                     // W_s stride (one block at a time)
+  static constexpr int CHU = (L == 1) ? 16 : 4;         // channels per dGamma staging pass
   static constexpr int FC = NSH * CHU;
   static constexpr int DGS = FC + 1;
+  static constexpr int TB = (L == 1) ? 4 : 1;           // tensor-product channels whose loads are batched
+  __host__ __device__ static constexpr int bw(int b) { return (ENVW - 64 * b) < 64 ? (ENVW - 64 * b) : 64; }   // block width
+  __host__ __device__ static constexpr int lhi(int b) { return (2 * b + 2) < NL ? (2 * b + 2) : NL; }            // block covers l in [2b, lhi)
 };
 
 template <int L> struct SmemTC {
@@ -63,15 +69,21 @@ template <int L> struct SmemTC {
   static constexpr int oC = oU + TM;                   // int
   static constexpr int oZZ = oC + TM;                  // int
   static constexpr int oE = oZZ + TM;                  // 4*TM floats: per-half partials, E_e, du partial
-  static constexpr int GSROWS = 12;                    // staged per-centre rows (Gamma / dGamma) of the tile's centres
+  static constexpr int GSROWS = (L == 1) ? 12 : 0;     // staged per-centre rows (Gamma / dGamma); 0 = always read from global
   static constexpr int oGS = oE + 4 * TM;
   static constexpr int oSEG = oGS + GSROWS * D::F;     // int: segment table seg[TM+1], nseg, warp counts (TM + 16 ints)
   static constexpr int oBAR = oSEG + TM + 16;          // 2 mbarriers + tmem pointer (8 floats)
   static constexpr int TOTAL = oBAR + 8;
   static constexpr size_t BYTES = (size_t)TOTAL * sizeof(float) + 1024;   // + alignment slack
-  static_assert(L == 1, "tensor-core pipeline: shared-memory plan is sized for l_max = 1");
-  static_assert(D::ENVW == 64 && D::SIN == 128, "block plan below assumes l_max = 1 widths");
-  static_assert(D::WS * TM <= OPF + 2 * WBF && D::DGS * TM <= 2 * OPF, "staging buffers alias the operand / weight regions");
+  // buffers that alias the operand / weight regions once those are dead
+  static constexpr int oWS = oOPL;                                 // env weights of one block, edge-major [128][65]
+  static constexpr int oDS = (L == 1) ? oWBH : oOPL;               // ds rows [q*U+u][128] for the tensor-product backward
+  static constexpr int oDG = oOPH;                                 // dG staging [128][DGS]
+  static_assert(L == 1 || L == 2, "tensor-core pipeline: shared-memory plan covers l_max = 1, 2");
+  static_assert(D::WS * TM <= OPF + 2 * WBF, "W_s must fit OPL + weight region");
+  static_assert(oDS + D::ENVW * TM <= oY, "DS_s must end before the persistent small arrays");
+  static_assert(oDG + D::DGS * TM <= oDS || L == 1, "dG staging must not overlap DS_s");
+  static_assert(L != 1 || D::DGS * TM <= 2 * OPF, "dG staging (l_max = 1) spans OPH + OPL");
   static_assert(BYTES <= 113 * 1024, "two CTAs per SM");
 };
 
@@ -82,6 +94,8 @@ struct RowSrc {
   int c_origin;        // cmin or c0
   __device__ __forceinline__ const float* row(int centre, int F) const { return base + (size_t)(centre - c_origin) * F; }
 };
+
+constexpr uint32_t TC_SCR_COL = 192;    // scratch accumulator columns (see the TMEM map below)
 
 struct TcCtx {
   float* sm;
@@ -213,6 +227,15 @@ template <class Fn> __device__ __forceinline__ void tc_epi(const TcCtx& c, uint3
   for (int i = 0; i < 32; i += 4) fn(c0 + i, v[i], v[i + 1], v[i + 2], v[i + 3]);
   (void)NC;
 }
+// block epilogue: bw = 64 (32 columns per thread) or 32 (16 columns per thread)
+template <class Fn> __device__ __forceinline__ void tc_epi_bw(const TcCtx& c, uint32_t dcol, int bw, Fn fn) {
+  if (bw == 64) { tc_epi(c, dcol, 64, fn); return; }
+  const int c0 = c.half * 16;
+  float v[16];
+  umma::tmem_ld16(c.tmem + ((uint32_t)(c.q * 32) << 16) + dcol + c0, v);
+#pragma unroll
+  for (int i = 0; i < 16; i += 4) fn(c0 + i, v[i], v[i + 1], v[i + 2], v[i + 3]);
+}
 // load a 64-row tile-SoA array (x^k, dX) of this tile into operand columns [0,64)
 template <int L> __device__ __forceinline__ void op_load_rows64(const TcCtx& c, const float* __restrict__ g /*tile base [64][128]*/) {
   float v[32];
@@ -221,6 +244,16 @@ template <int L> __device__ __forceinline__ void op_load_rows64(const TcCtx& c, 
   for (int i = 0; i < 32; ++i) v[i] = __ldg(gp + i * 128);      // all loads in flight before the first use
 #pragma unroll
   for (int i = 0; i < 32; i += 4) op_put4<L>(c, c.half * 32 + i, v[i], v[i + 1], v[i + 2], v[i + 3]);
+}
+// same for a block of `bw` rows (64 or 32) -> operand columns [0,bw)
+template <int L> __device__ __forceinline__ void op_load_rows_bw(const TcCtx& c, const float* __restrict__ g, int bw) {
+  if (bw == 64) { op_load_rows64<L>(c, g); return; }
+  float v[16];
+  const float* gp = g + (c.half * 16) * 128 + c.m;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __ldg(gp + i * 128);
+#pragma unroll
+  for (int i = 0; i < 16; i += 4) op_put4<L>(c, c.half * 16 + i, v[i], v[i + 1], v[i + 2], v[i + 3]);
 }
 // this thread's 32 values (its column half) of a 64-row tile-SoA array, all loads issued together
 __device__ __forceinline__ void ld_rows32(const TcCtx& c, const float* __restrict__ g, float* v) {
@@ -274,30 +307,65 @@ template <int L> __device__ __forceinline__ Geom tc_geom(const ChunkArgs& a, con
   return g;
 }
 
-// env-weight GEMM output (TMEM columns [dcol, dcol+ENVW)) -> W_s (edge-major, stride WS) in the OPL region
-template <int L> __device__ __forceinline__ void tc_env_to_ws(const TcCtx& c, uint32_t dcol) {
+// env-weight GEMM output of block b (TMEM columns [dcol, dcol+bw)) -> W_s (edge-major, stride WS)
+template <int L> __device__ __forceinline__ void tc_env_to_ws(const TcCtx& c, uint32_t dcol, int bw) {
   using D = DimsTC<L>; using SM = SmemTC<L>;
-  float* W_s = c.sm + SM::oOPL;
-  tc_epi(c, dcol, D::ENVW, [&](int n, float v0, float v1, float v2, float v3) {
+  float* W_s = c.sm + SM::oWS;
+  tc_epi_bw(c, dcol, bw, [&](int n, float v0, float v1, float v2, float v3) {
     float* p = W_s + c.m * D::WS + n;
     p[0] = v0; p[1] = v1; p[2] = v2; p[3] = v3;
   });
 }
-template <int L> __device__ __forceinline__ void tc_env_sum(const ChunkArgs& a, const ModelW& w, const TcCtx& c, int tile, int es, int nvalid,
+// Gamma partial sums of the features whose l lies in block b (columns of W_s = (l-2b)*U+u)
+template <int L> __device__ __forceinline__ void tc_env_sum(const ChunkArgs& a, const ModelW& w, const TcCtx& c, int tile, int es, int b,
                                                              float* __restrict__ gamma) {
   using D = DimsTC<L>; using SM = SmemTC<L>; constexpr int TM = 128;
-  const float* W_s = c.sm + SM::oOPL;
+  const float* W_s = c.sm + SM::oWS;
   const float* Y_s = c.sm + SM::oY;
   const int* c_s = reinterpret_cast<const int*>(c.sm + SM::oC);
   const int* seg = reinterpret_cast<const int*>(c.sm + SM::oSEG);
   const bool contin = a.rowptr[c_s[0]] < es;
   float* carry = a.carry + (size_t)tile * D::F;
   const float sc = w.inv_sqrt_n;
-  segsum_items<D::F, TM>(c_s, seg,
-      [&](int e, int f) { const int lm = f / U, u = f % U; return W_s[e * D::WS + lsel(lm) * U + u] * Y_s[lm * TM + e]; },
-      [&](int centre, int f, bool first, float v) {
-        if (first && contin) carry[f] = v * sc; else gamma[(size_t)(centre - a.c0) * D::F + f] = v * sc;
-      });
+  const int lm_lo = (2 * b) * (2 * b), lm_hi = D::lhi(b) * D::lhi(b);
+  const int nseg = seg[TM + 1];
+  const int NFb = (lm_hi - lm_lo) * U;
+  for (int wi = threadIdx.x; wi < NFb * nseg; wi += NT) {
+    const int f = wi % NFb, sgm = wi / NFb;
+    const int lm = lm_lo + f / U, u = f % U;
+    const float* wcol = W_s + (lsel(lm) - 2 * b) * U + u;
+    const float* ycol = Y_s + lm * TM;
+    const int e0 = seg[sgm], e1 = seg[sgm + 1];
+    float acc = 0.f;
+    int e = e0;
+    for (; e + 4 <= e1; e += 4) {
+      const float v0 = wcol[e * D::WS] * ycol[e], v1 = wcol[(e + 1) * D::WS] * ycol[e + 1];
+      const float v2 = wcol[(e + 2) * D::WS] * ycol[e + 2], v3 = wcol[(e + 3) * D::WS] * ycol[e + 3];
+      acc += v0; acc += v1; acc += v2; acc += v3;
+    }
+    for (; e < e1; ++e) acc += wcol[e * D::WS] * ycol[e];
+    const int fg = lm * U + u;
+    if (sgm == 0 && contin) carry[fg] = acc * sc; else gamma[(size_t)(c_s[e0] - a.c0) * D::F + fg] = acc * sc;
+  }
+}
+// env linear of x (operand [0,64)) for all blocks -> Gamma.  In: weight block env[0] requested; the
+// MLP accumulators are dead (block b lands in TMEM columns TC_SCR_COL / 0).  All MMAs run before the
+// first epilogue because W_s aliases the lo operand and the weight region.
+template <int L> __device__ __forceinline__ void tc_env_all(const ChunkArgs& a, const ModelW& w, TcCtx& c, const TcMat* env, int tile, int es,
+                                                             float* __restrict__ gamma) {
+  using D = DimsTC<L>;
+#pragma unroll 1
+  for (int b = 0; b < D::NB; ++b) {
+    tc_mma<L>(c, 64, D::bw(b), b == 0 ? TC_SCR_COL : 0u);
+    if (b + 1 < D::NB) tc_load_w<L>(c, env[b + 1]);
+  }
+#pragma unroll 1
+  for (int b = 0; b < D::NB; ++b) {
+    tc_env_to_ws<L>(c, b == 0 ? TC_SCR_COL : 0u, D::bw(b));
+    __syncthreads();
+    tc_env_sum<L>(a, w, c, tile, es, b, gamma);
+    if (b + 1 < D::NB) __syncthreads();              // W_s is rewritten by the next block
+  }
 }
 
 // s-part operand column of (scalar path q, channel u): K index inside the 64-wide "s" block
@@ -325,35 +393,38 @@ __device__ __forceinline__ void tc_load_vin(const ChunkArgs& a, int tile, int k,
 // tensor product drivers: thread (edge e = m, channel phase uh = half), channels u = uh + 2 i,
 // processed in batches of TB channels with all global loads of a batch issued before any use
 // ============================================================================================
-constexpr int TB = 4;
-
-// forward: s -> operand columns [0, N0*U) (the "s" K-block); optionally V^{k+1} -> global
+// forward for K-block b of the "s" operand: s[q] for l = q in [2b, lhi(b)) -> operand column (q-2b)*U+u.
+// With WANT_V (block 0 only) the full product is evaluated and V^{k+1} stored; otherwise only the
+// scalar paths (identical order in every kind: path q pairs irrep (q,(-1)^q) of V with l2 = q).
 template <int L, char KIND, bool FIRST, bool WANT_V>
-__device__ __forceinline__ void tc_tp_forward(const ChunkArgs& a, const LayerW& lw, const TcCtx& c, int tile, int k, const RowSrc& gsrc) {
+__device__ __forceinline__ void tc_tp_forward(const ChunkArgs& a, const LayerW& lw, const TcCtx& c, int tile, int k, const RowSrc& gsrc, int b) {
   using D = DimsTC<L>; using SM = SmemTC<L>; using TP = tpgen::TP<L, KIND>; using TPA = tpgen::TP<L, 'A'>; constexpr int TM = 128;
+  constexpr int TB = D::TB;
   const float* Y_s = c.sm + SM::oY;
   const int* c_s = reinterpret_cast<const int*>(c.sm + SM::oC);
   const int e = c.m, uh = c.half;
   const float* gam = gsrc.row(c_s[e], D::F);
   float* Vng = WANT_V ? a.V[k + 1] + (size_t)tile * U * TP::DOUT * TM : nullptr;
+  const int q_lo = 2 * b, q_hi = D::lhi(b);
 #pragma unroll 1
   for (int i0 = 0; i0 < D::CPT; i0 += TB) {
     float Vin[TB][TP::DIN], G[TB][D::NSH];
 #pragma unroll
-    for (int b = 0; b < TB; ++b) {
-      const int u = uh + D::CPH * (i0 + b);
-      tc_load_vin<L, FIRST, TP::DIN>(a, tile, k, e, u, Y_s, Vin[b]);
+    for (int bb = 0; bb < TB; ++bb) {
+      const int u = uh + D::CPH * (i0 + bb);
+      tc_load_vin<L, FIRST, TP::DIN>(a, tile, k, e, u, Y_s, Vin[bb]);
 #pragma unroll
-      for (int lm = 0; lm < D::NSH; ++lm) G[b][lm] = gam[lm * U + u];
+      for (int lm = 0; lm < D::NSH; ++lm) G[bb][lm] = gam[lm * U + u];
     }
 #pragma unroll
-    for (int b = 0; b < TB; ++b) {
-      const int u = uh + D::CPH * (i0 + b);
+    for (int bb = 0; bb < TB; ++bb) {
+      const int u = uh + D::CPH * (i0 + bb);
       float Vout[TP::DOUT], s[TP::N0];
-      if (WANT_V) TP::template fwd<U>(Vin[b], G[b], lw.omega + u, Vout, s);
-      else TPA::template fwd<U>(Vin[b], G[b], nullptr, nullptr, s);     // scalar paths only (same order in every kind)
+      if (WANT_V) TP::template fwd<U>(Vin[bb], G[bb], lw.omega + u, Vout, s);
+      else TPA::template fwd<U>(Vin[bb], G[bb], nullptr, nullptr, s);
 #pragma unroll
-      for (int q = 0; q < TP::N0; ++q) op_put1<L>(c, e, s_col(q, u), s[q]);
+      for (int q = 0; q < TP::N0; ++q)
+        if (q >= q_lo && q < q_hi) op_put1<L>(c, e, (q - q_lo) * U + u, s[q]);
       if (WANT_V) {
 #pragma unroll
         for (int cc = 0; cc < TP::DOUT; ++cc) Vng[(u * TP::DOUT + cc) * TM + e] = Vout[cc];
@@ -370,8 +441,9 @@ __device__ __forceinline__ void tc_tp_backward(const ChunkArgs& a, const LayerW&
                                                float* __restrict__ dgamma_out, float* dYp, const RowSrc& gsrc) {
   using D = DimsTC<L>; using SM = SmemTC<L>; using TP = tpgen::TP<L, KIND>; constexpr int TM = 128;
   const int t = threadIdx.x;
-  const float* DS_s = c.sm + SM::oWBH;
-  float* DG = c.sm + SM::oOPH;
+  constexpr int TB = D::TB;
+  const float* DS_s = c.sm + SM::oDS;
+  float* DG = c.sm + SM::oDG;
   const float* Y_s = c.sm + SM::oY;
   const int* c_s = reinterpret_cast<const int*>(c.sm + SM::oC);
   const int e = c.m, uh = c.half;
@@ -519,34 +591,51 @@ __device__ __forceinline__ void tc_mlp_bwd_hidden(TcCtx& c, const TcMat& w1_b, c
   }
 }
 
-// dz1 in operand, m0_bx requested: dX(global) += dz1 W0x^T ; ds = dz1 W0s^T -> DS_s (weight region)
+// dz1 in operand, m0_bx requested: dX(global) += dz1 W0x^T ; ds = dz1 W0s^T -> DS_s.
+// ds of all blocks is held in registers until the last MMA has read the operand / weight regions
+// that DS_s aliases.
 template <int L>
 __device__ __forceinline__ void tc_din(TcCtx& c, const TcLayerW& tl, float* __restrict__ dXg) {
-  using SM = SmemTC<L>; constexpr int TM = 128;
+  using D = DimsTC<L>; using SM = SmemTC<L>; constexpr int TM = 128;
   float dp[32];
   ld_rows32(c, dXg, dp);                              // in flight during the MMA
   tc_mma<L>(c, 64, 64, TC_SCR);
-  tc_load_w<L>(c, tl.m0_bs);
+  tc_load_w<L>(c, tl.m0_bs[0]);
   tc_epi(c, TC_SCR, 64, [&](int n, float v0, float v1, float v2, float v3) {
     const int j = n - c.half * 32;
     dXg[(n + 0) * TM + c.m] = dp[j] + v0; dXg[(n + 1) * TM + c.m] = dp[j + 1] + v1;
     dXg[(n + 2) * TM + c.m] = dp[j + 2] + v2; dXg[(n + 3) * TM + c.m] = dp[j + 3] + v3;
   });
-  tc_mma<L>(c, 64, 64, TC_SCR);                       // same operand (dz1), second weight block
-  float* DS_s = c.sm + SM::oWBH;                       // the weight region is free now
-  tc_epi(c, TC_SCR, 64, [&](int n, float v0, float v1, float v2, float v3) {
-    DS_s[(n + 0) * TM + c.m] = v0; DS_s[(n + 1) * TM + c.m] = v1; DS_s[(n + 2) * TM + c.m] = v2; DS_s[(n + 3) * TM + c.m] = v3;
-  });
+  float dsr[D::NB][32];                               // this thread's ds values per block (32 or 16 used)
+#pragma unroll
+  for (int b = 0; b < D::NB; ++b) {
+    tc_mma<L>(c, 64, D::bw(b), TC_SCR);               // same operand (dz1), next weight block
+    if (b + 1 < D::NB) tc_load_w<L>(c, tl.m0_bs[b + 1]);
+    tc_epi_bw(c, TC_SCR, D::bw(b), [&](int n, float v0, float v1, float v2, float v3) {
+      const int j = n - c.half * (D::bw(b) / 2);
+      dsr[b][j] = v0; dsr[b][j + 1] = v1; dsr[b][j + 2] = v2; dsr[b][j + 3] = v3;
+    });
+  }
+  umma::fence_before_sync();
+  __syncthreads();                                     // every thread has finished its TMEM reads; operands / weights are dead
+  float* DS_s = c.sm + SM::oDS;
+#pragma unroll
+  for (int b = 0; b < D::NB; ++b) {
+#pragma unroll
+    for (int j = 0; j < D::bw(b) / 2; ++j) DS_s[(64 * b + c.half * (D::bw(b) / 2) + j) * TM + c.m] = dsr[b][j];
+  }
   __syncthreads();
 }
 
-// phase 2 of layer kk.  In: x^kk in operand [0,64), weight block env_kk requested.
-// Out: dw (operand [0,64)), DY_s = d/dY of the environment sum; requests `next`.
+// phase 2 of layer kk.  In: x^kk in operand [0,64), weight block env[0] requested, dsrc = dGamma_kk rows.
+// For every block b: w_b = x env_b (TMEM) -> dw_b (operand), dY partial; then dxacc += dw_b env_b^T.
+// With emb_b != nullptr (layer 0 in B0) the embed backward dw0 emb^T is accumulated as well.
+// Out: dxacc[32] = this thread's 32 columns of the correction to dx^kk, DY_s = d/dY of the env sum.
+// Requests `next` before the last epilogue.
 template <int L>
-__device__ __forceinline__ void tc_phase2(const ChunkArgs& a, const ModelW& w, TcCtx& c, int kk, const TcMat& next, const RowSrc& dsrc) {
+__device__ __forceinline__ void tc_phase2(const ChunkArgs& a, const ModelW& w, TcCtx& c, const TcLayerW& tl, const TcMat* emb_b, int tile,
+                                          const float* __restrict__ Xtile, const TcMat& next, const RowSrc& dsrc, float* dxacc) {
   using D = DimsTC<L>; using SM = SmemTC<L>; constexpr int TM = 128;
-  tc_mma<L>(c, 64, D::ENVW, TC_SCR);
-  tc_load_w<L>(c, next);
   const float* Y_s = c.sm + SM::oY;
   const int* c_s = reinterpret_cast<const int*>(c.sm + SM::oC);
   float* DY_s = c.sm + SM::oDY;
@@ -555,23 +644,53 @@ __device__ __forceinline__ void tc_phase2(const ChunkArgs& a, const ModelW& w, T
 #pragma unroll
   for (int lm = 0; lm < D::NSH; ++lm) dYp[lm] = 0.f;
 #pragma unroll
-  for (int l = 0; l <= L; ++l) {
-    float wv[16], dw[16];
-    tc_ld16(c, TC_SCR + l * U + c.half * 16, wv);
+  for (int i = 0; i < 32; ++i) dxacc[i] = 0.f;
+  // w of ALL blocks must be computed from x before the operand is overwritten by dw: TMEM scratch holds
+  // one block, so x is re-staged from global for every further block (NB <= 2)
+#pragma unroll 1
+  for (int b = 0; b < D::NB; ++b) {
+    tc_mma<L>(c, 64, D::bw(b), TC_SCR);                // w_b = x env_b
+    tc_load_w<L>(c, tl.env_b[b]);
 #pragma unroll
-    for (int i = 0; i < 16; ++i) {
-      const int u = c.half * 16 + i;
-      float acc = 0.f;
+    for (int l = 2 * b; l < D::lhi(b); ++l) {
+      float wv[16], dw[16];
+      tc_ld16(c, TC_SCR + (l - 2 * b) * U + c.half * 16, wv);
 #pragma unroll
-      for (int lm = l * l; lm < (l + 1) * (l + 1); ++lm) {
-        const float dg = dgam[lm * U + u] * w.inv_sqrt_n;
-        acc += dg * Y_s[lm * TM + c.m];
-        dYp[lm] += dg * wv[i];
+      for (int i = 0; i < 16; ++i) {
+        const int u = c.half * 16 + i;
+        float acc = 0.f;
+#pragma unroll
+        for (int lm = l * l; lm < (l + 1) * (l + 1); ++lm) {
+          const float dg = dgam[lm * U + u] * w.inv_sqrt_n;
+          acc += dg * Y_s[lm * TM + c.m];
+          dYp[lm] += dg * wv[i];
+        }
+        dw[i] = acc;
       }
-      dw[i] = acc;
-    }
 #pragma unroll
-    for (int i = 0; i < 16; i += 4) op_put4<L>(c, l * U + c.half * 16 + i, dw[i], dw[i + 1], dw[i + 2], dw[i + 3]);
+      for (int i = 0; i < 16; i += 4) op_put4<L>(c, (l - 2 * b) * U + c.half * 16 + i, dw[i], dw[i + 1], dw[i + 2], dw[i + 3]);
+    }
+    tc_mma<L>(c, D::bw(b), 64, TC_SCR);                // dw_b env_b^T
+    if (b + 1 < D::NB) tc_load_w<L>(c, tl.env[b + 1]);
+    else if (emb_b) tc_load_w<L>(c, emb_b[0]);
+    else tc_load_w<L>(c, next);
+    tc_epi(c, TC_SCR, 64, [&](int n, float v0, float v1, float v2, float v3) {
+      const int j = n - c.half * 32;
+      dxacc[j] += v0; dxacc[j + 1] += v1; dxacc[j + 2] += v2; dxacc[j + 3] += v3;
+    });
+    if (b + 1 < D::NB) op_load_rows64<L>(c, Xtile);        // x again for the next block's w
+  }
+  if (emb_b) {
+#pragma unroll 1
+    for (int b = 0; b < D::NB; ++b) {
+      op_load_rows_bw<L>(c, a.W0 + ((size_t)tile * D::ENVW + 64 * b) * TM, D::bw(b));     // dw0 block
+      tc_mma<L>(c, D::bw(b), 64, TC_SCR);
+      if (b + 1 < D::NB) tc_load_w<L>(c, emb_b[b + 1]); else tc_load_w<L>(c, next);
+      tc_epi(c, TC_SCR, 64, [&](int n, float v0, float v1, float v2, float v3) {
+        const int j = n - c.half * 32;
+        dxacc[j] += v0; dxacc[j + 1] += v1; dxacc[j + 2] += v2; dxacc[j + 3] += v3;
+      });
+    }
   }
   if (c.half == 1) {
 #pragma unroll
@@ -616,7 +735,7 @@ __global__ void __launch_bounds__(NT, 2) k_f0_tc(const __grid_constant__ ChunkAr
   tc_load_w<L>(c, tw.two1);
   const float* w0 = w.two.w[0];
   const float* wi = w0 + g.zi * H; const float* wj = w0 + (w.T + g.zj) * H;
-  tc_mlp_hidden_fwd<L>(c, tw.two2, tw.emb, [&](int n) { return __ldg(wi + n) + __ldg(wj + n); });
+  tc_mlp_hidden_fwd<L>(c, tw.two2, tw.emb[0], [&](int n) { return __ldg(wi + n) + __ldg(wj + n); });
   {
     float* X0g = a.X[0] + (size_t)tile * S * TM;
     tc_epi(c, TC_M, 64, [&](int n, float v0, float v1, float v2, float v3) {
@@ -625,35 +744,38 @@ __global__ void __launch_bounds__(NT, 2) k_f0_tc(const __grid_constant__ ChunkAr
       X0g[(n + 0) * TM + c.m] = v0; X0g[(n + 1) * TM + c.m] = v1; X0g[(n + 2) * TM + c.m] = v2; X0g[(n + 3) * TM + c.m] = v3;
     });
   }
-  tc_mma<L>(c, 64, D::ENVW, TC_SCR);                 // embed linear
-  tc_load_w<L>(c, tw.layer[0].env);
-  {
+  {  // embed linear (all blocks) -> w0 in HBM/L2
     float* W0g = a.W0 + (size_t)tile * D::ENVW * TM;
-    tc_epi(c, TC_SCR, D::ENVW, [&](int n, float v0, float v1, float v2, float v3) {
-      W0g[(n + 0) * TM + c.m] = v0; W0g[(n + 1) * TM + c.m] = v1; W0g[(n + 2) * TM + c.m] = v2; W0g[(n + 3) * TM + c.m] = v3;
-    });
+#pragma unroll 1
+    for (int b = 0; b < D::NB; ++b) {
+      tc_mma<L>(c, 64, D::bw(b), TC_SCR);
+      if (b + 1 < D::NB) tc_load_w<L>(c, tw.emb[b + 1]); else tc_load_w<L>(c, tw.layer[0].env[0]);
+      tc_epi_bw(c, TC_SCR, D::bw(b), [&](int n, float v0, float v1, float v2, float v3) {
+        float* p = W0g + (size_t)(64 * b + n) * TM + c.m;
+        p[0] = v0; p[TM] = v1; p[2 * TM] = v2; p[3 * TM] = v3;
+      });
+    }
   }
-  tc_mma<L>(c, 64, D::ENVW, TC_SCR);                 // env linear of layer 0 (same operand x^0)
-  tc_env_to_ws<L>(c, TC_SCR);
-  __syncthreads();
-  tc_env_sum<L>(a, w, c, tile, es, nvalid, a.gamma[0]);
+  tc_env_all<L>(a, w, c, tw.layer[0].env, tile, es, a.gamma[0]);    // env linear of layer 0 (same operand x^0)
   tc_end(c);
 }
 
-// layer-0 GEMM of a latent MLP: z1 = [x || s] W0 as two accumulating K-blocks (s first, then x)
-// in: weight block m0s requested, geometry published.  out: z1 in TMEM, m1 requested.
+// layer-0 GEMM of a latent MLP: z1 = [x || s] W0 as accumulating K-blocks (s blocks first, then x)
+// in: weight block m0s[0] requested, geometry published.  out: z1 in TMEM, m1 requested.
 template <int L, char KIND, bool FIRST, bool WANT_V>
 __device__ __forceinline__ void tc_latent_z1(const ChunkArgs& a, const LayerW& lw, const TcLayerW& tl, TcCtx& c, int tile, int k,
                                              const float* __restrict__ Xg, const RowSrc& gsrc) {
-  tc_tp_forward<L, KIND, FIRST, WANT_V>(a, lw, c, tile, k, gsrc);
-  ALG_TS(a, 2, 16);
-  tc_mma<L>(c, 64, 64, TC_Z1, 0);
-  ALG_TS(a, 2, 17);
+  using D = DimsTC<L>;
+  tc_tp_forward<L, KIND, FIRST, WANT_V>(a, lw, c, tile, k, gsrc, 0);
+  tc_mma<L>(c, D::bw(0), 64, TC_Z1, 0);
+  if (D::NB > 1) {
+    tc_load_w<L>(c, tl.m0s[1]);
+    tc_tp_forward<L, KIND, FIRST, false>(a, lw, c, tile, k, gsrc, 1);
+    tc_mma<L>(c, D::bw(D::NB - 1), 64, TC_Z1, 1);
+  }
   tc_load_w<L>(c, tl.m0x);
   op_load_rows64<L>(c, Xg);
-  ALG_TS(a, 2, 18);
   tc_mma<L>(c, 64, 64, TC_Z1, 1);
-  ALG_TS(a, 2, 19);
   tc_load_w<L>(c, tl.m1);
 }
 
@@ -670,14 +792,14 @@ __global__ void __launch_bounds__(NT, 2) k_fk_tc(const __grid_constant__ ChunkAr
   const int nvalid = min(TM, a.e1 - es);
   const LayerW& lw = w.layer[k];
   const TcLayerW& tl = tw.layer[k];
-  tc_load_w<L>(c, tl.m0s);
+  tc_load_w<L>(c, tl.m0s[0]);
   const Geom g = tc_geom<L>(a, w, c, es, nvalid);
   const float* Xg = a.X[k] + (size_t)tile * S * TM;
   __syncthreads();
   seg_build<TM>(reinterpret_cast<const int*>(c.sm + SM::oC), nvalid, reinterpret_cast<int*>(c.sm + SM::oSEG));
   const RowSrc gsrc = tc_stage_rows<L>(c, a.gamma[k], a.c0, nvalid);
   tc_latent_z1<L, KIND, FIRST, true>(a, lw, tl, c, tile, k, Xg, gsrc);
-  tc_mlp_hidden_fwd<L>(c, tl.m2, tw.layer[k + 1].env, NoBias());
+  tc_mlp_hidden_fwd<L>(c, tl.m2, tw.layer[k + 1].env[0], NoBias());
   {
     float* Xng = a.X[k + 1] + (size_t)tile * S * TM;
     float xp[32];
@@ -690,10 +812,7 @@ __global__ void __launch_bounds__(NT, 2) k_fk_tc(const __grid_constant__ ChunkAr
       Xng[(n + 0) * TM + c.m] = x0; Xng[(n + 1) * TM + c.m] = x1; Xng[(n + 2) * TM + c.m] = x2; Xng[(n + 3) * TM + c.m] = x3;
     });
   }
-  tc_mma<L>(c, 64, D::ENVW, TC_SCR);
-  tc_env_to_ws<L>(c, TC_SCR);
-  __syncthreads();
-  tc_env_sum<L>(a, w, c, tile, es, nvalid, a.gamma[k + 1]);
+  tc_env_all<L>(a, w, c, tw.layer[k + 1].env, tile, es, a.gamma[k + 1]);
   tc_end(c);
 }
 
@@ -711,7 +830,7 @@ __global__ void __launch_bounds__(NT, 2) k_t_tc(const __grid_constant__ ChunkArg
   const LayerW& lw = w.layer[k];
   const TcLayerW& tl = tw.layer[k];
   ALG_TS(a, 2, 0);
-  tc_load_w<L>(c, tl.m0s);
+  tc_load_w<L>(c, tl.m0s[0]);
   const Geom g = tc_geom<L>(a, w, c, es, nvalid);
   const float* Xg = a.X[k] + (size_t)tile * S * TM;
   __syncthreads();
@@ -823,25 +942,25 @@ __global__ void __launch_bounds__(NT, 2) k_bk_tc(const __grid_constant__ ChunkAr
   const int nvalid = min(TM, a.e1 - es);
   const LayerW& lw = w.layer[k];
   const TcLayerW& tl = tw.layer[k];
-  tc_load_w<L>(c, tw.layer[k + 1].env);
+  tc_load_w<L>(c, tw.layer[k + 1].env[0]);
   const Geom g = tc_geom<L>(a, w, c, es, nvalid);
-  op_load_rows64<L>(c, a.X[k + 1] + (size_t)tile * S * TM);
+  const float* Xn = a.X[k + 1] + (size_t)tile * S * TM;
+  op_load_rows64<L>(c, Xn);
   __syncthreads();
   seg_build<TM>(reinterpret_cast<const int*>(c.sm + SM::oC), nvalid, reinterpret_cast<int*>(c.sm + SM::oSEG));
   float* dXg = a.dX + (size_t)tile * S * TM;
   const RowSrc dsrc = tc_stage_rows<L>(c, a.dgamma[k + 1], a.c0, nvalid);
-  tc_phase2<L>(a, w, c, k + 1, tw.layer[k + 1].env_b, dsrc);
   float dxn[32];                                      // complete dx^{k+1} of this thread's 32 columns (kept in registers)
-  ld_rows32(c, dXg, dxn);
-  tc_mma<L>(c, D::ENVW, 64, TC_SCR);                  // dw env^T
-  tc_load_w<L>(c, tl.m0s);
-  tc_epi(c, TC_SCR, 64, [&](int n, float v0, float v1, float v2, float v3) {
-    const int j = n - c.half * 32;
-    dxn[j] += v0; dxn[j + 1] += v1; dxn[j + 2] += v2; dxn[j + 3] += v3;
-  });
+  tc_phase2<L>(a, w, c, tw.layer[k + 1], nullptr, tile, Xn, tl.m0s[0], dsrc, dxn);
+  {
+    float dp[32];
+    ld_rows32(c, dXg, dp);
+#pragma unroll
+    for (int i = 0; i < 32; ++i) dxn[i] += dp[i];
+  }
   // ---- recompute layer k forward (z1, z2, m stay in TMEM)
   const float* Xg = a.X[k] + (size_t)tile * S * TM;
-  const RowSrc gsrc = tc_stage_rows<L>(c, a.gamma[k], a.c0, nvalid);    // dGamma rows are consumed (barrier inside tc_mma)
+  const RowSrc gsrc = tc_stage_rows<L>(c, a.gamma[k], a.c0, nvalid);    // dGamma rows are consumed (barriers inside tc_mma)
   tc_latent_z1<L, KIND, FIRST, false>(a, lw, tl, c, tile, k, Xg, gsrc);
   tc_mlp_hidden_fwd<L>(c, tl.m2, tl.m2_b, NoBias());
   {
@@ -914,18 +1033,13 @@ __global__ void __launch_bounds__(NT, 2) k_b0_tc(const __grid_constant__ ChunkAr
   const float* w0 = w.two.w[0];
   const float* wi = w0 + g.zi * H; const float* wj = w0 + (w.T + g.zj) * H;
   auto bias = [&](int n) { return __ldg(wi + n) + __ldg(wj + n); };
-  tc_mlp_hidden_fwd<L>(c, tw.two2, tw.layer[0].env, bias);
+  tc_mlp_hidden_fwd<L>(c, tw.two2, tw.layer[0].env[0], bias);
   // ---- phase 2 of layer 0 and the embed backward: dx0 = dX + dw env0^T + dw0 emb^T
-  op_load_rows64<L>(c, a.X[0] + (size_t)tile * S * TM);
+  const float* X0 = a.X[0] + (size_t)tile * S * TM;
+  op_load_rows64<L>(c, X0);
   const RowSrc dsrc = tc_stage_rows<L>(c, a.dgamma[0], a.c0, nvalid);
-  tc_phase2<L>(a, w, c, 0, tw.layer[0].env_b, dsrc);
-  tc_mma<L>(c, D::ENVW, 64, TC_SCR, 0);
-  tc_load_w<L>(c, tw.emb_b);
-  {
-    op_load_rows64<L>(c, a.W0 + (size_t)tile * D::ENVW * TM);   // dw0 (written by the layer-0 TP backward)
-  }
-  tc_mma<L>(c, D::ENVW, 64, TC_SCR, 1);
-  tc_load_w<L>(c, tw.two2_b);
+  float dx0[32];
+  tc_phase2<L>(a, w, c, tw.layer[0], tw.emb_b, tile, X0, tw.two2_b, dsrc, dx0);
   const float* dXg = a.dX + (size_t)tile * S * TM;
   float du_tot;
   {
@@ -934,12 +1048,12 @@ __global__ void __launch_bounds__(NT, 2) k_b0_tc(const __grid_constant__ ChunkAr
     ld_rows32(c, dXg, dp);
     for (int c0 = c.half * 32; c0 < c.half * 32 + 32; c0 += 16) {
       float v[16], mv[16];
-      tc_ld16x2(c, TC_SCR + c0, v, TC_M + c0, mv);
+      tc_ld16(c, TC_M + c0, mv);
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
-        const float dx0 = v[i] + dp[c0 - c.half * 32 + i];
-        dup += dx0 * mv[i];
-        v[i] = dx0 * g.u;
+        const float dxv = dx0[c0 - c.half * 32 + i] + dp[c0 - c.half * 32 + i];
+        dup += dxv * mv[i];
+        v[i] = dxv * g.u;
       }
 #pragma unroll
       for (int i = 0; i < 16; i += 4) op_put4<L>(c, c0 + i, v[i], v[i + 1], v[i + 2], v[i + 3]);

@@ -11,7 +11,8 @@ from test_gpu_parity import E_ATOL, E_RTOL, F_ATOL, V_RTOL, _random_system, chec
 
 pytestmark = pytest.mark.gpu
 
-L1_CASES = ["Cu_r5", "Cu_r15", "aspirin_r15"]     # golden cases with l_max = 1 (2, 1, 2 layers)
+L1_CASES = ["Cu_r5", "Cu_r15", "aspirin_r15",     # golden cases with l_max = 1 (2, 1, 2 layers)
+            "CuPd_r5", "aspirin_r5"]              # and l_max = 2 (3, 2 layers)
 
 
 @pytest.mark.parametrize("name", L1_CASES)
@@ -26,7 +27,7 @@ def test_tc_golden_parity(name, ensure_built):
     assert err_ours < max(10 * err_ref, 2e-5)
 
 
-@pytest.mark.parametrize("name", ["Cu_r15", "aspirin_r15"])
+@pytest.mark.parametrize("name", ["Cu_r15", "aspirin_r15", "CuPd_r5"])
 def test_tc_multichunk(name, ensure_built):
     atom, lst, z = load_golden(name)
     pair = make_pair(name, z, atom, gemm="tc", chunk_edges="4096")
@@ -77,8 +78,8 @@ def test_tc_intermediates(name, ensure_built):
     assert not bad, bad
 
 
-@pytest.mark.parametrize("nl,ntypes", [(1, 1), (2, 2), (3, 3)])
-def test_tc_live_oracle(nl, ntypes, ensure_built, tmp_path):
+@pytest.mark.parametrize("nl,ntypes,lmax", [(1, 1, 1), (2, 2, 1), (3, 3, 1), (1, 2, 2), (2, 1, 2), (3, 2, 2)])
+def test_tc_live_oracle(nl, ntypes, lmax, ensure_built, tmp_path):
     from oracle import allegro_torch as AT
     from oracle import lmp_harness as H
     from oracle.ref_pair import RefPairAllegro
@@ -88,9 +89,9 @@ def test_tc_live_oracle(nl, ntypes, ensure_built, tmp_path):
     pos, types, cell = _random_system(200, 14.0, ntypes, seed=50 + nl)
     atoms = H.make_single_rank(types, pos, cell, [True] * 3, 5.5)
     lst = H.build_full_list(atoms, 5.5)
-    cfg = AT.default_config(type_names=names, r_max=4.5, l_max=1, num_layers=nl, avg_num_neighbors=20.0,
+    cfg = AT.default_config(type_names=names, r_max=4.5, l_max=lmax, num_layers=nl, avg_num_neighbors=20.0,
                             per_type_energy_scales=[1.0 + 0.1 * t for t in range(ntypes)],
-                            per_type_energy_shifts=[0.3 * t for t in range(ntypes)], num_bessels=8 if nl != 3 else 12, seed=77 + nl)
+                            per_type_energy_shifts=[0.3 * t for t in range(ntypes)], num_bessels=8 if nl != 3 else 12, seed=77 + nl + 10 * lmax)
     pth = str(tmp_path / "m.nequip.pth")
     AT.save_torchscript(cfg, pth)
     export_alg(pth, str(tmp_path / "m.alg"))
@@ -120,7 +121,7 @@ def test_tc_live_oracle(nl, ntypes, ensure_built, tmp_path):
 
 def test_tc_rejects_unsupported_lmax(ensure_built):
     from pair_allegro_b200 import capi
-    atom, lst, z = load_golden("CuPd_r5")          # l_max = 2
-    pair = make_pair("CuPd_r5", z, atom)
-    with pytest.raises(capi.AllegroError, match="l_max = 1"):
+    atom, lst, z = load_golden("Cu2AgO4_r5")       # l_max = 3
+    pair = make_pair("Cu2AgO4_r5", z, atom)
+    with pytest.raises(capi.AllegroError, match="l_max = 1, 2"):
         pair.handle.set_option("gemm", "tc")
