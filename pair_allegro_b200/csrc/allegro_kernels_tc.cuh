@@ -606,23 +606,29 @@ __device__ __forceinline__ void tc_din(TcCtx& c, const TcLayerW& tl, float* __re
     dXg[(n + 0) * TM + c.m] = dp[j] + v0; dXg[(n + 1) * TM + c.m] = dp[j + 1] + v1;
     dXg[(n + 2) * TM + c.m] = dp[j + 2] + v2; dXg[(n + 3) * TM + c.m] = dp[j + 3] + v3;
   });
-  float dsr[D::NB][32];                               // this thread's ds values per block (32 or 16 used)
-#pragma unroll
-  for (int b = 0; b < D::NB; ++b) {
-    tc_mma<L>(c, 64, D::bw(b), TC_SCR);               // same operand (dz1), next weight block
-    if (b + 1 < D::NB) tc_load_w<L>(c, tl.m0_bs[b + 1]);
-    tc_epi_bw(c, TC_SCR, D::bw(b), [&](int n, float v0, float v1, float v2, float v3) {
-      const int j = n - c.half * (D::bw(b) / 2);
-      dsr[b][j] = v0; dsr[b][j + 1] = v1; dsr[b][j + 2] = v2; dsr[b][j + 3] = v3;
-    });
-  }
-  umma::fence_before_sync();
-  __syncthreads();                                     // every thread has finished its TMEM reads; operands / weights are dead
   float* DS_s = c.sm + SM::oDS;
+  if constexpr (D::NB == 1) {
+    // DS_s aliases only the weight region, dead once the (single) MMA has completed
+    tc_mma<L>(c, 64, 64, TC_SCR);
+    tc_epi(c, TC_SCR, 64, [&](int n, float v0, float v1, float v2, float v3) {
+      float* p = DS_s + n * TM + c.m;
+      p[0] = v0; p[TM] = v1; p[2 * TM] = v2; p[3 * TM] = v3;
+    });
+  } else {
+    float dsr[32];                                    // block 0 is held in registers: DS_s aliases the lo operand of block 1's MMA
+    tc_mma<L>(c, 64, 64, TC_SCR);
+    tc_load_w<L>(c, tl.m0_bs[1]);
+    tc_epi(c, TC_SCR, 64, [&](int n, float v0, float v1, float v2, float v3) {
+      const int j = n - c.half * 32;
+      dsr[j] = v0; dsr[j + 1] = v1; dsr[j + 2] = v2; dsr[j + 3] = v3;
+    });
+    tc_mma<L>(c, 64, D::bw(1), TC_SCR);               // same operand (dz1); operands / weights are dead afterwards
 #pragma unroll
-  for (int b = 0; b < D::NB; ++b) {
-#pragma unroll
-    for (int j = 0; j < D::bw(b) / 2; ++j) DS_s[(64 * b + c.half * (D::bw(b) / 2) + j) * TM + c.m] = dsr[b][j];
+    for (int j = 0; j < 32; ++j) DS_s[(c.half * 32 + j) * TM + c.m] = dsr[j];
+    tc_epi_bw(c, TC_SCR, D::bw(1), [&](int n, float v0, float v1, float v2, float v3) {
+      float* p = DS_s + (64 + n) * TM + c.m;
+      p[0] = v0; p[TM] = v1; p[2 * TM] = v2; p[3 * TM] = v3;
+    });
   }
   __syncthreads();
 }
@@ -674,24 +680,26 @@ __device__ __forceinline__ void tc_phase2(const ChunkArgs& a, const ModelW& w, T
     if (b + 1 < D::NB) tc_load_w<L>(c, tl.env[b + 1]);
     else if (emb_b) tc_load_w<L>(c, emb_b[0]);
     else tc_load_w<L>(c, next);
-    tc_epi(c, TC_SCR, 64, [&](int n, float v0, float v1, float v2, float v3) {
-      const int j = n - c.half * 32;
-      dxacc[j] += v0; dxacc[j + 1] += v1; dxacc[j + 2] += v2; dxacc[j + 3] += v3;
-    });
-    if (b + 1 < D::NB) op_load_rows64<L>(c, Xtile);        // x again for the next block's w
-  }
-  if (emb_b) {
-#pragma unroll 1
-    for (int b = 0; b < D::NB; ++b) {
-      op_load_rows_bw<L>(c, a.W0 + ((size_t)tile * D::ENVW + 64 * b) * TM, D::bw(b));     // dw0 block
-      tc_mma<L>(c, D::bw(b), 64, TC_SCR);
-      if (b + 1 < D::NB) tc_load_w<L>(c, emb_b[b + 1]); else tc_load_w<L>(c, next);
+    if (b + 1 < D::NB) {                                // scratch is needed for the next block's w: drain to registers
       tc_epi(c, TC_SCR, 64, [&](int n, float v0, float v1, float v2, float v3) {
         const int j = n - c.half * 32;
         dxacc[j] += v0; dxacc[j + 1] += v1; dxacc[j + 2] += v2; dxacc[j + 3] += v3;
       });
+      op_load_rows64<L>(c, Xtile);                      // x again for the next block's w
     }
   }
+  if (emb_b) {                                          // embed backward accumulates onto the last block's product in TMEM
+#pragma unroll 1
+    for (int b = 0; b < D::NB; ++b) {
+      op_load_rows_bw<L>(c, a.W0 + ((size_t)tile * D::ENVW + 64 * b) * TM, D::bw(b));     // dw0 block
+      tc_mma<L>(c, D::bw(b), 64, TC_SCR, 1);
+      if (b + 1 < D::NB) tc_load_w<L>(c, emb_b[b + 1]); else tc_load_w<L>(c, next);
+    }
+  }
+  tc_epi(c, TC_SCR, 64, [&](int n, float v0, float v1, float v2, float v3) {
+    const int j = n - c.half * 32;
+    dxacc[j] += v0; dxacc[j + 1] += v1; dxacc[j + 2] += v2; dxacc[j + 3] += v3;
+  });
   if (c.half == 1) {
 #pragma unroll
     for (int lm = 0; lm < D::NSH; ++lm) DY_s[lm * TM + c.m] = dYp[lm];
