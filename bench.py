@@ -47,8 +47,8 @@ def log(*a):
 
 
 def model_config(avg_nn):
-    from oracle import allegro_torch as AT
-    return AT.default_config(type_names=["Ag"], r_max=R_MAX, avg_num_neighbors=float(avg_nn), seed=2, **MODEL)
+    from pair_allegro_b200 import modelgen
+    return modelgen.default_config(type_names=["Ag"], r_max=R_MAX, avg_num_neighbors=float(avg_nn), seed=2, **MODEL)
 
 
 def flop_model(L, nl, B=8, T=1):
@@ -83,7 +83,7 @@ def flop_model(L, nl, B=8, T=1):
 # ------------------------------------------------------------------------------------------
 def build_rank_system(rank, world):
     """this rank's atoms (+ghosts), full neighbour list and halo plan"""
-    from oracle import lmp_harness as H
+    from lmpshim import harness as H
     grid = H.proc_grid(world)
     t0 = time.time()
     rng = np.random.default_rng(2)
@@ -182,9 +182,10 @@ def cpu_reference_run(steps, warmup, threads=None):
     os.environ["CUDA_VISIBLE_DEVICES"] = ""
     import torch
     from lmpshim import driver
+    from lmpshim import harness as H
     from oracle import allegro_torch as AT
-    from oracle import lmp_harness as H
     from oracle.ref_pair import RefPairAllegro
+    from pair_allegro_b200 import modelgen
     threads = threads or os.cpu_count() or 1
     torch.set_num_threads(threads)
     os.environ.setdefault("OMP_NUM_THREADS", str(threads))
@@ -193,7 +194,9 @@ def cpu_reference_run(steps, warmup, threads=None):
     lst = H.build_full_list(atoms, R_MAX + SKIN)
     d = tempfile.mkdtemp(prefix="alg_ref_")
     pth = os.path.join(d, "c2.nequip.pth")
-    AT.save_torchscript(model_config(26.0), pth)
+    alg = os.path.join(d, "c2.alg")
+    modelgen.random_alg(model_config(26.0), alg)        # the weights the GPU arm evaluates ...
+    AT.save_torchscript_from_alg(alg, pth)               # ... as the TorchScript artifact the reference loads
     E = int((((atoms.x[np.repeat(np.arange(atoms.nlocal), lst.numneigh[:atoms.nlocal])] - atoms.x[lst.neigh_flat]) ** 2).sum(1) <= R_MAX ** 2).sum())
     if os.path.exists(driver.REF_LIB):
         kind = "reference"
@@ -303,9 +306,7 @@ class Halo:
 def run_ours(args):
     import torch
     import torch.distributed as dist
-    from oracle import allegro_torch as AT
-    from pair_allegro_b200 import capi
-    from pair_allegro_b200.export import export_alg
+    from pair_allegro_b200 import capi, modelgen
     from pair_allegro_b200.pair import PairAllegroB200
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -325,13 +326,11 @@ def run_ours(args):
     ntot = nl + ng
     # model files (random init; identical on every rank)
     d = tempfile.mkdtemp(prefix="alg_bench_")
-    pth = os.path.join(d, "c2.nequip.pth")
-    # measured mean number of neighbours inside r_max (reported; used as avg_num_neighbors)
-    AT.save_torchscript(model_config(26.0), pth)
-    export_alg(pth, os.path.join(d, "c2.alg"))
+    alg = os.path.join(d, "c2.alg")
+    modelgen.random_alg(model_config(26.0), alg)          # numpy random init, same seed on every rank (no oracle involved)
     pair = PairAllegroB200(device=local_rank, debug_mode=False)
     pair.settings([])
-    pair.coeff(["*", "*", pth, "Ag"], 1)
+    pair.coeff(["*", "*", alg, "Ag"], 1)
     pair.init_style()
     h = pair.handle
     if args.chunk_edges:

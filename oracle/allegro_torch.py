@@ -21,6 +21,7 @@ import math
 import os
 from typing import Dict, List, Optional
 
+import numpy as np
 import torch
 
 _ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -293,4 +294,64 @@ def save_torchscript(cfg: Dict, path: str, dtype=torch.float32) -> AllegroOracle
     m = build_model(cfg, dtype)
     sm = torch.jit.script(m)
     torch.jit.save(sm, path, _extra_files=metadata_from_config(cfg))
+    return m
+
+
+def config_from_alg_header(hdr: Dict[str, str]) -> Dict:
+    """inverse of the `.alg` header written by pair_allegro_b200 (export.py / modelgen.py)"""
+    names = hdr["type_names"].split()
+    T = len(names)
+    pc = hdr.get("per_edge_type_cutoff", "").split()
+    return default_config(
+        type_names=names, r_max=float(hdr["r_max"]),
+        per_edge_type_cutoff=None if not pc else [[float(pc[i * T + j]) for j in range(T)] for i in range(T)],
+        num_bessels=int(hdr["num_bessels"]), polynomial_cutoff_p=float(hdr["polynomial_cutoff_p"]),
+        l_max=int(hdr["l_max"]), num_layers=int(hdr["num_layers"]),
+        num_scalar_features=int(hdr["num_scalar_features"]), num_tensor_features=int(hdr["num_tensor_features"]),
+        mlp_depth=int(hdr["mlp_depth"]), mlp_width=int(hdr["mlp_width"]), readout_width=int(hdr["readout_width"]),
+        avg_num_neighbors=float(hdr["avg_num_neighbors"]), allow_tf32=hdr.get("allow_tf32", "0") == "1", seed=0)
+
+
+def model_from_alg(alg_path: str, dtype=torch.float32):
+    """Oracle model carrying exactly the weights of a `.alg` file (e.g. one written by
+    pair_allegro_b200.modelgen): both arms of a comparison then evaluate identical parameters.
+    Returns (model, cfg)."""
+    from pair_allegro_b200.export import read_alg
+    hdr, ten = read_alg(alg_path)
+    cfg = config_from_alg_header(hdr)
+    cfg["per_type_energy_scales"] = [float(v) for v in ten["scales"]]
+    cfg["per_type_energy_shifts"] = [float(v) for v in ten["shifts"]]
+    m = AllegroOracle(cfg)
+    D = int(cfg["mlp_depth"])
+    sd = {}
+    for i in range(D + 1):
+        sd["twobody.weights.%d" % i] = ten["twobody.w%d" % i]
+    sd["embed_linear"] = ten["embed_linear"]
+    for k in range(int(cfg["num_layers"])):
+        sd["layers.%d.env_linear" % k] = ten["layer%d.env_linear" % k]
+        sd["layers.%d.omega" % k] = ten["layer%d.omega" % k]
+        for i in range(D + 1):
+            sd["layers.%d.mlp.weights.%d" % (k, i)] = ten["layer%d.mlp.w%d" % (k, i)]
+        sd["layers.%d.alpha" % k] = ten["layer%d.alpha" % k]
+    sd["readout.weights.0"] = ten["readout.w0"]
+    sd["readout.weights.1"] = ten["readout.w1"]
+    sd["cutoff_table"] = ten["cutoff_table"]
+    missing, unexpected = m.load_state_dict({k: torch.from_numpy(np.array(v)) for k, v in sd.items()}, strict=False)
+    assert not unexpected, unexpected
+    assert all(("cbig" in k or "qpath" in k or "mixmat" in k or "scal_q" in k or k in ("bessel_n", "scales", "shifts")) for k in missing), missing
+    if dtype == torch.float64:
+        for p in m.parameters():
+            p.data = p.data.to(torch.float64)
+        for layer in m.layers:
+            layer.mixmat = layer.mixmat.to(torch.float64)
+    m.eval()
+    for p in m.parameters():
+        p.requires_grad_(False)
+    return m, cfg
+
+
+def save_torchscript_from_alg(alg_path: str, pth_path: str, dtype=torch.float32):
+    """`.alg` -> `.nequip.pth` the reference glue can load (same weights, metadata in _extra_files)"""
+    m, cfg = model_from_alg(alg_path, dtype)
+    torch.jit.save(torch.jit.script(m), pth_path, _extra_files=metadata_from_config(cfg))
     return m

@@ -2,7 +2,7 @@
 
 LAMMPS-free CPU restatement of the reference pair style `PairNequIPAllegro<false>`
 (`pair_style allegro`), function by function, against the LAMMPS stand-in of
-oracle/lmp_harness.py.  Each method cites the reference lines it follows
+lmpshim/harness.py.  Each method cites the reference lines it follows
 (/root/reference/pair_nequip_allegro.cpp).  The model call goes through torch.jit exactly
 as `call()` does (cpp:409-430): load with the five metadata keys (cpp:214-222), eval,
 freeze when not frozen (cpp:228-232), fusion strategy DYNAMIC/10 (cpp:259-263), TF32 flags
@@ -20,7 +20,7 @@ from typing import Dict, List, Optional
 import numpy as np
 import torch
 
-from .lmp_harness import NEIGHMASK, Atoms, NeighList
+from lmpshim.harness import NEIGHMASK, Atoms, NeighList
 
 
 class RefPairAllegro:

@@ -8,7 +8,7 @@ pair style for a real LAMMPS build is src/pair_allegro_b200.cpp; both bind the s
 
 `atom` / `list` arguments are duck-typed LAMMPS stand-ins with the fields the reference
 reads: atom.x,type,tag,nlocal,nghost,ntypes,f ; list.inum,gnum,ilist,numneigh and the
-neighbour storage as (neigh_flat, first) -- see oracle/lmp_harness.py for the test harness.
+neighbour storage as (neigh_flat, first) -- see lmpshim/harness.py for the test harness.
 """
 import os
 

@@ -23,7 +23,7 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 from oracle import allegro_torch as AT  # noqa: E402
-from oracle import lmp_harness as H  # noqa: E402
+from lmpshim import harness as H  # noqa: E402
 from oracle.ref_pair import RefPairAllegro  # noqa: E402
 from pair_allegro_b200.export import export_alg  # noqa: E402
 

@@ -12,7 +12,7 @@ class _NS:
 
 
 def load_golden(name):
-    """golden case -> (atom, list, npz) with the LAMMPS stand-in fields (oracle/lmp_harness.py)"""
+    """golden case -> (atom, list, npz) with the LAMMPS stand-in fields (lmpshim/harness.py)"""
     z = np.load(os.path.join(GOLDEN, name + ".npz"))
     atom = _NS()
     atom.x = z["x"].copy()

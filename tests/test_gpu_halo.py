@@ -14,7 +14,7 @@ pytestmark = pytest.mark.gpu
 
 
 def test_halo_pack_unpack_and_device_step(ensure_built):
-    from oracle import lmp_harness as H
+    from lmpshim import harness as H
     from pair_allegro_b200 import capi
     lib = capi.load_library()
     name = "CuPd_r5"

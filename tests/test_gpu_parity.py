@@ -119,7 +119,7 @@ def test_intermediates(name, ensure_built):
 
 
 def _random_system(n, box, ntypes, seed):
-    from oracle import lmp_harness as H
+    from lmpshim import harness as H
     rng = np.random.default_rng(seed)
     # jittered lattice so no two atoms are closer than ~1 A
     m = int(np.ceil(n ** (1 / 3)))
@@ -133,7 +133,7 @@ def _random_system(n, box, ntypes, seed):
 def test_live_oracle_parity(L, nl, ntypes, ensure_built, tmp_path):
     """fresh random-init weights + random periodic box, libtorch (CPU) oracle run on the box"""
     from oracle import allegro_torch as AT
-    from oracle import lmp_harness as H
+    from lmpshim import harness as H
     from oracle.ref_pair import RefPairAllegro
     from pair_allegro_b200.export import export_alg
     from pair_allegro_b200.pair import PairAllegroB200

@@ -81,7 +81,7 @@ def test_tc_intermediates(name, ensure_built):
 @pytest.mark.parametrize("nl,ntypes,lmax", [(1, 1, 1), (2, 2, 1), (3, 3, 1), (1, 2, 2), (2, 1, 2), (3, 2, 2)])
 def test_tc_live_oracle(nl, ntypes, lmax, ensure_built, tmp_path):
     from oracle import allegro_torch as AT
-    from oracle import lmp_harness as H
+    from lmpshim import harness as H
     from oracle.ref_pair import RefPairAllegro
     from pair_allegro_b200.export import export_alg
     from pair_allegro_b200.pair import PairAllegroB200

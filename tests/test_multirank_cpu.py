@@ -23,7 +23,7 @@ def _worker(rank, world, port, tmp):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     torch.set_num_threads(1)
     from oracle import allegro_torch as AT
-    from oracle import lmp_harness as H
+    from lmpshim import harness as H
     from oracle.ref_pair import RefPairAllegro
     pos, types, cell = H.fcc_box(6, a=4.09, jitter=0.05, seed=4)
     types = (np.arange(len(pos)) % 2 + 1).astype(np.int32)
@@ -85,7 +85,7 @@ def _worker(rank, world, port, tmp):
 def test_halo_exchange_reproduces_single_rank(world):
     sys.path.insert(0, ROOT)
     from oracle import allegro_torch as AT
-    from oracle import lmp_harness as H
+    from lmpshim import harness as H
     from oracle.ref_pair import RefPairAllegro
     with tempfile.TemporaryDirectory() as tmp:
         cfg = AT.default_config(type_names=["A", "B"], r_max=5.0, l_max=1, num_layers=2, avg_num_neighbors=28.0, seed=9)

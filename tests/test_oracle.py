@@ -11,7 +11,7 @@ import torch
 from conftest import GOLDEN_CASES
 from helpers import alg_path, golden_config, load_golden
 from oracle import allegro_torch as AT
-from oracle import lmp_harness as H
+from lmpshim import harness as H
 from oracle.analytic_numpy import AnalyticAllegro
 from oracle.ref_pair import RefPairAllegro
 from pair_allegro_b200.export import export_alg, read_alg

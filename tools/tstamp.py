@@ -5,7 +5,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from oracle import allegro_torch as AT
-from oracle import lmp_harness as H
+from lmpshim import harness as H
 from pair_allegro_b200.export import export_alg
 from pair_allegro_b200.pair import PairAllegroB200
 pos, types, cell = H.fcc_box(24)
