@@ -45,6 +45,15 @@ def _load(path):
     lib.shim_get_virial.argtypes = [vp, vp]
     lib.shim_get_eatom.argtypes = [vp, vp]
     lib.shim_get_eatom.restype = C.c_int
+    lib.shim_set_ghost_owner.argtypes = [vp, vp]
+    lib.shim_set_timestep.argtypes = [vp, C.c_longlong]
+    if hasattr(lib, "shim_compute_create"):
+        lib.shim_compute_create.argtypes = [vp, C.c_int, C.POINTER(C.c_char_p)]
+        lib.shim_compute_create.restype = C.c_int
+        lib.shim_compute_vector.argtypes = [vp, C.c_int, vp, C.c_int]
+        lib.shim_compute_vector.restype = C.c_int
+        lib.shim_compute_peratom.argtypes = [vp, C.c_int, vp, C.c_int]
+        lib.shim_compute_peratom.restype = C.c_int
     return lib
 
 
@@ -109,6 +118,30 @@ class ShimLammps:
         eatom = np.zeros(self.ntot)
         has = self.lib.shim_get_eatom(self.h, eatom.ctypes.data) == 0
         return dict(f=f, eng_vdwl=self.lib.shim_get_eng(self.h), virial=vir, eatom=eatom if has else None)
+
+    # ---- compute allegro / compute allegro/atom (shim.cpp: shim_compute_*) ----------------------------
+    def set_ghost_owner(self, owner_of_ghosts):
+        """[nghost] local index each ghost is an image of: lets comm->reverse_comm(compute) fold ghost rows"""
+        o = np.ascontiguousarray(owner_of_ghosts, dtype=np.int32)
+        assert len(o) == self.ntot - self.nlocal
+        self.lib.shim_set_ghost_owner(self.h, o.ctypes.data)
+
+    def compute_create(self, words):
+        """words = the LAMMPS command after `compute`, e.g. ["ae", "all", "allegro/atom", "atomic_energy", "1", "0"]"""
+        idx = self.lib.shim_compute_create(self.h, len(words), self._argv(words))
+        if idx < 0:
+            raise ShimError(self.lib.shim_last_error(self.h).decode())
+        return idx
+
+    def compute_vector(self, idx, n):
+        out = np.zeros(n)
+        self._ck(self.lib.shim_compute_vector(self.h, idx, out.ctypes.data, n))
+        return out
+
+    def compute_peratom(self, idx, ncols):
+        out = np.zeros((self.nlocal, ncols))
+        self._ck(self.lib.shim_compute_peratom(self.h, idx, out.ctypes.data, ncols))
+        return out
 
     def close(self):
         if self.h:

@@ -96,7 +96,9 @@ class Atom {
 class Comm {
  public:
   int me = 0, nprocs = 1;
-  void reverse_comm(Compute*) {}
+  Atom* atom = nullptr;          // harness wiring for reverse_comm(Compute*) (compute.h)
+  int* ghost_owner = nullptr;    // [nghost] local index of the atom each ghost is an image of
+  inline void reverse_comm(Compute*);
   void reverse_comm() {}
   void forward_comm() {}
 };
@@ -166,7 +168,7 @@ class LAMMPS {
   MPI_Comm world = MPI_COMM_WORLD;
   LAMMPS()
       : memory(new Memory), error(new Error), atom(new Atom), comm(new Comm), domain(new Domain), force(new Force),
-        neighbor(new Neighbor), update(new Update), output(new Output) {}
+        neighbor(new Neighbor), update(new Update), output(new Output) { comm->atom = atom; }
   ~LAMMPS() {
     delete memory; delete error; delete atom; delete comm; delete domain; delete force; delete neighbor; delete update; delete output;
   }

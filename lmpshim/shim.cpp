@@ -11,6 +11,12 @@
 #include "lammps.h"
 #include "pair.h"
 #include SHIM_PAIR_HEADER
+#ifdef SHIM_COMPUTE_HEADER
+//   -DSHIM_COMPUTE_HEADER='<compute_allegro.h>'        -DSHIM_COMPUTE_TEMPLATE=ComputeAllegro       (oracle/_ref)
+//   -DSHIM_COMPUTE_HEADER='"compute_allegro_b200.h"'   -DSHIM_COMPUTE_TEMPLATE=ComputeAllegroB200   (this repo)
+#include "compute.h"
+#include SHIM_COMPUTE_HEADER
+#endif
 
 using namespace LAMMPS_NS;
 
@@ -24,6 +30,10 @@ struct Shim {
   std::vector<int> type, ilist, numneigh, neigh;
   std::vector<tagint> tag;
   std::vector<int*> firstneigh;
+  std::vector<int> ghost_owner;
+#ifdef SHIM_COMPUTE_HEADER
+  std::vector<Compute*> computes;
+#endif
   std::string err;
 };
 template <class F> int guard(Shim* s, F&& fn) {
@@ -61,6 +71,9 @@ API void* shim_create(int ntypes, int nlocal, int nghost, const double* x, const
 API void shim_destroy(void* p) {
   Shim* s = (Shim*)p;
   if (!s) return;
+#ifdef SHIM_COMPUTE_HEADER
+  for (Compute* c : s->computes) delete c;
+#endif
   delete s->pair;
   delete s;
 }
@@ -123,3 +136,54 @@ API int shim_get_eatom(void* p, double* out) {
   memcpy(out, s->pair->eatom, sizeof(double) * (s->lmp.atom->nlocal + s->lmp.atom->nghost));
   return 0;
 }
+
+// ---- `compute allegro` / `compute allegro/atom` (reference: compute/compute_allegro.cpp) -------------------
+API void shim_set_ghost_owner(void* p, const int* owner /*[nghost]*/) {
+  Shim* s = (Shim*)p;
+  s->ghost_owner.assign(owner, owner + s->lmp.atom->nghost);
+  s->lmp.comm->ghost_owner = s->ghost_owner.data();
+}
+API void shim_set_timestep(void* p, long long step) { ((Shim*)p)->lmp.update->ntimestep = step; }
+#ifdef SHIM_COMPUTE_HEADER
+// arg = the words of the LAMMPS command `compute ID group style args...`; returns the compute's index or -1
+API int shim_compute_create(void* p, int narg, char** arg) {
+  Shim* s = (Shim*)p;
+  int idx = -1;
+  const int rc = guard(s, [&] {
+    if (narg < 3) throw std::runtime_error("compute: too few arguments");
+    Compute* c = nullptr;
+    if (strcmp(arg[2], "allegro") == 0) c = new SHIM_COMPUTE_TEMPLATE<0>(&s->lmp, narg, arg);
+    else if (strcmp(arg[2], "allegro/atom") == 0) c = new SHIM_COMPUTE_TEMPLATE<1>(&s->lmp, narg, arg);
+    else throw std::runtime_error(std::string("unknown compute style ") + arg[2]);
+    c->init();
+    s->computes.push_back(c);
+    idx = (int)s->computes.size() - 1;
+  });
+  return rc == 0 ? idx : -1;
+}
+API int shim_compute_vector(void* p, int idx, double* out, int n) {
+  Shim* s = (Shim*)p;
+  return guard(s, [&] {
+    Compute* c = s->computes.at(idx);
+    if (!c->vector_flag || n != c->size_vector) throw std::runtime_error("compute is not a global vector of that length");
+    c->compute_vector();
+    memcpy(out, c->vector, sizeof(double) * n);
+  });
+}
+// out[nlocal][ncols]
+API int shim_compute_peratom(void* p, int idx, double* out, int ncols) {
+  Shim* s = (Shim*)p;
+  return guard(s, [&] {
+    Compute* c = s->computes.at(idx);
+    if (!c->peratom_flag || ncols != (c->size_peratom_cols ? c->size_peratom_cols : 1)) throw std::runtime_error("compute is not per-atom with that many columns");
+    c->compute_peratom();
+    const int nlocal = s->lmp.atom->nlocal;
+    for (int i = 0; i < nlocal; ++i)
+      for (int j = 0; j < ncols; ++j) out[(size_t)i * ncols + j] = c->size_peratom_cols ? c->array_atom[i][j] : c->vector_atom[i];
+  });
+}
+API long long shim_compute_invoked(void* p, int idx, int peratom) {
+  Compute* c = ((Shim*)p)->computes.at(idx);
+  return peratom ? c->invoked_peratom : c->invoked_vector;
+}
+#endif

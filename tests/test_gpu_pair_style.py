@@ -93,3 +93,42 @@ lmp.compute(3, 1)
     d = np.linalg.norm(atom.x[ei[0]] - atom.x[ei[1]], axis=1)
     for (i, j, rr), e0, e1, dd in zip(got, ei[0], ei[1], d):
         assert int(i) == atom.tag[e0] - 1 and int(j) == atom.tag[e1] - 1 and abs(float(rr) - dd) < 1e-9
+
+
+@pytest.mark.parametrize("name", ["CuPd_r5", "aspirin_r15"])
+def test_cpp_compute_allegro(name, ours_lib):
+    """`compute allegro` / `compute allegro/atom` of this repo (src/compute_allegro_b200.cpp) satisfy the
+    same relations -- and print the same errors -- as the reference's unmodified compute
+    (tests/test_reference_shim.py::test_reference_compute_allegro), and agree with it numerically"""
+    import tempfile
+
+    from test_reference_shim import check_compute_outputs, run_reference_compute
+    atom, lst, z = load_golden(name)
+    lmp = driver.ShimLammps(ours_lib, atom, lst)
+    lmp.set_ghost_owner(atom.owner[atom.nlocal:])
+    lmp.pair_style([])
+    lmp.pair_coeff(["*", "*", alg_path(name)] + str(z["type_names"]).split())
+    lmp.init(newton_pair=1)
+    errs = []
+    for words in (["c", "all", "allegro", "virial"], ["c", "mobile", "allegro", "virial", "9"], ["c", "all", "allegro", "virial", "0"],
+                  ["c", "all", "allegro/atom", "forces", "3"]):
+        with pytest.raises(driver.ShimError) as ei:
+            lmp.compute_create(words)
+        errs.append(str(ei.value))
+    ae = lmp.compute_create(["ae", "all", "allegro/atom", "atomic_energy", "1", "0"])
+    fo = lmp.compute_create(["fo", "all", "allegro/atom", "forces", "3", "1"])
+    vi = lmp.compute_create(["vi", "all", "allegro", "virial", "9"])
+    bad = lmp.compute_create(["bad", "all", "allegro", "virial", "6"])
+    out = lmp.compute(eflag=3, vflag=1)
+    with pytest.raises(driver.ShimError) as ei:
+        lmp.compute_vector(bad, 6)
+    errs.append(str(ei.value))
+    ours = dict(f=out["f"], virial=out["virial"], eatom=out["eatom"], errs=np.array(errs),
+                c_ae=lmp.compute_peratom(ae, 1), c_fo=lmp.compute_peratom(fo, 3), c_vi=lmp.compute_vector(vi, 9))
+    check_compute_outputs(ours, atom)
+    if os.path.exists(driver.REF_LIB):                     # the reference's own compute on the same system (CPU, subprocess)
+        with tempfile.TemporaryDirectory() as tmp:
+            ref = run_reference_compute(name, tmp)
+        np.testing.assert_allclose(ours["c_ae"], ref["c_ae"], rtol=1e-5, atol=1e-5)
+        assert np.abs(ours["c_fo"] - ref["c_fo"]).max() < 1e-4
+        assert np.abs(ours["c_vi"] - ref["c_vi"]).max() < 1e-4 * max(1.0, np.abs(ref["c_vi"]).max())
