@@ -540,18 +540,64 @@ __device__ __forceinline__ void tc_dy_store(const ChunkArgs& a, const TcCtx& c, 
 constexpr uint32_t TC_Z1 = 0, TC_Z2 = 64, TC_M = 128, TC_SCR = 192;
 struct NoBias { __device__ __forceinline__ float operator()(int) const { return 0.f; } };
 
+// activation record of one MLP evaluation kept for the backward kernels (tile-SoA, [3][64][128] per tile):
+// rows [0,64) = act'(z1 + bias), [64,128) = act'(z2), [128,192) = m (pre-envelope output)
+constexpr int ZD_ROWS = 3 * 64;
 // hidden layers of an MLP whose layer-0 pre-activation z1 is complete in TMEM (w1 requested):
-// leaves z2 and m (pre-envelope output) in TMEM, requests `next`
-template <int L, class Bias>
-__device__ __forceinline__ void tc_mlp_hidden_fwd(TcCtx& c, const TcMat& w2, const TcMat& next, Bias bias) {
+// leaves z2 and m (pre-envelope output) in TMEM, requests `next`.  With STORE the activation
+// derivatives are written to `zd` so that the backward kernels need no recomputation.
+template <int L, bool STORE, class Bias>
+__device__ __forceinline__ void tc_mlp_hidden_fwd(TcCtx& c, const TcMat& w2, const TcMat& next, Bias bias, float* __restrict__ zd = nullptr) {
+  constexpr int TM = 128;
   tc_epi(c, TC_Z1, 64, [&](int n, float v0, float v1, float v2, float v3) {
-    op_put4<L>(c, n, silu_act(v0 + bias(n)), silu_act(v1 + bias(n + 1)), silu_act(v2 + bias(n + 2)), silu_act(v3 + bias(n + 3)));
+    if constexpr (STORE) {
+      float d0, d1, d2, d3;
+      const float r0 = silu_act(v0 + bias(n), d0), r1 = silu_act(v1 + bias(n + 1), d1);
+      const float r2 = silu_act(v2 + bias(n + 2), d2), r3 = silu_act(v3 + bias(n + 3), d3);
+      op_put4<L>(c, n, r0, r1, r2, r3);
+      float* p = zd + n * TM + c.m;
+      p[0] = d0; p[TM] = d1; p[2 * TM] = d2; p[3 * TM] = d3;
+    } else {
+      op_put4<L>(c, n, silu_act(v0 + bias(n)), silu_act(v1 + bias(n + 1)), silu_act(v2 + bias(n + 2)), silu_act(v3 + bias(n + 3)));
+    }
   });
   tc_mma<L>(c, 64, 64, TC_Z2);
   tc_load_w<L>(c, w2);
-  tc_epi(c, TC_Z2, 64, [&](int n, float v0, float v1, float v2, float v3) { op_put4<L>(c, n, silu_act(v0), silu_act(v1), silu_act(v2), silu_act(v3)); });
+  tc_epi(c, TC_Z2, 64, [&](int n, float v0, float v1, float v2, float v3) {
+    if constexpr (STORE) {
+      float d0, d1, d2, d3;
+      const float r0 = silu_act(v0, d0), r1 = silu_act(v1, d1), r2 = silu_act(v2, d2), r3 = silu_act(v3, d3);
+      op_put4<L>(c, n, r0, r1, r2, r3);
+      float* p = zd + (64 + n) * TM + c.m;
+      p[0] = d0; p[TM] = d1; p[2 * TM] = d2; p[3 * TM] = d3;
+    } else {
+      op_put4<L>(c, n, silu_act(v0), silu_act(v1), silu_act(v2), silu_act(v3));
+    }
+  });
   tc_mma<L>(c, 64, 64, TC_M);
   tc_load_w<L>(c, next);
+}
+
+// backward through the hidden layers with the STORED derivatives: dm in operand [0,64), w2_b requested:
+// dz2 = (dm W2^T) act'(z2); dz1 = (dz2 W1^T) act'(z1) -> operand; requests `next`
+template <int L>
+__device__ __forceinline__ void tc_mlp_bwd_hidden_st(TcCtx& c, const TcMat& w1_b, const TcMat& next, const float* __restrict__ zd) {
+  constexpr int TM = 128;
+  float d[32];
+  ld_rows32(c, zd + 64 * TM, d);                      // act'(z2): in flight during the MMA
+  tc_mma<L>(c, 64, 64, TC_SCR);
+  tc_load_w<L>(c, w1_b);
+  tc_epi(c, TC_SCR, 64, [&](int n, float v0, float v1, float v2, float v3) {
+    const int j = n - c.half * 32;
+    op_put4<L>(c, n, v0 * d[j], v1 * d[j + 1], v2 * d[j + 2], v3 * d[j + 3]);
+  });
+  ld_rows32(c, zd, d);                                // act'(z1 + bias)
+  tc_mma<L>(c, 64, 64, TC_SCR);
+  tc_load_w<L>(c, next);
+  tc_epi(c, TC_SCR, 64, [&](int n, float v0, float v1, float v2, float v3) {
+    const int j = n - c.half * 32;
+    op_put4<L>(c, n, v0 * d[j], v1 * d[j + 1], v2 * d[j + 2], v3 * d[j + 3]);
+  });
 }
 
 // dm in operand [0,64), w2_b requested: dz2 = (dm W2^T) act'(z2); dz1 = (dz2 W1^T) act'(z1+bias) -> operand; requests `next`
@@ -743,10 +789,13 @@ __global__ void __launch_bounds__(NT, 2) k_f0_tc(const __grid_constant__ ChunkAr
   tc_load_w<L>(c, tw.two1);
   const float* w0 = w.two.w[0];
   const float* wi = w0 + g.zi * H; const float* wj = w0 + (w.T + g.zj) * H;
-  tc_mlp_hidden_fwd<L>(c, tw.two2, tw.emb[0], [&](int n) { return __ldg(wi + n) + __ldg(wj + n); });
+  float* zd = a.ZD[0] + (size_t)tile * ZD_ROWS * TM;
+  tc_mlp_hidden_fwd<L, true>(c, tw.two2, tw.emb[0], [&](int n) { return __ldg(wi + n) + __ldg(wj + n); }, zd);
   {
     float* X0g = a.X[0] + (size_t)tile * S * TM;
     tc_epi(c, TC_M, 64, [&](int n, float v0, float v1, float v2, float v3) {
+      float* mp = zd + (128 + n) * TM + c.m;
+      mp[0] = v0; mp[TM] = v1; mp[2 * TM] = v2; mp[3 * TM] = v3;
       v0 *= g.u; v1 *= g.u; v2 *= g.u; v3 *= g.u;
       op_put4<L>(c, n, v0, v1, v2, v3);
       X0g[(n + 0) * TM + c.m] = v0; X0g[(n + 1) * TM + c.m] = v1; X0g[(n + 2) * TM + c.m] = v2; X0g[(n + 3) * TM + c.m] = v3;
@@ -807,13 +856,16 @@ __global__ void __launch_bounds__(NT, 2) k_fk_tc(const __grid_constant__ ChunkAr
   seg_build<TM>(reinterpret_cast<const int*>(c.sm + SM::oC), nvalid, reinterpret_cast<int*>(c.sm + SM::oSEG));
   const RowSrc gsrc = tc_stage_rows<L>(c, a.gamma[k], a.c0, nvalid);
   tc_latent_z1<L, KIND, FIRST, true>(a, lw, tl, c, tile, k, Xg, gsrc);
-  tc_mlp_hidden_fwd<L>(c, tl.m2, tw.layer[k + 1].env[0], NoBias());
+  float* zd = a.ZD[k + 1] + (size_t)tile * ZD_ROWS * TM;
+  tc_mlp_hidden_fwd<L, true>(c, tl.m2, tw.layer[k + 1].env[0], NoBias(), zd);
   {
     float* Xng = a.X[k + 1] + (size_t)tile * S * TM;
     float xp[32];
     ld_rows32(c, Xg, xp);
     tc_epi(c, TC_M, 64, [&](int n, float v0, float v1, float v2, float v3) {
       const int j = n - c.half * 32;
+      float* mp = zd + (128 + n) * TM + c.m;
+      mp[0] = v0; mp[TM] = v1; mp[2 * TM] = v2; mp[3 * TM] = v3;
       const float x0 = lw.a * xp[j] + lw.b * v0 * g.u, x1 = lw.a * xp[j + 1] + lw.b * v1 * g.u;
       const float x2 = lw.a * xp[j + 2] + lw.b * v2 * g.u, x3 = lw.a * xp[j + 3] + lw.b * v3 * g.u;
       op_put4<L>(c, n, x0, x1, x2, x3);
@@ -849,7 +901,7 @@ __global__ void __launch_bounds__(NT, 2) k_t_tc(const __grid_constant__ ChunkArg
   ALG_TS(a, 2, 2);
   tc_latent_z1<L, 'A', FIRST, false>(a, lw, tl, c, tile, k, Xg, gsrc);
   ALG_TS(a, 2, 3);
-  tc_mlp_hidden_fwd<L>(c, tl.m2, tw.ro0, NoBias());
+  tc_mlp_hidden_fwd<L, false>(c, tl.m2, tw.ro0, NoBias());
   ALG_TS(a, 2, 4);
   {
     float xp[32];
@@ -959,40 +1011,33 @@ __global__ void __launch_bounds__(NT, 2) k_bk_tc(const __grid_constant__ ChunkAr
   float* dXg = a.dX + (size_t)tile * S * TM;
   const RowSrc dsrc = tc_stage_rows<L>(c, a.dgamma[k + 1], a.c0, nvalid);
   float dxn[32];                                      // complete dx^{k+1} of this thread's 32 columns (kept in registers)
-  tc_phase2<L>(a, w, c, tw.layer[k + 1], nullptr, tile, Xn, tl.m0s[0], dsrc, dxn);
+  tc_phase2<L>(a, w, c, tw.layer[k + 1], nullptr, tile, Xn, tl.m2_b, dsrc, dxn);
+  const float* zd = a.ZD[k + 1] + (size_t)tile * ZD_ROWS * TM;      // act'(z1), act'(z2), m of layer k (written by FK)
   {
-    float dp[32];
+    float dp[32], mv[32];
     ld_rows32(c, dXg, dp);
-#pragma unroll
-    for (int i = 0; i < 32; ++i) dxn[i] += dp[i];
-  }
-  // ---- recompute layer k forward (z1, z2, m stay in TMEM)
-  const float* Xg = a.X[k] + (size_t)tile * S * TM;
-  const RowSrc gsrc = tc_stage_rows<L>(c, a.gamma[k], a.c0, nvalid);    // dGamma rows are consumed (barriers inside tc_mma)
-  tc_latent_z1<L, KIND, FIRST, false>(a, lw, tl, c, tile, k, Xg, gsrc);
-  tc_mlp_hidden_fwd<L>(c, tl.m2, tl.m2_b, NoBias());
-  {
+    ld_rows32(c, zd + 128 * TM, mv);
     float dup = 0.f;
-    for (int c0 = c.half * 32; c0 < c.half * 32 + 32; c0 += 16) {
-      float mv[16], v[16];
-      tc_ld16(c, TC_M + c0, mv);
 #pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        const float dx1 = dxn[c0 - c.half * 32 + i];
-        dXg[(c0 + i) * TM + c.m] = lw.a * dx1;
+    for (int i = 0; i < 32; i += 4) {
+      float v[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float dx1 = dxn[i + q] + dp[i + q];
+        dXg[(c.half * 32 + i + q) * TM + c.m] = lw.a * dx1;
         const float dxt = lw.b * dx1;
-        dup += dxt * mv[i];
-        v[i] = dxt * g.u;
+        dup += dxt * mv[i + q];
+        v[q] = dxt * g.u;
       }
-#pragma unroll
-      for (int i = 0; i < 16; i += 4) op_put4<L>(c, c0 + i, v[i], v[i + 1], v[i + 2], v[i + 3]);
+      op_put4<L>(c, c.half * 32 + i, v[0], v[1], v[2], v[3]);
     }
     float* e_s = c.sm + SM::oE;
     if (c.half == 1) e_s[c.m] = dup;
     __syncthreads();
     if (c.half == 0) a.du[(size_t)tile * TM + c.m] += dup + e_s[c.m];
   }
-  tc_mlp_bwd_hidden<L>(c, tl.m1_b, tl.m0_bx, NoBias());
+  const RowSrc gsrc = tc_stage_rows<L>(c, a.gamma[k], a.c0, nvalid);    // dGamma rows are consumed (barrier above)
+  tc_mlp_bwd_hidden_st<L>(c, tl.m1_b, tl.m0_bx, zd);
   tc_din<L>(c, tl, dXg);
   float dYp[D::NSH];
   tc_tp_backward<L, KIND, FIRST, true>(a, lw, c, tile, k, es, nvalid, a.dV[(k + 1) & 1], FIRST ? nullptr : a.dV[k & 1], a.dgamma[k], dYp, gsrc);
@@ -1011,11 +1056,42 @@ __global__ void __launch_bounds__(NT, 2) k_b0_tc(const __grid_constant__ ChunkAr
   const int tile = blockIdx.x;
   const int es = a.e0 + tile * TM;
   const int nvalid = min(TM, a.e1 - es);
-  tc_load_w<L>(c, tw.two0);
+  tc_load_w<L>(c, tw.layer[0].env[0]);
   const Geom g = tc_geom<L>(a, w, c, es, nvalid);
+  // ---- phase 2 of layer 0 and the embed backward: dx0 = dX + dw env0^T + dw0 emb^T
+  const float* X0 = a.X[0] + (size_t)tile * S * TM;
+  op_load_rows64<L>(c, X0);
   __syncthreads();
   seg_build<TM>(reinterpret_cast<const int*>(c.sm + SM::oC), nvalid, reinterpret_cast<int*>(c.sm + SM::oSEG));
-  // ---- recompute the two-body MLP first: z1, z2, m0 stay in TMEM
+  const RowSrc dsrc = tc_stage_rows<L>(c, a.dgamma[0], a.c0, nvalid);
+  float dx0[32];
+  tc_phase2<L>(a, w, c, tw.layer[0], tw.emb_b, tile, X0, tw.two2_b, dsrc, dx0);
+  const float* dXg = a.dX + (size_t)tile * S * TM;
+  const float* zd = a.ZD[0] + (size_t)tile * ZD_ROWS * TM;          // act'(z1 + bias), act'(z2), m0 of the two-body MLP (written by F0)
+  float du_tot;
+  {
+    float dp[32], mv[32];
+    ld_rows32(c, dXg, dp);
+    ld_rows32(c, zd + 128 * TM, mv);
+    float dup = 0.f;
+#pragma unroll
+    for (int i = 0; i < 32; i += 4) {
+      float v[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float dxv = dx0[i + q] + dp[i + q];
+        dup += dxv * mv[i + q];
+        v[q] = dxv * g.u;
+      }
+      op_put4<L>(c, c.half * 32 + i, v[0], v[1], v[2], v[3]);
+    }
+    float* e_s = c.sm + SM::oE;
+    e_s[c.half * TM + c.m] = dup;
+    __syncthreads();
+    du_tot = e_s[c.m] + e_s[TM + c.m] + a.du[(size_t)tile * TM + c.m];
+  }
+  tc_mlp_bwd_hidden_st<L>(c, tw.two1_b, tw.two0_b, zd);
+  // Bessel basis and its radial derivative (for d/dr of bessel * u)
   float bes[MAXB], dbes[MAXB];
   {
     const float pref = sqrtf(2.0f / g.rc);
@@ -1030,48 +1106,7 @@ __global__ void __launch_bounds__(NT, 2) k_b0_tc(const __grid_constant__ ChunkAr
         dbes[n] = pref * (kn / g.rc * cs / g.r - sn / (g.r * g.r));
       } else { bes[n] = 0.f; dbes[n] = 0.f; }
     }
-#pragma unroll
-    for (int k4 = 0; k4 < 16; k4 += 4) {
-      if (c.half == 0) op_put4<L>(c, k4, bes[k4] * g.u, bes[k4 + 1] * g.u, bes[k4 + 2] * g.u, bes[k4 + 3] * g.u);
-      else op_put4<L>(c, 16 + k4, 0.f, 0.f, 0.f, 0.f);
-    }
   }
-  tc_mma<L>(c, 32, 64, TC_Z1);
-  tc_load_w<L>(c, tw.two1);
-  const float* w0 = w.two.w[0];
-  const float* wi = w0 + g.zi * H; const float* wj = w0 + (w.T + g.zj) * H;
-  auto bias = [&](int n) { return __ldg(wi + n) + __ldg(wj + n); };
-  tc_mlp_hidden_fwd<L>(c, tw.two2, tw.layer[0].env[0], bias);
-  // ---- phase 2 of layer 0 and the embed backward: dx0 = dX + dw env0^T + dw0 emb^T
-  const float* X0 = a.X[0] + (size_t)tile * S * TM;
-  op_load_rows64<L>(c, X0);
-  const RowSrc dsrc = tc_stage_rows<L>(c, a.dgamma[0], a.c0, nvalid);
-  float dx0[32];
-  tc_phase2<L>(a, w, c, tw.layer[0], tw.emb_b, tile, X0, tw.two2_b, dsrc, dx0);
-  const float* dXg = a.dX + (size_t)tile * S * TM;
-  float du_tot;
-  {
-    float dup = 0.f;
-    float dp[32];
-    ld_rows32(c, dXg, dp);
-    for (int c0 = c.half * 32; c0 < c.half * 32 + 32; c0 += 16) {
-      float v[16], mv[16];
-      tc_ld16(c, TC_M + c0, mv);
-#pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        const float dxv = dx0[c0 - c.half * 32 + i] + dp[c0 - c.half * 32 + i];
-        dup += dxv * mv[i];
-        v[i] = dxv * g.u;
-      }
-#pragma unroll
-      for (int i = 0; i < 16; i += 4) op_put4<L>(c, c0 + i, v[i], v[i + 1], v[i + 2], v[i + 3]);
-    }
-    float* e_s = c.sm + SM::oE;
-    e_s[c.half * TM + c.m] = dup;
-    __syncthreads();
-    du_tot = e_s[c.m] + e_s[TM + c.m] + a.du[(size_t)tile * TM + c.m];
-  }
-  tc_mlp_bwd_hidden<L>(c, tw.two1_b, tw.two0_b, bias);
   tc_mma<L>(c, 64, 32, TC_SCR);                          // d(bessel*u) = dz1 W0[bessel rows]^T  (N padded to 32)
   float gx = 0.f, gy = 0.f, gz = 0.f;
   float* G3 = c.sm + SM::oOPH;                           // [3][128] g components ; virial rows after
