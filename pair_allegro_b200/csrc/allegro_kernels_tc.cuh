@@ -110,7 +110,9 @@ struct TcCtx {
 template <int L> __device__ __forceinline__ TcCtx tc_begin(float* sm_raw, const TcW& tw) {
   using SM = SmemTC<L>;
   TcCtx c;
-  c.sm = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(sm_raw) + 1023) & ~uintptr_t(1023));
+  // 1024-byte alignment by pointer arithmetic on the __shared__ array (an integer round trip would hide the
+  // address space from the compiler and turn every LDS/STS into a generic LD/ST)
+  c.sm = sm_raw + (((1024u - (umma::smem_u32(sm_raw) & 1023u)) & 1023u) >> 2);
   c.mbar = reinterpret_cast<uint64_t*>(c.sm + SM::oBAR);
   c.wbar = c.mbar + 1;
   uint32_t* tptr = reinterpret_cast<uint32_t*>(c.mbar + 2);

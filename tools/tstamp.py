@@ -22,10 +22,10 @@ for _ in range(2):
     pair.compute(atoms, lst)
 ts = pair.handle.get_output("tstamp").reshape(5, 32)
 t = ts[2]
-names = {1: "geom+sync", 2: "stage rows", 16: " tp fwd", 17: " mma s-block", 18: " load x rows", 19: " mma x-block", 4: "hidden fwd (2 epi + 2 mma)",
+names = {1: "geom+sync", 2: "stage rows", 3: "latent z1 (tp fwd, mma s, x rows, mma x)", 4: "hidden fwd (2 epi + 2 mma)",
          5: "x^n epilogue", 6: "mma readout", 7: "readout epi", 8: "mma dx", 9: "dx epi + du + E loop", 10: "bwd hidden (2 mma + 2 epi)", 11: "dIN (2 mma + 2 epi)",
          12: "tp backward (+segsum)", 13: "dy store", 14: "tc_end"}
-order = [1, 2, 16, 17, 18, 19, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14]
+order = [1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14]
 prev = t[0]
 print("k_t_tc CTA 148: total %d cycles" % (t[14] - t[0]))
 for i in order:
