@@ -373,27 +373,42 @@ template <int L> __device__ __forceinline__ void tc_env_all(const ChunkArgs& a, 
 // s-part operand column of (scalar path q, channel u): K index inside the 64-wide "s" block
 __device__ __forceinline__ int s_col(int q, int u) { return q * U + u; }
 
-template <int L, bool FIRST, int DIN>
-__device__ __forceinline__ void tc_load_vin(const ChunkArgs& a, int tile, int k, int e, int u, const float* Y_s, float* Vin) {
-  using D = DimsTC<L>; constexpr int TM = 128;
-  if (FIRST) {
-    const float* W0g = a.W0 + (size_t)tile * D::ENVW * TM;
+// raw global inputs of one tensor-product channel: FIRST layers read the L+1 embed weights w0[l][u]
+// (V^0 = w0 (x) Y is formed in registers), later layers read V^k[u][DIN]
+template <int L, bool FIRST, int DIN> struct VinRaw {
+  static constexpr int N = FIRST ? (L + 1) : DIN;
+  float v[N];
+  __device__ __forceinline__ void issue(const ChunkArgs& a, int tile, int k, int e, int u) {
+    using D = DimsTC<L>; constexpr int TM = 128;
+    if (FIRST) {
+      const float* W0g = a.W0 + (size_t)tile * D::ENVW * TM;
 #pragma unroll
-    for (int l = 0; l <= L; ++l) {
-      const float wv = W0g[(l * U + u) * TM + e];
+      for (int l = 0; l <= L; ++l) v[l] = W0g[(l * U + u) * TM + e];
+    } else {
+      const float* Vg = a.V[k] + ((size_t)tile * U + u) * DIN * TM;
 #pragma unroll
-      for (int lm = l * l; lm < (l + 1) * (l + 1); ++lm) Vin[lm] = wv * Y_s[lm * TM + e];
+      for (int cc = 0; cc < DIN; ++cc) v[cc] = Vg[cc * TM + e];
     }
-  } else {
-    const float* Vg = a.V[k] + ((size_t)tile * U + u) * DIN * TM;
-#pragma unroll
-    for (int cc = 0; cc < DIN; ++cc) Vin[cc] = Vg[cc * TM + e];
   }
-}
+  __device__ __forceinline__ void expand(int e, const float* Y_s, float* Vin) const {
+    constexpr int TM = 128;
+    if (FIRST) {
+#pragma unroll
+      for (int l = 0; l <= L; ++l) {
+#pragma unroll
+        for (int lm = l * l; lm < (l + 1) * (l + 1); ++lm) Vin[lm] = v[l] * Y_s[lm * TM + e];
+      }
+    } else {
+#pragma unroll
+      for (int cc = 0; cc < DIN; ++cc) Vin[cc] = v[cc];
+    }
+  }
+};
 
 // ============================================================================================
 // tensor product drivers: thread (edge e = m, channel phase uh = half), channels u = uh + 2 i,
-// processed in batches of TB channels with all global loads of a batch issued before any use
+// processed in batches of TB channels.  The global loads of batch s+1 are issued before batch s is
+// evaluated (register double buffering), so only the first batch exposes the memory latency.
 // ============================================================================================
 // forward for K-block b of the "s" operand: s[q] for l = q in [2b, lhi(b)) -> operand column (q-2b)*U+u.
 // With WANT_V (block 0 only) the full product is evaluated and V^{k+1} stored; otherwise only the
@@ -402,48 +417,62 @@ template <int L, char KIND, bool FIRST, bool WANT_V>
 __device__ __forceinline__ void tc_tp_forward(const ChunkArgs& a, const LayerW& lw, const TcCtx& c, int tile, int k, const RowSrc& gsrc, int b) {
   using D = DimsTC<L>; using SM = SmemTC<L>; using TP = tpgen::TP<L, KIND>; using TPA = tpgen::TP<L, 'A'>; constexpr int TM = 128;
   constexpr int TB = D::TB;
+  constexpr int NS = D::CPT / TB;
+  static_assert(NS % 2 == 0, "double buffering");
+  using Raw = VinRaw<L, FIRST, TP::DIN>;
   const float* Y_s = c.sm + SM::oY;
   const int* c_s = reinterpret_cast<const int*>(c.sm + SM::oC);
   const int e = c.m, uh = c.half;
   const float* gam = gsrc.row(c_s[e], D::F);
   float* Vng = WANT_V ? a.V[k + 1] + (size_t)tile * U * TP::DOUT * TM : nullptr;
   const int q_lo = 2 * b, q_hi = D::lhi(b);
-#pragma unroll 1
-  for (int i0 = 0; i0 < D::CPT; i0 += TB) {
-    float Vin[TB][TP::DIN], G[TB][D::NSH];
+  auto issue = [&](int s, Raw (&r)[TB]) {
+#pragma unroll
+    for (int bb = 0; bb < TB; ++bb) r[bb].issue(a, tile, k, e, uh + D::CPH * (s * TB + bb));
+  };
+  auto eval = [&](int s, const Raw (&r)[TB]) {
 #pragma unroll
     for (int bb = 0; bb < TB; ++bb) {
-      const int u = uh + D::CPH * (i0 + bb);
-      tc_load_vin<L, FIRST, TP::DIN>(a, tile, k, e, u, Y_s, Vin[bb]);
+      const int u = uh + D::CPH * (s * TB + bb);
+      float Vin[TP::DIN], G[D::NSH], Vout[TP::DOUT], sc[TP::N0];
+      r[bb].expand(e, Y_s, Vin);
 #pragma unroll
-      for (int lm = 0; lm < D::NSH; ++lm) G[bb][lm] = gam[lm * U + u];
-    }
-#pragma unroll
-    for (int bb = 0; bb < TB; ++bb) {
-      const int u = uh + D::CPH * (i0 + bb);
-      float Vout[TP::DOUT], s[TP::N0];
-      if (WANT_V) TP::template fwd<U>(Vin[bb], G[bb], lw.omega + u, Vout, s);
-      else TPA::template fwd<U>(Vin[bb], G[bb], nullptr, nullptr, s);
+      for (int lm = 0; lm < D::NSH; ++lm) G[lm] = gam[lm * U + u];
+      if (WANT_V) TP::template fwd<U>(Vin, G, lw.omega + u, Vout, sc);
+      else TPA::template fwd<U>(Vin, G, nullptr, nullptr, sc);
 #pragma unroll
       for (int q = 0; q < TP::N0; ++q)
-        if (q >= q_lo && q < q_hi) op_put1<L>(c, e, (q - q_lo) * U + u, s[q]);
+        if (q >= q_lo && q < q_hi) op_put1<L>(c, e, (q - q_lo) * U + u, sc[q]);
       if (WANT_V) {
 #pragma unroll
         for (int cc = 0; cc < TP::DOUT; ++cc) Vng[(u * TP::DOUT + cc) * TM + e] = Vout[cc];
       }
     }
+  };
+  Raw ra[TB], rb[TB];
+  issue(0, ra);
+#pragma unroll 1
+  for (int s = 0; s < NS; s += 2) {
+    issue(s + 1, rb);
+    eval(s, ra);
+    if (s + 2 < NS) issue(s + 2, ra);
+    eval(s + 1, rb);
   }
 }
 
 // backward over all channels in passes of CHU, dG segmented sum -> dgamma_out.
-// ds is read from DS_s (= WBH.. region, [q*U+u][128]); dG staged in the OPH/OPL regions.
+// ds is read from DS_s ([q*U+u][128]); dG staged in the OPH/OPL regions.
 template <int L, char KIND, bool FIRST, bool HAS_DVOUT>
 __device__ __forceinline__ void tc_tp_backward(const ChunkArgs& a, const LayerW& lw, const TcCtx& c, int tile, int k, int es, int nvalid,
                                                const float* __restrict__ dVnext, float* __restrict__ dVprev,
                                                float* __restrict__ dgamma_out, float* dYp, const RowSrc& gsrc) {
   using D = DimsTC<L>; using SM = SmemTC<L>; using TP = tpgen::TP<L, KIND>; constexpr int TM = 128;
-  const int t = threadIdx.x;
   constexpr int TB = D::TB;
+  constexpr int BPP = D::CHU / D::CPH / TB;           // batches per pass
+  constexpr int NPASS = U / D::CHU;
+  static_assert(D::CHU / D::CPH % TB == 0 && BPP % 2 == 0, "batching / double buffering");
+  using Raw = VinRaw<L, FIRST, TP::DIN>;
+  struct In { Raw vin; float dv[HAS_DVOUT ? TP::DOUT : 1]; };
   const float* DS_s = c.sm + SM::oDS;
   float* DG = c.sm + SM::oDG;
   const float* Y_s = c.sm + SM::oY;
@@ -455,50 +484,60 @@ __device__ __forceinline__ void tc_tp_backward(const ChunkArgs& a, const LayerW&
 #pragma unroll
     for (int lm = 0; lm < D::NSH; ++lm) dYp[lm] = 0.f;
   }
-  static_assert(D::CHU / D::CPH % TB == 0, "batching");
-#pragma unroll 1
-  for (int pass = 0; pass < U / D::CHU; ++pass) {
-#pragma unroll 1
-    for (int j0 = 0; j0 < D::CHU / D::CPH; j0 += TB) {
-      float Vin[TB][TP::DIN], G[TB][D::NSH], dVout[TB][TP::DOUT], ds[TB][TP::N0];
+  auto chan = [&](int pass, int j) { return pass * D::CHU + uh + D::CPH * j; };
+  auto issue = [&](int pass, int jb, In (&r)[TB]) {
 #pragma unroll
-      for (int b = 0; b < TB; ++b) {
-        const int ul = uh + D::CPH * (j0 + b);
-        const int u = pass * D::CHU + ul;
-        tc_load_vin<L, FIRST, TP::DIN>(a, tile, k, e, u, Y_s, Vin[b]);
+    for (int bb = 0; bb < TB; ++bb) {
+      const int u = chan(pass, jb * TB + bb);
+      r[bb].vin.issue(a, tile, k, e, u);
+      if (HAS_DVOUT) {
+        const float* dVg = dVnext + ((size_t)tile * U + u) * TP::DOUT * TM;
 #pragma unroll
-        for (int lm = 0; lm < D::NSH; ++lm) G[b][lm] = gam[lm * U + u];
-        if (HAS_DVOUT) {
-          const float* dVg = dVnext + ((size_t)tile * U + u) * TP::DOUT * TM;
+        for (int cc = 0; cc < TP::DOUT; ++cc) r[bb].dv[cc] = dVg[cc * TM + e];
+      }
+    }
+  };
+  auto eval = [&](int pass, int jb, const In (&r)[TB]) {
 #pragma unroll
-          for (int cc = 0; cc < TP::DOUT; ++cc) dVout[b][cc] = dVg[cc * TM + e];
+    for (int bb = 0; bb < TB; ++bb) {
+      const int ul = uh + D::CPH * (jb * TB + bb);
+      const int u = pass * D::CHU + ul;
+      float Vin[TP::DIN], G[D::NSH], ds[TP::N0], dVin[TP::DIN], dG[D::NSH];
+      r[bb].vin.expand(e, Y_s, Vin);
+#pragma unroll
+      for (int lm = 0; lm < D::NSH; ++lm) G[lm] = gam[lm * U + u];
+#pragma unroll
+      for (int q = 0; q < TP::N0; ++q) ds[q] = DS_s[s_col(q, u) * TM + e];
+      TP::template bwd<U>(Vin, G, lw.omega + u, r[bb].dv, ds, dVin, dG);
+      if (FIRST) {
+#pragma unroll
+        for (int l = 0; l <= L; ++l) {
+          const float wv = r[bb].vin.v[l];
+          float dw = 0.f;
+#pragma unroll
+          for (int lm = l * l; lm < (l + 1) * (l + 1); ++lm) { dw += dVin[lm] * Y_s[lm * TM + e]; dYp[lm] += dVin[lm] * wv; }
+          W0g[(l * U + u) * TM + e] = dw;      // in place: w0 -> dw0
         }
+      } else {
+        float* dVp = dVprev + ((size_t)tile * U + u) * TP::DIN * TM;
 #pragma unroll
-        for (int q = 0; q < TP::N0; ++q) ds[b][q] = DS_s[s_col(q, u) * TM + e];
+        for (int cc = 0; cc < TP::DIN; ++cc) dVp[cc * TM + e] = dVin[cc];
       }
 #pragma unroll
-      for (int b = 0; b < TB; ++b) {
-        const int ul = uh + D::CPH * (j0 + b);
-        const int u = pass * D::CHU + ul;
-        float dVin[TP::DIN], dG[D::NSH];
-        TP::template bwd<U>(Vin[b], G[b], lw.omega + u, dVout[b], ds[b], dVin, dG);
-        if (FIRST) {
-#pragma unroll
-          for (int l = 0; l <= L; ++l) {
-            const float wv = W0g[(l * U + u) * TM + e];
-            float dw = 0.f;
-#pragma unroll
-            for (int lm = l * l; lm < (l + 1) * (l + 1); ++lm) { dw += dVin[lm] * Y_s[lm * TM + e]; dYp[lm] += dVin[lm] * wv; }
-            W0g[(l * U + u) * TM + e] = dw;      // in place: w0 -> dw0
-          }
-        } else {
-          float* dVp = dVprev + ((size_t)tile * U + u) * TP::DIN * TM;
-#pragma unroll
-          for (int cc = 0; cc < TP::DIN; ++cc) dVp[cc * TM + e] = dVin[cc];
-        }
-#pragma unroll
-        for (int lm = 0; lm < D::NSH; ++lm) DG[e * D::DGS + lm * D::CHU + ul] = dG[lm];
-      }
+      for (int lm = 0; lm < D::NSH; ++lm) DG[e * D::DGS + lm * D::CHU + ul] = dG[lm];
+    }
+  };
+  In ra[TB], rb[TB];
+  issue(0, 0, ra);
+#pragma unroll 1
+  for (int pass = 0; pass < NPASS; ++pass) {
+#pragma unroll 1
+    for (int jb = 0; jb < BPP; jb += 2) {
+      issue(pass, jb + 1, rb);
+      eval(pass, jb, ra);
+      if (jb + 2 < BPP) issue(pass, jb + 2, ra);
+      else if (pass + 1 < NPASS) issue(pass + 1, 0, ra);
+      eval(pass, jb + 1, rb);
     }
     __syncthreads();
     {
@@ -515,7 +554,7 @@ __device__ __forceinline__ void tc_tp_backward(const ChunkArgs& a, const LayerW&
     }
     __syncthreads();
   }
-  (void)t; (void)nvalid;
+  (void)nvalid;
 }
 
 // dY: DY_s (phase-2 part, smem) + the two channel-halves' partials (FIRST layers) -> global dY
@@ -686,9 +725,9 @@ __device__ __forceinline__ void tc_din(TcCtx& c, const TcLayerW& tl, float* __re
 // With emb_b != nullptr (layer 0 in B0) the embed backward dw0 emb^T is accumulated as well.
 // Out: dxacc[32] = this thread's 32 columns of the correction to dx^kk, DY_s = d/dY of the env sum.
 // Requests `next` before the last epilogue.
-template <int L>
+template <int L, class Pre>
 __device__ __forceinline__ void tc_phase2(const ChunkArgs& a, const ModelW& w, TcCtx& c, const TcLayerW& tl, const TcMat* emb_b, int tile,
-                                          const float* __restrict__ Xtile, const TcMat& next, const RowSrc& dsrc, float* dxacc) {
+                                          const float* __restrict__ Xtile, const TcMat& next, const RowSrc& dsrc, float* dxacc, Pre pre) {
   using D = DimsTC<L>; using SM = SmemTC<L>; constexpr int TM = 128;
   const float* Y_s = c.sm + SM::oY;
   const int* c_s = reinterpret_cast<const int*>(c.sm + SM::oC);
@@ -724,6 +763,7 @@ __device__ __forceinline__ void tc_phase2(const ChunkArgs& a, const ModelW& w, T
 #pragma unroll
       for (int i = 0; i < 16; i += 4) op_put4<L>(c, (l - 2 * b) * U + c.half * 16 + i, dw[i], dw[i + 1], dw[i + 2], dw[i + 3]);
     }
+    if (b + 1 == D::NB && !emb_b) pre();               // caller's global loads fly during the last MMA
     tc_mma<L>(c, D::bw(b), 64, TC_SCR);                // dw_b env_b^T
     if (b + 1 < D::NB) tc_load_w<L>(c, tl.env[b + 1]);
     else if (emb_b) tc_load_w<L>(c, emb_b[0]);
@@ -740,6 +780,7 @@ __device__ __forceinline__ void tc_phase2(const ChunkArgs& a, const ModelW& w, T
 #pragma unroll 1
     for (int b = 0; b < D::NB; ++b) {
       op_load_rows_bw<L>(c, a.W0 + ((size_t)tile * D::ENVW + 64 * b) * TM, D::bw(b));     // dw0 block
+      if (b + 1 == D::NB) pre();
       tc_mma<L>(c, D::bw(b), 64, TC_SCR, 1);
       if (b + 1 < D::NB) tc_load_w<L>(c, emb_b[b + 1]); else tc_load_w<L>(c, next);
     }
@@ -1013,12 +1054,11 @@ __global__ void __launch_bounds__(NT, 2) k_bk_tc(const __grid_constant__ ChunkAr
   float* dXg = a.dX + (size_t)tile * S * TM;
   const RowSrc dsrc = tc_stage_rows<L>(c, a.dgamma[k + 1], a.c0, nvalid);
   float dxn[32];                                      // complete dx^{k+1} of this thread's 32 columns (kept in registers)
-  tc_phase2<L>(a, w, c, tw.layer[k + 1], nullptr, tile, Xn, tl.m2_b, dsrc, dxn);
   const float* zd = a.ZD[k + 1] + (size_t)tile * ZD_ROWS * TM;      // act'(z1), act'(z2), m of layer k (written by FK)
   {
     float dp[32], mv[32];
-    ld_rows32(c, dXg, dp);
-    ld_rows32(c, zd + 128 * TM, mv);
+    tc_phase2<L>(a, w, c, tw.layer[k + 1], nullptr, tile, Xn, tl.m2_b, dsrc, dxn,
+                 [&] { ld_rows32(c, dXg, dp); ld_rows32(c, zd + 128 * TM, mv); });
     float dup = 0.f;
 #pragma unroll
     for (int i = 0; i < 32; i += 4) {
@@ -1067,14 +1107,13 @@ __global__ void __launch_bounds__(NT, 2) k_b0_tc(const __grid_constant__ ChunkAr
   seg_build<TM>(reinterpret_cast<const int*>(c.sm + SM::oC), nvalid, reinterpret_cast<int*>(c.sm + SM::oSEG));
   const RowSrc dsrc = tc_stage_rows<L>(c, a.dgamma[0], a.c0, nvalid);
   float dx0[32];
-  tc_phase2<L>(a, w, c, tw.layer[0], tw.emb_b, tile, X0, tw.two2_b, dsrc, dx0);
   const float* dXg = a.dX + (size_t)tile * S * TM;
   const float* zd = a.ZD[0] + (size_t)tile * ZD_ROWS * TM;          // act'(z1 + bias), act'(z2), m0 of the two-body MLP (written by F0)
   float du_tot;
   {
     float dp[32], mv[32];
-    ld_rows32(c, dXg, dp);
-    ld_rows32(c, zd + 128 * TM, mv);
+    tc_phase2<L>(a, w, c, tw.layer[0], tw.emb_b, tile, X0, tw.two2_b, dsrc, dx0,
+                 [&] { ld_rows32(c, dXg, dp); ld_rows32(c, zd + 128 * TM, mv); });
     float dup = 0.f;
 #pragma unroll
     for (int i = 0; i < 32; i += 4) {
