@@ -180,3 +180,82 @@ extern "C" ALG_API int alg_debug_umma_gemm2(const float* A, const float* W, floa
   if (e != cudaSuccess) { fprintf(stderr, "alg_debug_umma_gemm: %s\n", cudaGetErrorString(e)); return ALG_ECUDA; }
   return ALG_OK;
 }
+
+// ---- tcgen05.mma issue-rate microbenchmark -----------------------------------------------------------
+// every CTA repeats `iters` times: issue 8*groups kind::tf32 MMAs (M=128, N, K=8 each; operands = whatever is in
+// shared memory; group g accumulates into TMEM accumulator g % nacc), commit, (sync_each ? wait : continue).
+// cycles[0] = clock64 ticks of CTA 0 from the first issue to the last completion wake-up, cycles[1] = time spent
+// inside the issue loops.  blocks_per_sm = 2 shows the contention the pipeline kernels see.
+namespace {
+__global__ void __launch_bounds__(128, 2) k_mma_rate(int N, int nacc, int groups, int iters, int sync_each, long long* cycles) {
+  extern __shared__ __align__(1024) float sm_raw[];
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_base_s;
+  float* sm = sm_raw + (((1024u - (umma::smem_u32(sm_raw) & 1023u)) & 1023u) >> 2);
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+  for (int i = threadIdx.x; i < 128 * 64 + 256 * 64; i += blockDim.x) sm[i] = 1.0f;
+  if (warp == 0) umma::tmem_alloc(&tmem_base_s, 256);
+  if (threadIdx.x == 0) umma::mbar_init(&bar, 1);
+  umma::fence_async_smem();
+  umma::fence_before_sync();
+  __syncthreads();
+  umma::fence_after_sync();
+  long long t0 = clock64(), tissue = 0;
+  uint32_t ph = 0;
+  const uint32_t sbase = __shfl_sync(0xffffffffu, umma::smem_u32(sm), 0);
+  const uint32_t tm = __shfl_sync(0xffffffffu, tmem_base_s, 0);
+  const uint32_t mb = __shfl_sync(0xffffffffu, umma::smem_u32(&bar), 0);
+  const uint64_t dA = umma::make_desc_k_sw128_addr(sbase), dW = umma::make_desc_k_sw128_addr(sbase + 128 * 64 * 4);
+  const uint32_t idesc = umma::make_idesc_tf32(N);
+  const uint32_t wpan = (uint32_t)(N * 32 * 4) >> 4;
+#pragma unroll 1
+  for (int it = 0; it < iters; ++it) {
+    if (warp == 0) {
+      if (umma::elect_one()) {
+        const long long ti = clock64();
+        uint32_t acc = 0;
+#pragma unroll 1
+        for (int g = 0; g < groups; ++g) {
+          const uint32_t td = tm + acc * (uint32_t)N;
+          umma::mma_tf32(td, dA, dW, idesc, 1);
+          umma::mma_tf32(td, dA + 2, dW + 2, idesc, 1);
+          umma::mma_tf32(td, dA + 4, dW + 4, idesc, 1);
+          umma::mma_tf32(td, dA + 6, dW + 6, idesc, 1);
+          umma::mma_tf32(td, dA + 1024, dW + wpan, idesc, 1);
+          umma::mma_tf32(td, dA + 1026, dW + wpan + 2, idesc, 1);
+          umma::mma_tf32(td, dA + 1028, dW + wpan + 4, idesc, 1);
+          umma::mma_tf32(td, dA + 1030, dW + wpan + 6, idesc, 1);
+          acc = (acc + 1 == (uint32_t)nacc) ? 0 : acc + 1;
+        }
+        if (sync_each || it == iters - 1)
+          asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(mb) : "memory");
+        tissue += clock64() - ti;
+      }
+      __syncwarp();
+    }
+    if (sync_each || it == iters - 1) {
+      umma::mbar_wait(&bar, ph);
+      ph ^= 1;
+      umma::fence_after_sync();
+    }
+  }
+  if (threadIdx.x == 0 && blockIdx.x == 0) cycles[0] = clock64() - t0;
+  if (tissue && blockIdx.x == 0) cycles[1] = tissue;
+  umma::fence_before_sync();
+  __syncthreads();
+  if (warp == 0) umma::tmem_dealloc(tmem_base_s, 256);
+}
+}  // namespace
+
+extern "C" ALG_API int alg_debug_mma_rate(int N, int nacc, int groups, int iters, int sync_each, int nblocks, long long* cycles2) {
+  long long* d;
+  if (cudaMalloc(&d, 2 * sizeof(long long)) != cudaSuccess) return -1;
+  cudaMemset(d, 0, 2 * sizeof(long long));
+  const int smem = (128 * 64 + 256 * 64) * 4 + 1024;
+  cudaFuncSetAttribute(k_mma_rate, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  k_mma_rate<<<nblocks, 128, smem>>>(N, nacc, groups, iters, sync_each, d);
+  cudaError_t e = cudaDeviceSynchronize();
+  cudaMemcpy(cycles2, d, 2 * sizeof(long long), cudaMemcpyDeviceToHost);
+  cudaFree(d);
+  return e == cudaSuccess ? 0 : -(int)e;
+}

@@ -146,48 +146,61 @@ template <int L> __device__ __forceinline__ void tc_load_w(TcCtx& c, const TcMat
   }
 }
 
-// all threads: operands are written -> thread 0 issues the MMAs -> everybody waits for completion
-template <int L> __device__ __forceinline__ void tc_mma(TcCtx& c, int K, int N, uint32_t dcol, uint32_t accumulate = 0) {
-  using SM = SmemTC<L>;
-  const bool issuer = threadIdx.x == 0;
-  uint64_t dAh = 0, dAl = 0, dWh = 0, dWl = 0;
-  if (issuer) {   // everything that does not depend on the other threads happens before the barrier
-    umma::mbar_wait(c.wbar, c.wph);                  // weight block landed (requested one epilogue ago)
-    dAh = umma::make_desc_k_sw128(c.sm + SM::oOPH); dAl = umma::make_desc_k_sw128(c.sm + SM::oOPL);
-    dWh = umma::make_desc_k_sw128(c.sm + SM::oWBH); dWl = umma::make_desc_k_sw128(c.sm + SM::oWBL);
+// all threads: operands are written -> one elected lane of warp 0 issues the MMAs -> everybody waits for completion.
+// Everything the issuing code touches is made provably warp-uniform (warp index and base addresses pass through
+// __shfl_sync, the branch is on the warp index, the lane is chosen by elect.sync): the descriptors then live in
+// uniform registers and every tcgen05.mma is a single UTCHMMA -- with a per-thread `threadIdx.x == 0` branch
+// ptxas wraps each MMA in an ELECT / R2UR waterfall loop (~170 cycles per MMA measured).
+template <int L> __device__ __forceinline__ void tc_mma8(uint32_t td, uint64_t da, uint64_t db, uint32_t idesc, uint32_t wpan, int K, uint32_t acc) {
+  // start-address field is in 16-byte units: operand panel = 128*32*4 B = 1024 units, 8 k = 32 B = 2 units
+  umma::mma_tf32(td, da, db, idesc, acc);
+  umma::mma_tf32(td, da + 2, db + 2, idesc, 1);
+  umma::mma_tf32(td, da + 4, db + 4, idesc, 1);
+  umma::mma_tf32(td, da + 6, db + 6, idesc, 1);
+  if (K > 32) {
+    umma::mma_tf32(td, da + 1024, db + wpan, idesc, 1);
+    umma::mma_tf32(td, da + 1026, db + wpan + 2, idesc, 1);
+    umma::mma_tf32(td, da + 1028, db + wpan + 4, idesc, 1);
+    umma::mma_tf32(td, da + 1030, db + wpan + 6, idesc, 1);
   }
+}
+template <int L> __device__ __forceinline__ void tc_mma(TcCtx& c, int K, int N, uint32_t dcol, uint32_t accumulate = 0, long long* ts = nullptr) {
+  using SM = SmemTC<L>;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+  if (warp == 0) umma::mbar_wait(c.wbar, c.wph);      // weight block landed (requested one epilogue ago)
+  if (ts && threadIdx.x == 0 && blockIdx.x == 148) ts[0] = clock64();
   umma::fence_async_smem();
   umma::fence_before_sync();
   __syncthreads();
-  if (issuer) {
+  if (ts && threadIdx.x == 0 && blockIdx.x == 148) ts[1] = clock64();
+  if (warp == 0) {
     umma::fence_after_sync();
+    const uint32_t sbase = __shfl_sync(0xffffffffu, umma::smem_u32(c.sm), 0);
+    const uint32_t td = __shfl_sync(0xffffffffu, c.tmem, 0) + dcol;
+    const uint32_t mbar = __shfl_sync(0xffffffffu, umma::smem_u32(c.mbar), 0);
+    const int passes = __shfl_sync(0xffffffffu, c.passes, 0);
+    const uint64_t dAh = umma::make_desc_k_sw128_addr(sbase + SM::oOPH * 4), dAl = umma::make_desc_k_sw128_addr(sbase + SM::oOPL * 4);
+    const uint64_t dWh = umma::make_desc_k_sw128_addr(sbase + SM::oWBH * 4), dWl = umma::make_desc_k_sw128_addr(sbase + SM::oWBL * 4);
     const uint32_t idesc = umma::make_idesc_tf32(N);
     const uint32_t wpan = (uint32_t)(N * 32 * 4) >> 4;             // weight panel stride in 16-byte units
-    const uint32_t td = c.tmem + dcol;
-    uint32_t acc = accumulate;
-#pragma unroll 1
-    for (int p = 0; p < c.passes; ++p) {
-      const uint64_t da0 = (c.passes == 3 && p == 0) ? dAl : dAh;  // lo*hi, hi*lo, hi*hi
-      const uint64_t db0 = (c.passes == 3 && p == 1) ? dWl : dWh;
-      // start-address field is in 16-byte units: operand panel = 128*32*4 B = 1024 units, 8 k = 32 B = 2 units
-      umma::mma_tf32(td, da0, db0, idesc, acc);
-      umma::mma_tf32(td, da0 + 2, db0 + 2, idesc, 1);
-      umma::mma_tf32(td, da0 + 4, db0 + 4, idesc, 1);
-      umma::mma_tf32(td, da0 + 6, db0 + 6, idesc, 1);
-      if (K > 32) {
-        umma::mma_tf32(td, da0 + 1024, db0 + wpan, idesc, 1);
-        umma::mma_tf32(td, da0 + 1026, db0 + wpan + 2, idesc, 1);
-        umma::mma_tf32(td, da0 + 1028, db0 + wpan + 4, idesc, 1);
-        umma::mma_tf32(td, da0 + 1030, db0 + wpan + 6, idesc, 1);
+    if (umma::elect_one()) {
+      if (passes == 3) {                                            // lo*hi, hi*lo, hi*hi
+        tc_mma8<L>(td, dAl, dWh, idesc, wpan, K, accumulate);
+        tc_mma8<L>(td, dAh, dWl, idesc, wpan, K, 1);
+        tc_mma8<L>(td, dAh, dWh, idesc, wpan, K, 1);
+      } else {
+        tc_mma8<L>(td, dAh, dWh, idesc, wpan, K, accumulate);
       }
-      acc = 1;
+      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(mbar) : "memory");
     }
-    umma::mma_commit(c.mbar);
+    __syncwarp();
+    if (ts && threadIdx.x == 0 && blockIdx.x == 148) ts[2] = clock64();
   }
   c.wph ^= 1;
   umma::mbar_wait(c.mbar, c.mph);
   c.mph ^= 1;
   umma::fence_after_sync();
+  if (ts && threadIdx.x == 0 && blockIdx.x == 148) ts[3] = clock64();
 }
 
 // this thread's row m, 16 columns starting at absolute TMEM column col
@@ -645,7 +658,7 @@ __device__ __forceinline__ void tc_mlp_bwd_hidden_st(TcCtx& c, const TcMat& w1_b
 template <int L, class Bias>
 __device__ __forceinline__ void tc_mlp_bwd_hidden(TcCtx& c, const TcMat& w1_b, const TcMat& next, Bias bias, long long* ts = nullptr) {
   if (ts && blockIdx.x == 148 && threadIdx.x == 0) ts[20] = clock64();
-  tc_mma<L>(c, 64, 64, TC_SCR);
+  tc_mma<L>(c, 64, 64, TC_SCR, 0, ts ? ts + 28 : nullptr);
   if (ts && blockIdx.x == 148 && threadIdx.x == 0) ts[21] = clock64();
   tc_load_w<L>(c, w1_b);
   if (ts && blockIdx.x == 148 && threadIdx.x == 0) ts[24] = clock64();

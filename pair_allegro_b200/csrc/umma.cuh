@@ -76,6 +76,23 @@ __device__ __forceinline__ uint64_t make_desc_k_sw128(const void* p) {
   d |= (uint64_t)2 << 61;                                       // layout type SWIZZLE_128B
   return d;
 }
+// same from a shared-space byte address (lets the caller keep the address in a uniform register)
+__device__ __forceinline__ uint64_t make_desc_k_sw128_addr(uint32_t saddr) {
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)1 << 16) | ((uint64_t)((1024u >> 4) & 0x3FFF) << 32) | ((uint64_t)1 << 46) |
+         ((uint64_t)2 << 61);
+}
+// one lane of a converged warp
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n\t"
+      ".reg .b32 rx;\n\t"
+      ".reg .pred px;\n\t"
+      "elect.sync rx|px, %1;\n\t"
+      "@px mov.s32 %0, 1;\n\t"
+      "}" : "+r"(pred) : "r"(0xffffffffu));
+  return pred != 0;
+}
 // instruction descriptor: D=F32, A=B=TF32, both K-major, M=128, N
 __host__ __device__ constexpr uint32_t make_idesc_tf32(int N) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((128u >> 4) << 24);
