@@ -477,6 +477,13 @@ def run_ours(args):
             pair.compute(atoms, lst, eflag_atom=0)
         extra["e2e_host_api_list_every_step"] = {"value": nl * 3 / (time.perf_counter() - t0) / 1e6, "unit": "Matom-steps/s",
                                                  "note": "alg_compute_host from pageable numpy buffers, neighbour list flattened+uploaded every step"}
+        # same entry point the way the LAMMPS pair style drives it: neighbor->ago > 0 between list rebuilds
+        t0 = time.perf_counter()
+        for i in range(NEIGH_EVERY):
+            atoms.f[:] = 0
+            pair.compute(atoms, lst, eflag_atom=0, neigh_ago=i)
+        extra["e2e_host_api"] = {"value": nl * NEIGH_EVERY / (time.perf_counter() - t0) / 1e6, "unit": "Matom-steps/s",
+                                 "note": "alg_compute_host from pageable numpy buffers (x up, f down every step), neighbour list uploaded every %d steps (option neigh_ago = neighbor->ago)" % NEIGH_EVERY}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:

@@ -82,7 +82,11 @@ ALG_API int alg_set_type_map(alg_handle* h, int ntypes, const int* lammps_type_t
  *   "profile"      "1": time every pipeline kernel with CUDA events (alg_get_stats)
  *   "gemm"         "tc": dense contractions on the tcgen05 tensor cores (l_max = 1) | "ffma": FP32 pipe
  *   "precision"    "strict": fp32-level accuracy (3xTF32 split on the tensor cores) | "tf32": one
- *                  TF32 pass (fast mode, ~1e-3 relative accuracy; tensor-core path only) */
+ *                  TF32 pass (fast mode, ~1e-3 relative accuracy; tensor-core path only)
+ *   "neigh_ago"    LAMMPS' neighbor->ago (steps since the last neighbour-list rebuild), set before
+ *                  alg_compute_host: when > 0 and the atom counts are unchanged, the device copy of the
+ *                  list uploaded by the previous call is reused (the reference re-reads and re-uploads
+ *                  its edge tensors every step, pair_nequip_allegro.cpp:524-529,638-641); default 0 */
 ALG_API int alg_set_option(alg_handle* h, const char* key, const char* value);
 
 /* Host-pointer force evaluation: replaces the body of PairNequIPAllegro<false>::compute()

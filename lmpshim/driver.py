@@ -47,6 +47,7 @@ def _load(path):
     lib.shim_get_eatom.restype = C.c_int
     lib.shim_set_ghost_owner.argtypes = [vp, vp]
     lib.shim_set_timestep.argtypes = [vp, C.c_longlong]
+    lib.shim_set_neigh_ago.argtypes = [vp, C.c_int]
     if hasattr(lib, "shim_compute_create"):
         lib.shim_compute_create.argtypes = [vp, C.c_int, C.POINTER(C.c_char_p)]
         lib.shim_compute_create.restype = C.c_int
@@ -106,8 +107,14 @@ class ShimLammps:
         self.lib.shim_pair_flags(self.h, C.byref(a), C.byref(b))
         return dict(restartinfo=a.value, manybody_flag=b.value, neigh_request=self.lib.shim_neigh_request_flags(self.h))
 
-    def compute(self, eflag=3, vflag=1, zero=True):
-        """eflag: 1 global energy | 2 per-atom ; vflag: 1 global virial | 4 per-atom (LAMMPS bit flags)"""
+    def set_positions(self, x):
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        self.lib.shim_set_positions(self.h, x.ctypes.data)
+
+    def compute(self, eflag=3, vflag=1, zero=True, neigh_ago=0):
+        """eflag: 1 global energy | 2 per-atom ; vflag: 1 global virial | 4 per-atom (LAMMPS bit flags);
+        neigh_ago = neighbor->ago (0 = the list was rebuilt this step)"""
+        self.lib.shim_set_neigh_ago(self.h, neigh_ago)
         if zero:
             self.lib.shim_zero_forces(self.h)
         self._ck(self.lib.shim_pair_compute(self.h, eflag, vflag))

@@ -105,6 +105,7 @@ API void shim_set_list(void* p, int inum, int gnum, const int* ilist, const int*
   if (s->pair) s->pair->init_list(0, &s->list);
 }
 
+API void shim_set_neigh_ago(void* p, int ago) { ((Shim*)p)->lmp.neighbor->ago = ago; }
 API int shim_set_newton(void* p, int newton_pair) { ((Shim*)p)->lmp.force->newton_pair = newton_pair; return 0; }
 
 API int shim_pair_create(void* p) {

@@ -97,6 +97,9 @@ struct alg_handle {
   const Pipeline* pipe_ffma = nullptr;
   const Pipeline* pipe_tc = nullptr;
   bool use_tc = false;
+  int neigh_ago = 0;                       // option neigh_ago: steps since the caller's last neighbour-list rebuild
+  int list_nlocal = -1, list_ntot = -1, list_reused = 0;
+  long long list_tot = -1;                 // device-resident copy of the host neighbour list (alg_compute_host)
   // type map
   int ntypes = 0;
   DevBuf d_tmap, d_cutsq, d_scale, d_shift;
@@ -610,6 +613,9 @@ extern "C" int alg_set_option(alg_handle* h, const char* key, const char* value)
       h->use_tc = true; h->pipe = h->pipe_tc;
     } else return fail(h, ALG_EINVAL, "gemm must be ffma or tc");
     h->pinfo = h->pipe->info(h->nl);
+  } else if (k == "neigh_ago") {
+    h->neigh_ago = atoi(v.c_str());
+    if (h->neigh_ago < 0) return fail(h, ALG_EINVAL, "neigh_ago must be >= 0");
   } else if (k == "precision") {
     if (v == "strict") h->tcw.passes = 3; else if (v == "tf32") h->tcw.passes = 1; else return fail(h, ALG_EINVAL, "precision must be strict or tf32");
   }
@@ -803,29 +809,36 @@ extern "C" int alg_compute_host(alg_handle* h, int nlocal, int nghost, const dou
   CK(cudaSetDevice(h->device));
   cudaStream_t st = h->stream;
   const int ntot = nlocal + nghost;
-  // flatten the paged LAMMPS list (ilist order, jlist order) into pinned staging
-  CK(h->h_first.ensure(sizeof(long long) * (nlocal + 1) + sizeof(int) * nlocal));
-  long long* first = h->h_first.as<long long>();
-  int* cnt = reinterpret_cast<int*>(first + nlocal + 1);
-  long long tot = 0;
-  for (int ii = 0; ii < nlocal; ++ii) { first[ii] = tot; cnt[ii] = numneigh[ilist[ii]]; tot += cnt[ii]; }
-  first[nlocal] = tot;
-  CK(h->h_stage.ensure(sizeof(int) * std::max<long long>(tot, 1)));
-  int* stage = h->h_stage.as<int>();
-#pragma omp parallel for schedule(static)
-  for (int ii = 0; ii < nlocal; ++ii) memcpy(stage + first[ii], firstneigh[ilist[ii]], sizeof(int) * cnt[ii]);
   CK(h->d_x.ensure(sizeof(double) * 3 * ntot));
   CK(h->d_type.ensure(sizeof(int) * ntot));
-  CK(h->d_ilist.ensure(sizeof(int) * nlocal));
-  CK(h->d_cand.ensure(sizeof(int) * std::max<long long>(tot, 1)));
-  CK(h->d_first.ensure(sizeof(long long) * (nlocal + 1)));
-  CK(h->d_numneigh.ensure(sizeof(int) * nlocal));
   CK(cudaMemcpyAsync(h->d_x.p, x, sizeof(double) * 3 * ntot, cudaMemcpyHostToDevice, st));
   CK(cudaMemcpyAsync(h->d_type.p, type, sizeof(int) * ntot, cudaMemcpyHostToDevice, st));
-  CK(cudaMemcpyAsync(h->d_ilist.p, ilist, sizeof(int) * nlocal, cudaMemcpyHostToDevice, st));
-  CK(cudaMemcpyAsync(h->d_cand.p, stage, sizeof(int) * tot, cudaMemcpyHostToDevice, st));
-  CK(cudaMemcpyAsync(h->d_first.p, first, sizeof(long long) * (nlocal + 1), cudaMemcpyHostToDevice, st));
-  CK(cudaMemcpyAsync(h->d_numneigh.p, cnt, sizeof(int) * nlocal, cudaMemcpyHostToDevice, st));
+  // LAMMPS rebuilds the neighbour list only every few steps (neighbor->ago == 0 on a rebuild step): with
+  // option neigh_ago > 0 the device copy of the list uploaded by the last call is reused when the atom
+  // counts still match; otherwise the paged list is flattened (ilist order, jlist order) and uploaded
+  const bool reuse = h->neigh_ago > 0 && h->list_nlocal == nlocal && h->list_ntot == ntot && h->list_tot >= 0;
+  if (!reuse) {
+    CK(h->h_first.ensure(sizeof(long long) * (nlocal + 1) + sizeof(int) * nlocal));
+    long long* first = h->h_first.as<long long>();
+    int* cnt = reinterpret_cast<int*>(first + nlocal + 1);
+    long long tot = 0;
+    for (int ii = 0; ii < nlocal; ++ii) { first[ii] = tot; cnt[ii] = numneigh[ilist[ii]]; tot += cnt[ii]; }
+    first[nlocal] = tot;
+    CK(h->h_stage.ensure(sizeof(int) * std::max<long long>(tot, 1)));
+    int* stage = h->h_stage.as<int>();
+#pragma omp parallel for schedule(static)
+    for (int ii = 0; ii < nlocal; ++ii) memcpy(stage + first[ii], firstneigh[ilist[ii]], sizeof(int) * cnt[ii]);
+    CK(h->d_ilist.ensure(sizeof(int) * nlocal));
+    CK(h->d_cand.ensure(sizeof(int) * std::max<long long>(tot, 1)));
+    CK(h->d_first.ensure(sizeof(long long) * (nlocal + 1)));
+    CK(h->d_numneigh.ensure(sizeof(int) * nlocal));
+    CK(cudaMemcpyAsync(h->d_ilist.p, ilist, sizeof(int) * nlocal, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(h->d_cand.p, stage, sizeof(int) * tot, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(h->d_first.p, first, sizeof(long long) * (nlocal + 1), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(h->d_numneigh.p, cnt, sizeof(int) * nlocal, cudaMemcpyHostToDevice, st));
+    h->list_nlocal = nlocal; h->list_ntot = ntot; h->list_tot = tot;
+  }
+  h->list_reused = reuse ? 1 : 0;
   NeighAcc acc{h->d_cand.as<int>(), h->d_first.as<long long>(), h->d_numneigh.as<int>(), 0, 0, 1};
   if (eflag_atom && eatom) CK(h->d_eatom_out.ensure(sizeof(double) * ntot));
   double eng_l = 0.0, vir_l[6] = {0, 0, 0, 0, 0, 0};
@@ -972,6 +985,7 @@ extern "C" int alg_get_stats(alg_handle* h, const char* what, double* out, int n
   if (k == "kernel_ms") { src = h->kernel_ms; m = KID_COUNT; }
   else if (k == "kernel_launches") { src = h->kernel_n; m = KID_COUNT; }
   else if (k == "step") { src = h->step_stats; m = 4; }
+  else if (k == "list_reused") { if (n > 0) out[0] = h->list_reused; return ALG_OK; }
   else return fail(h, ALG_ENOTFOUND, "unknown stats group " + k);
   for (int i = 0; i < n && i < m; ++i) out[i] = src[i];
   return ALG_OK;

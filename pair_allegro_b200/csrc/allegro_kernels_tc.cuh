@@ -419,7 +419,7 @@ template <int L, bool FIRST, int DIN> struct VinRaw {
 };
 
 // ============================================================================================
-// tensor product drivers: thread (edge e = m, channel phase uh = half), channels u = uh + 2 i,
+// tensor product drivers: thread (edge e = m, channel half uh = half) owns a contiguous block of channels,
 // processed in batches of TB channels.  The global loads of batch s+1 are issued before batch s is
 // evaluated (register double buffering), so only the first batch exposes the memory latency.
 // ============================================================================================
@@ -441,12 +441,13 @@ __device__ __forceinline__ void tc_tp_forward(const ChunkArgs& a, const LayerW& 
   const int q_lo = 2 * b, q_hi = D::lhi(b);
   auto issue = [&](int s, Raw (&r)[TB]) {
 #pragma unroll
-    for (int bb = 0; bb < TB; ++bb) r[bb].issue(a, tile, k, e, uh + D::CPH * (s * TB + bb));
+    for (int bb = 0; bb < TB; ++bb) r[bb].issue(a, tile, k, e, uh * D::CPT + s * TB + bb);
   };
   auto eval = [&](int s, const Raw (&r)[TB]) {
+    float sq[TP::N0][TB];                               // scalar paths of the batch (4 consecutive channels -> one 128-bit store)
 #pragma unroll
     for (int bb = 0; bb < TB; ++bb) {
-      const int u = uh + D::CPH * (s * TB + bb);
+      const int u = uh * D::CPT + s * TB + bb;
       float Vin[TP::DIN], G[D::NSH], Vout[TP::DOUT], sc[TP::N0];
       r[bb].expand(e, Y_s, Vin);
 #pragma unroll
@@ -454,11 +455,21 @@ __device__ __forceinline__ void tc_tp_forward(const ChunkArgs& a, const LayerW& 
       if (WANT_V) TP::template fwd<U>(Vin, G, lw.omega + u, Vout, sc);
       else TPA::template fwd<U>(Vin, G, nullptr, nullptr, sc);
 #pragma unroll
-      for (int q = 0; q < TP::N0; ++q)
-        if (q >= q_lo && q < q_hi) op_put1<L>(c, e, (q - q_lo) * U + u, sc[q]);
+      for (int q = 0; q < TP::N0; ++q) sq[q][bb] = sc[q];
       if (WANT_V) {
 #pragma unroll
         for (int cc = 0; cc < TP::DOUT; ++cc) Vng[(u * TP::DOUT + cc) * TM + e] = Vout[cc];
+      }
+    }
+    const int u0 = uh * D::CPT + s * TB;
+#pragma unroll
+    for (int q = 0; q < TP::N0; ++q) {
+      if (q >= q_lo && q < q_hi) {
+        if constexpr (TB == 4) op_put4<L>(c, (q - q_lo) * U + u0, sq[q][0], sq[q][1], sq[q][2], sq[q][3]);
+        else {
+#pragma unroll
+          for (int bb = 0; bb < TB; ++bb) op_put1<L>(c, e, (q - q_lo) * U + u0 + bb, sq[q][bb]);
+        }
       }
     }
   };
@@ -497,7 +508,8 @@ __device__ __forceinline__ void tc_tp_backward(const ChunkArgs& a, const LayerW&
 #pragma unroll
     for (int lm = 0; lm < D::NSH; ++lm) dYp[lm] = 0.f;
   }
-  auto chan = [&](int pass, int j) { return pass * D::CHU + uh + D::CPH * j; };
+  constexpr int CPP = D::CHU / D::CPH;               // channels per pass and thread (contiguous block per half)
+  auto chan = [&](int pass, int j) { return pass * D::CHU + uh * CPP + j; };
   auto issue = [&](int pass, int jb, In (&r)[TB]) {
 #pragma unroll
     for (int bb = 0; bb < TB; ++bb) {
@@ -513,7 +525,7 @@ __device__ __forceinline__ void tc_tp_backward(const ChunkArgs& a, const LayerW&
   auto eval = [&](int pass, int jb, const In (&r)[TB]) {
 #pragma unroll
     for (int bb = 0; bb < TB; ++bb) {
-      const int ul = uh + D::CPH * (jb * TB + bb);
+      const int ul = uh * CPP + jb * TB + bb;
       const int u = pass * D::CHU + ul;
       float Vin[TP::DIN], G[D::NSH], ds[TP::N0], dVin[TP::DIN], dG[D::NSH];
       r[bb].vin.expand(e, Y_s, Vin);

@@ -32,6 +32,7 @@ class PairAllegroB200:
         self.virial = np.zeros(6)
         self.eatom = None
         self.debug_lines = []
+        self._neigh_ago = 0
 
     # pair_nequip_allegro.cpp:168-172
     def settings(self, args):
@@ -105,9 +106,13 @@ class PairAllegroB200:
         return self.cutoff
 
     # pair_nequip_allegro.cpp:333-407
-    def compute(self, atom, lst, eflag=1, vflag=1, eflag_atom=1, vflag_atom=0):
+    def compute(self, atom, lst, eflag=1, vflag=1, eflag_atom=1, vflag_atom=0, neigh_ago=0):
+        """neigh_ago = LAMMPS' neighbor->ago (0 on a rebuild step): > 0 reuses the device copy of the list"""
         if lst.inum == 0:
             return
+        if neigh_ago != self._neigh_ago:
+            self.handle.set_option("neigh_ago", str(int(neigh_ago)))
+            self._neigh_ago = neigh_ago
         if vflag_atom:
             raise RuntimeError("Pair styles nequip and allegro do not support per-atom virial")
         ntot = lst.inum + lst.gnum

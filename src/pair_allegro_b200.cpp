@@ -242,6 +242,9 @@ void PairAllegroB200::compute(int eflag, int vflag)
 
   if (vflag_atom) { error->all(FLERR, "Pair styles nequip and allegro do not support per-atom virial"); }
 
+  // neighbor->ago == 0 on the steps LAMMPS rebuilt the list: in between the device copy is reused
+  alg_set_option(handle, "neigh_ago", std::to_string(neighbor->ago).c_str());
+
   // atom->x / atom->f are contiguous [ntotal][3] (LAMMPS memory->create layout): x[0], f[0]
   double eng = 0.0, vir[6] = {0, 0, 0, 0, 0, 0};
   int rc = alg_compute_host(handle, inum, nghost, &x[0][0], atom->type, list->ilist, list->numneigh, list->firstneigh,

@@ -132,3 +132,34 @@ def test_cpp_compute_allegro(name, ours_lib):
         np.testing.assert_allclose(ours["c_ae"], ref["c_ae"], rtol=1e-5, atol=1e-5)
         assert np.abs(ours["c_fo"] - ref["c_fo"]).max() < 1e-4
         assert np.abs(ours["c_vi"] - ref["c_vi"]).max() < 1e-4 * max(1.0, np.abs(ref["c_vi"]).max())
+
+
+def test_neighbour_list_reuse_between_rebuilds(ours_lib):
+    """neighbor->ago > 0: the device copy of the list is reused (no flatten + upload), result identical to
+    a full upload at the moved positions; ago == 0 or changed atom counts force the upload"""
+    from pair_allegro_b200.pair import PairAllegroB200
+    name = "CuPd_r5"
+    atom, lst, z = load_golden(name)
+    rng = np.random.default_rng(1)
+    x1 = atom.x + rng.normal(0, 0.02, atom.x.shape)
+    x1[atom.nlocal:] = x1[atom.owner[atom.nlocal:]] + (atom.x[atom.nlocal:] - atom.x[atom.owner[atom.nlocal:]])   # ghosts follow owners
+    # C++ pair style through the shim
+    lmp = driver.ShimLammps(ours_lib, atom, lst)
+    lmp.pair_style([])
+    lmp.pair_coeff(["*", "*", alg_path(name)] + str(z["type_names"]).split())
+    lmp.init(newton_pair=1)
+    lmp.compute(eflag=3, vflag=1, neigh_ago=0)
+    lmp.set_positions(x1)
+    reused = lmp.compute(eflag=3, vflag=1, neigh_ago=1)
+    fresh = lmp.compute(eflag=3, vflag=1, neigh_ago=0)
+    assert np.array_equal(reused["f"], fresh["f"]) and reused["eng_vdwl"] == fresh["eng_vdwl"]
+    assert np.array_equal(reused["eatom"], fresh["eatom"]) and np.array_equal(reused["virial"], fresh["virial"])
+    # Python mirror: the stats group tells whether the upload was skipped
+    pair = PairAllegroB200(device=0, debug_mode=False)
+    pair.coeff(["*", "*", alg_path(name)] + str(z["type_names"]).split(), atom.ntypes)
+    pair.compute(atom, lst, neigh_ago=3)                       # nothing cached yet -> uploaded
+    assert pair.handle.stats("list_reused", 1)[0] == 0
+    pair.compute(atom, lst, neigh_ago=1)
+    assert pair.handle.stats("list_reused", 1)[0] == 1
+    pair.compute(atom, lst, neigh_ago=0)
+    assert pair.handle.stats("list_reused", 1)[0] == 0
