@@ -1,4 +1,4 @@
-// Tensor-core (tcgen05) variant of the five fused edge-tile kernels, l_max = 1.
+// Tensor-core (tcgen05) variant of the five fused edge-tile kernels, l_max = 1 and 2.
 //
 // Same staging and the same HBM buffers as allegro_kernels.cuh (F0 / FK / T / BK / B0, kernel
 // boundaries at the per-centre environment sums), but every dense contraction runs on the
@@ -8,14 +8,17 @@
 //     every epilogue (TMEM lane m is readable by warps w with w%4 == m/32);
 //   * A operands (activations) are written by their producer thread straight into the K-major
 //     SWIZZLE_128B shared-memory layout of umma.cuh, B operands (weights) are pre-swizzled on
-//     the host and fetched by one TMA bulk copy (cp.async.bulk) per GEMM, overlapped with the
-//     previous epilogue;
-//   * accumulators live in TMEM; in the backward kernels the pre-activations z1, z2 and the
-//     pre-envelope MLP output m STAY in TMEM between the forward recompute and the backward
-//     GEMMs (no shared-memory copies, act'(z) re-evaluated from TMEM);
+//     the host and fetched by one TMA bulk copy (cp.async.bulk) per GEMM block, overlapped with
+//     the previous epilogue;
+//   * accumulators live in TMEM.  k_t_tc (forward + backward of the last layer in one kernel)
+//     keeps z1, z2 and the pre-envelope MLP output m in TMEM and re-evaluates act'(z) from there;
+//     k_f0_tc / k_fk_tc write act'(z1), act'(z2), m to the activation record a.ZD so that
+//     k_b0_tc / k_bk_tc run the backward without recomputing the forward;
+//   * MMAs are issued by one elected lane of warp 0 from warp-uniform descriptors (tc_mma);
 //   * strict mode = 3xTF32 (a = hi + lo split of both operands, lo*hi + hi*lo + hi*hi
 //     accumulated in fp32): error ~5e-7, i.e. fp32-level (tests/test_gpu_umma.py);
-//     fast mode = single TF32 pass.
+//     fast mode = single TF32 pass;
+//   * l_max = 2: the l-indexed width 32*(l_max+1) = 96 is processed as 64-wide blocks (DimsTC::NB).
 #pragma once
 #include "alg_common.cuh"
 #include "tp_gen.cuh"
@@ -71,7 +74,9 @@ template <int L> struct SmemTC {
   static constexpr int oE = oZZ + TM;                  // 4*TM floats: per-half partials, E_e, du partial
   static constexpr int GSROWS = (L == 1) ? 12 : 0;     // staged per-centre rows (Gamma / dGamma); 0 = always read from global
   static constexpr int oGS = oE + 4 * TM;
-  static constexpr int oSEG = oGS + GSROWS * D::F;     // int: segment table seg[TM+1], nseg, warp counts (TM + 16 ints)
+  static constexpr int GSSTRIDE = D::F + 4;            // staged row stride: +4 floats so that the rows of different centres start in
+                                                       // different banks (lanes of one warp read feature f of 1-3 distinct centres)
+  static constexpr int oSEG = oGS + GSROWS * GSSTRIDE; // int: segment table seg[TM+1], nseg, warp counts (TM + 16 ints)
   static constexpr int oBAR = oSEG + TM + 16;          // 2 mbarriers + tmem pointer (8 floats)
   static constexpr int TOTAL = oBAR + 8;
   static constexpr size_t BYTES = (size_t)TOTAL * sizeof(float) + 1024;   // + alignment slack
@@ -92,7 +97,8 @@ template <int L> struct SmemTC {
 struct RowSrc {
   const float* base;   // staged: smem row of centre cmin ; else global row of centre c0
   int c_origin;        // cmin or c0
-  __device__ __forceinline__ const float* row(int centre, int F) const { return base + (size_t)(centre - c_origin) * F; }
+  int stride;          // floats between consecutive centres (staged rows are padded: see tc_stage_rows)
+  __device__ __forceinline__ const float* row(int centre, int /*F*/) const { return base + (size_t)(centre - c_origin) * stride; }
 };
 
 constexpr uint32_t TC_SCR_COL = 192;    // scratch accumulator columns (see the TMEM map below)
@@ -287,10 +293,14 @@ template <int L> __device__ __forceinline__ RowSrc tc_stage_rows(const TcCtx& c,
   if (span <= SM::GSROWS) {
     float* GS = c.sm + SM::oGS;
     const float4* src = reinterpret_cast<const float4*>(gbase + (size_t)(cmin - c0) * D::F);
-    for (int i = threadIdx.x; i < span * D::F / 4; i += NT) reinterpret_cast<float4*>(GS)[i] = src[i];
-    r.base = GS; r.c_origin = cmin;
+    constexpr int RV = D::F / 4;                       // float4 per row
+    for (int i = threadIdx.x; i < span * RV; i += NT) {
+      const int rw = i / RV, cv = i - rw * RV;
+      reinterpret_cast<float4*>(GS + rw * SM::GSSTRIDE)[cv] = src[i];
+    }
+    r.base = GS; r.c_origin = cmin; r.stride = SM::GSSTRIDE;
   } else {
-    r.base = gbase; r.c_origin = c0;
+    r.base = gbase; r.c_origin = c0; r.stride = D::F;
   }
   __syncthreads();
   return r;
@@ -1071,19 +1081,23 @@ __global__ void __launch_bounds__(NT, 2) k_bk_tc(const __grid_constant__ ChunkAr
   const LayerW& lw = w.layer[k];
   const TcLayerW& tl = tw.layer[k];
   tc_load_w<L>(c, tw.layer[k + 1].env[0]);
+  ALG_TS(a, 3, 0);
   const Geom g = tc_geom<L>(a, w, c, es, nvalid);
   const float* Xn = a.X[k + 1] + (size_t)tile * S * TM;
   op_load_rows64<L>(c, Xn);
   __syncthreads();
   seg_build<TM>(reinterpret_cast<const int*>(c.sm + SM::oC), nvalid, reinterpret_cast<int*>(c.sm + SM::oSEG));
+  ALG_TS(a, 3, 1);
   float* dXg = a.dX + (size_t)tile * S * TM;
   const RowSrc dsrc = tc_stage_rows<L>(c, a.dgamma[k + 1], a.c0, nvalid);
+  ALG_TS(a, 3, 2);
   float dxn[32];                                      // complete dx^{k+1} of this thread's 32 columns (kept in registers)
   const float* zd = a.ZD[k + 1] + (size_t)tile * ZD_ROWS * TM;      // act'(z1), act'(z2), m of layer k (written by FK)
   {
     float dp[32], mv[32];
     tc_phase2<L>(a, w, c, tw.layer[k + 1], nullptr, tile, Xn, tl.m2_b, dsrc, dxn,
                  [&] { ld_rows32(c, dXg, dp); ld_rows32(c, zd + 128 * TM, mv); });
+  ALG_TS(a, 3, 3);
     float dup = 0.f;
 #pragma unroll
     for (int i = 0; i < 32; i += 4) {
@@ -1104,11 +1118,16 @@ __global__ void __launch_bounds__(NT, 2) k_bk_tc(const __grid_constant__ ChunkAr
     if (c.half == 0) a.du[(size_t)tile * TM + c.m] += dup + e_s[c.m];
   }
   const RowSrc gsrc = tc_stage_rows<L>(c, a.gamma[k], a.c0, nvalid);    // dGamma rows are consumed (barrier above)
+  ALG_TS(a, 3, 4);
   tc_mlp_bwd_hidden_st<L>(c, tl.m1_b, tl.m0_bx, zd);
+  ALG_TS(a, 3, 5);
   tc_din<L>(c, tl, dXg);
+  ALG_TS(a, 3, 6);
   float dYp[D::NSH];
   tc_tp_backward<L, KIND, FIRST, true>(a, lw, c, tile, k, es, nvalid, a.dV[(k + 1) & 1], FIRST ? nullptr : a.dV[k & 1], a.dgamma[k], dYp, gsrc);
+  ALG_TS(a, 3, 7);
   tc_dy_store<L, false>(a, c, tile, dYp, FIRST);
+  ALG_TS(a, 3, 8);
   tc_end(c);
 }
 
