@@ -110,7 +110,7 @@ struct alg_handle {
   // per-step scratch
   DevBuf d_x, d_type, d_ilist, d_numneigh, d_cand, d_first, d_cnt, d_rowptr, d_scan_tmp;
   DevBuf d_mtype, d_edge_j, d_edge_c, d_rvec, d_esum, d_facc, d_vacc, d_forces, d_eall, d_red, d_edge_index, d_edge_energy, d_edge_grad, d_eatom_out;
-  DevBuf d_tstamp, c_ZD[3], c_X[3], c_W0, c_V[3], c_dX, c_dV[2], c_dY, c_du, c_gamma[3], c_dgamma[3], c_carry, c_ecarry;
+  DevBuf d_tstamp, c_ZD[4], c_X[3], c_W0, c_V[3], c_dX, c_dV[2], c_dY, c_du, c_gamma[3], c_dgamma[3], c_carry, c_ecarry;
   PinBuf h_stage, h_rowptr, h_out, h_first;
   // results
   int last_nlocal = 0, last_ntot = 0;
@@ -556,7 +556,7 @@ extern "C" void alg_destroy(alg_handle* h) {
   DevBuf* bufs[] = {&h->weights, &h->d_tmap, &h->d_cutsq, &h->d_scale, &h->d_shift, &h->d_x, &h->d_type, &h->d_ilist, &h->d_numneigh,
                     &h->d_cand, &h->d_first, &h->d_cnt, &h->d_rowptr, &h->d_scan_tmp, &h->d_mtype, &h->d_edge_j, &h->d_edge_c, &h->d_rvec,
                     &h->d_esum, &h->d_facc, &h->d_vacc, &h->d_forces, &h->d_eall, &h->d_red, &h->d_edge_index, &h->d_edge_energy,
-                    &h->d_edge_grad, &h->d_eatom_out, &h->tc_weights, &h->d_tstamp, &h->c_ZD[0], &h->c_ZD[1], &h->c_ZD[2], &h->c_W0, &h->c_dX, &h->c_dY, &h->c_du, &h->c_carry, &h->c_ecarry,
+                    &h->d_edge_grad, &h->d_eatom_out, &h->tc_weights, &h->d_tstamp, &h->c_ZD[0], &h->c_ZD[1], &h->c_ZD[2], &h->c_ZD[3], &h->c_W0, &h->c_dX, &h->c_dY, &h->c_du, &h->c_carry, &h->c_ecarry,
                     &h->c_X[0], &h->c_X[1], &h->c_X[2], &h->c_V[0], &h->c_V[1], &h->c_V[2], &h->c_dV[0], &h->c_dV[1],
                     &h->c_gamma[0], &h->c_gamma[1], &h->c_gamma[2], &h->c_dgamma[0], &h->c_dgamma[1], &h->c_dgamma[2]};
   for (DevBuf* b : bufs) b->release();
@@ -633,7 +633,7 @@ static int ensure_chunk_buffers(alg_handle* h, long max_tiles, long max_centres)
   CK(h->c_W0.ensure(sizeof(float) * max_tiles * pi.ENVW * TM));
   for (int k = 1; k < h->nl; ++k) CK(h->c_V[k].ensure(sizeof(float) * max_tiles * U * pi.vdim[k] * TM));
   CK(h->c_dX.ensure(sizeof(float) * max_tiles * S * TM));
-  if (h->use_tc) for (int k = 0; k < h->nl; ++k) CK(h->c_ZD[k].ensure(sizeof(float) * max_tiles * 3 * 64 * TM));   // stage 0 = two-body, 1+k = layer k
+  if (h->use_tc) for (int k = 0; k <= h->nl; ++k) CK(h->c_ZD[k].ensure(sizeof(float) * max_tiles * 3 * 64 * TM));   // stage 0 = two-body, 1+k = layer k
   if (h->nl > 1) for (int q = 0; q < 2; ++q) CK(h->c_dV[q].ensure(sizeof(float) * max_tiles * U * pi.dvdim * TM));
   CK(h->c_dY.ensure(sizeof(float) * max_tiles * pi.NSH * TM));
   CK(h->c_du.ensure(sizeof(float) * max_tiles * TM));
@@ -735,7 +735,7 @@ static int run_step(alg_handle* h, int nlocal, int nghost, const double* d_x, co
   a.rvec = h->d_rvec.as<float4>(); a.edge_j = h->d_edge_j.as<int>(); a.edge_c = h->d_edge_c.as<int>();
   a.rowptr = h->d_rowptr.as<int>(); a.ilist = d_ilist;
   for (int k = 0; k < 3; ++k) { a.X[k] = h->c_X[k].as<float>(); a.V[k] = h->c_V[k].as<float>(); a.gamma[k] = h->c_gamma[k].as<float>(); a.dgamma[k] = h->c_dgamma[k].as<float>(); }
-  for (int k = 0; k < 3; ++k) a.ZD[k] = h->c_ZD[k].as<float>();
+  for (int k = 0; k < 4; ++k) a.ZD[k] = h->c_ZD[k].as<float>();
   a.W0 = h->c_W0.as<float>(); a.dX = h->c_dX.as<float>(); a.dV[0] = h->c_dV[0].as<float>(); a.dV[1] = h->c_dV[1].as<float>();
   a.dY = h->c_dY.as<float>(); a.du = h->c_du.as<float>(); a.carry = h->c_carry.as<float>(); a.ecarry = h->c_ecarry.as<double>();
   a.esum = h->d_esum.as<double>();

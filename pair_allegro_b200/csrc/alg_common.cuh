@@ -82,7 +82,7 @@ struct ChunkArgs {
   float* W0;            // embed weights w0 / later dw0  [tile][ENVW][TM]
   float* V[3];          // V^k, k = 1..nl-1     [tile][U][DIM_k][TM]
   float* dX;            // [tile][S][TM]
-  float* ZD[3];         // tensor-core pipeline: stored act'(z1), act'(z2), m per MLP stage  [tile][3*64][TM]
+  float* ZD[4];         // tensor-core pipeline: stored act'(z1), act'(z2), m per MLP stage (0 = two-body, 1+k = layer k)  [tile][3*64][TM]
   float* dV[2];         // ping-pong gradient of V  [tile][U][DIM][TM]
   float* dY;            // [tile][NSH][TM]
   float* du;            // [tile][TM]

@@ -259,3 +259,119 @@ extern "C" ALG_API int alg_debug_mma_rate(int N, int nacc, int groups, int iters
   cudaFree(d);
   return e == cudaSuccess ? 0 : -(int)e;
 }
+
+// ---- A operand in tensor memory: correctness + rate -------------------------------------------------
+// C[128][N] = A^T W with A (given as A[k*128+m]) split hi/lo and written to TMEM by the thread that owns row m
+// (columns [128,128+K) = hi, [192,192+K) = lo), W in shared memory as in the pipeline, D in TMEM columns [0,N).
+// rate_iters > 0 additionally repeats the 3-pass MMA group `rate_iters` times and reports cycles per MMA.
+namespace {
+__global__ void __launch_bounds__(128, 2) k_umma_ta_test(const float* __restrict__ A, const float* __restrict__ W, float* __restrict__ C,
+                                                         int K, int N, int passes, int rate_iters, long long* cycles) {
+  extern __shared__ __align__(1024) float sm_raw[];
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_base_s;
+  float* sm = sm_raw + (((1024u - (umma::smem_u32(sm_raw) & 1023u)) & 1023u) >> 2);
+  float* W_hi = sm;
+  float* W_lo = sm + 64 * 64;
+  const int t = threadIdx.x;
+  const int warp = __shfl_sync(0xffffffffu, t >> 5, 0);
+  for (int i = t; i < N * K; i += blockDim.x) {
+    const int k = i / N, n = i % N;
+    const float w = W[i];
+    const int o = umma::opk_idx(n, k, N);
+    W_hi[o] = umma::tf32_hi(w);
+    W_lo[o] = umma::tf32_lo(w);
+  }
+  if (warp == 0) umma::tmem_alloc(&tmem_base_s, 256);
+  if (t == 0) umma::mbar_init(&bar, 1);
+  umma::fence_async_smem();
+  umma::fence_before_sync();
+  __syncthreads();
+  umma::fence_after_sync();
+  const uint32_t tmem = tmem_base_s;
+  {  // row m = t: K values -> TMEM
+    const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
+    for (int k0 = 0; k0 < K; k0 += 16) {
+      float hi[16], lo[16];
+      for (int i = 0; i < 16; ++i) { const float a = A[(size_t)(k0 + i) * 128 + t]; hi[i] = umma::tf32_hi(a); lo[i] = a - hi[i]; }
+      umma::tmem_st16(lane_base + 128 + k0, hi);
+      umma::tmem_st16(lane_base + 192 + k0, lo);
+    }
+    umma::tmem_st_wait();
+  }
+  umma::fence_before_sync();
+  __syncthreads();
+  umma::fence_after_sync();
+  long long t0 = 0;
+  uint32_t ph = 0;
+  const uint32_t sbase = __shfl_sync(0xffffffffu, umma::smem_u32(sm), 0);
+  const uint32_t tm = __shfl_sync(0xffffffffu, tmem, 0);
+  const uint32_t mb = __shfl_sync(0xffffffffu, umma::smem_u32(&bar), 0);
+  const uint64_t dWh = umma::make_desc_k_sw128_addr(sbase), dWl = umma::make_desc_k_sw128_addr(sbase + 64 * 64 * 4);
+  const uint32_t idesc = umma::make_idesc_tf32(N);
+  const uint32_t wpan = (uint32_t)(N * 32 * 4) >> 4;
+  const int reps = rate_iters > 0 ? rate_iters : 1;
+  if (warp == 0) {
+    if (umma::elect_one()) {
+      t0 = clock64();
+      auto group = [&](uint32_t ta, uint64_t db, uint32_t acc) {      // K/8 MMAs, constant offsets
+        umma::mma_tf32_ta(tm, ta, db, idesc, acc);
+        umma::mma_tf32_ta(tm, ta + 8, db + 2, idesc, 1);
+        umma::mma_tf32_ta(tm, ta + 16, db + 4, idesc, 1);
+        umma::mma_tf32_ta(tm, ta + 24, db + 6, idesc, 1);
+        if (K > 32) {
+          umma::mma_tf32_ta(tm, ta + 32, db + wpan, idesc, 1);
+          umma::mma_tf32_ta(tm, ta + 40, db + wpan + 2, idesc, 1);
+          umma::mma_tf32_ta(tm, ta + 48, db + wpan + 4, idesc, 1);
+          umma::mma_tf32_ta(tm, ta + 56, db + wpan + 6, idesc, 1);
+        }
+      };
+#pragma unroll 1
+      for (int it = 0; it < reps; ++it) {
+        const uint32_t acc0 = (it == 0) ? 0u : 1u;
+        if (passes == 3) {
+          group(tm + 192, dWh, acc0);
+          group(tm + 128, dWl, 1);
+          group(tm + 128, dWh, 1);
+        } else {
+          group(tm + 128, dWh, acc0);
+        }
+      }
+      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(mb) : "memory");
+    }
+    __syncwarp();
+  }
+  umma::mbar_wait(&bar, ph);
+  umma::fence_after_sync();
+  if (t == 0 && blockIdx.x == 0 && cycles) cycles[0] = clock64() - t0;
+  {
+    const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
+    for (int c0 = 0; c0 < N; c0 += 16) {
+      float v[16];
+      umma::tmem_ld16(lane_base + c0, v);
+      if (blockIdx.x == 0) for (int i = 0; i < 16; ++i) C[(size_t)t * N + c0 + i] = v[i];
+    }
+  }
+  umma::fence_before_sync();
+  __syncthreads();
+  if (warp == 0) umma::tmem_dealloc(tmem, 256);
+}
+}  // namespace
+
+extern "C" ALG_API int alg_debug_umma_gemm_ta(const float* A, const float* W, float* C, int K, int N, int passes, int rate_iters, int nblocks,
+                                              long long* cycles) {
+  if (K % 16 || K > 64 || N % 16 || N > 64) return ALG_EINVAL;
+  float *dA, *dW, *dC; long long* dcy;
+  cudaMalloc(&dA, sizeof(float) * 128 * K); cudaMalloc(&dW, sizeof(float) * N * K); cudaMalloc(&dC, sizeof(float) * 128 * N); cudaMalloc(&dcy, 8);
+  cudaMemcpy(dA, A, sizeof(float) * 128 * K, cudaMemcpyHostToDevice);
+  cudaMemcpy(dW, W, sizeof(float) * N * K, cudaMemcpyHostToDevice);
+  cudaMemset(dcy, 0, 8);
+  const int smem = 2 * 64 * 64 * 4 + 1024;
+  cudaFuncSetAttribute(k_umma_ta_test, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  k_umma_ta_test<<<nblocks, 128, smem>>>(dA, dW, dC, K, N, passes, rate_iters, dcy);
+  cudaError_t e = cudaDeviceSynchronize();
+  cudaMemcpy(C, dC, sizeof(float) * 128 * N, cudaMemcpyDeviceToHost);
+  if (cycles) cudaMemcpy(cycles, dcy, 8, cudaMemcpyDeviceToHost);
+  cudaFree(dA); cudaFree(dW); cudaFree(dC); cudaFree(dcy);
+  return e == cudaSuccess ? 0 : -(int)e;
+}

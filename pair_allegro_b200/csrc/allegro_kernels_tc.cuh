@@ -101,7 +101,7 @@ struct RowSrc {
   __device__ __forceinline__ const float* row(int centre, int /*F*/) const { return base + (size_t)(centre - c_origin) * stride; }
 };
 
-constexpr uint32_t TC_SCR_COL = 192;    // scratch accumulator columns (see the TMEM map below)
+constexpr uint32_t TC_SCR_COL = 128;    // first accumulator block (TC_ACC, see tc_mma)
 
 struct TcCtx {
   float* sm;
@@ -157,17 +157,19 @@ template <int L> __device__ __forceinline__ void tc_load_w(TcCtx& c, const TcMat
 // __shfl_sync, the branch is on the warp index, the lane is chosen by elect.sync): the descriptors then live in
 // uniform registers and every tcgen05.mma is a single UTCHMMA -- with a per-thread `threadIdx.x == 0` branch
 // ptxas wraps each MMA in an ELECT / R2UR waterfall loop (~170 cycles per MMA measured).
-template <int L> __device__ __forceinline__ void tc_mma8(uint32_t td, uint64_t da, uint64_t db, uint32_t idesc, uint32_t wpan, int K, uint32_t acc) {
-  // start-address field is in 16-byte units: operand panel = 128*32*4 B = 1024 units, 8 k = 32 B = 2 units
-  umma::mma_tf32(td, da, db, idesc, acc);
-  umma::mma_tf32(td, da + 2, db + 2, idesc, 1);
-  umma::mma_tf32(td, da + 4, db + 4, idesc, 1);
-  umma::mma_tf32(td, da + 6, db + 6, idesc, 1);
+// TMEM column map (256 columns per CTA): A operand hi [0,64), lo [64,128); accumulators [128,192) and [192,256)
+constexpr uint32_t TC_AHI = 0, TC_ALO = 64, TC_ACC = 128, TC_ACC2 = 192;
+template <int L> __device__ __forceinline__ void tc_mma8(uint32_t td, uint32_t ta, uint64_t db, uint32_t idesc, uint32_t wpan, int K, uint32_t acc) {
+  // A: 8 k = 8 TMEM columns per MMA; B: start-address field in 16-byte units, 8 k = 32 B = 2 units, panel stride wpan
+  umma::mma_tf32_ta(td, ta, db, idesc, acc);
+  umma::mma_tf32_ta(td, ta + 8, db + 2, idesc, 1);
+  umma::mma_tf32_ta(td, ta + 16, db + 4, idesc, 1);
+  umma::mma_tf32_ta(td, ta + 24, db + 6, idesc, 1);
   if (K > 32) {
-    umma::mma_tf32(td, da + 1024, db + wpan, idesc, 1);
-    umma::mma_tf32(td, da + 1026, db + wpan + 2, idesc, 1);
-    umma::mma_tf32(td, da + 1028, db + wpan + 4, idesc, 1);
-    umma::mma_tf32(td, da + 1030, db + wpan + 6, idesc, 1);
+    umma::mma_tf32_ta(td, ta + 32, db + wpan, idesc, 1);
+    umma::mma_tf32_ta(td, ta + 40, db + wpan + 2, idesc, 1);
+    umma::mma_tf32_ta(td, ta + 48, db + wpan + 4, idesc, 1);
+    umma::mma_tf32_ta(td, ta + 56, db + wpan + 6, idesc, 1);
   }
 }
 template <int L> __device__ __forceinline__ void tc_mma(TcCtx& c, int K, int N, uint32_t dcol, uint32_t accumulate = 0, long long* ts = nullptr) {
@@ -175,27 +177,27 @@ template <int L> __device__ __forceinline__ void tc_mma(TcCtx& c, int K, int N, 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   if (warp == 0) umma::mbar_wait(c.wbar, c.wph);      // weight block landed (requested one epilogue ago)
   if (ts && threadIdx.x == 0 && blockIdx.x == 148) ts[0] = clock64();
-  umma::fence_async_smem();
+  umma::tmem_st_wait();                                // this thread's operand columns are in tensor memory
   umma::fence_before_sync();
   __syncthreads();
   if (ts && threadIdx.x == 0 && blockIdx.x == 148) ts[1] = clock64();
   if (warp == 0) {
     umma::fence_after_sync();
     const uint32_t sbase = __shfl_sync(0xffffffffu, umma::smem_u32(c.sm), 0);
-    const uint32_t td = __shfl_sync(0xffffffffu, c.tmem, 0) + dcol;
+    const uint32_t tm = __shfl_sync(0xffffffffu, c.tmem, 0);
     const uint32_t mbar = __shfl_sync(0xffffffffu, umma::smem_u32(c.mbar), 0);
     const int passes = __shfl_sync(0xffffffffu, c.passes, 0);
-    const uint64_t dAh = umma::make_desc_k_sw128_addr(sbase + SM::oOPH * 4), dAl = umma::make_desc_k_sw128_addr(sbase + SM::oOPL * 4);
+    const uint32_t td = tm + dcol;
     const uint64_t dWh = umma::make_desc_k_sw128_addr(sbase + SM::oWBH * 4), dWl = umma::make_desc_k_sw128_addr(sbase + SM::oWBL * 4);
     const uint32_t idesc = umma::make_idesc_tf32(N);
     const uint32_t wpan = (uint32_t)(N * 32 * 4) >> 4;             // weight panel stride in 16-byte units
     if (umma::elect_one()) {
       if (passes == 3) {                                            // lo*hi, hi*lo, hi*hi
-        tc_mma8<L>(td, dAl, dWh, idesc, wpan, K, accumulate);
-        tc_mma8<L>(td, dAh, dWl, idesc, wpan, K, 1);
-        tc_mma8<L>(td, dAh, dWh, idesc, wpan, K, 1);
+        tc_mma8<L>(td, tm + TC_ALO, dWh, idesc, wpan, K, accumulate);
+        tc_mma8<L>(td, tm + TC_AHI, dWl, idesc, wpan, K, 1);
+        tc_mma8<L>(td, tm + TC_AHI, dWh, idesc, wpan, K, 1);
       } else {
-        tc_mma8<L>(td, dAh, dWh, idesc, wpan, K, accumulate);
+        tc_mma8<L>(td, tm + TC_AHI, dWh, idesc, wpan, K, accumulate);
       }
       asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(mbar) : "memory");
     }
@@ -223,20 +225,19 @@ __device__ __forceinline__ void tc_ld16x2(const TcCtx& c, uint32_t colA, float* 
 #pragma unroll
   for (int i = 0; i < 16; ++i) { a[i] = __uint_as_float(ra[i]); b[i] = __uint_as_float(rb[i]); }
 }
-// write 4 consecutive k (k4 % 4 == 0) of row m into the A operand (hi [+ lo])
+// write 4 consecutive k (k4 % 4 == 0) of row m into the A operand in tensor memory (hi [+ lo])
 template <int L> __device__ __forceinline__ void op_put4(const TcCtx& c, int k4, float a, float b, float d, float e) {
-  using SM = SmemTC<L>;
-  const int o = umma::opk_idx(c.m, k4, 128);
+  const uint32_t t0 = c.tmem + ((uint32_t)(c.q * 32) << 16) + (uint32_t)k4;
   const float ah = umma::tf32_hi(a), bh = umma::tf32_hi(b), dh = umma::tf32_hi(d), eh = umma::tf32_hi(e);
-  *reinterpret_cast<float4*>(c.sm + SM::oOPH + o) = make_float4(ah, bh, dh, eh);
-  if (c.passes == 3) *reinterpret_cast<float4*>(c.sm + SM::oOPL + o) = make_float4(a - ah, b - bh, d - dh, e - eh);
+  umma::tmem_st4(t0 + TC_AHI, ah, bh, dh, eh);
+  if (c.passes == 3) umma::tmem_st4(t0 + TC_ALO, a - ah, b - bh, d - dh, e - eh);
 }
-template <int L> __device__ __forceinline__ void op_put1(const TcCtx& c, int row, int k, float a) {
-  using SM = SmemTC<L>;
-  const int o = umma::opk_idx(row, k, 128);
+// one element of this thread's own row
+template <int L> __device__ __forceinline__ void op_put1(const TcCtx& c, int /*row == c.m*/, int k, float a) {
+  const uint32_t t0 = c.tmem + ((uint32_t)(c.q * 32) << 16) + (uint32_t)k;
   const float ah = umma::tf32_hi(a);
-  c.sm[SM::oOPH + o] = ah;
-  if (c.passes == 3) c.sm[SM::oOPL + o] = a - ah;
+  umma::tmem_st1(t0 + TC_AHI, ah);
+  if (c.passes == 3) umma::tmem_st1(t0 + TC_ALO, a - ah);
 }
 // epilogue over this thread's half of NC columns: fn(n, v0..v3) for 4 consecutive columns n..n+3
 template <class Fn> __device__ __forceinline__ void tc_epi(const TcCtx& c, uint32_t dcol, int NC, Fn fn) {
@@ -277,10 +278,11 @@ template <int L> __device__ __forceinline__ void op_load_rows_bw(const TcCtx& c,
   for (int i = 0; i < 16; i += 4) op_put4<L>(c, c.half * 16 + i, v[i], v[i + 1], v[i + 2], v[i + 3]);
 }
 // this thread's 32 values (its column half) of a 64-row tile-SoA array, all loads issued together
-__device__ __forceinline__ void ld_rows32(const TcCtx& c, const float* __restrict__ g, float* v) {
+template <bool CG = false>
+__device__ __forceinline__ void ld_rows32(const TcCtx& c, const float* g, float* v) {
   const float* gp = g + (c.half * 32) * 128 + c.m;
 #pragma unroll
-  for (int i = 0; i < 32; ++i) v[i] = gp[i * 128];
+  for (int i = 0; i < 32; ++i) v[i] = CG ? __ldcg(gp + i * 128) : gp[i * 128];
 }
 
 // all threads; c_s must be published.  Ends with a barrier.
@@ -381,12 +383,12 @@ template <int L> __device__ __forceinline__ void tc_env_all(const ChunkArgs& a, 
   using D = DimsTC<L>;
 #pragma unroll 1
   for (int b = 0; b < D::NB; ++b) {
-    tc_mma<L>(c, 64, D::bw(b), b == 0 ? TC_SCR_COL : 0u);
+    tc_mma<L>(c, 64, D::bw(b), b == 0 ? TC_ACC : TC_ACC2);
     if (b + 1 < D::NB) tc_load_w<L>(c, env[b + 1]);
   }
 #pragma unroll 1
   for (int b = 0; b < D::NB; ++b) {
-    tc_env_to_ws<L>(c, b == 0 ? TC_SCR_COL : 0u, D::bw(b));
+    tc_env_to_ws<L>(c, b == 0 ? TC_ACC : TC_ACC2, D::bw(b));
     __syncthreads();
     tc_env_sum<L>(a, w, c, tile, es, b, gamma);
     if (b + 1 < D::NB) __syncthreads();              // W_s is rewritten by the next block
@@ -612,8 +614,9 @@ __device__ __forceinline__ void tc_dy_store(const ChunkArgs& a, const TcCtx& c, 
   __syncthreads();
 }
 
-// TMEM column map (256 columns per CTA): z1 [0,64)  z2 [64,128)  m [128,192)  scratch [192,256)
-constexpr uint32_t TC_Z1 = 0, TC_Z2 = 64, TC_M = 128, TC_SCR = 192;
+// every GEMM of a chain accumulates into the same TMEM block: its epilogue has consumed the previous result
+// (and the next MMA is issued behind a CTA barrier) before it is overwritten
+constexpr uint32_t TC_Z1 = TC_ACC, TC_Z2 = TC_ACC, TC_M = TC_ACC, TC_SCR = TC_ACC;
 struct NoBias { __device__ __forceinline__ float operator()(int) const { return 0.f; } };
 
 // activation record of one MLP evaluation kept for the backward kernels (tile-SoA, [3][64][128] per tile):
@@ -656,61 +659,25 @@ __device__ __forceinline__ void tc_mlp_hidden_fwd(TcCtx& c, const TcMat& w2, con
 
 // backward through the hidden layers with the STORED derivatives: dm in operand [0,64), w2_b requested:
 // dz2 = (dm W2^T) act'(z2); dz1 = (dz2 W1^T) act'(z1) -> operand; requests `next`
-template <int L>
-__device__ __forceinline__ void tc_mlp_bwd_hidden_st(TcCtx& c, const TcMat& w1_b, const TcMat& next, const float* __restrict__ zd) {
+// CG: the record was written by this very thread earlier in the same kernel (k_t_tc): read it with ld.global.cg
+template <int L, bool CG = false>
+__device__ __forceinline__ void tc_mlp_bwd_hidden_st(TcCtx& c, const TcMat& w1_b, const TcMat& next, const float* zd) {
   constexpr int TM = 128;
   float d[32];
-  ld_rows32(c, zd + 64 * TM, d);                      // act'(z2): in flight during the MMA
+  ld_rows32<CG>(c, zd + 64 * TM, d);                  // act'(z2): in flight during the MMA
   tc_mma<L>(c, 64, 64, TC_SCR);
   tc_load_w<L>(c, w1_b);
   tc_epi(c, TC_SCR, 64, [&](int n, float v0, float v1, float v2, float v3) {
     const int j = n - c.half * 32;
     op_put4<L>(c, n, v0 * d[j], v1 * d[j + 1], v2 * d[j + 2], v3 * d[j + 3]);
   });
-  ld_rows32(c, zd, d);                                // act'(z1 + bias)
+  ld_rows32<CG>(c, zd, d);                            // act'(z1 + bias)
   tc_mma<L>(c, 64, 64, TC_SCR);
   tc_load_w<L>(c, next);
   tc_epi(c, TC_SCR, 64, [&](int n, float v0, float v1, float v2, float v3) {
     const int j = n - c.half * 32;
     op_put4<L>(c, n, v0 * d[j], v1 * d[j + 1], v2 * d[j + 2], v3 * d[j + 3]);
   });
-}
-
-// dm in operand [0,64), w2_b requested: dz2 = (dm W2^T) act'(z2); dz1 = (dz2 W1^T) act'(z1+bias) -> operand; requests `next`
-template <int L, class Bias>
-__device__ __forceinline__ void tc_mlp_bwd_hidden(TcCtx& c, const TcMat& w1_b, const TcMat& next, Bias bias, long long* ts = nullptr) {
-  if (ts && blockIdx.x == 148 && threadIdx.x == 0) ts[20] = clock64();
-  tc_mma<L>(c, 64, 64, TC_SCR, 0, ts ? ts + 28 : nullptr);
-  if (ts && blockIdx.x == 148 && threadIdx.x == 0) ts[21] = clock64();
-  tc_load_w<L>(c, w1_b);
-  if (ts && blockIdx.x == 148 && threadIdx.x == 0) ts[24] = clock64();
-  if (ts && blockIdx.x == 148 && threadIdx.x == 200) ts[26] = clock64();
-  for (int c0 = c.half * 32; c0 < c.half * 32 + 32; c0 += 16) {
-    float v[16], z[16];
-    tc_ld16x2(c, TC_SCR + c0, v, TC_Z2 + c0, z);
-#pragma unroll
-    for (int i = 0; i < 16; i += 4) {
-      float d0, d1, d2, d3;
-      silu_act(z[i], d0); silu_act(z[i + 1], d1); silu_act(z[i + 2], d2); silu_act(z[i + 3], d3);
-      op_put4<L>(c, c0 + i, v[i] * d0, v[i + 1] * d1, v[i + 2] * d2, v[i + 3] * d3);
-    }
-  }
-  if (ts && blockIdx.x == 148 && threadIdx.x == 0) ts[22] = clock64();
-  if (ts && blockIdx.x == 148 && threadIdx.x == 200) ts[27] = clock64();
-  tc_mma<L>(c, 64, 64, TC_SCR);
-  if (ts && blockIdx.x == 148 && threadIdx.x == 0) ts[23] = clock64();
-  tc_load_w<L>(c, next);
-  for (int c0 = c.half * 32; c0 < c.half * 32 + 32; c0 += 16) {
-    float v[16], z[16];
-    tc_ld16x2(c, TC_SCR + c0, v, TC_Z1 + c0, z);
-#pragma unroll
-    for (int i = 0; i < 16; i += 4) {
-      float d0, d1, d2, d3;
-      silu_act(z[i] + bias(c0 + i), d0); silu_act(z[i + 1] + bias(c0 + i + 1), d1);
-      silu_act(z[i + 2] + bias(c0 + i + 2), d2); silu_act(z[i + 3] + bias(c0 + i + 3), d3);
-      op_put4<L>(c, c0 + i, v[i] * d0, v[i + 1] * d1, v[i + 2] * d2, v[i + 3] * d3);
-    }
-  }
 }
 
 // dz1 in operand, m0_bx requested: dX(global) += dz1 W0x^T ; ds = dz1 W0s^T -> DS_s.
@@ -979,13 +946,18 @@ __global__ void __launch_bounds__(NT, 2) k_t_tc(const __grid_constant__ ChunkArg
   ALG_TS(a, 2, 2);
   tc_latent_z1<L, 'A', FIRST, false>(a, lw, tl, c, tile, k, Xg, gsrc);
   ALG_TS(a, 2, 3);
-  tc_mlp_hidden_fwd<L, false>(c, tl.m2, tw.ro0, NoBias());
+  // act'(z1), act'(z2), m of this layer: written and read back by the same thread (the accumulators and the
+  // A operand occupy all of this CTA's tensor memory)
+  float* zd = a.ZD[k + 1] + (size_t)tile * ZD_ROWS * TM;
+  tc_mlp_hidden_fwd<L, true>(c, tl.m2, tw.ro0, NoBias(), zd);
   ALG_TS(a, 2, 4);
   {
     float xp[32];
     ld_rows32(c, Xg, xp);
     tc_epi(c, TC_M, 64, [&](int n, float v0, float v1, float v2, float v3) {        // x^n -> operand
       const int j = n - c.half * 32;
+      float* mp = zd + (128 + n) * TM + c.m;
+      mp[0] = v0; mp[TM] = v1; mp[2 * TM] = v2; mp[3 * TM] = v3;
       op_put4<L>(c, n, lw.a * xp[j] + lw.b * v0 * g.u, lw.a * xp[j + 1] + lw.b * v1 * g.u,
                  lw.a * xp[j + 2] + lw.b * v2 * g.u, lw.a * xp[j + 3] + lw.b * v3 * g.u);
     });
@@ -1013,6 +985,8 @@ __global__ void __launch_bounds__(NT, 2) k_t_tc(const __grid_constant__ ChunkArg
     e_s[c.half * TM + c.m] = ee;
   }
   ALG_TS(a, 2, 7);
+  float mv[32];
+  ld_rows32<true>(c, zd + 128 * TM, mv);             // m: in flight during the MMA
   tc_mma<L>(c, R, 64, TC_SCR);                       // dx^n = dz ro0^T   (the barrier inside orders e_s)
   ALG_TS(a, 2, 8);
   tc_load_w<L>(c, tl.m2_b);
@@ -1024,19 +998,18 @@ __global__ void __launch_bounds__(NT, 2) k_t_tc(const __grid_constant__ ChunkArg
   float* dXg = a.dX + (size_t)tile * S * TM;
   {
     float dup = 0.f;
-    for (int c0 = c.half * 32; c0 < c.half * 32 + 32; c0 += 16) {
-      float v[16], mv[16];
-      tc_ld16x2(c, TC_SCR + c0, v, TC_M + c0, mv);
+    tc_epi(c, TC_SCR, 64, [&](int n, float v0, float v1, float v2, float v3) {
+      const int j = n - c.half * 32;
+      float v[4] = {v0, v1, v2, v3};
 #pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        dXg[(c0 + i) * TM + c.m] = lw.a * v[i];
-        v[i] *= lw.b;                 // dxt
-        dup += v[i] * mv[i];
-        v[i] *= g.u;                  // dm
+      for (int q = 0; q < 4; ++q) {
+        dXg[(n + q) * TM + c.m] = lw.a * v[q];
+        v[q] *= lw.b;                 // dxt
+        dup += v[q] * mv[j + q];
+        v[q] *= g.u;                  // dm
       }
-#pragma unroll
-      for (int i = 0; i < 16; i += 4) op_put4<L>(c, c0 + i, v[i], v[i + 1], v[i + 2], v[i + 3]);
-    }
+      op_put4<L>(c, n, v[0], v[1], v[2], v[3]);
+    });
     if (c.half == 1) e_s[3 * TM + c.m] = dup;
     __syncthreads();
     if (c.half == 0) a.du[(size_t)tile * TM + c.m] = dup + e_s[3 * TM + c.m];
@@ -1052,7 +1025,7 @@ __global__ void __launch_bounds__(NT, 2) k_t_tc(const __grid_constant__ ChunkArg
     }
   }
   ALG_TS(a, 2, 9);
-  tc_mlp_bwd_hidden<L>(c, tl.m1_b, tl.m0_bx, NoBias(), a.tstamp ? a.tstamp + 64 : nullptr);
+  tc_mlp_bwd_hidden_st<L, true>(c, tl.m1_b, tl.m0_bx, zd);
   ALG_TS(a, 2, 10);
   tc_din<L>(c, tl, dXg);
   ALG_TS(a, 2, 11);
