@@ -646,11 +646,13 @@ static int ensure_chunk_buffers(alg_handle* h, long max_tiles, long max_centres)
   return ALG_OK;
 }
 
-static void detile(const std::vector<float>& raw, int ntiles, int rows, int TM, long E, std::vector<double>& out) {
+// row4 = the float4-packed row layout the tensor-core pipeline uses for x^k / dX (allegro_kernels_tc.cuh: st_row4)
+static void detile(const std::vector<float>& raw, int ntiles, int rows, int TM, long E, std::vector<double>& out, bool row4 = false) {
   out.assign((size_t)E * rows, 0.0);
   for (long e = 0; e < E; ++e) {
     const long t = e / TM, m = e % TM;
-    for (int r = 0; r < rows; ++r) out[(size_t)e * rows + r] = raw[((size_t)t * rows + r) * TM + m];
+    for (int r = 0; r < rows; ++r)
+      out[(size_t)e * rows + r] = row4 ? raw[(size_t)t * rows * TM + ((size_t)(r >> 2) * TM + m) * 4 + (r & 3)] : raw[((size_t)t * rows + r) * TM + m];
   }
 }
 
@@ -945,10 +947,10 @@ extern "C" int alg_get_output(alg_handle* h, const char* name, const double** pt
       return fail(h, ALG_ENOTFOUND, "intermediate outputs need a single-chunk run (raise chunk_edges)");
     } else if (key.size() == 2 && key[0] == 'x' && key[1] >= '0' && key[1] < '0' + h->nl) {
       CK(fetchf(h->c_X[key[1] - '0'].p, (size_t)h->dbg_ntiles * S * pi.TM, raw));
-      detile(raw, h->dbg_ntiles, S, pi.TM, E, out);
+      detile(raw, h->dbg_ntiles, S, pi.TM, E, out, h->use_tc);
     } else if (key == "dx0") {
       CK(fetchf(h->c_dX.p, (size_t)h->dbg_ntiles * S * pi.TM, raw));
-      detile(raw, h->dbg_ntiles, S, pi.TM, E, out);
+      detile(raw, h->dbg_ntiles, S, pi.TM, E, out, h->use_tc);
     } else if (key == "du") {
       CK(fetchf(h->c_du.p, (size_t)h->dbg_ntiles * pi.TM, raw));
       detile(raw, h->dbg_ntiles, 1, pi.TM, E, out);

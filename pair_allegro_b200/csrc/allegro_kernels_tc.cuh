@@ -258,18 +258,32 @@ template <class Fn> __device__ __forceinline__ void tc_epi_bw(const TcCtx& c, ui
 #pragma unroll
   for (int i = 0; i < 16; i += 4) fn(c0 + i, v[i], v[i + 1], v[i + 2], v[i + 3]);
 }
-// load a 64-row tile-SoA array (x^k, dX) of this tile into operand columns [0,64)
-template <int L> __device__ __forceinline__ void op_load_rows64(const TcCtx& c, const float* __restrict__ g /*tile base [64][128]*/) {
-  float v[32];
-  const float* gp = g + (c.half * 32) * 128 + c.m;
-#pragma unroll
-  for (int i = 0; i < 32; ++i) v[i] = __ldg(gp + i * 128);      // all loads in flight before the first use
-#pragma unroll
-  for (int i = 0; i < 32; i += 4) op_put4<L>(c, c.half * 32 + i, v[i], v[i + 1], v[i + 2], v[i + 3]);
+// "row4" tile layout of the arrays that are only ever touched through the epilogue mapping (x^k, dX and the
+// activation record ZD): element (row n, edge m) lives at ((n/4)*128 + m)*4 + n%4, so a thread's 4 consecutive
+// rows are one 128-bit access and a warp covers 512 contiguous bytes
+__device__ __forceinline__ void st_row4(float* g, int n4, int m, float a, float b, float d, float e) {
+  *reinterpret_cast<float4*>(g + (((n4 >> 2) * 128 + m) << 2)) = make_float4(a, b, d, e);
 }
-// same for a block of `bw` rows (64 or 32) -> operand columns [0,bw)
+// load a 64-row tile array (x^k, dX; row4 layout) of this tile into operand columns [0,64)
+template <int L> __device__ __forceinline__ void op_load_rows64(const TcCtx& c, const float* __restrict__ g /*tile base, row4 layout*/) {
+  float4 v[8];
+  const float4* gp = reinterpret_cast<const float4*>(g) + (c.half * 8) * 128 + c.m;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = __ldg(gp + i * 128);       // all loads in flight before the first use
+#pragma unroll
+  for (int i = 0; i < 8; ++i) op_put4<L>(c, c.half * 32 + 4 * i, v[i].x, v[i].y, v[i].z, v[i].w);
+}
+// a block of `bw` rows (64 or 32) of a plain tile-SoA array [row][128] -> operand columns [0,bw)
 template <int L> __device__ __forceinline__ void op_load_rows_bw(const TcCtx& c, const float* __restrict__ g, int bw) {
-  if (bw == 64) { op_load_rows64<L>(c, g); return; }
+  if (bw == 64) {      // plain tile-SoA rows [row][128] (w0 / dw0 are indexed by channel in the tensor-product drivers)
+    float v[32];
+    const float* gp = g + (c.half * 32) * 128 + c.m;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __ldg(gp + i * 128);
+#pragma unroll
+    for (int i = 0; i < 32; i += 4) op_put4<L>(c, c.half * 32 + i, v[i], v[i + 1], v[i + 2], v[i + 3]);
+    return;
+  }
   float v[16];
   const float* gp = g + (c.half * 16) * 128 + c.m;
 #pragma unroll
@@ -277,12 +291,15 @@ template <int L> __device__ __forceinline__ void op_load_rows_bw(const TcCtx& c,
 #pragma unroll
   for (int i = 0; i < 16; i += 4) op_put4<L>(c, c.half * 16 + i, v[i], v[i + 1], v[i + 2], v[i + 3]);
 }
-// this thread's 32 values (its column half) of a 64-row tile-SoA array, all loads issued together
+// this thread's 32 values (its column half) of a 64-row tile array in row4 layout, all loads issued together
 template <bool CG = false>
 __device__ __forceinline__ void ld_rows32(const TcCtx& c, const float* g, float* v) {
-  const float* gp = g + (c.half * 32) * 128 + c.m;
+  const float4* gp = reinterpret_cast<const float4*>(g) + (c.half * 8) * 128 + c.m;
 #pragma unroll
-  for (int i = 0; i < 32; ++i) v[i] = CG ? __ldcg(gp + i * 128) : gp[i * 128];
+  for (int i = 0; i < 8; ++i) {
+    const float4 q = CG ? __ldcg(gp + i * 128) : gp[i * 128];
+    v[4 * i] = q.x; v[4 * i + 1] = q.y; v[4 * i + 2] = q.z; v[4 * i + 3] = q.w;
+  }
 }
 
 // all threads; c_s must be published.  Ends with a barrier.
@@ -309,10 +326,19 @@ template <int L> __device__ __forceinline__ RowSrc tc_stage_rows(const TcCtx& c,
 }
 
 // geometry of row m (both halves compute, half 0 publishes Y_s, u_s, c_s, zz_s)
-template <int L> __device__ __forceinline__ Geom tc_geom(const ChunkArgs& a, const ModelW& w, const TcCtx& c, int es, int nvalid) {
+// the first global loads of every kernel (edge vector, centre slot), issued before the TMEM allocation /
+// barrier of tc_begin so that their DRAM latency overlaps the CTA start-up
+struct GeomIn { float4 rv; int centre; };
+__device__ __forceinline__ GeomIn tc_geom_load(const ChunkArgs& a, int es, int nvalid) {
+  const int e = es + min((int)(threadIdx.x & 127), nvalid - 1);
+  GeomIn gi;
+  gi.rv = a.rvec[e];
+  gi.centre = a.edge_c[e];
+  return gi;
+}
+template <int L> __device__ __forceinline__ Geom tc_geom(const ChunkArgs& a, const ModelW& w, const TcCtx& c, const GeomIn& gi) {
   using D = DimsTC<L>; using SM = SmemTC<L>; constexpr int TM = 128;
-  const int e = es + min(c.m, nvalid - 1);
-  const float4 rv = a.rvec[e];
+  const float4 rv = gi.rv;
   Geom g;
   const int zz = __float_as_int(rv.w);
   g.zi = zz & 255; g.zj = zz >> 8;
@@ -328,7 +354,7 @@ template <int L> __device__ __forceinline__ Geom tc_geom(const ChunkArgs& a, con
 #pragma unroll
     for (int k = 0; k < D::NSH; ++k) c.sm[SM::oY + k * TM + c.m] = Y[k];
     c.sm[SM::oU + c.m] = g.u;
-    reinterpret_cast<int*>(c.sm + SM::oC)[c.m] = a.edge_c[e];
+    reinterpret_cast<int*>(c.sm + SM::oC)[c.m] = gi.centre;
     reinterpret_cast<int*>(c.sm + SM::oZZ)[c.m] = zz;
   }
   return g;
@@ -634,8 +660,7 @@ __device__ __forceinline__ void tc_mlp_hidden_fwd(TcCtx& c, const TcMat& w2, con
       const float r0 = silu_act(v0 + bias(n), d0), r1 = silu_act(v1 + bias(n + 1), d1);
       const float r2 = silu_act(v2 + bias(n + 2), d2), r3 = silu_act(v3 + bias(n + 3), d3);
       op_put4<L>(c, n, r0, r1, r2, r3);
-      float* p = zd + n * TM + c.m;
-      p[0] = d0; p[TM] = d1; p[2 * TM] = d2; p[3 * TM] = d3;
+      st_row4(zd, n, c.m, d0, d1, d2, d3);
     } else {
       op_put4<L>(c, n, silu_act(v0 + bias(n)), silu_act(v1 + bias(n + 1)), silu_act(v2 + bias(n + 2)), silu_act(v3 + bias(n + 3)));
     }
@@ -647,8 +672,7 @@ __device__ __forceinline__ void tc_mlp_hidden_fwd(TcCtx& c, const TcMat& w2, con
       float d0, d1, d2, d3;
       const float r0 = silu_act(v0, d0), r1 = silu_act(v1, d1), r2 = silu_act(v2, d2), r3 = silu_act(v3, d3);
       op_put4<L>(c, n, r0, r1, r2, r3);
-      float* p = zd + (64 + n) * TM + c.m;
-      p[0] = d0; p[TM] = d1; p[2 * TM] = d2; p[3 * TM] = d3;
+      st_row4(zd + 64 * TM, n, c.m, d0, d1, d2, d3);
     } else {
       op_put4<L>(c, n, silu_act(v0), silu_act(v1), silu_act(v2), silu_act(v3));
     }
@@ -684,7 +708,7 @@ __device__ __forceinline__ void tc_mlp_bwd_hidden_st(TcCtx& c, const TcMat& w1_b
 // ds of all blocks is held in registers until the last MMA has read the operand / weight regions
 // that DS_s aliases.
 template <int L>
-__device__ __forceinline__ void tc_din(TcCtx& c, const TcLayerW& tl, float* __restrict__ dXg) {
+__device__ __forceinline__ void tc_din(TcCtx& c, const TcLayerW& tl, float* dXg) {
   using D = DimsTC<L>; using SM = SmemTC<L>; constexpr int TM = 128;
   float dp[32];
   ld_rows32(c, dXg, dp);                              // in flight during the MMA
@@ -692,8 +716,7 @@ __device__ __forceinline__ void tc_din(TcCtx& c, const TcLayerW& tl, float* __re
   tc_load_w<L>(c, tl.m0_bs[0]);
   tc_epi(c, TC_SCR, 64, [&](int n, float v0, float v1, float v2, float v3) {
     const int j = n - c.half * 32;
-    dXg[(n + 0) * TM + c.m] = dp[j] + v0; dXg[(n + 1) * TM + c.m] = dp[j + 1] + v1;
-    dXg[(n + 2) * TM + c.m] = dp[j + 2] + v2; dXg[(n + 3) * TM + c.m] = dp[j + 3] + v3;
+    st_row4(dXg, n, c.m, dp[j] + v0, dp[j + 1] + v1, dp[j + 2] + v2, dp[j + 3] + v3);
   });
   float* DS_s = c.sm + SM::oDS;
   if constexpr (D::NB == 1) {
@@ -809,12 +832,13 @@ template <int L>
 __global__ void __launch_bounds__(NT, 2) k_f0_tc(const __grid_constant__ ChunkArgs a, const __grid_constant__ ModelW w, const __grid_constant__ TcW tw) {
   using D = DimsTC<L>; using SM = SmemTC<L>; constexpr int TM = 128;
   extern __shared__ __align__(1024) float sm_raw[];
-  TcCtx c = tc_begin<L>(sm_raw, tw);
   const int tile = blockIdx.x;
   const int es = a.e0 + tile * TM;
   const int nvalid = min(TM, a.e1 - es);
+  const GeomIn gi = tc_geom_load(a, es, nvalid);
+  TcCtx c = tc_begin<L>(sm_raw, tw);
   tc_load_w<L>(c, tw.two0);
-  const Geom g = tc_geom<L>(a, w, c, es, nvalid);
+  const Geom g = tc_geom<L>(a, w, c, gi);
   __syncthreads();
   seg_build<TM>(reinterpret_cast<const int*>(c.sm + SM::oC), nvalid, reinterpret_cast<int*>(c.sm + SM::oSEG));
   {  // Bessel*u -> operand columns [0,32) (zero padded beyond num_bessels)
@@ -839,11 +863,10 @@ __global__ void __launch_bounds__(NT, 2) k_f0_tc(const __grid_constant__ ChunkAr
   {
     float* X0g = a.X[0] + (size_t)tile * S * TM;
     tc_epi(c, TC_M, 64, [&](int n, float v0, float v1, float v2, float v3) {
-      float* mp = zd + (128 + n) * TM + c.m;
-      mp[0] = v0; mp[TM] = v1; mp[2 * TM] = v2; mp[3 * TM] = v3;
+      st_row4(zd + 128 * TM, n, c.m, v0, v1, v2, v3);
       v0 *= g.u; v1 *= g.u; v2 *= g.u; v3 *= g.u;
       op_put4<L>(c, n, v0, v1, v2, v3);
-      X0g[(n + 0) * TM + c.m] = v0; X0g[(n + 1) * TM + c.m] = v1; X0g[(n + 2) * TM + c.m] = v2; X0g[(n + 3) * TM + c.m] = v3;
+      st_row4(X0g, n, c.m, v0, v1, v2, v3);
     });
   }
   {  // embed linear (all blocks) -> w0 in HBM/L2
@@ -888,14 +911,15 @@ template <int L, char KIND, bool FIRST>
 __global__ void __launch_bounds__(NT, 2) k_fk_tc(const __grid_constant__ ChunkArgs a, const __grid_constant__ ModelW w, const __grid_constant__ TcW tw, const int k) {
   using D = DimsTC<L>; using SM = SmemTC<L>; constexpr int TM = 128;
   extern __shared__ __align__(1024) float sm_raw[];
-  TcCtx c = tc_begin<L>(sm_raw, tw);
   const int tile = blockIdx.x;
   const int es = a.e0 + tile * TM;
   const int nvalid = min(TM, a.e1 - es);
+  const GeomIn gi = tc_geom_load(a, es, nvalid);
+  TcCtx c = tc_begin<L>(sm_raw, tw);
   const LayerW& lw = w.layer[k];
   const TcLayerW& tl = tw.layer[k];
   tc_load_w<L>(c, tl.m0s[0]);
-  const Geom g = tc_geom<L>(a, w, c, es, nvalid);
+  const Geom g = tc_geom<L>(a, w, c, gi);
   const float* Xg = a.X[k] + (size_t)tile * S * TM;
   __syncthreads();
   seg_build<TM>(reinterpret_cast<const int*>(c.sm + SM::oC), nvalid, reinterpret_cast<int*>(c.sm + SM::oSEG));
@@ -909,12 +933,11 @@ __global__ void __launch_bounds__(NT, 2) k_fk_tc(const __grid_constant__ ChunkAr
     ld_rows32(c, Xg, xp);
     tc_epi(c, TC_M, 64, [&](int n, float v0, float v1, float v2, float v3) {
       const int j = n - c.half * 32;
-      float* mp = zd + (128 + n) * TM + c.m;
-      mp[0] = v0; mp[TM] = v1; mp[2 * TM] = v2; mp[3 * TM] = v3;
+      st_row4(zd + 128 * TM, n, c.m, v0, v1, v2, v3);
       const float x0 = lw.a * xp[j] + lw.b * v0 * g.u, x1 = lw.a * xp[j + 1] + lw.b * v1 * g.u;
       const float x2 = lw.a * xp[j + 2] + lw.b * v2 * g.u, x3 = lw.a * xp[j + 3] + lw.b * v3 * g.u;
       op_put4<L>(c, n, x0, x1, x2, x3);
-      Xng[(n + 0) * TM + c.m] = x0; Xng[(n + 1) * TM + c.m] = x1; Xng[(n + 2) * TM + c.m] = x2; Xng[(n + 3) * TM + c.m] = x3;
+      st_row4(Xng, n, c.m, x0, x1, x2, x3);
     });
   }
   tc_env_all<L>(a, w, c, tw.layer[k + 1].env, tile, es, a.gamma[k + 1]);
@@ -928,15 +951,16 @@ template <int L, bool FIRST>
 __global__ void __launch_bounds__(NT, 2) k_t_tc(const __grid_constant__ ChunkArgs a, const __grid_constant__ ModelW w, const __grid_constant__ TcW tw, const int k) {
   using D = DimsTC<L>; using SM = SmemTC<L>; constexpr int TM = 128;
   extern __shared__ __align__(1024) float sm_raw[];
-  TcCtx c = tc_begin<L>(sm_raw, tw);
   const int tile = blockIdx.x;
   const int es = a.e0 + tile * TM;
   const int nvalid = min(TM, a.e1 - es);
+  const GeomIn gi = tc_geom_load(a, es, nvalid);
+  TcCtx c = tc_begin<L>(sm_raw, tw);
   const LayerW& lw = w.layer[k];
   const TcLayerW& tl = tw.layer[k];
   ALG_TS(a, 2, 0);
   tc_load_w<L>(c, tl.m0s[0]);
-  const Geom g = tc_geom<L>(a, w, c, es, nvalid);
+  const Geom g = tc_geom<L>(a, w, c, gi);
   const float* Xg = a.X[k] + (size_t)tile * S * TM;
   __syncthreads();
   seg_build<TM>(reinterpret_cast<const int*>(c.sm + SM::oC), nvalid, reinterpret_cast<int*>(c.sm + SM::oSEG));
@@ -956,8 +980,7 @@ __global__ void __launch_bounds__(NT, 2) k_t_tc(const __grid_constant__ ChunkArg
     ld_rows32(c, Xg, xp);
     tc_epi(c, TC_M, 64, [&](int n, float v0, float v1, float v2, float v3) {        // x^n -> operand
       const int j = n - c.half * 32;
-      float* mp = zd + (128 + n) * TM + c.m;
-      mp[0] = v0; mp[TM] = v1; mp[2 * TM] = v2; mp[3 * TM] = v3;
+      st_row4(zd + 128 * TM, n, c.m, v0, v1, v2, v3);
       op_put4<L>(c, n, lw.a * xp[j] + lw.b * v0 * g.u, lw.a * xp[j + 1] + lw.b * v1 * g.u,
                  lw.a * xp[j + 2] + lw.b * v2 * g.u, lw.a * xp[j + 3] + lw.b * v3 * g.u);
     });
@@ -1001,9 +1024,9 @@ __global__ void __launch_bounds__(NT, 2) k_t_tc(const __grid_constant__ ChunkArg
     tc_epi(c, TC_SCR, 64, [&](int n, float v0, float v1, float v2, float v3) {
       const int j = n - c.half * 32;
       float v[4] = {v0, v1, v2, v3};
+      st_row4(dXg, n, c.m, lw.a * v0, lw.a * v1, lw.a * v2, lw.a * v3);
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
-        dXg[(n + q) * TM + c.m] = lw.a * v[q];
         v[q] *= lw.b;                 // dxt
         dup += v[q] * mv[j + q];
         v[q] *= g.u;                  // dm
@@ -1047,15 +1070,16 @@ template <int L, char KIND, bool FIRST>
 __global__ void __launch_bounds__(NT, 2) k_bk_tc(const __grid_constant__ ChunkArgs a, const __grid_constant__ ModelW w, const __grid_constant__ TcW tw, const int k) {
   using D = DimsTC<L>; using SM = SmemTC<L>; constexpr int TM = 128;
   extern __shared__ __align__(1024) float sm_raw[];
-  TcCtx c = tc_begin<L>(sm_raw, tw);
   const int tile = blockIdx.x;
   const int es = a.e0 + tile * TM;
   const int nvalid = min(TM, a.e1 - es);
+  const GeomIn gi = tc_geom_load(a, es, nvalid);
+  TcCtx c = tc_begin<L>(sm_raw, tw);
   const LayerW& lw = w.layer[k];
   const TcLayerW& tl = tw.layer[k];
   tc_load_w<L>(c, tw.layer[k + 1].env[0]);
   ALG_TS(a, 3, 0);
-  const Geom g = tc_geom<L>(a, w, c, es, nvalid);
+  const Geom g = tc_geom<L>(a, w, c, gi);
   const float* Xn = a.X[k + 1] + (size_t)tile * S * TM;
   op_load_rows64<L>(c, Xn);
   __syncthreads();
@@ -1074,15 +1098,16 @@ __global__ void __launch_bounds__(NT, 2) k_bk_tc(const __grid_constant__ ChunkAr
     float dup = 0.f;
 #pragma unroll
     for (int i = 0; i < 32; i += 4) {
-      float v[4];
+      float v[4], dxa[4];
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         const float dx1 = dxn[i + q] + dp[i + q];
-        dXg[(c.half * 32 + i + q) * TM + c.m] = lw.a * dx1;
+        dxa[q] = lw.a * dx1;
         const float dxt = lw.b * dx1;
         dup += dxt * mv[i + q];
         v[q] = dxt * g.u;
       }
+      st_row4(dXg, c.half * 32 + i, c.m, dxa[0], dxa[1], dxa[2], dxa[3]);
       op_put4<L>(c, c.half * 32 + i, v[0], v[1], v[2], v[3]);
     }
     float* e_s = c.sm + SM::oE;
@@ -1111,12 +1136,13 @@ template <int L>
 __global__ void __launch_bounds__(NT, 2) k_b0_tc(const __grid_constant__ ChunkArgs a, const __grid_constant__ ModelW w, const __grid_constant__ TcW tw) {
   using D = DimsTC<L>; using SM = SmemTC<L>; constexpr int TM = 128;
   extern __shared__ __align__(1024) float sm_raw[];
-  TcCtx c = tc_begin<L>(sm_raw, tw);
   const int tile = blockIdx.x;
   const int es = a.e0 + tile * TM;
   const int nvalid = min(TM, a.e1 - es);
+  const GeomIn gi = tc_geom_load(a, es, nvalid);
+  TcCtx c = tc_begin<L>(sm_raw, tw);
   tc_load_w<L>(c, tw.layer[0].env[0]);
-  const Geom g = tc_geom<L>(a, w, c, es, nvalid);
+  const Geom g = tc_geom<L>(a, w, c, gi);
   // ---- phase 2 of layer 0 and the embed backward: dx0 = dX + dw env0^T + dw0 emb^T
   const float* X0 = a.X[0] + (size_t)tile * S * TM;
   op_load_rows64<L>(c, X0);
