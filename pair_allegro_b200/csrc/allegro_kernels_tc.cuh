@@ -77,7 +77,7 @@ template <int L> struct SmemTC {
   static constexpr int GSSTRIDE = D::F + 4;            // staged row stride: +4 floats so that the rows of different centres start in
                                                        // different banks (lanes of one warp read feature f of 1-3 distinct centres)
   static constexpr int oSEG = oGS + GSROWS * GSSTRIDE; // int: segment table seg[TM+1], nseg, warp counts (TM + 16 ints)
-  static constexpr int oBAR = oSEG + TM + 16;          // 2 mbarriers + tmem pointer (8 floats)
+  static constexpr int oBAR = oSEG + TM + 16;          // 3 mbarriers + tmem pointer (8 floats: mbar, wbar, tmem ptr, wbar2)
   static constexpr int TOTAL = oBAR + 8;
   static constexpr size_t BYTES = (size_t)TOTAL * sizeof(float) + 1024;   // + alignment slack
   // buffers that alias the operand / weight regions once those are dead
@@ -108,7 +108,8 @@ struct TcCtx {
   uint32_t tmem;
   uint64_t* mbar;
   uint64_t* wbar;
-  uint32_t mph, wph;
+  uint64_t* wbar2;     // second weight buffer (tc_load_w2 / tc_mma_pair)
+  uint32_t mph, wph, wph2;
   int passes;
   int m, half, q;
 };
@@ -121,16 +122,17 @@ template <int L> __device__ __forceinline__ TcCtx tc_begin(float* sm_raw, const 
   c.sm = sm_raw + (((1024u - (umma::smem_u32(sm_raw) & 1023u)) & 1023u) >> 2);
   c.mbar = reinterpret_cast<uint64_t*>(c.sm + SM::oBAR);
   c.wbar = c.mbar + 1;
+  c.wbar2 = c.mbar + 3;
   uint32_t* tptr = reinterpret_cast<uint32_t*>(c.mbar + 2);
   const int t = threadIdx.x;
   if ((t >> 5) == 0) umma::tmem_alloc(tptr, 256);
-  if (t == 0) { umma::mbar_init(c.mbar, 1); umma::mbar_init(c.wbar, 1); }
+  if (t == 0) { umma::mbar_init(c.mbar, 1); umma::mbar_init(c.wbar, 1); umma::mbar_init(c.wbar2, 1); }
   umma::fence_async_smem();
   umma::fence_before_sync();
   __syncthreads();
   umma::fence_after_sync();
   c.tmem = *tptr;
-  c.mph = c.wph = 0;
+  c.mph = c.wph = c.wph2 = 0;
   c.passes = tw.passes;
   c.m = t & 127; c.half = t >> 7; c.q = (t >> 5) & 3;
   return c;
@@ -157,6 +159,18 @@ template <int L> __device__ __forceinline__ void tc_load_w(TcCtx& c, const TcMat
 // __shfl_sync, the branch is on the warp index, the lane is chosen by elect.sync): the descriptors then live in
 // uniform registers and every tcgen05.mma is a single UTCHMMA -- with a per-thread `threadIdx.x == 0` branch
 // ptxas wraps each MMA in an ELECT / R2UR waterfall loop (~170 cycles per MMA measured).
+// second weight buffer = the scratch region at the start of the shared-memory plan (oOPH / oOPL), free whenever no
+// W_s / DS_s / dG staging is live: lets two GEMMs that share their A operand be issued as one group (tc_mma_pair)
+template <int L> __device__ __forceinline__ void tc_load_w2(TcCtx& c, const TcMat& w) {
+  using SM = SmemTC<L>;
+  if (threadIdx.x == 0) {
+    const uint32_t bytes = (uint32_t)(w.N * w.K) * 4u;
+    umma::mbar_expect_tx(c.wbar2, c.passes == 3 ? 2 * bytes : bytes);
+    umma::bulk_g2s(c.sm + SM::oOPH, w.hi, bytes, c.wbar2);
+    if (c.passes == 3) umma::bulk_g2s(c.sm + SM::oOPL, w.lo, bytes, c.wbar2);
+  }
+}
+
 // TMEM column map (256 columns per CTA): A operand hi [0,64), lo [64,128); accumulators [128,192) and [192,256)
 constexpr uint32_t TC_AHI = 0, TC_ALO = 64, TC_ACC = 128, TC_ACC2 = 192;
 template <int L> __device__ __forceinline__ void tc_mma8(uint32_t td, uint32_t ta, uint64_t db, uint32_t idesc, uint32_t wpan, int K, uint32_t acc) {
@@ -209,6 +223,48 @@ template <int L> __device__ __forceinline__ void tc_mma(TcCtx& c, int K, int N, 
   c.mph ^= 1;
   umma::fence_after_sync();
   if (ts && threadIdx.x == 0 && blockIdx.x == 148) ts[3] = clock64();
+}
+
+// two GEMMs on the SAME A operand (K columns), weights in buffer 1 (N1 -> dcol1) and buffer 2 (N2 -> dcol2):
+// one barrier, one MMA group, one commit, one wake-up
+template <int L> __device__ __forceinline__ void tc_mma_pair(TcCtx& c, int K, int N1, uint32_t dcol1, int N2, uint32_t dcol2) {
+  using SM = SmemTC<L>;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+  if (warp == 0) { umma::mbar_wait(c.wbar, c.wph); umma::mbar_wait(c.wbar2, c.wph2); }
+  umma::tmem_st_wait();
+  umma::fence_before_sync();
+  __syncthreads();
+  if (warp == 0) {
+    umma::fence_after_sync();
+    const uint32_t sbase = __shfl_sync(0xffffffffu, umma::smem_u32(c.sm), 0);
+    const uint32_t tm = __shfl_sync(0xffffffffu, c.tmem, 0);
+    const uint32_t mbar = __shfl_sync(0xffffffffu, umma::smem_u32(c.mbar), 0);
+    const int passes = __shfl_sync(0xffffffffu, c.passes, 0);
+    const uint64_t dW1h = umma::make_desc_k_sw128_addr(sbase + SM::oWBH * 4), dW1l = umma::make_desc_k_sw128_addr(sbase + SM::oWBL * 4);
+    const uint64_t dW2h = umma::make_desc_k_sw128_addr(sbase + SM::oOPH * 4), dW2l = umma::make_desc_k_sw128_addr(sbase + SM::oOPL * 4);
+    const uint32_t id1 = umma::make_idesc_tf32(N1), id2 = umma::make_idesc_tf32(N2);
+    const uint32_t wp1 = (uint32_t)(N1 * 32 * 4) >> 4, wp2 = (uint32_t)(N2 * 32 * 4) >> 4;
+    if (umma::elect_one()) {
+      if (passes == 3) {
+        tc_mma8<L>(tm + dcol1, tm + TC_ALO, dW1h, id1, wp1, K, 0);
+        tc_mma8<L>(tm + dcol2, tm + TC_ALO, dW2h, id2, wp2, K, 0);
+        tc_mma8<L>(tm + dcol1, tm + TC_AHI, dW1l, id1, wp1, K, 1);
+        tc_mma8<L>(tm + dcol2, tm + TC_AHI, dW2l, id2, wp2, K, 1);
+        tc_mma8<L>(tm + dcol1, tm + TC_AHI, dW1h, id1, wp1, K, 1);
+        tc_mma8<L>(tm + dcol2, tm + TC_AHI, dW2h, id2, wp2, K, 1);
+      } else {
+        tc_mma8<L>(tm + dcol1, tm + TC_AHI, dW1h, id1, wp1, K, 0);
+        tc_mma8<L>(tm + dcol2, tm + TC_AHI, dW2h, id2, wp2, K, 0);
+      }
+      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(mbar) : "memory");
+    }
+    __syncwarp();
+  }
+  c.wph ^= 1;
+  c.wph2 ^= 1;
+  umma::mbar_wait(c.mbar, c.mph);
+  c.mph ^= 1;
+  umma::fence_after_sync();
 }
 
 // this thread's row m, 16 columns starting at absolute TMEM column col
@@ -401,24 +457,28 @@ template <int L> __device__ __forceinline__ void tc_env_sum(const ChunkArgs& a, 
     if (sgm == 0 && contin) carry[fg] = acc * sc; else gamma[(size_t)(c_s[e0] - a.c0) * D::F + fg] = acc * sc;
   }
 }
-// env linear of x (operand [0,64)) for all blocks -> Gamma.  In: weight block env[0] requested; the
-// MLP accumulators are dead (block b lands in TMEM columns TC_SCR_COL / 0).  All MMAs run before the
-// first epilogue because W_s aliases the lo operand and the weight region.
-template <int L> __device__ __forceinline__ void tc_env_all(const ChunkArgs& a, const ModelW& w, TcCtx& c, const TcMat* env, int tile, int es,
-                                                             float* __restrict__ gamma) {
+// env-weight accumulators (block 0 in TMEM columns col0, block 1 in col1) -> Gamma
+template <int L> __device__ __forceinline__ void tc_env_finish(const ChunkArgs& a, const ModelW& w, TcCtx& c, int tile, int es, float* __restrict__ gamma,
+                                                                uint32_t col0, uint32_t col1) {
   using D = DimsTC<L>;
 #pragma unroll 1
   for (int b = 0; b < D::NB; ++b) {
-    tc_mma<L>(c, 64, D::bw(b), b == 0 ? TC_ACC : TC_ACC2);
-    if (b + 1 < D::NB) tc_load_w<L>(c, env[b + 1]);
-  }
-#pragma unroll 1
-  for (int b = 0; b < D::NB; ++b) {
-    tc_env_to_ws<L>(c, b == 0 ? TC_ACC : TC_ACC2, D::bw(b));
+    tc_env_to_ws<L>(c, b == 0 ? col0 : col1, D::bw(b));
     __syncthreads();
     tc_env_sum<L>(a, w, c, tile, es, b, gamma);
     if (b + 1 < D::NB) __syncthreads();              // W_s is rewritten by the next block
   }
+}
+// env linear of x (operand [0,64)) for all blocks -> Gamma.  In: weight block env[0] requested (buffer 1) and, for
+// l_max = 2, env[1] requested into weight buffer 2 (tc_load_w2): both blocks run as one MMA group.  W_s aliases
+// weight buffer 2 and is only written after the group has completed.
+template <int L> __device__ __forceinline__ void tc_env_all(const ChunkArgs& a, const ModelW& w, TcCtx& c, const TcMat* env, int tile, int es,
+                                                             float* __restrict__ gamma) {
+  using D = DimsTC<L>;
+  if constexpr (D::NB == 1) tc_mma<L>(c, 64, D::bw(0), TC_ACC);
+  else tc_mma_pair<L>(c, 64, D::bw(0), TC_ACC, D::bw(1), TC_ACC2);
+  tc_env_finish<L>(a, w, c, tile, es, gamma, TC_ACC, TC_ACC2);
+  (void)env;
 }
 
 // s-part operand column of (scalar path q, channel u): K index inside the 64-wide "s" block
@@ -684,8 +744,9 @@ __device__ __forceinline__ void tc_mlp_hidden_fwd(TcCtx& c, const TcMat& w2, con
 // backward through the hidden layers with the STORED derivatives: dm in operand [0,64), w2_b requested:
 // dz2 = (dm W2^T) act'(z2); dz1 = (dz2 W1^T) act'(z1) -> operand; requests `next`
 // CG: the record was written by this very thread earlier in the same kernel (k_t_tc): read it with ld.global.cg
+// next2 (optional): weights of a GEMM that shares the operand with `next` -> weight buffer 2 (tc_mma_pair)
 template <int L, bool CG = false>
-__device__ __forceinline__ void tc_mlp_bwd_hidden_st(TcCtx& c, const TcMat& w1_b, const TcMat& next, const float* zd) {
+__device__ __forceinline__ void tc_mlp_bwd_hidden_st(TcCtx& c, const TcMat& w1_b, const TcMat& next, const float* zd, const TcMat* next2 = nullptr) {
   constexpr int TM = 128;
   float d[32];
   ld_rows32<CG>(c, zd + 64 * TM, d);                  // act'(z2): in flight during the MMA
@@ -698,6 +759,7 @@ __device__ __forceinline__ void tc_mlp_bwd_hidden_st(TcCtx& c, const TcMat& w1_b
   ld_rows32<CG>(c, zd, d);                            // act'(z1 + bias)
   tc_mma<L>(c, 64, 64, TC_SCR);
   tc_load_w<L>(c, next);
+  if (next2) tc_load_w2<L>(c, *next2);
   tc_epi(c, TC_SCR, 64, [&](int n, float v0, float v1, float v2, float v3) {
     const int j = n - c.half * 32;
     op_put4<L>(c, n, v0 * d[j], v1 * d[j + 1], v2 * d[j + 2], v3 * d[j + 3]);
@@ -711,33 +773,32 @@ template <int L>
 __device__ __forceinline__ void tc_din(TcCtx& c, const TcLayerW& tl, float* dXg) {
   using D = DimsTC<L>; using SM = SmemTC<L>; constexpr int TM = 128;
   float dp[32];
-  ld_rows32(c, dXg, dp);                              // in flight during the MMA
-  tc_mma<L>(c, 64, 64, TC_SCR);
-  tc_load_w<L>(c, tl.m0_bs[0]);
-  tc_epi(c, TC_SCR, 64, [&](int n, float v0, float v1, float v2, float v3) {
+  ld_rows32(c, dXg, dp);                              // in flight during the MMAs
+  // dz1 W0x^T -> TC_ACC and dz1 W0s[block 0]^T -> TC_ACC2 as one MMA group (m0_bs[0] was requested into weight
+  // buffer 2 by the caller's tc_load_w2 -- see tc_mlp_bwd_hidden_st)
+  tc_mma_pair<L>(c, 64, 64, TC_ACC, 64, TC_ACC2);
+  if (D::NB > 1) tc_load_w<L>(c, tl.m0_bs[1]);
+  tc_epi(c, TC_ACC, 64, [&](int n, float v0, float v1, float v2, float v3) {
     const int j = n - c.half * 32;
     st_row4(dXg, n, c.m, dp[j] + v0, dp[j + 1] + v1, dp[j + 2] + v2, dp[j + 3] + v3);
   });
   float* DS_s = c.sm + SM::oDS;
   if constexpr (D::NB == 1) {
-    // DS_s aliases only the weight region, dead once the (single) MMA has completed
-    tc_mma<L>(c, 64, 64, TC_SCR);
-    tc_epi(c, TC_SCR, 64, [&](int n, float v0, float v1, float v2, float v3) {
+    // DS_s aliases only weight buffer 1, dead once the MMA group has completed
+    tc_epi(c, TC_ACC2, 64, [&](int n, float v0, float v1, float v2, float v3) {
       float* p = DS_s + n * TM + c.m;
       p[0] = v0; p[TM] = v1; p[2 * TM] = v2; p[3 * TM] = v3;
     });
   } else {
-    float dsr[32];                                    // block 0 is held in registers: DS_s aliases the lo operand of block 1's MMA
-    tc_mma<L>(c, 64, 64, TC_SCR);
-    tc_load_w<L>(c, tl.m0_bs[1]);
-    tc_epi(c, TC_SCR, 64, [&](int n, float v0, float v1, float v2, float v3) {
+    float dsr[32];                                    // block 0 is held in registers: DS_s aliases the weights of block 1's MMA
+    tc_epi(c, TC_ACC2, 64, [&](int n, float v0, float v1, float v2, float v3) {
       const int j = n - c.half * 32;
       dsr[j] = v0; dsr[j + 1] = v1; dsr[j + 2] = v2; dsr[j + 3] = v3;
     });
-    tc_mma<L>(c, 64, D::bw(1), TC_SCR);               // same operand (dz1); operands / weights are dead afterwards
+    tc_mma<L>(c, 64, D::bw(1), TC_ACC);               // same operand (dz1); weights are dead afterwards
 #pragma unroll
     for (int j = 0; j < 32; ++j) DS_s[(c.half * 32 + j) * TM + c.m] = dsr[j];
-    tc_epi_bw(c, TC_SCR, D::bw(1), [&](int n, float v0, float v1, float v2, float v3) {
+    tc_epi_bw(c, TC_ACC, D::bw(1), [&](int n, float v0, float v1, float v2, float v3) {
       float* p = DS_s + (64 + n) * TM + c.m;
       p[0] = v0; p[TM] = v1; p[2 * TM] = v2; p[3 * TM] = v3;
     });
@@ -860,6 +921,7 @@ __global__ void __launch_bounds__(NT, 2) k_f0_tc(const __grid_constant__ ChunkAr
   const float* wi = w0 + g.zi * H; const float* wj = w0 + (w.T + g.zj) * H;
   float* zd = a.ZD[0] + (size_t)tile * ZD_ROWS * TM;
   tc_mlp_hidden_fwd<L, true>(c, tw.two2, tw.emb[0], [&](int n) { return __ldg(wi + n) + __ldg(wj + n); }, zd);
+  tc_load_w2<L>(c, D::NB == 1 ? tw.layer[0].env[0] : tw.emb[1]);      // partner of the emb[0] GEMM (same operand x^0)
   {
     float* X0g = a.X[0] + (size_t)tile * S * TM;
     tc_epi(c, TC_M, 64, [&](int n, float v0, float v1, float v2, float v3) {
@@ -869,19 +931,29 @@ __global__ void __launch_bounds__(NT, 2) k_f0_tc(const __grid_constant__ ChunkAr
       st_row4(X0g, n, c.m, v0, v1, v2, v3);
     });
   }
-  {  // embed linear (all blocks) -> w0 in HBM/L2
+  {  // embed linear -> w0 in HBM/L2, env linear of layer 0 -> Gamma_0: both read the operand x^0
     float* W0g = a.W0 + (size_t)tile * D::ENVW * TM;
-#pragma unroll 1
-    for (int b = 0; b < D::NB; ++b) {
-      tc_mma<L>(c, 64, D::bw(b), TC_SCR);
-      if (b + 1 < D::NB) tc_load_w<L>(c, tw.emb[b + 1]); else tc_load_w<L>(c, tw.layer[0].env[0]);
-      tc_epi_bw(c, TC_SCR, D::bw(b), [&](int n, float v0, float v1, float v2, float v3) {
+    auto w0_store = [&](int b, uint32_t col) {
+      tc_epi_bw(c, col, D::bw(b), [&](int n, float v0, float v1, float v2, float v3) {
         float* p = W0g + (size_t)(64 * b + n) * TM + c.m;
         p[0] = v0; p[TM] = v1; p[2 * TM] = v2; p[3 * TM] = v3;
       });
+    };
+    if constexpr (D::NB == 1) {
+      // l_max = 1: emb (buffer 1) and env_0 (buffer 2) as one MMA group
+      tc_mma_pair<L>(c, 64, D::bw(0), TC_ACC, D::bw(0), TC_ACC2);
+      w0_store(0, TC_ACC);
+      tc_env_finish<L>(a, w, c, tile, es, a.gamma[0], TC_ACC2, TC_ACC2);
+    } else {
+      // l_max = 2: the two emb blocks as one group, then the two env blocks
+      tc_mma_pair<L>(c, 64, D::bw(0), TC_ACC, D::bw(1), TC_ACC2);
+      tc_load_w<L>(c, tw.layer[0].env[0]);
+      tc_load_w2<L>(c, tw.layer[0].env[1]);
+      w0_store(0, TC_ACC);
+      w0_store(1, TC_ACC2);
+      tc_env_all<L>(a, w, c, tw.layer[0].env, tile, es, a.gamma[0]);
     }
   }
-  tc_env_all<L>(a, w, c, tw.layer[0].env, tile, es, a.gamma[0]);    // env linear of layer 0 (same operand x^0)
   tc_end(c);
 }
 
@@ -927,6 +999,7 @@ __global__ void __launch_bounds__(NT, 2) k_fk_tc(const __grid_constant__ ChunkAr
   tc_latent_z1<L, KIND, FIRST, true>(a, lw, tl, c, tile, k, Xg, gsrc);
   float* zd = a.ZD[k + 1] + (size_t)tile * ZD_ROWS * TM;
   tc_mlp_hidden_fwd<L, true>(c, tl.m2, tw.layer[k + 1].env[0], NoBias(), zd);
+  if (D::NB > 1) tc_load_w2<L>(c, tw.layer[k + 1].env[1]);
   {
     float* Xng = a.X[k + 1] + (size_t)tile * S * TM;
     float xp[32];
@@ -1048,7 +1121,7 @@ __global__ void __launch_bounds__(NT, 2) k_t_tc(const __grid_constant__ ChunkArg
     }
   }
   ALG_TS(a, 2, 9);
-  tc_mlp_bwd_hidden_st<L, true>(c, tl.m1_b, tl.m0_bx, zd);
+  tc_mlp_bwd_hidden_st<L, true>(c, tl.m1_b, tl.m0_bx, zd, &tl.m0_bs[0]);
   ALG_TS(a, 2, 10);
   tc_din<L>(c, tl, dXg);
   ALG_TS(a, 2, 11);
@@ -1117,7 +1190,7 @@ __global__ void __launch_bounds__(NT, 2) k_bk_tc(const __grid_constant__ ChunkAr
   }
   const RowSrc gsrc = tc_stage_rows<L>(c, a.gamma[k], a.c0, nvalid);    // dGamma rows are consumed (barrier above)
   ALG_TS(a, 3, 4);
-  tc_mlp_bwd_hidden_st<L>(c, tl.m1_b, tl.m0_bx, zd);
+  tc_mlp_bwd_hidden_st<L>(c, tl.m1_b, tl.m0_bx, zd, &tl.m0_bs[0]);
   ALG_TS(a, 3, 5);
   tc_din<L>(c, tl, dXg);
   ALG_TS(a, 3, 6);

@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""phase timing of one steady-state CTA of k_t_tc (clock64 marks, debug=1)"""
+"""phase timing of one steady-state CTA of k_t_tc and k_bk_tc (clock64 marks, option debug=1)"""
 import os, sys
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -32,10 +32,6 @@ for i in order:
     print("  %-32s %7d" % (names[i], t[i] - prev))
     prev = t[i]
 
-b = ts[2]
-print("bwd hidden detail (T kernel): mma1 %d  epi1 %d  mma2 %d  epi2(to mark10) %d" % (b[21]-b[20], b[22]-b[21], b[23]-b[22], t[10]-b[23]))
-print("thread0: tc_load_w %d  epi-loop %d ; thread200: epi-loop %d (start offset vs t0 %d)" % (b[24]-b[21], b[22]-b[24], b[27]-b[26], b[26]-b[21]))
-print("tc_mma detail (first bwd-hidden MMA): entry->barrier %d  issue %d  commit->wake %d" % (b[29]-b[28], b[30]-b[29], b[31]-b[30]))
 t = ts[3]
 print("k_bk_tc CTA 148: total %d cycles" % (t[8] - t[0]))
 for i, nm in enumerate(["geom + x rows + seg build", "stage dgamma rows", "phase 2 (2 mma, dw epi, dx epi)", "du + dm + stage gamma rows", "bwd hidden (2 mma + 2 epi)", "dIN (2 mma + 2 epi)", "tp backward (+segsum)", "dy store"]):
