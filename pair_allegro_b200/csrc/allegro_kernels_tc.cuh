@@ -321,13 +321,20 @@ __device__ __forceinline__ void st_row4(float* g, int n4, int m, float a, float 
   *reinterpret_cast<float4*>(g + (((n4 >> 2) * 128 + m) << 2)) = make_float4(a, b, d, e);
 }
 // load a 64-row tile array (x^k, dX; row4 layout) of this tile into operand columns [0,64)
-template <int L> __device__ __forceinline__ void op_load_rows64(const TcCtx& c, const float* __restrict__ g /*tile base, row4 layout*/) {
-  float4 v[8];
-  const float4* gp = reinterpret_cast<const float4*>(g) + (c.half * 8) * 128 + c.m;
+// split form: issue the 8 loads early (no TcCtx needed), write the operand later
+__device__ __forceinline__ void ld_rows_x8(const float* __restrict__ g /*tile base, row4 layout*/, float4 (&v)[8]) {
+  const float4* gp = reinterpret_cast<const float4*>(g) + ((threadIdx.x >> 7) * 8) * 128 + (threadIdx.x & 127);
 #pragma unroll
-  for (int i = 0; i < 8; ++i) v[i] = __ldg(gp + i * 128);       // all loads in flight before the first use
+  for (int i = 0; i < 8; ++i) v[i] = __ldg(gp + i * 128);
+}
+template <int L> __device__ __forceinline__ void op_put_x8(const TcCtx& c, const float4 (&v)[8]) {
 #pragma unroll
   for (int i = 0; i < 8; ++i) op_put4<L>(c, c.half * 32 + 4 * i, v[i].x, v[i].y, v[i].z, v[i].w);
+}
+template <int L> __device__ __forceinline__ void op_load_rows64(const TcCtx& c, const float* __restrict__ g /*tile base, row4 layout*/) {
+  float4 v[8];
+  ld_rows_x8(g, v);                                             // all loads in flight before the first use
+  op_put_x8<L>(c, v);
 }
 // a block of `bw` rows (64 or 32) of a plain tile-SoA array [row][128] -> operand columns [0,bw)
 template <int L> __device__ __forceinline__ void op_load_rows_bw(const TcCtx& c, const float* __restrict__ g, int bw) {
@@ -963,15 +970,18 @@ template <int L, char KIND, bool FIRST, bool WANT_V>
 __device__ __forceinline__ void tc_latent_z1(const ChunkArgs& a, const LayerW& lw, const TcLayerW& tl, TcCtx& c, int tile, int k,
                                              const float* __restrict__ Xg, const RowSrc& gsrc) {
   using D = DimsTC<L>;
+  float4 xv[8];                                       // x^k rows: loads fly during the last s-block MMA
   tc_tp_forward<L, KIND, FIRST, WANT_V>(a, lw, c, tile, k, gsrc, 0);
+  if (D::NB == 1) ld_rows_x8(Xg, xv);
   tc_mma<L>(c, D::bw(0), 64, TC_Z1, 0);
   if (D::NB > 1) {
     tc_load_w<L>(c, tl.m0s[1]);
     tc_tp_forward<L, KIND, FIRST, false>(a, lw, c, tile, k, gsrc, 1);
+    ld_rows_x8(Xg, xv);
     tc_mma<L>(c, D::bw(D::NB - 1), 64, TC_Z1, 1);
   }
   tc_load_w<L>(c, tl.m0x);
-  op_load_rows64<L>(c, Xg);
+  op_put_x8<L>(c, xv);
   tc_mma<L>(c, 64, 64, TC_Z1, 1);
   tc_load_w<L>(c, tl.m1);
 }
@@ -1147,14 +1157,16 @@ __global__ void __launch_bounds__(NT, 2) k_bk_tc(const __grid_constant__ ChunkAr
   const int es = a.e0 + tile * TM;
   const int nvalid = min(TM, a.e1 - es);
   const GeomIn gi = tc_geom_load(a, es, nvalid);
+  const float* Xn = a.X[k + 1] + (size_t)tile * S * TM;
+  float4 xv[8];
+  ld_rows_x8(Xn, xv);                                  // DRAM latency overlaps the CTA start-up and the geometry
   TcCtx c = tc_begin<L>(sm_raw, tw);
   const LayerW& lw = w.layer[k];
   const TcLayerW& tl = tw.layer[k];
   tc_load_w<L>(c, tw.layer[k + 1].env[0]);
   ALG_TS(a, 3, 0);
   const Geom g = tc_geom<L>(a, w, c, gi);
-  const float* Xn = a.X[k + 1] + (size_t)tile * S * TM;
-  op_load_rows64<L>(c, Xn);
+  op_put_x8<L>(c, xv);
   __syncthreads();
   seg_build<TM>(reinterpret_cast<const int*>(c.sm + SM::oC), nvalid, reinterpret_cast<int*>(c.sm + SM::oSEG));
   ALG_TS(a, 3, 1);
@@ -1213,12 +1225,14 @@ __global__ void __launch_bounds__(NT, 2) k_b0_tc(const __grid_constant__ ChunkAr
   const int es = a.e0 + tile * TM;
   const int nvalid = min(TM, a.e1 - es);
   const GeomIn gi = tc_geom_load(a, es, nvalid);
+  const float* X0 = a.X[0] + (size_t)tile * S * TM;
+  float4 xv[8];
+  ld_rows_x8(X0, xv);                                  // DRAM latency overlaps the CTA start-up and the geometry
   TcCtx c = tc_begin<L>(sm_raw, tw);
   tc_load_w<L>(c, tw.layer[0].env[0]);
   const Geom g = tc_geom<L>(a, w, c, gi);
   // ---- phase 2 of layer 0 and the embed backward: dx0 = dX + dw env0^T + dw0 emb^T
-  const float* X0 = a.X[0] + (size_t)tile * S * TM;
-  op_load_rows64<L>(c, X0);
+  op_put_x8<L>(c, xv);
   __syncthreads();
   seg_build<TM>(reinterpret_cast<const int*>(c.sm + SM::oC), nvalid, reinterpret_cast<int*>(c.sm + SM::oSEG));
   const RowSrc dsrc = tc_stage_rows<L>(c, a.dgamma[0], a.c0, nvalid);
