@@ -958,6 +958,15 @@ extern "C" int alg_get_output(alg_handle* h, const char* name, const double** pt
       const int k = key[1] - '0';
       CK(fetchf(h->c_V[k].p, (size_t)h->dbg_ntiles * U * pi.vdim[k] * pi.TM, raw));
       detile(raw, h->dbg_ntiles, U * pi.vdim[k], pi.TM, E, out);      // [E][u][comp]
+      if (h->use_tc && pi.vdim[k] % 4 == 0) {                           // tensor-core pipeline: comp4 packing inside a channel block
+        const int vd = pi.vdim[k], TMv = pi.TM;
+        for (long e = 0; e < E; ++e) {
+          const long t = e / TMv, m = e % TMv;
+          for (int u = 0; u < U; ++u)
+            for (int cc = 0; cc < vd; ++cc)
+              out[((size_t)e * U + u) * vd + cc] = raw[((size_t)t * U + u) * vd * TMv + ((size_t)(cc >> 2) * TMv + m) * 4 + (cc & 3)];
+        }
+      }
     } else if ((key.rfind("gamma", 0) == 0 && key.size() == 6) || (key.rfind("dgamma", 0) == 0 && key.size() == 7)) {
       const bool d = key[0] == 'd';
       const int k = key.back() - '0';

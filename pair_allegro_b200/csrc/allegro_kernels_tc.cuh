@@ -491,6 +491,30 @@ template <int L> __device__ __forceinline__ void tc_env_all(const ChunkArgs& a, 
 // s-part operand column of (scalar path q, channel u): K index inside the 64-wide "s" block
 __device__ __forceinline__ int s_col(int q, int u) { return q * U + u; }
 
+// per-channel component vectors of V^k / dV^k (N components of edge e, channel block base `g` = [N][128] floats):
+// when N is a multiple of 4 the components are packed in groups of four per edge ("comp4": ((cc/4)*128 + e)*4 + cc%4)
+// so that a channel is N/4 128-bit accesses; otherwise plain [cc][128]
+template <int N> __device__ __forceinline__ void vec_load(const float* g, int e, float* v) {
+  if constexpr (N % 4 == 0) {
+#pragma unroll
+    for (int q = 0; q < N / 4; ++q) {
+      const float4 t = *reinterpret_cast<const float4*>(g + ((q * 128 + e) << 2));
+      v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
+    }
+  } else {
+#pragma unroll
+    for (int cc = 0; cc < N; ++cc) v[cc] = g[cc * 128 + e];
+  }
+}
+template <int N> __device__ __forceinline__ void vec_store(float* g, int e, const float* v) {
+  if constexpr (N % 4 == 0) {
+#pragma unroll
+    for (int q = 0; q < N / 4; ++q) *reinterpret_cast<float4*>(g + ((q * 128 + e) << 2)) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+  } else {
+#pragma unroll
+    for (int cc = 0; cc < N; ++cc) g[cc * 128 + e] = v[cc];
+  }
+}
 // raw global inputs of one tensor-product channel: FIRST layers read the L+1 embed weights w0[l][u]
 // (V^0 = w0 (x) Y is formed in registers), later layers read V^k[u][DIN]
 template <int L, bool FIRST, int DIN> struct VinRaw {
@@ -503,9 +527,7 @@ template <int L, bool FIRST, int DIN> struct VinRaw {
 #pragma unroll
       for (int l = 0; l <= L; ++l) v[l] = W0g[(l * U + u) * TM + e];
     } else {
-      const float* Vg = a.V[k] + ((size_t)tile * U + u) * DIN * TM;
-#pragma unroll
-      for (int cc = 0; cc < DIN; ++cc) v[cc] = Vg[cc * TM + e];
+      vec_load<DIN>(a.V[k] + ((size_t)tile * U + u) * DIN * TM, e, v);
     }
   }
   __device__ __forceinline__ void expand(int e, const float* Y_s, float* Vin) const {
@@ -561,10 +583,7 @@ __device__ __forceinline__ void tc_tp_forward(const ChunkArgs& a, const LayerW& 
       else TPA::template fwd<U>(Vin, G, nullptr, nullptr, sc);
 #pragma unroll
       for (int q = 0; q < TP::N0; ++q) sq[q][bb] = sc[q];
-      if (WANT_V) {
-#pragma unroll
-        for (int cc = 0; cc < TP::DOUT; ++cc) Vng[(u * TP::DOUT + cc) * TM + e] = Vout[cc];
-      }
+      if (WANT_V) vec_store<TP::DOUT>(Vng + (size_t)u * TP::DOUT * TM, e, Vout);
     }
     const int u0 = uh * D::CPT + s * TB;
 #pragma unroll
@@ -620,11 +639,7 @@ __device__ __forceinline__ void tc_tp_backward(const ChunkArgs& a, const LayerW&
     for (int bb = 0; bb < TB; ++bb) {
       const int u = chan(pass, jb * TB + bb);
       r[bb].vin.issue(a, tile, k, e, u);
-      if (HAS_DVOUT) {
-        const float* dVg = dVnext + ((size_t)tile * U + u) * TP::DOUT * TM;
-#pragma unroll
-        for (int cc = 0; cc < TP::DOUT; ++cc) r[bb].dv[cc] = dVg[cc * TM + e];
-      }
+      if (HAS_DVOUT) vec_load<TP::DOUT>(dVnext + ((size_t)tile * U + u) * TP::DOUT * TM, e, r[bb].dv);
     }
   };
   auto eval = [&](int pass, int jb, const In (&r)[TB]) {
@@ -649,9 +664,7 @@ __device__ __forceinline__ void tc_tp_backward(const ChunkArgs& a, const LayerW&
           W0g[(l * U + u) * TM + e] = dw;      // in place: w0 -> dw0
         }
       } else {
-        float* dVp = dVprev + ((size_t)tile * U + u) * TP::DIN * TM;
-#pragma unroll
-        for (int cc = 0; cc < TP::DIN; ++cc) dVp[cc * TM + e] = dVin[cc];
+        vec_store<TP::DIN>(dVprev + ((size_t)tile * U + u) * TP::DIN * TM, e, dVin);
       }
 #pragma unroll
       for (int lm = 0; lm < D::NSH; ++lm) DG[e * D::DGS + lm * D::CHU + ul] = dG[lm];
