@@ -566,21 +566,25 @@ __device__ __forceinline__ void tc_tp_forward(const ChunkArgs& a, const LayerW& 
   const float* gam = gsrc.row(c_s[e], D::F);
   float* Vng = WANT_V ? a.V[k + 1] + (size_t)tile * U * TP::DOUT * TM : nullptr;
   const int q_lo = 2 * b, q_hi = D::lhi(b);
-  auto issue = [&](int s, Raw (&r)[TB]) {
+  struct In { Raw vin; float G[D::NSH]; };
+  auto issue = [&](int s, In (&r)[TB]) {
 #pragma unroll
-    for (int bb = 0; bb < TB; ++bb) r[bb].issue(a, tile, k, e, uh * D::CPT + s * TB + bb);
+    for (int bb = 0; bb < TB; ++bb) {
+      const int u = uh * D::CPT + s * TB + bb;
+      r[bb].vin.issue(a, tile, k, e, u);
+#pragma unroll
+      for (int lm = 0; lm < D::NSH; ++lm) r[bb].G[lm] = gam[lm * U + u];
+    }
   };
-  auto eval = [&](int s, const Raw (&r)[TB]) {
+  auto eval = [&](int s, const In (&r)[TB]) {
     float sq[TP::N0][TB];                               // scalar paths of the batch (4 consecutive channels -> one 128-bit store)
 #pragma unroll
     for (int bb = 0; bb < TB; ++bb) {
       const int u = uh * D::CPT + s * TB + bb;
-      float Vin[TP::DIN], G[D::NSH], Vout[TP::DOUT], sc[TP::N0];
-      r[bb].expand(e, Y_s, Vin);
-#pragma unroll
-      for (int lm = 0; lm < D::NSH; ++lm) G[lm] = gam[lm * U + u];
-      if (WANT_V) TP::template fwd<U>(Vin, G, lw.omega + u, Vout, sc);
-      else TPA::template fwd<U>(Vin, G, nullptr, nullptr, sc);
+      float Vin[TP::DIN], Vout[TP::DOUT], sc[TP::N0];
+      r[bb].vin.expand(e, Y_s, Vin);
+      if (WANT_V) TP::template fwd<U>(Vin, r[bb].G, lw.omega + u, Vout, sc);
+      else TPA::template fwd<U>(Vin, r[bb].G, nullptr, nullptr, sc);
 #pragma unroll
       for (int q = 0; q < TP::N0; ++q) sq[q][bb] = sc[q];
       if (WANT_V) vec_store<TP::DOUT>(Vng + (size_t)u * TP::DOUT * TM, e, Vout);
@@ -597,7 +601,7 @@ __device__ __forceinline__ void tc_tp_forward(const ChunkArgs& a, const LayerW& 
       }
     }
   };
-  Raw ra[TB], rb[TB];
+  In ra[TB], rb[TB];
   issue(0, ra);
 #pragma unroll 1
   for (int s = 0; s < NS; s += 2) {
@@ -923,16 +927,26 @@ __global__ void __launch_bounds__(NT, 2) k_f0_tc(const __grid_constant__ ChunkAr
   __syncthreads();
   seg_build<TM>(reinterpret_cast<const int*>(c.sm + SM::oC), nvalid, reinterpret_cast<int*>(c.sm + SM::oSEG));
   {  // Bessel*u -> operand columns [0,32) (zero padded beyond num_bessels)
-    const float pref = sqrtf(2.0f / g.rc);
-    const float xr = g.r / g.rc;
-    for (int k4 = c.half * 16; k4 < c.half * 16 + 16; k4 += 4) {
-      float b[4];
+    // sin((n+1) theta) by the Chebyshev recurrence s_{n+1} = 2 cos(theta) s_n - s_{n-1}: one sincosf per edge
+    if (c.half == 0) {
+      float s1, c1;
+      sincosf(3.14159265358979323846f * (g.r / g.rc), &s1, &c1);
+      const float sc = sqrtf(2.0f / g.rc) / g.r * g.u, c2 = 2.0f * c1;
+      float sp = 0.f, sn = s1;
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int n = k4 + i;
-        b[i] = n < w.B ? pref * sinf((float)(n + 1) * (3.14159265358979323846f * xr)) / g.r * g.u : 0.f;
+      for (int k4 = 0; k4 < MAXB; k4 += 4) {
+        float b[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          b[i] = (k4 + i) < w.B ? sn * sc : 0.f;
+          const float nx = c2 * sn - sp;
+          sp = sn; sn = nx;
+        }
+        op_put4<L>(c, k4, b[0], b[1], b[2], b[3]);
       }
-      op_put4<L>(c, k4, b[0], b[1], b[2], b[3]);
+    } else {
+#pragma unroll
+      for (int k4 = 16; k4 < 32; k4 += 4) op_put4<L>(c, k4, 0.f, 0.f, 0.f, 0.f);
     }
   }
   tc_mma<L>(c, 32, 64, TC_Z1);
@@ -1278,17 +1292,20 @@ __global__ void __launch_bounds__(NT, 2) k_b0_tc(const __grid_constant__ ChunkAr
   // Bessel basis and its radial derivative (for d/dr of bessel * u)
   float bes[MAXB], dbes[MAXB];
   {
-    const float pref = sqrtf(2.0f / g.rc);
-    const float xr = g.r / g.rc;
+    // sin / cos((n+1) theta) by the Chebyshev recurrence (one sincosf per edge); only half 0 consumes them
+    const float pref = sqrtf(2.0f / g.rc), ir = 1.0f / g.r, irc = 1.0f / g.rc;
+    float s1, c1;
+    sincosf(3.14159265358979323846f * (g.r * irc), &s1, &c1);
+    const float c2 = 2.0f * c1;
+    float sp = 0.f, sn = s1, cp = 1.f, cs = c1;
 #pragma unroll
     for (int n = 0; n < MAXB; ++n) {
-      if (n < w.B) {
-        const float kn = (float)(n + 1) * 3.14159265358979323846f;
-        float sn, cs;
-        sincosf(kn * xr, &sn, &cs);
-        bes[n] = pref * sn / g.r;
-        dbes[n] = pref * (kn / g.rc * cs / g.r - sn / (g.r * g.r));
-      } else { bes[n] = 0.f; dbes[n] = 0.f; }
+      const float kn = (float)(n + 1) * 3.14159265358979323846f;
+      const bool on = n < w.B;
+      bes[n] = on ? pref * sn * ir : 0.f;
+      dbes[n] = on ? pref * (kn * irc * cs * ir - sn * ir * ir) : 0.f;
+      const float ns = c2 * sn - sp, nc = c2 * cs - cp;
+      sp = sn; sn = ns; cp = cs; cs = nc;
     }
   }
   tc_mma<L>(c, 64, 32, TC_SCR);                          // d(bessel*u) = dz1 W0[bessel rows]^T  (N padded to 32)
