@@ -517,9 +517,28 @@ template <int N> __device__ __forceinline__ void vec_store(float* g, int e, cons
 }
 // raw global inputs of one tensor-product channel: FIRST layers read the L+1 embed weights w0[l][u]
 // (V^0 = w0 (x) Y is formed in registers), later layers read V^k[u][DIN]
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 template <int L, bool FIRST, int DIN> struct VinRaw {
   static constexpr int N = FIRST ? (L + 1) : DIN;
   float v[N];
+  // pull the lines a later issue() will read into L2 (no registers held)
+  __device__ __forceinline__ static void prefetch(const ChunkArgs& a, int tile, int k, int e, int u) {
+    using D = DimsTC<L>; constexpr int TM = 128;
+    if (FIRST) {
+      const float* W0g = a.W0 + (size_t)tile * D::ENVW * TM;
+#pragma unroll
+      for (int l = 0; l <= L; ++l) prefetch_l2(W0g + (l * U + u) * TM + e);
+    } else {
+      const float* Vg = a.V[k] + ((size_t)tile * U + u) * DIN * TM;
+      if constexpr (DIN % 4 == 0) {
+#pragma unroll
+        for (int q = 0; q < DIN / 4; ++q) prefetch_l2(Vg + ((q * 128 + e) << 2));
+      } else {
+#pragma unroll
+        for (int cc = 0; cc < DIN; ++cc) prefetch_l2(Vg + cc * TM + e);
+      }
+    }
+  }
   __device__ __forceinline__ void issue(const ChunkArgs& a, int tile, int k, int e, int u) {
     using D = DimsTC<L>; constexpr int TM = 128;
     if (FIRST) {
@@ -603,6 +622,10 @@ __device__ __forceinline__ void tc_tp_forward(const ChunkArgs& a, const LayerW& 
   };
   In ra[TB], rb[TB];
   issue(0, ra);
+  if (b == 0) {
+#pragma unroll 1
+    for (int i = TB; i < D::CPT; ++i) Raw::prefetch(a, tile, k, e, uh * D::CPT + i);
+  }
 #pragma unroll 1
   for (int s = 0; s < NS; s += 2) {
     issue(s + 1, rb);
@@ -676,6 +699,21 @@ __device__ __forceinline__ void tc_tp_backward(const ChunkArgs& a, const LayerW&
   };
   In ra[TB], rb[TB];
   issue(0, 0, ra);
+#pragma unroll 1
+  for (int i = TB; i < U / D::CPH; ++i) {               // all remaining channels of this thread -> L2
+    const int u = chan(i / CPP, i % CPP);
+    Raw::prefetch(a, tile, k, e, u);
+    if (HAS_DVOUT) {
+      const float* dVg = dVnext + ((size_t)tile * U + u) * TP::DOUT * TM;
+      if constexpr (TP::DOUT % 4 == 0) {
+#pragma unroll
+        for (int q = 0; q < TP::DOUT / 4; ++q) prefetch_l2(dVg + ((q * 128 + e) << 2));
+      } else {
+#pragma unroll
+        for (int cc = 0; cc < TP::DOUT; ++cc) prefetch_l2(dVg + cc * TM + e);
+      }
+    }
+  }
 #pragma unroll 1
   for (int pass = 0; pass < NPASS; ++pass) {
 #pragma unroll 1
