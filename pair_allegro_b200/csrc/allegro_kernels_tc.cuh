@@ -391,6 +391,7 @@ template <int L> __device__ __forceinline__ RowSrc tc_stage_rows(const TcCtx& c,
 // geometry of row m (both halves compute, half 0 publishes Y_s, u_s, c_s, zz_s)
 // the first global loads of every kernel (edge vector, centre slot), issued before the TMEM allocation /
 // barrier of tc_begin so that their DRAM latency overlaps the CTA start-up
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 struct GeomIn { float4 rv; int centre; };
 __device__ __forceinline__ GeomIn tc_geom_load(const ChunkArgs& a, int es, int nvalid) {
   const int e = es + min((int)(threadIdx.x & 127), nvalid - 1);
@@ -398,6 +399,16 @@ __device__ __forceinline__ GeomIn tc_geom_load(const ChunkArgs& a, int es, int n
   gi.rv = a.rvec[e];
   gi.centre = a.edge_c[e];
   return gi;
+}
+// pull a contiguous per-tile array into L2 at kernel start (one 128-byte line per thread and step): the kernels
+// are latency-bound, their later loads then hit L2 instead of DRAM
+__device__ __forceinline__ void tc_prefetch(const float* p, int nfloats) {
+  for (int i = threadIdx.x * 32; i < nfloats; i += NT * 32) prefetch_l2(p + i);
+}
+// the per-centre row (Gamma / dGamma, F floats) of this thread's centre: lane m pulls line (m mod F/32)
+template <int L> __device__ __forceinline__ void tc_prefetch_row(const float* gbase, int c0, const GeomIn& gi) {
+  using D = DimsTC<L>;
+  prefetch_l2(gbase + (size_t)(gi.centre - c0) * D::F + (threadIdx.x % (D::F / 32)) * 32);
 }
 template <int L> __device__ __forceinline__ Geom tc_geom(const ChunkArgs& a, const ModelW& w, const TcCtx& c, const GeomIn& gi) {
   using D = DimsTC<L>; using SM = SmemTC<L>; constexpr int TM = 128;
@@ -517,7 +528,6 @@ template <int N> __device__ __forceinline__ void vec_store(float* g, int e, cons
 }
 // raw global inputs of one tensor-product channel: FIRST layers read the L+1 embed weights w0[l][u]
 // (V^0 = w0 (x) Y is formed in registers), later layers read V^k[u][DIN]
-__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 template <int L, bool FIRST, int DIN> struct VinRaw {
   static constexpr int N = FIRST ? (L + 1) : DIN;
   float v[N];
@@ -1062,6 +1072,8 @@ __global__ void __launch_bounds__(NT, 2) k_fk_tc(const __grid_constant__ ChunkAr
   const int es = a.e0 + tile * TM;
   const int nvalid = min(TM, a.e1 - es);
   const GeomIn gi = tc_geom_load(a, es, nvalid);
+  tc_prefetch(a.X[k] + (size_t)tile * S * TM, S * TM);
+  tc_prefetch_row<L>(a.gamma[k], a.c0, gi);
   TcCtx c = tc_begin<L>(sm_raw, tw);
   const LayerW& lw = w.layer[k];
   const TcLayerW& tl = tw.layer[k];
@@ -1103,6 +1115,8 @@ __global__ void __launch_bounds__(NT, 2) k_t_tc(const __grid_constant__ ChunkArg
   const int es = a.e0 + tile * TM;
   const int nvalid = min(TM, a.e1 - es);
   const GeomIn gi = tc_geom_load(a, es, nvalid);
+  tc_prefetch(a.X[k] + (size_t)tile * S * TM, S * TM);
+  tc_prefetch_row<L>(a.gamma[k], a.c0, gi);
   TcCtx c = tc_begin<L>(sm_raw, tw);
   const LayerW& lw = w.layer[k];
   const TcLayerW& tl = tw.layer[k];
@@ -1225,6 +1239,11 @@ __global__ void __launch_bounds__(NT, 2) k_bk_tc(const __grid_constant__ ChunkAr
   const float* Xn = a.X[k + 1] + (size_t)tile * S * TM;
   float4 xv[8];
   ld_rows_x8(Xn, xv);                                  // DRAM latency overlaps the CTA start-up and the geometry
+  tc_prefetch_row<L>(a.dgamma[k + 1], a.c0, gi);
+  tc_prefetch_row<L>(a.gamma[k], a.c0, gi);
+  tc_prefetch(a.dX + (size_t)tile * S * TM, S * TM);
+  tc_prefetch(a.ZD[k + 1] + (size_t)tile * ZD_ROWS * TM, ZD_ROWS * TM);
+  tc_prefetch(a.dY + (size_t)tile * D::NSH * TM, D::NSH * TM);
   TcCtx c = tc_begin<L>(sm_raw, tw);
   const LayerW& lw = w.layer[k];
   const TcLayerW& tl = tw.layer[k];
@@ -1293,6 +1312,12 @@ __global__ void __launch_bounds__(NT, 2) k_b0_tc(const __grid_constant__ ChunkAr
   const float* X0 = a.X[0] + (size_t)tile * S * TM;
   float4 xv[8];
   ld_rows_x8(X0, xv);                                  // DRAM latency overlaps the CTA start-up and the geometry
+  tc_prefetch_row<L>(a.dgamma[0], a.c0, gi);
+  tc_prefetch(a.dX + (size_t)tile * S * TM, S * TM);
+  tc_prefetch(a.ZD[0] + (size_t)tile * ZD_ROWS * TM, ZD_ROWS * TM);
+  tc_prefetch(a.W0 + (size_t)tile * D::ENVW * TM, D::ENVW * TM);
+  tc_prefetch(a.dY + (size_t)tile * D::NSH * TM, D::NSH * TM);
+  tc_prefetch(a.du + (size_t)tile * TM, TM);
   TcCtx c = tc_begin<L>(sm_raw, tw);
   tc_load_w<L>(c, tw.layer[0].env[0]);
   const Geom g = tc_geom<L>(a, w, c, gi);
