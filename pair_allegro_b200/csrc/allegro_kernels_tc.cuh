@@ -60,7 +60,9 @@ template <int L> struct DimsTC {
 template <int L> struct SmemTC {
   using D = DimsTC<L>;
   static constexpr int TM = 128;
-  static constexpr int OPF = TM * 64;                  // operand capacity: K <= 64
+  // the A operand lives in tensor memory; [oOPH, oWBH) is a 64-KB scratch region (env-weight / ds / dG staging,
+  // reduction scratch) whose two halves double as the hi / lo image of weight buffer 2 (tc_load_w2)
+  static constexpr int OPF = TM * 64;
   static constexpr int WBF = 4096;                     // weight block capacity: N*K <= 64*64
   static constexpr int oOPH = 0;
   static constexpr int oOPL = oOPH + OPF;
@@ -80,7 +82,7 @@ template <int L> struct SmemTC {
   static constexpr int oBAR = oSEG + TM + 16;          // 3 mbarriers + tmem pointer (8 floats: mbar, wbar, tmem ptr, wbar2)
   static constexpr int TOTAL = oBAR + 8;
   static constexpr size_t BYTES = (size_t)TOTAL * sizeof(float) + 1024;   // + alignment slack
-  // buffers that alias the operand / weight regions once those are dead
+  // buffers inside the scratch / weight regions (live ranges never overlap a weight block that is still in use)
   static constexpr int oWS = oOPL;                                 // env weights of one block, edge-major [128][65]
   static constexpr int oDS = (L == 1) ? oWBH : oOPL;               // ds rows [q*U+u][128] for the tensor-product backward
   static constexpr int oDG = oOPH;                                 // dG staging [128][DGS]
@@ -101,7 +103,6 @@ struct RowSrc {
   __device__ __forceinline__ const float* row(int centre, int /*F*/) const { return base + (size_t)(centre - c_origin) * stride; }
 };
 
-constexpr uint32_t TC_SCR_COL = 128;    // first accumulator block (TC_ACC, see tc_mma)
 
 struct TcCtx {
   float* sm;
@@ -270,16 +271,6 @@ template <int L> __device__ __forceinline__ void tc_mma_pair(TcCtx& c, int K, in
 // this thread's row m, 16 columns starting at absolute TMEM column col
 __device__ __forceinline__ void tc_ld16(const TcCtx& c, uint32_t col, float* v) {
   umma::tmem_ld16(c.tmem + ((uint32_t)(c.q * 32) << 16) + col, v);
-}
-// two 16-column loads from different TMEM regions in flight together
-__device__ __forceinline__ void tc_ld16x2(const TcCtx& c, uint32_t colA, float* a, uint32_t colB, float* b) {
-  uint32_t ra[16], rb[16];
-  const uint32_t base = c.tmem + ((uint32_t)(c.q * 32) << 16);
-  umma::tmem_ld16_nowait(base + colA, ra);
-  umma::tmem_ld16_nowait(base + colB, rb);
-  umma::tmem_ld_wait();
-#pragma unroll
-  for (int i = 0; i < 16; ++i) { a[i] = __uint_as_float(ra[i]); b[i] = __uint_as_float(rb[i]); }
 }
 // write 4 consecutive k (k4 % 4 == 0) of row m into the A operand in tensor memory (hi [+ lo])
 template <int L> __device__ __forceinline__ void op_put4(const TcCtx& c, int k4, float a, float b, float d, float e) {
@@ -839,8 +830,8 @@ __device__ __forceinline__ void tc_mlp_bwd_hidden_st(TcCtx& c, const TcMat& w1_b
 }
 
 // dz1 in operand, m0_bx requested: dX(global) += dz1 W0x^T ; ds = dz1 W0s^T -> DS_s.
-// ds of all blocks is held in registers until the last MMA has read the operand / weight regions
-// that DS_s aliases.
+// (l_max = 2: the first ds block is held in registers until the MMA that still reads the weight region DS_s aliases
+// has completed.)
 template <int L>
 __device__ __forceinline__ void tc_din(TcCtx& c, const TcLayerW& tl, float* dXg) {
   using D = DimsTC<L>; using SM = SmemTC<L>; constexpr int TM = 128;
