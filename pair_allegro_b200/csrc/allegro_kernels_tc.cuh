@@ -1235,6 +1235,7 @@ __global__ void __launch_bounds__(NT, 2) k_bk_tc(const __grid_constant__ ChunkAr
   tc_prefetch(a.dX + (size_t)tile * S * TM, S * TM);
   tc_prefetch(a.ZD[k + 1] + (size_t)tile * ZD_ROWS * TM, ZD_ROWS * TM);
   tc_prefetch(a.dY + (size_t)tile * D::NSH * TM, D::NSH * TM);
+  tc_prefetch(a.du + (size_t)tile * TM, TM);
   TcCtx c = tc_begin<L>(sm_raw, tw);
   const LayerW& lw = w.layer[k];
   const TcLayerW& tl = tw.layer[k];
