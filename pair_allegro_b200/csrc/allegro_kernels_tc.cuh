@@ -49,7 +49,7 @@ template <int L> struct DimsTC {
   static constexpr int CPT = U / CPH;      // 16
   static constexpr int NB = (NL + 1) / 2;               // 64-wide blocks of the l-indexed width
   static constexpr int WS = 64 + 1;                     // W_s stride (one block at a time)
-  static constexpr int CHU = (L == 1) ? 16 : 4;         // channels per dGamma staging pass
+  static constexpr int CHU = (L == 1) ? 16 : 8;         // channels per dGamma staging pass
   static constexpr int FC = NSH * CHU;
   static constexpr int DGS = FC + 1;
   static constexpr int TB = (L == 1) ? 4 : 1;           // tensor-product channels whose loads are batched
@@ -84,7 +84,8 @@ template <int L> struct SmemTC {
   static constexpr size_t BYTES = (size_t)TOTAL * sizeof(float) + 1024;   // + alignment slack
   // buffers inside the scratch / weight regions (live ranges never overlap a weight block that is still in use)
   static constexpr int oWS = oOPL;                                 // env weights of one block, edge-major [128][65]
-  static constexpr int oDS = (L == 1) ? oWBH : oOPL;               // ds rows [q*U+u][128] for the tensor-product backward
+  static constexpr int oDS = (L == 1) ? oWBH : ((D::DGS * TM + 127) / 128) * 128;   // ds rows [q*U+u][128] for the tensor-product backward
+                                                                   // (l_max = 2: right behind the dG staging)
   static constexpr int oDG = oOPH;                                 // dG staging [128][DGS]
   static_assert(L == 1 || L == 2, "tensor-core pipeline: shared-memory plan covers l_max = 1, 2");
   static_assert(D::WS * TM <= OPF + 2 * WBF, "W_s must fit OPL + weight region");
