@@ -4,16 +4,15 @@ import os, sys
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-from oracle import allegro_torch as AT
 from lmpshim import harness as H
-from pair_allegro_b200.export import export_alg
+from pair_allegro_b200 import modelgen
 from pair_allegro_b200.pair import PairAllegroB200
 pos, types, cell = H.fcc_box(24)
 atoms = H.make_single_rank(types, pos, cell, [True] * 3, 6.0)
 lst = H.build_full_list(atoms, 6.0)
-cfg = AT.default_config(type_names=["Ag"], r_max=5.0, l_max=1, num_layers=2, avg_num_neighbors=28.0, seed=2)
+cfg = modelgen.default_config(type_names=["Ag"], r_max=5.0, l_max=1, num_layers=2, avg_num_neighbors=28.0, seed=2)
 os.makedirs("/tmp/qb", exist_ok=True)
-AT.save_torchscript(cfg, "/tmp/qb/m.nequip.pth"); export_alg("/tmp/qb/m.nequip.pth", "/tmp/qb/m.alg")
+modelgen.random_alg(cfg, "/tmp/qb/m.alg")
 pair = PairAllegroB200(device=0, debug_mode=False)
 pair.coeff(["*", "*", "/tmp/qb/m.alg", "Ag"], 1)
 pair.handle.set_option("debug", "1")
