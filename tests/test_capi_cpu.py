@@ -118,3 +118,16 @@ def test_cpp_pair_style_error_paths_cpu(ensure_built):
         with pytest.raises(driver.ShimError, match="no CPU fallback"):
             lmp.pair_coeff(["*", "*", alg_path("Cu_r5"), "Cu"])
     assert lmp.flags()["restartinfo"] == 0 and lmp.flags()["manybody_flag"] == 1
+
+
+def test_header_documents_every_option_key():
+    """every key alg_set_option accepts (csrc/alg_api.cu) is documented in include/allegro_b200.h"""
+    import re
+    src = open(os.path.join(ROOT, "pair_allegro_b200", "csrc", "alg_api.cu")).read()
+    body = src[src.index('extern "C" int alg_set_option'):]
+    body = body[:body.index("\n}\n")]
+    keys = set(re.findall(r'k == "([a-z_]+)"', body))
+    hdr = open(os.path.join(ROOT, "include", "allegro_b200.h")).read()
+    assert keys >= {"filter", "chunk_edges", "gemm", "precision", "neigh_ago"}
+    missing = [k for k in keys if '"%s"' % k not in hdr]
+    assert not missing, missing
