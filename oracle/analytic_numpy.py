@@ -122,9 +122,16 @@ class AnalyticAllegro:
                 g = g * ds[i - 1]
         return g
 
-    def run(self, rvec, center, zi, zj, n_centers):
+    def run(self, rvec, center, zi, zj, n_centers, store_quant=None):
         """rvec [E,3] (x_j - x_i), center [E] centre slots, zi/zj model types.
-        returns dict with energies, per-edge gradient g_e = dE_tot/drvec and intermediates."""
+        returns dict with energies, per-edge gradient g_e = dE_tot/drvec and intermediates.
+        store_quant (study hook, tests/study_bf16_storage.py): dict {"zd": f, "v": f, "dv": f} of functions
+        applied to the arrays the CUDA pipeline keeps in HBM between kernels -- the activation record
+        (act'(z1), act'(z2), m), V^k (k >= 1) and dV^k -- to predict what a narrower storage format costs."""
+        sq = store_quant or {}
+        qzd = sq.get("zd", lambda t: t)
+        qv = sq.get("v", lambda t: t)
+        qdv = sq.get("dv", lambda t: t)
         w, L, U, S, nsh = self.w, self.L, self.U, self.S, self.nsh
         E = len(rvec)
         I = {}
@@ -149,7 +156,8 @@ class AnalyticAllegro:
         # ---------------- F0
         m0, d2b = self.mlp_fwd("twobody", in2b)
         xs = [m0 * u[:, None]]
-        ms = [m0]
+        d2b = [qzd(t) for t in d2b]
+        ms = [qzd(m0)]
         w0 = (xs[0] @ w["embed_linear"]).reshape(E, L + 1, U)
         V = w0[:, self.lsel, :] * Y[:, :, None]
         Vs = [V]
@@ -166,12 +174,12 @@ class AnalyticAllegro:
             Vout, s = tp_fwd(K, Vs[k], Gam[center], w["layer%d.omega" % k], not last)
             ss.append(s)
             mk, dk = self.mlp_fwd("layer%d.mlp" % k, np.concatenate([xs[k], s.reshape(E, -1)], 1))
-            mlpd.append(dk); ms.append(mk)
+            mlpd.append([qzd(t) for t in dk]); ms.append(qzd(mk))
             al = float(w["layer%d.alpha" % k][0])
             a_, b_ = 1 / math.sqrt(1 + al * al), al / math.sqrt(1 + al * al)
             xs.append(a_ * xs[k] + b_ * mk * u[:, None])
             if not last:
-                Vs.append(Vout)
+                Vs.append(qv(Vout))
         z = xs[-1] @ w["readout.w0"]
         r1, dr1 = silu(z)
         e_edge = (r1 @ w["readout.w1"])[:, 0]
@@ -205,7 +213,7 @@ class AnalyticAllegro:
             dwk = np.zeros((E, L + 1, U))
             np.add.at(dwk, (slice(None), self.lsel), dwy * Y[:, :, None])
             dx = dx + dwk.reshape(E, -1) @ w["layer%d.env_linear" % k].T
-            dV = dVin
+            dV = qdv(dVin) if k > 0 else dVin
             dXs[k] = dx.copy()
         # V0 = w0 (x) Y
         dY += (dV * w0[:, self.lsel, :]).sum(2)
@@ -213,7 +221,7 @@ class AnalyticAllegro:
         np.add.at(dw0, (slice(None), self.lsel), dV * Y[:, :, None])
         dx = dx + dw0.reshape(E, -1) @ w["embed_linear"].T
         # x0 = m0 * u ; two-body MLP
-        du += (dx * m0).sum(1)
+        du += (dx * ms[0]).sum(1)
         din = self.mlp_bwd("twobody", d2b, dx * u[:, None])
         dbu = din[:, 2 * T:]
         dr = (dbu * (dbes * u[:, None] + bes * du_dr[:, None])).sum(1) + du * du_dr
