@@ -161,13 +161,61 @@ class ClockSampler:
         return out
 
 
+def _flatten(d, prefix=""):
+    out = {}
+    if isinstance(d, dict):
+        for k, v in d.items():
+            out.update(_flatten(v, prefix + "/" + str(k).lower()))
+    elif isinstance(d, (list, tuple)):
+        for i, v in enumerate(d):
+            out.update(_flatten(v, prefix + "/" + str(i)))
+    elif isinstance(d, (int, float)) and not isinstance(d, bool):
+        out[prefix] = float(d)
+    return out
+
+
+def parse_measured_peaks(d):
+    """MEASURED_PEAKS.json is driver-written and its exact schema is not part of this repo: accept any nesting
+    whose key paths name the quantity (bf16 / tflop ... hbm / gb / bandwidth / copy) and, when present,
+    the flavour (sustained vs burst/peak).  Returns None when nothing usable is found."""
+    flat = _flatten(d)
+    tf = {k: v for k, v in flat.items() if any(t in k for t in ("bf16", "tflop", "tf_s", "tfs", "tensor")) and "hbm" not in k}
+    bw = {k: v for k, v in flat.items() if any(t in k for t in ("hbm", "gbs", "gb_s", "gbps", "bandwidth", "copy", "tbs", "tb_s"))}
+
+    def norm_tf(v):
+        return v / 1e3 if v > 2e4 else v            # GFLOP/s -> TFLOP/s
+
+    def norm_bw(v):
+        return v * 1e3 if v < 50 else v             # TB/s -> GB/s
+
+    def pick(cands, want, avoid):
+        for k, v in cands.items():
+            if any(w in k for w in want):
+                return v
+        for k, v in cands.items():
+            if not any(w in k for w in avoid):
+                return v
+        return next(iter(cands.values())) if cands else None
+
+    sus = pick(tf, ("sustain", "steady", "long"), ("burst", "peak"))
+    bur = pick(tf, ("burst", "peak", "alone"), ("sustain", "steady", "long"))
+    hbm = pick(bw, ("sustain", "steady", "long"), ("burst", "peak")) if bw else None
+    if sus is None and bur is None:
+        return None
+    sus = norm_tf(sus if sus is not None else bur)
+    bur = norm_tf(bur if bur is not None else sus)
+    if not (100.0 < sus < 5000.0):
+        return None
+    return dict(hbm_gbs=norm_bw(hbm) if hbm else 6650.0, bf16=bur, bf16_sustained=sus, source="measured")
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
         try:
-            d = json.load(open(p))
-            return dict(hbm_gbs=float(d.get("hbm_gbs", 6650.0)), bf16=float(d.get("bf16_tflops", 1590.0)),
-                        bf16_sustained=float(d.get("bf16_tflops_sustained", d.get("bf16_tflops", 1590.0))), source="measured")
+            r = parse_measured_peaks(json.load(open(p)))
+            if r:
+                return r
         except Exception:
             pass
     return dict(hbm_gbs=6650.0, bf16=1590.0, bf16_sustained=1400.0, source="fallback")

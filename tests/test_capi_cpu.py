@@ -131,3 +131,18 @@ def test_header_documents_every_option_key():
     assert keys >= {"filter", "chunk_edges", "gemm", "precision", "neigh_ago"}
     missing = [k for k in keys if '"%s"' % k not in hdr]
     assert not missing, missing
+
+
+def test_bench_measured_peaks_parser():
+    """bench.py accepts the driver-written MEASURED_PEAKS.json in any plausible nesting / unit"""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    b = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(b)
+    r = b.parse_measured_peaks({"hbm_gbs": 6551, "bf16_tflops": 1648, "bf16_tflops_sustained": 1384})
+    assert r["bf16_sustained"] == 1384 and r["bf16"] == 1648 and r["hbm_gbs"] == 6551 and r["source"] == "measured"
+    r = b.parse_measured_peaks({"hbm": {"copy_GBs_sustained": 6551.0}, "bf16": {"dense_TFLOPs_burst": 1648.2, "dense_TFLOPs_sustained": 1384.1}})
+    assert abs(r["bf16_sustained"] - 1384.1) < 1e-9 and abs(r["bf16"] - 1648.2) < 1e-9
+    r = b.parse_measured_peaks({"peaks": {"HBM_TB_s": 6.55, "bf16_dense_gflops": 1650000.0}})
+    assert abs(r["hbm_gbs"] - 6550.0) < 1e-6 and abs(r["bf16_sustained"] - 1650.0) < 1e-6
+    assert b.parse_measured_peaks({"foo": 1}) is None
