@@ -152,3 +152,37 @@ def test_brick_decomposition_covers_box():
         own_pos = np.stack([parts[r].x[i] for r, i in zip(p.owner_rank[gh], p.owner_index[gh])])
         d = p.x[gh] - own_pos
         assert np.abs(d - np.round(d / L) * L).max() < 1e-9
+
+
+@pytest.mark.parametrize("seed,box,rcut", [(0, (7.0, 8.0, 9.0), 5.0), (1, (4.0, 11.0, 6.0), 6.5), (2, (3.2, 3.4, 3.1), 7.0)])
+def test_harness_list_matches_brute_force(seed, box, rcut):
+    """the reference's "inputs" check (tests/test_python_repro_allegro.py:219-286) for the harness itself:
+    the (tag_i, tag_j, r_ij) multiset of the full neighbour list within the cutoff equals an independent
+    brute-force enumeration over periodic images (boxes smaller than the cutoff included)"""
+    rng = np.random.default_rng(seed)
+    n = 14
+    cell = np.diag(box)
+    pos = rng.random((n, 3)) * np.array(box)
+    types = np.ones(n, dtype=np.int32)
+    atoms = H.make_single_rank(types, pos, cell, [True] * 3, rcut)
+    lst = H.build_full_list(atoms, rcut)
+    got = []
+    for i in range(atoms.nlocal):
+        for j in lst.firstneigh(i):
+            d = np.linalg.norm(atoms.x[j] - atoms.x[i])
+            if d <= rcut:
+                got.append((int(atoms.tag[i]), int(atoms.tag[j]), round(float(d), 9)))
+    ref = []
+    wrapped = atoms.x[:atoms.nlocal]
+    kmax = [int(np.ceil(rcut / b)) + 1 for b in box]
+    for i in range(n):
+        for j in range(n):
+            for a in range(-kmax[0], kmax[0] + 1):
+                for b in range(-kmax[1], kmax[1] + 1):
+                    for c in range(-kmax[2], kmax[2] + 1):
+                        if i == j and a == b == c == 0:
+                            continue
+                        d = np.linalg.norm(wrapped[j] + np.array([a, b, c]) * np.array(box) - wrapped[i])
+                        if d <= rcut:
+                            ref.append((int(atoms.tag[i]), int(atoms.tag[j]), round(float(d), 9)))
+    assert len(got) == len(ref) and sorted(got) == sorted(ref)
