@@ -76,7 +76,21 @@ ALG_API int alg_set_type_map(alg_handle* h, int ntypes, const int* lammps_type_t
 /* Options (string key/value, all optional):
  *   "filter"       "le" (default; host path rsq <= cut^2, pair_nequip_allegro.cpp:507,599)
  *                  | "lt" (Kokkos path rsq < cut^2, pair_nequip_allegro_kokkos.cpp:189)
- *   "chunk_edges"  edges processed per pipeline pass (activation buffers are sized by this)
+ *   "pipeline"     "auto" (default) | "fused" | "tiled".  fused = ONE persistent kernel over centre-aligned tiles
+ *                  (every atom's edges inside one 128-edge tile, all phases of a tile in one CTA, inter-phase state in
+ *                  CTA-private L2-resident scratch, no host synchronisation); needs <= 128 neighbours inside the cutoff
+ *                  per atom.  tiled = the chunked edge-tile pipeline (any neighbour count; one host synchronisation per
+ *                  step on the CSR row pointer).  auto = fused, and tiled from the first step on that meets an atom
+ *                  with more than 128 neighbours (that step is repeated transparently), or when debug=1.
+ *   "max_neighbors" alg_compute_device only: extent(1) of the caller's 2-D neighbour view.  Sizes the edge arrays to
+ *                  nlocal*max_neighbors so that a fully asynchronous step can never overflow them; without it they
+ *                  are sized from the previous step's edge count (+12.5 %), like the reference's 1.05 padding
+ *                  (pair_nequip_allegro_kokkos.cpp:218-229)
+ *   "host_register" "1" (default) | "0": alg_compute_host pins the caller's x / f / type arrays with cudaHostRegister
+ *                  (cached per array address and size; LAMMPS keeps atom->x / f at the same address until they grow)
+ *                  so that the per-step copies are asynchronous DMA.  Switch off when the caller frees and
+ *                  re-allocates these arrays between calls.
+ *   "chunk_edges"  tiled pipeline: edges processed per pipeline pass (activation buffers are sized by this)
  *   "keep_edges"   "1": materialise the int64 [2,E] edge_index for alg_get_edges
  *   "debug"        "1": keep per-edge gradients / intermediates for alg_get_output
  *   "profile"      "1": time every pipeline kernel with CUDA events (alg_get_stats)
@@ -115,7 +129,12 @@ ALG_API int alg_compute_host(alg_handle* h, int nlocal, int nghost, const double
  * d_eatom (may be NULL) assigned for locals (:311-313).  `eng` and `virial6` are HOST
  * pointers written before return (the call synchronises the stream once for them, like
  * the reference's parallel_reduce result :318 and virial .cpu() :329); pass NULL for both
- * to keep the call fully asynchronous.  `stream` is a cudaStream_t (0 = legacy default). */
+ * to keep the call fully asynchronous: nothing in the call then waits for the device (the tile plan of the fused
+ * pipeline is built on the device; the reference blocks on its edge count every step,
+ * pair_nequip_allegro_kokkos.cpp:203-206).  Such a step is verified lazily: if it met an atom with more than 128
+ * neighbours, or overflowed edge arrays sized without max_neighbors, it wrote no forces and the NEXT call on the handle
+ * returns ALG_ESTATE (then switches to the tiled pipeline / larger arrays).  Calls that pass `eng` or `virial6` are
+ * verified before they return and such steps are repeated transparently.  `stream` is a cudaStream_t (0 = legacy default). */
 ALG_API int alg_compute_device(alg_handle* h, int nlocal, int nghost, const double* d_x, const int* d_type,
                        const int* d_ilist, const int* d_numneigh, const int* d_neighbors,
                        int64_t stride_i, int64_t stride_jj,
@@ -143,7 +162,8 @@ ALG_API int alg_get_timings(alg_handle* h, double* ms3);
 
 /* Counters of the last compute (doubles): what = "step" -> [own kernel launches, edges, chunks,
  * tiles]; with option profile=1 also "kernel_ms" / "kernel_launches" -> per kernel family
- * [F0, FK, T, BK, B0, fixup] summed CUDA-event durations (ms) and launch counts. */
+ * [F0, FK, T, BK, B0, fixup, fused] summed CUDA-event durations (ms) and launch counts; "pipeline" -> [1 if the
+ * last step ran the fused kernel, CTAs in the fused grid, 1 once the tiled fallback became sticky]. */
 ALG_API int alg_get_stats(alg_handle* h, const char* what, double* out, int n);
 
 /* Ghost halo helpers for spatial-domain multi-GPU runs (replace LAMMPS

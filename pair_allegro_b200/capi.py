@@ -192,7 +192,7 @@ class Handle:
         return t
 
 
-KERNEL_FAMILIES = ["F0", "FK", "T", "BK", "B0", "fixup"]
+KERNEL_FAMILIES = ["F0", "FK", "T", "BK", "B0", "fixup", "fused"]
 
 
 def version():

@@ -97,6 +97,25 @@ struct alg_handle {
   const Pipeline* pipe_ffma = nullptr;
   const Pipeline* pipe_tc = nullptr;
   bool use_tc = false;
+  // fused persistent pipeline (centre-aligned tiles, allegro_kernels_tc.cuh: k_fused_tc)
+  int pipeline_mode = 0;                   // option pipeline: 0 = auto, 1 = fused, 2 = tiled
+  bool force_tiled = false;                // sticky: a centre with more than 128 edges was seen -> chunked edge-tile pipeline
+  int fused_grid = 0;                      // resident CTAs of the fused kernel on this device
+  long edge_cap_hint = 0;                  // upper bound on the edge count known to the caller path (0 = unknown)
+  long max_neighbors = 0;                  // option max_neighbors: extent(1) of the caller's 2-D neighbour view
+  long last_E_known = -1; int last_E_nlocal = -1;
+  DevBuf d_blk, d_blk_base, d_tile_c0, d_info;
+  PinBuf h_info;
+  cudaEvent_t ev_info = nullptr;
+  bool info_pending = false;               // an asynchronous fused step has not been verified yet
+  bool last_fused = false;
+  std::string deferred_err;                // failure of an asynchronous step, reported by the next call
+  std::pair<const void*, size_t> reg[3] = {{nullptr, 0}, {nullptr, 0}, {nullptr, 0}};   // caller arrays (x, f, type) pinned with cudaHostRegister
+  bool host_register = true;               // option host_register
+  DevBuf d_f_stage;
+  PinBuf h_eatom;
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t ev_copy = nullptr, ev_order = nullptr;
   int neigh_ago = 0;                       // option neigh_ago: steps since the caller's last neighbour-list rebuild
   int list_nlocal = -1, list_ntot = -1, list_reused = 0;
   long long list_tot = -1;                 // device-resident copy of the host neighbour list (alg_compute_host)
@@ -110,7 +129,7 @@ struct alg_handle {
   // per-step scratch
   DevBuf d_x, d_type, d_ilist, d_numneigh, d_cand, d_first, d_cnt, d_rowptr, d_scan_tmp;
   DevBuf d_mtype, d_edge_j, d_edge_c, d_rvec, d_esum, d_facc, d_vacc, d_forces, d_eall, d_red, d_edge_index, d_edge_energy, d_edge_grad, d_eatom_out;
-  DevBuf d_tstamp, c_ZD[4], c_X[3], c_W0, c_V[3], c_dX, c_dV[2], c_dY, c_du, c_gamma[3], c_dgamma[3], c_carry, c_ecarry;
+  DevBuf c_ZD[4], c_X[3], c_W0, c_V[3], c_dX, c_dV[2], c_dY, c_du, c_gamma[3], c_dgamma[3], c_carry, c_ecarry;
   PinBuf h_stage, h_rowptr, h_out, h_first;
   // results
   int last_nlocal = 0, last_ntot = 0;
@@ -119,8 +138,8 @@ struct alg_handle {
   std::map<std::string, std::vector<double>> outputs;
   double timings[3] = {0, 0, 0};
   Prof prof;
-  double kernel_ms[KID_COUNT] = {0, 0, 0, 0, 0, 0};
-  double kernel_n[KID_COUNT] = {0, 0, 0, 0, 0, 0};
+  double kernel_ms[KID_COUNT] = {0, 0, 0, 0, 0, 0, 0};
+  double kernel_n[KID_COUNT] = {0, 0, 0, 0, 0, 0, 0};
   double step_stats[4] = {0, 0, 0, 0};   // launches of own kernels, edges, chunks, tiles
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   // debug bookkeeping of the last single-chunk run
@@ -215,7 +234,7 @@ template <bool FILL>
 __global__ void k_edges(int nlocal, const double* __restrict__ x, const int* __restrict__ type, const int* __restrict__ ilist,
                         NeighAcc acc, const double* __restrict__ cutsq, int ntypes, int filter_le,
                         int* __restrict__ cnt_out, const int* __restrict__ rowptr, const int* __restrict__ tmap,
-                        int* __restrict__ edge_j, int* __restrict__ edge_c, float4* __restrict__ rvec) {
+                        int* __restrict__ edge_j, int* __restrict__ edge_c, float4* __restrict__ rvec, long cap) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= nlocal) return;
@@ -242,6 +261,7 @@ __global__ void k_edges(int nlocal, const double* __restrict__ x, const int* __r
     if (FILL) {
       if (keep) {
         const int pos = base + __popc(m & ((1u << lane) - 1u));
+        if (pos >= cap) continue;                       // edge arrays too small (flagged by k_plan; the host retries)
         edge_j[pos] = j;
         edge_c[pos] = ii;
         const int zj = tmap[type[j] - 1];
@@ -255,12 +275,56 @@ __global__ void k_edges(int nlocal, const double* __restrict__ x, const int* __r
   if (!FILL && lane == 0) cnt_out[ii] = total;
 }
 
-__global__ void k_edge_index(long E, const int* __restrict__ edge_j, const int* __restrict__ edge_c, const int* __restrict__ ilist,
-                             long long* __restrict__ out) {
-  const long e = blockIdx.x * (long)blockDim.x + threadIdx.x;
-  if (e >= E) return;
-  out[e] = ilist[edge_c[e]];
-  out[E + e] = edge_j[e];
+__global__ void k_edge_index(const int* __restrict__ rowptr, int nlocal, long cap, const int* __restrict__ edge_j, const int* __restrict__ edge_c,
+                             const int* __restrict__ ilist, long long* __restrict__ out) {
+  const long E = rowptr[nlocal];
+  if (E > cap) return;
+  for (long e = blockIdx.x * (long)blockDim.x + threadIdx.x; e < E; e += (long)gridDim.x * blockDim.x) {
+    out[e] = ilist[edge_c[e]];
+    out[E + e] = edge_j[e];
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// tile plan of the fused kernel: centre-aligned tiles of <= 128 edges and <= 128 centres.  Centres are split into
+// blocks of PLAN_CB; one thread packs its block greedily (tiles never span blocks), pass 0 counts the tiles of a
+// block, pass 1 (after an exclusive scan) writes the first centre of every tile.
+// info: [0] ntiles, [1] max degree, [2] E, [3] 1 if E exceeds the capacity of the edge arrays
+// ------------------------------------------------------------------------------------------
+constexpr int PLAN_CB = 256;
+constexpr int PLAN_ROWS = 128;
+template <bool FILL>
+__global__ void k_plan(int nlocal, const int* __restrict__ rowptr, int* __restrict__ blk_tiles, const int* __restrict__ blk_base,
+                       int* __restrict__ tile_c0, int* __restrict__ info, long cap) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  const int nblk = (nlocal + PLAN_CB - 1) / PLAN_CB;
+  if (b >= nblk) return;
+  const int cb = b * PLAN_CB, ce = min(nlocal, cb + PLAN_CB);
+  int rows = 0, span = 0, nt = 0, maxdeg = 0;
+  int base = FILL ? blk_base[b] : 0;
+  int prev = rowptr[cb];
+  for (int c = cb; c < ce; ++c) {
+    const int nxt = rowptr[c + 1];
+    const int deg = nxt - prev;
+    prev = nxt;
+    maxdeg = max(maxdeg, deg);
+    if (span > 0 && (rows + deg > PLAN_ROWS || span == PLAN_ROWS)) { ++nt; rows = 0; span = 0; }
+    if (FILL && span == 0) tile_c0[base + nt] = c;
+    rows += deg; ++span;
+  }
+  if (span > 0) ++nt;
+  if (!FILL) {
+    blk_tiles[b] = nt;
+    if (b == 0) blk_tiles[nblk] = 0;
+    atomicMax(info + 1, maxdeg);
+  } else if (b == nblk - 1) {
+    const int ntiles = base + nt;
+    tile_c0[ntiles] = nlocal;
+    info[0] = ntiles;
+    const int E = rowptr[nlocal];
+    info[2] = E;
+    info[3] = E > cap ? 1 : 0;
+  }
 }
 
 __global__ void k_mtype(int ntot, const int* __restrict__ type, const int* __restrict__ tmap, int* __restrict__ mtype) {
@@ -269,9 +333,12 @@ __global__ void k_mtype(int ntot, const int* __restrict__ type, const int* __res
 }
 
 // finalize: fixed-point accumulators -> model forces (double), optionally f += ; per-atom energies
-__global__ void k_forces(int ntot, const unsigned long long* __restrict__ facc, double* __restrict__ forces, double* __restrict__ f_inout) {
+// info != nullptr (fused pipeline): a step the fused kernel refused (info[1] > 128 or info[3]) must not touch f; the host repeats it
+__global__ void k_forces(int ntot, const unsigned long long* __restrict__ facc, double* __restrict__ forces, double* __restrict__ f_inout,
+                         const int* __restrict__ info) {
   const long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
   if (i >= 3L * ntot) return;
+  if (info && (info[1] > PLAN_ROWS || info[3] != 0)) return;
   const double v = (double)(long long)facc[i] * FIX_INV;
   forces[i] = v;
   if (f_inout) f_inout[i] += v;
@@ -512,6 +579,7 @@ static int setup_model(alg_handle* h) {
     CK(h->pipe_tc->init());
     // default: tensor-core pipeline in strict (3xTF32) mode whenever the model is supported
     h->use_tc = true; h->pipe = h->pipe_tc; h->pinfo = h->pipe->info(h->nl);
+    h->fused_grid = h->pipe_tc->fused_grid ? h->pipe_tc->fused_grid(h->nl) : 0;
   }
   h->tensors.clear();
   return ALG_OK;
@@ -543,6 +611,10 @@ extern "C" int alg_create(const char* weight_path, int cuda_device, alg_handle**
     g_create_error = std::string("CUDA error: ") + cudaGetErrorString(e); delete h; return ALG_ECUDA;
   }
   for (int i = 0; i < 4; ++i) cudaEventCreate(&h->ev[i]);
+  cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking);
+  cudaEventCreateWithFlags(&h->ev_info, cudaEventDisableTiming);
+  cudaEventCreateWithFlags(&h->ev_copy, cudaEventDisableTiming);
+  cudaEventCreateWithFlags(&h->ev_order, cudaEventDisableTiming);
   rc = setup_model(h);
   if (rc != ALG_OK) { g_create_error = h->err; alg_destroy(h); return rc; }
   *out = h;
@@ -553,10 +625,15 @@ extern "C" void alg_destroy(alg_handle* h) {
   if (!h) return;
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
+  if (h->copy_stream) { cudaStreamSynchronize(h->copy_stream); cudaStreamDestroy(h->copy_stream); }
+  for (auto& r : h->reg) if (r.first) { cudaHostUnregister(const_cast<void*>(r.first)); cudaGetLastError(); }
+  for (cudaEvent_t e : {h->ev_info, h->ev_copy, h->ev_order}) if (e) cudaEventDestroy(e);
+  h->d_blk.release(); h->d_blk_base.release(); h->d_tile_c0.release(); h->d_info.release(); h->d_f_stage.release();
+  h->h_info.release(); h->h_eatom.release();
   DevBuf* bufs[] = {&h->weights, &h->d_tmap, &h->d_cutsq, &h->d_scale, &h->d_shift, &h->d_x, &h->d_type, &h->d_ilist, &h->d_numneigh,
                     &h->d_cand, &h->d_first, &h->d_cnt, &h->d_rowptr, &h->d_scan_tmp, &h->d_mtype, &h->d_edge_j, &h->d_edge_c, &h->d_rvec,
                     &h->d_esum, &h->d_facc, &h->d_vacc, &h->d_forces, &h->d_eall, &h->d_red, &h->d_edge_index, &h->d_edge_energy,
-                    &h->d_edge_grad, &h->d_eatom_out, &h->tc_weights, &h->d_tstamp, &h->c_ZD[0], &h->c_ZD[1], &h->c_ZD[2], &h->c_ZD[3], &h->c_W0, &h->c_dX, &h->c_dY, &h->c_du, &h->c_carry, &h->c_ecarry,
+                    &h->d_edge_grad, &h->d_eatom_out, &h->tc_weights, &h->c_ZD[0], &h->c_ZD[1], &h->c_ZD[2], &h->c_ZD[3], &h->c_W0, &h->c_dX, &h->c_dY, &h->c_du, &h->c_carry, &h->c_ecarry,
                     &h->c_X[0], &h->c_X[1], &h->c_X[2], &h->c_V[0], &h->c_V[1], &h->c_V[2], &h->c_dV[0], &h->c_dV[1],
                     &h->c_gamma[0], &h->c_gamma[1], &h->c_gamma[2], &h->c_dgamma[0], &h->c_dgamma[1], &h->c_dgamma[2]};
   for (DevBuf* b : bufs) b->release();
@@ -613,6 +690,18 @@ extern "C" int alg_set_option(alg_handle* h, const char* key, const char* value)
       h->use_tc = true; h->pipe = h->pipe_tc;
     } else return fail(h, ALG_EINVAL, "gemm must be ffma or tc");
     h->pinfo = h->pipe->info(h->nl);
+  } else if (k == "pipeline") {
+    if (v == "auto") h->pipeline_mode = 0;
+    else if (v == "fused") {
+      if (!h->pipe_tc || !h->pipe_tc->run_fused || h->fused_grid <= 0) return fail(h, ALG_EINVAL, "pipeline=fused needs the tensor-core pipeline of this model");
+      h->pipeline_mode = 1;
+    } else if (v == "tiled") h->pipeline_mode = 2;
+    else return fail(h, ALG_EINVAL, "pipeline must be auto, fused or tiled");
+  } else if (k == "max_neighbors") {
+    h->max_neighbors = atol(v.c_str());
+    if (h->max_neighbors < 0) return fail(h, ALG_EINVAL, "max_neighbors must be >= 0");
+  } else if (k == "host_register") {
+    h->host_register = v != "0";
   } else if (k == "neigh_ago") {
     h->neigh_ago = atoi(v.c_str());
     if (h->neigh_ago < 0) return fail(h, ALG_EINVAL, "neigh_ago must be >= 0");
@@ -656,59 +745,76 @@ static void detile(const std::vector<float>& raw, int ntiles, int rows, int TM, 
   }
 }
 
-// d_x/d_type/d_ilist are device pointers; acc describes the device-resident neighbour list.
-static int run_step(alg_handle* h, int nlocal, int nghost, const double* d_x, const int* d_type, const int* d_ilist, NeighAcc acc,
-                    int eflag_atom, int vflag_global, double* d_f_inout, double* d_eatom, double* eng, double* virial6) {
+// everything one force evaluation needs, on the device (d_* = device pointers); acc describes the device-resident
+// neighbour list.  Host-API extras: the caller's f is read-modified-written through d_f_inout, then copied back.
+struct StepIO {
+  int nlocal, nghost;
+  const double* d_x; const int* d_type; const int* d_ilist;
+  NeighAcc acc;
+  int eflag_atom, vflag_global;
+  double* d_f_inout; double* d_eatom;
+  long cap_hint;                 // upper bound on the number of edges (0 = unknown)
+  cudaEvent_t wait_f;            // host API: d_f_inout is being uploaded on another stream; wait for this before the store
+  double* h_f; double* h_eatom_stage;   // host API: copy d_f_inout / d_eatom back (async, before the final synchronisation)
+};
+
+static void fill_args(alg_handle* h, const StepIO& io, ChunkArgs& a) {
+  a = ChunkArgs{};
+  a.rvec = h->d_rvec.as<float4>(); a.edge_j = h->d_edge_j.as<int>(); a.edge_c = h->d_edge_c.as<int>();
+  a.rowptr = h->d_rowptr.as<int>(); a.ilist = io.d_ilist;
+  for (int k = 0; k < 3; ++k) { a.X[k] = h->c_X[k].as<float>(); a.V[k] = h->c_V[k].as<float>(); a.gamma[k] = h->c_gamma[k].as<float>(); a.dgamma[k] = h->c_dgamma[k].as<float>(); }
+  for (int k = 0; k < 4; ++k) a.ZD[k] = h->c_ZD[k].as<float>();
+  a.W0 = h->c_W0.as<float>(); a.dX = h->c_dX.as<float>(); a.dV[0] = h->c_dV[0].as<float>(); a.dV[1] = h->c_dV[1].as<float>();
+  a.dY = h->c_dY.as<float>(); a.du = h->c_du.as<float>(); a.carry = h->c_carry.as<float>(); a.ecarry = h->c_ecarry.as<double>();
+  a.esum = h->d_esum.as<double>();
+  a.edge_energy = h->debug ? h->d_edge_energy.as<float>() : nullptr;
+  a.edge_grad = h->debug ? h->d_edge_grad.as<float>() : nullptr;
+  a.facc = h->d_facc.as<unsigned long long>();
+  a.vacc = h->d_vacc.as<unsigned long long>();
+}
+
+static int ensure_edge_arrays(alg_handle* h, long cap) {
+  cap = std::max<long>(cap, 1);
+  CK(h->d_edge_j.ensure(sizeof(int) * cap));
+  CK(h->d_edge_c.ensure(sizeof(int) * cap));
+  CK(h->d_rvec.ensure(sizeof(float4) * cap));
+  if (h->keep_edges) CK(h->d_edge_index.ensure(sizeof(long long) * 2 * cap));
+  if (h->debug) {
+    CK(h->d_edge_energy.ensure(sizeof(float) * cap));
+    CK(h->d_edge_grad.ensure(sizeof(float) * 3 * cap));
+  }
+  return ALG_OK;
+}
+
+static void launch_edge_fill(alg_handle* h, const StepIO& io, long cap) {
   cudaStream_t st = h->stream;
-  const int ntot = nlocal + nghost;
+  const int wblocks = (int)(((long)io.nlocal * 32 + 255) / 256);
+  k_edges<true><<<wblocks, 256, 0, st>>>(io.nlocal, io.d_x, io.d_type, io.d_ilist, io.acc, h->d_cutsq.as<double>(), h->ntypes, h->filter_le ? 1 : 0,
+                                         nullptr, h->d_rowptr.as<int>(), h->d_tmap.as<int>(), h->d_edge_j.as<int>(), h->d_edge_c.as<int>(),
+                                         h->d_rvec.as<float4>(), cap);
+  if (h->keep_edges)
+    k_edge_index<<<1024, 256, 0, st>>>(h->d_rowptr.as<int>(), io.nlocal, cap, h->d_edge_j.as<int>(), h->d_edge_c.as<int>(), io.d_ilist,
+                                       h->d_edge_index.as<long long>());
+}
+
+// ---- chunked edge-tile pipeline (any neighbour count; synchronises once on the CSR row pointer)
+static int step_tiled(alg_handle* h, const StepIO& io) {
+  cudaStream_t st = h->stream;
+  const int nlocal = io.nlocal;
   const PipelineInfo& pi = h->pinfo;
   const int TM = pi.TM;
-  h->last_nlocal = nlocal; h->last_ntot = ntot; h->last_E = 0;
-  h->outputs.clear();
-  CK(cudaEventRecord(h->ev[0], st));
-  // ---- K1: count, scan, fill
-  CK(h->d_cnt.ensure(sizeof(int) * (nlocal + 1)));
-  CK(h->d_rowptr.ensure(sizeof(int) * (nlocal + 1)));
-  CK(h->d_mtype.ensure(sizeof(int) * ntot));
-  const int wblocks = (int)(((long)nlocal * 32 + 255) / 256);
-  k_mtype<<<(ntot + 255) / 256, 256, 0, st>>>(ntot, d_type, h->d_tmap.as<int>(), h->d_mtype.as<int>());
-  k_edges<false><<<wblocks, 256, 0, st>>>(nlocal, d_x, d_type, d_ilist, acc, h->d_cutsq.as<double>(), h->ntypes, h->filter_le ? 1 : 0,
-                                          h->d_cnt.as<int>(), nullptr, nullptr, nullptr, nullptr, nullptr);
-  CK(cudaMemsetAsync(h->d_cnt.as<int>() + nlocal, 0, sizeof(int), st));
-  size_t tmp_bytes = 0;
-  cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, h->d_cnt.as<int>(), h->d_rowptr.as<int>(), nlocal + 1, st);
-  CK(h->d_scan_tmp.ensure(tmp_bytes));
-  CK(cub::DeviceScan::ExclusiveSum(h->d_scan_tmp.p, tmp_bytes, h->d_cnt.as<int>(), h->d_rowptr.as<int>(), nlocal + 1, st));
   CK(h->h_rowptr.ensure(sizeof(int) * (nlocal + 1)));
   CK(cudaMemcpyAsync(h->h_rowptr.p, h->d_rowptr.p, sizeof(int) * (nlocal + 1), cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
   const int* rowptr = h->h_rowptr.as<int>();
   const long E = rowptr[nlocal];
-  h->last_E = E;
-  CK(h->d_edge_j.ensure(sizeof(int) * std::max<long>(E, 1)));
-  CK(h->d_edge_c.ensure(sizeof(int) * std::max<long>(E, 1)));
-  CK(h->d_rvec.ensure(sizeof(float4) * std::max<long>(E, 1)));
-  k_edges<true><<<wblocks, 256, 0, st>>>(nlocal, d_x, d_type, d_ilist, acc, h->d_cutsq.as<double>(), h->ntypes, h->filter_le ? 1 : 0,
-                                         nullptr, h->d_rowptr.as<int>(), h->d_tmap.as<int>(), h->d_edge_j.as<int>(), h->d_edge_c.as<int>(),
-                                         h->d_rvec.as<float4>());
-  if (h->keep_edges) {
-    CK(h->d_edge_index.ensure(sizeof(long long) * 2 * std::max<long>(E, 1)));
-    if (E > 0) k_edge_index<<<(unsigned)((E + 255) / 256), 256, 0, st>>>(E, h->d_edge_j.as<int>(), h->d_edge_c.as<int>(), d_ilist, h->d_edge_index.as<long long>());
-  }
+  h->last_E = E; h->last_E_known = E; h->last_E_nlocal = nlocal;
+  int rc = ensure_edge_arrays(h, E);
+  if (rc != ALG_OK) return rc;
+  launch_edge_fill(h, io, E);
   CK(cudaGetLastError());
   CK(cudaEventRecord(h->ev[1], st));
-  // ---- per-step accumulators
-  CK(h->d_esum.ensure(sizeof(double) * nlocal));
-  CK(h->d_facc.ensure(sizeof(unsigned long long) * 3 * ntot));
-  CK(h->d_vacc.ensure(sizeof(unsigned long long) * 8));
-  CK(cudaMemsetAsync(h->d_esum.p, 0, sizeof(double) * nlocal, st));
-  CK(cudaMemsetAsync(h->d_facc.p, 0, sizeof(unsigned long long) * 3 * ntot, st));
-  CK(cudaMemsetAsync(h->d_vacc.p, 0, sizeof(unsigned long long) * 8, st));
-  if (h->debug) {
-    CK(h->d_edge_energy.ensure(sizeof(float) * std::max<long>(E, 1)));
-    CK(h->d_edge_grad.ensure(sizeof(float) * 3 * std::max<long>(E, 1)));
-  }
-  // ---- chunk plan (centre aligned)
+  // chunk plan (centre aligned)
   struct Chunk { int c0, c1, e0, e1; };
   std::vector<Chunk> chunks;
   const long CE = std::max<long>(h->chunk_edges, TM);
@@ -731,27 +837,10 @@ static int run_step(alg_handle* h, int nlocal, int nghost, const double* d_x, co
     }
     c0 = c1;
   }
-  int rc = ensure_chunk_buffers(h, max_tiles, max_cent);
+  rc = ensure_chunk_buffers(h, max_tiles, max_cent);
   if (rc != ALG_OK) return rc;
-  ChunkArgs a{};
-  a.rvec = h->d_rvec.as<float4>(); a.edge_j = h->d_edge_j.as<int>(); a.edge_c = h->d_edge_c.as<int>();
-  a.rowptr = h->d_rowptr.as<int>(); a.ilist = d_ilist;
-  for (int k = 0; k < 3; ++k) { a.X[k] = h->c_X[k].as<float>(); a.V[k] = h->c_V[k].as<float>(); a.gamma[k] = h->c_gamma[k].as<float>(); a.dgamma[k] = h->c_dgamma[k].as<float>(); }
-  for (int k = 0; k < 4; ++k) a.ZD[k] = h->c_ZD[k].as<float>();
-  a.W0 = h->c_W0.as<float>(); a.dX = h->c_dX.as<float>(); a.dV[0] = h->c_dV[0].as<float>(); a.dV[1] = h->c_dV[1].as<float>();
-  a.dY = h->c_dY.as<float>(); a.du = h->c_du.as<float>(); a.carry = h->c_carry.as<float>(); a.ecarry = h->c_ecarry.as<double>();
-  a.esum = h->d_esum.as<double>();
-  a.edge_energy = h->debug ? h->d_edge_energy.as<float>() : nullptr;
-  a.edge_grad = h->debug ? h->d_edge_grad.as<float>() : nullptr;
-  a.facc = h->d_facc.as<unsigned long long>();
-  a.vacc = h->d_vacc.as<unsigned long long>();
-  a.tstamp = nullptr;
-  if (h->debug) {
-    CK(h->d_tstamp.ensure(sizeof(long long) * 5 * 32));
-    CK(cudaMemsetAsync(h->d_tstamp.p, 0, sizeof(long long) * 5 * 32, st));
-    a.tstamp = h->d_tstamp.as<long long>();
-  }
-  h->prof.reset();
+  ChunkArgs a;
+  fill_args(h, io, a);
   long tiles_total = 0;
   for (const Chunk& c : chunks) {
     a.e0 = c.e0; a.e1 = c.e1; a.c0 = c.c0;
@@ -759,44 +848,200 @@ static int run_step(alg_handle* h, int nlocal, int nghost, const double* d_x, co
     tiles_total += ntiles;
     CK(h->pipe->run_chunk(a, h->mw, &h->tcw, ntiles, st, &h->prof));
   }
-  // own kernels outside the chunk pipeline: k_mtype, k_edges x2, [k_edge_index], 4 finalize kernels
-  h->step_stats[0] = (double)h->prof.launches + 3 + (h->keep_edges && E > 0 ? 1 : 0) + 4;
   h->step_stats[1] = (double)E; h->step_stats[2] = (double)chunks.size(); h->step_stats[3] = (double)tiles_total;
-  CK(cudaEventRecord(h->ev[2], st));
-  // ---- finalize
-  CK(h->d_forces.ensure(sizeof(double) * 3 * ntot));
-  CK(h->d_eall.ensure(sizeof(double) * ntot));
-  const int eblocks = (nlocal + 1023) / 1024;
-  CK(h->d_red.ensure(sizeof(double) * (eblocks + 8)));
-  k_forces<<<(unsigned)((3L * ntot + 255) / 256), 256, 0, st>>>(ntot, h->d_facc.as<unsigned long long>(), h->d_forces.as<double>(), d_f_inout);
-  k_eall_ghost<<<(ntot + 255) / 256, 256, 0, st>>>(ntot, h->d_mtype.as<int>(), h->d_shift.as<double>(), h->d_eall.as<double>());
-  k_eall_local<<<eblocks, 256, 0, st>>>(nlocal, d_ilist, h->d_mtype.as<int>(), h->d_esum.as<double>(), h->d_scale.as<double>(),
-                                        h->d_shift.as<double>(), 1.0 / std::sqrt(h->avg_n), h->d_eall.as<double>(),
-                                        eflag_atom ? d_eatom : nullptr, h->d_red.as<double>() + 8);
-  k_final_scalars<<<1, 32, 0, st>>>(eblocks, h->d_red.as<double>() + 8, h->d_vacc.as<unsigned long long>(), h->d_red.as<double>());
-  CK(cudaGetLastError());
-  CK(cudaEventRecord(h->ev[3], st));
-  if (eng || virial6) {
-    CK(h->h_out.ensure(sizeof(double) * 8));
-    CK(cudaMemcpyAsync(h->h_out.p, h->d_red.p, sizeof(double) * 7, cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
-    const double* o = h->h_out.as<double>();
-    if (eng) *eng = o[0];
-    if (virial6 && vflag_global) for (int q = 0; q < 6; ++q) virial6[q] = o[1 + q];
-    float ms;
-    for (int q = 0; q < 3; ++q) { cudaEventElapsedTime(&ms, h->ev[q], h->ev[q + 1]); h->timings[q] = ms; }
-    if (h->prof.on) {
-      for (int q = 0; q < KID_COUNT; ++q) { h->kernel_ms[q] = 0; h->kernel_n[q] = 0; }
-      for (size_t r = 0; r < h->prof.ids.size(); ++r) {
-        cudaEventElapsedTime(&ms, h->prof.ev[2 * r], h->prof.ev[2 * r + 1]);
-        h->kernel_ms[h->prof.ids[r]] += ms; h->kernel_n[h->prof.ids[r]] += 1;
-      }
-    }
-  }
   h->dbg_ntiles = chunks.size() == 1 ? (chunks[0].e1 - chunks[0].e0 + TM - 1) / TM : 0;
   h->dbg_c0 = chunks.size() == 1 ? chunks[0].c0 : 0;
   h->dbg_ncent = chunks.size() == 1 ? chunks[0].c1 - chunks[0].c0 : 0;
   return ALG_OK;
+}
+
+// ---- fused persistent pipeline: no host synchronisation; the tile plan is built on the device
+static int step_fused(alg_handle* h, const StepIO& io, long cap) {
+  cudaStream_t st = h->stream;
+  const int nlocal = io.nlocal;
+  const PipelineInfo& pi = h->pinfo;
+  int rc = ensure_edge_arrays(h, cap);
+  if (rc != ALG_OK) return rc;
+  const int nblk = (nlocal + PLAN_CB - 1) / PLAN_CB;
+  CK(h->d_blk.ensure(sizeof(int) * (nblk + 1)));
+  CK(h->d_blk_base.ensure(sizeof(int) * (nblk + 1)));
+  CK(h->d_tile_c0.ensure(sizeof(int) * ((size_t)nlocal + nblk + 2)));
+  CK(h->d_info.ensure(sizeof(int) * 8));
+  CK(cudaMemsetAsync(h->d_info.p, 0, sizeof(int) * 8, st));
+  const int pb = (nblk + 127) / 128;
+  k_plan<false><<<pb, 128, 0, st>>>(nlocal, h->d_rowptr.as<int>(), h->d_blk.as<int>(), nullptr, nullptr, h->d_info.as<int>(), cap);
+  size_t tmp_bytes = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, h->d_blk.as<int>(), h->d_blk_base.as<int>(), nblk + 1, st);
+  CK(h->d_scan_tmp.ensure(tmp_bytes));
+  CK(cub::DeviceScan::ExclusiveSum(h->d_scan_tmp.p, tmp_bytes, h->d_blk.as<int>(), h->d_blk_base.as<int>(), nblk + 1, st));
+  k_plan<true><<<pb, 128, 0, st>>>(nlocal, h->d_rowptr.as<int>(), nullptr, h->d_blk_base.as<int>(), h->d_tile_c0.as<int>(), h->d_info.as<int>(), cap);
+  launch_edge_fill(h, io, cap);
+  CK(cudaGetLastError());
+  CK(cudaEventRecord(h->ev[1], st));
+  const int grid = h->fused_grid;
+  rc = ensure_chunk_buffers(h, grid, (long)grid * PLAN_ROWS);
+  if (rc != ALG_OK) return rc;
+  ChunkArgs a;
+  fill_args(h, io, a);
+  a.e0 = 0; a.e1 = 0; a.c0 = 0;
+  FusedPlan plan{h->d_tile_c0.as<int>(), h->d_info.as<int>(), PLAN_ROWS};
+  CK(h->pipe->run_fused(a, h->mw, &h->tcw, plan, grid, st, &h->prof));
+  h->prof.launches += 2;                               // k_plan x2
+  h->dbg_ntiles = 0; h->dbg_c0 = 0; h->dbg_ncent = 0;
+  (void)pi;
+  return ALG_OK;
+}
+
+// the verdict of an asynchronous fused step is read here (by the next call, or by a getter)
+static int resolve_pending(alg_handle* h) {
+  if (!h->info_pending) return ALG_OK;
+  h->info_pending = false;
+  CK(cudaEventSynchronize(h->ev_info));
+  const int* info = h->h_info.as<int>();
+  h->last_E = info[2]; h->last_E_known = info[2];
+  h->step_stats[1] = info[2]; h->step_stats[3] = info[0];
+  if (info[1] > PLAN_ROWS) {
+    h->force_tiled = true;
+    return fail(h, ALG_ESTATE, "the previous asynchronous alg_compute_device step met an atom with more than 128 neighbours inside the cutoff "
+                               "and produced no forces; the chunked pipeline is selected from now on (pass eng != NULL to have such steps "
+                               "re-run transparently)");
+  }
+  if (info[3]) return fail(h, ALG_ESTATE, "the previous asynchronous alg_compute_device step overflowed its edge buffers and produced no forces "
+                                          "(set option max_neighbors, or pass eng != NULL to have such steps re-run transparently)");
+  return ALG_OK;
+}
+
+static bool fused_selected(const alg_handle* h) {
+  if (h->pipeline_mode == 2 || !h->use_tc || !h->pipe || !h->pipe->run_fused || h->fused_grid <= 0) return false;
+  if (h->pipeline_mode == 1) return true;
+  return !h->force_tiled && !h->debug;               // auto: per-stage intermediates (debug=1) exist only in the chunked pipeline
+}
+
+static int run_step(alg_handle* h, const StepIO& io, double* eng, double* virial6) {
+  cudaStream_t st = h->stream;
+  const int nlocal = io.nlocal, ntot = io.nlocal + io.nghost;
+  int rc = resolve_pending(h);
+  if (rc != ALG_OK) return rc;
+  h->last_nlocal = nlocal; h->last_ntot = ntot; h->last_E = 0;
+  h->outputs.clear();
+  CK(cudaEventRecord(h->ev[0], st));
+  // ---- K1: count + scan (the fill runs inside the pipeline step once the capacity is known)
+  CK(h->d_cnt.ensure(sizeof(int) * (nlocal + 1)));
+  CK(h->d_rowptr.ensure(sizeof(int) * (nlocal + 1)));
+  CK(h->d_mtype.ensure(sizeof(int) * ntot));
+  const int wblocks = (int)(((long)nlocal * 32 + 255) / 256);
+  k_mtype<<<(ntot + 255) / 256, 256, 0, st>>>(ntot, io.d_type, h->d_tmap.as<int>(), h->d_mtype.as<int>());
+  k_edges<false><<<wblocks, 256, 0, st>>>(nlocal, io.d_x, io.d_type, io.d_ilist, io.acc, h->d_cutsq.as<double>(), h->ntypes, h->filter_le ? 1 : 0,
+                                          h->d_cnt.as<int>(), nullptr, nullptr, nullptr, nullptr, nullptr, 0);
+  CK(cudaMemsetAsync(h->d_cnt.as<int>() + nlocal, 0, sizeof(int), st));
+  size_t tmp_bytes = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, h->d_cnt.as<int>(), h->d_rowptr.as<int>(), nlocal + 1, st);
+  CK(h->d_scan_tmp.ensure(tmp_bytes));
+  CK(cub::DeviceScan::ExclusiveSum(h->d_scan_tmp.p, tmp_bytes, h->d_cnt.as<int>(), h->d_rowptr.as<int>(), nlocal + 1, st));
+  CK(h->d_esum.ensure(sizeof(double) * nlocal));
+  CK(h->d_facc.ensure(sizeof(unsigned long long) * 3 * ntot));
+  CK(h->d_vacc.ensure(sizeof(unsigned long long) * 8));
+  CK(h->d_forces.ensure(sizeof(double) * 3 * ntot));
+  CK(h->d_eall.ensure(sizeof(double) * ntot));
+  const int eblocks = (nlocal + 1023) / 1024;
+  CK(h->d_red.ensure(sizeof(double) * (eblocks + 8)));
+  CK(h->h_out.ensure(sizeof(double) * 8));
+  CK(h->h_info.ensure(sizeof(int) * 8));
+  const bool want_sync = eng || virial6 || io.h_f;
+  bool fused = fused_selected(h);
+  long cap = 0;
+  for (int attempt = 0;; ++attempt) {
+    CK(cudaMemsetAsync(h->d_esum.p, 0, sizeof(double) * nlocal, st));
+    CK(cudaMemsetAsync(h->d_facc.p, 0, sizeof(unsigned long long) * 3 * ntot, st));
+    CK(cudaMemsetAsync(h->d_vacc.p, 0, sizeof(unsigned long long) * 8, st));
+    h->prof.reset();
+    if (fused) {
+      if (cap == 0) {
+        if (io.cap_hint > 0) cap = io.cap_hint;
+        else if (h->last_E_known >= 0 && h->last_E_nlocal == nlocal) cap = h->last_E_known + h->last_E_known / 8 + 4096;
+        else {                                           // first step on this system: read the edge count once
+          int E0 = 0;
+          CK(cudaMemcpyAsync(&E0, h->d_rowptr.as<int>() + nlocal, sizeof(int), cudaMemcpyDeviceToHost, st));
+          CK(cudaStreamSynchronize(st));
+          cap = (long)E0 + E0 / 8 + 4096;
+          h->last_E_known = E0;
+        }
+        h->last_E_nlocal = nlocal;
+      }
+      rc = step_fused(h, io, cap);
+    } else {
+      rc = step_tiled(h, io);
+    }
+    if (rc != ALG_OK) return rc;
+    h->last_fused = fused;
+    // own kernels outside the pipeline: k_mtype, k_edges x2, [k_edge_index], 4 finalize kernels
+    h->step_stats[0] = (double)h->prof.launches + 3 + (h->keep_edges ? 1 : 0) + 4;
+    CK(cudaEventRecord(h->ev[2], st));
+    // ---- finalize
+    if (io.wait_f) CK(cudaStreamWaitEvent(st, io.wait_f, 0));
+    k_forces<<<(unsigned)((3L * ntot + 255) / 256), 256, 0, st>>>(ntot, h->d_facc.as<unsigned long long>(), h->d_forces.as<double>(), io.d_f_inout,
+                                                                  fused ? h->d_info.as<int>() : nullptr);
+    k_eall_ghost<<<(ntot + 255) / 256, 256, 0, st>>>(ntot, h->d_mtype.as<int>(), h->d_shift.as<double>(), h->d_eall.as<double>());
+    k_eall_local<<<eblocks, 256, 0, st>>>(nlocal, io.d_ilist, h->d_mtype.as<int>(), h->d_esum.as<double>(), h->d_scale.as<double>(),
+                                          h->d_shift.as<double>(), 1.0 / std::sqrt(h->avg_n), h->d_eall.as<double>(),
+                                          io.eflag_atom ? io.d_eatom : nullptr, h->d_red.as<double>() + 8);
+    k_final_scalars<<<1, 32, 0, st>>>(eblocks, h->d_red.as<double>() + 8, h->d_vacc.as<unsigned long long>(), h->d_red.as<double>());
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(h->ev[3], st));
+    if (fused) CK(cudaMemcpyAsync(h->h_info.p, h->d_info.p, sizeof(int) * 8, cudaMemcpyDeviceToHost, st));
+    if (!want_sync) {
+      if (fused) { CK(cudaEventRecord(h->ev_info, st)); h->info_pending = true; h->step_stats[1] = -1; h->step_stats[2] = 1; h->step_stats[3] = -1; }
+      return ALG_OK;
+    }
+    if (io.h_f) CK(cudaMemcpyAsync(io.h_f, io.d_f_inout, sizeof(double) * 3 * ntot, cudaMemcpyDeviceToHost, st));
+    if (io.h_eatom_stage && io.eflag_atom) CK(cudaMemcpyAsync(io.h_eatom_stage, io.d_eatom, sizeof(double) * ntot, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(h->h_out.p, h->d_red.p, sizeof(double) * 7, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (fused) {
+      const int* info = h->h_info.as<int>();
+      h->last_E = info[2]; h->last_E_known = info[2];
+      h->step_stats[1] = info[2]; h->step_stats[2] = 1; h->step_stats[3] = info[0];
+      if (info[1] > PLAN_ROWS) {                         // an atom with more than 128 neighbours: chunked pipeline from now on
+        if (h->pipeline_mode == 1) return fail(h, ALG_EINVAL, "pipeline=fused: an atom has more than 128 neighbours inside the cutoff");
+        h->force_tiled = true; fused = false;
+        continue;
+      }
+      if (info[3]) {                                     // edge arrays too small (capacity hysteresis): grow and repeat
+        if (attempt >= 2) return fail(h, ALG_ECUDA, "edge buffer capacity could not be established");
+        cap = (long)info[2] + info[2] / 8 + 4096;
+        continue;
+      }
+    }
+    break;
+  }
+  const double* o = h->h_out.as<double>();
+  if (eng) *eng = o[0];
+  if (virial6 && io.vflag_global) for (int q = 0; q < 6; ++q) virial6[q] = o[1 + q];
+  float ms;
+  for (int q = 0; q < 3; ++q) { cudaEventElapsedTime(&ms, h->ev[q], h->ev[q + 1]); h->timings[q] = ms; }
+  if (h->prof.on) {
+    for (int q = 0; q < KID_COUNT; ++q) { h->kernel_ms[q] = 0; h->kernel_n[q] = 0; }
+    for (size_t r = 0; r < h->prof.ids.size(); ++r) {
+      cudaEventElapsedTime(&ms, h->prof.ev[2 * r], h->prof.ev[2 * r + 1]);
+      h->kernel_ms[h->prof.ids[r]] += ms; h->kernel_n[h->prof.ids[r]] += 1;
+    }
+  }
+  return ALG_OK;
+}
+
+// pin a caller-owned host array for asynchronous DMA (one cached registration per role; re-registered when the
+// caller's array moves or grows).  Returns false when the range cannot be pinned: the copy is then a plain
+// (driver-staged) cudaMemcpyAsync.
+static bool pin_host(alg_handle* h, int role, const void* p, size_t bytes) {
+  if (!h->host_register || !p || bytes == 0) return false;
+  auto& slot = h->reg[role];
+  if (slot.first == p && slot.second >= bytes) return true;
+  if (slot.first) { cudaHostUnregister(const_cast<void*>(slot.first)); cudaGetLastError(); slot = {nullptr, 0}; }
+  cudaError_t e = cudaHostRegister(const_cast<void*>(p), bytes, cudaHostRegisterDefault);
+  if (e == cudaErrorHostMemoryAlreadyRegistered) { cudaGetLastError(); return true; }   // already pinned by the caller
+  if (e != cudaSuccess) { cudaGetLastError(); return false; }
+  slot = {p, bytes};
+  return true;
 }
 
 extern "C" int alg_compute_host(alg_handle* h, int nlocal, int nghost, const double* x, const int* type, const int* ilist,
@@ -813,8 +1058,18 @@ extern "C" int alg_compute_host(alg_handle* h, int nlocal, int nghost, const dou
   const int ntot = nlocal + nghost;
   CK(h->d_x.ensure(sizeof(double) * 3 * ntot));
   CK(h->d_type.ensure(sizeof(int) * ntot));
+  CK(h->d_f_stage.ensure(sizeof(double) * 3 * ntot));
+  // the caller's arrays (LAMMPS atom->x / f / type keep their address until they grow) are pinned once, so that the
+  // per-step copies are asynchronous DMA instead of driver-staged pageable copies
+  pin_host(h, 0, x, sizeof(double) * 3 * ntot);
+  pin_host(h, 1, f, sizeof(double) * 3 * ntot);
+  pin_host(h, 2, type, sizeof(int) * ntot);
   CK(cudaMemcpyAsync(h->d_x.p, x, sizeof(double) * 3 * ntot, cudaMemcpyHostToDevice, st));
   CK(cudaMemcpyAsync(h->d_type.p, type, sizeof(int) * ntot, cudaMemcpyHostToDevice, st));
+  // f travels to the device on a second stream while the network runs; the store kernel adds the model forces to it
+  // (f += forces for ALL atoms incl. ghosts, cpp:370-377) and the sum is copied back before the final synchronisation
+  CK(cudaMemcpyAsync(h->d_f_stage.p, f, sizeof(double) * 3 * ntot, cudaMemcpyHostToDevice, h->copy_stream));
+  CK(cudaEventRecord(h->ev_copy, h->copy_stream));
   // LAMMPS rebuilds the neighbour list only every few steps (neighbor->ago == 0 on a rebuild step): with
   // option neigh_ago > 0 the device copy of the list uploaded by the last call is reused when the atom
   // counts still match; otherwise the paged list is flattened (ilist order, jlist order) and uploaded
@@ -828,37 +1083,41 @@ extern "C" int alg_compute_host(alg_handle* h, int nlocal, int nghost, const dou
     first[nlocal] = tot;
     CK(h->h_stage.ensure(sizeof(int) * std::max<long long>(tot, 1)));
     int* stage = h->h_stage.as<int>();
-#pragma omp parallel for schedule(static)
-    for (int ii = 0; ii < nlocal; ++ii) memcpy(stage + first[ii], firstneigh[ilist[ii]], sizeof(int) * cnt[ii]);
     CK(h->d_ilist.ensure(sizeof(int) * nlocal));
     CK(h->d_cand.ensure(sizeof(int) * std::max<long long>(tot, 1)));
     CK(h->d_first.ensure(sizeof(long long) * (nlocal + 1)));
     CK(h->d_numneigh.ensure(sizeof(int) * nlocal));
     CK(cudaMemcpyAsync(h->d_ilist.p, ilist, sizeof(int) * nlocal, cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(h->d_cand.p, stage, sizeof(int) * tot, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(h->d_first.p, first, sizeof(long long) * (nlocal + 1), cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(h->d_numneigh.p, cnt, sizeof(int) * nlocal, cudaMemcpyHostToDevice, st));
+    // flatten the paged list into pinned memory in slabs of centres; the upload of slab s overlaps the flattening of s+1
+    const int SLAB = 1 << 16;
+    for (int s0 = 0; s0 < nlocal; s0 += SLAB) {
+      const int s1 = std::min(nlocal, s0 + SLAB);
+#pragma omp parallel for schedule(static)
+      for (int ii = s0; ii < s1; ++ii) memcpy(stage + first[ii], firstneigh[ilist[ii]], sizeof(int) * cnt[ii]);
+      const long long nb = first[s1] - first[s0];
+      if (nb > 0) CK(cudaMemcpyAsync(h->d_cand.as<int>() + first[s0], stage + first[s0], sizeof(int) * nb, cudaMemcpyHostToDevice, st));
+    }
     h->list_nlocal = nlocal; h->list_ntot = ntot; h->list_tot = tot;
   }
   h->list_reused = reuse ? 1 : 0;
-  NeighAcc acc{h->d_cand.as<int>(), h->d_first.as<long long>(), h->d_numneigh.as<int>(), 0, 0, 1};
-  if (eflag_atom && eatom) CK(h->d_eatom_out.ensure(sizeof(double) * ntot));
+  const bool want_eatom = eflag_atom && eatom;
+  if (want_eatom) { CK(h->d_eatom_out.ensure(sizeof(double) * ntot)); CK(h->h_eatom.ensure(sizeof(double) * ntot)); }
   double eng_l = 0.0, vir_l[6] = {0, 0, 0, 0, 0, 0};
-  int rc = run_step(h, nlocal, nghost, h->d_x.as<double>(), h->d_type.as<int>(), h->d_ilist.as<int>(), acc, eflag_atom && eatom ? 1 : 0,
-                    1, nullptr, (eflag_atom && eatom) ? h->d_eatom_out.as<double>() : nullptr, &eng_l, vir_l);
+  StepIO io{};
+  io.nlocal = nlocal; io.nghost = nghost; io.d_x = h->d_x.as<double>(); io.d_type = h->d_type.as<int>(); io.d_ilist = h->d_ilist.as<int>();
+  io.acc = NeighAcc{h->d_cand.as<int>(), h->d_first.as<long long>(), h->d_numneigh.as<int>(), 0, 0, 1};
+  io.eflag_atom = want_eatom ? 1 : 0; io.vflag_global = 1;
+  io.d_f_inout = h->d_f_stage.as<double>(); io.d_eatom = want_eatom ? h->d_eatom_out.as<double>() : nullptr;
+  io.cap_hint = (long)std::max<long long>(h->list_tot, 1);      // the edge list is a subset of the candidates
+  io.wait_f = h->ev_copy; io.h_f = f; io.h_eatom_stage = want_eatom ? h->h_eatom.as<double>() : nullptr;
+  int rc = run_step(h, io, &eng_l, vir_l);
   if (rc != ALG_OK) return rc;
-  // store: f += forces for ALL atoms incl. ghosts (cpp:370-377), eatom for locals (cpp:378)
-  auto& fo = h->outputs["forces"];
-  fo.resize((size_t)3 * ntot);
-  CK(cudaMemcpyAsync(fo.data(), h->d_forces.p, sizeof(double) * 3 * ntot, cudaMemcpyDeviceToHost, st));
-  auto& eo = h->outputs["atomic_energy"];
-  eo.resize(ntot);
-  CK(cudaMemcpyAsync(eo.data(), h->d_eall.p, sizeof(double) * ntot, cudaMemcpyDeviceToHost, st));
-  CK(cudaStreamSynchronize(st));
-#pragma omp parallel for schedule(static)
-  for (long i = 0; i < 3L * ntot; ++i) f[i] += fo[i];
-  if (eflag_atom && eatom)
+  if (want_eatom) {                                  // eatom for locals (cpp:378)
+    const double* eo = h->h_eatom.as<double>();
     for (int ii = 0; ii < nlocal; ++ii) eatom[ilist[ii]] = eo[ilist[ii]];
+  }
   if (eng) *eng = eng_l;
   if (vflag_global && virial6) for (int q = 0; q < 6; ++q) virial6[q] = vir_l[q];
   auto& vo = h->outputs["virial"];
@@ -878,22 +1137,26 @@ extern "C" int alg_compute_device(alg_handle* h, int nlocal, int nghost, const d
   CK(cudaSetDevice(h->device));
   // order our stream after the caller's stream and vice versa
   cudaStream_t cs = reinterpret_cast<cudaStream_t>(stream);
-  cudaEvent_t evt;
-  CK(cudaEventCreateWithFlags(&evt, cudaEventDisableTiming));
-  CK(cudaEventRecord(evt, cs));
-  CK(cudaStreamWaitEvent(h->stream, evt, 0));
-  NeighAcc acc{d_neighbors, nullptr, d_numneigh, (long long)stride_i, (long long)stride_jj, 0};
-  int rc = run_step(h, nlocal, nghost, d_x, d_type, d_ilist, acc, eflag_atom && d_eatom ? 1 : 0, vflag_global, d_f, d_eatom, eng, virial6);
-  cudaEventRecord(evt, h->stream);
-  cudaStreamWaitEvent(cs, evt, 0);
-  cudaEventDestroy(evt);
+  CK(cudaEventRecord(h->ev_order, cs));
+  CK(cudaStreamWaitEvent(h->stream, h->ev_order, 0));
+  StepIO io{};
+  io.nlocal = nlocal; io.nghost = nghost; io.d_x = d_x; io.d_type = d_type; io.d_ilist = d_ilist;
+  io.acc = NeighAcc{d_neighbors, nullptr, d_numneigh, (long long)stride_i, (long long)stride_jj, 0};
+  io.eflag_atom = eflag_atom && d_eatom ? 1 : 0; io.vflag_global = vflag_global;
+  io.d_f_inout = d_f; io.d_eatom = d_eatom;
+  io.cap_hint = h->max_neighbors > 0 ? (long)nlocal * h->max_neighbors : 0;
+  int rc = run_step(h, io, eng, virial6);
+  cudaEventRecord(h->ev_order, h->stream);
+  cudaStreamWaitEvent(cs, h->ev_order, 0);
   return rc;
 }
+
 
 extern "C" int alg_get_edges(alg_handle* h, const int64_t** edge_index, int64_t* nedges) {
   if (!h || !edge_index || !nedges) return ALG_EINVAL;
   if (!h->keep_edges) return fail(h, ALG_ESTATE, "alg_get_edges needs option keep_edges=1 before the compute");
   CK(cudaSetDevice(h->device));
+  { int rc = resolve_pending(h); if (rc != ALG_OK) return rc; }
   const long E = h->last_E;
   h->edges_host.resize((size_t)2 * E);
   if (E > 0) {
@@ -908,6 +1171,7 @@ extern "C" int alg_get_edges(alg_handle* h, const int64_t** edge_index, int64_t*
 extern "C" int alg_get_output(alg_handle* h, const char* name, const double** ptr, int64_t* n) {
   if (!h || !name || !ptr || !n) return ALG_EINVAL;
   CK(cudaSetDevice(h->device));
+  { int rc = resolve_pending(h); if (rc != ALG_OK) return rc; }
   const std::string key(name);
   auto it = h->outputs.find(key);
   if (it == h->outputs.end()) {
@@ -934,17 +1198,12 @@ extern "C" int alg_get_output(alg_handle* h, const char* name, const double** pt
       CK(fetchf(h->d_edge_energy.p, E, raw)); out.assign(raw.begin(), raw.end());
     } else if (key == "edge_grad") {
       CK(fetchf(h->d_edge_grad.p, 3 * E, raw)); out.assign(raw.begin(), raw.end());
-    } else if (key == "tstamp") {
-      std::vector<long long> ts(5 * 32);
-      CK(cudaMemcpyAsync(ts.data(), h->d_tstamp.p, sizeof(long long) * ts.size(), cudaMemcpyDeviceToHost, st));
-      CK(cudaStreamSynchronize(st));
-      out.assign(ts.begin(), ts.end());
     } else if (key == "edge_vec") {
       CK(fetchf(h->d_rvec.p, 4 * E, raw));
       out.resize((size_t)3 * E);
       for (long e = 0; e < E; ++e) for (int q = 0; q < 3; ++q) out[3 * e + q] = raw[4 * e + q];
     } else if (h->dbg_ntiles == 0) {
-      return fail(h, ALG_ENOTFOUND, "intermediate outputs need a single-chunk run (raise chunk_edges)");
+      return fail(h, ALG_ENOTFOUND, "intermediate outputs need a single-chunk run of the chunked pipeline (option pipeline=tiled, raise chunk_edges)");
     } else if (key.size() == 2 && key[0] == 'x' && key[1] >= '0' && key[1] < '0' + h->nl) {
       CK(fetchf(h->c_X[key[1] - '0'].p, (size_t)h->dbg_ntiles * S * pi.TM, raw));
       detile(raw, h->dbg_ntiles, S, pi.TM, E, out, h->use_tc);
@@ -993,10 +1252,16 @@ extern "C" int alg_get_stats(alg_handle* h, const char* what, double* out, int n
   if (!h || !what || !out) return ALG_EINVAL;
   const std::string k(what);
   const double* src = nullptr; int m = 0;
+  { int rc = resolve_pending(h); if (rc != ALG_OK) return rc; }
   if (k == "kernel_ms") { src = h->kernel_ms; m = KID_COUNT; }
   else if (k == "kernel_launches") { src = h->kernel_n; m = KID_COUNT; }
   else if (k == "step") { src = h->step_stats; m = 4; }
   else if (k == "list_reused") { if (n > 0) out[0] = h->list_reused; return ALG_OK; }
+  else if (k == "pipeline") {                       // [1 if the last step ran the fused kernel, CTAs of the fused grid, sticky tiled fallback]
+    const double v[3] = {h->last_fused ? 1.0 : 0.0, (double)h->fused_grid, h->force_tiled ? 1.0 : 0.0};
+    for (int i = 0; i < n && i < 3; ++i) out[i] = v[i];
+    return ALG_OK;
+  }
   else return fail(h, ALG_ENOTFOUND, "unknown stats group " + k);
   for (int i = 0; i < n && i < m; ++i) out[i] = src[i];
   return ALG_OK;

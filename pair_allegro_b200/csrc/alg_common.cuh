@@ -95,10 +95,7 @@ struct ChunkArgs {
   float* edge_grad;     // [E][3] or nullptr (debug)
   unsigned long long* facc;   // [ntot][3] fixed-point force accumulators
   unsigned long long* vacc;   // [6] fixed-point virial accumulators
-  long long* tstamp;          // debug: [5 kernels][32] clock64() marks of one CTA, or nullptr
 };
-// phase time stamps of CTA 148 (a CTA of the second wave half, steady state) -- debug only
-#define ALG_TS(a, kern, i) do { if ((a).tstamp && blockIdx.x == 148 && threadIdx.x == 0) (a).tstamp[(kern) * 32 + (i)] = clock64(); } while (0)
 
 // ------------------------------------------------------------------------------------------
 // sigmoid via the SFU: ex2.approx (2 ulp) + rcp.approx (1 ulp); absolute error of s <~ 2e-7,

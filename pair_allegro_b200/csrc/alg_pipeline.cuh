@@ -16,7 +16,7 @@ struct PipelineInfo {
 };
 
 // optional per-kernel CUDA-event timing (option profile=1) and launch counting
-enum { KID_F0 = 0, KID_FK = 1, KID_T = 2, KID_BK = 3, KID_B0 = 4, KID_FIXUP = 5, KID_COUNT = 6 };
+enum { KID_F0 = 0, KID_FK = 1, KID_T = 2, KID_BK = 3, KID_B0 = 4, KID_FIXUP = 5, KID_FUSED = 6, KID_COUNT = 7 };
 struct Prof {
   bool on = false;
   std::vector<cudaEvent_t> ev;
@@ -42,6 +42,9 @@ struct Pipeline {
   PipelineInfo (*info)(int nl);
   cudaError_t (*init)();                                                       // opt-in shared memory
   cudaError_t (*run_chunk)(const ChunkArgs& a, const ModelW& w, const TcW* tw, int ntiles, cudaStream_t st, Prof* prof);
+  // fused persistent kernel over centre-aligned tiles (tensor-core pipeline only; nullptr otherwise)
+  int (*fused_grid)(int nl);                                                   // resident CTAs of the whole device (0 = unsupported)
+  cudaError_t (*run_fused)(const ChunkArgs& a, const ModelW& w, const TcW* tw, const FusedPlan& plan, int grid, cudaStream_t st, Prof* prof);
 };
 
 const Pipeline* get_pipeline(int L);
@@ -141,8 +144,31 @@ template <int L> cudaError_t init_tc_impl() {
   ALG_SET((k_bk_tc<L, 'C', true>));
   ALG_SET((k_bk_tc<L, 'D', false>));
   ALG_SET((k_b0_tc<L>));
+  ALG_SET((k_fused_tc<L, 1>));
+  ALG_SET((k_fused_tc<L, 2>));
+  ALG_SET((k_fused_tc<L, 3>));
 #undef ALG_SET
   return cudaSuccess;
+}
+template <int L> int fused_grid_tc_impl(int nl) {
+  int dev = 0, sms = 0, per_sm = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0;
+  cudaError_t e;
+  if (nl == 1) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fused_tc<L, 1>, NT, SmemTC<L>::BYTES);
+  else if (nl == 2) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fused_tc<L, 2>, NT, SmemTC<L>::BYTES);
+  else e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fused_tc<L, 3>, NT, SmemTC<L>::BYTES);
+  if (e != cudaSuccess || per_sm < 1) return 0;
+  if (per_sm > 2) per_sm = 2;                        // tensor memory: 256 of 512 columns per CTA
+  return sms * per_sm;
+}
+template <int L> cudaError_t run_fused_tc_impl(const ChunkArgs& a, const ModelW& w, const TcW* twp, const FusedPlan& plan, int grid, cudaStream_t st, Prof* pf) {
+  const size_t sm = SmemTC<L>::BYTES;
+  pf->begin(KID_FUSED, st);
+  if (w.nl == 1) k_fused_tc<L, 1><<<grid, NT, sm, st>>>(a, w, *twp, plan);
+  else if (w.nl == 2) k_fused_tc<L, 2><<<grid, NT, sm, st>>>(a, w, *twp, plan);
+  else k_fused_tc<L, 3><<<grid, NT, sm, st>>>(a, w, *twp, plan);
+  pf->end(st);
+  return cudaGetLastError();
 }
 template <int L> cudaError_t run_chunk_tc_impl(const ChunkArgs& a, const ModelW& w, const TcW* twp, int ntiles, cudaStream_t st, Prof* pf) {
   using D = DimsTC<L>;
@@ -187,13 +213,14 @@ template <int L> cudaError_t run_chunk_tc_impl(const ChunkArgs& a, const ModelW&
 }
 #define ALG_DEFINE_PIPELINE_TC(L)                                                                  \
   const Pipeline* get_pipeline_tc_L##L() {                                                         \
-    static const Pipeline p = {&info_tc_impl<L>, &init_tc_impl<L>, &run_chunk_tc_impl<L>};         \
+    static const Pipeline p = {&info_tc_impl<L>, &init_tc_impl<L>, &run_chunk_tc_impl<L>,          \
+                               &fused_grid_tc_impl<L>, &run_fused_tc_impl<L>};                     \
     return &p;                                                                                     \
   }
 
 #define ALG_DEFINE_PIPELINE(L)                                                             \
   const Pipeline* get_pipeline_L##L() {                                                    \
-    static const Pipeline p = {&info_impl<L>, &init_impl<L>, &run_chunk_impl<L>};          \
+    static const Pipeline p = {&info_impl<L>, &init_impl<L>, &run_chunk_impl<L>, nullptr, nullptr}; \
     return &p;                                                                             \
   }
 #endif

@@ -114,6 +114,8 @@ struct TcCtx {
   uint32_t mph, wph, wph2;
   int passes;
   int m, half, q;
+  int c0;              // first centre slot of the Gamma / dGamma rows this CTA addresses (chunk origin, or the tile's first centre)
+  size_t goff;         // float offset of this CTA's private Gamma / dGamma rows (fused kernel; 0 in the chunked pipeline)
 };
 
 template <int L> __device__ __forceinline__ TcCtx tc_begin(float* sm_raw, const TcW& tw) {
@@ -137,6 +139,7 @@ template <int L> __device__ __forceinline__ TcCtx tc_begin(float* sm_raw, const 
   c.mph = c.wph = c.wph2 = 0;
   c.passes = tw.passes;
   c.m = t & 127; c.half = t >> 7; c.q = (t >> 5) & 3;
+  c.c0 = 0; c.goff = 0;
   return c;
 }
 __device__ __forceinline__ void tc_end(TcCtx& c) {
@@ -188,15 +191,13 @@ template <int L> __device__ __forceinline__ void tc_mma8(uint32_t td, uint32_t t
     umma::mma_tf32_ta(td, ta + 56, db + wpan + 6, idesc, 1);
   }
 }
-template <int L> __device__ __forceinline__ void tc_mma(TcCtx& c, int K, int N, uint32_t dcol, uint32_t accumulate = 0, long long* ts = nullptr) {
+template <int L> __device__ __forceinline__ void tc_mma(TcCtx& c, int K, int N, uint32_t dcol, uint32_t accumulate = 0) {
   using SM = SmemTC<L>;
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   if (warp == 0) umma::mbar_wait(c.wbar, c.wph);      // weight block landed (requested one epilogue ago)
-  if (ts && threadIdx.x == 0 && blockIdx.x == 148) ts[0] = clock64();
   umma::tmem_st_wait();                                // this thread's operand columns are in tensor memory
   umma::fence_before_sync();
   __syncthreads();
-  if (ts && threadIdx.x == 0 && blockIdx.x == 148) ts[1] = clock64();
   if (warp == 0) {
     umma::fence_after_sync();
     const uint32_t sbase = __shfl_sync(0xffffffffu, umma::smem_u32(c.sm), 0);
@@ -218,13 +219,11 @@ template <int L> __device__ __forceinline__ void tc_mma(TcCtx& c, int K, int N, 
       asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(mbar) : "memory");
     }
     __syncwarp();
-    if (ts && threadIdx.x == 0 && blockIdx.x == 148) ts[2] = clock64();
   }
   c.wph ^= 1;
   umma::mbar_wait(c.mbar, c.mph);
   c.mph ^= 1;
   umma::fence_after_sync();
-  if (ts && threadIdx.x == 0 && blockIdx.x == 148) ts[3] = clock64();
 }
 
 // two GEMMs on the SAME A operand (K columns), weights in buffer 1 (N1 -> dcol1) and buffer 2 (N2 -> dcol2):
@@ -314,27 +313,27 @@ __device__ __forceinline__ void st_row4(float* g, int n4, int m, float a, float 
 }
 // load a 64-row tile array (x^k, dX; row4 layout) of this tile into operand columns [0,64)
 // split form: issue the 8 loads early (no TcCtx needed), write the operand later
-__device__ __forceinline__ void ld_rows_x8(const float* __restrict__ g /*tile base, row4 layout*/, float4 (&v)[8]) {
+__device__ __forceinline__ void ld_rows_x8(const float* g /*tile base, row4 layout*/, float4 (&v)[8]) {
   const float4* gp = reinterpret_cast<const float4*>(g) + ((threadIdx.x >> 7) * 8) * 128 + (threadIdx.x & 127);
 #pragma unroll
-  for (int i = 0; i < 8; ++i) v[i] = __ldg(gp + i * 128);
+  for (int i = 0; i < 8; ++i) v[i] = gp[i * 128];
 }
 template <int L> __device__ __forceinline__ void op_put_x8(const TcCtx& c, const float4 (&v)[8]) {
 #pragma unroll
   for (int i = 0; i < 8; ++i) op_put4<L>(c, c.half * 32 + 4 * i, v[i].x, v[i].y, v[i].z, v[i].w);
 }
-template <int L> __device__ __forceinline__ void op_load_rows64(const TcCtx& c, const float* __restrict__ g /*tile base, row4 layout*/) {
+template <int L> __device__ __forceinline__ void op_load_rows64(const TcCtx& c, const float* g /*tile base, row4 layout*/) {
   float4 v[8];
   ld_rows_x8(g, v);                                             // all loads in flight before the first use
   op_put_x8<L>(c, v);
 }
 // a block of `bw` rows (64 or 32) of a plain tile-SoA array [row][128] -> operand columns [0,bw)
-template <int L> __device__ __forceinline__ void op_load_rows_bw(const TcCtx& c, const float* __restrict__ g, int bw) {
+template <int L> __device__ __forceinline__ void op_load_rows_bw(const TcCtx& c, const float* g, int bw) {
   if (bw == 64) {      // plain tile-SoA rows [row][128] (w0 / dw0 are indexed by channel in the tensor-product drivers)
     float v[32];
     const float* gp = g + (c.half * 32) * 128 + c.m;
 #pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = __ldg(gp + i * 128);
+    for (int i = 0; i < 32; ++i) v[i] = gp[i * 128];
 #pragma unroll
     for (int i = 0; i < 32; i += 4) op_put4<L>(c, c.half * 32 + i, v[i], v[i + 1], v[i + 2], v[i + 3]);
     return;
@@ -342,7 +341,7 @@ template <int L> __device__ __forceinline__ void op_load_rows_bw(const TcCtx& c,
   float v[16];
   const float* gp = g + (c.half * 16) * 128 + c.m;
 #pragma unroll
-  for (int i = 0; i < 16; ++i) v[i] = __ldg(gp + i * 128);
+  for (int i = 0; i < 16; ++i) v[i] = gp[i * 128];
 #pragma unroll
   for (int i = 0; i < 16; i += 4) op_put4<L>(c, c.half * 16 + i, v[i], v[i + 1], v[i + 2], v[i + 3]);
 }
@@ -358,7 +357,7 @@ __device__ __forceinline__ void ld_rows32(const TcCtx& c, const float* g, float*
 }
 
 // all threads; c_s must be published.  Ends with a barrier.
-template <int L> __device__ __forceinline__ RowSrc tc_stage_rows(const TcCtx& c, const float* __restrict__ gbase, int c0, int nvalid) {
+template <int L> __device__ __forceinline__ RowSrc tc_stage_rows(const TcCtx& c, const float* gbase, int c0, int nvalid) {
   using D = DimsTC<L>; using SM = SmemTC<L>;
   const int* c_s = reinterpret_cast<const int*>(c.sm + SM::oC);
   const int cmin = c_s[0];
@@ -437,7 +436,7 @@ template <int L> __device__ __forceinline__ void tc_env_to_ws(const TcCtx& c, ui
 }
 // Gamma partial sums of the features whose l lies in block b (columns of W_s = (l-2b)*U+u)
 template <int L> __device__ __forceinline__ void tc_env_sum(const ChunkArgs& a, const ModelW& w, const TcCtx& c, int tile, int es, int b,
-                                                             float* __restrict__ gamma) {
+                                                             float* gamma) {
   using D = DimsTC<L>; using SM = SmemTC<L>; constexpr int TM = 128;
   const float* W_s = c.sm + SM::oWS;
   const float* Y_s = c.sm + SM::oY;
@@ -464,11 +463,11 @@ template <int L> __device__ __forceinline__ void tc_env_sum(const ChunkArgs& a, 
     }
     for (; e < e1; ++e) acc += wcol[e * D::WS] * ycol[e];
     const int fg = lm * U + u;
-    if (sgm == 0 && contin) carry[fg] = acc * sc; else gamma[(size_t)(c_s[e0] - a.c0) * D::F + fg] = acc * sc;
+    if (sgm == 0 && contin) carry[fg] = acc * sc; else gamma[(size_t)(c_s[e0] - c.c0) * D::F + fg] = acc * sc;
   }
 }
 // env-weight accumulators (block 0 in TMEM columns col0, block 1 in col1) -> Gamma
-template <int L> __device__ __forceinline__ void tc_env_finish(const ChunkArgs& a, const ModelW& w, TcCtx& c, int tile, int es, float* __restrict__ gamma,
+template <int L> __device__ __forceinline__ void tc_env_finish(const ChunkArgs& a, const ModelW& w, TcCtx& c, int tile, int es, float* gamma,
                                                                 uint32_t col0, uint32_t col1) {
   using D = DimsTC<L>;
 #pragma unroll 1
@@ -483,7 +482,7 @@ template <int L> __device__ __forceinline__ void tc_env_finish(const ChunkArgs& 
 // l_max = 2, env[1] requested into weight buffer 2 (tc_load_w2): both blocks run as one MMA group.  W_s aliases
 // weight buffer 2 and is only written after the group has completed.
 template <int L> __device__ __forceinline__ void tc_env_all(const ChunkArgs& a, const ModelW& w, TcCtx& c, const TcMat* env, int tile, int es,
-                                                             float* __restrict__ gamma) {
+                                                             float* gamma) {
   using D = DimsTC<L>;
   if constexpr (D::NB == 1) tc_mma<L>(c, 64, D::bw(0), TC_ACC);
   else tc_mma_pair<L>(c, 64, D::bw(0), TC_ACC, D::bw(1), TC_ACC2);
@@ -641,8 +640,8 @@ __device__ __forceinline__ void tc_tp_forward(const ChunkArgs& a, const LayerW& 
 // ds is read from DS_s ([q*U+u][128]); dG staged in the OPH/OPL regions.
 template <int L, char KIND, bool FIRST, bool HAS_DVOUT>
 __device__ __forceinline__ void tc_tp_backward(const ChunkArgs& a, const LayerW& lw, const TcCtx& c, int tile, int k, int es, int nvalid,
-                                               const float* __restrict__ dVnext, float* __restrict__ dVprev,
-                                               float* __restrict__ dgamma_out, float* dYp, const RowSrc& gsrc) {
+                                               const float* dVnext, float* dVprev,
+                                               float* dgamma_out, float* dYp, const RowSrc& gsrc) {
   using D = DimsTC<L>; using SM = SmemTC<L>; using TP = tpgen::TP<L, KIND>; constexpr int TM = 128;
   constexpr int TB = D::TB;
   constexpr int BPP = D::CHU / D::CPH / TB;           // batches per pass
@@ -736,7 +735,7 @@ __device__ __forceinline__ void tc_tp_backward(const ChunkArgs& a, const LayerW&
           [&](int centre, int f, bool first, float v) {
             const int lm = f / D::CHU, ul = f % D::CHU;
             const int fg = lm * U + pass * D::CHU + ul;
-            if (first && contin) carry[fg] = v; else dgamma_out[(size_t)(centre - a.c0) * D::F + fg] = v;
+            if (first && contin) carry[fg] = v; else dgamma_out[(size_t)(centre - c.c0) * D::F + fg] = v;
           });
     }
     __syncthreads();
@@ -776,7 +775,7 @@ constexpr int ZD_ROWS = 3 * 64;
 // leaves z2 and m (pre-envelope output) in TMEM, requests `next`.  With STORE the activation
 // derivatives are written to `zd` so that the backward kernels need no recomputation.
 template <int L, bool STORE, class Bias>
-__device__ __forceinline__ void tc_mlp_hidden_fwd(TcCtx& c, const TcMat& w2, const TcMat& next, Bias bias, float* __restrict__ zd = nullptr) {
+__device__ __forceinline__ void tc_mlp_hidden_fwd(TcCtx& c, const TcMat& w2, const TcMat& next, Bias bias, float* zd = nullptr) {
   constexpr int TM = 128;
   tc_epi(c, TC_Z1, 64, [&](int n, float v0, float v1, float v2, float v3) {
     if constexpr (STORE) {
@@ -877,7 +876,7 @@ __device__ __forceinline__ void tc_din(TcCtx& c, const TcLayerW& tl, float* dXg)
 // Requests `next` before the last epilogue.
 template <int L, class Pre>
 __device__ __forceinline__ void tc_phase2(const ChunkArgs& a, const ModelW& w, TcCtx& c, const TcLayerW& tl, const TcMat* emb_b, int tile,
-                                          const float* __restrict__ Xtile, const TcMat& next, const RowSrc& dsrc, float* dxacc, Pre pre) {
+                                          const float* Xtile, const TcMat& next, const RowSrc& dsrc, float* dxacc, Pre pre) {
   using D = DimsTC<L>; using SM = SmemTC<L>; constexpr int TM = 128;
   const float* Y_s = c.sm + SM::oY;
   const int* c_s = reinterpret_cast<const int*>(c.sm + SM::oC);
@@ -953,19 +952,14 @@ __device__ __forceinline__ void tc_phase2(const ChunkArgs& a, const ModelW& w, T
 // ============================================================================================
 // F0
 // ============================================================================================
+// Every phase is a device function ("body") that starts from the published tile geometry (Y_s, u_s, c_s, zz_s, segment
+// table; see tc_tile_begin) and the per-thread Geom: the chunked pipeline wraps each body in its own kernel (tile =
+// blockIdx.x), the fused persistent kernel (k_fused_tc) runs all bodies of a tile back to back in one CTA.
+// `tile` indexes the per-tile scratch arrays (chunk tile number, or the CTA slot in the fused kernel).
 template <int L>
-__global__ void __launch_bounds__(NT, 2) k_f0_tc(const __grid_constant__ ChunkArgs a, const __grid_constant__ ModelW w, const __grid_constant__ TcW tw) {
+__device__ __forceinline__ void f0_body(const ChunkArgs& a, const ModelW& w, const TcW& tw, TcCtx& c, const Geom& g, int tile, int es, int nvalid) {
   using D = DimsTC<L>; using SM = SmemTC<L>; constexpr int TM = 128;
-  extern __shared__ __align__(1024) float sm_raw[];
-  const int tile = blockIdx.x;
-  const int es = a.e0 + tile * TM;
-  const int nvalid = min(TM, a.e1 - es);
-  const GeomIn gi = tc_geom_load(a, es, nvalid);
-  TcCtx c = tc_begin<L>(sm_raw, tw);
   tc_load_w<L>(c, tw.two0);
-  const Geom g = tc_geom<L>(a, w, c, gi);
-  __syncthreads();
-  seg_build<TM>(reinterpret_cast<const int*>(c.sm + SM::oC), nvalid, reinterpret_cast<int*>(c.sm + SM::oSEG));
   {  // Bessel*u -> operand columns [0,32) (zero padded beyond num_bessels)
     // sin((n+1) theta) by the Chebyshev recurrence s_{n+1} = 2 cos(theta) s_n - s_{n-1}: one sincosf per edge
     if (c.half == 0) {
@@ -1017,7 +1011,7 @@ __global__ void __launch_bounds__(NT, 2) k_f0_tc(const __grid_constant__ ChunkAr
       // l_max = 1: emb (buffer 1) and env_0 (buffer 2) as one MMA group
       tc_mma_pair<L>(c, 64, D::bw(0), TC_ACC, D::bw(0), TC_ACC2);
       w0_store(0, TC_ACC);
-      tc_env_finish<L>(a, w, c, tile, es, a.gamma[0], TC_ACC2, TC_ACC2);
+      tc_env_finish<L>(a, w, c, tile, es, (a.gamma[0] + c.goff), TC_ACC2, TC_ACC2);
     } else {
       // l_max = 2: the two emb blocks as one group, then the two env blocks
       tc_mma_pair<L>(c, 64, D::bw(0), TC_ACC, D::bw(1), TC_ACC2);
@@ -1025,9 +1019,32 @@ __global__ void __launch_bounds__(NT, 2) k_f0_tc(const __grid_constant__ ChunkAr
       tc_load_w2<L>(c, tw.layer[0].env[1]);
       w0_store(0, TC_ACC);
       w0_store(1, TC_ACC2);
-      tc_env_all<L>(a, w, c, tw.layer[0].env, tile, es, a.gamma[0]);
+      tc_env_all<L>(a, w, c, tw.layer[0].env, tile, es, (a.gamma[0] + c.goff));
     }
   }
+  (void)nvalid;
+}
+// geometry of the tile -> shared memory (Y_s, u_s, c_s, zz_s) + segment table; returns this thread's Geom
+template <int L>
+__device__ __forceinline__ Geom tc_tile_begin(const ChunkArgs& a, const ModelW& w, const TcCtx& c, const GeomIn& gi, int nvalid) {
+  using SM = SmemTC<L>;
+  const Geom g = tc_geom<L>(a, w, c, gi);
+  __syncthreads();
+  seg_build<128>(reinterpret_cast<const int*>(c.sm + SM::oC), nvalid, reinterpret_cast<int*>(c.sm + SM::oSEG));
+  return g;
+}
+template <int L>
+__global__ void __launch_bounds__(NT, 2) k_f0_tc(const __grid_constant__ ChunkArgs a, const __grid_constant__ ModelW w, const __grid_constant__ TcW tw) {
+  constexpr int TM = 128;
+  extern __shared__ __align__(1024) float sm_raw[];
+  const int tile = blockIdx.x;
+  const int es = a.e0 + tile * TM;
+  const int nvalid = min(TM, a.e1 - es);
+  const GeomIn gi = tc_geom_load(a, es, nvalid);
+  TcCtx c = tc_begin<L>(sm_raw, tw);
+  c.c0 = a.c0;
+  const Geom g = tc_tile_begin<L>(a, w, c, gi, nvalid);
+  f0_body<L>(a, w, tw, c, g, tile, es, nvalid);
   tc_end(c);
 }
 
@@ -1035,7 +1052,7 @@ __global__ void __launch_bounds__(NT, 2) k_f0_tc(const __grid_constant__ ChunkAr
 // in: weight block m0s[0] requested, geometry published.  out: z1 in TMEM, m1 requested.
 template <int L, char KIND, bool FIRST, bool WANT_V>
 __device__ __forceinline__ void tc_latent_z1(const ChunkArgs& a, const LayerW& lw, const TcLayerW& tl, TcCtx& c, int tile, int k,
-                                             const float* __restrict__ Xg, const RowSrc& gsrc) {
+                                             const float* Xg, const RowSrc& gsrc) {
   using D = DimsTC<L>;
   float4 xv[8];                                       // x^k rows: loads fly during the last s-block MMA
   tc_tp_forward<L, KIND, FIRST, WANT_V>(a, lw, c, tile, k, gsrc, 0);
@@ -1057,24 +1074,13 @@ __device__ __forceinline__ void tc_latent_z1(const ChunkArgs& a, const LayerW& l
 // FK
 // ============================================================================================
 template <int L, char KIND, bool FIRST>
-__global__ void __launch_bounds__(NT, 2) k_fk_tc(const __grid_constant__ ChunkArgs a, const __grid_constant__ ModelW w, const __grid_constant__ TcW tw, const int k) {
-  using D = DimsTC<L>; using SM = SmemTC<L>; constexpr int TM = 128;
-  extern __shared__ __align__(1024) float sm_raw[];
-  const int tile = blockIdx.x;
-  const int es = a.e0 + tile * TM;
-  const int nvalid = min(TM, a.e1 - es);
-  const GeomIn gi = tc_geom_load(a, es, nvalid);
-  tc_prefetch(a.X[k] + (size_t)tile * S * TM, S * TM);
-  tc_prefetch_row<L>(a.gamma[k], a.c0, gi);
-  TcCtx c = tc_begin<L>(sm_raw, tw);
+__device__ __forceinline__ void fk_body(const ChunkArgs& a, const ModelW& w, const TcW& tw, TcCtx& c, const Geom& g, int tile, int es, int nvalid, const int k) {
+  using D = DimsTC<L>; constexpr int TM = 128;
   const LayerW& lw = w.layer[k];
   const TcLayerW& tl = tw.layer[k];
   tc_load_w<L>(c, tl.m0s[0]);
-  const Geom g = tc_geom<L>(a, w, c, gi);
   const float* Xg = a.X[k] + (size_t)tile * S * TM;
-  __syncthreads();
-  seg_build<TM>(reinterpret_cast<const int*>(c.sm + SM::oC), nvalid, reinterpret_cast<int*>(c.sm + SM::oSEG));
-  const RowSrc gsrc = tc_stage_rows<L>(c, a.gamma[k], a.c0, nvalid);
+  const RowSrc gsrc = tc_stage_rows<L>(c, (a.gamma[k] + c.goff), c.c0, nvalid);
   tc_latent_z1<L, KIND, FIRST, true>(a, lw, tl, c, tile, k, Xg, gsrc);
   float* zd = a.ZD[k + 1] + (size_t)tile * ZD_ROWS * TM;
   tc_mlp_hidden_fwd<L, true>(c, tl.m2, tw.layer[k + 1].env[0], NoBias(), zd);
@@ -1092,16 +1098,11 @@ __global__ void __launch_bounds__(NT, 2) k_fk_tc(const __grid_constant__ ChunkAr
       st_row4(Xng, n, c.m, x0, x1, x2, x3);
     });
   }
-  tc_env_all<L>(a, w, c, tw.layer[k + 1].env, tile, es, a.gamma[k + 1]);
-  tc_end(c);
+  tc_env_all<L>(a, w, c, tw.layer[k + 1].env, tile, es, (a.gamma[k + 1] + c.goff));
 }
-
-// ============================================================================================
-// T
-// ============================================================================================
-template <int L, bool FIRST>
-__global__ void __launch_bounds__(NT, 2) k_t_tc(const __grid_constant__ ChunkArgs a, const __grid_constant__ ModelW w, const __grid_constant__ TcW tw, const int k) {
-  using D = DimsTC<L>; using SM = SmemTC<L>; constexpr int TM = 128;
+template <int L, char KIND, bool FIRST>
+__global__ void __launch_bounds__(NT, 2) k_fk_tc(const __grid_constant__ ChunkArgs a, const __grid_constant__ ModelW w, const __grid_constant__ TcW tw, const int k) {
+  constexpr int TM = 128;
   extern __shared__ __align__(1024) float sm_raw[];
   const int tile = blockIdx.x;
   const int es = a.e0 + tile * TM;
@@ -1110,25 +1111,29 @@ __global__ void __launch_bounds__(NT, 2) k_t_tc(const __grid_constant__ ChunkArg
   tc_prefetch(a.X[k] + (size_t)tile * S * TM, S * TM);
   tc_prefetch_row<L>(a.gamma[k], a.c0, gi);
   TcCtx c = tc_begin<L>(sm_raw, tw);
+  c.c0 = a.c0;
+  const Geom g = tc_tile_begin<L>(a, w, c, gi, nvalid);
+  fk_body<L, KIND, FIRST>(a, w, tw, c, g, tile, es, nvalid, k);
+  tc_end(c);
+}
+
+// ============================================================================================
+// T
+// ============================================================================================
+template <int L, bool FIRST>
+__device__ __forceinline__ void t_body(const ChunkArgs& a, const ModelW& w, const TcW& tw, TcCtx& c, const Geom& g, int tile, int es, int nvalid, const int k) {
+  using D = DimsTC<L>; using SM = SmemTC<L>; constexpr int TM = 128;
   const LayerW& lw = w.layer[k];
   const TcLayerW& tl = tw.layer[k];
-  ALG_TS(a, 2, 0);
   tc_load_w<L>(c, tl.m0s[0]);
-  const Geom g = tc_geom<L>(a, w, c, gi);
   const float* Xg = a.X[k] + (size_t)tile * S * TM;
-  __syncthreads();
-  seg_build<TM>(reinterpret_cast<const int*>(c.sm + SM::oC), nvalid, reinterpret_cast<int*>(c.sm + SM::oSEG));
-  ALG_TS(a, 2, 1);
   const int* c_s = reinterpret_cast<const int*>(c.sm + SM::oC);
-  const RowSrc gsrc = tc_stage_rows<L>(c, a.gamma[k], a.c0, nvalid);
-  ALG_TS(a, 2, 2);
+  const RowSrc gsrc = tc_stage_rows<L>(c, (a.gamma[k] + c.goff), c.c0, nvalid);
   tc_latent_z1<L, 'A', FIRST, false>(a, lw, tl, c, tile, k, Xg, gsrc);
-  ALG_TS(a, 2, 3);
   // act'(z1), act'(z2), m of this layer: written and read back by the same thread (the accumulators and the
   // A operand occupy all of this CTA's tensor memory)
   float* zd = a.ZD[k + 1] + (size_t)tile * ZD_ROWS * TM;
   tc_mlp_hidden_fwd<L, true>(c, tl.m2, tw.ro0, NoBias(), zd);
-  ALG_TS(a, 2, 4);
   {
     float xp[32];
     ld_rows32(c, Xg, xp);
@@ -1139,9 +1144,7 @@ __global__ void __launch_bounds__(NT, 2) k_t_tc(const __grid_constant__ ChunkArg
                  lw.a * xp[j + 2] + lw.b * v2 * g.u, lw.a * xp[j + 3] + lw.b * v3 * g.u);
     });
   }
-  ALG_TS(a, 2, 5);
   tc_mma<L>(c, 64, R, TC_SCR);                       // readout hidden
-  ALG_TS(a, 2, 6);
   tc_load_w<L>(c, tw.ro0_b);
   float* e_s = c.sm + SM::oE;
   {
@@ -1161,11 +1164,9 @@ __global__ void __launch_bounds__(NT, 2) k_t_tc(const __grid_constant__ ChunkArg
     for (int i = 0; i < 16; i += 4) op_put4<L>(c, c.half * 16 + i, dz[i], dz[i + 1], dz[i + 2], dz[i + 3]);
     e_s[c.half * TM + c.m] = ee;
   }
-  ALG_TS(a, 2, 7);
   float mv[32];
   ld_rows32<true>(c, zd + 128 * TM, mv);             // m: in flight during the MMA
   tc_mma<L>(c, R, 64, TC_SCR);                       // dx^n = dz ro0^T   (the barrier inside orders e_s)
-  ALG_TS(a, 2, 8);
   tc_load_w<L>(c, tl.m2_b);
   if (c.half == 0) {
     const float ee = e_s[c.m] + e_s[TM + c.m];
@@ -1201,62 +1202,50 @@ __global__ void __launch_bounds__(NT, 2) k_t_tc(const __grid_constant__ ChunkArg
       if (sgm == 0 && contin) a.ecarry[tile] = acc; else a.esum[c_s[seg[sgm]]] = acc;
     }
   }
-  ALG_TS(a, 2, 9);
   tc_mlp_bwd_hidden_st<L, true>(c, tl.m1_b, tl.m0_bx, zd, &tl.m0_bs[0]);
-  ALG_TS(a, 2, 10);
   tc_din<L>(c, tl, dXg);
-  ALG_TS(a, 2, 11);
   float dYp[D::NSH];
-  tc_tp_backward<L, 'A', FIRST, false>(a, lw, c, tile, k, es, nvalid, nullptr, FIRST ? nullptr : a.dV[k & 1], a.dgamma[k], dYp, gsrc);
-  ALG_TS(a, 2, 12);
+  tc_tp_backward<L, 'A', FIRST, false>(a, lw, c, tile, k, es, nvalid, nullptr, FIRST ? nullptr : a.dV[k & 1], (a.dgamma[k] + c.goff), dYp, gsrc);
   for (int i = threadIdx.x; i < D::NSH * TM; i += NT) c.sm[SM::oDY + i] = 0.f;
   __syncthreads();
   tc_dy_store<L, true>(a, c, tile, dYp, FIRST);
-  ALG_TS(a, 2, 13);
+}
+template <int L, bool FIRST>
+__global__ void __launch_bounds__(NT, 2) k_t_tc(const __grid_constant__ ChunkArgs a, const __grid_constant__ ModelW w, const __grid_constant__ TcW tw, const int k) {
+  constexpr int TM = 128;
+  extern __shared__ __align__(1024) float sm_raw[];
+  const int tile = blockIdx.x;
+  const int es = a.e0 + tile * TM;
+  const int nvalid = min(TM, a.e1 - es);
+  const GeomIn gi = tc_geom_load(a, es, nvalid);
+  tc_prefetch(a.X[k] + (size_t)tile * S * TM, S * TM);
+  tc_prefetch_row<L>(a.gamma[k], a.c0, gi);
+  TcCtx c = tc_begin<L>(sm_raw, tw);
+  c.c0 = a.c0;
+  const Geom g = tc_tile_begin<L>(a, w, c, gi, nvalid);
+  t_body<L, FIRST>(a, w, tw, c, g, tile, es, nvalid, k);
   tc_end(c);
-  ALG_TS(a, 2, 14);
 }
 
 // ============================================================================================
 // BK
 // ============================================================================================
 template <int L, char KIND, bool FIRST>
-__global__ void __launch_bounds__(NT, 2) k_bk_tc(const __grid_constant__ ChunkArgs a, const __grid_constant__ ModelW w, const __grid_constant__ TcW tw, const int k) {
+__device__ __forceinline__ void bk_body(const ChunkArgs& a, const ModelW& w, const TcW& tw, TcCtx& c, const Geom& g, int tile, int es, int nvalid, const int k) {
   using D = DimsTC<L>; using SM = SmemTC<L>; constexpr int TM = 128;
-  extern __shared__ __align__(1024) float sm_raw[];
-  const int tile = blockIdx.x;
-  const int es = a.e0 + tile * TM;
-  const int nvalid = min(TM, a.e1 - es);
-  const GeomIn gi = tc_geom_load(a, es, nvalid);
   const float* Xn = a.X[k + 1] + (size_t)tile * S * TM;
-  float4 xv[8];
-  ld_rows_x8(Xn, xv);                                  // DRAM latency overlaps the CTA start-up and the geometry
-  tc_prefetch_row<L>(a.dgamma[k + 1], a.c0, gi);
-  tc_prefetch_row<L>(a.gamma[k], a.c0, gi);
-  tc_prefetch(a.dX + (size_t)tile * S * TM, S * TM);
-  tc_prefetch(a.ZD[k + 1] + (size_t)tile * ZD_ROWS * TM, ZD_ROWS * TM);
-  tc_prefetch(a.dY + (size_t)tile * D::NSH * TM, D::NSH * TM);
-  tc_prefetch(a.du + (size_t)tile * TM, TM);
-  TcCtx c = tc_begin<L>(sm_raw, tw);
   const LayerW& lw = w.layer[k];
   const TcLayerW& tl = tw.layer[k];
   tc_load_w<L>(c, tw.layer[k + 1].env[0]);
-  ALG_TS(a, 3, 0);
-  const Geom g = tc_geom<L>(a, w, c, gi);
-  op_put_x8<L>(c, xv);
-  __syncthreads();
-  seg_build<TM>(reinterpret_cast<const int*>(c.sm + SM::oC), nvalid, reinterpret_cast<int*>(c.sm + SM::oSEG));
-  ALG_TS(a, 3, 1);
+  op_load_rows64<L>(c, Xn);
   float* dXg = a.dX + (size_t)tile * S * TM;
-  const RowSrc dsrc = tc_stage_rows<L>(c, a.dgamma[k + 1], a.c0, nvalid);
-  ALG_TS(a, 3, 2);
+  const RowSrc dsrc = tc_stage_rows<L>(c, (a.dgamma[k + 1] + c.goff), c.c0, nvalid);
   float dxn[32];                                      // complete dx^{k+1} of this thread's 32 columns (kept in registers)
   const float* zd = a.ZD[k + 1] + (size_t)tile * ZD_ROWS * TM;      // act'(z1), act'(z2), m of layer k (written by FK)
   {
     float dp[32], mv[32];
     tc_phase2<L>(a, w, c, tw.layer[k + 1], nullptr, tile, Xn, tl.m2_b, dsrc, dxn,
                  [&] { ld_rows32(c, dXg, dp); ld_rows32(c, zd + 128 * TM, mv); });
-  ALG_TS(a, 3, 3);
     float dup = 0.f;
 #pragma unroll
     for (int i = 0; i < 32; i += 4) {
@@ -1277,17 +1266,32 @@ __global__ void __launch_bounds__(NT, 2) k_bk_tc(const __grid_constant__ ChunkAr
     __syncthreads();
     if (c.half == 0) a.du[(size_t)tile * TM + c.m] += dup + e_s[c.m];
   }
-  const RowSrc gsrc = tc_stage_rows<L>(c, a.gamma[k], a.c0, nvalid);    // dGamma rows are consumed (barrier above)
-  ALG_TS(a, 3, 4);
+  const RowSrc gsrc = tc_stage_rows<L>(c, (a.gamma[k] + c.goff), c.c0, nvalid);    // dGamma rows are consumed (barrier above)
   tc_mlp_bwd_hidden_st<L>(c, tl.m1_b, tl.m0_bx, zd, &tl.m0_bs[0]);
-  ALG_TS(a, 3, 5);
   tc_din<L>(c, tl, dXg);
-  ALG_TS(a, 3, 6);
   float dYp[D::NSH];
-  tc_tp_backward<L, KIND, FIRST, true>(a, lw, c, tile, k, es, nvalid, a.dV[(k + 1) & 1], FIRST ? nullptr : a.dV[k & 1], a.dgamma[k], dYp, gsrc);
-  ALG_TS(a, 3, 7);
+  tc_tp_backward<L, KIND, FIRST, true>(a, lw, c, tile, k, es, nvalid, a.dV[(k + 1) & 1], FIRST ? nullptr : a.dV[k & 1], (a.dgamma[k] + c.goff), dYp, gsrc);
   tc_dy_store<L, false>(a, c, tile, dYp, FIRST);
-  ALG_TS(a, 3, 8);
+}
+template <int L, char KIND, bool FIRST>
+__global__ void __launch_bounds__(NT, 2) k_bk_tc(const __grid_constant__ ChunkArgs a, const __grid_constant__ ModelW w, const __grid_constant__ TcW tw, const int k) {
+  using D = DimsTC<L>; constexpr int TM = 128;
+  extern __shared__ __align__(1024) float sm_raw[];
+  const int tile = blockIdx.x;
+  const int es = a.e0 + tile * TM;
+  const int nvalid = min(TM, a.e1 - es);
+  const GeomIn gi = tc_geom_load(a, es, nvalid);
+  tc_prefetch(a.X[k + 1] + (size_t)tile * S * TM, S * TM);
+  tc_prefetch_row<L>(a.dgamma[k + 1], a.c0, gi);
+  tc_prefetch_row<L>(a.gamma[k], a.c0, gi);
+  tc_prefetch(a.dX + (size_t)tile * S * TM, S * TM);
+  tc_prefetch(a.ZD[k + 1] + (size_t)tile * ZD_ROWS * TM, ZD_ROWS * TM);
+  tc_prefetch(a.dY + (size_t)tile * D::NSH * TM, D::NSH * TM);
+  tc_prefetch(a.du + (size_t)tile * TM, TM);
+  TcCtx c = tc_begin<L>(sm_raw, tw);
+  c.c0 = a.c0;
+  const Geom g = tc_tile_begin<L>(a, w, c, gi, nvalid);
+  bk_body<L, KIND, FIRST>(a, w, tw, c, g, tile, es, nvalid, k);
   tc_end(c);
 }
 
@@ -1295,30 +1299,13 @@ __global__ void __launch_bounds__(NT, 2) k_bk_tc(const __grid_constant__ ChunkAr
 // B0
 // ============================================================================================
 template <int L>
-__global__ void __launch_bounds__(NT, 2) k_b0_tc(const __grid_constant__ ChunkArgs a, const __grid_constant__ ModelW w, const __grid_constant__ TcW tw) {
+__device__ __forceinline__ void b0_body(const ChunkArgs& a, const ModelW& w, const TcW& tw, TcCtx& c, const Geom& g, int tile, int es, int nvalid) {
   using D = DimsTC<L>; using SM = SmemTC<L>; constexpr int TM = 128;
-  extern __shared__ __align__(1024) float sm_raw[];
-  const int tile = blockIdx.x;
-  const int es = a.e0 + tile * TM;
-  const int nvalid = min(TM, a.e1 - es);
-  const GeomIn gi = tc_geom_load(a, es, nvalid);
   const float* X0 = a.X[0] + (size_t)tile * S * TM;
-  float4 xv[8];
-  ld_rows_x8(X0, xv);                                  // DRAM latency overlaps the CTA start-up and the geometry
-  tc_prefetch_row<L>(a.dgamma[0], a.c0, gi);
-  tc_prefetch(a.dX + (size_t)tile * S * TM, S * TM);
-  tc_prefetch(a.ZD[0] + (size_t)tile * ZD_ROWS * TM, ZD_ROWS * TM);
-  tc_prefetch(a.W0 + (size_t)tile * D::ENVW * TM, D::ENVW * TM);
-  tc_prefetch(a.dY + (size_t)tile * D::NSH * TM, D::NSH * TM);
-  tc_prefetch(a.du + (size_t)tile * TM, TM);
-  TcCtx c = tc_begin<L>(sm_raw, tw);
   tc_load_w<L>(c, tw.layer[0].env[0]);
-  const Geom g = tc_geom<L>(a, w, c, gi);
   // ---- phase 2 of layer 0 and the embed backward: dx0 = dX + dw env0^T + dw0 emb^T
-  op_put_x8<L>(c, xv);
-  __syncthreads();
-  seg_build<TM>(reinterpret_cast<const int*>(c.sm + SM::oC), nvalid, reinterpret_cast<int*>(c.sm + SM::oSEG));
-  const RowSrc dsrc = tc_stage_rows<L>(c, a.dgamma[0], a.c0, nvalid);
+  op_load_rows64<L>(c, X0);
+  const RowSrc dsrc = tc_stage_rows<L>(c, (a.dgamma[0] + c.goff), c.c0, nvalid);
   float dx0[32];
   const float* dXg = a.dX + (size_t)tile * S * TM;
   const float* zd = a.ZD[0] + (size_t)tile * ZD_ROWS * TM;          // act'(z1 + bias), act'(z2), m0 of the two-body MLP (written by F0)
@@ -1431,6 +1418,88 @@ __global__ void __launch_bounds__(NT, 2) k_b0_tc(const __grid_constant__ ChunkAr
         if ((t & 31) == 0) atomicAdd(a.vacc + q, (unsigned long long)v);
       }
     }
+  }
+}
+template <int L>
+__global__ void __launch_bounds__(NT, 2) k_b0_tc(const __grid_constant__ ChunkArgs a, const __grid_constant__ ModelW w, const __grid_constant__ TcW tw) {
+  using D = DimsTC<L>; constexpr int TM = 128;
+  extern __shared__ __align__(1024) float sm_raw[];
+  const int tile = blockIdx.x;
+  const int es = a.e0 + tile * TM;
+  const int nvalid = min(TM, a.e1 - es);
+  const GeomIn gi = tc_geom_load(a, es, nvalid);
+  tc_prefetch(a.X[0] + (size_t)tile * S * TM, S * TM);
+  tc_prefetch_row<L>(a.dgamma[0], a.c0, gi);
+  tc_prefetch(a.dX + (size_t)tile * S * TM, S * TM);
+  tc_prefetch(a.ZD[0] + (size_t)tile * ZD_ROWS * TM, ZD_ROWS * TM);
+  tc_prefetch(a.W0 + (size_t)tile * D::ENVW * TM, D::ENVW * TM);
+  tc_prefetch(a.dY + (size_t)tile * D::NSH * TM, D::NSH * TM);
+  tc_prefetch(a.du + (size_t)tile * TM, TM);
+  TcCtx c = tc_begin<L>(sm_raw, tw);
+  c.c0 = a.c0;
+  const Geom g = tc_tile_begin<L>(a, w, c, gi, nvalid);
+  b0_body<L>(a, w, tw, c, g, tile, es, nvalid);
+  tc_end(c);
+}
+
+// ============================================================================================
+// Fused persistent kernel: centre-aligned tiles (every centre's CSR row lies inside ONE tile of <= 128 edges, plan built on
+// the device by k_plan_*), one CTA walks tiles t = blockIdx.x, blockIdx.x + gridDim.x, ... and runs ALL phases of a tile
+// (F0, FK.., T, BK.., B0) back to back.  Environment sums are complete inside the tile, so there are no kernel boundaries
+// and no carries; the inter-phase state (x^k, w0, V^k, activation record, dX, dV, dY, du, Gamma/dGamma rows) lives in
+// CTA-private scratch ("slot" = blockIdx.x) that is rewritten for every tile and therefore stays in L2: DRAM traffic is
+// the edge list in and the force/energy accumulators out.  TMEM, the mbarriers and the geometry are set up once per CTA /
+// once per tile instead of once per phase.
+// ============================================================================================
+struct FusedPlan {
+  const int* tile_c0;     // [ntiles + 1] first centre slot of every tile (tile_c0[ntiles] = nlocal)
+  const int* info;        // [0] = ntiles, [1] = max degree, [2] = E, [3] = edge capacity overflow flag
+  int max_rows;           // 128
+};
+template <int L, int NLAYERS>
+__global__ void __launch_bounds__(NT, 2) k_fused_tc(const __grid_constant__ ChunkArgs a, const __grid_constant__ ModelW w, const __grid_constant__ TcW tw,
+                                                    const __grid_constant__ FusedPlan plan) {
+  using D = DimsTC<L>; constexpr int TM = 128;
+  extern __shared__ __align__(1024) float sm_raw[];
+  const int ntiles = plan.info[0];
+  if (plan.info[1] > TM || plan.info[3] != 0) return;          // a centre with more than 128 edges / edge arrays too small: the host falls back
+  if ((int)blockIdx.x >= ntiles) return;
+  TcCtx c = tc_begin<L>(sm_raw, tw);
+  const int slot = blockIdx.x;
+  c.goff = (size_t)slot * TM * D::F;
+#pragma unroll 1
+  for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+    const int c0 = plan.tile_c0[t], c1 = plan.tile_c0[t + 1];
+    const int es = a.rowptr[c0];
+    const int nvalid = a.rowptr[c1] - es;
+    if (nvalid <= 0) continue;                                  // only centres without neighbours
+    c.c0 = c0;
+    const GeomIn gi = tc_geom_load(a, es, nvalid);
+    const Geom g = tc_tile_begin<L>(a, w, c, gi, nvalid);
+    f0_body<L>(a, w, tw, c, g, slot, es, nvalid);
+    __syncthreads();
+    if constexpr (NLAYERS == 1) {
+      t_body<L, true>(a, w, tw, c, g, slot, es, nvalid, 0);
+    } else if constexpr (NLAYERS == 2) {
+      fk_body<L, 'B', true>(a, w, tw, c, g, slot, es, nvalid, 0);
+      __syncthreads();
+      t_body<L, false>(a, w, tw, c, g, slot, es, nvalid, 1);
+      __syncthreads();
+      bk_body<L, 'B', true>(a, w, tw, c, g, slot, es, nvalid, 0);
+    } else {
+      fk_body<L, 'C', true>(a, w, tw, c, g, slot, es, nvalid, 0);
+      __syncthreads();
+      fk_body<L, 'D', false>(a, w, tw, c, g, slot, es, nvalid, 1);
+      __syncthreads();
+      t_body<L, false>(a, w, tw, c, g, slot, es, nvalid, 2);
+      __syncthreads();
+      bk_body<L, 'D', false>(a, w, tw, c, g, slot, es, nvalid, 1);
+      __syncthreads();
+      bk_body<L, 'C', true>(a, w, tw, c, g, slot, es, nvalid, 0);
+    }
+    __syncthreads();
+    b0_body<L>(a, w, tw, c, g, slot, es, nvalid);
+    __syncthreads();
   }
   tc_end(c);
 }

@@ -18,8 +18,12 @@ from . import capi
 
 
 class PairAllegroB200:
-    def __init__(self, device=0, debug_mode=None):
+    def __init__(self, device=0, debug_mode=None, pin_host=False):
         # pair_nequip_allegro.cpp:66-125
+        # pin_host: let the library cudaHostRegister the x / f / type arrays it is handed (what the C++ pair style does
+        # for LAMMPS' long-lived atom arrays).  Off by default here: numpy arrays of a test may be freed and re-allocated
+        # at the same address between two calls, which a cached registration cannot see.
+        self.pin_host = pin_host
         self.restartinfo = 0
         self.manybody_flag = 1
         self.device = device
@@ -91,6 +95,7 @@ class PairAllegroB200:
         else:
             self.cutoff_matrix[:, :] = self.cutoff
         self.handle.set_type_map(self.type_mapper, self.cutoff_matrix)
+        self.handle.set_option("host_register", "1" if self.pin_host else "0")
         if self.debug_mode:
             self.handle.set_option("keep_edges", "1")
 

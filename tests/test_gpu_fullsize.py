@@ -65,7 +65,8 @@ def test_c2_full_size_properties(c2, ensure_built, tmp_path):
     tc2 = _run(atoms, lst, alg, gemm="tc")
     assert np.array_equal(tc["f"], tc2["f"]) and np.array_equal(tc["e"], tc2["e"]) and tc["pe"] == tc2["pe"]
     # chunking only regroups per-centre sums: results agree to fp32 round-off
-    sm = _run(atoms, lst, alg, gemm="tc", chunk_edges=str(1 << 19))
+    # (tc = the fused persistent kernel, the default; sm = the chunked edge-tile pipeline in small chunks)
+    sm = _run(atoms, lst, alg, gemm="tc", pipeline="tiled", chunk_edges=str(1 << 19))
     assert np.abs(sm["f"] - tc["f"]).max() < 2e-5
     np.testing.assert_allclose(sm["e"], tc["e"], rtol=2e-6, atol=2e-6)
     # the two pipelines (tensor core 3xTF32 / FP32 pipe) agree within the strict tolerances

@@ -58,7 +58,7 @@ def test_halo_pack_unpack_and_device_step(ensure_built):
 def test_stats_and_timings(ensure_built):
     name = "CuPd_r5"
     atom, lst, z = load_golden(name)
-    pair = make_pair(name, z, atom, profile="1", chunk_edges="4096")
+    pair = make_pair(name, z, atom, profile="1", chunk_edges="4096", pipeline="tiled")
     pair.compute(atom, lst)
     h = pair.handle
     st = h.stats("step", 4)

@@ -20,6 +20,7 @@ def main():
     chunk = sys.argv[4] if len(sys.argv) > 4 else "1048576"
     gemm = sys.argv[5] if len(sys.argv) > 5 else "ffma"
     prec = sys.argv[6] if len(sys.argv) > 6 else "strict"
+    pipeline = sys.argv[7] if len(sys.argv) > 7 else "auto"
     pos, types, cell = H.fcc_box(ncell)
     t0 = time.time()
     atoms = H.make_single_rank(types, pos, cell, [True] * 3, 6.0)
@@ -35,6 +36,7 @@ def main():
     if gemm == "tc":
         pair.handle.set_option("precision", prec)
     pair.handle.set_option("profile", "1")
+    pair.handle.set_option("pipeline", pipeline)
     for it in range(4):
         atoms.f[:] = 0
         t0 = time.time()
@@ -43,7 +45,8 @@ def main():
         tm = pair.handle.timings()
         print("iter %d: wall %.1f ms  device: edges %.2f ms, network %.2f ms, finalize %.2f ms  -> %.3f Matom-steps/s (device)  eng %.6f" %
               (it, dt * 1e3, tm[0], tm[1], tm[2], atoms.nlocal / (tm.sum() * 1e-3) / 1e6, pair.eng_vdwl))
-    print("kernel ms:", dict(zip(["F0", "FK", "T", "BK", "B0", "fixup"], np.round(pair.handle.stats("kernel_ms", 6), 2))))
+    print("kernel ms:", dict(zip(["F0", "FK", "T", "BK", "B0", "fixup", "fused"], np.round(pair.handle.stats("kernel_ms", 7), 2))),
+          "pipeline:", pair.handle.stats("pipeline", 3), "step:", pair.handle.stats("step", 4))
 
 
 if __name__ == "__main__":
