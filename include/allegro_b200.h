@@ -69,7 +69,9 @@ ALG_API int alg_metadata(const alg_handle* h, double* r_max, int* num_types, con
 /* Replaces the tail of coeff() (pair_nequip_allegro.cpp:274-328; Kokkos copy
  * pair_nequip_allegro_kokkos.cpp:365-386): `lammps_type_to_model[t-1]` = model type index of
  * LAMMPS type t (type_mapper, -1 = unmapped), `cutoff_matrix` = ntypes x ntypes row-major,
- * indexed [centre LAMMPS type-1][neighbour LAMMPS type-1] (may be asymmetric). */
+ * indexed [centre LAMMPS type-1][neighbour LAMMPS type-1] (may be asymmetric).  An unmapped LAMMPS type is legal as
+ * long as no atom carries it (the reference fails inside the model's type embedding otherwise): a compute that meets
+ * such an atom builds no edge for it and returns ALG_EINVAL ("atom with a LAMMPS type that has no model type"). */
 ALG_API int alg_set_type_map(alg_handle* h, int ntypes, const int* lammps_type_to_model,
                      const double* cutoff_matrix);
 
@@ -82,6 +84,8 @@ ALG_API int alg_set_type_map(alg_handle* h, int ntypes, const int* lammps_type_t
  *                  per atom.  tiled = the chunked edge-tile pipeline (any neighbour count; one host synchronisation per
  *                  step on the CSR row pointer).  auto = fused, and tiled from the first step on that meets an atom
  *                  with more than 128 neighbours (that step is repeated transparently), or when debug=1.
+ *   "fused_batch"  fused pipeline: tiles a CTA takes from the tile queue at once and runs phase by phase (default 8; the
+ *                  code of one phase then stays in the instruction cache for the whole batch)
  *   "max_neighbors" alg_compute_device only: extent(1) of the caller's 2-D neighbour view.  Sizes the edge arrays to
  *                  nlocal*max_neighbors so that a fully asynchronous step can never overflow them; without it they
  *                  are sized from the previous step's edge count (+12.5 %), like the reference's 1.05 padding
@@ -174,6 +178,11 @@ ALG_API int alg_get_stats(alg_handle* h, const char* what, double* out, int n);
 ALG_API int alg_halo_pack(const double* d_x, const int* d_list, int n, const double* d_shift, double* d_buf,
                   void* stream);
 ALG_API int alg_halo_unpack_add(double* d_f, const int* d_list, int n, const double* d_buf, void* stream);
+
+/* Number of CUDA devices visible to this process (torch::cuda::device_count() in the reference's device
+ * selection, pair_nequip_allegro.cpp:102-118: rank >= count is an error, or wraps around in debug mode); returns 0
+ * when no device is usable (then alg_create fails with ALG_ECUDA -- there is no CPU fallback). */
+ALG_API int alg_device_count(void);
 
 /* library / build identification, e.g. "allegro_b200 0.1.0 sm_100a" */
 ALG_API const char* alg_version(void);

@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, "liballegro_b200.so")
 
 EXPORTS = ["alg_create", "alg_destroy", "alg_last_error", "alg_metadata", "alg_set_type_map", "alg_set_option",
            "alg_compute_host", "alg_compute_device", "alg_get_edges", "alg_get_output", "alg_get_timings", "alg_get_stats",
-           "alg_halo_pack", "alg_halo_unpack_add", "alg_version"]
+           "alg_halo_pack", "alg_halo_unpack_add", "alg_version", "alg_device_count"]
 
 _lib = None
 
@@ -66,6 +66,8 @@ def load_library(path=None):
     lib.alg_halo_pack.restype = C.c_int
     lib.alg_halo_unpack_add.argtypes = [vp, vp, C.c_int, vp, vp]
     lib.alg_halo_unpack_add.restype = C.c_int
+    lib.alg_device_count.argtypes = []
+    lib.alg_device_count.restype = C.c_int
     lib.alg_version.argtypes = []
     lib.alg_version.restype = C.c_char_p
     if path is None:

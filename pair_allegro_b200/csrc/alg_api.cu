@@ -101,6 +101,7 @@ struct alg_handle {
   int pipeline_mode = 0;                   // option pipeline: 0 = auto, 1 = fused, 2 = tiled
   bool force_tiled = false;                // sticky: a centre with more than 128 edges was seen -> chunked edge-tile pipeline
   int fused_grid = 0;                      // resident CTAs of the fused kernel on this device
+  int fused_batch = 8;                     // option fused_batch: tiles a CTA runs phase by phase before it takes the next batch
   long edge_cap_hint = 0;                  // upper bound on the edge count known to the caller path (0 = unknown)
   long max_neighbors = 0;                  // option max_neighbors: extent(1) of the caller's 2-D neighbour view
   long last_E_known = -1; int last_E_nlocal = -1;
@@ -187,8 +188,15 @@ static bool read_alg(const char* path, alg_handle* h, std::string& err) {
       ts >> name >> dt >> nd;
       HostTensor t; t.dtype = dt;
       for (int i = 0; i < nd; ++i) { long d; ts >> d; t.dims.push_back(d); }
-      long off, nb; ts >> off >> nb;
-      if (data_offset < 0 || data_offset + off + nb > sz) { err = "tensor " + name + " out of file bounds"; return false; }
+      long off = -1, nb = -1; ts >> off >> nb;
+      long cnt = 1;
+      bool dims_ok = nd >= 0 && nd <= 8 && (long)t.dims.size() == nd;
+      for (long d : t.dims) { if (d < 0 || (d > 0 && cnt > (1L << 40) / d)) dims_ok = false; else cnt *= d; }
+      const long esz = dt == "f32" ? 4 : (dt == "f64" ? 8 : (dt == "i32" ? 4 : (dt == "i64" ? 8 : 0)));
+      if (ts.fail() || !dims_ok || esz == 0) { err = "malformed tensor record '" + name + "' in weight file header"; return false; }
+      if (data_offset < 0 || off < 0 || nb < 0 || nb != cnt * esz || data_offset > sz || off > sz - data_offset || nb > sz - data_offset - off) {
+        err = "tensor " + name + " out of file bounds"; return false;
+      }
       t.data.assign(raw.begin() + data_offset + off, raw.begin() + data_offset + off + nb);
       h->tensors[name] = std::move(t);
     } else {
@@ -203,7 +211,7 @@ static const float* tf32(alg_handle* h, const std::string& name, long d0, long d
   if (it == h->tensors.end()) { err = "weight file misses tensor " + name; return nullptr; }
   const HostTensor& t = it->second;
   long n = 1; for (long d : t.dims) n *= d;
-  if (t.dtype != "f32" || n != d0 * d1) {
+  if (t.dtype != "f32" || n != d0 * d1 || t.data.size() != (size_t)n * sizeof(float)) {
     err = "tensor " + name + " has unexpected shape/dtype (expected " + std::to_string(d0) + "x" + std::to_string(d1) + " f32)";
     return nullptr;
   }
@@ -233,7 +241,7 @@ __device__ __forceinline__ double rsq_nofma(const double* __restrict__ x, int i,
 template <bool FILL>
 __global__ void k_edges(int nlocal, const double* __restrict__ x, const int* __restrict__ type, const int* __restrict__ ilist,
                         NeighAcc acc, const double* __restrict__ cutsq, int ntypes, int filter_le,
-                        int* __restrict__ cnt_out, const int* __restrict__ rowptr, const int* __restrict__ tmap,
+                        int* __restrict__ cnt_out, const int* __restrict__ rowptr, const int* __restrict__ mtype,
                         int* __restrict__ edge_j, int* __restrict__ edge_c, float4* __restrict__ rvec, long cap) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
@@ -246,7 +254,8 @@ __global__ void k_edges(int nlocal, const double* __restrict__ x, const int* __r
   else { n = acc.cnt[i]; ptr = acc.base + (long long)i * acc.stride_i; st = acc.stride_jj; }
   int total = 0;
   int base = FILL ? rowptr[ii] : 0;
-  const int zi = FILL ? tmap[ti] : 0;
+  const int zi = mtype[i];
+  if (zi < 0) n = 0;                                  // unmapped centre: no edges (the step reports the error, see k_mtype)
   for (int j0 = 0; j0 < n; j0 += 32) {
     const int jj = j0 + lane;
     bool keep = false;
@@ -255,7 +264,7 @@ __global__ void k_edges(int nlocal, const double* __restrict__ x, const int* __r
       j = ptr[(long long)jj * st] & NEIGHMASK;
       const double rsq = rsq_nofma(x, i, j, dx, dy, dz);
       const double c2 = cutsq[ti * ntypes + (type[j] - 1)];
-      keep = filter_le ? (rsq <= c2) : (rsq < c2);
+      keep = (filter_le ? (rsq <= c2) : (rsq < c2)) && mtype[j] >= 0;
     }
     const unsigned m = __ballot_sync(0xffffffffu, keep);
     if (FILL) {
@@ -264,7 +273,7 @@ __global__ void k_edges(int nlocal, const double* __restrict__ x, const int* __r
         if (pos >= cap) continue;                       // edge arrays too small (flagged by k_plan; the host retries)
         edge_j[pos] = j;
         edge_c[pos] = ii;
-        const int zj = tmap[type[j] - 1];
+        const int zj = mtype[j];
         rvec[pos] = make_float4((float)(-dx), (float)(-dy), (float)(-dz), __int_as_float(zi | (zj << 8)));
       }
       base += __popc(m);
@@ -327,9 +336,14 @@ __global__ void k_plan(int nlocal, const int* __restrict__ rowptr, int* __restri
   }
 }
 
-__global__ void k_mtype(int ntot, const int* __restrict__ type, const int* __restrict__ tmap, int* __restrict__ mtype) {
+// model type per atom; an atom whose LAMMPS type has no model type raises flags[0] (the step then fails with ALG_EINVAL)
+__global__ void k_mtype(int ntot, const int* __restrict__ type, const int* __restrict__ tmap, int ntypes, int* __restrict__ mtype, int* __restrict__ flags) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < ntot) mtype[i] = tmap[type[i] - 1];
+  if (i >= ntot) return;
+  const int t = type[i] - 1;
+  const int z = (t >= 0 && t < ntypes) ? tmap[t] : -1;
+  mtype[i] = z;
+  if (z < 0) flags[0] = 1 + i;
 }
 
 // finalize: fixed-point accumulators -> model forces (double), optionally f += ; per-atom energies
@@ -588,7 +602,12 @@ static int setup_model(alg_handle* h) {
 // ------------------------------------------------------------------------------------------
 // C-ABI
 // ------------------------------------------------------------------------------------------
-extern "C" const char* alg_version(void) { return "allegro_b200 0.1.0 sm_100a"; }
+extern "C" const char* alg_version(void) { return "allegro_b200 0.2.0 sm_100a"; }
+extern "C" int alg_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
 
 extern "C" const char* alg_last_error(const alg_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
 
@@ -697,6 +716,10 @@ extern "C" int alg_set_option(alg_handle* h, const char* key, const char* value)
       h->pipeline_mode = 1;
     } else if (v == "tiled") h->pipeline_mode = 2;
     else return fail(h, ALG_EINVAL, "pipeline must be auto, fused or tiled");
+  } else if (k == "fused_batch") {
+    const int b = atoi(v.c_str());
+    if (b < 1 || b > 64) return fail(h, ALG_EINVAL, "fused_batch must be in 1..64");
+    h->fused_batch = b;
   } else if (k == "max_neighbors") {
     h->max_neighbors = atol(v.c_str());
     if (h->max_neighbors < 0) return fail(h, ALG_EINVAL, "max_neighbors must be >= 0");
@@ -790,7 +813,7 @@ static void launch_edge_fill(alg_handle* h, const StepIO& io, long cap) {
   cudaStream_t st = h->stream;
   const int wblocks = (int)(((long)io.nlocal * 32 + 255) / 256);
   k_edges<true><<<wblocks, 256, 0, st>>>(io.nlocal, io.d_x, io.d_type, io.d_ilist, io.acc, h->d_cutsq.as<double>(), h->ntypes, h->filter_le ? 1 : 0,
-                                         nullptr, h->d_rowptr.as<int>(), h->d_tmap.as<int>(), h->d_edge_j.as<int>(), h->d_edge_c.as<int>(),
+                                         nullptr, h->d_rowptr.as<int>(), h->d_mtype.as<int>(), h->d_edge_j.as<int>(), h->d_edge_c.as<int>(),
                                          h->d_rvec.as<float4>(), cap);
   if (h->keep_edges)
     k_edge_index<<<1024, 256, 0, st>>>(h->d_rowptr.as<int>(), io.nlocal, cap, h->d_edge_j.as<int>(), h->d_edge_c.as<int>(), io.d_ilist,
@@ -866,7 +889,6 @@ static int step_fused(alg_handle* h, const StepIO& io, long cap) {
   CK(h->d_blk.ensure(sizeof(int) * (nblk + 1)));
   CK(h->d_blk_base.ensure(sizeof(int) * (nblk + 1)));
   CK(h->d_tile_c0.ensure(sizeof(int) * ((size_t)nlocal + nblk + 2)));
-  CK(h->d_info.ensure(sizeof(int) * 8));
   CK(cudaMemsetAsync(h->d_info.p, 0, sizeof(int) * 8, st));
   const int pb = (nblk + 127) / 128;
   k_plan<false><<<pb, 128, 0, st>>>(nlocal, h->d_rowptr.as<int>(), h->d_blk.as<int>(), nullptr, nullptr, h->d_info.as<int>(), cap);
@@ -879,12 +901,13 @@ static int step_fused(alg_handle* h, const StepIO& io, long cap) {
   CK(cudaGetLastError());
   CK(cudaEventRecord(h->ev[1], st));
   const int grid = h->fused_grid;
-  rc = ensure_chunk_buffers(h, grid, (long)grid * PLAN_ROWS);
+  const int batch = h->fused_batch;
+  rc = ensure_chunk_buffers(h, (long)grid * batch, (long)grid * batch * PLAN_ROWS);
   if (rc != ALG_OK) return rc;
   ChunkArgs a;
   fill_args(h, io, a);
   a.e0 = 0; a.e1 = 0; a.c0 = 0;
-  FusedPlan plan{h->d_tile_c0.as<int>(), h->d_info.as<int>(), PLAN_ROWS};
+  FusedPlan plan{h->d_tile_c0.as<int>(), h->d_info.as<int>(), PLAN_ROWS, batch};      // info[5] (tile queue) was zeroed above
   CK(h->pipe->run_fused(a, h->mw, &h->tcw, plan, grid, st, &h->prof));
   h->prof.launches += 2;                               // k_plan x2
   h->dbg_ntiles = 0; h->dbg_c0 = 0; h->dbg_ncent = 0;
@@ -898,6 +921,9 @@ static int resolve_pending(alg_handle* h) {
   h->info_pending = false;
   CK(cudaEventSynchronize(h->ev_info));
   const int* info = h->h_info.as<int>();
+  if (info[8] != 0)
+    return fail(h, ALG_EINVAL, "the previous asynchronous step met atom " + std::to_string(info[8] - 1) + " whose LAMMPS type has no model type");
+  if (!h->last_fused) return ALG_OK;
   h->last_E = info[2]; h->last_E_known = info[2];
   h->step_stats[1] = info[2]; h->step_stats[3] = info[0];
   if (info[1] > PLAN_ROWS) {
@@ -930,9 +956,11 @@ static int run_step(alg_handle* h, const StepIO& io, double* eng, double* virial
   CK(h->d_rowptr.ensure(sizeof(int) * (nlocal + 1)));
   CK(h->d_mtype.ensure(sizeof(int) * ntot));
   const int wblocks = (int)(((long)nlocal * 32 + 255) / 256);
-  k_mtype<<<(ntot + 255) / 256, 256, 0, st>>>(ntot, io.d_type, h->d_tmap.as<int>(), h->d_mtype.as<int>());
+  CK(h->d_info.ensure(sizeof(int) * 16));              // [0..3] fused tile plan (see k_plan), [8] 1 + index of an atom without model type
+  CK(cudaMemsetAsync(h->d_info.p, 0, sizeof(int) * 16, st));
+  k_mtype<<<(ntot + 255) / 256, 256, 0, st>>>(ntot, io.d_type, h->d_tmap.as<int>(), h->ntypes, h->d_mtype.as<int>(), h->d_info.as<int>() + 8);
   k_edges<false><<<wblocks, 256, 0, st>>>(nlocal, io.d_x, io.d_type, io.d_ilist, io.acc, h->d_cutsq.as<double>(), h->ntypes, h->filter_le ? 1 : 0,
-                                          h->d_cnt.as<int>(), nullptr, nullptr, nullptr, nullptr, nullptr, 0);
+                                          h->d_cnt.as<int>(), nullptr, h->d_mtype.as<int>(), nullptr, nullptr, nullptr, 0);
   CK(cudaMemsetAsync(h->d_cnt.as<int>() + nlocal, 0, sizeof(int), st));
   size_t tmp_bytes = 0;
   cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, h->d_cnt.as<int>(), h->d_rowptr.as<int>(), nlocal + 1, st);
@@ -946,7 +974,7 @@ static int run_step(alg_handle* h, const StepIO& io, double* eng, double* virial
   const int eblocks = (nlocal + 1023) / 1024;
   CK(h->d_red.ensure(sizeof(double) * (eblocks + 8)));
   CK(h->h_out.ensure(sizeof(double) * 8));
-  CK(h->h_info.ensure(sizeof(int) * 8));
+  CK(h->h_info.ensure(sizeof(int) * 16));
   const bool want_sync = eng || virial6 || io.h_f;
   bool fused = fused_selected(h);
   long cap = 0;
@@ -988,15 +1016,19 @@ static int run_step(alg_handle* h, const StepIO& io, double* eng, double* virial
     k_final_scalars<<<1, 32, 0, st>>>(eblocks, h->d_red.as<double>() + 8, h->d_vacc.as<unsigned long long>(), h->d_red.as<double>());
     CK(cudaGetLastError());
     CK(cudaEventRecord(h->ev[3], st));
-    if (fused) CK(cudaMemcpyAsync(h->h_info.p, h->d_info.p, sizeof(int) * 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(h->h_info.p, h->d_info.p, sizeof(int) * 16, cudaMemcpyDeviceToHost, st));
     if (!want_sync) {
-      if (fused) { CK(cudaEventRecord(h->ev_info, st)); h->info_pending = true; h->step_stats[1] = -1; h->step_stats[2] = 1; h->step_stats[3] = -1; }
+      CK(cudaEventRecord(h->ev_info, st)); h->info_pending = true;
+      if (fused) { h->step_stats[1] = -1; h->step_stats[2] = 1; h->step_stats[3] = -1; }
       return ALG_OK;
     }
     if (io.h_f) CK(cudaMemcpyAsync(io.h_f, io.d_f_inout, sizeof(double) * 3 * ntot, cudaMemcpyDeviceToHost, st));
     if (io.h_eatom_stage && io.eflag_atom) CK(cudaMemcpyAsync(io.h_eatom_stage, io.d_eatom, sizeof(double) * ntot, cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(h->h_out.p, h->d_red.p, sizeof(double) * 7, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
+    if (h->h_info.as<int>()[8] != 0)
+      return fail(h, ALG_EINVAL, "atom " + std::to_string(h->h_info.as<int>()[8] - 1) + " has a LAMMPS type that has no model type "
+                                 "(its name in pair_coeff matches no type name of the model)");
     if (fused) {
       const int* info = h->h_info.as<int>();
       h->last_E = info[2]; h->last_E_known = info[2];

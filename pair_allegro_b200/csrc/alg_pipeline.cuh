@@ -133,7 +133,8 @@ template <int L> cudaError_t init_tc_impl() {
   const int b = (int)SmemTC<L>::BYTES;
   cudaError_t e;
 #define ALG_SET(kern) \
-  if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, b)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, b)) != cudaSuccess) return e; \
+  if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared)) != cudaSuccess) return e;
   ALG_SET((k_f0_tc<L>));
   ALG_SET((k_fk_tc<L, 'B', true>));
   ALG_SET((k_fk_tc<L, 'C', true>));
@@ -151,15 +152,15 @@ template <int L> cudaError_t init_tc_impl() {
   return cudaSuccess;
 }
 template <int L> int fused_grid_tc_impl(int nl) {
-  int dev = 0, sms = 0, per_sm = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0;
-  cudaError_t e;
-  if (nl == 1) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fused_tc<L, 1>, NT, SmemTC<L>::BYTES);
-  else if (nl == 2) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fused_tc<L, 2>, NT, SmemTC<L>::BYTES);
-  else e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fused_tc<L, 3>, NT, SmemTC<L>::BYTES);
-  if (e != cudaSuccess || per_sm < 1) return 0;
-  if (per_sm > 2) per_sm = 2;                        // tensor memory: 256 of 512 columns per CTA
-  return sms * per_sm;
+  int dev = 0, sms = 0, smem_sm = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess ||
+      cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev) != cudaSuccess) return 0;
+  // resident CTAs per SM: shared memory (+1 KB the driver reserves per CTA), at most 2 (tensor memory: 256 of 512 columns per CTA;
+  // registers: 128 x 256 threads).  The kernel pulls tiles from a queue, so a smaller residency at run time only costs balance.
+  int per_sm = (int)(smem_sm / (SmemTC<L>::BYTES + 1024));
+  if (per_sm > 2) per_sm = 2;
+  (void)nl;
+  return per_sm < 1 ? 0 : sms * per_sm;
 }
 template <int L> cudaError_t run_fused_tc_impl(const ChunkArgs& a, const ModelW& w, const TcW* twp, const FusedPlan& plan, int grid, cudaStream_t st, Prof* pf) {
   const size_t sm = SmemTC<L>::BYTES;

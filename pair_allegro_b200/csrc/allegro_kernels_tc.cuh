@@ -26,6 +26,11 @@
 
 namespace alg {
 
+// the large building blocks: inlined.  (Measured on the B200: as real functions -- __noinline__, one copy each -- the
+// chunked pipeline went from 21.5 to 33.8 ms on a 256 k-atom box: the context struct lands in local memory and every
+// call spills the live accumulators.)
+#define ALG_NI __forceinline__
+
 struct TcMat { const float* hi; const float* lo; int N, K; };   // smem image: K/32 panels x N rows x 32 floats
 // every image is one MMA block: N <= 64 rows, K <= 64 columns (16 KB) so that a CTA needs only
 // ~104 KB of shared memory and two CTAs share an SM (their phases overlap)
@@ -79,8 +84,8 @@ template <int L> struct SmemTC {
   static constexpr int GSSTRIDE = D::F + 4;            // staged row stride: +4 floats so that the rows of different centres start in
                                                        // different banks (lanes of one warp read feature f of 1-3 distinct centres)
   static constexpr int oSEG = oGS + GSROWS * GSSTRIDE; // int: segment table seg[TM+1], nseg, warp counts (TM + 16 ints)
-  static constexpr int oBAR = oSEG + TM + 16;          // 3 mbarriers + tmem pointer (8 floats: mbar, wbar, tmem ptr, wbar2)
-  static constexpr int TOTAL = oBAR + 8;
+  static constexpr int oBAR = oSEG + TM + 16;          // 3 mbarriers + tmem pointer (8 floats: mbar, wbar, tmem ptr, wbar2), fused kernel: tile number
+  static constexpr int TOTAL = oBAR + 12;
   static constexpr size_t BYTES = (size_t)TOTAL * sizeof(float) + 1024;   // + alignment slack
   // buffers inside the scratch / weight regions (live ranges never overlap a weight block that is still in use)
   static constexpr int oWS = oOPL;                                 // env weights of one block, edge-major [128][65]
@@ -191,7 +196,7 @@ template <int L> __device__ __forceinline__ void tc_mma8(uint32_t td, uint32_t t
     umma::mma_tf32_ta(td, ta + 56, db + wpan + 6, idesc, 1);
   }
 }
-template <int L> __device__ __forceinline__ void tc_mma(TcCtx& c, int K, int N, uint32_t dcol, uint32_t accumulate = 0) {
+template <int L> __device__ ALG_NI void tc_mma(TcCtx& c, int K, int N, uint32_t dcol, uint32_t accumulate = 0) {
   using SM = SmemTC<L>;
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   if (warp == 0) umma::mbar_wait(c.wbar, c.wph);      // weight block landed (requested one epilogue ago)
@@ -228,7 +233,7 @@ template <int L> __device__ __forceinline__ void tc_mma(TcCtx& c, int K, int N, 
 
 // two GEMMs on the SAME A operand (K columns), weights in buffer 1 (N1 -> dcol1) and buffer 2 (N2 -> dcol2):
 // one barrier, one MMA group, one commit, one wake-up
-template <int L> __device__ __forceinline__ void tc_mma_pair(TcCtx& c, int K, int N1, uint32_t dcol1, int N2, uint32_t dcol2) {
+template <int L> __device__ ALG_NI void tc_mma_pair(TcCtx& c, int K, int N1, uint32_t dcol1, int N2, uint32_t dcol2) {
   using SM = SmemTC<L>;
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   if (warp == 0) { umma::mbar_wait(c.wbar, c.wph); umma::mbar_wait(c.wbar2, c.wph2); }
@@ -357,7 +362,7 @@ __device__ __forceinline__ void ld_rows32(const TcCtx& c, const float* g, float*
 }
 
 // all threads; c_s must be published.  Ends with a barrier.
-template <int L> __device__ __forceinline__ RowSrc tc_stage_rows(const TcCtx& c, const float* gbase, int c0, int nvalid) {
+template <int L> __device__ ALG_NI RowSrc tc_stage_rows(const TcCtx& c, const float* gbase, int c0, int nvalid) {
   using D = DimsTC<L>; using SM = SmemTC<L>;
   const int* c_s = reinterpret_cast<const int*>(c.sm + SM::oC);
   const int cmin = c_s[0];
@@ -467,7 +472,7 @@ template <int L> __device__ __forceinline__ void tc_env_sum(const ChunkArgs& a, 
   }
 }
 // env-weight accumulators (block 0 in TMEM columns col0, block 1 in col1) -> Gamma
-template <int L> __device__ __forceinline__ void tc_env_finish(const ChunkArgs& a, const ModelW& w, TcCtx& c, int tile, int es, float* gamma,
+template <int L> __device__ ALG_NI void tc_env_finish(const ChunkArgs& a, const ModelW& w, TcCtx& c, int tile, int es, float* gamma,
                                                                 uint32_t col0, uint32_t col1) {
   using D = DimsTC<L>;
 #pragma unroll 1
@@ -481,7 +486,7 @@ template <int L> __device__ __forceinline__ void tc_env_finish(const ChunkArgs& 
 // env linear of x (operand [0,64)) for all blocks -> Gamma.  In: weight block env[0] requested (buffer 1) and, for
 // l_max = 2, env[1] requested into weight buffer 2 (tc_load_w2): both blocks run as one MMA group.  W_s aliases
 // weight buffer 2 and is only written after the group has completed.
-template <int L> __device__ __forceinline__ void tc_env_all(const ChunkArgs& a, const ModelW& w, TcCtx& c, const TcMat* env, int tile, int es,
+template <int L> __device__ ALG_NI void tc_env_all(const ChunkArgs& a, const ModelW& w, TcCtx& c, const TcMat* env, int tile, int es,
                                                              float* gamma) {
   using D = DimsTC<L>;
   if constexpr (D::NB == 1) tc_mma<L>(c, 64, D::bw(0), TC_ACC);
@@ -574,7 +579,7 @@ template <int L, bool FIRST, int DIN> struct VinRaw {
 // With WANT_V (block 0 only) the full product is evaluated and V^{k+1} stored; otherwise only the
 // scalar paths (identical order in every kind: path q pairs irrep (q,(-1)^q) of V with l2 = q).
 template <int L, char KIND, bool FIRST, bool WANT_V>
-__device__ __forceinline__ void tc_tp_forward(const ChunkArgs& a, const LayerW& lw, const TcCtx& c, int tile, int k, const RowSrc& gsrc, int b) {
+__device__ ALG_NI void tc_tp_forward(const ChunkArgs& a, const LayerW& lw, const TcCtx& c, int tile, int k, const RowSrc& gsrc, int b) {
   using D = DimsTC<L>; using SM = SmemTC<L>; using TP = tpgen::TP<L, KIND>; using TPA = tpgen::TP<L, 'A'>; constexpr int TM = 128;
   constexpr int TB = D::TB;
   constexpr int NS = D::CPT / TB;
@@ -639,7 +644,7 @@ __device__ __forceinline__ void tc_tp_forward(const ChunkArgs& a, const LayerW& 
 // backward over all channels in passes of CHU, dG segmented sum -> dgamma_out.
 // ds is read from DS_s ([q*U+u][128]); dG staged in the OPH/OPL regions.
 template <int L, char KIND, bool FIRST, bool HAS_DVOUT>
-__device__ __forceinline__ void tc_tp_backward(const ChunkArgs& a, const LayerW& lw, const TcCtx& c, int tile, int k, int es, int nvalid,
+__device__ ALG_NI void tc_tp_backward(const ChunkArgs& a, const LayerW& lw, const TcCtx& c, int tile, int k, int es, int nvalid,
                                                const float* dVnext, float* dVprev,
                                                float* dgamma_out, float* dYp, const RowSrc& gsrc) {
   using D = DimsTC<L>; using SM = SmemTC<L>; using TP = tpgen::TP<L, KIND>; constexpr int TM = 128;
@@ -745,7 +750,7 @@ __device__ __forceinline__ void tc_tp_backward(const ChunkArgs& a, const LayerW&
 
 // dY: DY_s (phase-2 part, smem) + the two channel-halves' partials (FIRST layers) -> global dY
 template <int L, bool ASSIGN>
-__device__ __forceinline__ void tc_dy_store(const ChunkArgs& a, const TcCtx& c, int tile, const float* dYp, bool have) {
+__device__ ALG_NI void tc_dy_store(const ChunkArgs& a, const TcCtx& c, int tile, const float* dYp, bool have) {
   using D = DimsTC<L>; using SM = SmemTC<L>; constexpr int TM = 128;
   float* P = c.sm + SM::oOPH;     // [2][NSH][128]
   if (have) {
@@ -775,7 +780,7 @@ constexpr int ZD_ROWS = 3 * 64;
 // leaves z2 and m (pre-envelope output) in TMEM, requests `next`.  With STORE the activation
 // derivatives are written to `zd` so that the backward kernels need no recomputation.
 template <int L, bool STORE, class Bias>
-__device__ __forceinline__ void tc_mlp_hidden_fwd(TcCtx& c, const TcMat& w2, const TcMat& next, Bias bias, float* zd = nullptr) {
+__device__ ALG_NI void tc_mlp_hidden_fwd(TcCtx& c, const TcMat& w2, const TcMat& next, Bias bias, float* zd = nullptr) {
   constexpr int TM = 128;
   tc_epi(c, TC_Z1, 64, [&](int n, float v0, float v1, float v2, float v3) {
     if constexpr (STORE) {
@@ -809,7 +814,7 @@ __device__ __forceinline__ void tc_mlp_hidden_fwd(TcCtx& c, const TcMat& w2, con
 // CG: the record was written by this very thread earlier in the same kernel (k_t_tc): read it with ld.global.cg
 // next2 (optional): weights of a GEMM that shares the operand with `next` -> weight buffer 2 (tc_mma_pair)
 template <int L, bool CG = false>
-__device__ __forceinline__ void tc_mlp_bwd_hidden_st(TcCtx& c, const TcMat& w1_b, const TcMat& next, const float* zd, const TcMat* next2 = nullptr) {
+__device__ ALG_NI void tc_mlp_bwd_hidden_st(TcCtx& c, const TcMat& w1_b, const TcMat& next, const float* zd, const TcMat* next2 = nullptr) {
   constexpr int TM = 128;
   float d[32];
   ld_rows32<CG>(c, zd + 64 * TM, d);                  // act'(z2): in flight during the MMA
@@ -833,7 +838,7 @@ __device__ __forceinline__ void tc_mlp_bwd_hidden_st(TcCtx& c, const TcMat& w1_b
 // (l_max = 2: the first ds block is held in registers until the MMA that still reads the weight region DS_s aliases
 // has completed.)
 template <int L>
-__device__ __forceinline__ void tc_din(TcCtx& c, const TcLayerW& tl, float* dXg) {
+__device__ ALG_NI void tc_din(TcCtx& c, const TcLayerW& tl, float* dXg) {
   using D = DimsTC<L>; using SM = SmemTC<L>; constexpr int TM = 128;
   float dp[32];
   ld_rows32(c, dXg, dp);                              // in flight during the MMAs
@@ -952,6 +957,33 @@ __device__ __forceinline__ void tc_phase2(const ChunkArgs& a, const ModelW& w, T
 // ============================================================================================
 // F0
 // ============================================================================================
+// L2 prefetch of the per-tile state a phase reads (issued before the geometry: the phases are latency-bound)
+template <int L> __device__ __forceinline__ void fk_prefetch(const ChunkArgs& a, const TcCtx* c, int tile, int k, const GeomIn& gi, int c0, size_t goff) {
+  tc_prefetch(a.X[k] + (size_t)tile * S * 128, S * 128);
+  tc_prefetch_row<L>(a.gamma[k] + goff, c0, gi);
+  (void)c;
+}
+template <int L> __device__ __forceinline__ void bk_prefetch(const ChunkArgs& a, int tile, int k, const GeomIn& gi, int c0, size_t goff) {
+  using D = DimsTC<L>; constexpr int TM = 128;
+  tc_prefetch(a.X[k + 1] + (size_t)tile * S * TM, S * TM);
+  tc_prefetch_row<L>(a.dgamma[k + 1] + goff, c0, gi);
+  tc_prefetch_row<L>(a.gamma[k] + goff, c0, gi);
+  tc_prefetch(a.dX + (size_t)tile * S * TM, S * TM);
+  tc_prefetch(a.ZD[k + 1] + (size_t)tile * ZD_ROWS * TM, ZD_ROWS * TM);
+  tc_prefetch(a.dY + (size_t)tile * D::NSH * TM, D::NSH * TM);
+  tc_prefetch(a.du + (size_t)tile * TM, TM);
+}
+template <int L> __device__ __forceinline__ void b0_prefetch(const ChunkArgs& a, int tile, const GeomIn& gi, int c0, size_t goff) {
+  using D = DimsTC<L>; constexpr int TM = 128;
+  tc_prefetch(a.X[0] + (size_t)tile * S * TM, S * TM);
+  tc_prefetch_row<L>(a.dgamma[0] + goff, c0, gi);
+  tc_prefetch(a.dX + (size_t)tile * S * TM, S * TM);
+  tc_prefetch(a.ZD[0] + (size_t)tile * ZD_ROWS * TM, ZD_ROWS * TM);
+  tc_prefetch(a.W0 + (size_t)tile * D::ENVW * TM, D::ENVW * TM);
+  tc_prefetch(a.dY + (size_t)tile * D::NSH * TM, D::NSH * TM);
+  tc_prefetch(a.du + (size_t)tile * TM, TM);
+}
+
 // Every phase is a device function ("body") that starts from the published tile geometry (Y_s, u_s, c_s, zz_s, segment
 // table; see tc_tile_begin) and the per-thread Geom: the chunked pipeline wraps each body in its own kernel (tile =
 // blockIdx.x), the fused persistent kernel (k_fused_tc) runs all bodies of a tile back to back in one CTA.
@@ -1453,8 +1485,9 @@ __global__ void __launch_bounds__(NT, 2) k_b0_tc(const __grid_constant__ ChunkAr
 // ============================================================================================
 struct FusedPlan {
   const int* tile_c0;     // [ntiles + 1] first centre slot of every tile (tile_c0[ntiles] = nlocal)
-  const int* info;        // [0] = ntiles, [1] = max degree, [2] = E, [3] = edge capacity overflow flag
+  int* info;              // [0] = ntiles, [1] = max degree, [2] = E, [3] = edge capacity overflow flag, [5] = tile counter (work queue)
   int max_rows;           // 128
+  int batch;              // tiles a CTA takes from the queue at once (scratch slots per CTA)
 };
 template <int L, int NLAYERS>
 __global__ void __launch_bounds__(NT, 2) k_fused_tc(const __grid_constant__ ChunkArgs a, const __grid_constant__ ModelW w, const __grid_constant__ TcW tw,
@@ -1463,44 +1496,59 @@ __global__ void __launch_bounds__(NT, 2) k_fused_tc(const __grid_constant__ Chun
   extern __shared__ __align__(1024) float sm_raw[];
   const int ntiles = plan.info[0];
   if (plan.info[1] > TM || plan.info[3] != 0) return;          // a centre with more than 128 edges / edge arrays too small: the host falls back
-  if ((int)blockIdx.x >= ntiles) return;
   TcCtx c = tc_begin<L>(sm_raw, tw);
-  const int slot = blockIdx.x;
-  c.goff = (size_t)slot * TM * D::F;
-#pragma unroll 1
-  for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+  const int B = plan.batch;
+  int* next_tile = reinterpret_cast<int*>(c.sm + SmemTC<L>::oBAR) + 10;    // after the mbarriers / TMEM pointer
+  // one phase of one tile of the batch: geometry -> shared memory, then the phase body on the tile's private scratch slot
+  int es = 0, nvalid = 0, slot = 0;
+  auto enter = [&](int t, int tb) -> bool {
     const int c0 = plan.tile_c0[t], c1 = plan.tile_c0[t + 1];
-    const int es = a.rowptr[c0];
-    const int nvalid = a.rowptr[c1] - es;
-    if (nvalid <= 0) continue;                                  // only centres without neighbours
+    es = a.rowptr[c0];
+    nvalid = a.rowptr[c1] - es;
+    if (nvalid <= 0) return false;                              // only centres without neighbours
+    slot = (int)blockIdx.x * B + tb;
     c.c0 = c0;
-    const GeomIn gi = tc_geom_load(a, es, nvalid);
-    const Geom g = tc_tile_begin<L>(a, w, c, gi, nvalid);
-    f0_body<L>(a, w, tw, c, g, slot, es, nvalid);
-    __syncthreads();
-    if constexpr (NLAYERS == 1) {
-      t_body<L, true>(a, w, tw, c, g, slot, es, nvalid, 0);
-    } else if constexpr (NLAYERS == 2) {
-      fk_body<L, 'B', true>(a, w, tw, c, g, slot, es, nvalid, 0);
-      __syncthreads();
-      t_body<L, false>(a, w, tw, c, g, slot, es, nvalid, 1);
-      __syncthreads();
-      bk_body<L, 'B', true>(a, w, tw, c, g, slot, es, nvalid, 0);
-    } else {
-      fk_body<L, 'C', true>(a, w, tw, c, g, slot, es, nvalid, 0);
-      __syncthreads();
-      fk_body<L, 'D', false>(a, w, tw, c, g, slot, es, nvalid, 1);
-      __syncthreads();
-      t_body<L, false>(a, w, tw, c, g, slot, es, nvalid, 2);
-      __syncthreads();
-      bk_body<L, 'D', false>(a, w, tw, c, g, slot, es, nvalid, 1);
-      __syncthreads();
-      bk_body<L, 'C', true>(a, w, tw, c, g, slot, es, nvalid, 0);
-    }
-    __syncthreads();
-    b0_body<L>(a, w, tw, c, g, slot, es, nvalid);
-    __syncthreads();
+    c.goff = (size_t)slot * TM * D::F;
+    return true;
+  };
+#define ALG_PHASE(PRE, ...)                                                      \
+  _Pragma("unroll 1") for (int tb = 0; tb < nb; ++tb) {                           \
+    if (!enter(t0 + tb, tb)) continue;                                            \
+    const GeomIn gi = tc_geom_load(a, es, nvalid);                                \
+    PRE;                                                                          \
+    const Geom g = tc_tile_begin<L>(a, w, c, gi, nvalid);                         \
+    __VA_ARGS__;                                                                  \
+    __syncthreads();                                                              \
   }
+#pragma unroll 1
+  for (;;) {
+    // dynamic queue of tile batches: the result does not depend on which CTA runs a tile (fixed-point accumulation), so
+    // the kernel balances itself whatever the number of resident CTAs is.  A batch runs phase by phase (all tiles
+    // through F0, then all through FK, ...): the code of one phase stays in the instruction cache for the whole batch
+    // (with one tile at a time the 280 KB of phase code were re-fetched per tile: 37 % "no instruction" stalls)
+    if (threadIdx.x == 0) *next_tile = atomicAdd(plan.info + 5, 1);
+    __syncthreads();
+    const int t0 = *next_tile * B;
+    __syncthreads();
+    if (t0 >= ntiles) break;
+    const int nb = min(B, ntiles - t0);
+    ALG_PHASE((void)0, f0_body<L>(a, w, tw, c, g, slot, es, nvalid));
+    if constexpr (NLAYERS == 1) {
+      ALG_PHASE(fk_prefetch<L>(a, &c, slot, 0, gi, c.c0, c.goff), (t_body<L, true>(a, w, tw, c, g, slot, es, nvalid, 0)));
+    } else if constexpr (NLAYERS == 2) {
+      ALG_PHASE(fk_prefetch<L>(a, &c, slot, 0, gi, c.c0, c.goff), (fk_body<L, 'B', true>(a, w, tw, c, g, slot, es, nvalid, 0)));
+      ALG_PHASE(fk_prefetch<L>(a, &c, slot, 1, gi, c.c0, c.goff), (t_body<L, false>(a, w, tw, c, g, slot, es, nvalid, 1)));
+      ALG_PHASE(bk_prefetch<L>(a, slot, 0, gi, c.c0, c.goff), (bk_body<L, 'B', true>(a, w, tw, c, g, slot, es, nvalid, 0)));
+    } else {
+      ALG_PHASE(fk_prefetch<L>(a, &c, slot, 0, gi, c.c0, c.goff), (fk_body<L, 'C', true>(a, w, tw, c, g, slot, es, nvalid, 0)));
+      ALG_PHASE(fk_prefetch<L>(a, &c, slot, 1, gi, c.c0, c.goff), (fk_body<L, 'D', false>(a, w, tw, c, g, slot, es, nvalid, 1)));
+      ALG_PHASE(fk_prefetch<L>(a, &c, slot, 2, gi, c.c0, c.goff), (t_body<L, false>(a, w, tw, c, g, slot, es, nvalid, 2)));
+      ALG_PHASE(bk_prefetch<L>(a, slot, 1, gi, c.c0, c.goff), (bk_body<L, 'D', false>(a, w, tw, c, g, slot, es, nvalid, 1)));
+      ALG_PHASE(bk_prefetch<L>(a, slot, 0, gi, c.c0, c.goff), (bk_body<L, 'C', true>(a, w, tw, c, g, slot, es, nvalid, 0)));
+    }
+    ALG_PHASE(b0_prefetch<L>(a, slot, gi, c.c0, c.goff), b0_body<L>(a, w, tw, c, g, slot, es, nvalid));
+  }
+#undef ALG_PHASE
   tc_end(c);
 }
 

@@ -55,7 +55,12 @@ class PairAllegroB200:
                 cand = model_path[:-len(ext)] + ".alg"
                 if os.path.exists(cand):
                     return cand
-                raise RuntimeError("no exported weights %s for %s: run `python -m pair_allegro_b200.export %s %s`"
+                if ext == ".nequip.pt2":
+                    raise RuntimeError("no exported weights %s for %s: an AOT-Inductor package cannot be converted; export the "
+                                       "weights of the same model to %s (python -m pair_allegro_b200.export <model>.nequip.pth %s)"
+                                       % (cand, model_path, cand, cand))
+                raise RuntimeError("no exported weights %s for %s: run `python -m pair_allegro_b200.export %s %s` "
+                                   "(supports TorchScript files carrying an allegro_b200_config entry)"
                                    % (cand, model_path, model_path, cand))
         raise RuntimeError("Only accepts model paths with extension `.nequip.pth`, `.nequip.pt2` or `.alg`, but found" + model_path)
 

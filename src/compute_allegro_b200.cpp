@@ -91,6 +91,11 @@ template <int peratom> void ComputeAllegroB200<peratom>::compute_peratom()
     rows = q.data();
     for (int i = 0; i < nlocal; i++)
       for (int j = 0; j < nperatom; j++) array_atom[i][j] = rows[(size_t) i * nperatom + j];
+  } else {
+    // empty domain: pair->compute returned early (cpp:341) and produced nothing this step; the ghost rows this rank
+    // still has to send in the reverse communication are zeros (never a stale or null pointer)
+    zero_rows.assign((size_t) (atom->nlocal + atom->nghost) * nperatom, 0.0);
+    rows = zero_rows.data();
   }
   if (newton) comm->reverse_comm(this);    // ghost rows are added to their owners, even if this domain is empty
 }

@@ -17,6 +17,7 @@ ComputeStyle(allegro/atom, ComputeAllegroB200<1>)
 #define LMP_COMPUTE_ALLEGRO_B200_H
 
 #include "compute.h"
+#include <vector>
 
 #include <string>
 
@@ -35,6 +36,7 @@ template <int peratom> class ComputeAllegroB200 : public Compute {
  protected:
   std::string quantity;
   const double *rows = nullptr;    // custom_output[quantity] of the current step, [ntot][nperatom]
+  std::vector<double> zero_rows;   // what an empty domain sends in the reverse communication
   int newton = 0, nperatom = 0, nmax = 0;
 };
 

@@ -49,8 +49,8 @@ PairAllegroB200::PairAllegroB200(LAMMPS *lmp) : Pair(lmp)
     }
   }
 
-  // device = node-local rank (cpp:91-120); the range check against the number of visible
-  // devices happens in alg_create (error -> error->all below), wrap-around only in debug mode
+  // device = node-local rank (cpp:91-120).  More ranks than visible devices is an error, except in debug mode
+  // where the rank wraps around so that multi-rank tests can share one GPU (cpp:102-118).
   device_index = 0;
   if (comm->nprocs > 1) {
     MPI_Comm shmcomm;
@@ -60,6 +60,17 @@ PairAllegroB200::PairAllegroB200(LAMMPS *lmp) : Pair(lmp)
     device_index = shmrank;
   }
   if (const char *env_d = std::getenv("ALLEGRO_B200_DEVICE")) device_index = std::atoi(env_d);
+  const int devicecount = alg_device_count();
+  if (devicecount > 0 && device_index >= devicecount) {
+    if (debug_mode) {
+      std::cerr << "WARNING (Allegro): my rank (" << device_index << ") is bigger than the number of visible devices (" << devicecount
+                << "), wrapping around to use device " << device_index % devicecount << " again!!!";
+      device_index = device_index % devicecount;
+    } else {
+      std::cerr << "ERROR (Allegro): my rank (" << device_index << ") is bigger than the number of visible devices (" << devicecount << ")!!!";
+      error->all(FLERR, "pair_allegro: mismatch between number of ranks and number of available GPUs");
+    }
+  }
   if (debug_mode) std::cout << "Allegro is using device cuda:" << device_index << "\n";
 }
 
@@ -130,8 +141,16 @@ std::string PairAllegroB200::resolve_weight_path(const std::string &path) const
       std::string cand = path.substr(0, path.size() - strlen(ext)) + ".alg";
       struct stat st;
       if (stat(cand.c_str(), &st) == 0) return cand;
+      // the exporter reads TorchScript files written by this repo's model builder (they carry an `allegro_b200_config`
+      // entry); an AOT-Inductor package cannot be read back at all, and a nequip-compile'd TorchScript file needs the
+      // nequip/allegro importer that is not part of this build
+      if (std::string(ext) == ".nequip.pt2")
+        throw std::runtime_error("no exported weights " + cand + " for " + path +
+                                 ": an AOT-Inductor package cannot be converted; export the weights of the same model to " + cand +
+                                 " (python -m pair_allegro_b200.export <model>.nequip.pth " + cand + ")");
       throw std::runtime_error("no exported weights " + cand + " for " + path +
-                               ": run `python -m pair_allegro_b200.export " + path + " " + cand + "`");
+                               ": run `python -m pair_allegro_b200.export " + path + " " + cand +
+                               "` (supports TorchScript files carrying an allegro_b200_config entry)");
     }
   }
   throw std::runtime_error("Only accepts model paths with extension `.nequip.pth`, `.nequip.pt2` or `.alg`, but found" + path);
