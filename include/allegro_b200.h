@@ -78,14 +78,15 @@ ALG_API int alg_set_type_map(alg_handle* h, int ntypes, const int* lammps_type_t
 /* Options (string key/value, all optional):
  *   "filter"       "le" (default; host path rsq <= cut^2, pair_nequip_allegro.cpp:507,599)
  *                  | "lt" (Kokkos path rsq < cut^2, pair_nequip_allegro_kokkos.cpp:189)
- *   "pipeline"     "auto" (default) | "fused" | "tiled".  fused = ONE persistent kernel over centre-aligned tiles
- *                  (every atom's edges inside one 128-edge tile, all phases of a tile in one CTA, inter-phase state in
- *                  CTA-private L2-resident scratch, no host synchronisation); needs <= 128 neighbours inside the cutoff
- *                  per atom.  tiled = the chunked edge-tile pipeline (any neighbour count; one host synchronisation per
- *                  step on the CSR row pointer).  auto = fused, and tiled from the first step on that meets an atom
- *                  with more than 128 neighbours (that step is repeated transparently), or when debug=1.
- *   "fused_batch"  fused pipeline: tiles a CTA takes from the tile queue at once and runs phase by phase (default 8; the
- *                  code of one phase then stays in the instruction cache for the whole batch)
+ *   "pipeline"     "auto" (default) | "fused" | "tiled".  fused = ONE persistent kernel: the edge list is cut on the device
+ *                  into centre-aligned batches of fused_batch*128 edges, a CTA runs a batch through all phases and
+ *                  combines the per-atom sums itself; inter-phase state in CTA-private scratch; no host synchronisation,
+ *                  no fix-up launches.  Needs <= fused_batch*128 neighbours inside the cutoff per atom.  tiled = the
+ *                  chunked edge-tile pipeline (any neighbour count; one host synchronisation per step on the CSR row
+ *                  pointer, one kernel per phase and chunk).  auto = fused, and tiled from the first step on that meets
+ *                  an atom with more neighbours than a batch holds (that step is repeated transparently), or when debug=1.
+ *   "fused_batch"  fused pipeline: 128-edge tiles per batch (default 8).  A CTA runs the tiles of a batch phase by phase, so
+ *                  the code of one phase stays in the instruction cache for the whole batch
  *   "max_neighbors" alg_compute_device only: extent(1) of the caller's 2-D neighbour view.  Sizes the edge arrays to
  *                  nlocal*max_neighbors so that a fully asynchronous step can never overflow them; without it they
  *                  are sized from the previous step's edge count (+12.5 %), like the reference's 1.05 padding
@@ -135,7 +136,7 @@ ALG_API int alg_compute_host(alg_handle* h, int nlocal, int nghost, const double
  * the reference's parallel_reduce result :318 and virial .cpu() :329); pass NULL for both
  * to keep the call fully asynchronous: nothing in the call then waits for the device (the tile plan of the fused
  * pipeline is built on the device; the reference blocks on its edge count every step,
- * pair_nequip_allegro_kokkos.cpp:203-206).  Such a step is verified lazily: if it met an atom with more than 128
+ * pair_nequip_allegro_kokkos.cpp:203-206).  Such a step is verified lazily: if it met an atom with more than fused_batch*128
  * neighbours, or overflowed edge arrays sized without max_neighbors, it wrote no forces and the NEXT call on the handle
  * returns ALG_ESTATE (then switches to the tiled pipeline / larger arrays).  Calls that pass `eng` or `virial6` are
  * verified before they return and such steps are repeated transparently.  `stream` is a cudaStream_t (0 = legacy default). */
@@ -170,11 +171,40 @@ ALG_API int alg_get_timings(alg_handle* h, double* ms3);
  * last step ran the fused kernel, CTAs in the fused grid, 1 once the tiled fallback became sticky]. */
 ALG_API int alg_get_stats(alg_handle* h, const char* what, double* out, int n);
 
-/* Ghost halo helpers for spatial-domain multi-GPU runs (replace LAMMPS
- * comm->forward_comm / reverse_comm pack/unpack for x and f; the transport between ranks is
- * NCCL and lives in the caller).  Device pointers; stream-ordered.
+/* ---- ghost halo exchange of spatial-domain multi-GPU runs (one rank per GPU) -------------------------------------------
+ * Replaces what LAMMPS' Comm does around the reference pair style: comm->forward_comm() (ghost x <- owner x + image
+ * shift) before compute() and comm->reverse_comm() (owner f += ghost f) after it -- required because Allegro runs with
+ * `newton on` (pair_nequip_allegro.cpp:149; same owner-accumulation protocol as compute/compute_allegro.cpp:159-189).
+ * Transport: grouped ncclSend/ncclRecv to all neighbouring domains at once over NVLink; periodic self-images of a rank stay
+ * on the device.  The reverse unpack is a sorted segmented sum (fixed order), so forces are bit-reproducible.
+ * NCCL is bound at run time (libnccl.so.2); alg_comm_create(nranks = 1) needs no NCCL at all.
+ *
+ * alg_comm_unique_id : rank 0 creates the 128-byte NCCL id and distributes it by any out-of-band means (MPI_Bcast in
+ *                      LAMMPS, torch.distributed in bench.py).
+ * alg_comm_set_plan  : per peer p (peer_rank[p] may be the rank itself = periodic self-images):
+ *                      send_index[p][0..send_count[p])  local atoms whose positions peer p needs as ghosts (host ints),
+ *                      send_shift[p]                    [send_count][3] image shift added to those positions, or NULL,
+ *                      recv_begin[p], recv_count[p]     the contiguous ghost slice [begin, begin+count) of x / f that
+ *                                                       holds peer p's atoms, in the order of p's send_index for this rank.
+ * alg_comm_forward / alg_comm_reverse : device pointers x / f of [nlocal+nghost][3] doubles; stream-ordered, no host sync.
+ * alg_comm_allreduce_sum : in-place sum over ranks of n <= 64 host doubles (eng_vdwl, virial: LAMMPS' MPI_Allreduce). */
+typedef struct alg_comm alg_comm;
+ALG_API int alg_comm_unique_id(char* id128);
+ALG_API int alg_comm_create(int cuda_device, int nranks, int rank, const char* id128, alg_comm** out);
+ALG_API void alg_comm_destroy(alg_comm* c);
+ALG_API const char* alg_comm_last_error(const alg_comm* c);
+ALG_API int alg_comm_set_plan(alg_comm* c, int npeer, const int* peer_rank, const int* send_count, const int* const* send_index,
+                      const double* const* send_shift, const int* recv_begin, const int* recv_count);
+ALG_API int alg_comm_forward(alg_comm* c, double* d_x, void* stream);
+ALG_API int alg_comm_reverse(alg_comm* c, double* d_f, void* stream);
+ALG_API int alg_comm_allreduce_sum(alg_comm* c, double* values, int n, void* stream);
+/* [bytes sent to other ranks per forward, per reverse, packed entries, distinct owner atoms] */
+ALG_API int alg_comm_stats(const alg_comm* c, double* out4);
+
+/* Building blocks of the above for callers that bring their own transport (LAMMPS pack/unpack_forward/reverse_comm):
  *   pack:        buf[k][0..2] = x[list[k]][0..2] + shift[k][0..2]   (d_shift may be NULL)
- *   unpack_add:  f[list[k]][0..2] += buf[k][0..2]        (atomic; list entries may repeat) */
+ *   unpack_add:  f[list[k]][0..2] += buf[k][0..2]   (fp64 atomics: list entries may repeat, and then the summation
+ *                order -- hence the last bits -- is not fixed; alg_comm_reverse is the deterministic path) */
 ALG_API int alg_halo_pack(const double* d_x, const int* d_list, int n, const double* d_shift, double* d_buf,
                   void* stream);
 ALG_API int alg_halo_unpack_add(double* d_f, const int* d_list, int n, const double* d_buf, void* stream);

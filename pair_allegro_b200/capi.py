@@ -14,7 +14,9 @@ LIB_PATH = os.path.join(_HERE, "liballegro_b200.so")
 
 EXPORTS = ["alg_create", "alg_destroy", "alg_last_error", "alg_metadata", "alg_set_type_map", "alg_set_option",
            "alg_compute_host", "alg_compute_device", "alg_get_edges", "alg_get_output", "alg_get_timings", "alg_get_stats",
-           "alg_halo_pack", "alg_halo_unpack_add", "alg_version", "alg_device_count"]
+           "alg_halo_pack", "alg_halo_unpack_add", "alg_version", "alg_device_count",
+           "alg_comm_unique_id", "alg_comm_create", "alg_comm_destroy", "alg_comm_last_error", "alg_comm_set_plan", "alg_comm_forward",
+           "alg_comm_reverse", "alg_comm_allreduce_sum", "alg_comm_stats"]
 
 _lib = None
 
@@ -66,6 +68,24 @@ def load_library(path=None):
     lib.alg_halo_pack.restype = C.c_int
     lib.alg_halo_unpack_add.argtypes = [vp, vp, C.c_int, vp, vp]
     lib.alg_halo_unpack_add.restype = C.c_int
+    lib.alg_comm_unique_id.argtypes = [C.c_char_p]
+    lib.alg_comm_unique_id.restype = C.c_int
+    lib.alg_comm_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_char_p, C.POINTER(vp)]
+    lib.alg_comm_create.restype = C.c_int
+    lib.alg_comm_destroy.argtypes = [vp]
+    lib.alg_comm_destroy.restype = None
+    lib.alg_comm_last_error.argtypes = [vp]
+    lib.alg_comm_last_error.restype = C.c_char_p
+    lib.alg_comm_set_plan.argtypes = [vp, C.c_int, ip, ip, C.POINTER(ip), C.POINTER(dp), ip, ip]
+    lib.alg_comm_set_plan.restype = C.c_int
+    lib.alg_comm_forward.argtypes = [vp, vp, vp]
+    lib.alg_comm_forward.restype = C.c_int
+    lib.alg_comm_reverse.argtypes = [vp, vp, vp]
+    lib.alg_comm_reverse.restype = C.c_int
+    lib.alg_comm_allreduce_sum.argtypes = [vp, dp, C.c_int, vp]
+    lib.alg_comm_allreduce_sum.restype = C.c_int
+    lib.alg_comm_stats.argtypes = [vp, dp]
+    lib.alg_comm_stats.restype = C.c_int
     lib.alg_device_count.argtypes = []
     lib.alg_device_count.restype = C.c_int
     lib.alg_version.argtypes = []
@@ -192,6 +212,80 @@ class Handle:
         t = np.zeros(3)
         self._check(self.lib.alg_get_timings(self.h, _dptr(t)))
         return t
+
+
+class Comm:
+    """ghost halo exchange over NCCL (alg_comm_*): the product-side replacement of LAMMPS comm->forward_comm / reverse_comm"""
+
+    def __init__(self, device, nranks=1, rank=0, unique_id=None):
+        self.lib = load_library()
+        self.c = C.c_void_p()
+        rc = self.lib.alg_comm_create(int(device), int(nranks), int(rank), unique_id, C.byref(self.c))
+        if rc != 0:
+            msg = self.lib.alg_comm_last_error(None).decode()
+            self.c = None
+            raise AllegroError(rc, msg)
+        self.rank, self.nranks = rank, nranks
+
+    @staticmethod
+    def unique_id():
+        lib = load_library()
+        buf = C.create_string_buffer(128)
+        rc = lib.alg_comm_unique_id(buf)
+        if rc != 0:
+            raise AllegroError(rc, lib.alg_comm_last_error(None).decode())
+        return buf.raw
+
+    def _check(self, rc):
+        if rc != 0:
+            raise AllegroError(rc, self.lib.alg_comm_last_error(self.c).decode())
+
+    def set_plan(self, plan):
+        """plan = dict(recv_slices={peer: (a, b)}, send_index={peer: int32[n]}, send_shift={peer: f64[n,3]}) as built by
+        lmpshim/harness.py (decompose_rank / the single-rank self-image plan)"""
+        peers = sorted(plan["send_index"].keys())
+        n = len(peers)
+        self._keep = []
+        pr = (C.c_int * max(n, 1))(*peers)
+        sc = (C.c_int * max(n, 1))(*[len(plan["send_index"][p]) for p in peers])
+        rb = (C.c_int * max(n, 1))(*[int(plan["recv_slices"][p][0]) for p in peers])
+        rcnt = (C.c_int * max(n, 1))(*[int(plan["recv_slices"][p][1] - plan["recv_slices"][p][0]) for p in peers])
+        si = (C.POINTER(C.c_int) * max(n, 1))()
+        ss = (C.POINTER(C.c_double) * max(n, 1))()
+        for k, p in enumerate(peers):
+            a = np.ascontiguousarray(plan["send_index"][p], dtype=np.int32)
+            b = np.ascontiguousarray(plan["send_shift"][p], dtype=np.float64)
+            self._keep += [a, b]
+            si[k] = _iptr(a)
+            ss[k] = _dptr(b)
+        self._check(self.lib.alg_comm_set_plan(self.c, n, pr, sc, si, ss, rb, rcnt))
+
+    def forward(self, d_x, stream=0):
+        self._check(self.lib.alg_comm_forward(self.c, d_x, stream or None))
+
+    def reverse(self, d_f, stream=0):
+        self._check(self.lib.alg_comm_reverse(self.c, d_f, stream or None))
+
+    def allreduce_sum(self, values, stream=0):
+        v = np.ascontiguousarray(values, dtype=np.float64).copy()
+        self._check(self.lib.alg_comm_allreduce_sum(self.c, _dptr(v), len(v), stream or None))
+        return v
+
+    def stats(self):
+        t = np.zeros(4)
+        self._check(self.lib.alg_comm_stats(self.c, _dptr(t)))
+        return t
+
+    def close(self):
+        if getattr(self, "c", None):
+            self.lib.alg_comm_destroy(self.c)
+            self.c = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 KERNEL_FAMILIES = ["F0", "FK", "T", "BK", "B0", "fixup", "fused"]

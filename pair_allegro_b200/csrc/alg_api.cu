@@ -295,33 +295,39 @@ __global__ void k_edge_index(const int* __restrict__ rowptr, int nlocal, long ca
 }
 
 // ------------------------------------------------------------------------------------------
-// tile plan of the fused kernel: centre-aligned tiles of <= 128 edges and <= 128 centres.  Centres are split into
-// blocks of PLAN_CB; one thread packs its block greedily (tiles never span blocks), pass 0 counts the tiles of a
-// block, pass 1 (after an exclusive scan) writes the first centre of every tile.
-// info: [0] ntiles, [1] max degree, [2] E, [3] 1 if E exceeds the capacity of the edge arrays
+// batch plan of the fused kernel: centre-aligned batches of <= `rows` edges and <= `rows` centres (rows = B*128).
+// Centres are split into blocks of PLAN_CB; one thread packs its block greedily (batches never span blocks), pass 0
+// counts the batches of a block, pass 1 (after an exclusive scan) writes the first centre of every batch.
+// info: [0] nbatch, [1] max degree, [2] E, [3] 1 if E exceeds the capacity of the edge arrays, [6] number of 128-edge tiles
 // ------------------------------------------------------------------------------------------
-constexpr int PLAN_CB = 256;
-constexpr int PLAN_ROWS = 128;
+constexpr int PLAN_CB = 1024;      // centres per planning block (one thread packs them greedily from shared memory)
+constexpr int PLAN_TPB = 8;        // planning blocks per CUDA block (8 x 1024 row pointers staged in 32 KB of shared memory)
 template <bool FILL>
-__global__ void k_plan(int nlocal, const int* __restrict__ rowptr, int* __restrict__ blk_tiles, const int* __restrict__ blk_base,
-                       int* __restrict__ tile_c0, int* __restrict__ info, long cap) {
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(256) k_plan(int nlocal, const int* __restrict__ rowptr, int* __restrict__ blk_tiles, const int* __restrict__ blk_base,
+                                              int* __restrict__ tile_c0, int* __restrict__ info, long cap, int PLAN_ROWS) {
+  __shared__ int rp[PLAN_TPB * PLAN_CB + 1];
   const int nblk = (nlocal + PLAN_CB - 1) / PLAN_CB;
-  if (b >= nblk) return;
+  const int c_base = blockIdx.x * PLAN_TPB * PLAN_CB;
+  const int c_end = min(nlocal, c_base + PLAN_TPB * PLAN_CB);
+  for (int i = threadIdx.x; i <= c_end - c_base; i += blockDim.x) rp[i] = rowptr[c_base + i];
+  __syncthreads();
+  const int b = blockIdx.x * PLAN_TPB + threadIdx.x;
+  if (threadIdx.x >= PLAN_TPB || b >= nblk) return;
   const int cb = b * PLAN_CB, ce = min(nlocal, cb + PLAN_CB);
-  int rows = 0, span = 0, nt = 0, maxdeg = 0;
+  int rows = 0, span = 0, nt = 0, maxdeg = 0, tiles = 0;
   int base = FILL ? blk_base[b] : 0;
-  int prev = rowptr[cb];
+  int prev = rp[cb - c_base];
   for (int c = cb; c < ce; ++c) {
-    const int nxt = rowptr[c + 1];
+    const int nxt = rp[c + 1 - c_base];
     const int deg = nxt - prev;
     prev = nxt;
     maxdeg = max(maxdeg, deg);
-    if (span > 0 && (rows + deg > PLAN_ROWS || span == PLAN_ROWS)) { ++nt; rows = 0; span = 0; }
+    if (span > 0 && (rows + deg > PLAN_ROWS || span == PLAN_ROWS)) { ++nt; tiles += (rows + 127) >> 7; rows = 0; span = 0; }
     if (FILL && span == 0) tile_c0[base + nt] = c;
     rows += deg; ++span;
   }
-  if (span > 0) ++nt;
+  if (span > 0) { ++nt; tiles += (rows + 127) >> 7; }
+  if (FILL) atomicAdd(info + 6, tiles);
   if (!FILL) {
     blk_tiles[b] = nt;
     if (b == 0) blk_tiles[nblk] = 0;
@@ -347,12 +353,12 @@ __global__ void k_mtype(int ntot, const int* __restrict__ type, const int* __res
 }
 
 // finalize: fixed-point accumulators -> model forces (double), optionally f += ; per-atom energies
-// info != nullptr (fused pipeline): a step the fused kernel refused (info[1] > 128 or info[3]) must not touch f; the host repeats it
+// info != nullptr (fused pipeline): a step the fused kernel refused (info[1] > rows or info[3]) must not touch f; the host repeats it
 __global__ void k_forces(int ntot, const unsigned long long* __restrict__ facc, double* __restrict__ forces, double* __restrict__ f_inout,
-                         const int* __restrict__ info) {
+                         const int* __restrict__ info, int rows) {
   const long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
   if (i >= 3L * ntot) return;
-  if (info && (info[1] > PLAN_ROWS || info[3] != 0)) return;
+  if (info && (info[1] > rows || info[3] != 0)) return;
   const double v = (double)(long long)facc[i] * FIX_INV;
   forces[i] = v;
   if (f_inout) f_inout[i] += v;
@@ -890,24 +896,24 @@ static int step_fused(alg_handle* h, const StepIO& io, long cap) {
   CK(h->d_blk_base.ensure(sizeof(int) * (nblk + 1)));
   CK(h->d_tile_c0.ensure(sizeof(int) * ((size_t)nlocal + nblk + 2)));
   CK(cudaMemsetAsync(h->d_info.p, 0, sizeof(int) * 8, st));
-  const int pb = (nblk + 127) / 128;
-  k_plan<false><<<pb, 128, 0, st>>>(nlocal, h->d_rowptr.as<int>(), h->d_blk.as<int>(), nullptr, nullptr, h->d_info.as<int>(), cap);
+  const int pb = (nblk + PLAN_TPB - 1) / PLAN_TPB;
+  k_plan<false><<<pb, 256, 0, st>>>(nlocal, h->d_rowptr.as<int>(), h->d_blk.as<int>(), nullptr, nullptr, h->d_info.as<int>(), cap, h->fused_batch * 128);
   size_t tmp_bytes = 0;
   cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, h->d_blk.as<int>(), h->d_blk_base.as<int>(), nblk + 1, st);
   CK(h->d_scan_tmp.ensure(tmp_bytes));
   CK(cub::DeviceScan::ExclusiveSum(h->d_scan_tmp.p, tmp_bytes, h->d_blk.as<int>(), h->d_blk_base.as<int>(), nblk + 1, st));
-  k_plan<true><<<pb, 128, 0, st>>>(nlocal, h->d_rowptr.as<int>(), nullptr, h->d_blk_base.as<int>(), h->d_tile_c0.as<int>(), h->d_info.as<int>(), cap);
+  k_plan<true><<<pb, 256, 0, st>>>(nlocal, h->d_rowptr.as<int>(), nullptr, h->d_blk_base.as<int>(), h->d_tile_c0.as<int>(), h->d_info.as<int>(), cap, h->fused_batch * 128);
   launch_edge_fill(h, io, cap);
   CK(cudaGetLastError());
   CK(cudaEventRecord(h->ev[1], st));
   const int grid = h->fused_grid;
   const int batch = h->fused_batch;
-  rc = ensure_chunk_buffers(h, (long)grid * batch, (long)grid * batch * PLAN_ROWS);
+  rc = ensure_chunk_buffers(h, (long)grid * batch, (long)grid * batch * 128);
   if (rc != ALG_OK) return rc;
   ChunkArgs a;
   fill_args(h, io, a);
   a.e0 = 0; a.e1 = 0; a.c0 = 0;
-  FusedPlan plan{h->d_tile_c0.as<int>(), h->d_info.as<int>(), PLAN_ROWS, batch};      // info[5] (tile queue) was zeroed above
+  FusedPlan plan{h->d_tile_c0.as<int>(), h->d_info.as<int>(), batch};      // info[5] (tile queue) was zeroed above
   CK(h->pipe->run_fused(a, h->mw, &h->tcw, plan, grid, st, &h->prof));
   h->prof.launches += 2;                               // k_plan x2
   h->dbg_ntiles = 0; h->dbg_c0 = 0; h->dbg_ncent = 0;
@@ -925,10 +931,10 @@ static int resolve_pending(alg_handle* h) {
     return fail(h, ALG_EINVAL, "the previous asynchronous step met atom " + std::to_string(info[8] - 1) + " whose LAMMPS type has no model type");
   if (!h->last_fused) return ALG_OK;
   h->last_E = info[2]; h->last_E_known = info[2];
-  h->step_stats[1] = info[2]; h->step_stats[3] = info[0];
-  if (info[1] > PLAN_ROWS) {
+  h->step_stats[1] = info[2]; h->step_stats[2] = info[0]; h->step_stats[3] = info[6];
+  if (info[1] > h->fused_batch * 128) {
     h->force_tiled = true;
-    return fail(h, ALG_ESTATE, "the previous asynchronous alg_compute_device step met an atom with more than 128 neighbours inside the cutoff "
+    return fail(h, ALG_ESTATE, "the previous asynchronous alg_compute_device step met an atom with more than fused_batch*128 neighbours inside the cutoff "
                                "and produced no forces; the chunked pipeline is selected from now on (pass eng != NULL to have such steps "
                                "re-run transparently)");
   }
@@ -1008,7 +1014,7 @@ static int run_step(alg_handle* h, const StepIO& io, double* eng, double* virial
     // ---- finalize
     if (io.wait_f) CK(cudaStreamWaitEvent(st, io.wait_f, 0));
     k_forces<<<(unsigned)((3L * ntot + 255) / 256), 256, 0, st>>>(ntot, h->d_facc.as<unsigned long long>(), h->d_forces.as<double>(), io.d_f_inout,
-                                                                  fused ? h->d_info.as<int>() : nullptr);
+                                                                  fused ? h->d_info.as<int>() : nullptr, h->fused_batch * 128);
     k_eall_ghost<<<(ntot + 255) / 256, 256, 0, st>>>(ntot, h->d_mtype.as<int>(), h->d_shift.as<double>(), h->d_eall.as<double>());
     k_eall_local<<<eblocks, 256, 0, st>>>(nlocal, io.d_ilist, h->d_mtype.as<int>(), h->d_esum.as<double>(), h->d_scale.as<double>(),
                                           h->d_shift.as<double>(), 1.0 / std::sqrt(h->avg_n), h->d_eall.as<double>(),
@@ -1032,9 +1038,9 @@ static int run_step(alg_handle* h, const StepIO& io, double* eng, double* virial
     if (fused) {
       const int* info = h->h_info.as<int>();
       h->last_E = info[2]; h->last_E_known = info[2];
-      h->step_stats[1] = info[2]; h->step_stats[2] = 1; h->step_stats[3] = info[0];
-      if (info[1] > PLAN_ROWS) {                         // an atom with more than 128 neighbours: chunked pipeline from now on
-        if (h->pipeline_mode == 1) return fail(h, ALG_EINVAL, "pipeline=fused: an atom has more than 128 neighbours inside the cutoff");
+      h->step_stats[1] = info[2]; h->step_stats[2] = info[0]; h->step_stats[3] = info[6];
+      if (info[1] > h->fused_batch * 128) {              // an atom with more neighbours than a batch holds: chunked pipeline from now on
+        if (h->pipeline_mode == 1) return fail(h, ALG_EINVAL, "pipeline=fused: an atom has more than fused_batch*128 neighbours inside the cutoff");
         h->force_tiled = true; fused = false;
         continue;
       }

@@ -196,7 +196,29 @@ template <int L> __device__ __forceinline__ void tc_mma8(uint32_t td, uint32_t t
     umma::mma_tf32_ta(td, ta + 56, db + wpan + 6, idesc, 1);
   }
 }
-template <int L> __device__ ALG_NI void tc_mma(TcCtx& c, int K, int N, uint32_t dcol, uint32_t accumulate = 0) {
+// MMA issue of one GEMM block: a REAL function (one copy), called by warp 0 only, all arguments warp-uniform scalars.
+// Inlined, the descriptor arithmetic + 24 UTCHMMA of every call site were ~4.5 KB of code that 7 of 8 warps skip: half of
+// the T phase's 87 KB, which made the two resident CTAs of the fused kernel (in different phases) miss the instruction cache.
+//   wh / wl : shared-space byte addresses of the weight image (hi / lo); tm: TMEM base; commit_mbar: 0 = no commit
+static __device__ __noinline__ void tc_issue(uint32_t wh, uint32_t wl, uint32_t tm, int passes, int K, int N, uint32_t dcol, uint32_t accumulate,
+                                      uint32_t commit_mbar) {
+  const uint32_t td = tm + dcol;
+  const uint64_t dWh = umma::make_desc_k_sw128_addr(wh), dWl = umma::make_desc_k_sw128_addr(wl);
+  const uint32_t idesc = umma::make_idesc_tf32(N);
+  const uint32_t wpan = (uint32_t)(N * 32 * 4) >> 4;               // weight panel stride in 16-byte units
+  if (umma::elect_one()) {
+    if (passes == 3) {                                              // lo*hi, hi*lo, hi*hi
+      tc_mma8<1>(td, tm + TC_ALO, dWh, idesc, wpan, K, accumulate);
+      tc_mma8<1>(td, tm + TC_AHI, dWl, idesc, wpan, K, 1);
+      tc_mma8<1>(td, tm + TC_AHI, dWh, idesc, wpan, K, 1);
+    } else {
+      tc_mma8<1>(td, tm + TC_AHI, dWh, idesc, wpan, K, accumulate);
+    }
+    if (commit_mbar) asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(commit_mbar) : "memory");
+  }
+  __syncwarp();
+}
+template <int L> __device__ __forceinline__ void tc_mma(TcCtx& c, int K, int N, uint32_t dcol, uint32_t accumulate = 0) {
   using SM = SmemTC<L>;
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   if (warp == 0) umma::mbar_wait(c.wbar, c.wph);      // weight block landed (requested one epilogue ago)
@@ -209,21 +231,7 @@ template <int L> __device__ ALG_NI void tc_mma(TcCtx& c, int K, int N, uint32_t 
     const uint32_t tm = __shfl_sync(0xffffffffu, c.tmem, 0);
     const uint32_t mbar = __shfl_sync(0xffffffffu, umma::smem_u32(c.mbar), 0);
     const int passes = __shfl_sync(0xffffffffu, c.passes, 0);
-    const uint32_t td = tm + dcol;
-    const uint64_t dWh = umma::make_desc_k_sw128_addr(sbase + SM::oWBH * 4), dWl = umma::make_desc_k_sw128_addr(sbase + SM::oWBL * 4);
-    const uint32_t idesc = umma::make_idesc_tf32(N);
-    const uint32_t wpan = (uint32_t)(N * 32 * 4) >> 4;             // weight panel stride in 16-byte units
-    if (umma::elect_one()) {
-      if (passes == 3) {                                            // lo*hi, hi*lo, hi*hi
-        tc_mma8<L>(td, tm + TC_ALO, dWh, idesc, wpan, K, accumulate);
-        tc_mma8<L>(td, tm + TC_AHI, dWl, idesc, wpan, K, 1);
-        tc_mma8<L>(td, tm + TC_AHI, dWh, idesc, wpan, K, 1);
-      } else {
-        tc_mma8<L>(td, tm + TC_AHI, dWh, idesc, wpan, K, accumulate);
-      }
-      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(mbar) : "memory");
-    }
-    __syncwarp();
+    tc_issue(sbase + SM::oWBH * 4, sbase + SM::oWBL * 4, tm, passes, K, N, dcol, accumulate, mbar);
   }
   c.wph ^= 1;
   umma::mbar_wait(c.mbar, c.mph);
@@ -233,7 +241,7 @@ template <int L> __device__ ALG_NI void tc_mma(TcCtx& c, int K, int N, uint32_t 
 
 // two GEMMs on the SAME A operand (K columns), weights in buffer 1 (N1 -> dcol1) and buffer 2 (N2 -> dcol2):
 // one barrier, one MMA group, one commit, one wake-up
-template <int L> __device__ ALG_NI void tc_mma_pair(TcCtx& c, int K, int N1, uint32_t dcol1, int N2, uint32_t dcol2) {
+template <int L> __device__ __forceinline__ void tc_mma_pair(TcCtx& c, int K, int N1, uint32_t dcol1, int N2, uint32_t dcol2) {
   using SM = SmemTC<L>;
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   if (warp == 0) { umma::mbar_wait(c.wbar, c.wph); umma::mbar_wait(c.wbar2, c.wph2); }
@@ -246,25 +254,8 @@ template <int L> __device__ ALG_NI void tc_mma_pair(TcCtx& c, int K, int N1, uin
     const uint32_t tm = __shfl_sync(0xffffffffu, c.tmem, 0);
     const uint32_t mbar = __shfl_sync(0xffffffffu, umma::smem_u32(c.mbar), 0);
     const int passes = __shfl_sync(0xffffffffu, c.passes, 0);
-    const uint64_t dW1h = umma::make_desc_k_sw128_addr(sbase + SM::oWBH * 4), dW1l = umma::make_desc_k_sw128_addr(sbase + SM::oWBL * 4);
-    const uint64_t dW2h = umma::make_desc_k_sw128_addr(sbase + SM::oOPH * 4), dW2l = umma::make_desc_k_sw128_addr(sbase + SM::oOPL * 4);
-    const uint32_t id1 = umma::make_idesc_tf32(N1), id2 = umma::make_idesc_tf32(N2);
-    const uint32_t wp1 = (uint32_t)(N1 * 32 * 4) >> 4, wp2 = (uint32_t)(N2 * 32 * 4) >> 4;
-    if (umma::elect_one()) {
-      if (passes == 3) {
-        tc_mma8<L>(tm + dcol1, tm + TC_ALO, dW1h, id1, wp1, K, 0);
-        tc_mma8<L>(tm + dcol2, tm + TC_ALO, dW2h, id2, wp2, K, 0);
-        tc_mma8<L>(tm + dcol1, tm + TC_AHI, dW1l, id1, wp1, K, 1);
-        tc_mma8<L>(tm + dcol2, tm + TC_AHI, dW2l, id2, wp2, K, 1);
-        tc_mma8<L>(tm + dcol1, tm + TC_AHI, dW1h, id1, wp1, K, 1);
-        tc_mma8<L>(tm + dcol2, tm + TC_AHI, dW2h, id2, wp2, K, 1);
-      } else {
-        tc_mma8<L>(tm + dcol1, tm + TC_AHI, dW1h, id1, wp1, K, 0);
-        tc_mma8<L>(tm + dcol2, tm + TC_AHI, dW2h, id2, wp2, K, 0);
-      }
-      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(mbar) : "memory");
-    }
-    __syncwarp();
+    tc_issue(sbase + SM::oWBH * 4, sbase + SM::oWBL * 4, tm, passes, K, N1, dcol1, 0, 0);
+    tc_issue(sbase + SM::oOPH * 4, sbase + SM::oOPL * 4, tm, passes, K, N2, dcol2, 0, mbar);
   }
   c.wph ^= 1;
   c.wph2 ^= 1;
@@ -1475,80 +1466,116 @@ __global__ void __launch_bounds__(NT, 2) k_b0_tc(const __grid_constant__ ChunkAr
 }
 
 // ============================================================================================
-// Fused persistent kernel: centre-aligned tiles (every centre's CSR row lies inside ONE tile of <= 128 edges, plan built on
-// the device by k_plan_*), one CTA walks tiles t = blockIdx.x, blockIdx.x + gridDim.x, ... and runs ALL phases of a tile
-// (F0, FK.., T, BK.., B0) back to back.  Environment sums are complete inside the tile, so there are no kernel boundaries
-// and no carries; the inter-phase state (x^k, w0, V^k, activation record, dX, dV, dY, du, Gamma/dGamma rows) lives in
-// CTA-private scratch ("slot" = blockIdx.x) that is rewritten for every tile and therefore stays in L2: DRAM traffic is
-// the edge list in and the force/energy accumulators out.  TMEM, the mbarriers and the geometry are set up once per CTA /
-// once per tile instead of once per phase.
+// Fused persistent kernel.  The edge list is cut into centre-aligned BATCHES of at most B*128 edges (plan built on the
+// device by k_plan); a batch is B edge-aligned 128-edge tiles, exactly the layout of a (tiny) chunk of the chunked
+// pipeline.  One CTA takes a batch from a queue and runs it phase by phase -- all its tiles through F0, then FK, ... --
+// so the code of one phase stays in the instruction cache for the whole batch, and combines the per-centre sums of
+// rows that straddle two tiles itself (fused_fixup) before the next phase starts: no kernel boundaries, no fix-up
+// launches, no host synchronisation.  The inter-phase state lives in CTA-private scratch slots that are rewritten for
+// every batch.  TMEM and the mbarriers are set up once per CTA.
 // ============================================================================================
 struct FusedPlan {
-  const int* tile_c0;     // [ntiles + 1] first centre slot of every tile (tile_c0[ntiles] = nlocal)
-  int* info;              // [0] = ntiles, [1] = max degree, [2] = E, [3] = edge capacity overflow flag, [5] = tile counter (work queue)
-  int max_rows;           // 128
-  int batch;              // tiles a CTA takes from the queue at once (scratch slots per CTA)
+  const int* batch_c0;    // [nbatch + 1] first centre slot of every batch (batch_c0[nbatch] = nlocal)
+  int* info;              // [0] = nbatch, [1] = max degree, [2] = E, [3] = edge capacity overflow flag, [5] = batch queue, [6] = tiles
+  int batch;              // B: tiles per batch (scratch slots per CTA); a centre needs at most B*128 edges
 };
+// rows of centres whose CSR row straddles tiles of this batch: the tile in which the row STARTS adds the carries of the
+// following tiles in tile order (same rule as k_fixup of the chunked pipeline)
+template <int NF>
+__device__ __forceinline__ void fused_fixup(const ChunkArgs& a, const TcCtx& c, int e0, int e1, int nb, int slot0, float* out) {
+#pragma unroll 1
+  for (int tb = 0; tb + 1 < nb; ++tb) {
+    const int es = e0 + tb * 128, ee = min(es + 128, e1);
+    const int ce = a.edge_c[ee - 1];
+    const int rb = a.rowptr[ce], re = a.rowptr[ce + 1];
+    if (rb < es || re <= ee) continue;                          // row does not start here, or ends here
+    for (int f = threadIdx.x; f < NF; f += NT) {
+      float acc = out[(size_t)(ce - c.c0) * NF + f];
+      for (int t2 = tb + 1; t2 < nb && e0 + t2 * 128 < re; ++t2) acc += a.carry[(size_t)(slot0 + t2) * NF + f];
+      out[(size_t)(ce - c.c0) * NF + f] = acc;
+    }
+  }
+  __syncthreads();
+}
+__device__ __forceinline__ void fused_fixup_e(const ChunkArgs& a, int e0, int e1, int nb, int slot0) {
+  for (int tb = threadIdx.x; tb + 1 < nb; tb += NT) {
+    const int es = e0 + tb * 128, ee = min(es + 128, e1);
+    const int ce = a.edge_c[ee - 1];
+    const int rb = a.rowptr[ce], re = a.rowptr[ce + 1];
+    if (rb < es || re <= ee) continue;
+    double acc = a.esum[ce];
+    for (int t2 = tb + 1; t2 < nb && e0 + t2 * 128 < re; ++t2) acc += a.ecarry[slot0 + t2];
+    a.esum[ce] = acc;
+  }
+}
 template <int L, int NLAYERS>
 __global__ void __launch_bounds__(NT, 2) k_fused_tc(const __grid_constant__ ChunkArgs a, const __grid_constant__ ModelW w, const __grid_constant__ TcW tw,
                                                     const __grid_constant__ FusedPlan plan) {
   using D = DimsTC<L>; constexpr int TM = 128;
   extern __shared__ __align__(1024) float sm_raw[];
-  const int ntiles = plan.info[0];
-  if (plan.info[1] > TM || plan.info[3] != 0) return;          // a centre with more than 128 edges / edge arrays too small: the host falls back
-  TcCtx c = tc_begin<L>(sm_raw, tw);
+  const int nbatch = plan.info[0];
   const int B = plan.batch;
-  int* next_tile = reinterpret_cast<int*>(c.sm + SmemTC<L>::oBAR) + 10;    // after the mbarriers / TMEM pointer
+  if (plan.info[1] > B * TM || plan.info[3] != 0) return;      // a centre with more edges than a batch holds / edge arrays too small: the host falls back
+  TcCtx c = tc_begin<L>(sm_raw, tw);
+  int* next_batch = reinterpret_cast<int*>(c.sm + SmemTC<L>::oBAR) + 10;    // after the mbarriers / TMEM pointer
+  const int slot0 = (int)blockIdx.x * B;
+  c.goff = (size_t)slot0 * TM * D::F;
+  int e0 = 0, e1 = 0;
   // one phase of one tile of the batch: geometry -> shared memory, then the phase body on the tile's private scratch slot
-  int es = 0, nvalid = 0, slot = 0;
-  auto enter = [&](int t, int tb) -> bool {
-    const int c0 = plan.tile_c0[t], c1 = plan.tile_c0[t + 1];
-    es = a.rowptr[c0];
-    nvalid = a.rowptr[c1] - es;
-    if (nvalid <= 0) return false;                              // only centres without neighbours
-    slot = (int)blockIdx.x * B + tb;
-    c.c0 = c0;
-    c.goff = (size_t)slot * TM * D::F;
-    return true;
-  };
 #define ALG_PHASE(PRE, ...)                                                      \
   _Pragma("unroll 1") for (int tb = 0; tb < nb; ++tb) {                           \
-    if (!enter(t0 + tb, tb)) continue;                                            \
+    const int es = e0 + tb * TM, nvalid = min(TM, e1 - es), slot = slot0 + tb;    \
     const GeomIn gi = tc_geom_load(a, es, nvalid);                                \
     PRE;                                                                          \
     const Geom g = tc_tile_begin<L>(a, w, c, gi, nvalid);                         \
     __VA_ARGS__;                                                                  \
     __syncthreads();                                                              \
   }
+#define ALG_FIX(ptr) fused_fixup<D::F>(a, c, e0, e1, nb, slot0, (ptr) + c.goff)
 #pragma unroll 1
   for (;;) {
-    // dynamic queue of tile batches: the result does not depend on which CTA runs a tile (fixed-point accumulation), so
-    // the kernel balances itself whatever the number of resident CTAs is.  A batch runs phase by phase (all tiles
-    // through F0, then all through FK, ...): the code of one phase stays in the instruction cache for the whole batch
-    // (with one tile at a time the 280 KB of phase code were re-fetched per tile: 37 % "no instruction" stalls)
-    if (threadIdx.x == 0) *next_tile = atomicAdd(plan.info + 5, 1);
+    // dynamic batch queue: the result does not depend on which CTA runs a batch (fixed-point accumulation), so the
+    // kernel balances itself whatever the number of resident CTAs is
+    if (threadIdx.x == 0) *next_batch = atomicAdd(plan.info + 5, 1);
     __syncthreads();
-    const int t0 = *next_tile * B;
+    const int b = *next_batch;
     __syncthreads();
-    if (t0 >= ntiles) break;
-    const int nb = min(B, ntiles - t0);
+    if (b >= nbatch) break;
+    const int bc0 = plan.batch_c0[b];
+    e0 = a.rowptr[bc0]; e1 = a.rowptr[plan.batch_c0[b + 1]];
+    const int nb = (e1 - e0 + TM - 1) / TM;
+    if (nb <= 0) continue;                                      // only centres without neighbours
+    c.c0 = bc0;
     ALG_PHASE((void)0, f0_body<L>(a, w, tw, c, g, slot, es, nvalid));
+    ALG_FIX(a.gamma[0]);
     if constexpr (NLAYERS == 1) {
       ALG_PHASE(fk_prefetch<L>(a, &c, slot, 0, gi, c.c0, c.goff), (t_body<L, true>(a, w, tw, c, g, slot, es, nvalid, 0)));
     } else if constexpr (NLAYERS == 2) {
       ALG_PHASE(fk_prefetch<L>(a, &c, slot, 0, gi, c.c0, c.goff), (fk_body<L, 'B', true>(a, w, tw, c, g, slot, es, nvalid, 0)));
+      ALG_FIX(a.gamma[1]);
       ALG_PHASE(fk_prefetch<L>(a, &c, slot, 1, gi, c.c0, c.goff), (t_body<L, false>(a, w, tw, c, g, slot, es, nvalid, 1)));
-      ALG_PHASE(bk_prefetch<L>(a, slot, 0, gi, c.c0, c.goff), (bk_body<L, 'B', true>(a, w, tw, c, g, slot, es, nvalid, 0)));
     } else {
       ALG_PHASE(fk_prefetch<L>(a, &c, slot, 0, gi, c.c0, c.goff), (fk_body<L, 'C', true>(a, w, tw, c, g, slot, es, nvalid, 0)));
+      ALG_FIX(a.gamma[1]);
       ALG_PHASE(fk_prefetch<L>(a, &c, slot, 1, gi, c.c0, c.goff), (fk_body<L, 'D', false>(a, w, tw, c, g, slot, es, nvalid, 1)));
+      ALG_FIX(a.gamma[2]);
       ALG_PHASE(fk_prefetch<L>(a, &c, slot, 2, gi, c.c0, c.goff), (t_body<L, false>(a, w, tw, c, g, slot, es, nvalid, 2)));
+    }
+    fused_fixup_e(a, e0, e1, nb, slot0);
+    ALG_FIX(a.dgamma[NLAYERS - 1]);
+    if constexpr (NLAYERS == 2) {
+      ALG_PHASE(bk_prefetch<L>(a, slot, 0, gi, c.c0, c.goff), (bk_body<L, 'B', true>(a, w, tw, c, g, slot, es, nvalid, 0)));
+      ALG_FIX(a.dgamma[0]);
+    } else if constexpr (NLAYERS == 3) {
       ALG_PHASE(bk_prefetch<L>(a, slot, 1, gi, c.c0, c.goff), (bk_body<L, 'D', false>(a, w, tw, c, g, slot, es, nvalid, 1)));
+      ALG_FIX(a.dgamma[1]);
       ALG_PHASE(bk_prefetch<L>(a, slot, 0, gi, c.c0, c.goff), (bk_body<L, 'C', true>(a, w, tw, c, g, slot, es, nvalid, 0)));
+      ALG_FIX(a.dgamma[0]);
     }
     ALG_PHASE(b0_prefetch<L>(a, slot, gi, c.c0, c.goff), b0_body<L>(a, w, tw, c, g, slot, es, nvalid));
   }
 #undef ALG_PHASE
+#undef ALG_FIX
   tc_end(c);
 }
 

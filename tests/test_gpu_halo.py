@@ -68,3 +68,38 @@ def test_stats_and_timings(ensure_built):
     assert kms[:5].min() > 0 and kn[0] == st[2]               # one F0 launch per chunk
     t = h.timings()
     assert t.min() >= 0 and t[1] > 0
+
+
+def test_comm_single_rank_self_images(ensure_built):
+    """alg_comm_* with one rank: every ghost is a periodic image of a local atom, the exchange never leaves the device.
+    forward reproduces the ghost positions bit-exactly; reverse folds the ghost forces onto their owners as a sorted
+    segmented sum -- bit-identical run to run although several images of one atom are added (no fp64 atomics)."""
+    from lmpshim import harness as H
+    from pair_allegro_b200 import capi
+    name = "Cu_r5"                                             # 4-atom cell, r_max 5: ~30 images per atom
+    atom, lst, z = load_golden(name)
+    nl, ng = atom.nlocal, atom.nghost
+    dev = torch.device("cuda:0")
+    owner = atom.owner[nl:].astype(np.int32)
+    plan = dict(recv_slices={0: (nl, nl + ng)}, send_index={0: owner}, send_shift={0: atom.x[nl:] - atom.x[owner]})
+    comm = capi.Comm(0, 1, 0)
+    comm.set_plan(plan)
+    st = torch.cuda.current_stream().cuda_stream
+    d_x = torch.from_numpy(atom.x).to(dev)
+    d_x[nl:] = float("nan")
+    comm.forward(d_x.data_ptr(), st)
+    torch.cuda.synchronize()
+    assert np.array_equal(d_x.cpu().numpy(), atom.x)
+    ref = H.reverse_comm_single_rank(atom, z["f"])
+    outs = []
+    for _ in range(3):
+        d_f = torch.from_numpy(z["f"].copy()).to(dev)
+        comm.reverse(d_f.data_ptr(), st)
+        torch.cuda.synchronize()
+        outs.append(d_f[:nl].cpu().numpy())
+    assert np.abs(outs[0] - ref).max() < 1e-12
+    assert np.array_equal(outs[0], outs[1]) and np.array_equal(outs[0], outs[2])
+    s = comm.stats()
+    assert s[0] == 0 and int(s[2]) == ng and int(s[3]) <= nl   # nothing leaves the device; <= nlocal distinct owners
+    assert np.allclose(comm.allreduce_sum([1.5, 2.5]), [1.5, 2.5])
+    comm.close()
