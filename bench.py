@@ -3,19 +3,23 @@
 analytic backward -> f/E/virial written; neighbour-list construction excluded, like LAMMPS
 "Pair" time) on N B200s of one node.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config c2|c3|c5] [--scaling weak|strong]
   torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-Workload (BASELINE.json configs[1] / configs[3], SURVEY.md section 8d "C2"/"C4"): FCC a=4.09 A,
-63^3 cells = 1,000,188 atoms PER GPU, N(0,0.05 A) jitter, 1 species, r_max 5.0, Allegro l_max=1,
-2 layers, test-yaml widths, random-init weights (seed 2), strict fp32.  N>1 = weak scaling:
-the box is replicated along the brick grid 2x1x1 / 2x2x1 / 2x2x2, one spatial sub-domain per
-rank, ghost positions (forward) and ghost forces (reverse) exchanged every step over NCCL.
+Workloads (BASELINE.json configs):
+  c2 (default; configs[1] / configs[3]): FCC a=4.09 A, 63^3 cells = 1,000,188 atoms PER GPU, N(0,0.05 A) jitter, 1 species,
+      r_max 5.0, Allegro l_max=1, 2 layers.  N>1 = weak scaling: the 1 M-atom box is replicated along the brick grid
+      2x1x1 / 2x2x1 / 2x2x2, one spatial sub-domain per rank.
+  c3 (configs[2]): water-like H/O liquid, 666,668 molecules = 2,000,004 atoms, r_max 6.0, l_max=2, 2 layers, virial every step.
+  c5 (configs[4]): Li3PO4-like 4-species box, 8,000,000 atoms, r_max 5.0, l_max=3, 3 layers; N>1 = STRONG scaling of that box.
+All: test-yaml widths (S=64, U=32, MLP 2x64, readout 32), random-init weights, strict fp32 (3xTF32 on tcgen05).
+Ghost positions (forward) and ghost forces (reverse) are exchanged every step by the product halo code (alg_comm_*:
+grouped ncclSend/ncclRecv over NVLink); per-rank energies / virials are summed with one small allreduce.
 
-One JSON line on stdout (rank 0).  `value` = device-resident steps (inputs already in HBM);
-`e2e` = the same step driven from pinned HOST buffers (x H2D, forces+energy D2H every step,
-neighbour list re-uploaded on rebuild steps only, every 10th step as in production MD).
-`--impl reference` times the reference's CPU path (oracle restatement of pair_style allegro +
+One JSON line on stdout (rank 0).  `value` = device-resident steps (inputs already in HBM, alg_compute_device, fully
+asynchronous); `e2e` = the literal plugin call alg_compute_host from HOST arrays (x / type / f in host memory, host<->device
+copies inside the call, neighbour list re-uploaded on rebuild steps only -- neighbor->ago, every 10th step as in MD).
+`--impl reference` times the reference's CPU path (the reference's own pair style compiled against the LAMMPS shim +
 libtorch TorchScript, all host threads) on a bounded sample of the same workload.
 """
 import argparse
@@ -33,28 +37,35 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-NCELL = int(os.environ.get("ALG_BENCH_NCELL", "63"))       # 63^3*4 = 1,000,188 atoms per GPU
-LATTICE = 4.09
-R_MAX = 5.0
 SKIN = 1.0
-MODEL = dict(l_max=1, num_layers=2)
-REF_SAMPLE_NCELL = int(os.environ.get("ALG_BENCH_REF_NCELL", "12"))   # 6,912-atom sample for the CPU arm
 NEIGH_EVERY = 10
+CONFIGS = {
+    "c2": dict(name="C2/C4", l_max=1, num_layers=2, type_names=["Ag"], r_max=5.0, avg_nn=26.0, seed=2, scaling="weak",
+               ncell=int(os.environ.get("ALG_BENCH_NCELL", "63")), ref_ncell=int(os.environ.get("ALG_BENCH_REF_NCELL", "12")),
+               what="FCC Ag-like, a=4.09 A, N(0,0.05 A) jitter, 1 species, r_max=5.0, Allegro l_max=1 2 layers"),
+    "c3": dict(name="C3", l_max=2, num_layers=2, type_names=["H", "O"], r_max=6.0, avg_nn=90.0, seed=3, scaling="strong",
+               nmol=int(os.environ.get("ALG_BENCH_NMOL", "666668")), ref_nmol=int(os.environ.get("ALG_BENCH_REF_NMOL", "1000")),
+               what="water-like H/O liquid (0.1 atoms/A^3), 2 species, r_max=6.0, Allegro l_max=2 2 layers, virial every step"),
+    "c5": dict(name="C5", l_max=3, num_layers=3, type_names=["Li", "P", "O", "X"], r_max=5.0, avg_nn=47.0, seed=5, scaling="strong",
+               natoms=int(os.environ.get("ALG_BENCH_NATOMS", "8000000")), ref_natoms=int(os.environ.get("ALG_BENCH_REF_NATOMS", "3000")),
+               what="Li3PO4-like 4-species jittered lattice (0.09 atoms/A^3), r_max=5.0, Allegro l_max=3 3 layers"),
+}
 
 
 def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
-def model_config(avg_nn):
+def model_config(cfg):
     from pair_allegro_b200 import modelgen
-    return modelgen.default_config(type_names=["Ag"], r_max=R_MAX, avg_num_neighbors=float(avg_nn), seed=2, **MODEL)
+    return modelgen.default_config(type_names=cfg["type_names"], r_max=cfg["r_max"], avg_num_neighbors=float(cfg["avg_nn"]), seed=cfg["seed"],
+                                   l_max=cfg["l_max"], num_layers=cfg["num_layers"])
 
 
 def flop_model(L, nl, B=8, T=1):
-    """ALGORITHMIC flops per edge of each kernel family (DESIGN.md "Roofline"): GEMM 2*K*N,
+    """ALGORITHMIC flops per edge of each phase (DESIGN.md "Roofline"): GEMM 2*K*N,
     tensor product 3 flops per CG non-zero per channel (+2 per mixed output component), forward
-    + input-gradient backward; recomputation inside the backward kernels is NOT counted."""
+    + input-gradient backward; recomputation inside the backward phases is NOT counted."""
     S, H, U, R = 64, 64, 32, 32
     tables = json.load(open(os.path.join(ROOT, "tables", "allegro_tables.json")))["L"][str(L)]
     kinds = {1: ["A"], 2: ["B", "A"], 3: ["C", "D", "A"]}[nl]
@@ -70,43 +81,63 @@ def flop_model(L, nl, B=8, T=1):
     two = 2 * ((2 * T + B) * H + H * H + H * S)
     env = 2 * S * ENVW + 2 * NSH * U
     fam = {"F0": two + 2 * S * ENVW + env, "FK": 0.0, "T": 0.0, "BK": 0.0, "B0": 0.0}
+    gemm = {"F0": two + 4 * S * ENVW, "FK": 0.0, "T": 0.0, "BK": 0.0, "B0": 0.0}       # dense-contraction share (runs on the tensor pipe)
     for k, kind in enumerate(kinds):
         if k < nl - 1:
             fam["FK"] += tp(kind) + mlp + env
+            gemm["FK"] += mlp + 2 * S * ENVW
             fam["BK"] += env + 2 * NSH * U + mlp + 2 * tp(kind)
+            gemm["BK"] += 2 * S * ENVW + 2 * S * ENVW + mlp
         else:
             fam["T"] += tp(kind) + mlp + 2 * (S * R + R) + 2 * (R + R * S) + mlp + 2 * tp(kind)
+            gemm["T"] += mlp + 2 * S * R + 2 * R * S + mlp
     fam["B0"] = env + 2 * NSH * U + 2 * ENVW * S + two + 60
-    return fam
+    gemm["B0"] = 2 * S * ENVW + 2 * S * ENVW + 2 * ENVW * S + two
+    return fam, gemm
 
 
 # ------------------------------------------------------------------------------------------
-def build_rank_system(rank, world):
-    """this rank's atoms (+ghosts), full neighbour list and halo plan"""
+def config_box(cfg, world, scaling):
+    """(pos, types, cell) of the WHOLE periodic box for `world` ranks"""
     from lmpshim import harness as H
-    grid = H.proc_grid(world)
+    if "ncell" in cfg:
+        pos, types, cell = H.fcc_box(cfg["ncell"], a=4.09, jitter=0.05, seed=cfg["seed"])
+    elif "nmol" in cfg:
+        pos, types, cell = H.water_like_box(cfg["nmol"], density=0.1, seed=cfg["seed"])
+    else:
+        pos, types, cell = H.multi_species_box(cfg["natoms"], fractions=(3, 1, 4, 0.5), density=0.09, seed=cfg["seed"])
+    if scaling == "weak" and world > 1:
+        # exact periodic replicas of the single-GPU box along the brick grid: the N-rank energy is N x the single-box energy
+        grid = H.proc_grid(world)
+        L = np.diag(cell)
+        reps = [np.array([a, b, c]) * L for a in range(grid[0]) for b in range(grid[1]) for c in range(grid[2])]
+        pos = np.concatenate([pos + r for r in reps])
+        types = np.tile(types, len(reps))
+        cell = np.diag(L * np.array(grid))
+    return pos, types, cell
+
+
+def build_rank_system(cfg, rank, world, scaling, dev):
+    """this rank's atoms (+ghosts), halo plan and FULL neighbour list (torch, on the device)"""
+    from lmpshim import harness as H
+    from lmpshim.nlist_torch import as_neighlist, build_full_list_torch
     t0 = time.time()
-    rng = np.random.default_rng(2)
-    n = [NCELL * g for g in grid]
-    base = np.array([[0, 0, 0], [0.5, 0.5, 0], [0.5, 0, 0.5], [0, 0.5, 0.5]])
-    g = np.stack(np.meshgrid(np.arange(n[0]), np.arange(n[1]), np.arange(n[2]), indexing="ij"), -1).reshape(-1, 3)
-    pos = (g[:, None, :] + base[None]).reshape(-1, 3) * LATTICE
-    pos = pos + rng.normal(0.0, 0.05, pos.shape)
-    types = np.ones(len(pos), dtype=np.int32)
-    cell = np.diag([LATTICE * k for k in n])
-    rcomm = R_MAX + SKIN
+    pos, types, cell = config_box(cfg, world, scaling)
+    rcomm = cfg["r_max"] + SKIN
     if world == 1:
         atoms = H.make_single_rank(types, pos, cell, [True] * 3, rcomm)
+        own = atoms.owner[atoms.nlocal:].astype(np.int32)
         # single rank: every ghost is an image of a local atom -> self halo plan
-        plan = dict(recv_slices={0: (atoms.nlocal, atoms.nlocal + atoms.nghost)},
-                    send_index={0: atoms.owner[atoms.nlocal:].astype(np.int32)},
-                    send_shift={0: atoms.x[atoms.nlocal:] - atoms.x[atoms.owner[atoms.nlocal:]]})
+        plan = dict(recv_slices={0: (atoms.nlocal, atoms.nlocal + atoms.nghost)}, send_index={0: own}, send_shift={0: atoms.x[atoms.nlocal:] - atoms.x[own]})
     else:
         atoms, plan = H.decompose_rank(pos, types, cell, [True] * 3, world, rank, rcomm)
-    del pos, g
-    lst = H.build_full_list(atoms, rcomm)
-    log("[rank %d] atoms %d ghosts %d candidates %d (harness %.1fs)" % (rank, atoms.nlocal, atoms.nghost, int(lst.numneigh.sum()), time.time() - t0))
-    return atoms, lst, plan
+    ntotal = len(pos)
+    del pos
+    t1 = time.time()
+    res = build_full_list_torch(atoms.x, atoms.nlocal, rcomm, device=dev)
+    lst = as_neighlist(atoms, res)
+    log("[rank %d] atoms %d ghosts %d candidates %d (domains %.1fs, neighbour list %.1fs)" % (rank, atoms.nlocal, atoms.nghost, res["candidates"], t1 - t0, time.time() - t1))
+    return atoms, lst, plan, res, ntotal
 
 
 class ClockSampler:
@@ -222,11 +253,20 @@ def measured_peaks():
 
 
 # ------------------------------------------------------------------------------------------
-def cpu_reference_run(steps, warmup, threads=None):
-    """the reference's CPU path on a bounded sample (FCC REF_SAMPLE_NCELL^3 cells) of the same
-    workload: the reference's OWN pair style (oracle/_ref, compiled from
-    /root/reference/pair_nequip_allegro.cpp against lmpshim + libtorch) when it was built, else
-    the Python restatement oracle/ref_pair.py.  CUDA is hidden from libtorch (CPU path)."""
+def sample_box(cfg):
+    """bounded sample of the config's workload for the CPU arm (same generator, same density, fewer atoms)"""
+    from lmpshim import harness as H
+    if "ncell" in cfg:
+        return H.fcc_box(cfg["ref_ncell"], a=4.09, jitter=0.05, seed=cfg["seed"]), "FCC %d^3 cells" % cfg["ref_ncell"]
+    if "nmol" in cfg:
+        return H.water_like_box(cfg["ref_nmol"], density=0.1, seed=cfg["seed"]), "%d water-like molecules" % cfg["ref_nmol"]
+    return H.multi_species_box(cfg["ref_natoms"], fractions=(3, 1, 4, 0.5), density=0.09, seed=cfg["seed"]), "%d-atom 4-species box" % cfg["ref_natoms"]
+
+
+def cpu_reference_run(cfg, steps, warmup, threads=None):
+    """the reference's CPU path on a bounded sample of the same workload: the reference's OWN pair style (oracle/_ref,
+    compiled from /root/reference/pair_nequip_allegro.cpp against lmpshim + libtorch) when it was built, else the Python
+    restatement oracle/ref_pair.py.  CUDA is hidden from libtorch (CPU path)."""
     os.environ["CUDA_VISIBLE_DEVICES"] = ""
     import torch
     from lmpshim import driver
@@ -237,20 +277,22 @@ def cpu_reference_run(steps, warmup, threads=None):
     threads = threads or os.cpu_count() or 1
     torch.set_num_threads(threads)
     os.environ.setdefault("OMP_NUM_THREADS", str(threads))
-    pos, types, cell = H.fcc_box(REF_SAMPLE_NCELL, a=LATTICE, jitter=0.05, seed=2)
-    atoms = H.make_single_rank(types, pos, cell, [True] * 3, R_MAX + SKIN)
-    lst = H.build_full_list(atoms, R_MAX + SKIN)
+    (pos, types, cell), box_desc = sample_box(cfg)
+    rn = cfg["r_max"] + SKIN
+    atoms = H.make_single_rank(types, pos, cell, [True] * 3, rn)
+    lst = H.build_full_list(atoms, rn)
     d = tempfile.mkdtemp(prefix="alg_ref_")
-    pth = os.path.join(d, "c2.nequip.pth")
-    alg = os.path.join(d, "c2.alg")
-    modelgen.random_alg(model_config(26.0), alg)        # the weights the GPU arm evaluates ...
+    pth = os.path.join(d, "m.nequip.pth")
+    alg = os.path.join(d, "m.alg")
+    modelgen.random_alg(model_config(cfg), alg)          # the weights the GPU arm evaluates ...
     AT.save_torchscript_from_alg(alg, pth)               # ... as the TorchScript artifact the reference loads
-    E = int((((atoms.x[np.repeat(np.arange(atoms.nlocal), lst.numneigh[:atoms.nlocal])] - atoms.x[lst.neigh_flat]) ** 2).sum(1) <= R_MAX ** 2).sum())
+    E = int((((atoms.x[np.repeat(np.arange(atoms.nlocal), lst.numneigh[:atoms.nlocal])] - atoms.x[lst.neigh_flat]) ** 2).sum(1) <= cfg["r_max"] ** 2).sum())
+    names = cfg["type_names"][:atoms.ntypes]
     if os.path.exists(driver.REF_LIB):
         kind = "reference"
         lmp = driver.ShimLammps(driver.REF_LIB, atoms, lst)
         lmp.pair_style([])
-        lmp.pair_coeff(["*", "*", pth, "Ag"])
+        lmp.pair_coeff(["*", "*", pth] + names)
         lmp.init(newton_pair=1)
         step = lambda: lmp.compute(eflag=3, vflag=1)
         what = "the reference's own PairNequIPAllegro<false>::compute (oracle/_ref: unmodified sources + lmpshim + libtorch TorchScript)"
@@ -258,7 +300,7 @@ def cpu_reference_run(steps, warmup, threads=None):
         kind = "port"
         pair = RefPairAllegro()
         pair.settings([])
-        pair.coeff(["*", "*", pth, "Ag"], 1)
+        pair.coeff(["*", "*", pth] + names, atoms.ntypes)
         pair.init_style()
 
         def step():
@@ -272,21 +314,22 @@ def cpu_reference_run(steps, warmup, threads=None):
         step()
     dt = time.perf_counter() - t0
     return dict(value=atoms.nlocal * steps / dt / 1e6, ms_per_step=dt / steps * 1e3, atoms=atoms.nlocal, edges=E, cores=threads, kind=kind,
-                sample="FCC %d^3 cells = %d atoms (%d edges), %d evals of %s, %d threads, torch %s"
-                       % (REF_SAMPLE_NCELL, atoms.nlocal, E, steps, what, threads, torch.__version__))
+                sample="%s = %d atoms (%d edges), %d evals of %s, %d threads, torch %s"
+                       % (box_desc, atoms.nlocal, E, steps, what, threads, torch.__version__))
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
+    cfg = CONFIGS[args.config]
     steps = max(1, args.steps)
     warm = max(1, min(args.warmup, 3))
-    r = cpu_reference_run(steps, warm)
+    r = cpu_reference_run(cfg, steps, warm)
     line = {"impl": "reference", "metric": "Matom-steps/s force eval", "value": r["value"], "unit": "Matom-steps/s", "n_gpus": args.gpus,
-            "steps": steps, "warmup": warm, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+            "steps": steps, "warmup": warm, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": args.scaling or cfg["scaling"],
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "C2 FCC Ag-like 1-species r_max=5 Allegro l_max=1 2 layers random-init (bounded CPU sample)",
+            "config": {"workload": "%s: %s, random-init (bounded CPU sample)" % (cfg["name"], cfg["what"]),
                        "sample_atoms": r["atoms"], "sample_edges": r["edges"]},
             "cpu_baseline": {"value": r["value"], "unit": "Matom-steps/s", "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]},
             "e2e": {"value": r["value"], "unit": "Matom-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -295,60 +338,29 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------
-class Halo:
-    """forward ghost-position / reverse ghost-force exchange (LAMMPS comm->forward_comm /
-    reverse_comm for x and f, required by newton on -- pair_nequip_allegro.cpp:149): device
-    pack/unpack kernels from the C-ABI + NCCL point-to-point between ranks; images owned by the
-    rank itself are handled on the device without NCCL."""
-
-    def __init__(self, plan, rank, world, dev, lib):
-        import torch
-        self.torch = torch
-        self.rank, self.world, self.lib = rank, world, lib
-        self.recv = plan["recv_slices"]
-        self.send_idx = {s: torch.from_numpy(v).to(dev) for s, v in plan["send_index"].items()}
-        self.send_shift = {s: torch.from_numpy(np.ascontiguousarray(v)).to(dev) for s, v in plan["send_shift"].items()}
-        self.sbuf = {s: torch.empty(len(v), 3, dtype=torch.float64, device=dev) for s, v in plan["send_index"].items()}
-        self.bytes_per_step = 0
-        for s, v in plan["send_index"].items():
-            if s != rank:
-                self.bytes_per_step += 2 * 24 * len(v)
-
-    def _stream(self):
-        return self.torch.cuda.current_stream().cuda_stream
-
-    def forward(self, d_x):
-        import torch.distributed as dist
-        ops = []
-        for s, idx in self.send_idx.items():
-            buf = self.sbuf[s] if s != self.rank else d_x[self.recv[s][0]:self.recv[s][1]]
-            rc = self.lib.alg_halo_pack(d_x.data_ptr(), idx.data_ptr(), idx.numel(), self.send_shift[s].data_ptr(), buf.data_ptr(), self._stream())
-            assert rc == 0
-            if s != self.rank:
-                ops.append(dist.P2POp(dist.isend, buf, s))
-        for s, (a, b) in self.recv.items():
-            if s != self.rank:
-                ops.append(dist.P2POp(dist.irecv, d_x[a:b], s))
-        if ops:
-            for w in dist.batch_isend_irecv(ops):
-                w.wait()
-
-    def reverse(self, d_f):
-        import torch.distributed as dist
-        ops = []
-        for s, (a, b) in self.recv.items():
-            if s != self.rank:
-                ops.append(dist.P2POp(dist.isend, d_f[a:b], s))
-        for s in self.send_idx:
-            if s != self.rank:
-                ops.append(dist.P2POp(dist.irecv, self.sbuf[s], s))
-        if ops:
-            for w in dist.batch_isend_irecv(ops):
-                w.wait()
-        for s, idx in self.send_idx.items():
-            buf = self.sbuf[s] if s != self.rank else d_f[self.recv[s][0]:self.recv[s][1]]
-            rc = self.lib.alg_halo_unpack_add(d_f.data_ptr(), idx.data_ptr(), idx.numel(), buf.data_ptr(), self._stream())
-            assert rc == 0
+def tf32_dense_peak(dev):
+    """measured dense TF32 tensor-core throughput of this GPU (cuBLAS, torch.matmul with allow_tf32): the peak the kind::tf32
+    MMAs of the strict (3xTF32) path execute against"""
+    import torch
+    old = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = True
+    try:
+        n = 8192
+        a = torch.randn(n, n, device=dev)
+        b = torch.randn(n, n, device=dev)
+        for _ in range(2):
+            a @ b
+        best = 0.0
+        for _ in range(5):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            a @ b
+            e1.record()
+            torch.cuda.synchronize()
+            best = max(best, 2.0 * n ** 3 / (e0.elapsed_time(e1) * 1e-3) / 1e12)
+        return best
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = old
 
 
 def run_ours(args):
@@ -357,6 +369,8 @@ def run_ours(args):
     from pair_allegro_b200 import capi, modelgen
     from pair_allegro_b200.pair import PairAllegroB200
 
+    cfg = CONFIGS[args.config]
+    scaling = args.scaling or cfg["scaling"]
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -369,46 +383,63 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
     K, W = max(1, args.steps), max(3, args.warmup)
 
-    atoms, lst, plan = build_rank_system(rank, world)
+    atoms, lst, plan, nres, ntotal = build_rank_system(cfg, rank, world, scaling, dev)
     nl, ng = atoms.nlocal, atoms.nghost
     ntot = nl + ng
-    # model files (random init; identical on every rank)
+    names = cfg["type_names"][:atoms.ntypes] if atoms.ntypes <= len(cfg["type_names"]) else cfg["type_names"]
+    # model file (random init; identical on every rank)
     d = tempfile.mkdtemp(prefix="alg_bench_")
-    alg = os.path.join(d, "c2.alg")
-    modelgen.random_alg(model_config(26.0), alg)          # numpy random init, same seed on every rank (no oracle involved)
-    pair = PairAllegroB200(device=local_rank, debug_mode=False)
-    pair.settings([])
-    pair.coeff(["*", "*", alg, "Ag"], 1)
-    pair.init_style()
+    alg = os.path.join(d, "m.alg")
+    modelgen.random_alg(model_config(cfg), alg)          # numpy random init, same seed on every rank (no oracle involved)
+
+    def make_pair(pin):
+        pr = PairAllegroB200(device=local_rank, debug_mode=False, pin_host=pin)
+        pr.settings([])
+        pr.coeff(["*", "*", alg] + cfg["type_names"][:atoms.ntypes], atoms.ntypes)
+        pr.init_style()
+        hh = pr.handle
+        if args.chunk_edges:
+            hh.set_option("chunk_edges", str(args.chunk_edges))
+        if cfg["l_max"] <= 2 or args.gemm == "ffma":
+            hh.set_option("gemm", args.gemm)      # tc: tcgen05 tensor cores | ffma: FP32 pipe
+        if args.gemm == "tc":
+            hh.set_option("precision", args.precision)
+        hh.set_option("pipeline", args.pipeline)
+        if args.fused_batch:
+            hh.set_option("fused_batch", str(args.fused_batch))
+        return pr
+
+    pair = make_pair(True)
     h = pair.handle
-    if args.chunk_edges:
-        h.set_option("chunk_edges", str(args.chunk_edges))
-    h.set_option("gemm", args.gemm)           # tc: tcgen05 tensor cores (default for l_max=1) | ffma: FP32 pipe
-    if args.gemm == "tc":
-        h.set_option("precision", args.precision)
-    lib = capi.load_library()
+    # ---- halo: product code (alg_comm_*), NCCL id distributed over the torch.distributed rendezvous
+    ident = None
+    if world > 1:
+        idt = torch.zeros(128, dtype=torch.uint8, device=dev)
+        if rank == 0:
+            idt = torch.frombuffer(bytearray(capi.Comm.unique_id()), dtype=torch.uint8).to(dev)
+        dist.broadcast(idt, src=0)
+        ident = bytes(idt.cpu().numpy().tobytes())
+    comm = capi.Comm(local_rank, world, rank, ident)
+    comm.set_plan(plan)
 
     # ---- device-resident inputs (the Kokkos-style entry: alg_compute_device)
-    maxn = int(lst.numneigh[:nl].max())
-    nb = np.zeros((nl, maxn), dtype=np.int32)
-    cols = np.arange(len(lst.neigh_flat)) - np.repeat(lst.first[:nl], lst.numneigh[:nl])
-    nb[np.repeat(np.arange(nl), lst.numneigh[:nl]), cols] = lst.neigh_flat
-    d_nb = torch.from_numpy(nb).to(dev)
-    d_num = torch.from_numpy(lst.numneigh[:nl].copy()).to(dev)
+    maxn = int(nres["maxn"])
+    d_nb, d_num = nres["nb2d"], nres["numneigh"]
+    h.set_option("max_neighbors", str(maxn))
     d_x = torch.from_numpy(atoms.x).to(dev)
     d_type = torch.from_numpy(atoms.type).to(dev)
     d_ilist = torch.arange(nl, dtype=torch.int32, device=dev)
     d_f = torch.zeros(ntot, 3, dtype=torch.float64, device=dev)
-    halo = Halo(plan, rank, world, dev, lib)
     cs = torch.cuda.current_stream().cuda_stream
+    vflag = True
 
     def step_device(scalars=False):
         d_f.zero_()
-        halo.forward(d_x)
+        comm.forward(d_x.data_ptr(), cs)
         eng, vir = h.compute_device(nl, ng, d_x.data_ptr(), d_type.data_ptr(), d_ilist.data_ptr(), d_num.data_ptr(), d_nb.data_ptr(),
-                                    maxn, 1, d_f.data_ptr(), 0, want_scalars=scalars, vflag=True, stream=cs)
-        halo.reverse(d_f)
-        return eng
+                                    maxn, 1, d_f.data_ptr(), 0, want_scalars=scalars, vflag=vflag, stream=cs)
+        comm.reverse(d_f.data_ptr(), cs)
+        return eng, vir
 
     def barrier():
         if world > 1:
@@ -433,9 +464,38 @@ def run_ours(args):
 
     for _ in range(W):
         step_device()
-    eng0 = step_device(scalars=True)
+    eng0, vir0 = step_device(scalars=True)
+    torch.cuda.synchronize()
     stats = h.stats("step", 4)
+    pipe = h.stats("pipeline", 3)
     E = int(stats[1])
+    tot = comm.allreduce_sum(np.concatenate([[eng0], vir0, d_f[:nl].sum(0).cpu().numpy()]), cs)      # LAMMPS' MPI_Allreduce of eng_vdwl / virial
+    eng_total, fsum = float(tot[0]), tot[7:10]
+    # ---- parity guards of the multi-GPU run (asserted, not just printed)
+    assert np.abs(fsum).max() < 1e-6 * max(1.0, ntotal) ** 0.5 + 1e-3, "total force on the periodic box is not zero: %r" % (fsum,)
+    energy_check = {"total": eng_total, "sum_force": [float(v) for v in fsum]}
+    if world > 1 and scaling == "weak" and not args.no_energy_check:
+        # the N-rank box is N exact periodic replicas of the single-GPU box: its energy must be N x the single-box energy
+        e1box = None
+        if rank == 0:
+            from lmpshim import harness as H
+            from lmpshim.nlist_torch import build_full_list_torch
+            pos1, types1, cell1 = config_box(cfg, 1, "weak")
+            a1 = H.make_single_rank(types1, pos1, cell1, [True] * 3, cfg["r_max"] + SKIN)
+            r1 = build_full_list_torch(a1.x, a1.nlocal, cfg["r_max"] + SKIN, device=dev, want_host=False)
+            p1 = make_pair(False)
+            x1 = torch.from_numpy(a1.x).to(dev); t1 = torch.from_numpy(a1.type).to(dev)
+            f1 = torch.zeros(a1.nlocal + a1.nghost, 3, dtype=torch.float64, device=dev)
+            il1 = torch.arange(a1.nlocal, dtype=torch.int32, device=dev)
+            e1box, _ = p1.handle.compute_device(a1.nlocal, a1.nghost, x1.data_ptr(), t1.data_ptr(), il1.data_ptr(), r1["numneigh"].data_ptr(),
+                                                r1["nb2d"].data_ptr(), int(r1["maxn"]), 1, f1.data_ptr(), 0, want_scalars=True, stream=cs)
+            torch.cuda.synchronize()
+            del p1, x1, t1, f1, il1, r1, a1
+            rel = abs(eng_total - world * e1box) / max(1.0, abs(world * e1box))
+            log("[energy check] %d ranks: %.6f  vs  %d x single box %.6f  (rel %.2e)" % (world, eng_total, world, e1box, rel))
+            assert rel < 1e-6, "multi-GPU energy differs from N x the single-box energy"
+            energy_check.update({"single_box": e1box, "rel_diff_vs_n_x_single": rel})
+        barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()
     ms = timed(step_device, K)
@@ -446,98 +506,109 @@ def run_ours(args):
         dist.all_reduce(t)
         total_atoms = int(t.item())
     value = total_atoms * K / (ms * 1e-3) / 1e6
-    launches_per_step = int(stats[0]) + (3 * len(halo.send_idx))   # + halo pack/unpack kernels (+zero_)
+    launches_per_step = int(stats[0]) + 3      # + halo pack, unpack, zero_
 
     # ---- per-kernel timing pass (CUDA events inside the library, profile=1) for the roofline
     h.set_option("profile", "1")
-    kms = np.zeros(6)
-    kn = np.zeros(6)
+    NK = len(capi.KERNEL_FAMILIES)
+    kms, kn = np.zeros(NK), np.zeros(NK)
     PS = 3
     for _ in range(PS):
         step_device(scalars=True)
-        kms += h.stats("kernel_ms", 6)
-        kn += h.stats("kernel_launches", 6)
+        kms += h.stats("kernel_ms", NK)
+        kn += h.stats("kernel_launches", NK)
     h.set_option("profile", "0")
     kms /= PS
     kn /= PS
-    fam = flop_model(MODEL["l_max"], MODEL["num_layers"])
-    names = capi.KERNEL_FAMILIES
-    dom = int(np.argmax(kms[:5]))
+    fam, gemmf = flop_model(cfg["l_max"], cfg["num_layers"], T=len(cfg["type_names"]))
+    names_k = capi.KERNEL_FAMILIES
     peaks = measured_peaks()
-    dom_name = names[dom]
-    flops_per_launch = fam[dom_name] * E / max(kn[dom], 1)
-    dur = kms[dom] / max(kn[dom], 1) * 1e-3
+    tf32_peak = tf32_dense_peak(dev) if rank == 0 else None
+    passes = 3 if args.precision == "strict" else 1
+    fused = bool(pipe[0])
+    alg_flops_edge = float(sum(fam.values()))
+    gemm_flops_edge = float(sum(gemmf.values()))
+    if fused:
+        dom_name, dur, nlaunch = "k_fused_tc", kms[6] * 1e-3, max(kn[6], 1)
+        flops_per_launch = alg_flops_edge * E / nlaunch
+        gemm_per_launch = gemm_flops_edge * E / nlaunch
+        dur = dur / nlaunch
+    else:
+        dom = int(np.argmax(kms[:5]))
+        dom_name = "k_" + names_k[dom].lower() + ("_tc" if h.stats("pipeline", 3)[1] > 0 and args.gemm == "tc" else "")
+        nlaunch = max(kn[dom], 1)
+        dur = kms[dom] / nlaunch * 1e-3
+        flops_per_launch = fam[names_k[dom]] * E / nlaunch
+        gemm_per_launch = gemmf[names_k[dom]] * E / nlaunch
     achieved = flops_per_launch / dur / 1e12
     traffic = None
     tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
     if os.path.exists(tp):
         try:
             tj = json.load(open(tp))
-            if dom_name in tj:
-                traffic = tj[dom_name]["dram_bytes_per_edge"] * E / max(kn[dom], 1)
+            key = "fused_%s" % args.config if fused else names_k[dom]
+            if key in tj:
+                traffic = tj[key]["dram_bytes_per_edge"] * E / nlaunch
         except Exception:
             pass
-    sm_clock = (clocks.get("sm_mhz") or 1965.0) * 1e6
-    if args.gemm == "tc":
-        note = ("dense contractions on tcgen05 (kind::tf32, TMEM accumulators, TMA-fed weights); precision=%s -> %d TF32 MMA pass(es) per GEMM, "
-                "i.e. executed tensor flops = %dx the algorithmic GEMM flops; peak quoted is the measured dense bf16 figure (TF32 dense peak is half of it)"
-                % (args.precision, 3 if args.precision == "strict" else 1, 3 if args.precision == "strict" else 1))
-    else:
-        note = ("FP32-pipe path (gemm=ffma): fp32 pipe peak at the sampled clock = %.1f TFLOP/s, frac_of_fp32_pipe = %.3f"
-                % (148 * 128 * 2 * sm_clock / 1e12, achieved / (148 * 128 * 2 * sm_clock / 1e12)))
-    roofline = {"bound": "tensor", "kernel": "k_" + dom_name.lower() + ("_tc" if args.gemm == "tc" else ""), "achieved": achieved, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
-                "frac": achieved / peaks["bf16_sustained"], "traffic": traffic, "peak_source": peaks["source"] + " bf16 sustained (MEASURED_PEAKS.json)" if peaks["source"] == "measured" else "fallback (B200_PROFILING.md)",
-                "note": note,
-                "launch_ms": dur * 1e3, "launches_per_step": float(kn[dom]),
-                "kernel_ms_per_step": {names[i]: float(kms[i]) for i in range(6)},
-                "algorithmic_flops_per_edge": {k: float(v) for k, v in fam.items()}}
+    executed_tensor = gemm_per_launch * passes / dur / 1e12
+    roofline = {"bound": "tensor", "kernel": dom_name, "achieved": achieved, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
+                "frac": achieved / peaks["bf16_sustained"], "traffic": traffic,
+                "peak_source": peaks["source"] + " bf16 sustained (MEASURED_PEAKS.json)" if peaks["source"] == "measured" else "fallback (B200_PROFILING.md)",
+                "launch_ms": dur * 1e3, "launches_per_step": float(nlaunch),
+                "algorithmic_flops_per_edge": alg_flops_edge, "gemm_flops_per_edge": gemm_flops_edge, "edges_per_launch": E / nlaunch,
+                "executed_tensor_tflops": executed_tensor, "tf32_dense_peak_measured": tf32_peak,
+                "frac_of_tf32_peak_executed": (executed_tensor / tf32_peak) if tf32_peak else None,
+                "note": ("achieved = ALGORITHMIC fp32 flops (GEMM 2KN + tensor products, forward + input-gradient backward) per launch / CUDA-event launch time; "
+                         "the dense contractions run on tcgen05 kind::tf32 with %d MMA pass(es) per GEMM (strict = 3xTF32), so the tensor pipe executes "
+                         "executed_tensor_tflops = %dx the algorithmic GEMM flops, to be read against tf32_dense_peak_measured (cuBLAS TF32, this GPU); "
+                         "the contract's peak is the measured dense bf16 figure" % (passes, passes)),
+                "kernel_ms_per_step": {names_k[i]: float(kms[i]) for i in range(NK)},
+                "algorithmic_flops_per_edge_by_phase": {k: float(v) for k, v in fam.items()}}
+    if not fused:
+        roofline["per_kernel"] = {names_k[i]: {"ms_per_step": float(kms[i]), "algorithmic_tflops": float(fam[names_k[i]] * E / max(kms[i], 1e-9) / 1e9),
+                                               "frac_of_bf16_peak": float(fam[names_k[i]] * E / max(kms[i], 1e-9) / 1e9 / peaks["bf16_sustained"])} for i in range(5)}
 
-    # ---- e2e: pinned host buffers, H2D x / D2H f+E every step, list re-upload every NEIGH_EVERY steps
-    h_x = torch.from_numpy(atoms.x[:nl].copy()).pin_memory()
-    h_f = torch.empty(nl, 3, dtype=torch.float64).pin_memory()
-    h_nb = torch.from_numpy(nb).pin_memory()
-    h_num = torch.from_numpy(lst.numneigh[:nl].copy()).pin_memory()
+    # ---- e2e: the literal plugin call (alg_compute_host) from HOST arrays; the neighbour list is re-uploaded every NEIGH_EVERY
+    #      steps (LAMMPS passes neighbor->ago), x / type / f cross PCIe inside the call every step
     counter = {"i": 0}
 
     def step_e2e():
-        if counter["i"] % NEIGH_EVERY == 0:
-            d_nb.copy_(h_nb, non_blocking=True)
-            d_num.copy_(h_num, non_blocking=True)
+        atoms.f[:] = 0
+        pair.compute(atoms, lst, eflag=1, vflag=1, eflag_atom=0, neigh_ago=counter["i"] % NEIGH_EVERY)
         counter["i"] += 1
-        d_x[:nl].copy_(h_x, non_blocking=True)
-        eng = step_device(scalars=True)
-        h_f.copy_(d_f[:nl], non_blocking=True)
-        torch.cuda.current_stream().synchronize()
-        return eng
 
     for _ in range(2):
         step_e2e()
     counter["i"] = 0
-    ms_e2e = timed(step_e2e, K)
-    e2e_val = total_atoms * K / (ms_e2e * 1e-3) / 1e6
-    h2d = 24 * nl + (nb.nbytes + 4 * nl) / NEIGH_EVERY
-    d2h = 24 * nl + 56 + 4 * (nl + 1)
+    KE = max(K, NEIGH_EVERY) if args.e2e_full_cycle else K
+    ms_e2e = timed(step_e2e, KE)
+    e2e_val = total_atoms * KE / (ms_e2e * 1e-3) / 1e6
+    list_bytes = 4 * int(lst.numneigh[:nl].sum()) + 16 * nl
+    uploads = len([i for i in range(KE) if i % NEIGH_EVERY == 0])
+    h2d = (24 + 4 + 24) * ntot + list_bytes * uploads / KE
+    d2h = 24 * ntot + 7 * 8 + 64
     extra = {}
-    if world == 1:   # the literal host entry point (alg_compute_host: everything incl. the list from host memory, every step)
-        t0 = time.perf_counter()
-        for _ in range(3):
-            atoms.f[:] = 0
-            pair.compute(atoms, lst, eflag_atom=0)
-        extra["e2e_host_api_list_every_step"] = {"value": nl * 3 / (time.perf_counter() - t0) / 1e6, "unit": "Matom-steps/s",
-                                                 "note": "alg_compute_host from pageable numpy buffers, neighbour list flattened+uploaded every step"}
-        # same entry point the way the LAMMPS pair style drives it: neighbor->ago > 0 between list rebuilds
-        t0 = time.perf_counter()
-        for i in range(NEIGH_EVERY):
-            atoms.f[:] = 0
-            pair.compute(atoms, lst, eflag_atom=0, neigh_ago=i)
-        extra["e2e_host_api"] = {"value": nl * NEIGH_EVERY / (time.perf_counter() - t0) / 1e6, "unit": "Matom-steps/s",
-                                 "note": "alg_compute_host from pageable numpy buffers (x up, f down every step), neighbour list uploaded every %d steps (option neigh_ago = neighbor->ago)" % NEIGH_EVERY}
+    # the same through the device entry with pinned host staging + the halo (what a GPU-resident caller with host I/O pays)
+    h_x = torch.from_numpy(atoms.x[:nl].copy()).pin_memory()
+    h_f = torch.empty(nl, 3, dtype=torch.float64).pin_memory()
+
+    def step_e2e_dev():
+        d_x[:nl].copy_(h_x, non_blocking=True)
+        step_device(scalars=True)
+        h_f.copy_(d_f[:nl], non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    step_e2e_dev()
+    ms_e2e_dev = timed(step_e2e_dev, K)
+    extra["e2e_device_entry"] = {"value": total_atoms * K / (ms_e2e_dev * 1e-3) / 1e6, "unit": "Matom-steps/s",
+                                 "note": "pinned host x -> device, NCCL halo, alg_compute_device (scalars read back), local forces -> pinned host, every step"}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         # separate process: libtorch must not see the GPU (CPU path), and its threads must not fight ours
         try:
-            rr = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "3", "--warmup", "1"],
+            rr = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--config", args.config, "--steps", "3", "--warmup", "1"],
                                 capture_output=True, text=True, timeout=900, env=dict(os.environ, CUDA_VISIBLE_DEVICES=""))
             cpu = json.loads(rr.stdout.strip().splitlines()[-1])["cpu_baseline"]
         except Exception as ex:   # the baseline is a reported number; never let it kill the GPU result
@@ -545,19 +616,24 @@ def run_ours(args):
 
     if rank == 0:
         grid = {1: "1x1x1", 2: "2x1x1", 4: "2x2x1", 8: "2x2x2"}[world]
+        cst = comm.stats()
         line = {"metric": "Matom-steps/s force eval", "value": value, "unit": "Matom-steps/s", "n_gpus": world, "steps": K, "warmup": W,
-                "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": "C2/C4: FCC Ag-like %d^3 cells per GPU (%d atoms/GPU, %d edges on rank 0), r_max=5.0, Allegro l_max=1 2 layers S=64 U=32 MLP 2x64, random-init seed 2, strict fp32"
-                                       % (NCELL, nl, E), "domains": grid, "atoms_total": total_atoms, "ghosts_rank0": ng,
+                "ms_per_step": ms / K, "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": "%s: %s; %d atoms in total (%d on rank 0, %d edges on rank 0), S=64 U=32 MLP 2x64 readout 32, random-init seed %d, strict fp32"
+                                       % (cfg["name"], cfg["what"], total_atoms, nl, E, cfg["seed"]),
+                           "domains": grid, "atoms_total": total_atoms, "ghosts_rank0": ng,
                            "l2_policy": "inputs larger than L2 (neighbour list + per-edge state >> 126 MB); no explicit flush",
-                           "halo": "NCCL p2p forward x / reverse f every step" if world > 1 else "self-image halo on device every step",
-                           "chunk_edges": int(args.chunk_edges or 1 << 21), "gemm": args.gemm, "precision": args.precision},
+                           "halo": "alg_comm_* (product code): grouped ncclSend/ncclRecv forward x / reverse f every step" if world > 1 else "periodic self-image halo on the device every step (alg_comm_*, no NCCL)",
+                           "pipeline": "fused" if fused else "tiled", "fused_batch": int(args.fused_batch or 8), "gemm": args.gemm if cfg["l_max"] <= 2 or args.gemm == "ffma" else "tc", "precision": args.precision},
                 "clocks": clocks, "gpu_launches": launches_per_step * K,
                 "e2e": {"value": e2e_val, "unit": "Matom-steps/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                        "ms_per_step": ms_e2e / K, "neigh_upload_every": NEIGH_EVERY},
-                "roofline": roofline, "cpu_baseline": cpu, "energy_check": eng0, "halo_bytes_per_step": halo.bytes_per_step}
+                        "ms_per_step": ms_e2e / KE, "steps": KE, "neigh_upload_every": NEIGH_EVERY,
+                        "api": "alg_compute_host (host arrays; x, type, f H2D and f D2H inside the call; neigh_ago = step % 10)"},
+                "roofline": roofline, "cpu_baseline": cpu, "energy_check": energy_check,
+                "halo_bytes_per_step": int(cst[0] + cst[1])}
         line.update(extra)
         print(json.dumps(line), flush=True)
+    comm.close()
     if world > 1:
         dist.destroy_process_group()
     return 0
@@ -569,9 +645,15 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="c2", choices=sorted(CONFIGS))
+    ap.add_argument("--scaling", default=None, choices=["weak", "strong"], help="default: weak for c2, strong for c3 / c5")
     ap.add_argument("--chunk-edges", type=int, default=0)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-energy-check", action="store_true", help="N>1 weak scaling: skip the N x single-box energy assertion")
+    ap.add_argument("--e2e-full-cycle", action="store_true", help="time at least one full neighbour-list cycle (10 steps) in the e2e leg")
     ap.add_argument("--gemm", default="tc", choices=["tc", "ffma"])
+    ap.add_argument("--pipeline", default="auto", choices=["auto", "fused", "tiled"])
+    ap.add_argument("--fused-batch", type=int, default=0)
     ap.add_argument("--precision", default="strict", choices=["strict", "tf32"], help="strict = 3xTF32 (fp32-level), tf32 = fast mode")
     args = ap.parse_args()
     if args.impl == "reference":

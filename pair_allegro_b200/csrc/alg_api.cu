@@ -27,7 +27,7 @@ const Pipeline* get_pipeline(int L) {
   }
   return nullptr;
 }
-const Pipeline* get_pipeline_tc(int L) { return L == 1 ? get_pipeline_tc_L1() : (L == 2 ? get_pipeline_tc_L2() : nullptr); }
+const Pipeline* get_pipeline_tc(int L) { return L == 1 ? get_pipeline_tc_L1() : (L == 2 ? get_pipeline_tc_L2() : (L == 3 ? get_pipeline_tc_L3() : nullptr)); }
 }  // namespace alg
 
 using namespace alg;
@@ -711,7 +711,7 @@ extern "C" int alg_set_option(alg_handle* h, const char* key, const char* value)
   else if (k == "gemm") {
     if (v == "ffma") { h->use_tc = false; h->pipe = h->pipe_ffma; }
     else if (v == "tc") {
-      if (!h->pipe_tc) return fail(h, ALG_EINVAL, "gemm=tc: the tensor-core pipeline of this build supports l_max = 1, 2");
+      if (!h->pipe_tc) return fail(h, ALG_EINVAL, "gemm=tc: no tensor-core pipeline for this model");
       h->use_tc = true; h->pipe = h->pipe_tc;
     } else return fail(h, ALG_EINVAL, "gemm must be ffma or tc");
     h->pinfo = h->pipe->info(h->nl);

@@ -231,5 +231,6 @@ const Pipeline* get_pipeline_L2();
 const Pipeline* get_pipeline_L3();
 const Pipeline* get_pipeline_tc_L1();
 const Pipeline* get_pipeline_tc_L2();
+const Pipeline* get_pipeline_tc_L3();
 
 }  // namespace alg

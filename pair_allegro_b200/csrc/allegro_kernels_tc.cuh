@@ -58,6 +58,7 @@ template <int L> struct DimsTC {
   static constexpr int FC = NSH * CHU;
   static constexpr int DGS = FC + 1;
   static constexpr int TB = (L == 1) ? 4 : 1;           // tensor-product channels whose loads are batched
+  static constexpr int MINB = (L == 3) ? 1 : 2;         // resident CTAs per SM (__launch_bounds__)
   __host__ __device__ static constexpr int bw(int b) { return (ENVW - 64 * b) < 64 ? (ENVW - 64 * b) : 64; }   // block width
   __host__ __device__ static constexpr int lhi(int b) { return (2 * b + 2) < NL ? (2 * b + 2) : NL; }            // block covers l in [2b, lhi)
 };
@@ -69,9 +70,13 @@ template <int L> struct SmemTC {
   // reduction scratch) whose two halves double as the hi / lo image of weight buffer 2 (tc_load_w2)
   static constexpr int OPF = TM * 64;
   static constexpr int WBF = 4096;                     // weight block capacity: N*K <= 64*64
+  // scratch floats: l_max <= 2: 2*OPF (64 KB, two CTAs per SM); l_max = 3: dG staging [128][129] + ds rows [128][128]
+  // (130 KB -> one CTA per SM, which is what the persistent fused kernel wants anyway)
+  static constexpr int DGPAD = ((D::DGS * TM + 127) / 128) * 128;
+  static constexpr int SCR = (L <= 2) ? 2 * OPF : ((DGPAD + D::ENVW * TM + 255) / 256) * 256;   // weight images behind it: 1024-byte aligned
   static constexpr int oOPH = 0;
   static constexpr int oOPL = oOPH + OPF;
-  static constexpr int oWBH = oOPL + OPF;
+  static constexpr int oWBH = SCR;
   static constexpr int oWBL = oWBH + WBF;
   static constexpr int oY = oWBL + WBF;
   static constexpr int oDY = oY + D::NSH * TM;
@@ -89,15 +94,19 @@ template <int L> struct SmemTC {
   static constexpr size_t BYTES = (size_t)TOTAL * sizeof(float) + 1024;   // + alignment slack
   // buffers inside the scratch / weight regions (live ranges never overlap a weight block that is still in use)
   static constexpr int oWS = oOPL;                                 // env weights of one block, edge-major [128][65]
-  static constexpr int oDS = (L == 1) ? oWBH : ((D::DGS * TM + 127) / 128) * 128;   // ds rows [q*U+u][128] for the tensor-product backward
-                                                                   // (l_max = 2: right behind the dG staging)
+  static constexpr int oDS = (L == 1) ? oWBH : DGPAD;              // ds rows [q*U+u][128] for the tensor-product backward
+                                                                   // (l_max >= 2: right behind the dG staging)
   static constexpr int oDG = oOPH;                                 // dG staging [128][DGS]
-  static_assert(L == 1 || L == 2, "tensor-core pipeline: shared-memory plan covers l_max = 1, 2");
+  static_assert(L >= 1 && L <= 3, "tensor-core pipeline: l_max = 1..3");
   static_assert(D::WS * TM <= OPF + 2 * WBF, "W_s must fit OPL + weight region");
+  static_assert(L <= 2 || oWS + D::WS * TM <= SCR, "l_max = 3: W_s inside the scratch region");
   static_assert(oDS + D::ENVW * TM <= oY, "DS_s must end before the persistent small arrays");
+  static_assert(L <= 2 || oDS + D::ENVW * TM <= SCR, "l_max = 3: DS_s inside the scratch region (the weight buffers stay live)");
   static_assert(oDG + D::DGS * TM <= oDS || L == 1, "dG staging must not overlap DS_s");
   static_assert(L != 1 || D::DGS * TM <= 2 * OPF, "dG staging (l_max = 1) spans OPH + OPL");
-  static_assert(BYTES <= 113 * 1024, "two CTAs per SM");
+  static_assert(L == 3 || BYTES <= 113 * 1024, "two CTAs per SM");
+  static_assert(BYTES <= 227 * 1024, "shared memory per CTA");
+  static_assert(oWBH % 256 == 0 && oWBL % 256 == 0 && oOPL % 256 == 0, "SWIZZLE_128B operand images need 1024-byte alignment");
 };
 
 // per-centre rows (Gamma_k or dGamma_k) of the centres touched by this tile: staged in shared memory
@@ -1057,7 +1066,7 @@ __device__ __forceinline__ Geom tc_tile_begin(const ChunkArgs& a, const ModelW& 
   return g;
 }
 template <int L>
-__global__ void __launch_bounds__(NT, 2) k_f0_tc(const __grid_constant__ ChunkArgs a, const __grid_constant__ ModelW w, const __grid_constant__ TcW tw) {
+__global__ void __launch_bounds__(NT, DimsTC<L>::MINB) k_f0_tc(const __grid_constant__ ChunkArgs a, const __grid_constant__ ModelW w, const __grid_constant__ TcW tw) {
   constexpr int TM = 128;
   extern __shared__ __align__(1024) float sm_raw[];
   const int tile = blockIdx.x;
@@ -1124,7 +1133,7 @@ __device__ __forceinline__ void fk_body(const ChunkArgs& a, const ModelW& w, con
   tc_env_all<L>(a, w, c, tw.layer[k + 1].env, tile, es, (a.gamma[k + 1] + c.goff));
 }
 template <int L, char KIND, bool FIRST>
-__global__ void __launch_bounds__(NT, 2) k_fk_tc(const __grid_constant__ ChunkArgs a, const __grid_constant__ ModelW w, const __grid_constant__ TcW tw, const int k) {
+__global__ void __launch_bounds__(NT, DimsTC<L>::MINB) k_fk_tc(const __grid_constant__ ChunkArgs a, const __grid_constant__ ModelW w, const __grid_constant__ TcW tw, const int k) {
   constexpr int TM = 128;
   extern __shared__ __align__(1024) float sm_raw[];
   const int tile = blockIdx.x;
@@ -1234,7 +1243,7 @@ __device__ __forceinline__ void t_body(const ChunkArgs& a, const ModelW& w, cons
   tc_dy_store<L, true>(a, c, tile, dYp, FIRST);
 }
 template <int L, bool FIRST>
-__global__ void __launch_bounds__(NT, 2) k_t_tc(const __grid_constant__ ChunkArgs a, const __grid_constant__ ModelW w, const __grid_constant__ TcW tw, const int k) {
+__global__ void __launch_bounds__(NT, DimsTC<L>::MINB) k_t_tc(const __grid_constant__ ChunkArgs a, const __grid_constant__ ModelW w, const __grid_constant__ TcW tw, const int k) {
   constexpr int TM = 128;
   extern __shared__ __align__(1024) float sm_raw[];
   const int tile = blockIdx.x;
@@ -1297,7 +1306,7 @@ __device__ __forceinline__ void bk_body(const ChunkArgs& a, const ModelW& w, con
   tc_dy_store<L, false>(a, c, tile, dYp, FIRST);
 }
 template <int L, char KIND, bool FIRST>
-__global__ void __launch_bounds__(NT, 2) k_bk_tc(const __grid_constant__ ChunkArgs a, const __grid_constant__ ModelW w, const __grid_constant__ TcW tw, const int k) {
+__global__ void __launch_bounds__(NT, DimsTC<L>::MINB) k_bk_tc(const __grid_constant__ ChunkArgs a, const __grid_constant__ ModelW w, const __grid_constant__ TcW tw, const int k) {
   using D = DimsTC<L>; constexpr int TM = 128;
   extern __shared__ __align__(1024) float sm_raw[];
   const int tile = blockIdx.x;
@@ -1444,7 +1453,7 @@ __device__ __forceinline__ void b0_body(const ChunkArgs& a, const ModelW& w, con
   }
 }
 template <int L>
-__global__ void __launch_bounds__(NT, 2) k_b0_tc(const __grid_constant__ ChunkArgs a, const __grid_constant__ ModelW w, const __grid_constant__ TcW tw) {
+__global__ void __launch_bounds__(NT, DimsTC<L>::MINB) k_b0_tc(const __grid_constant__ ChunkArgs a, const __grid_constant__ ModelW w, const __grid_constant__ TcW tw) {
   using D = DimsTC<L>; constexpr int TM = 128;
   extern __shared__ __align__(1024) float sm_raw[];
   const int tile = blockIdx.x;
@@ -1509,7 +1518,7 @@ __device__ __forceinline__ void fused_fixup_e(const ChunkArgs& a, int e0, int e1
   }
 }
 template <int L, int NLAYERS>
-__global__ void __launch_bounds__(NT, 2) k_fused_tc(const __grid_constant__ ChunkArgs a, const __grid_constant__ ModelW w, const __grid_constant__ TcW tw,
+__global__ void __launch_bounds__(NT, DimsTC<L>::MINB) k_fused_tc(const __grid_constant__ ChunkArgs a, const __grid_constant__ ModelW w, const __grid_constant__ TcW tw,
                                                     const __grid_constant__ FusedPlan plan) {
   using D = DimsTC<L>; constexpr int TM = 128;
   extern __shared__ __align__(1024) float sm_raw[];

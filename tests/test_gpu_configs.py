@@ -52,4 +52,4 @@ def test_c5_multi_species(ensure_built, tmp_path):
     pos, types, cell = H.multi_species_box(700, fractions=(3, 1, 4), density=0.09, seed=5)   # box ~19.8 A
     cfg = modelgen.default_config(type_names=["Li", "P", "O"], r_max=5.5, l_max=3, num_layers=3, avg_num_neighbors=60.0,
                                   per_edge_type_cutoff=[[5.5, 5.0, 5.5], [5.0, 4.5, 5.0], [5.5, 5.0, 5.5]], seed=5)
-    _compare(pos, types, cell, ["Li", "P", "O"], cfg, ["ffma"], tmp_path, 6.5)
+    _compare(pos, types, cell, ["Li", "P", "O"], cfg, ["tc", "ffma"], tmp_path, 6.5)

@@ -11,8 +11,7 @@ from test_gpu_parity import E_ATOL, E_RTOL, F_ATOL, V_RTOL, check_outputs, make_
 
 pytestmark = pytest.mark.gpu
 
-# Cu_r15: 1204 neighbours per atom -> chunked pipeline ; Cu2AgO4_r5: l_max = 3 (FP32-pipe pipeline)
-FUSED_CASES = [c for c in GOLDEN_CASES if c not in ("Cu_r15", "Cu2AgO4_r5")]
+FUSED_CASES = [c for c in GOLDEN_CASES if c != "Cu_r15"]     # Cu_r15: 1204 neighbours per atom -> chunked pipeline
 
 
 @pytest.mark.parametrize("name", FUSED_CASES)
@@ -53,7 +52,7 @@ def _fcc(ncell, seed=7):
     return atoms, H.build_full_list(atoms, 6.0)
 
 
-@pytest.mark.parametrize("lmax,nlayers", [(1, 1), (1, 2), (1, 3), (2, 2), (2, 3)])
+@pytest.mark.parametrize("lmax,nlayers", [(1, 1), (1, 2), (1, 3), (2, 2), (2, 3), (3, 3)])
 def test_fused_equals_tiled(lmax, nlayers, ensure_built, tmp_path):
     """same kernels bodies, different tiling: agreement to fp32 round-off on a 2048-atom box (many tiles per CTA slot)"""
     from pair_allegro_b200 import modelgen

@@ -78,7 +78,7 @@ def test_tc_intermediates(name, ensure_built):
     assert not bad, bad
 
 
-@pytest.mark.parametrize("nl,ntypes,lmax", [(1, 1, 1), (2, 2, 1), (3, 3, 1), (1, 2, 2), (2, 1, 2), (3, 2, 2)])
+@pytest.mark.parametrize("nl,ntypes,lmax", [(1, 1, 1), (2, 2, 1), (3, 3, 1), (1, 2, 2), (2, 1, 2), (3, 2, 2), (2, 2, 3), (3, 3, 3)])
 def test_tc_live_oracle(nl, ntypes, lmax, ensure_built, tmp_path):
     from oracle import allegro_torch as AT
     from lmpshim import harness as H
@@ -119,9 +119,12 @@ def test_tc_live_oracle(nl, ntypes, lmax, ensure_built, tmp_path):
             assert df < 5e-3 * max(1.0, np.abs(f_ref).max()) and de < 5e-3 * max(1.0, np.abs(e_ref).max())
 
 
-def test_tc_rejects_unsupported_lmax(ensure_built):
-    from pair_allegro_b200 import capi
-    atom, lst, z = load_golden("Cu2AgO4_r5")       # l_max = 3
-    pair = make_pair("Cu2AgO4_r5", z, atom)
-    with pytest.raises(capi.AllegroError, match="l_max = 1, 2"):
-        pair.handle.set_option("gemm", "tc")
+def test_tc_covers_lmax3(ensure_built):
+    """l_max = 3 (config C5's architecture) runs on the tensor cores too: one CTA per SM (130 KB of staging), same tolerances"""
+    from test_gpu_parity import check_outputs
+    atom, lst, z = load_golden("Cu2AgO4_r5")       # l_max = 3, 3 layers
+    for pipeline in ("tiled", "fused"):
+        atom.f[:] = 0
+        pair = make_pair("Cu2AgO4_r5", z, atom, gemm="tc", pipeline=pipeline)
+        pair.compute(atom, lst)
+        check_outputs(pair, atom, z)
