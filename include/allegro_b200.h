@@ -87,6 +87,8 @@ ALG_API int alg_set_type_map(alg_handle* h, int ntypes, const int* lammps_type_t
  *                  an atom with more neighbours than a batch holds (that step is repeated transparently), or when debug=1.
  *   "fused_batch"  fused pipeline: 128-edge tiles per batch (default 8).  A CTA runs the tiles of a batch phase by phase, so
  *                  the code of one phase stays in the instruction cache for the whole batch
+ *   "phase_align"  fused pipeline: "1" (default) keeps the CTAs that share an SM in the same phase (bounded wait at every phase
+ *                  change) so that they share the instruction cache; "0" lets them drift
  *   "max_neighbors" alg_compute_device only: extent(1) of the caller's 2-D neighbour view.  Sizes the edge arrays to
  *                  nlocal*max_neighbors so that a fully asynchronous step can never overflow them; without it they
  *                  are sized from the previous step's edge count (+12.5 %), like the reference's 1.05 padding

@@ -105,7 +105,9 @@ struct alg_handle {
   long edge_cap_hint = 0;                  // upper bound on the edge count known to the caller path (0 = unknown)
   long max_neighbors = 0;                  // option max_neighbors: extent(1) of the caller's 2-D neighbour view
   long last_E_known = -1; int last_E_nlocal = -1;
-  DevBuf d_blk, d_blk_base, d_tile_c0, d_info;
+  DevBuf d_blk, d_blk_base, d_tile_c0, d_info, d_sm_phase;
+  int num_sms = 148;
+  bool phase_align = true;                 // option phase_align
   PinBuf h_info;
   cudaEvent_t ev_info = nullptr;
   bool info_pending = false;               // an asynchronous fused step has not been verified yet
@@ -314,6 +316,9 @@ __global__ void __launch_bounds__(256) k_plan(int nlocal, const int* __restrict_
   const int b = blockIdx.x * PLAN_TPB + threadIdx.x;
   if (threadIdx.x >= PLAN_TPB || b >= nblk) return;
   const int cb = b * PLAN_CB, ce = min(nlocal, cb + PLAN_CB);
+  // the last ~4 % of the centres are cut into quarter-size batches: the batch queue then drains evenly (a full batch is
+  // ~1/24 of a CTA's share at 1 M atoms; without this the last round leaves most SMs idle)
+  if (PLAN_ROWS >= 512 && (long)cb * 25 >= (long)nlocal * 24) PLAN_ROWS >>= 2;
   int rows = 0, span = 0, nt = 0, maxdeg = 0, tiles = 0;
   int base = FILL ? blk_base[b] : 0;
   int prev = rp[cb - c_base];
@@ -600,6 +605,7 @@ static int setup_model(alg_handle* h) {
     // default: tensor-core pipeline in strict (3xTF32) mode whenever the model is supported
     h->use_tc = true; h->pipe = h->pipe_tc; h->pinfo = h->pipe->info(h->nl);
     h->fused_grid = h->pipe_tc->fused_grid ? h->pipe_tc->fused_grid(h->nl) : 0;
+    cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, h->device);
   }
   h->tensors.clear();
   return ALG_OK;
@@ -653,7 +659,7 @@ extern "C" void alg_destroy(alg_handle* h) {
   if (h->copy_stream) { cudaStreamSynchronize(h->copy_stream); cudaStreamDestroy(h->copy_stream); }
   for (auto& r : h->reg) if (r.first) { cudaHostUnregister(const_cast<void*>(r.first)); cudaGetLastError(); }
   for (cudaEvent_t e : {h->ev_info, h->ev_copy, h->ev_order}) if (e) cudaEventDestroy(e);
-  h->d_blk.release(); h->d_blk_base.release(); h->d_tile_c0.release(); h->d_info.release(); h->d_f_stage.release();
+  h->d_sm_phase.release(); h->d_blk.release(); h->d_blk_base.release(); h->d_tile_c0.release(); h->d_info.release(); h->d_f_stage.release();
   h->h_info.release(); h->h_eatom.release();
   DevBuf* bufs[] = {&h->weights, &h->d_tmap, &h->d_cutsq, &h->d_scale, &h->d_shift, &h->d_x, &h->d_type, &h->d_ilist, &h->d_numneigh,
                     &h->d_cand, &h->d_first, &h->d_cnt, &h->d_rowptr, &h->d_scan_tmp, &h->d_mtype, &h->d_edge_j, &h->d_edge_c, &h->d_rvec,
@@ -726,6 +732,8 @@ extern "C" int alg_set_option(alg_handle* h, const char* key, const char* value)
     const int b = atoi(v.c_str());
     if (b < 1 || b > 64) return fail(h, ALG_EINVAL, "fused_batch must be in 1..64");
     h->fused_batch = b;
+  } else if (k == "phase_align") {
+    h->phase_align = v != "0";
   } else if (k == "max_neighbors") {
     h->max_neighbors = atol(v.c_str());
     if (h->max_neighbors < 0) return fail(h, ALG_EINVAL, "max_neighbors must be >= 0");
@@ -913,7 +921,9 @@ static int step_fused(alg_handle* h, const StepIO& io, long cap) {
   ChunkArgs a;
   fill_args(h, io, a);
   a.e0 = 0; a.e1 = 0; a.c0 = 0;
-  FusedPlan plan{h->d_tile_c0.as<int>(), h->d_info.as<int>(), batch};      // info[5] (tile queue) was zeroed above
+  CK(h->d_sm_phase.ensure(sizeof(unsigned) * 1024));
+  CK(cudaMemsetAsync(h->d_sm_phase.p, 0, sizeof(unsigned) * 1024, st));
+  FusedPlan plan{h->d_tile_c0.as<int>(), h->d_info.as<int>(), batch, h->num_sms, h->phase_align ? h->d_sm_phase.as<unsigned>() : nullptr};      // info[5] (tile queue) was zeroed above
   CK(h->pipe->run_fused(a, h->mw, &h->tcw, plan, grid, st, &h->prof));
   h->prof.launches += 2;                               // k_plan x2
   h->dbg_ntiles = 0; h->dbg_c0 = 0; h->dbg_ncent = 0;

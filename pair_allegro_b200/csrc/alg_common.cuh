@@ -111,6 +111,27 @@ __device__ __forceinline__ float silu_act(float z) {
   return ACT_C * z * sigmoid_fast(z);
 }
 
+// ---- packed-pair versions for the tensor-core epilogues (sm_100 FFMA2 / FMUL2 / FADD2: two fp32 lanes per instruction).
+// The epilogues are bound by instruction issue, not by FP32 throughput: c*silu and its derivative cost 7 packed
+// instructions + 4 MUFU per PAIR (5.5 per element) instead of ~14 scalar ones.
+__device__ __forceinline__ float ex2_approx(float x) { float r; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+// r = c*z*s, d = c*(s + z*s*(1-s)), s = sigmoid(z) = 1/(1 + 2^(-z*log2 e))  (same formulas as silu_act, up to rounding)
+__device__ __forceinline__ void silu_act2(float2 z, float2& r, float2& d) {
+  const float2 t = __fmul2_rn(z, make_float2(-1.4426950408889634f, -1.4426950408889634f));
+  const float2 den = __fadd2_rn(make_float2(ex2_approx(t.x), ex2_approx(t.y)), make_float2(1.f, 1.f));
+  const float2 s = make_float2(rcp_approx(den.x), rcp_approx(den.y));
+  const float2 zs = __fmul2_rn(z, s);
+  r = __fmul2_rn(zs, make_float2(ACT_C, ACT_C));
+  const float2 oms = __ffma2_rn(s, make_float2(-1.f, -1.f), make_float2(1.f, 1.f));
+  d = __fmul2_rn(__ffma2_rn(zs, oms, s), make_float2(ACT_C, ACT_C));
+}
+__device__ __forceinline__ float2 silu_act2(float2 z) {
+  const float2 t = __fmul2_rn(z, make_float2(-1.4426950408889634f, -1.4426950408889634f));
+  const float2 den = __fadd2_rn(make_float2(ex2_approx(t.x), ex2_approx(t.y)), make_float2(1.f, 1.f));
+  const float2 s = make_float2(rcp_approx(den.x), rcp_approx(den.y));
+  return __fmul2_rn(__fmul2_rn(z, s), make_float2(ACT_C, ACT_C));
+}
+
 // ------------------------------------------------------------------------------------------
 // Tile GEMM on the FP32 pipe:  out(m, n) = sum_k A_s[k*TM + m] * W[k*ldw + col0 + n]
 // for a TM x NC output block; A in shared memory ([K][TM]), W in global memory (L1-resident,

@@ -277,12 +277,23 @@ template <int L> __device__ __forceinline__ void tc_mma_pair(TcCtx& c, int K, in
 __device__ __forceinline__ void tc_ld16(const TcCtx& c, uint32_t col, float* v) {
   umma::tmem_ld16(c.tmem + ((uint32_t)(c.q * 32) << 16) + col, v);
 }
-// write 4 consecutive k (k4 % 4 == 0) of row m into the A operand in tensor memory (hi [+ lo])
+// write 4 consecutive k (k4 % 4 == 0) of row m into the A operand in tensor memory (hi [+ lo]).
+// hi / lo by Veltkamp splitting with packed-pair arithmetic (4 FFMA2/FMUL2 per PAIR): t = 8193 a, hi = t - (t - a) keeps the
+// top 11 significant bits of a (round to nearest -> exactly representable in TF32), lo = a - hi is exact.
+__device__ __forceinline__ void tf32_split2(float2 a, float2& hi, float2& lo) {
+  const float2 m1 = make_float2(-1.f, -1.f);
+  const float2 t = __fmul2_rn(a, make_float2(8193.f, 8193.f));
+  const float2 u = __ffma2_rn(a, m1, t);
+  hi = __ffma2_rn(u, m1, t);
+  lo = __ffma2_rn(hi, m1, a);
+}
 template <int L> __device__ __forceinline__ void op_put4(const TcCtx& c, int k4, float a, float b, float d, float e) {
   const uint32_t t0 = c.tmem + ((uint32_t)(c.q * 32) << 16) + (uint32_t)k4;
-  const float ah = umma::tf32_hi(a), bh = umma::tf32_hi(b), dh = umma::tf32_hi(d), eh = umma::tf32_hi(e);
-  umma::tmem_st4(t0 + TC_AHI, ah, bh, dh, eh);
-  if (c.passes == 3) umma::tmem_st4(t0 + TC_ALO, a - ah, b - bh, d - dh, e - eh);
+  float2 h0, l0, h1, l1;
+  tf32_split2(make_float2(a, b), h0, l0);
+  tf32_split2(make_float2(d, e), h1, l1);
+  umma::tmem_st4(t0 + TC_AHI, h0.x, h0.y, h1.x, h1.y);
+  if (c.passes == 3) umma::tmem_st4(t0 + TC_ALO, l0.x, l0.y, l1.x, l1.y);
 }
 // one element of this thread's own row
 template <int L> __device__ __forceinline__ void op_put1(const TcCtx& c, int /*row == c.m*/, int k, float a) {
@@ -784,25 +795,28 @@ __device__ ALG_NI void tc_mlp_hidden_fwd(TcCtx& c, const TcMat& w2, const TcMat&
   constexpr int TM = 128;
   tc_epi(c, TC_Z1, 64, [&](int n, float v0, float v1, float v2, float v3) {
     if constexpr (STORE) {
-      float d0, d1, d2, d3;
-      const float r0 = silu_act(v0 + bias(n), d0), r1 = silu_act(v1 + bias(n + 1), d1);
-      const float r2 = silu_act(v2 + bias(n + 2), d2), r3 = silu_act(v3 + bias(n + 3), d3);
-      op_put4<L>(c, n, r0, r1, r2, r3);
-      st_row4(zd, n, c.m, d0, d1, d2, d3);
+      float2 r01, r23, d01, d23;
+      silu_act2(make_float2(v0 + bias(n), v1 + bias(n + 1)), r01, d01);
+      silu_act2(make_float2(v2 + bias(n + 2), v3 + bias(n + 3)), r23, d23);
+      op_put4<L>(c, n, r01.x, r01.y, r23.x, r23.y);
+      st_row4(zd, n, c.m, d01.x, d01.y, d23.x, d23.y);
     } else {
-      op_put4<L>(c, n, silu_act(v0 + bias(n)), silu_act(v1 + bias(n + 1)), silu_act(v2 + bias(n + 2)), silu_act(v3 + bias(n + 3)));
+      const float2 r01 = silu_act2(make_float2(v0 + bias(n), v1 + bias(n + 1))), r23 = silu_act2(make_float2(v2 + bias(n + 2), v3 + bias(n + 3)));
+      op_put4<L>(c, n, r01.x, r01.y, r23.x, r23.y);
     }
   });
   tc_mma<L>(c, 64, 64, TC_Z2);
   tc_load_w<L>(c, w2);
   tc_epi(c, TC_Z2, 64, [&](int n, float v0, float v1, float v2, float v3) {
     if constexpr (STORE) {
-      float d0, d1, d2, d3;
-      const float r0 = silu_act(v0, d0), r1 = silu_act(v1, d1), r2 = silu_act(v2, d2), r3 = silu_act(v3, d3);
-      op_put4<L>(c, n, r0, r1, r2, r3);
-      st_row4(zd + 64 * TM, n, c.m, d0, d1, d2, d3);
+      float2 r01, r23, d01, d23;
+      silu_act2(make_float2(v0, v1), r01, d01);
+      silu_act2(make_float2(v2, v3), r23, d23);
+      op_put4<L>(c, n, r01.x, r01.y, r23.x, r23.y);
+      st_row4(zd + 64 * TM, n, c.m, d01.x, d01.y, d23.x, d23.y);
     } else {
-      op_put4<L>(c, n, silu_act(v0), silu_act(v1), silu_act(v2), silu_act(v3));
+      const float2 r01 = silu_act2(make_float2(v0, v1)), r23 = silu_act2(make_float2(v2, v3));
+      op_put4<L>(c, n, r01.x, r01.y, r23.x, r23.y);
     }
   });
   tc_mma<L>(c, 64, 64, TC_M);
@@ -1487,18 +1501,40 @@ struct FusedPlan {
   const int* batch_c0;    // [nbatch + 1] first centre slot of every batch (batch_c0[nbatch] = nlocal)
   int* info;              // [0] = nbatch, [1] = max degree, [2] = E, [3] = edge capacity overflow flag, [5] = batch queue, [6] = tiles
   int batch;              // B: tiles per batch (scratch slots per CTA); a centre needs at most B*128 edges
+  int num_sms;
+  unsigned* sm_phase;     // [number of SMs] phase tickets of the CTAs resident on each SM (zeroed before the launch), or nullptr
 };
+// Keep the CTAs that share an SM in the SAME phase: every CTA adds one ticket per phase it enters and waits (bounded) until
+// all its co-residents have entered that phase too.  Two CTAs in different phases execute ~130 KB of different code and
+// evict each other from the instruction cache (measured: 15 % of all warp stalls were "no instruction"; the chunked
+// pipeline, where an SM only ever runs one phase at a time, has none).  The wait is bounded by a cycle budget, so a CTA
+// without a partner (odd residency, partner already finished) only loses the alignment, never deadlocks.
+__device__ __forceinline__ void fused_phase_align(unsigned* sm_phase, unsigned& my_phase, unsigned residents) {
+  if (sm_phase == nullptr || residents < 2) return;
+  if (threadIdx.x == 0) {
+    unsigned smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    ++my_phase;
+    atomicAdd(sm_phase + smid, 1u);
+    const unsigned want = my_phase * residents;
+    const long long t0 = clock64();
+    while (*reinterpret_cast<volatile unsigned*>(sm_phase + smid) < want && clock64() - t0 < 400000) { }
+  }
+  __syncthreads();
+}
 // rows of centres whose CSR row straddles tiles of this batch: the tile in which the row STARTS adds the carries of the
 // following tiles in tile order (same rule as k_fixup of the chunked pipeline)
 template <int NF>
 __device__ __forceinline__ void fused_fixup(const ChunkArgs& a, const TcCtx& c, int e0, int e1, int nb, int slot0, float* out) {
+  // one warp per tile boundary (a batch has at most 63 of them); the lanes share the row's features
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 #pragma unroll 1
-  for (int tb = 0; tb + 1 < nb; ++tb) {
+  for (int tb = warp; tb + 1 < nb; tb += NT / 32) {
     const int es = e0 + tb * 128, ee = min(es + 128, e1);
     const int ce = a.edge_c[ee - 1];
     const int rb = a.rowptr[ce], re = a.rowptr[ce + 1];
     if (rb < es || re <= ee) continue;                          // row does not start here, or ends here
-    for (int f = threadIdx.x; f < NF; f += NT) {
+    for (int f = lane; f < NF; f += 32) {
       float acc = out[(size_t)(ce - c.c0) * NF + f];
       for (int t2 = tb + 1; t2 < nb && e0 + t2 * 128 < re; ++t2) acc += a.carry[(size_t)(slot0 + t2) * NF + f];
       out[(size_t)(ce - c.c0) * NF + f] = acc;
@@ -1530,8 +1566,11 @@ __global__ void __launch_bounds__(NT, DimsTC<L>::MINB) k_fused_tc(const __grid_c
   const int slot0 = (int)blockIdx.x * B;
   c.goff = (size_t)slot0 * TM * D::F;
   int e0 = 0, e1 = 0;
+  unsigned my_phase = 0;
+  const unsigned residents = (gridDim.x + plan.num_sms - 1) / plan.num_sms;
   // one phase of one tile of the batch: geometry -> shared memory, then the phase body on the tile's private scratch slot
 #define ALG_PHASE(PRE, ...)                                                      \
+  fused_phase_align(plan.sm_phase, my_phase, residents);                          \
   _Pragma("unroll 1") for (int tb = 0; tb < nb; ++tb) {                           \
     const int es = e0 + tb * TM, nvalid = min(TM, e1 - es), slot = slot0 + tb;    \
     const GeomIn gi = tc_geom_load(a, es, nvalid);                                \
@@ -1549,11 +1588,21 @@ __global__ void __launch_bounds__(NT, DimsTC<L>::MINB) k_fused_tc(const __grid_c
     __syncthreads();
     const int b = *next_batch;
     __syncthreads();
-    if (b >= nbatch) break;
+    if (b >= nbatch) {
+      if (plan.sm_phase && threadIdx.x == 0) { unsigned smid; asm volatile("mov.u32 %0, %%smid;" : "=r"(smid)); atomicAdd(plan.sm_phase + smid, 1u << 24); }
+      break;
+    }
     const int bc0 = plan.batch_c0[b];
     e0 = a.rowptr[bc0]; e1 = a.rowptr[plan.batch_c0[b + 1]];
     const int nb = (e1 - e0 + TM - 1) / TM;
-    if (nb <= 0) continue;                                      // only centres without neighbours
+    if (nb <= 0) {                                              // only centres without neighbours: hand in the tickets of the skipped phases
+      if (plan.sm_phase && residents >= 2 && threadIdx.x == 0) {
+        unsigned smid; asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        my_phase += 2 * NLAYERS + 1;
+        atomicAdd(plan.sm_phase + smid, 2u * NLAYERS + 1u);
+      }
+      continue;
+    }
     c.c0 = bc0;
     ALG_PHASE((void)0, f0_body<L>(a, w, tw, c, g, slot, es, nvalid));
     ALG_FIX(a.gamma[0]);
