@@ -500,6 +500,8 @@ def run_ours(args):
     sampler.start()
     ms = timed(step_device, K)
     clocks = sampler.stop()
+    step_device(scalars=True)                     # a synchronous step right behind the timed loop: the library's own per-phase CUDA events
+    last_ms = [float(v) for v in h.timings()]     # [edge build, network, store] of that step
     total_atoms = nl
     if world > 1:
         t = torch.tensor([nl], dtype=torch.float64, device=dev)
@@ -626,6 +628,7 @@ def run_ours(args):
                            "halo": "alg_comm_* (product code): grouped ncclSend/ncclRecv forward x / reverse f every step" if world > 1 else "periodic self-image halo on the device every step (alg_comm_*, no NCCL)",
                            "pipeline": "fused" if fused else "tiled", "fused_batch": int(args.fused_batch or 8), "gemm": args.gemm if cfg["l_max"] <= 2 or args.gemm == "ffma" else "tc", "precision": args.precision},
                 "clocks": clocks, "gpu_launches": launches_per_step * K,
+                "phase_ms_last_step": {"edge_build": last_ms[0], "network": last_ms[1], "store": last_ms[2]},
                 "e2e": {"value": e2e_val, "unit": "Matom-steps/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                         "ms_per_step": ms_e2e / KE, "steps": KE, "neigh_upload_every": NEIGH_EVERY,
                         "api": "alg_compute_host (host arrays; x, type, f H2D and f D2H inside the call; neigh_ago = step % 10)"},

@@ -11,6 +11,7 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "liballegro_b200.so")
+DEBUG_LIB_PATH = os.path.join(_HERE, "liballegro_b200_debug.so")      # tcgen05 primitive unit tests / micro-benchmarks (not the product)
 
 EXPORTS = ["alg_create", "alg_destroy", "alg_last_error", "alg_metadata", "alg_set_type_map", "alg_set_option",
            "alg_compute_host", "alg_compute_device", "alg_get_edges", "alg_get_output", "alg_get_timings", "alg_get_stats",
@@ -93,6 +94,13 @@ def load_library(path=None):
     if path is None:
         _lib = lib
     return lib
+
+
+def load_debug_library():
+    """the separate library with the tcgen05 unit-test kernels (csrc/alg_debug.cu)"""
+    if not os.path.exists(DEBUG_LIB_PATH):
+        raise FileNotFoundError("%s not found: build it with `make -C pair_allegro_b200/csrc`" % DEBUG_LIB_PATH)
+    return C.CDLL(DEBUG_LIB_PATH)
 
 
 def _dptr(a):

@@ -13,6 +13,9 @@
 #include <string>
 #include <vector>
 
+#ifdef _OPENMP
+#include <omp.h>
+#endif
 #include <cub/device/device_scan.cuh>
 
 #include "../../include/allegro_b200.h"
@@ -108,9 +111,14 @@ struct alg_handle {
   DevBuf d_blk, d_blk_base, d_tile_c0, d_info, d_sm_phase;
   int num_sms = 148;
   bool phase_align = true;                 // option phase_align
-  PinBuf h_info;
-  cudaEvent_t ev_info = nullptr;
-  bool info_pending = false;               // an asynchronous fused step has not been verified yet
+  // deferred verification of asynchronous steps: a ring of pinned info records, one event each, so that the host may run
+  // up to INFO_RING steps ahead of the device (it only blocks when a slot is about to be reused)
+  static constexpr int INFO_RING = 4;
+  PinBuf h_info;                           // INFO_RING x 16 ints; slot 0 doubles as the record of synchronous steps
+  cudaEvent_t ev_info[INFO_RING] = {nullptr, nullptr, nullptr, nullptr};
+  bool info_used[INFO_RING] = {false, false, false, false};
+  bool info_fused[INFO_RING] = {false, false, false, false};
+  unsigned info_head = 0, info_tail = 0;   // pending slots: [tail, head)
   bool last_fused = false;
   std::string deferred_err;                // failure of an asynchronous step, reported by the next call
   std::pair<const void*, size_t> reg[3] = {{nullptr, 0}, {nullptr, 0}, {nullptr, 0}};   // caller arrays (x, f, type) pinned with cudaHostRegister
@@ -643,7 +651,7 @@ extern "C" int alg_create(const char* weight_path, int cuda_device, alg_handle**
   }
   for (int i = 0; i < 4; ++i) cudaEventCreate(&h->ev[i]);
   cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking);
-  cudaEventCreateWithFlags(&h->ev_info, cudaEventDisableTiming);
+  for (int i = 0; i < alg_handle::INFO_RING; ++i) cudaEventCreateWithFlags(&h->ev_info[i], cudaEventDisableTiming);
   cudaEventCreateWithFlags(&h->ev_copy, cudaEventDisableTiming);
   cudaEventCreateWithFlags(&h->ev_order, cudaEventDisableTiming);
   rc = setup_model(h);
@@ -658,7 +666,7 @@ extern "C" void alg_destroy(alg_handle* h) {
   if (h->stream) cudaStreamSynchronize(h->stream);
   if (h->copy_stream) { cudaStreamSynchronize(h->copy_stream); cudaStreamDestroy(h->copy_stream); }
   for (auto& r : h->reg) if (r.first) { cudaHostUnregister(const_cast<void*>(r.first)); cudaGetLastError(); }
-  for (cudaEvent_t e : {h->ev_info, h->ev_copy, h->ev_order}) if (e) cudaEventDestroy(e);
+  for (cudaEvent_t e : {h->ev_info[0], h->ev_info[1], h->ev_info[2], h->ev_info[3], h->ev_copy, h->ev_order}) if (e) cudaEventDestroy(e);
   h->d_sm_phase.release(); h->d_blk.release(); h->d_blk_base.release(); h->d_tile_c0.release(); h->d_info.release(); h->d_f_stage.release();
   h->h_info.release(); h->h_eatom.release();
   DevBuf* bufs[] = {&h->weights, &h->d_tmap, &h->d_cutsq, &h->d_scale, &h->d_shift, &h->d_x, &h->d_type, &h->d_ilist, &h->d_numneigh,
@@ -931,25 +939,33 @@ static int step_fused(alg_handle* h, const StepIO& io, long cap) {
   return ALG_OK;
 }
 
-// the verdict of an asynchronous fused step is read here (by the next call, or by a getter)
-static int resolve_pending(alg_handle* h) {
-  if (!h->info_pending) return ALG_OK;
-  h->info_pending = false;
-  CK(cudaEventSynchronize(h->ev_info));
-  const int* info = h->h_info.as<int>();
-  if (info[8] != 0)
-    return fail(h, ALG_EINVAL, "the previous asynchronous step met atom " + std::to_string(info[8] - 1) + " whose LAMMPS type has no model type");
-  if (!h->last_fused) return ALG_OK;
-  h->last_E = info[2]; h->last_E_known = info[2];
-  h->step_stats[1] = info[2]; h->step_stats[2] = info[0]; h->step_stats[3] = info[6];
-  if (info[1] > h->fused_batch * 128) {
-    h->force_tiled = true;
-    return fail(h, ALG_ESTATE, "the previous asynchronous alg_compute_device step met an atom with more than fused_batch*128 neighbours inside the cutoff "
-                               "and produced no forces; the chunked pipeline is selected from now on (pass eng != NULL to have such steps "
-                               "re-run transparently)");
+// the verdict of asynchronous steps is read here: non-blocking at the start of a call (every record whose copy has landed),
+// blocking in the getters and when the ring is full
+static int resolve_pending(alg_handle* h, bool block = true, unsigned keep = 0) {
+  while (h->info_head - h->info_tail > keep) {
+    const int slot = (int)(h->info_tail % alg_handle::INFO_RING);
+    if (block || h->info_head - h->info_tail >= (unsigned)alg_handle::INFO_RING) CK(cudaEventSynchronize(h->ev_info[slot]));
+    else {
+      cudaError_t q = cudaEventQuery(h->ev_info[slot]);
+      if (q == cudaErrorNotReady) { cudaGetLastError(); break; }
+      CK(q);
+    }
+    ++h->info_tail;
+    const int* info = h->h_info.as<int>() + 16 * slot;
+    if (info[8] != 0)
+      return fail(h, ALG_EINVAL, "an earlier asynchronous step met atom " + std::to_string(info[8] - 1) + " whose LAMMPS type has no model type");
+    if (!h->info_fused[slot]) continue;
+    h->last_E = info[2]; h->last_E_known = info[2];
+    h->step_stats[1] = info[2]; h->step_stats[2] = info[0]; h->step_stats[3] = info[6];
+    if (info[1] > h->fused_batch * 128) {
+      h->force_tiled = true;
+      return fail(h, ALG_ESTATE, "an earlier asynchronous alg_compute_device step met an atom with more than fused_batch*128 neighbours inside the cutoff "
+                                 "and produced no forces; the chunked pipeline is selected from now on (pass eng != NULL to have such steps "
+                                 "re-run transparently)");
+    }
+    if (info[3]) return fail(h, ALG_ESTATE, "an earlier asynchronous alg_compute_device step overflowed its edge buffers and produced no forces "
+                                            "(set option max_neighbors, or pass eng != NULL to have such steps re-run transparently)");
   }
-  if (info[3]) return fail(h, ALG_ESTATE, "the previous asynchronous alg_compute_device step overflowed its edge buffers and produced no forces "
-                                          "(set option max_neighbors, or pass eng != NULL to have such steps re-run transparently)");
   return ALG_OK;
 }
 
@@ -962,7 +978,8 @@ static bool fused_selected(const alg_handle* h) {
 static int run_step(alg_handle* h, const StepIO& io, double* eng, double* virial6) {
   cudaStream_t st = h->stream;
   const int nlocal = io.nlocal, ntot = io.nlocal + io.nghost;
-  int rc = resolve_pending(h);
+  const bool want_sync = eng || virial6 || io.h_f;
+  int rc = resolve_pending(h, want_sync, want_sync ? 0 : alg_handle::INFO_RING - 1);   // asynchronous call: only free one ring slot
   if (rc != ALG_OK) return rc;
   h->last_nlocal = nlocal; h->last_ntot = ntot; h->last_E = 0;
   h->outputs.clear();
@@ -990,8 +1007,7 @@ static int run_step(alg_handle* h, const StepIO& io, double* eng, double* virial
   const int eblocks = (nlocal + 1023) / 1024;
   CK(h->d_red.ensure(sizeof(double) * (eblocks + 8)));
   CK(h->h_out.ensure(sizeof(double) * 8));
-  CK(h->h_info.ensure(sizeof(int) * 16));
-  const bool want_sync = eng || virial6 || io.h_f;
+  CK(h->h_info.ensure(sizeof(int) * 16 * alg_handle::INFO_RING));
   bool fused = fused_selected(h);
   long cap = 0;
   for (int attempt = 0;; ++attempt) {
@@ -1032,12 +1048,16 @@ static int run_step(alg_handle* h, const StepIO& io, double* eng, double* virial
     k_final_scalars<<<1, 32, 0, st>>>(eblocks, h->d_red.as<double>() + 8, h->d_vacc.as<unsigned long long>(), h->d_red.as<double>());
     CK(cudaGetLastError());
     CK(cudaEventRecord(h->ev[3], st));
-    CK(cudaMemcpyAsync(h->h_info.p, h->d_info.p, sizeof(int) * 16, cudaMemcpyDeviceToHost, st));
     if (!want_sync) {
-      CK(cudaEventRecord(h->ev_info, st)); h->info_pending = true;
+      const int slot = (int)(h->info_head % alg_handle::INFO_RING);
+      CK(cudaMemcpyAsync(h->h_info.as<int>() + 16 * slot, h->d_info.p, sizeof(int) * 16, cudaMemcpyDeviceToHost, st));
+      CK(cudaEventRecord(h->ev_info[slot], st));
+      h->info_fused[slot] = fused;
+      ++h->info_head;
       if (fused) { h->step_stats[1] = -1; h->step_stats[2] = 1; h->step_stats[3] = -1; }
       return ALG_OK;
     }
+    CK(cudaMemcpyAsync(h->h_info.p, h->d_info.p, sizeof(int) * 16, cudaMemcpyDeviceToHost, st));
     if (io.h_f) CK(cudaMemcpyAsync(io.h_f, io.d_f_inout, sizeof(double) * 3 * ntot, cudaMemcpyDeviceToHost, st));
     if (io.h_eatom_stage && io.eflag_atom) CK(cudaMemcpyAsync(io.h_eatom_stage, io.d_eatom, sizeof(double) * ntot, cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(h->h_out.p, h->d_red.p, sizeof(double) * 7, cudaMemcpyDeviceToHost, st));
@@ -1138,14 +1158,39 @@ extern "C" int alg_compute_host(alg_handle* h, int nlocal, int nghost, const dou
     CK(cudaMemcpyAsync(h->d_ilist.p, ilist, sizeof(int) * nlocal, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(h->d_first.p, first, sizeof(long long) * (nlocal + 1), cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(h->d_numneigh.p, cnt, sizeof(int) * nlocal, cudaMemcpyHostToDevice, st));
-    // flatten the paged list into pinned memory in slabs of centres; the upload of slab s overlaps the flattening of s+1
-    const int SLAB = 1 << 16;
-    for (int s0 = 0; s0 < nlocal; s0 += SLAB) {
-      const int s1 = std::min(nlocal, s0 + SLAB);
-#pragma omp parallel for schedule(static)
-      for (int ii = s0; ii < s1; ++ii) memcpy(stage + first[ii], firstneigh[ilist[ii]], sizeof(int) * cnt[ii]);
+    // flatten the paged list into pinned memory in slabs of ~16 MB; the upload of slab s overlaps the flattening of s+1.
+    // Rows that are contiguous in the caller's memory (LAMMPS stores the rows of one neighbour page back to back) are
+    // copied as one run, and every slab is split evenly over the host threads by BYTES (a row is only ~200 bytes).
+    const long long SLAB = 4ll << 20;                  // ints per slab
+    int s0 = 0;
+    while (s0 < nlocal) {
+      int s1 = s0;
+      while (s1 < nlocal && first[s1 + 1] - first[s0] <= SLAB) ++s1;
+      if (s1 == s0) s1 = s0 + 1;
       const long long nb = first[s1] - first[s0];
+      const int nrows = s1 - s0;
+#pragma omp parallel
+      {
+#ifdef _OPENMP
+        const int nth = omp_get_num_threads(), th = omp_get_thread_num();
+#else
+        const int nth = 1, th = 0;
+#endif
+        // thread th copies the rows whose first element lies in its byte range of the slab
+        const long long lo = first[s0] + nb * th / nth, hi = first[s0] + nb * (th + 1) / nth;
+        int r0 = (int)(std::lower_bound(first + s0, first + s1, lo) - first);
+        const int r1 = (int)(std::lower_bound(first + s0, first + s1, hi) - first);
+        while (r0 < r1) {                              // coalesce rows that are contiguous in the caller's memory
+          int r2 = r0 + 1;
+          const int* src = firstneigh[ilist[r0]];
+          while (r2 < r1 && firstneigh[ilist[r2]] == src + (first[r2] - first[r0])) ++r2;
+          memcpy(stage + first[r0], src, sizeof(int) * (size_t)(first[r2] - first[r0]));
+          r0 = r2;
+        }
+      }
+      (void)nrows;
       if (nb > 0) CK(cudaMemcpyAsync(h->d_cand.as<int>() + first[s0], stage + first[s0], sizeof(int) * nb, cudaMemcpyHostToDevice, st));
+      s0 = s1;
     }
     h->list_nlocal = nlocal; h->list_ntot = ntot; h->list_tot = tot;
   }

@@ -13,7 +13,7 @@ pytestmark = pytest.mark.gpu
 @pytest.mark.parametrize("passes", [1, 3])
 def test_umma_gemm(K, N, passes, ensure_built):
     from pair_allegro_b200 import capi
-    lib = capi.load_library()
+    lib = capi.load_debug_library()
     fn = lib.alg_debug_umma_gemm
     fn.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int]
     fn.restype = C.c_int

@@ -52,7 +52,7 @@ def run_reference(name, tmp, debug=False):
     return np.load(os.path.join(tmp, "out.npz")), r.stdout
 
 
-@pytest.mark.parametrize("name", ["Cu_r5", "Cu2AgO4_r5", "aspirin_r5", "CuPd_r5"])
+@pytest.mark.parametrize("name", ["Cu_r5", "Cu2AgO4_r5", "aspirin_r5", "CuPd_r5", "Cu_r15", "aspirin_r15"])
 def test_reference_sources_match_oracle_restatement(name):
     atom, lst, z = load_golden(name)
     with tempfile.TemporaryDirectory() as tmp:
@@ -67,10 +67,10 @@ def test_reference_sources_match_oracle_restatement(name):
     assert int(out["neigh_request"]) == 3                                   # REQ_FULL | REQ_GHOST (cpp:146)
 
 
-def test_reference_debug_edge_dump_matches():
+@pytest.mark.parametrize("name", ["Cu_r5", "Cu2AgO4_r5", "aspirin_r5", "CuPd_r5", "Cu_r15", "aspirin_r15"])
+def test_reference_debug_edge_dump_matches(name):
     """`_NEQUIP_LOG_LEVEL=DEBUG` edge dump of the real reference (cpp:562-565,620-633) == the
-    edge list of the oracle (bit-exact indices, printed distances)."""
-    name = "Cu_r5"
+    edge list of the oracle (bit-exact indices, printed distances) -- all six fixtures of tests/conftest.py:55-62"""
     atom, lst, z = load_golden(name)
     with tempfile.TemporaryDirectory() as tmp:
         _, stdout = run_reference(name, tmp, debug=True)
@@ -82,7 +82,7 @@ def test_reference_debug_edge_dump_matches():
     d = np.linalg.norm(atom.x[ei[0]] - atom.x[ei[1]], axis=1)
     for (i, j, r), e0, e1, rr in zip(got, ei[0], ei[1], d):
         assert int(i) == atom.tag[e0] - 1 and int(j) == atom.tag[e1] - 1
-        assert abs(float(r) - rr) < 1e-9
+        assert abs(float(r) - rr) < 1e-8                     # printed with 10 significant digits
 
 
 COMPUTE_SCRIPT = r"""

@@ -6,7 +6,7 @@ import os
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-lib = C.CDLL(os.path.join(ROOT, "pair_allegro_b200", "liballegro_b200.so"))
+lib = C.CDLL(os.path.join(ROOT, "pair_allegro_b200", "liballegro_b200_debug.so"))
 lib.alg_debug_mma_rate.argtypes = [C.c_int] * 6 + [C.POINTER(C.c_longlong)]
 out = (C.c_longlong * 2)()
 print("N nacc groups sync blocks : cycles/MMA (wall), cycles/MMA inside the issue loop, cycles per commit round trip")

@@ -7,7 +7,7 @@ import os
 import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-lib = C.CDLL(os.path.join(ROOT, "pair_allegro_b200", "liballegro_b200.so"))
+lib = C.CDLL(os.path.join(ROOT, "pair_allegro_b200", "liballegro_b200_debug.so"))
 vp = C.c_void_p
 lib.alg_debug_umma_gemm_ta.argtypes = [vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp]
 rng = np.random.default_rng(0)

@@ -2,7 +2,7 @@ import ctypes as C, sys, os
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from pair_allegro_b200 import capi
-lib = capi.load_library()
+lib = capi.load_debug_library()
 fn = lib.alg_debug_umma_gemm2
 fn.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]; fn.restype = C.c_int
 np.set_printoptions(precision=3, linewidth=220, suppress=True)
