@@ -11,6 +11,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 REF_LIB = os.path.join(ROOT, "oracle", "_ref", "libref_pair_allegro.so")
 OURS_LIB = os.path.join(ROOT, "src", "libpair_allegro_b200_shim.so")
+OURS_KK_LIB = os.path.join(ROOT, "src", "libpair_allegro_b200_kk_shim.so")
 
 
 class ShimError(RuntimeError):
@@ -153,6 +154,85 @@ class ShimLammps:
     def close(self):
         if self.h:
             self.lib.shim_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class ShimLammpsKK:
+    """one 'LAMMPS + KOKKOS instance': device-resident atoms + the 2-D device neighbour view + pair_style allegro/kk
+    (src/pair_allegro_b200_kokkos.cpp compiled against lmpshim/kokkos_shim.h; lmpshim/shim_kk.cpp)"""
+    FULL, HALFTHREAD, HALF = 1, 2, 4
+
+    def __init__(self, atom, lst, layout_left=True, neighflag=4, lib_path=OURS_KK_LIB):
+        if not os.path.exists(lib_path):
+            raise FileNotFoundError(lib_path)
+        lib = C.CDLL(lib_path, mode=C.RTLD_LOCAL)
+        vp = C.c_void_p
+        lib.shimkk_create.restype = vp
+        lib.shimkk_create.argtypes = [C.c_int, C.c_int, C.c_int, vp, vp, vp, C.c_int]
+        lib.shimkk_destroy.argtypes = [vp]
+        lib.shimkk_last_error.restype = C.c_char_p
+        lib.shimkk_last_error.argtypes = [vp]
+        lib.shimkk_set_list.argtypes = [vp, C.c_int, C.c_int, vp, vp, vp, vp, C.c_int]
+        lib.shimkk_set_newton.argtypes = [vp, C.c_int]
+        for fn in ("shimkk_pair_create", "shimkk_pair_init_style"):
+            getattr(lib, fn).argtypes = [vp]
+            getattr(lib, fn).restype = C.c_int
+        lib.shimkk_pair_settings.argtypes = [vp, C.c_int, C.POINTER(C.c_char_p)]
+        lib.shimkk_pair_coeff.argtypes = [vp, C.c_int, C.POINTER(C.c_char_p)]
+        lib.shimkk_pair_compute.argtypes = [vp, C.c_int, C.c_int, C.c_int]
+        lib.shimkk_pair_compute.restype = C.c_int
+        lib.shimkk_get_forces.argtypes = [vp, vp]
+        lib.shimkk_get_eng.argtypes = [vp]
+        lib.shimkk_get_eng.restype = C.c_double
+        lib.shimkk_get_virial.argtypes = [vp, vp]
+        lib.shimkk_get_eatom.argtypes = [vp, vp]
+        lib.shimkk_get_eatom.restype = C.c_int
+        self.lib = lib
+        x = np.ascontiguousarray(atom.x, dtype=np.float64)
+        t = np.ascontiguousarray(atom.type, dtype=np.int32)
+        tag = np.ascontiguousarray(atom.tag, dtype=np.int64)
+        self.ntot, self.nlocal = atom.nlocal + atom.nghost, atom.nlocal
+        self.h = lib.shimkk_create(atom.ntypes, atom.nlocal, atom.nghost, x.ctypes.data, t.ctypes.data, tag.ctypes.data, neighflag)
+        il = np.ascontiguousarray(lst.ilist[:self.ntot], dtype=np.int32)
+        nn = np.ascontiguousarray(lst.numneigh[:self.ntot], dtype=np.int32)
+        nf = np.ascontiguousarray(lst.neigh_flat, dtype=np.int32)
+        fi = np.ascontiguousarray(lst.first[:self.ntot], dtype=np.int64)
+        lib.shimkk_set_list(self.h, lst.inum, lst.gnum, il.ctypes.data, nn.ctypes.data, nf.ctypes.data, fi.ctypes.data, 1 if layout_left else 0)
+        self._ck(lib.shimkk_pair_create(self.h))
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise ShimError(self.lib.shimkk_last_error(self.h).decode())
+
+    def pair_style(self, args=()):
+        self._ck(self.lib.shimkk_pair_settings(self.h, len(args), ShimLammps._argv(args)))
+
+    def pair_coeff(self, args):
+        self._ck(self.lib.shimkk_pair_coeff(self.h, len(args), ShimLammps._argv(args)))
+
+    def init(self, newton_pair=1):
+        self.lib.shimkk_set_newton(self.h, newton_pair)
+        self._ck(self.lib.shimkk_pair_init_style(self.h))
+
+    def compute(self, eflag=3, vflag=1, zero=True):
+        self._ck(self.lib.shimkk_pair_compute(self.h, eflag, vflag, 1 if zero else 0))
+        f = np.zeros((self.ntot, 3))
+        self.lib.shimkk_get_forces(self.h, f.ctypes.data)
+        vir = np.zeros(6)
+        self.lib.shimkk_get_virial(self.h, vir.ctypes.data)
+        eatom = np.zeros(self.ntot)
+        has = self.lib.shimkk_get_eatom(self.h, eatom.ctypes.data) == 0
+        return dict(f=f, eng_vdwl=self.lib.shimkk_get_eng(self.h), virial=vir, eatom=eatom if has else None)
+
+    def close(self):
+        if self.h:
+            self.lib.shimkk_destroy(self.h)
             self.h = None
 
     def __del__(self):

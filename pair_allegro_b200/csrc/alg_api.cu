@@ -366,6 +366,43 @@ __global__ void k_mtype(int ntot, const int* __restrict__ type, const int* __res
 }
 
 // finalize: fixed-point accumulators -> model forces (double), optionally f += ; per-atom energies
+// Thread-per-atom variant of K1 for the KOKKOS device layout (LayoutLeft: d_neighbors(i,jj) at base[i + jj*stride_jj]): the
+// lanes of a warp are consecutive atoms, so every step of the jj loop is one coalesced read (the warp-per-atom kernel
+// above would touch 32 different lines per step).  Same filter, same (ilist, jlist) order.
+template <bool FILL>
+__global__ void k_edges_tpa(int nlocal, const double* __restrict__ x, const int* __restrict__ type, const int* __restrict__ ilist,
+                            NeighAcc acc, const double* __restrict__ cutsq, int ntypes, int filter_le,
+                            int* __restrict__ cnt_out, const int* __restrict__ rowptr, const int* __restrict__ mtype,
+                            int* __restrict__ edge_j, int* __restrict__ edge_c, float4* __restrict__ rvec, long cap) {
+  const int ii = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ii >= nlocal) return;
+  const int i = ilist[ii];
+  const int ti = type[i] - 1;
+  const int zi = mtype[i];
+  const int n = zi < 0 ? 0 : acc.cnt[i];
+  const int* ptr = acc.base + (long long)i * acc.stride_i;
+  int pos = FILL ? rowptr[ii] : 0, total = 0;
+  for (int jj = 0; jj < n; ++jj) {
+    const int j = ptr[(long long)jj * acc.stride_jj] & NEIGHMASK;
+    double dx, dy, dz;
+    const double rsq = rsq_nofma(x, i, j, dx, dy, dz);
+    const double c2 = cutsq[ti * ntypes + (type[j] - 1)];
+    const bool keep = (filter_le ? (rsq <= c2) : (rsq < c2)) && mtype[j] >= 0;
+    if (!keep) continue;
+    if (FILL) {
+      if (pos < cap) {
+        edge_j[pos] = j;
+        edge_c[pos] = ii;
+        rvec[pos] = make_float4((float)(-dx), (float)(-dy), (float)(-dz), __int_as_float(zi | (mtype[j] << 8)));
+      }
+      ++pos;
+    } else {
+      ++total;
+    }
+  }
+  if (!FILL) cnt_out[ii] = total;
+}
+
 // info != nullptr (fused pipeline): a step the fused kernel refused (info[1] > rows or info[3]) must not touch f; the host repeats it
 __global__ void k_forces(int ntot, const unsigned long long* __restrict__ facc, double* __restrict__ forces, double* __restrict__ f_inout,
                          const int* __restrict__ info, int rows) {
@@ -834,9 +871,14 @@ static int ensure_edge_arrays(alg_handle* h, long cap) {
 static void launch_edge_fill(alg_handle* h, const StepIO& io, long cap) {
   cudaStream_t st = h->stream;
   const int wblocks = (int)(((long)io.nlocal * 32 + 255) / 256);
-  k_edges<true><<<wblocks, 256, 0, st>>>(io.nlocal, io.d_x, io.d_type, io.d_ilist, io.acc, h->d_cutsq.as<double>(), h->ntypes, h->filter_le ? 1 : 0,
-                                         nullptr, h->d_rowptr.as<int>(), h->d_mtype.as<int>(), h->d_edge_j.as<int>(), h->d_edge_c.as<int>(),
-                                         h->d_rvec.as<float4>(), cap);
+  if (!io.acc.flat && io.acc.stride_i == 1 && io.acc.stride_jj > 1)
+    k_edges_tpa<true><<<(io.nlocal + 127) / 128, 128, 0, st>>>(io.nlocal, io.d_x, io.d_type, io.d_ilist, io.acc, h->d_cutsq.as<double>(), h->ntypes, h->filter_le ? 1 : 0,
+                                                               nullptr, h->d_rowptr.as<int>(), h->d_mtype.as<int>(), h->d_edge_j.as<int>(), h->d_edge_c.as<int>(),
+                                                               h->d_rvec.as<float4>(), cap);
+  else
+    k_edges<true><<<wblocks, 256, 0, st>>>(io.nlocal, io.d_x, io.d_type, io.d_ilist, io.acc, h->d_cutsq.as<double>(), h->ntypes, h->filter_le ? 1 : 0,
+                                           nullptr, h->d_rowptr.as<int>(), h->d_mtype.as<int>(), h->d_edge_j.as<int>(), h->d_edge_c.as<int>(),
+                                           h->d_rvec.as<float4>(), cap);
   if (h->keep_edges)
     k_edge_index<<<1024, 256, 0, st>>>(h->d_rowptr.as<int>(), io.nlocal, cap, h->d_edge_j.as<int>(), h->d_edge_c.as<int>(), io.d_ilist,
                                        h->d_edge_index.as<long long>());
@@ -992,8 +1034,13 @@ static int run_step(alg_handle* h, const StepIO& io, double* eng, double* virial
   CK(h->d_info.ensure(sizeof(int) * 16));              // [0..3] fused tile plan (see k_plan), [8] 1 + index of an atom without model type
   CK(cudaMemsetAsync(h->d_info.p, 0, sizeof(int) * 16, st));
   k_mtype<<<(ntot + 255) / 256, 256, 0, st>>>(ntot, io.d_type, h->d_tmap.as<int>(), h->ntypes, h->d_mtype.as<int>(), h->d_info.as<int>() + 8);
-  k_edges<false><<<wblocks, 256, 0, st>>>(nlocal, io.d_x, io.d_type, io.d_ilist, io.acc, h->d_cutsq.as<double>(), h->ntypes, h->filter_le ? 1 : 0,
-                                          h->d_cnt.as<int>(), nullptr, h->d_mtype.as<int>(), nullptr, nullptr, nullptr, 0);
+  const bool tpa = !io.acc.flat && io.acc.stride_i == 1 && io.acc.stride_jj > 1;     // KOKKOS LayoutLeft neighbour view
+  if (tpa)
+    k_edges_tpa<false><<<(nlocal + 127) / 128, 128, 0, st>>>(nlocal, io.d_x, io.d_type, io.d_ilist, io.acc, h->d_cutsq.as<double>(), h->ntypes, h->filter_le ? 1 : 0,
+                                                              h->d_cnt.as<int>(), nullptr, h->d_mtype.as<int>(), nullptr, nullptr, nullptr, 0);
+  else
+    k_edges<false><<<wblocks, 256, 0, st>>>(nlocal, io.d_x, io.d_type, io.d_ilist, io.acc, h->d_cutsq.as<double>(), h->ntypes, h->filter_le ? 1 : 0,
+                                            h->d_cnt.as<int>(), nullptr, h->d_mtype.as<int>(), nullptr, nullptr, nullptr, 0);
   CK(cudaMemsetAsync(h->d_cnt.as<int>() + nlocal, 0, sizeof(int), st));
   size_t tmp_bytes = 0;
   cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, h->d_cnt.as<int>(), h->d_rowptr.as<int>(), nlocal + 1, st);

@@ -163,3 +163,32 @@ def test_neighbour_list_reuse_between_rebuilds(ours_lib):
     assert pair.handle.stats("list_reused", 1)[0] == 1
     pair.compute(atom, lst, neigh_ago=0)
     assert pair.handle.stats("list_reused", 1)[0] == 0
+
+
+@pytest.mark.parametrize("layout_left", [True, False])
+@pytest.mark.parametrize("name", ["CuPd_r5", "aspirin_r5", "Cu_r15"])
+def test_cpp_pair_style_allegro_kk(name, layout_left, ensure_built):
+    """`pair_style allegro/kk` (src/pair_allegro_b200_kokkos.cpp, the twin of the reference's PairAllegroKokkos<false>,
+    pair_nequip_allegro_kokkos.cpp:87-353) on device-resident atoms and the KOKKOS 2-D neighbour view in both layouts
+    (LayoutLeft = the CUDA default -> thread-per-atom edge build; LayoutRight -> warp-per-atom)"""
+    from lmpshim import driver
+    atom, lst, z = load_golden(name)
+    lmp = driver.ShimLammpsKK(atom, lst, layout_left=layout_left)
+    lmp.pair_style([])
+    lmp.pair_coeff(["*", "*", alg_path(name)] + str(z["type_names"]).split())
+    lmp.init(newton_pair=1)
+    for eflag, vflag in ((3, 1), (0, 0), (1, 1)):       # (0, 0): the fully asynchronous call -- forces only
+        out = lmp.compute(eflag=eflag, vflag=vflag)
+        assert np.abs(out["f"] - z["f"]).max() < 1e-4
+        if eflag & 1:
+            assert abs(out["eng_vdwl"] - float(z["eng_vdwl"])) < 1e-5 * max(1.0, np.abs(z["eatom"][:atom.nlocal]).sum())
+        if eflag & 2:
+            np.testing.assert_allclose(out["eatom"][:atom.nlocal], z["eatom"][:atom.nlocal], rtol=1e-5, atol=1e-5)
+        if vflag:
+            assert np.abs(out["virial"] - z["virial6"]).max() < 1e-4 * max(1.0, np.abs(z["virial6"]).max())
+    # the reference rejects `neigh full` for allegro/kk (pair_nequip_allegro_kokkos.cpp:402-405)
+    bad = driver.ShimLammpsKK(atom, lst, neighflag=driver.ShimLammpsKK.FULL)
+    bad.pair_style([])
+    bad.pair_coeff(["*", "*", alg_path(name)] + str(z["type_names"]).split())
+    with pytest.raises(driver.ShimError, match="requires the 'neigh half' flag"):
+        bad.init(newton_pair=1)

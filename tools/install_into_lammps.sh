@@ -36,6 +36,12 @@ for f in "$here"/src/pair_allegro_b200.h "$here"/src/pair_allegro_b200.cpp "$her
          "$here"/src/compute_allegro_b200.cpp "$here"/include/allegro_b200.h; do
   if $link; then ln -sf "$f" "$lammps_dir/src/$(basename "$f")"; else cp "$f" "$lammps_dir/src/$(basename "$f")"; fi
 done
+# pair_style allegro/kk goes where the reference's patch_lammps.sh puts its Kokkos twin: <lammps>/src/KOKKOS (patch_lammps.sh:61-66)
+if [ -d "$lammps_dir/src/KOKKOS" ]; then
+  for f in "$here"/src/pair_allegro_b200_kokkos.h "$here"/src/pair_allegro_b200_kokkos.cpp; do
+    if $link; then ln -sf "$f" "$lammps_dir/src/KOKKOS/$(basename "$f")"; else cp "$f" "$lammps_dir/src/KOKKOS/$(basename "$f")"; fi
+  done
+fi
 if ! $patched; then
   cat >> "$lammps_dir/cmake/CMakeLists.txt" <<EOF2
 
