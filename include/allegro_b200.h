@@ -83,8 +83,9 @@ ALG_API int alg_set_type_map(alg_handle* h, int ntypes, const int* lammps_type_t
  *                  combines the per-atom sums itself; inter-phase state in CTA-private scratch; no host synchronisation,
  *                  no fix-up launches.  Needs <= fused_batch*128 neighbours inside the cutoff per atom.  tiled = the
  *                  chunked edge-tile pipeline (any neighbour count; one host synchronisation per step on the CSR row
- *                  pointer, one kernel per phase and chunk).  auto = fused, and tiled from the first step on that meets
- *                  an atom with more neighbours than a batch holds (that step is repeated transparently), or when debug=1.
+ *                  pointer, one kernel per phase and chunk).  auto = fused for l_max = 1 models -- tiled from the first step on
+ *                  that meets an atom with more neighbours than a batch holds (that step is repeated transparently) or
+ *                  when debug=1 -- and tiled for l_max >= 2, where the per-phase kernels are measured faster.
  *   "fused_batch"  fused pipeline: 128-edge tiles per batch (default 8).  A CTA runs the tiles of a batch phase by phase, so
  *                  the code of one phase stays in the instruction cache for the whole batch
  *   "phase_align"  fused pipeline: "1" (default) keeps the CTAs that share an SM in the same phase (bounded wait at every phase

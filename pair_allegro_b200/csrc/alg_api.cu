@@ -1014,7 +1014,12 @@ static int resolve_pending(alg_handle* h, bool block = true, unsigned keep = 0) 
 static bool fused_selected(const alg_handle* h) {
   if (h->pipeline_mode == 2 || !h->use_tc || !h->pipe || !h->pipe->run_fused || h->fused_grid <= 0) return false;
   if (h->pipeline_mode == 1) return true;
-  return !h->force_tiled && !h->debug;               // auto: per-stage intermediates (debug=1) exist only in the chunked pipeline
+  // auto: the fused kernel where it is the faster one.  Measured on the B200 (bench.py, strict fp32): l_max = 1 fused and
+  // chunked pipeline are within 4 % of each other (and only the fused one is asynchronous); for l_max >= 2 the per-phase
+  // kernels of the chunked pipeline are 1.25x (l_max = 2) / 1.5x (l_max = 3) faster -- the tensor-product code of those
+  // models is register-bound and ptxas allocates a stand-alone phase kernel better than the same phase inlined into the
+  // persistent kernel.  Per-stage intermediates (debug=1) exist only in the chunked pipeline.
+  return h->L == 1 && !h->force_tiled && !h->debug;
 }
 
 static int run_step(alg_handle* h, const StepIO& io, double* eng, double* virial6) {

@@ -90,7 +90,7 @@ template <int L> struct SmemTC {
                                                        // different banks (lanes of one warp read feature f of 1-3 distinct centres)
   static constexpr int oSEG = oGS + GSROWS * GSSTRIDE; // int: segment table seg[TM+1], nseg, warp counts (TM + 16 ints)
   static constexpr int oBAR = oSEG + TM + 16;          // 3 mbarriers + tmem pointer (8 floats: mbar, wbar, tmem ptr, wbar2), fused kernel: tile number
-  static constexpr int TOTAL = oBAR + 12;
+  static constexpr int TOTAL = oBAR + 12 + 12;         // + the fused kernel's batch / loop state (FS_*)
   static constexpr size_t BYTES = (size_t)TOTAL * sizeof(float) + 1024;   // + alignment slack
   // buffers inside the scratch / weight regions (live ranges never overlap a weight block that is still in use)
   static constexpr int oWS = oOPL;                                 // env weights of one block, edge-major [128][65]
@@ -1553,57 +1553,115 @@ __device__ __forceinline__ void fused_fixup_e(const ChunkArgs& a, int e0, int e1
     a.esum[ce] = acc;
   }
 }
+// The batch / loop state lives in shared memory (volatile), not in registers: the phase bodies were tuned to exactly
+// 128 (255) registers as stand-alone kernels; ~20 more values live across them made ptxas spill (800-byte frames for
+// l_max = 2) and the fused kernel up to 1.7x slower than the per-phase kernels.  Every tile-phase rebuilds its context
+// from shared memory, so nothing but the kernel parameters (constant bank) is live across a phase body.
+enum { FS_E0 = 0, FS_E1, FS_NB, FS_TB, FS_PHASE, FS_MPH, FS_WPH, FS_WPH2, FS_C0, FS_BATCH, FS_COUNT };
+template <int L> __device__ __forceinline__ volatile int* fused_state(float* sm_raw) {
+  float* sm = sm_raw + (((1024u - (umma::smem_u32(sm_raw) & 1023u)) & 1023u) >> 2);
+  return reinterpret_cast<volatile int*>(sm + SmemTC<L>::oBAR) + 12;
+}
+template <int L> __device__ __forceinline__ TcCtx fused_ctx(float* sm_raw, const TcW& tw, int batch) {
+  using SM = SmemTC<L>;
+  TcCtx c;
+  c.sm = sm_raw + (((1024u - (umma::smem_u32(sm_raw) & 1023u)) & 1023u) >> 2);
+  c.mbar = reinterpret_cast<uint64_t*>(c.sm + SM::oBAR);
+  c.wbar = c.mbar + 1;
+  c.wbar2 = c.mbar + 3;
+  c.tmem = *reinterpret_cast<volatile uint32_t*>(c.mbar + 2);
+  volatile int* fs = reinterpret_cast<volatile int*>(c.sm + SM::oBAR) + 12;
+  c.mph = (uint32_t)fs[FS_MPH]; c.wph = (uint32_t)fs[FS_WPH]; c.wph2 = (uint32_t)fs[FS_WPH2];
+  c.passes = tw.passes;
+  const int t = threadIdx.x;
+  c.m = t & 127; c.half = t >> 7; c.q = (t >> 5) & 3;
+  c.c0 = fs[FS_C0];
+  c.goff = (size_t)((int)blockIdx.x * batch) * 128 * DimsTC<L>::F;
+  return c;
+}
+__device__ __forceinline__ void fused_phase_align_s(unsigned* sm_phase, volatile int* fs, unsigned residents) {
+  if (sm_phase == nullptr || residents < 2) return;
+  if (threadIdx.x == 0) {
+    unsigned smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    const unsigned mine = (unsigned)fs[FS_PHASE] + 1u;
+    fs[FS_PHASE] = (int)mine;
+    atomicAdd(sm_phase + smid, 1u);
+    const unsigned want = mine * residents;
+    const long long t0 = clock64();
+    while (*reinterpret_cast<volatile unsigned*>(sm_phase + smid) < want && clock64() - t0 < 400000) { }
+  }
+  __syncthreads();
+}
 template <int L, int NLAYERS>
 __global__ void __launch_bounds__(NT, DimsTC<L>::MINB) k_fused_tc(const __grid_constant__ ChunkArgs a, const __grid_constant__ ModelW w, const __grid_constant__ TcW tw,
                                                     const __grid_constant__ FusedPlan plan) {
   using D = DimsTC<L>; constexpr int TM = 128;
   extern __shared__ __align__(1024) float sm_raw[];
-  const int nbatch = plan.info[0];
-  const int B = plan.batch;
-  if (plan.info[1] > B * TM || plan.info[3] != 0) return;      // a centre with more edges than a batch holds / edge arrays too small: the host falls back
-  TcCtx c = tc_begin<L>(sm_raw, tw);
-  int* next_batch = reinterpret_cast<int*>(c.sm + SmemTC<L>::oBAR) + 10;    // after the mbarriers / TMEM pointer
-  const int slot0 = (int)blockIdx.x * B;
-  c.goff = (size_t)slot0 * TM * D::F;
-  int e0 = 0, e1 = 0;
-  unsigned my_phase = 0;
-  const unsigned residents = (gridDim.x + plan.num_sms - 1) / plan.num_sms;
-  // one phase of one tile of the batch: geometry -> shared memory, then the phase body on the tile's private scratch slot
-#define ALG_PHASE(PRE, ...)                                                      \
-  fused_phase_align(plan.sm_phase, my_phase, residents);                          \
-  _Pragma("unroll 1") for (int tb = 0; tb < nb; ++tb) {                           \
-    const int es = e0 + tb * TM, nvalid = min(TM, e1 - es), slot = slot0 + tb;    \
-    const GeomIn gi = tc_geom_load(a, es, nvalid);                                \
-    PRE;                                                                          \
-    const Geom g = tc_tile_begin<L>(a, w, c, gi, nvalid);                         \
-    __VA_ARGS__;                                                                  \
-    __syncthreads();                                                              \
+  if (plan.info[1] > plan.batch * TM || plan.info[3] != 0) return;      // a centre with more edges than a batch holds / edge arrays too small: the host falls back
+  {
+    TcCtx c = tc_begin<L>(sm_raw, tw);
+    volatile int* fs = fused_state<L>(sm_raw);
+    if (threadIdx.x < FS_COUNT) fs[threadIdx.x] = 0;
+    __syncthreads();
+    (void)c;
   }
-#define ALG_FIX(ptr) fused_fixup<D::F>(a, c, e0, e1, nb, slot0, (ptr) + c.goff)
+  // one phase of one tile of the batch: geometry -> shared memory, then the phase body on the tile's private scratch slot
+#define ALG_PHASE(PRE, ...)                                                                        \
+  fused_phase_align_s(plan.sm_phase, fused_state<L>(sm_raw), (gridDim.x + plan.num_sms - 1) / plan.num_sms); \
+  _Pragma("unroll 1") for (;;) {                                                                    \
+    volatile int* fs = fused_state<L>(sm_raw);                                                      \
+    const int tb = fs[FS_TB];                                                                       \
+    if (tb >= fs[FS_NB]) break;                                                                     \
+    TcCtx c = fused_ctx<L>(sm_raw, tw, plan.batch);                                                 \
+    const int es = fs[FS_E0] + tb * TM, nvalid = min(TM, fs[FS_E1] - es), slot = (int)blockIdx.x * plan.batch + tb; \
+    const GeomIn gi = tc_geom_load(a, es, nvalid);                                                  \
+    PRE;                                                                                            \
+    const Geom g = tc_tile_begin<L>(a, w, c, gi, nvalid);                                           \
+    __VA_ARGS__;                                                                                    \
+    __syncthreads();                                                                                \
+    if (threadIdx.x == 0) { fs[FS_TB] = fs[FS_TB] + 1; fs[FS_MPH] = (int)c.mph; fs[FS_WPH] = (int)c.wph; fs[FS_WPH2] = (int)c.wph2; } \
+    __syncthreads();                                                                                \
+  }                                                                                                 \
+  __syncthreads();               /* every thread has seen the terminating tile index before it is reset */ \
+  if (threadIdx.x == 0) fused_state<L>(sm_raw)[FS_TB] = 0;                                          \
+  __syncthreads();
+#define ALG_FIX(ptr)                                                                                \
+  {                                                                                                 \
+    volatile int* fs = fused_state<L>(sm_raw);                                                      \
+    const TcCtx c = fused_ctx<L>(sm_raw, tw, plan.batch);                                           \
+    fused_fixup<D::F>(a, c, fs[FS_E0], fs[FS_E1], fs[FS_NB], (int)blockIdx.x * plan.batch, (ptr) + c.goff); \
+  }
 #pragma unroll 1
   for (;;) {
     // dynamic batch queue: the result does not depend on which CTA runs a batch (fixed-point accumulation), so the
     // kernel balances itself whatever the number of resident CTAs is
-    if (threadIdx.x == 0) *next_batch = atomicAdd(plan.info + 5, 1);
-    __syncthreads();
-    const int b = *next_batch;
-    __syncthreads();
-    if (b >= nbatch) {
-      if (plan.sm_phase && threadIdx.x == 0) { unsigned smid; asm volatile("mov.u32 %0, %%smid;" : "=r"(smid)); atomicAdd(plan.sm_phase + smid, 1u << 24); }
-      break;
-    }
-    const int bc0 = plan.batch_c0[b];
-    e0 = a.rowptr[bc0]; e1 = a.rowptr[plan.batch_c0[b + 1]];
-    const int nb = (e1 - e0 + TM - 1) / TM;
-    if (nb <= 0) {                                              // only centres without neighbours: hand in the tickets of the skipped phases
-      if (plan.sm_phase && residents >= 2 && threadIdx.x == 0) {
-        unsigned smid; asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-        my_phase += 2 * NLAYERS + 1;
-        atomicAdd(plan.sm_phase + smid, 2u * NLAYERS + 1u);
+    {
+      volatile int* fs = fused_state<L>(sm_raw);
+      if (threadIdx.x == 0) {
+        const int b = atomicAdd(plan.info + 5, 1);
+        fs[FS_BATCH] = b;
+        if (b < plan.info[0]) {
+          const int bc0 = plan.batch_c0[b];
+          const int e0 = a.rowptr[bc0], e1 = a.rowptr[plan.batch_c0[b + 1]];
+          fs[FS_E0] = e0; fs[FS_E1] = e1; fs[FS_NB] = (e1 - e0 + TM - 1) / TM; fs[FS_TB] = 0; fs[FS_C0] = bc0;
+        }
       }
-      continue;
+      __syncthreads();
+      if (fs[FS_BATCH] >= plan.info[0]) {
+        if (plan.sm_phase && threadIdx.x == 0) { unsigned smid; asm volatile("mov.u32 %0, %%smid;" : "=r"(smid)); atomicAdd(plan.sm_phase + smid, 1u << 24); }
+        break;
+      }
+      if (fs[FS_NB] <= 0) {                                     // only centres without neighbours: hand in the tickets of the skipped phases
+        if (plan.sm_phase && threadIdx.x == 0) {
+          unsigned smid; asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+          fs[FS_PHASE] = fs[FS_PHASE] + 2 * NLAYERS + 1;
+          atomicAdd(plan.sm_phase + smid, 2u * NLAYERS + 1u);
+        }
+        __syncthreads();
+        continue;
+      }
     }
-    c.c0 = bc0;
     ALG_PHASE((void)0, f0_body<L>(a, w, tw, c, g, slot, es, nvalid));
     ALG_FIX(a.gamma[0]);
     if constexpr (NLAYERS == 1) {
@@ -1619,7 +1677,10 @@ __global__ void __launch_bounds__(NT, DimsTC<L>::MINB) k_fused_tc(const __grid_c
       ALG_FIX(a.gamma[2]);
       ALG_PHASE(fk_prefetch<L>(a, &c, slot, 2, gi, c.c0, c.goff), (t_body<L, false>(a, w, tw, c, g, slot, es, nvalid, 2)));
     }
-    fused_fixup_e(a, e0, e1, nb, slot0);
+    {
+      volatile int* fs = fused_state<L>(sm_raw);
+      fused_fixup_e(a, fs[FS_E0], fs[FS_E1], fs[FS_NB], (int)blockIdx.x * plan.batch);
+    }
     ALG_FIX(a.dgamma[NLAYERS - 1]);
     if constexpr (NLAYERS == 2) {
       ALG_PHASE(bk_prefetch<L>(a, slot, 0, gi, c.c0, c.goff), (bk_body<L, 'B', true>(a, w, tw, c, g, slot, es, nvalid, 0)));
@@ -1634,7 +1695,10 @@ __global__ void __launch_bounds__(NT, DimsTC<L>::MINB) k_fused_tc(const __grid_c
   }
 #undef ALG_PHASE
 #undef ALG_FIX
-  tc_end(c);
+  {
+    TcCtx c = fused_ctx<L>(sm_raw, tw, plan.batch);
+    tc_end(c);
+  }
 }
 
 }  // namespace alg
