@@ -802,10 +802,10 @@ static int ensure_chunk_buffers(alg_handle* h, long max_tiles, long max_centres)
   const size_t TM = pi.TM;
   for (int k = 0; k < h->nl; ++k) CK(h->c_X[k].ensure(sizeof(float) * max_tiles * S * TM));
   CK(h->c_W0.ensure(sizeof(float) * max_tiles * pi.ENVW * TM));
-  for (int k = 1; k < h->nl; ++k) CK(h->c_V[k].ensure(sizeof(float) * max_tiles * U * pi.vdim[k] * TM));
+  for (int k = 1; k < h->nl; ++k) CK(h->c_V[k].ensure(sizeof(float) * max_tiles * U * pi.vstride[k] * TM));
   CK(h->c_dX.ensure(sizeof(float) * max_tiles * S * TM));
   if (h->use_tc) for (int k = 0; k <= h->nl; ++k) CK(h->c_ZD[k].ensure(sizeof(float) * max_tiles * 3 * 64 * TM));   // stage 0 = two-body, 1+k = layer k
-  if (h->nl > 1) for (int q = 0; q < 2; ++q) CK(h->c_dV[q].ensure(sizeof(float) * max_tiles * U * pi.dvdim * TM));
+  if (h->nl > 1) for (int q = 0; q < 2; ++q) CK(h->c_dV[q].ensure(sizeof(float) * max_tiles * U * pi.dvstride * TM));
   CK(h->c_dY.ensure(sizeof(float) * max_tiles * pi.NSH * TM));
   CK(h->c_du.ensure(sizeof(float) * max_tiles * TM));
   for (int k = 0; k < h->nl; ++k) {
@@ -1360,16 +1360,16 @@ extern "C" int alg_get_output(alg_handle* h, const char* name, const double** pt
       detile(raw, h->dbg_ntiles, 1, pi.TM, E, out);
     } else if (key.size() == 2 && key[0] == 'V' && key[1] >= '1' && key[1] < '0' + h->nl) {
       const int k = key[1] - '0';
-      CK(fetchf(h->c_V[k].p, (size_t)h->dbg_ntiles * U * pi.vdim[k] * pi.TM, raw));
-      detile(raw, h->dbg_ntiles, U * pi.vdim[k], pi.TM, E, out);      // [E][u][comp]
-      if (h->use_tc && pi.vdim[k] % 4 == 0) {                           // tensor-core pipeline: comp4 packing inside a channel block
-        const int vd = pi.vdim[k], TMv = pi.TM;
-        for (long e = 0; e < E; ++e) {
-          const long t = e / TMv, m = e % TMv;
-          for (int u = 0; u < U; ++u)
-            for (int cc = 0; cc < vd; ++cc)
-              out[((size_t)e * U + u) * vd + cc] = raw[((size_t)t * U + u) * vd * TMv + ((size_t)(cc >> 2) * TMv + m) * 4 + (cc & 3)];
-        }
+      const int vd = pi.vdim[k], vs = pi.vstride[k], TMv = pi.TM;
+      CK(fetchf(h->c_V[k].p, (size_t)h->dbg_ntiles * U * vs * TMv, raw));
+      out.assign((size_t)E * U * vd, 0.0);                              // [E][u][comp]
+      const bool comp4 = h->use_tc && vs % 4 == 0;                      // tensor-core pipeline: comp4 packing inside a (padded) channel block
+      for (long e = 0; e < E; ++e) {
+        const long t = e / TMv, m = e % TMv;
+        for (int u = 0; u < U; ++u)
+          for (int cc = 0; cc < vd; ++cc)
+            out[((size_t)e * U + u) * vd + cc] = comp4 ? raw[((size_t)t * U + u) * vs * TMv + ((size_t)(cc >> 2) * TMv + m) * 4 + (cc & 3)]
+                                                       : raw[(((size_t)t * U + u) * vs + cc) * TMv + m];
       }
     } else if ((key.rfind("gamma", 0) == 0 && key.size() == 6) || (key.rfind("dgamma", 0) == 0 && key.size() == 7)) {
       const bool d = key[0] == 'd';

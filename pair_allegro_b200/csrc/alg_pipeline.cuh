@@ -12,6 +12,8 @@ struct PipelineInfo {
   int L, TM, NSH, ENVW, F;
   int vdim[3];        // components per channel of V^k (k = 1..nl-1), index by k
   int dvdim;          // max over vdim
+  int vstride[3];     // storage components per channel of V^k (tensor-core pipeline: padded, see vpad)
+  int dvstride;
   size_t smem_bytes;
 };
 
@@ -58,6 +60,8 @@ template <int L> PipelineInfo info_impl(int nl) {
   if (nl == 2) p.vdim[1] = tpgen::TP<L, 'B'>::DOUT;
   if (nl == 3) { p.vdim[1] = tpgen::TP<L, 'C'>::DOUT; p.vdim[2] = tpgen::TP<L, 'D'>::DOUT; }
   p.dvdim = p.vdim[1] > p.vdim[2] ? p.vdim[1] : p.vdim[2];
+  for (int q = 0; q < 3; ++q) p.vstride[q] = p.vdim[q];
+  p.dvstride = p.dvdim;
   p.smem_bytes = Smem<L>::BYTES;
   return p;
 }
@@ -127,6 +131,8 @@ template <int L> PipelineInfo info_tc_impl(int nl) {
   PipelineInfo p = info_impl<L>(nl);
   p.TM = DimsTC<L>::TM;
   p.smem_bytes = SmemTC<L>::BYTES;
+  for (int q = 0; q < 3; ++q) p.vstride[q] = vpad(p.vdim[q]);
+  p.dvstride = vpad(p.dvdim);
   return p;
 }
 template <int L> cudaError_t init_tc_impl() {

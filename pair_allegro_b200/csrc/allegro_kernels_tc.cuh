@@ -509,15 +509,22 @@ template <int L> __device__ ALG_NI void tc_env_all(const ChunkArgs& a, const Mod
 // s-part operand column of (scalar path q, channel u): K index inside the 64-wide "s" block
 __device__ __forceinline__ int s_col(int q, int u) { return q * U + u; }
 
-// per-channel component vectors of V^k / dV^k (N components of edge e, channel block base `g` = [N][128] floats):
-// when N is a multiple of 4 the components are packed in groups of four per edge ("comp4": ((cc/4)*128 + e)*4 + cc%4)
-// so that a channel is N/4 128-bit accesses; otherwise plain [cc][128]
+// per-channel component vectors of V^k / dV^k (N components of edge e, channel block base `g`): when the (padded)
+// component count is a multiple of 4 the components are packed in groups of four per edge ("comp4":
+// ((cc/4)*128 + e)*4 + cc%4) so that a channel is NP/4 128-bit accesses and a warp covers 512 contiguous bytes;
+// otherwise plain [cc][128].  N % 4 == 3 (7, 31: the l_max = 1 / 3 full-parity sets) is padded by one component: a quarter
+// of the memory instructions of the l_max = 3 tensor-product phases for 3 % more bytes.
+__host__ __device__ constexpr int vpad(int n) { return (n % 4 == 3) ? n + 1 : n; }
 template <int N> __device__ __forceinline__ void vec_load(const float* g, int e, float* v) {
-  if constexpr (N % 4 == 0) {
+  constexpr int NP = vpad(N);
+  if constexpr (NP % 4 == 0) {
 #pragma unroll
-    for (int q = 0; q < N / 4; ++q) {
+    for (int q = 0; q < NP / 4; ++q) {
       const float4 t = *reinterpret_cast<const float4*>(g + ((q * 128 + e) << 2));
-      v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
+      v[4 * q] = t.x;
+      if (4 * q + 1 < N) v[4 * q + 1] = t.y;
+      if (4 * q + 2 < N) v[4 * q + 2] = t.z;
+      if (4 * q + 3 < N) v[4 * q + 3] = t.w;
     }
   } else {
 #pragma unroll
@@ -525,12 +532,25 @@ template <int N> __device__ __forceinline__ void vec_load(const float* g, int e,
   }
 }
 template <int N> __device__ __forceinline__ void vec_store(float* g, int e, const float* v) {
-  if constexpr (N % 4 == 0) {
+  constexpr int NP = vpad(N);
+  if constexpr (NP % 4 == 0) {
 #pragma unroll
-    for (int q = 0; q < N / 4; ++q) *reinterpret_cast<float4*>(g + ((q * 128 + e) << 2)) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+    for (int q = 0; q < NP / 4; ++q)
+      *reinterpret_cast<float4*>(g + ((q * 128 + e) << 2)) =
+          make_float4(v[4 * q], 4 * q + 1 < N ? v[4 * q + 1] : 0.f, 4 * q + 2 < N ? v[4 * q + 2] : 0.f, 4 * q + 3 < N ? v[4 * q + 3] : 0.f);
   } else {
 #pragma unroll
     for (int cc = 0; cc < N; ++cc) g[cc * 128 + e] = v[cc];
+  }
+}
+template <int N> __device__ __forceinline__ void vec_prefetch(const float* g, int e) {
+  constexpr int NP = vpad(N);
+  if constexpr (NP % 4 == 0) {
+#pragma unroll
+    for (int q = 0; q < NP / 4; ++q) prefetch_l2(g + ((q * 128 + e) << 2));
+  } else {
+#pragma unroll
+    for (int cc = 0; cc < N; ++cc) prefetch_l2(g + cc * 128 + e);
   }
 }
 // raw global inputs of one tensor-product channel: FIRST layers read the L+1 embed weights w0[l][u]
@@ -546,14 +566,7 @@ template <int L, bool FIRST, int DIN> struct VinRaw {
 #pragma unroll
       for (int l = 0; l <= L; ++l) prefetch_l2(W0g + (l * U + u) * TM + e);
     } else {
-      const float* Vg = a.V[k] + ((size_t)tile * U + u) * DIN * TM;
-      if constexpr (DIN % 4 == 0) {
-#pragma unroll
-        for (int q = 0; q < DIN / 4; ++q) prefetch_l2(Vg + ((q * 128 + e) << 2));
-      } else {
-#pragma unroll
-        for (int cc = 0; cc < DIN; ++cc) prefetch_l2(Vg + cc * TM + e);
-      }
+      vec_prefetch<DIN>(a.V[k] + ((size_t)tile * U + u) * vpad(DIN) * TM, e);
     }
   }
   __device__ __forceinline__ void issue(const ChunkArgs& a, int tile, int k, int e, int u) {
@@ -563,7 +576,7 @@ template <int L, bool FIRST, int DIN> struct VinRaw {
 #pragma unroll
       for (int l = 0; l <= L; ++l) v[l] = W0g[(l * U + u) * TM + e];
     } else {
-      vec_load<DIN>(a.V[k] + ((size_t)tile * U + u) * DIN * TM, e, v);
+      vec_load<DIN>(a.V[k] + ((size_t)tile * U + u) * vpad(DIN) * TM, e, v);
     }
   }
   __device__ __forceinline__ void expand(int e, const float* Y_s, float* Vin) const {
@@ -600,7 +613,7 @@ __device__ ALG_NI void tc_tp_forward(const ChunkArgs& a, const LayerW& lw, const
   const int* c_s = reinterpret_cast<const int*>(c.sm + SM::oC);
   const int e = c.m, uh = c.half;
   const float* gam = gsrc.row(c_s[e], D::F);
-  float* Vng = WANT_V ? a.V[k + 1] + (size_t)tile * U * TP::DOUT * TM : nullptr;
+  float* Vng = WANT_V ? a.V[k + 1] + (size_t)tile * U * vpad(TP::DOUT) * TM : nullptr;
   const int q_lo = 2 * b, q_hi = D::lhi(b);
   struct In { Raw vin; float G[D::NSH]; };
   auto issue = [&](int s, In (&r)[TB]) {
@@ -623,7 +636,7 @@ __device__ ALG_NI void tc_tp_forward(const ChunkArgs& a, const LayerW& lw, const
       else TPA::template fwd<U>(Vin, r[bb].G, nullptr, nullptr, sc);
 #pragma unroll
       for (int q = 0; q < TP::N0; ++q) sq[q][bb] = sc[q];
-      if (WANT_V) vec_store<TP::DOUT>(Vng + (size_t)u * TP::DOUT * TM, e, Vout);
+      if (WANT_V) vec_store<TP::DOUT>(Vng + (size_t)u * vpad(TP::DOUT) * TM, e, Vout);
     }
     const int u0 = uh * D::CPT + s * TB;
 #pragma unroll
@@ -683,7 +696,7 @@ __device__ ALG_NI void tc_tp_backward(const ChunkArgs& a, const LayerW& lw, cons
     for (int bb = 0; bb < TB; ++bb) {
       const int u = chan(pass, jb * TB + bb);
       r[bb].vin.issue(a, tile, k, e, u);
-      if (HAS_DVOUT) vec_load<TP::DOUT>(dVnext + ((size_t)tile * U + u) * TP::DOUT * TM, e, r[bb].dv);
+      if (HAS_DVOUT) vec_load<TP::DOUT>(dVnext + ((size_t)tile * U + u) * vpad(TP::DOUT) * TM, e, r[bb].dv);
     }
   };
   auto eval = [&](int pass, int jb, const In (&r)[TB]) {
@@ -708,7 +721,7 @@ __device__ ALG_NI void tc_tp_backward(const ChunkArgs& a, const LayerW& lw, cons
           W0g[(l * U + u) * TM + e] = dw;      // in place: w0 -> dw0
         }
       } else {
-        vec_store<TP::DIN>(dVprev + ((size_t)tile * U + u) * TP::DIN * TM, e, dVin);
+        vec_store<TP::DIN>(dVprev + ((size_t)tile * U + u) * vpad(TP::DIN) * TM, e, dVin);
       }
 #pragma unroll
       for (int lm = 0; lm < D::NSH; ++lm) DG[e * D::DGS + lm * D::CHU + ul] = dG[lm];
@@ -721,14 +734,7 @@ __device__ ALG_NI void tc_tp_backward(const ChunkArgs& a, const LayerW& lw, cons
     const int u = chan(i / CPP, i % CPP);
     Raw::prefetch(a, tile, k, e, u);
     if (HAS_DVOUT) {
-      const float* dVg = dVnext + ((size_t)tile * U + u) * TP::DOUT * TM;
-      if constexpr (TP::DOUT % 4 == 0) {
-#pragma unroll
-        for (int q = 0; q < TP::DOUT / 4; ++q) prefetch_l2(dVg + ((q * 128 + e) << 2));
-      } else {
-#pragma unroll
-        for (int cc = 0; cc < TP::DOUT; ++cc) prefetch_l2(dVg + cc * TM + e);
-      }
+      vec_prefetch<TP::DOUT>(dVnext + ((size_t)tile * U + u) * vpad(TP::DOUT) * TM, e);
     }
   }
 #pragma unroll 1
