@@ -19,6 +19,7 @@ KEYS = ["gpu__time_duration.sum", "launch__grid_size", "launch__registers_per_th
         "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio",
         "smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio",
         "smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_no_instruction_per_issue_active.ratio",
         "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum"]
 
 
