@@ -60,7 +60,7 @@ def test_fused_equals_tiled(lmax, nlayers, ensure_built, tmp_path):
     atoms, lst = _fcc(8)
     alg = str(tmp_path / "m.alg")
     modelgen.random_alg(modelgen.default_config(type_names=["Ag"], r_max=5.0, avg_num_neighbors=26.0, seed=11, l_max=lmax, num_layers=nlayers), alg)
-    out = {}
+    out, stats = {}, {}
     for mode in ("fused", "tiled"):
         pair = PairAllegroB200(device=0, debug_mode=False)
         pair.coeff(["*", "*", alg, "Ag"], 1)
@@ -73,7 +73,11 @@ def test_fused_equals_tiled(lmax, nlayers, ensure_built, tmp_path):
             runs.append((atoms.f.copy(), pair.eatom[:atoms.nlocal].copy(), pair.virial.copy(), pair.eng_vdwl))
         assert np.array_equal(runs[0][0], runs[1][0]) and np.array_equal(runs[0][1], runs[1][1]) and runs[0][3] == runs[1][3]
         out[mode] = runs[0]
+        stats[mode] = pair.handle.stats("step", 4)
         assert pair.handle.stats("pipeline", 3)[0] == (1 if mode == "fused" else 0)
+    # batch plan: centre-aligned batches of edge-aligned tiles waste at most one tile per batch
+    E, nbatch, ntile = (int(v) for v in stats["fused"][1:4])
+    assert (E + 127) // 128 <= ntile <= (E + 127) // 128 + nbatch and 1 <= nbatch <= ntile
     assert np.abs(out["fused"][0] - out["tiled"][0]).max() < 2e-5
     np.testing.assert_allclose(out["fused"][1], out["tiled"][1], rtol=2e-6, atol=2e-6)
     assert np.abs(out["fused"][2] - out["tiled"][2]).max() < 1e-5 * max(1.0, np.abs(out["tiled"][2]).max())
