@@ -82,10 +82,9 @@ ALG_API int alg_set_type_map(alg_handle* h, int ntypes, const int* lammps_type_t
  *                  into centre-aligned batches of fused_batch*128 edges, a CTA runs a batch through all phases and
  *                  combines the per-atom sums itself; inter-phase state in CTA-private scratch; no host synchronisation,
  *                  no fix-up launches.  Needs <= fused_batch*128 neighbours inside the cutoff per atom.  tiled = the
- *                  chunked edge-tile pipeline (any neighbour count; one host synchronisation per step on the CSR row
- *                  pointer, one kernel per phase and chunk).  auto = fused for l_max = 1 models -- tiled from the first step on
- *                  that meets an atom with more neighbours than a batch holds (that step is repeated transparently) or
- *                  when debug=1 -- and tiled for l_max >= 2, where the per-phase kernels are measured faster.
+ *                  chunked edge-tile pipeline (any neighbour count; one kernel per phase and chunk, fix-up kernels
+ *                  between them; see chunk_plan).  auto = tiled: measured 4 % (l_max 1) to 50 % (l_max 3) faster on
+ *                  the B200, and with the device-built chunk plan just as free of host synchronisation.
  *   "fused_batch"  fused pipeline: 128-edge tiles per batch (default 8).  A CTA runs the tiles of a batch phase by phase, so
  *                  the code of one phase stays in the instruction cache for the whole batch
  *   "phase_align"  fused pipeline: "1" (default) keeps the CTAs that share an SM in the same phase (bounded wait at every phase
@@ -99,6 +98,10 @@ ALG_API int alg_set_type_map(alg_handle* h, int ntypes, const int* lammps_type_t
  *                  so that the per-step copies are asynchronous DMA.  Switch off when the caller frees and
  *                  re-allocates these arrays between calls.
  *   "chunk_edges"  tiled pipeline: edges processed per pipeline pass (activation buffers are sized by this)
+ *   "chunk_plan"   tiled pipeline: "device" (default) builds the centre-aligned chunk plan on the device -- no host
+ *                  synchronisation; grids and launch counts are sized by the capacity of the edge arrays, surplus CTAs and
+ *                  launches exit at once -- | "host" copies the CSR row pointer to the host every step (round-1 behaviour;
+ *                  also used with debug=1 and after a step whose chunks did not fit the device plan's buffers)
  *   "keep_edges"   "1": materialise the int64 [2,E] edge_index for alg_get_edges
  *   "debug"        "1": keep per-edge gradients / intermediates for alg_get_output
  *   "profile"      "1": time every pipeline kernel with CUDA events (alg_get_stats)
@@ -171,7 +174,8 @@ ALG_API int alg_get_timings(alg_handle* h, double* ms3);
 /* Counters of the last compute (doubles): what = "step" -> [own kernel launches, edges, chunks,
  * tiles]; with option profile=1 also "kernel_ms" / "kernel_launches" -> per kernel family
  * [F0, FK, T, BK, B0, fixup, fused] summed CUDA-event durations (ms) and launch counts; "pipeline" -> [1 if the
- * last step ran the fused kernel, CTAs in the fused grid, 1 once the tiled fallback became sticky]. */
+ * last step ran the fused kernel, CTAs in the fused grid, 1 once the tiled fallback became sticky, 1 if the last chunked
+ * step used the device-built plan]. */
 ALG_API int alg_get_stats(alg_handle* h, const char* what, double* out, int n);
 
 /* ---- ghost halo exchange of spatial-domain multi-GPU runs (one rank per GPU) -------------------------------------------

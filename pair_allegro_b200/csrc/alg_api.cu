@@ -108,7 +108,9 @@ struct alg_handle {
   long edge_cap_hint = 0;                  // upper bound on the edge count known to the caller path (0 = unknown)
   long max_neighbors = 0;                  // option max_neighbors: extent(1) of the caller's 2-D neighbour view
   long last_E_known = -1; int last_E_nlocal = -1;
-  DevBuf d_blk, d_blk_base, d_tile_c0, d_info, d_sm_phase;
+  DevBuf d_blk, d_blk_base, d_tile_c0, d_info, d_sm_phase, d_cplan;
+  bool tiled_plan_device = true;           // option chunk_plan: device (default) | host
+  bool tiled_sync = false;                 // sticky: the device-built chunk plan did not fit the buffers -> host-built plan (one sync per step)
   int num_sms = 148;
   bool phase_align = true;                 // option phase_align
   // deferred verification of asynchronous steps: a ring of pinned info records, one event each, so that the host may run
@@ -117,9 +119,10 @@ struct alg_handle {
   PinBuf h_info;                           // INFO_RING x 16 ints; slot 0 doubles as the record of synchronous steps
   cudaEvent_t ev_info[INFO_RING] = {nullptr, nullptr, nullptr, nullptr};
   bool info_used[INFO_RING] = {false, false, false, false};
-  bool info_fused[INFO_RING] = {false, false, false, false};
+  int info_mode[INFO_RING] = {0, 0, 0, 0};  // 0 = host-planned chunked step, 1 = fused, 2 = device-planned chunked step
   unsigned info_head = 0, info_tail = 0;   // pending slots: [tail, head)
   bool last_fused = false;
+  int last_mode = 0;                       // 0 host-planned chunked, 1 fused, 2 device-planned chunked
   std::string deferred_err;                // failure of an asynchronous step, reported by the next call
   std::pair<const void*, size_t> reg[3] = {{nullptr, 0}, {nullptr, 0}, {nullptr, 0}};   // caller arrays (x, f, type) pinned with cudaHostRegister
   bool host_register = true;               // option host_register
@@ -366,6 +369,30 @@ __global__ void k_mtype(int ntot, const int* __restrict__ type, const int* __res
 }
 
 // finalize: fixed-point accumulators -> model forces (double), optionally f += ; per-atom energies
+// Chunk plan of the chunked pipeline, built on the device (the round-1 version copied the row pointer to the host and
+// blocked on it every step -- the same mid-step synchronisation as the reference's edge count, kokkos.cpp:203-206).
+// Chunk i = the centres whose row STARTS in [i*Q, (i+1)*Q): boundaries by binary search, one thread per chunk.
+// plan[3i..3i+2] = {e0, e1, c0}; chunks behind the last edge are empty (e0 == e1).  info[2] = E, info[3] |= capacity
+// overflow, info[9] = 1 when a chunk exceeds the buffers (max_edges edges or max_cent centres).
+__global__ void k_chunk_plan(int nlocal, const int* __restrict__ rowptr, long Q, int nch_max, int max_edges, int max_cent, long cap,
+                             int* __restrict__ plan, int* __restrict__ info) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nch_max) return;
+  const long E = rowptr[nlocal];
+  auto lb = [&](long v) {                           // first centre c in [0, nlocal] with rowptr[c] >= v
+    int lo = 0, hi = nlocal;
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if (rowptr[mid] < v) lo = mid + 1; else hi = mid; }
+    return lo;
+  };
+  const int ca = (long)i * Q >= E ? nlocal : lb((long)i * Q);
+  const int cb = (long)(i + 1) * Q >= E ? nlocal : lb((long)(i + 1) * Q);
+  int e0 = rowptr[ca], e1 = rowptr[cb];
+  if (e1 - e0 > max_edges || (e1 > e0 && cb - ca > max_cent)) { info[9] = 1; e1 = e0; }   // does not fit the buffers: no work, the host repeats the step
+  if (E > cap) e1 = e0;                                                                  // edge arrays too small (info[3]): no work either
+  plan[3 * i] = e0; plan[3 * i + 1] = e1; plan[3 * i + 2] = ca;
+  if (i == 0) { info[2] = (int)E; info[0] = (int)((E + Q - 1) / Q); if (E > cap) info[3] = 1; }
+}
+
 // Thread-per-atom variant of K1 for the KOKKOS device layout (LayoutLeft: d_neighbors(i,jj) at base[i + jj*stride_jj]): the
 // lanes of a warp are consecutive atoms, so every step of the jj loop is one coalesced read (the warp-per-atom kernel
 // above would touch 32 different lines per step).  Same filter, same (ilist, jlist) order.
@@ -403,12 +430,12 @@ __global__ void k_edges_tpa(int nlocal, const double* __restrict__ x, const int*
   if (!FILL) cnt_out[ii] = total;
 }
 
-// info != nullptr (fused pipeline): a step the fused kernel refused (info[1] > rows or info[3]) must not touch f; the host repeats it
+// info != nullptr (device-built plans): a step the pipeline refused (info[1] > rows, info[3] or info[9]) must not touch f; the host repeats it
 __global__ void k_forces(int ntot, const unsigned long long* __restrict__ facc, double* __restrict__ forces, double* __restrict__ f_inout,
                          const int* __restrict__ info, int rows) {
   const long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
   if (i >= 3L * ntot) return;
-  if (info && (info[1] > rows || info[3] != 0)) return;
+  if (info && (info[1] > rows || info[3] != 0 || info[9] != 0)) return;
   const double v = (double)(long long)facc[i] * FIX_INV;
   forces[i] = v;
   if (f_inout) f_inout[i] += v;
@@ -704,7 +731,7 @@ extern "C" void alg_destroy(alg_handle* h) {
   if (h->copy_stream) { cudaStreamSynchronize(h->copy_stream); cudaStreamDestroy(h->copy_stream); }
   for (auto& r : h->reg) if (r.first) { cudaHostUnregister(const_cast<void*>(r.first)); cudaGetLastError(); }
   for (cudaEvent_t e : {h->ev_info[0], h->ev_info[1], h->ev_info[2], h->ev_info[3], h->ev_copy, h->ev_order}) if (e) cudaEventDestroy(e);
-  h->d_sm_phase.release(); h->d_blk.release(); h->d_blk_base.release(); h->d_tile_c0.release(); h->d_info.release(); h->d_f_stage.release();
+  h->d_cplan.release(); h->d_sm_phase.release(); h->d_blk.release(); h->d_blk_base.release(); h->d_tile_c0.release(); h->d_info.release(); h->d_f_stage.release();
   h->h_info.release(); h->h_eatom.release();
   DevBuf* bufs[] = {&h->weights, &h->d_tmap, &h->d_cutsq, &h->d_scale, &h->d_shift, &h->d_x, &h->d_type, &h->d_ilist, &h->d_numneigh,
                     &h->d_cand, &h->d_first, &h->d_cnt, &h->d_rowptr, &h->d_scan_tmp, &h->d_mtype, &h->d_edge_j, &h->d_edge_c, &h->d_rvec,
@@ -777,6 +804,9 @@ extern "C" int alg_set_option(alg_handle* h, const char* key, const char* value)
     const int b = atoi(v.c_str());
     if (b < 1 || b > 64) return fail(h, ALG_EINVAL, "fused_batch must be in 1..64");
     h->fused_batch = b;
+  } else if (k == "chunk_plan") {
+    if (v == "device") h->tiled_plan_device = true; else if (v == "host") h->tiled_plan_device = false;
+    else return fail(h, ALG_EINVAL, "chunk_plan must be device or host");
   } else if (k == "phase_align") {
     h->phase_align = v != "0";
   } else if (k == "max_neighbors") {
@@ -942,6 +972,42 @@ static int step_tiled(alg_handle* h, const StepIO& io) {
   return ALG_OK;
 }
 
+// ---- chunked pipeline with the device-built plan: no host synchronisation.  The grids cover the largest possible chunk
+// and the number of launches the largest possible edge count (`cap`); CTAs / launches beyond the real plan exit at once.
+constexpr int CHUNK_SLACK = 4096;                    // a chunk may exceed Q by the neighbour count of one atom
+static int step_tiled_async(alg_handle* h, const StepIO& io, long cap) {
+  cudaStream_t st = h->stream;
+  const int nlocal = io.nlocal;
+  const PipelineInfo& pi = h->pinfo;
+  const int TM = pi.TM;
+  int rc = ensure_edge_arrays(h, cap);
+  if (rc != ALG_OK) return rc;
+  const long Q = std::max<long>(h->chunk_edges, 4 * TM);
+  const int nch_max = (int)((cap + Q - 1) / Q);
+  const int max_edges = (int)Q + CHUNK_SLACK;
+  const long max_tiles = (max_edges + TM - 1) / TM;
+  const long max_cent = std::min<long>(std::max<long>(Q / 4, 1024), nlocal);
+  CK(h->d_cplan.ensure(sizeof(int) * 3 * std::max(nch_max, 1)));
+  k_chunk_plan<<<(nch_max + 127) / 128, 128, 0, st>>>(nlocal, h->d_rowptr.as<int>(), Q, nch_max, max_edges, (int)max_cent, cap,
+                                                      h->d_cplan.as<int>(), h->d_info.as<int>());
+  launch_edge_fill(h, io, cap);
+  CK(cudaGetLastError());
+  CK(cudaEventRecord(h->ev[1], st));
+  rc = ensure_chunk_buffers(h, max_tiles, max_cent);
+  if (rc != ALG_OK) return rc;
+  ChunkArgs a;
+  fill_args(h, io, a);
+  a.plan = h->d_cplan.as<int>();
+  for (int ci = 0; ci < nch_max; ++ci) {
+    a.ci = ci;
+    CK(h->pipe->run_chunk(a, h->mw, &h->tcw, (int)max_tiles, st, &h->prof));
+  }
+  h->prof.launches += 1;                               // k_chunk_plan
+  h->step_stats[2] = (double)nch_max; h->step_stats[3] = -1;
+  h->dbg_ntiles = 0; h->dbg_c0 = 0; h->dbg_ncent = 0;
+  return ALG_OK;
+}
+
 // ---- fused persistent pipeline: no host synchronisation; the tile plan is built on the device
 static int step_fused(alg_handle* h, const StepIO& io, long cap) {
   cudaStream_t st = h->stream;
@@ -996,10 +1062,16 @@ static int resolve_pending(alg_handle* h, bool block = true, unsigned keep = 0) 
     const int* info = h->h_info.as<int>() + 16 * slot;
     if (info[8] != 0)
       return fail(h, ALG_EINVAL, "an earlier asynchronous step met atom " + std::to_string(info[8] - 1) + " whose LAMMPS type has no model type");
-    if (!h->info_fused[slot]) continue;
+    if (h->info_mode[slot] == 0) continue;
     h->last_E = info[2]; h->last_E_known = info[2];
-    h->step_stats[1] = info[2]; h->step_stats[2] = info[0]; h->step_stats[3] = info[6];
-    if (info[1] > h->fused_batch * 128) {
+    h->step_stats[1] = info[2]; h->step_stats[2] = info[0]; h->step_stats[3] = h->info_mode[slot] == 1 ? info[6] : (info[2] + 127) / 128;
+    if (info[9]) {
+      h->tiled_sync = true;
+      return fail(h, ALG_ESTATE, "an earlier asynchronous alg_compute_device step needed a chunk larger than its buffers (an atom with more than 4096 "
+                                 "neighbours, or fewer than 4 neighbours per atom on average) and produced no forces; the host-built chunk plan "
+                                 "is selected from now on");
+    }
+    if (h->info_mode[slot] == 1 && info[1] > h->fused_batch * 128) {
       h->force_tiled = true;
       return fail(h, ALG_ESTATE, "an earlier asynchronous alg_compute_device step met an atom with more than fused_batch*128 neighbours inside the cutoff "
                                  "and produced no forces; the chunked pipeline is selected from now on (pass eng != NULL to have such steps "
@@ -1014,12 +1086,12 @@ static int resolve_pending(alg_handle* h, bool block = true, unsigned keep = 0) 
 static bool fused_selected(const alg_handle* h) {
   if (h->pipeline_mode == 2 || !h->use_tc || !h->pipe || !h->pipe->run_fused || h->fused_grid <= 0) return false;
   if (h->pipeline_mode == 1) return true;
-  // auto: the fused kernel where it is the faster one.  Measured on the B200 (bench.py, strict fp32): l_max = 1 fused and
-  // chunked pipeline are within 4 % of each other (and only the fused one is asynchronous); for l_max >= 2 the per-phase
-  // kernels of the chunked pipeline are 1.25x (l_max = 2) / 1.5x (l_max = 3) faster -- the tensor-product code of those
-  // models is register-bound and ptxas allocates a stand-alone phase kernel better than the same phase inlined into the
-  // persistent kernel.  Per-stage intermediates (debug=1) exist only in the chunked pipeline.
-  return h->L == 1 && !h->force_tiled && !h->debug;
+  // auto: the faster pipeline as measured on the B200 (bench.py, strict fp32) -- the chunked per-phase kernels: 4 % faster
+  // for l_max = 1, 1.25x for l_max = 2, 1.5x for l_max = 3 (the persistent kernel streams the code of all phases through
+  // the instruction cache and ptxas allocates a stand-alone phase kernel better than the same phase inlined into one
+  // body).  With the device-built chunk plan (step_tiled_async) neither pipeline synchronises with the host, so the
+  // fused kernel's remaining advantage is the launch count (10 vs ~600 per step); it stays selectable (pipeline=fused).
+  return false;
 }
 
 static int run_step(alg_handle* h, const StepIO& io, double* eng, double* virial6) {
@@ -1062,12 +1134,16 @@ static int run_step(alg_handle* h, const StepIO& io, double* eng, double* virial
   CK(h->h_info.ensure(sizeof(int) * 16 * alg_handle::INFO_RING));
   bool fused = fused_selected(h);
   long cap = 0;
+  // chunked pipeline: device-built chunk plan (no host synchronisation) unless intermediates are wanted (debug=1 needs the
+  // host-side chunk bookkeeping) or an earlier step showed that the plan does not fit the buffers
+  auto tiled_async = [&] { return !fused && !h->debug && !h->tiled_sync && h->tiled_plan_device; };
   for (int attempt = 0;; ++attempt) {
     CK(cudaMemsetAsync(h->d_esum.p, 0, sizeof(double) * nlocal, st));
     CK(cudaMemsetAsync(h->d_facc.p, 0, sizeof(unsigned long long) * 3 * ntot, st));
     CK(cudaMemsetAsync(h->d_vacc.p, 0, sizeof(unsigned long long) * 8, st));
     h->prof.reset();
-    if (fused) {
+    const bool tasync = tiled_async();
+    if (fused || tasync) {
       if (cap == 0) {
         if (io.cap_hint > 0) cap = io.cap_hint;
         else if (h->last_E_known >= 0 && h->last_E_nlocal == nlocal) cap = h->last_E_known + h->last_E_known / 8 + 4096;
@@ -1080,19 +1156,21 @@ static int run_step(alg_handle* h, const StepIO& io, double* eng, double* virial
         }
         h->last_E_nlocal = nlocal;
       }
-      rc = step_fused(h, io, cap);
+      rc = fused ? step_fused(h, io, cap) : step_tiled_async(h, io, cap);
     } else {
       rc = step_tiled(h, io);
     }
     if (rc != ALG_OK) return rc;
     h->last_fused = fused;
+    const int mode = fused ? 1 : (tasync ? 2 : 0);
+    h->last_mode = mode;
     // own kernels outside the pipeline: k_mtype, k_edges x2, [k_edge_index], 4 finalize kernels
     h->step_stats[0] = (double)h->prof.launches + 3 + (h->keep_edges ? 1 : 0) + 4;
     CK(cudaEventRecord(h->ev[2], st));
     // ---- finalize
     if (io.wait_f) CK(cudaStreamWaitEvent(st, io.wait_f, 0));
     k_forces<<<(unsigned)((3L * ntot + 255) / 256), 256, 0, st>>>(ntot, h->d_facc.as<unsigned long long>(), h->d_forces.as<double>(), io.d_f_inout,
-                                                                  fused ? h->d_info.as<int>() : nullptr, h->fused_batch * 128);
+                                                                  mode ? h->d_info.as<int>() : nullptr, fused ? h->fused_batch * 128 : 0x7fffffff);
     k_eall_ghost<<<(ntot + 255) / 256, 256, 0, st>>>(ntot, h->d_mtype.as<int>(), h->d_shift.as<double>(), h->d_eall.as<double>());
     k_eall_local<<<eblocks, 256, 0, st>>>(nlocal, io.d_ilist, h->d_mtype.as<int>(), h->d_esum.as<double>(), h->d_scale.as<double>(),
                                           h->d_shift.as<double>(), 1.0 / std::sqrt(h->avg_n), h->d_eall.as<double>(),
@@ -1104,9 +1182,9 @@ static int run_step(alg_handle* h, const StepIO& io, double* eng, double* virial
       const int slot = (int)(h->info_head % alg_handle::INFO_RING);
       CK(cudaMemcpyAsync(h->h_info.as<int>() + 16 * slot, h->d_info.p, sizeof(int) * 16, cudaMemcpyDeviceToHost, st));
       CK(cudaEventRecord(h->ev_info[slot], st));
-      h->info_fused[slot] = fused;
+      h->info_mode[slot] = mode;
       ++h->info_head;
-      if (fused) { h->step_stats[1] = -1; h->step_stats[2] = 1; h->step_stats[3] = -1; }
+      if (mode) { h->step_stats[1] = -1; h->step_stats[3] = -1; }
       return ALG_OK;
     }
     CK(cudaMemcpyAsync(h->h_info.p, h->d_info.p, sizeof(int) * 16, cudaMemcpyDeviceToHost, st));
@@ -1117,11 +1195,15 @@ static int run_step(alg_handle* h, const StepIO& io, double* eng, double* virial
     if (h->h_info.as<int>()[8] != 0)
       return fail(h, ALG_EINVAL, "atom " + std::to_string(h->h_info.as<int>()[8] - 1) + " has a LAMMPS type that has no model type "
                                  "(its name in pair_coeff matches no type name of the model)");
-    if (fused) {
+    if (mode) {
       const int* info = h->h_info.as<int>();
       h->last_E = info[2]; h->last_E_known = info[2];
-      h->step_stats[1] = info[2]; h->step_stats[2] = info[0]; h->step_stats[3] = info[6];
-      if (info[1] > h->fused_batch * 128) {              // an atom with more neighbours than a batch holds: chunked pipeline from now on
+      h->step_stats[1] = info[2]; h->step_stats[2] = info[0]; h->step_stats[3] = fused ? info[6] : (info[2] + 127) / 128;
+      if (info[9]) {                                     // a chunk of the device-built plan does not fit the buffers: host-built plan from now on
+        h->tiled_sync = true;
+        continue;
+      }
+      if (fused && info[1] > h->fused_batch * 128) {     // an atom with more neighbours than a batch holds: chunked pipeline from now on
         if (h->pipeline_mode == 1) return fail(h, ALG_EINVAL, "pipeline=fused: an atom has more than fused_batch*128 neighbours inside the cutoff");
         h->force_tiled = true; fused = false;
         continue;
@@ -1403,8 +1485,8 @@ extern "C" int alg_get_stats(alg_handle* h, const char* what, double* out, int n
   else if (k == "step") { src = h->step_stats; m = 4; }
   else if (k == "list_reused") { if (n > 0) out[0] = h->list_reused; return ALG_OK; }
   else if (k == "pipeline") {                       // [1 if the last step ran the fused kernel, CTAs of the fused grid, sticky tiled fallback]
-    const double v[3] = {h->last_fused ? 1.0 : 0.0, (double)h->fused_grid, h->force_tiled ? 1.0 : 0.0};
-    for (int i = 0; i < n && i < 3; ++i) out[i] = v[i];
+    const double v[4] = {h->last_fused ? 1.0 : 0.0, (double)h->fused_grid, h->force_tiled ? 1.0 : 0.0, h->last_mode == 2 ? 1.0 : 0.0};
+    for (int i = 0; i < n && i < 4; ++i) out[i] = v[i];
     return ALG_OK;
   }
   else return fail(h, ALG_ENOTFOUND, "unknown stats group " + k);

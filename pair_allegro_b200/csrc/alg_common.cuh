@@ -76,8 +76,11 @@ struct ChunkArgs {
   const int* edge_c;    // [E] centre slot ii
   const int* rowptr;    // [nlocal+1]
   const int* ilist;     // [nlocal] centre slot -> atom index
-  // chunk
+  // chunk: edge range [e0, e1) and first centre slot c0 -- by value (host-built plan), or read from the device-built plan
+  // entry plan[3*ci .. 3*ci+2] when `plan` is set (no host synchronisation; see k_chunk_plan in alg_api.cu)
   int e0, e1, c0;
+  const int* plan;
+  int ci;
   float* X[3];          // x^k, k = 0..nl-1     [tile][S][TM]
   float* W0;            // embed weights w0 / later dw0  [tile][ENVW][TM]
   float* V[3];          // V^k, k = 1..nl-1     [tile][U][DIM_k][TM]
@@ -96,6 +99,12 @@ struct ChunkArgs {
   unsigned long long* facc;   // [ntot][3] fixed-point force accumulators
   unsigned long long* vacc;   // [6] fixed-point virial accumulators
 };
+
+struct ChunkBounds { int e0, e1, c0; };
+__device__ __forceinline__ ChunkBounds chunk_bounds(const ChunkArgs& a) {
+  if (a.plan) return ChunkBounds{a.plan[3 * a.ci], a.plan[3 * a.ci + 1], a.plan[3 * a.ci + 2]};
+  return ChunkBounds{a.e0, a.e1, a.c0};
+}
 
 // ------------------------------------------------------------------------------------------
 // sigmoid via the SFU: ex2.approx (2 ulp) + rcp.approx (1 ulp); absolute error of s <~ 2e-7,

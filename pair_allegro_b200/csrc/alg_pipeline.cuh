@@ -92,7 +92,7 @@ template <int L> cudaError_t run_chunk_impl(const ChunkArgs& a, const ModelW& w,
   const dim3 g(ntiles), b(NT);
 #define ALG_RUN(kid, ...) do { pf->begin(kid, st); __VA_ARGS__; pf->end(st); } while (0)
   auto fix = [&](float* out) {
-    ALG_RUN(KID_FIXUP, (k_fixup<TM><<<g, 128, 0, st>>>(a.edge_c, a.rowptr, a.e0, a.e1, a.c0, ntiles, D::F, out, a.carry)));
+    ALG_RUN(KID_FIXUP, (k_fixup<TM><<<g, 128, 0, st>>>(a.edge_c, a.rowptr, a.e0, a.e1, a.c0, ntiles, D::F, out, a.carry, a.plan, a.ci)));
   };
   ALG_RUN(KID_F0, (k_f0<L><<<g, b, sm, st>>>(a, w)));
   fix(a.gamma[0]);
@@ -111,7 +111,7 @@ template <int L> cudaError_t run_chunk_impl(const ChunkArgs& a, const ModelW& w,
     ALG_RUN(KID_T, (k_t<L, false><<<g, b, sm, st>>>(a, w, 2)));
   }
   fix(a.dgamma[nl - 1]);
-  ALG_RUN(KID_FIXUP, (k_fixup_e<TM><<<(ntiles + 127) / 128, 128, 0, st>>>(a.edge_c, a.rowptr, a.e0, a.e1, ntiles, a.esum, a.ecarry)));
+  ALG_RUN(KID_FIXUP, (k_fixup_e<TM><<<(ntiles + 127) / 128, 128, 0, st>>>(a.edge_c, a.rowptr, a.e0, a.e1, ntiles, a.esum, a.ecarry, a.plan, a.ci)));
   if (nl == 2) {
     ALG_RUN(KID_BK, (k_bk<L, 'B', true><<<g, b, sm, st>>>(a, w, 0)));
     fix(a.dgamma[0]);
@@ -181,40 +181,42 @@ template <int L> cudaError_t run_chunk_tc_impl(const ChunkArgs& a, const ModelW&
   using D = DimsTC<L>;
   constexpr int TM = D::TM;
   const size_t sm = SmemTC<L>::BYTES;
-  const dim3 g(ntiles), b(NT);
+  // the phase kernels are persistent over the tiles of the chunk: one wave of resident CTAs (2 per SM; 1 for l_max = 3)
+  static const int resident = fused_grid_tc_impl<L>(0);
+  const dim3 g(ntiles), b(NT), gp(resident > 0 && resident < ntiles ? resident : ntiles), gf(ntiles < 2368 ? ntiles : 2368);
   const TcW& tw = *twp;
 #define ALG_RUN(kid, ...) do { pf->begin(kid, st); __VA_ARGS__; pf->end(st); } while (0)
   auto fix = [&](float* out) {
-    ALG_RUN(KID_FIXUP, (k_fixup<TM><<<g, 128, 0, st>>>(a.edge_c, a.rowptr, a.e0, a.e1, a.c0, ntiles, D::F, out, a.carry)));
+    ALG_RUN(KID_FIXUP, (k_fixup<TM><<<gf, 128, 0, st>>>(a.edge_c, a.rowptr, a.e0, a.e1, a.c0, ntiles, D::F, out, a.carry, a.plan, a.ci)));
   };
-  ALG_RUN(KID_F0, (k_f0_tc<L><<<g, b, sm, st>>>(a, w, tw)));
+  ALG_RUN(KID_F0, (k_f0_tc<L><<<gp, b, sm, st>>>(a, w, tw)));
   fix(a.gamma[0]);
   const int nl = w.nl;
   if (nl == 1) {
-    ALG_RUN(KID_T, (k_t_tc<L, true><<<g, b, sm, st>>>(a, w, tw, 0)));
+    ALG_RUN(KID_T, (k_t_tc<L, true><<<gp, b, sm, st>>>(a, w, tw, 0)));
   } else if (nl == 2) {
-    ALG_RUN(KID_FK, (k_fk_tc<L, 'B', true><<<g, b, sm, st>>>(a, w, tw, 0)));
+    ALG_RUN(KID_FK, (k_fk_tc<L, 'B', true><<<gp, b, sm, st>>>(a, w, tw, 0)));
     fix(a.gamma[1]);
-    ALG_RUN(KID_T, (k_t_tc<L, false><<<g, b, sm, st>>>(a, w, tw, 1)));
+    ALG_RUN(KID_T, (k_t_tc<L, false><<<gp, b, sm, st>>>(a, w, tw, 1)));
   } else {
-    ALG_RUN(KID_FK, (k_fk_tc<L, 'C', true><<<g, b, sm, st>>>(a, w, tw, 0)));
+    ALG_RUN(KID_FK, (k_fk_tc<L, 'C', true><<<gp, b, sm, st>>>(a, w, tw, 0)));
     fix(a.gamma[1]);
-    ALG_RUN(KID_FK, (k_fk_tc<L, 'D', false><<<g, b, sm, st>>>(a, w, tw, 1)));
+    ALG_RUN(KID_FK, (k_fk_tc<L, 'D', false><<<gp, b, sm, st>>>(a, w, tw, 1)));
     fix(a.gamma[2]);
-    ALG_RUN(KID_T, (k_t_tc<L, false><<<g, b, sm, st>>>(a, w, tw, 2)));
+    ALG_RUN(KID_T, (k_t_tc<L, false><<<gp, b, sm, st>>>(a, w, tw, 2)));
   }
   fix(a.dgamma[nl - 1]);
-  ALG_RUN(KID_FIXUP, (k_fixup_e<TM><<<(ntiles + 127) / 128, 128, 0, st>>>(a.edge_c, a.rowptr, a.e0, a.e1, ntiles, a.esum, a.ecarry)));
+  ALG_RUN(KID_FIXUP, (k_fixup_e<TM><<<(gf.x + 127) / 128, 128, 0, st>>>(a.edge_c, a.rowptr, a.e0, a.e1, ntiles, a.esum, a.ecarry, a.plan, a.ci)));
   if (nl == 2) {
-    ALG_RUN(KID_BK, (k_bk_tc<L, 'B', true><<<g, b, sm, st>>>(a, w, tw, 0)));
+    ALG_RUN(KID_BK, (k_bk_tc<L, 'B', true><<<gp, b, sm, st>>>(a, w, tw, 0)));
     fix(a.dgamma[0]);
   } else if (nl == 3) {
-    ALG_RUN(KID_BK, (k_bk_tc<L, 'D', false><<<g, b, sm, st>>>(a, w, tw, 1)));
+    ALG_RUN(KID_BK, (k_bk_tc<L, 'D', false><<<gp, b, sm, st>>>(a, w, tw, 1)));
     fix(a.dgamma[1]);
-    ALG_RUN(KID_BK, (k_bk_tc<L, 'C', true><<<g, b, sm, st>>>(a, w, tw, 0)));
+    ALG_RUN(KID_BK, (k_bk_tc<L, 'C', true><<<gp, b, sm, st>>>(a, w, tw, 0)));
     fix(a.dgamma[0]);
   }
-  ALG_RUN(KID_B0, (k_b0_tc<L><<<g, b, sm, st>>>(a, w, tw)));
+  ALG_RUN(KID_B0, (k_b0_tc<L><<<gp, b, sm, st>>>(a, w, tw)));
 #undef ALG_RUN
   return cudaGetLastError();
 }

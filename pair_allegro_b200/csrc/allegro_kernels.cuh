@@ -89,7 +89,7 @@ template <int L> __device__ __forceinline__ void env_sum(const ChunkArgs& a, con
   segsum_items<D::F, TM>(c_s, seg,
       [&](int e, int f) { const int lm = f / U, u = f % U; return W_s[e * D::WS + lsel(lm) * U + u] * Y_s[lm * TM + e]; },
       [&](int centre, int f, bool first, float v) {
-        if (first && contin) carry[f] = v * sc; else gamma[(size_t)(centre - a.c0) * D::F + f] = v * sc;
+        if (first && contin) carry[f] = v * sc; else gamma[(size_t)(centre - chunk_bounds(a).c0) * D::F + f] = v * sc;
       });
   (void)nvalid;
 }
@@ -106,8 +106,10 @@ __global__ void __launch_bounds__(NT, Dims<L>::MINB) k_f0(const __grid_constant_
   using D = Dims<L>; using SM = Smem<L>; constexpr int TM = D::TM;
   extern __shared__ __align__(16) float sm[];
   const int t = threadIdx.x, tile = blockIdx.x;
-  const int es = a.e0 + tile * TM;
-  const int nvalid = min(TM, a.e1 - es);
+  const ChunkBounds cb = chunk_bounds(a);
+  const int es = cb.e0 + tile * TM;
+  if (es >= cb.e1) return;
+  const int nvalid = min(TM, cb.e1 - es);
   float* IN = sm + SM::oIN; float* A = sm + SM::oA; float* B = sm + SM::oB; float* C = sm + SM::oC; float* Dd = sm + SM::oD;
   const float* u_s = sm + SM::oU;
   const int* zz_s = reinterpret_cast<const int*>(sm + SM::oMisc) + TM;
@@ -181,8 +183,10 @@ __global__ void __launch_bounds__(NT, Dims<L>::MINB) k_fk(const __grid_constant_
   using D = Dims<L>; using SM = Smem<L>; using TP = tpgen::TP<L, KIND>; constexpr int TM = D::TM;
   extern __shared__ __align__(16) float sm[];
   const int t = threadIdx.x, tile = blockIdx.x;
-  const int es = a.e0 + tile * TM;
-  const int nvalid = min(TM, a.e1 - es);
+  const ChunkBounds cb = chunk_bounds(a);
+  const int es = cb.e0 + tile * TM;
+  if (es >= cb.e1) return;
+  const int nvalid = min(TM, cb.e1 - es);
   float* IN = sm + SM::oIN; float* A = sm + SM::oA; float* B = sm + SM::oB; float* C = sm + SM::oC;
   const float* u_s = sm + SM::oU; const float* Y_s = sm + SM::oY;
   const int* c_s = reinterpret_cast<const int*>(sm + SM::oMisc);
@@ -193,7 +197,7 @@ __global__ void __launch_bounds__(NT, Dims<L>::MINB) k_fk(const __grid_constant_
   seg_setup<L>(sm, nvalid);
   {  // tensor product: s -> IN rows S.., V^{k+1} -> global
     const int e = t % TM, uh = t / TM;
-    const float* gam = a.gamma[k] + (size_t)(c_s[e] - a.c0) * D::F;
+    const float* gam = a.gamma[k] + (size_t)(c_s[e] - chunk_bounds(a).c0) * D::F;
     float* Vng = a.V[k + 1] + (size_t)tile * U * TP::DOUT * TM;
 #pragma unroll 1
     for (int i = 0; i < D::CPT; ++i) {
@@ -276,7 +280,7 @@ __device__ __forceinline__ void tp_backward(const ChunkArgs& a, const LayerW& lw
   const float* Y_s = sm + SM::oY;
   const int* c_s = reinterpret_cast<const int*>(sm + SM::oMisc);
   const int e = t % TM, uh = t / TM;
-  const float* gam = a.gamma[k] + (size_t)(c_s[e] - a.c0) * D::F;
+  const float* gam = a.gamma[k] + (size_t)(c_s[e] - chunk_bounds(a).c0) * D::F;
   float* W0g = a.W0 + (size_t)tile * D::ENVW * TM;
   if (FIRST) {
 #pragma unroll
@@ -326,7 +330,7 @@ __device__ __forceinline__ void tp_backward(const ChunkArgs& a, const LayerW& lw
           [&](int centre, int f, bool first, float v) {
             const int lm = f / D::CHU, ul = f % D::CHU;
             const int fg = lm * U + pass * D::CHU + ul;
-            if (first && contin) carry[fg] = v; else dgamma_out[(size_t)(centre - a.c0) * D::F + fg] = v;
+            if (first && contin) carry[fg] = v; else dgamma_out[(size_t)(centre - chunk_bounds(a).c0) * D::F + fg] = v;
           });
     }
     __syncthreads();
@@ -370,7 +374,7 @@ __device__ __forceinline__ void phase2(const ChunkArgs& a, const ModelW& w, int 
   __syncthreads();
   {
     const int e = t % TM, uh = t / TM;
-    const float* dgam = a.dgamma[kk] + (size_t)(c_s[e] - a.c0) * D::F;
+    const float* dgam = a.dgamma[kk] + (size_t)(c_s[e] - chunk_bounds(a).c0) * D::F;
     float dYp[D::NSH];
 #pragma unroll
     for (int lm = 0; lm < D::NSH; ++lm) dYp[lm] = 0.f;
@@ -414,8 +418,10 @@ __global__ void __launch_bounds__(NT, Dims<L>::MINB) k_t(const __grid_constant__
   using D = Dims<L>; using SM = Smem<L>; using TP = tpgen::TP<L, 'A'>; constexpr int TM = D::TM;
   extern __shared__ __align__(16) float sm[];
   const int t = threadIdx.x, tile = blockIdx.x;
-  const int es = a.e0 + tile * TM;
-  const int nvalid = min(TM, a.e1 - es);
+  const ChunkBounds cb = chunk_bounds(a);
+  const int es = cb.e0 + tile * TM;
+  if (es >= cb.e1) return;
+  const int nvalid = min(TM, cb.e1 - es);
   float* IN = sm + SM::oIN; float* A = sm + SM::oA; float* B = sm + SM::oB; float* C = sm + SM::oC; float* Dd = sm + SM::oD;
   const float* u_s = sm + SM::oU; const float* Y_s = sm + SM::oY;
   const int* c_s = reinterpret_cast<const int*>(sm + SM::oMisc);
@@ -428,7 +434,7 @@ __global__ void __launch_bounds__(NT, Dims<L>::MINB) k_t(const __grid_constant__
   seg_setup<L>(sm, nvalid);
   {  // scalar tensor-product outputs s -> IN rows S..
     const int e = t % TM, uh = t / TM;
-    const float* gam = a.gamma[k] + (size_t)(c_s[e] - a.c0) * D::F;
+    const float* gam = a.gamma[k] + (size_t)(c_s[e] - chunk_bounds(a).c0) * D::F;
 #pragma unroll 1
     for (int i = 0; i < D::CPT; ++i) {
       const int u = uh + D::CPH * i;
@@ -516,8 +522,10 @@ __global__ void __launch_bounds__(NT, Dims<L>::MINB) k_bk(const __grid_constant_
   using D = Dims<L>; using SM = Smem<L>; using TP = tpgen::TP<L, KIND>; constexpr int TM = D::TM;
   extern __shared__ __align__(16) float sm[];
   const int t = threadIdx.x, tile = blockIdx.x;
-  const int es = a.e0 + tile * TM;
-  const int nvalid = min(TM, a.e1 - es);
+  const ChunkBounds cb = chunk_bounds(a);
+  const int es = cb.e0 + tile * TM;
+  if (es >= cb.e1) return;
+  const int nvalid = min(TM, cb.e1 - es);
   float* IN = sm + SM::oIN; float* A = sm + SM::oA; float* B = sm + SM::oB; float* C = sm + SM::oC;
   const float* u_s = sm + SM::oU; const float* Y_s = sm + SM::oY; float* DY_s = sm + SM::oDY;
   const int* c_s = reinterpret_cast<const int*>(sm + SM::oMisc);
@@ -532,7 +540,7 @@ __global__ void __launch_bounds__(NT, Dims<L>::MINB) k_bk(const __grid_constant_
   __syncthreads();
   {
     const int e = t % TM, uh = t / TM;
-    const float* gam = a.gamma[k] + (size_t)(c_s[e] - a.c0) * D::F;
+    const float* gam = a.gamma[k] + (size_t)(c_s[e] - chunk_bounds(a).c0) * D::F;
 #pragma unroll 1
     for (int i = 0; i < D::CPT; ++i) {
       const int u = uh + D::CPH * i;
@@ -586,8 +594,10 @@ __global__ void __launch_bounds__(NT, Dims<L>::MINB) k_b0(const __grid_constant_
   using D = Dims<L>; using SM = Smem<L>; constexpr int TM = D::TM;
   extern __shared__ __align__(16) float sm[];
   const int t = threadIdx.x, tile = blockIdx.x;
-  const int es = a.e0 + tile * TM;
-  const int nvalid = min(TM, a.e1 - es);
+  const ChunkBounds cb = chunk_bounds(a);
+  const int es = cb.e0 + tile * TM;
+  if (es >= cb.e1) return;
+  const int nvalid = min(TM, cb.e1 - es);
   float* IN = sm + SM::oIN; float* A = sm + SM::oA; float* B = sm + SM::oB; float* C = sm + SM::oC; float* Dd = sm + SM::oD;
   const float* u_s = sm + SM::oU; float* DY_s = sm + SM::oDY;
   const int* c_s = reinterpret_cast<const int*>(sm + SM::oMisc);
@@ -706,32 +716,35 @@ __global__ void __launch_bounds__(NT, Dims<L>::MINB) k_b0(const __grid_constant_
 // ============================================================================================
 template <int TM>
 __global__ void k_fixup(const int* __restrict__ edge_c, const int* __restrict__ rowptr, int e0, int e1, int c0, int ntiles, int NF,
-                        float* __restrict__ out, const float* __restrict__ carry) {
-  const int tile = blockIdx.x;
-  const int es = e0 + tile * TM;
-  const int ee = min(es + TM, e1);
-  const int c = edge_c[ee - 1];
-  const int rb = rowptr[c], re = rowptr[c + 1];
-  if (rb < es || re <= ee) return;                  // row does not start here, or ends here
-  for (int f = threadIdx.x; f < NF; f += blockDim.x) {
-    float acc = out[(size_t)(c - c0) * NF + f];
-    for (int t2 = tile + 1; t2 < ntiles && e0 + t2 * TM < re; ++t2) acc += carry[(size_t)t2 * NF + f];
-    out[(size_t)(c - c0) * NF + f] = acc;
+                        float* __restrict__ out, const float* __restrict__ carry, const int* __restrict__ plan, int ci) {
+  if (plan) { e0 = plan[3 * ci]; e1 = plan[3 * ci + 1]; c0 = plan[3 * ci + 2]; ntiles = (e1 - e0 + TM - 1) / TM; }
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {     // grid-stride: the grid need not know the tile count
+    const int es = e0 + tile * TM;
+    const int ee = min(es + TM, e1);
+    const int c = edge_c[ee - 1];
+    const int rb = rowptr[c], re = rowptr[c + 1];
+    if (rb < es || re <= ee) continue;              // row does not start here, or ends here
+    for (int f = threadIdx.x; f < NF; f += blockDim.x) {
+      float acc = out[(size_t)(c - c0) * NF + f];
+      for (int t2 = tile + 1; t2 < ntiles && e0 + t2 * TM < re; ++t2) acc += carry[(size_t)t2 * NF + f];
+      out[(size_t)(c - c0) * NF + f] = acc;
+    }
   }
 }
 template <int TM>
 __global__ void k_fixup_e(const int* __restrict__ edge_c, const int* __restrict__ rowptr, int e0, int e1, int ntiles,
-                          double* __restrict__ esum, const double* __restrict__ ecarry) {
-  const int tile = blockIdx.x * blockDim.x + threadIdx.x;
-  if (tile >= ntiles) return;
-  const int es = e0 + tile * TM;
-  const int ee = min(es + TM, e1);
-  const int c = edge_c[ee - 1];
-  const int rb = rowptr[c], re = rowptr[c + 1];
-  if (rb < es || re <= ee) return;
-  double acc = esum[c];
-  for (int t2 = tile + 1; t2 < ntiles && e0 + t2 * TM < re; ++t2) acc += ecarry[t2];
-  esum[c] = acc;
+                          double* __restrict__ esum, const double* __restrict__ ecarry, const int* __restrict__ plan, int ci) {
+  if (plan) { e0 = plan[3 * ci]; e1 = plan[3 * ci + 1]; ntiles = (e1 - e0 + TM - 1) / TM; }
+  for (int tile = blockIdx.x * blockDim.x + threadIdx.x; tile < ntiles; tile += gridDim.x * blockDim.x) {
+    const int es = e0 + tile * TM;
+    const int ee = min(es + TM, e1);
+    const int c = edge_c[ee - 1];
+    const int rb = rowptr[c], re = rowptr[c + 1];
+    if (rb < es || re <= ee) continue;
+    double acc = esum[c];
+    for (int t2 = tile + 1; t2 < ntiles && e0 + t2 * TM < re; ++t2) acc += ecarry[t2];
+    esum[c] = acc;
+  }
 }
 
 }  // namespace alg

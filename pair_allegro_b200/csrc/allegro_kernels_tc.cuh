@@ -1087,17 +1087,26 @@ __device__ __forceinline__ Geom tc_tile_begin(const ChunkArgs& a, const ModelW& 
 }
 template <int L>
 __global__ void __launch_bounds__(NT, DimsTC<L>::MINB) k_f0_tc(const __grid_constant__ ChunkArgs a, const __grid_constant__ ModelW w, const __grid_constant__ TcW tw) {
-  constexpr int TM = 128;
+  using D = DimsTC<L>; constexpr int TM = 128;
   extern __shared__ __align__(1024) float sm_raw[];
-  const int tile = blockIdx.x;
-  const int es = a.e0 + tile * TM;
-  const int nvalid = min(TM, a.e1 - es);
-  const GeomIn gi = tc_geom_load(a, es, nvalid);
+  // persistent over the tiles of the chunk: tile = blockIdx.x, blockIdx.x + gridDim.x, ... (TMEM / mbarriers set up once per CTA)
+  const ChunkBounds cb = chunk_bounds(a);
+  const int ntiles = (cb.e1 - cb.e0 + TM - 1) / TM;
+  if ((int)blockIdx.x >= ntiles) return;               // also: the empty chunks behind the last edge of a device-built plan
   TcCtx c = tc_begin<L>(sm_raw, tw);
-  c.c0 = a.c0;
-  const Geom g = tc_tile_begin<L>(a, w, c, gi, nvalid);
-  f0_body<L>(a, w, tw, c, g, tile, es, nvalid);
+  c.c0 = cb.c0;
+#pragma unroll 1
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int es = cb.e0 + tile * TM;
+    const int nvalid = min(TM, cb.e1 - es);
+    const GeomIn gi = tc_geom_load(a, es, nvalid);
+
+    const Geom g = tc_tile_begin<L>(a, w, c, gi, nvalid);
+    f0_body<L>(a, w, tw, c, g, tile, es, nvalid);
+    __syncthreads();
+  }
   tc_end(c);
+  (void)sizeof(D);
 }
 
 // layer-0 GEMM of a latent MLP: z1 = [x || s] W0 as accumulating K-blocks (s blocks first, then x)
@@ -1154,19 +1163,26 @@ __device__ __forceinline__ void fk_body(const ChunkArgs& a, const ModelW& w, con
 }
 template <int L, char KIND, bool FIRST>
 __global__ void __launch_bounds__(NT, DimsTC<L>::MINB) k_fk_tc(const __grid_constant__ ChunkArgs a, const __grid_constant__ ModelW w, const __grid_constant__ TcW tw, const int k) {
-  constexpr int TM = 128;
+  using D = DimsTC<L>; constexpr int TM = 128;
   extern __shared__ __align__(1024) float sm_raw[];
-  const int tile = blockIdx.x;
-  const int es = a.e0 + tile * TM;
-  const int nvalid = min(TM, a.e1 - es);
-  const GeomIn gi = tc_geom_load(a, es, nvalid);
-  tc_prefetch(a.X[k] + (size_t)tile * S * TM, S * TM);
-  tc_prefetch_row<L>(a.gamma[k], a.c0, gi);
+  // persistent over the tiles of the chunk: tile = blockIdx.x, blockIdx.x + gridDim.x, ... (TMEM / mbarriers set up once per CTA)
+  const ChunkBounds cb = chunk_bounds(a);
+  const int ntiles = (cb.e1 - cb.e0 + TM - 1) / TM;
+  if ((int)blockIdx.x >= ntiles) return;               // also: the empty chunks behind the last edge of a device-built plan
   TcCtx c = tc_begin<L>(sm_raw, tw);
-  c.c0 = a.c0;
-  const Geom g = tc_tile_begin<L>(a, w, c, gi, nvalid);
-  fk_body<L, KIND, FIRST>(a, w, tw, c, g, tile, es, nvalid, k);
+  c.c0 = cb.c0;
+#pragma unroll 1
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int es = cb.e0 + tile * TM;
+    const int nvalid = min(TM, cb.e1 - es);
+    const GeomIn gi = tc_geom_load(a, es, nvalid);
+    fk_prefetch<L>(a, &c, tile, k, gi, cb.c0, 0);
+    const Geom g = tc_tile_begin<L>(a, w, c, gi, nvalid);
+    fk_body<L, KIND, FIRST>(a, w, tw, c, g, tile, es, nvalid, k);
+    __syncthreads();
+  }
   tc_end(c);
+  (void)sizeof(D);
 }
 
 // ============================================================================================
@@ -1264,19 +1280,26 @@ __device__ __forceinline__ void t_body(const ChunkArgs& a, const ModelW& w, cons
 }
 template <int L, bool FIRST>
 __global__ void __launch_bounds__(NT, DimsTC<L>::MINB) k_t_tc(const __grid_constant__ ChunkArgs a, const __grid_constant__ ModelW w, const __grid_constant__ TcW tw, const int k) {
-  constexpr int TM = 128;
+  using D = DimsTC<L>; constexpr int TM = 128;
   extern __shared__ __align__(1024) float sm_raw[];
-  const int tile = blockIdx.x;
-  const int es = a.e0 + tile * TM;
-  const int nvalid = min(TM, a.e1 - es);
-  const GeomIn gi = tc_geom_load(a, es, nvalid);
-  tc_prefetch(a.X[k] + (size_t)tile * S * TM, S * TM);
-  tc_prefetch_row<L>(a.gamma[k], a.c0, gi);
+  // persistent over the tiles of the chunk: tile = blockIdx.x, blockIdx.x + gridDim.x, ... (TMEM / mbarriers set up once per CTA)
+  const ChunkBounds cb = chunk_bounds(a);
+  const int ntiles = (cb.e1 - cb.e0 + TM - 1) / TM;
+  if ((int)blockIdx.x >= ntiles) return;               // also: the empty chunks behind the last edge of a device-built plan
   TcCtx c = tc_begin<L>(sm_raw, tw);
-  c.c0 = a.c0;
-  const Geom g = tc_tile_begin<L>(a, w, c, gi, nvalid);
-  t_body<L, FIRST>(a, w, tw, c, g, tile, es, nvalid, k);
+  c.c0 = cb.c0;
+#pragma unroll 1
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int es = cb.e0 + tile * TM;
+    const int nvalid = min(TM, cb.e1 - es);
+    const GeomIn gi = tc_geom_load(a, es, nvalid);
+    fk_prefetch<L>(a, &c, tile, k, gi, cb.c0, 0);
+    const Geom g = tc_tile_begin<L>(a, w, c, gi, nvalid);
+    t_body<L, FIRST>(a, w, tw, c, g, tile, es, nvalid, k);
+    __syncthreads();
+  }
   tc_end(c);
+  (void)sizeof(D);
 }
 
 // ============================================================================================
@@ -1329,22 +1352,24 @@ template <int L, char KIND, bool FIRST>
 __global__ void __launch_bounds__(NT, DimsTC<L>::MINB) k_bk_tc(const __grid_constant__ ChunkArgs a, const __grid_constant__ ModelW w, const __grid_constant__ TcW tw, const int k) {
   using D = DimsTC<L>; constexpr int TM = 128;
   extern __shared__ __align__(1024) float sm_raw[];
-  const int tile = blockIdx.x;
-  const int es = a.e0 + tile * TM;
-  const int nvalid = min(TM, a.e1 - es);
-  const GeomIn gi = tc_geom_load(a, es, nvalid);
-  tc_prefetch(a.X[k + 1] + (size_t)tile * S * TM, S * TM);
-  tc_prefetch_row<L>(a.dgamma[k + 1], a.c0, gi);
-  tc_prefetch_row<L>(a.gamma[k], a.c0, gi);
-  tc_prefetch(a.dX + (size_t)tile * S * TM, S * TM);
-  tc_prefetch(a.ZD[k + 1] + (size_t)tile * ZD_ROWS * TM, ZD_ROWS * TM);
-  tc_prefetch(a.dY + (size_t)tile * D::NSH * TM, D::NSH * TM);
-  tc_prefetch(a.du + (size_t)tile * TM, TM);
+  // persistent over the tiles of the chunk: tile = blockIdx.x, blockIdx.x + gridDim.x, ... (TMEM / mbarriers set up once per CTA)
+  const ChunkBounds cb = chunk_bounds(a);
+  const int ntiles = (cb.e1 - cb.e0 + TM - 1) / TM;
+  if ((int)blockIdx.x >= ntiles) return;               // also: the empty chunks behind the last edge of a device-built plan
   TcCtx c = tc_begin<L>(sm_raw, tw);
-  c.c0 = a.c0;
-  const Geom g = tc_tile_begin<L>(a, w, c, gi, nvalid);
-  bk_body<L, KIND, FIRST>(a, w, tw, c, g, tile, es, nvalid, k);
+  c.c0 = cb.c0;
+#pragma unroll 1
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int es = cb.e0 + tile * TM;
+    const int nvalid = min(TM, cb.e1 - es);
+    const GeomIn gi = tc_geom_load(a, es, nvalid);
+    bk_prefetch<L>(a, tile, k, gi, cb.c0, 0);
+    const Geom g = tc_tile_begin<L>(a, w, c, gi, nvalid);
+    bk_body<L, KIND, FIRST>(a, w, tw, c, g, tile, es, nvalid, k);
+    __syncthreads();
+  }
   tc_end(c);
+  (void)sizeof(D);
 }
 
 // ============================================================================================
@@ -1476,22 +1501,24 @@ template <int L>
 __global__ void __launch_bounds__(NT, DimsTC<L>::MINB) k_b0_tc(const __grid_constant__ ChunkArgs a, const __grid_constant__ ModelW w, const __grid_constant__ TcW tw) {
   using D = DimsTC<L>; constexpr int TM = 128;
   extern __shared__ __align__(1024) float sm_raw[];
-  const int tile = blockIdx.x;
-  const int es = a.e0 + tile * TM;
-  const int nvalid = min(TM, a.e1 - es);
-  const GeomIn gi = tc_geom_load(a, es, nvalid);
-  tc_prefetch(a.X[0] + (size_t)tile * S * TM, S * TM);
-  tc_prefetch_row<L>(a.dgamma[0], a.c0, gi);
-  tc_prefetch(a.dX + (size_t)tile * S * TM, S * TM);
-  tc_prefetch(a.ZD[0] + (size_t)tile * ZD_ROWS * TM, ZD_ROWS * TM);
-  tc_prefetch(a.W0 + (size_t)tile * D::ENVW * TM, D::ENVW * TM);
-  tc_prefetch(a.dY + (size_t)tile * D::NSH * TM, D::NSH * TM);
-  tc_prefetch(a.du + (size_t)tile * TM, TM);
+  // persistent over the tiles of the chunk: tile = blockIdx.x, blockIdx.x + gridDim.x, ... (TMEM / mbarriers set up once per CTA)
+  const ChunkBounds cb = chunk_bounds(a);
+  const int ntiles = (cb.e1 - cb.e0 + TM - 1) / TM;
+  if ((int)blockIdx.x >= ntiles) return;               // also: the empty chunks behind the last edge of a device-built plan
   TcCtx c = tc_begin<L>(sm_raw, tw);
-  c.c0 = a.c0;
-  const Geom g = tc_tile_begin<L>(a, w, c, gi, nvalid);
-  b0_body<L>(a, w, tw, c, g, tile, es, nvalid);
+  c.c0 = cb.c0;
+#pragma unroll 1
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int es = cb.e0 + tile * TM;
+    const int nvalid = min(TM, cb.e1 - es);
+    const GeomIn gi = tc_geom_load(a, es, nvalid);
+    b0_prefetch<L>(a, tile, gi, cb.c0, 0);
+    const Geom g = tc_tile_begin<L>(a, w, c, gi, nvalid);
+    b0_body<L>(a, w, tw, c, g, tile, es, nvalid);
+    __syncthreads();
+  }
   tc_end(c);
+  (void)sizeof(D);
 }
 
 // ============================================================================================

@@ -65,7 +65,7 @@ def test_stats_and_timings(ensure_built):
     assert int(st[1]) == z["edge_index"].shape[1] and st[2] >= 2 and st[0] > 10      # edges, chunks, own launches
     kms = h.stats("kernel_ms", 6)
     kn = h.stats("kernel_launches", 6)
-    assert kms[:5].min() > 0 and kn[0] == st[2]               # one F0 launch per chunk
+    assert kms[:5].min() > 0 and kn[0] >= st[2]               # one F0 launch per chunk (device-built plan: plus empty ones up to the capacity)
     t = h.timings()
     assert t.min() >= 0 and t[1] > 0
 

@@ -37,6 +37,8 @@ def main():
         pair.handle.set_option("precision", prec)
     pair.handle.set_option("profile", "1")
     pair.handle.set_option("pipeline", pipeline)
+    if os.environ.get("ALG_CHUNK_PLAN"):
+        pair.handle.set_option("chunk_plan", os.environ["ALG_CHUNK_PLAN"])
     if os.environ.get("ALG_FUSED_BATCH"):
         pair.handle.set_option("fused_batch", os.environ["ALG_FUSED_BATCH"])
     for it in range(4):
