@@ -409,7 +409,7 @@ def run_ours(args):
             hh.set_option("fused_batch", str(args.fused_batch))
         return pr
 
-    pair = make_pair(True)
+    pair = make_pair(not args.no_pin)
     h = pair.handle
     # ---- halo: product code (alg_comm_*), NCCL id distributed over the torch.distributed rendezvous
     ident = None
@@ -575,10 +575,13 @@ def run_ours(args):
     #      steps (LAMMPS passes neighbor->ago), x / type / f cross PCIe inside the call every step
     counter = {"i": 0}
 
+    host_ms = []
+
     def step_e2e():
-        atoms.f[:] = 0
+        # (f is not re-zeroed between steps: LAMMPS' force_clear is not part of Pair::compute; the call adds to whatever f holds)
         pair.compute(atoms, lst, eflag=1, vflag=1, eflag_atom=0, neigh_ago=counter["i"] % NEIGH_EVERY)
         counter["i"] += 1
+        host_ms.append(h.stats("host_ms", 3))
 
     for _ in range(2):
         step_e2e()
@@ -586,7 +589,9 @@ def run_ours(args):
     # at least one full neighbour-list cycle, so that the list upload is amortised over NEIGH_EVERY steps as in production MD
     # (steps longer than half a second -- the l_max = 3 box -- keep --steps: the list upload is < 1 % of such a step anyway)
     KE = K if (args.e2e_short or ms / K > 500.0) else ((K + NEIGH_EVERY - 1) // NEIGH_EVERY) * NEIGH_EVERY
+    host_ms.clear()
     ms_e2e = timed(step_e2e, KE)
+    hm = np.array(host_ms)
     e2e_val = total_atoms * KE / (ms_e2e * 1e-3) / 1e6
     list_bytes = 4 * int(lst.numneigh[:nl].sum()) + 16 * nl
     uploads = len([i for i in range(KE) if i % NEIGH_EVERY == 0])
@@ -633,7 +638,9 @@ def run_ours(args):
                 "phase_ms_last_step": {"edge_build": last_ms[0], "network": last_ms[1], "store": last_ms[2]},
                 "e2e": {"value": e2e_val, "unit": "Matom-steps/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                         "ms_per_step": ms_e2e / KE, "steps": KE, "neigh_upload_every": NEIGH_EVERY,
-                        "api": "alg_compute_host (host arrays; x, type, f H2D and f D2H inside the call; neigh_ago = step % 10)"},
+                        "api": "alg_compute_host (host arrays; x, type, f H2D and f D2H inside the call; neigh_ago = step % 10)",
+                        "host_ms_per_call": {"whole_call_mean": float(hm[:, 1].mean()), "list_flatten_upload_on_rebuild_steps": float(hm[:, 0].max()),
+                                             "pinning_mean": float(hm[:, 2].mean())}},
                 "roofline": roofline, "cpu_baseline": cpu, "energy_check": energy_check,
                 "halo_bytes_per_step": int(cst[0] + cst[1])}
         line.update(extra)
@@ -654,6 +661,7 @@ def main():
     ap.add_argument("--scaling", default=None, choices=["weak", "strong"], help="default: weak for c2, strong for c3 / c5")
     ap.add_argument("--chunk-edges", type=int, default=0)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-pin", action="store_true", help="e2e leg: do not let the library pin (cudaHostRegister) the caller's x / f / type arrays")
     ap.add_argument("--no-energy-check", action="store_true", help="N>1 weak scaling: skip the N x single-box energy assertion")
     ap.add_argument("--e2e-short", action="store_true", help="e2e leg: time exactly --steps steps instead of whole neighbour-list cycles (10 steps)")
     ap.add_argument("--gemm", default="tc", choices=["tc", "ffma"])

@@ -175,7 +175,8 @@ ALG_API int alg_get_timings(alg_handle* h, double* ms3);
  * tiles]; with option profile=1 also "kernel_ms" / "kernel_launches" -> per kernel family
  * [F0, FK, T, BK, B0, fixup, fused] summed CUDA-event durations (ms) and launch counts; "pipeline" -> [1 if the
  * last step ran the fused kernel, CTAs in the fused grid, 1 once the tiled fallback became sticky, 1 if the last chunked
- * step used the device-built plan]. */
+ * step used the device-built plan]; "host_ms" -> wall times of the last alg_compute_host call in ms [neighbour-list
+ * flatten + upload issue (0 when the device copy was reused), whole call, pinning of the caller's arrays]. */
 ALG_API int alg_get_stats(alg_handle* h, const char* what, double* out, int n);
 
 /* ---- ghost halo exchange of spatial-domain multi-GPU runs (one rank per GPU) -------------------------------------------

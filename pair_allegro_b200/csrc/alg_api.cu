@@ -4,6 +4,7 @@
 // (compute/preprocess/call) and pair_nequip_allegro_kokkos.cpp:87-353.  No libtorch, no CPU
 // fallback: every failure surfaces as an error code.
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -155,6 +156,7 @@ struct alg_handle {
   double kernel_ms[KID_COUNT] = {0, 0, 0, 0, 0, 0, 0};
   double kernel_n[KID_COUNT] = {0, 0, 0, 0, 0, 0, 0};
   double step_stats[4] = {0, 0, 0, 0};   // launches of own kernels, edges, chunks, tiles
+  double host_ms[3] = {0, 0, 0};          // alg_compute_host wall times of the last call: list flatten + upload issue, whole call, pinning
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   // debug bookkeeping of the last single-chunk run
   int dbg_ntiles = 0, dbg_c0 = 0, dbg_ncent = 0;
@@ -1258,6 +1260,9 @@ extern "C" int alg_compute_host(alg_handle* h, int nlocal, int nghost, const dou
   CK(cudaSetDevice(h->device));
   cudaStream_t st = h->stream;
   const int ntot = nlocal + nghost;
+  const auto t_call = std::chrono::steady_clock::now();
+  auto ms_since = [](std::chrono::steady_clock::time_point t0) { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(); };
+  h->host_ms[0] = 0;
   CK(h->d_x.ensure(sizeof(double) * 3 * ntot));
   CK(h->d_type.ensure(sizeof(int) * ntot));
   CK(h->d_f_stage.ensure(sizeof(double) * 3 * ntot));
@@ -1266,6 +1271,7 @@ extern "C" int alg_compute_host(alg_handle* h, int nlocal, int nghost, const dou
   pin_host(h, 0, x, sizeof(double) * 3 * ntot);
   pin_host(h, 1, f, sizeof(double) * 3 * ntot);
   pin_host(h, 2, type, sizeof(int) * ntot);
+  h->host_ms[2] = ms_since(t_call);
   CK(cudaMemcpyAsync(h->d_x.p, x, sizeof(double) * 3 * ntot, cudaMemcpyHostToDevice, st));
   CK(cudaMemcpyAsync(h->d_type.p, type, sizeof(int) * ntot, cudaMemcpyHostToDevice, st));
   // f travels to the device on a second stream while the network runs; the store kernel adds the model forces to it
@@ -1277,6 +1283,7 @@ extern "C" int alg_compute_host(alg_handle* h, int nlocal, int nghost, const dou
   // counts still match; otherwise the paged list is flattened (ilist order, jlist order) and uploaded
   const bool reuse = h->neigh_ago > 0 && h->list_nlocal == nlocal && h->list_ntot == ntot && h->list_tot >= 0;
   if (!reuse) {
+    const auto t_list = std::chrono::steady_clock::now();
     CK(h->h_first.ensure(sizeof(long long) * (nlocal + 1) + sizeof(int) * nlocal));
     long long* first = h->h_first.as<long long>();
     int* cnt = reinterpret_cast<int*>(first + nlocal + 1);
@@ -1327,6 +1334,7 @@ extern "C" int alg_compute_host(alg_handle* h, int nlocal, int nghost, const dou
       s0 = s1;
     }
     h->list_nlocal = nlocal; h->list_ntot = ntot; h->list_tot = tot;
+    h->host_ms[0] = ms_since(t_list);
   }
   h->list_reused = reuse ? 1 : 0;
   const bool want_eatom = eflag_atom && eatom;
@@ -1349,6 +1357,7 @@ extern "C" int alg_compute_host(alg_handle* h, int nlocal, int nghost, const dou
   if (vflag_global && virial6) for (int q = 0; q < 6; ++q) virial6[q] = vir_l[q];
   auto& vo = h->outputs["virial"];
   vo = {vir_l[0], vir_l[3], vir_l[4], vir_l[3], vir_l[1], vir_l[5], vir_l[4], vir_l[5], vir_l[2]};
+  h->host_ms[1] = ms_since(t_call);
   return ALG_OK;
 }
 
@@ -1483,6 +1492,7 @@ extern "C" int alg_get_stats(alg_handle* h, const char* what, double* out, int n
   if (k == "kernel_ms") { src = h->kernel_ms; m = KID_COUNT; }
   else if (k == "kernel_launches") { src = h->kernel_n; m = KID_COUNT; }
   else if (k == "step") { src = h->step_stats; m = 4; }
+  else if (k == "host_ms") { src = h->host_ms; m = 3; }
   else if (k == "list_reused") { if (n > 0) out[0] = h->list_reused; return ALG_OK; }
   else if (k == "pipeline") {                       // [1 if the last step ran the fused kernel, CTAs of the fused grid, sticky tiled fallback]
     const double v[4] = {h->last_fused ? 1.0 : 0.0, (double)h->fused_grid, h->force_tiled ? 1.0 : 0.0, h->last_mode == 2 ? 1.0 : 0.0};
