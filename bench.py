@@ -543,16 +543,16 @@ def run_ours(args):
         flops_per_launch = fam[names_k[dom]] * E / nlaunch
         gemm_per_launch = gemmf[names_k[dom]] * E / nlaunch
     achieved = flops_per_launch / dur / 1e12
-    traffic = None
+    traffic, tj = None, {}
     tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
-    if os.path.exists(tp):
+    if os.path.exists(tp) and args.config == "c2":          # the committed ncu --set full captures are of the C2 architecture
         try:
             tj = json.load(open(tp))
-            key = "fused_%s" % args.config if fused else names_k[dom]
+            key = "fused_c2" if fused else names_k[dom]
             if key in tj:
                 traffic = tj[key]["dram_bytes_per_edge"] * E / nlaunch
         except Exception:
-            pass
+            tj = {}
     executed_tensor = gemm_per_launch * passes / dur / 1e12
     roofline = {"bound": "tensor", "kernel": dom_name, "achieved": achieved, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
                 "frac": achieved / peaks["bf16_sustained"], "traffic": traffic,
@@ -567,9 +567,18 @@ def run_ours(args):
                          "the contract's peak is the measured dense bf16 figure" % (passes, passes)),
                 "kernel_ms_per_step": {names_k[i]: float(kms[i]) for i in range(NK)},
                 "algorithmic_flops_per_edge_by_phase": {k: float(v) for k, v in fam.items()}}
+    if fused and "fused_c2" in tj:
+        roofline["ncu"] = {k: tj["fused_c2"].get(k) for k in ("tensor_pipe_active_pct", "issue_active_pct", "dram_bytes_per_edge", "source")}
     if not fused:
-        roofline["per_kernel"] = {names_k[i]: {"ms_per_step": float(kms[i]), "algorithmic_tflops": float(fam[names_k[i]] * E / max(kms[i], 1e-9) / 1e9),
-                                               "frac_of_bf16_peak": float(fam[names_k[i]] * E / max(kms[i], 1e-9) / 1e9 / peaks["bf16_sustained"])} for i in range(5)}
+        roofline["per_kernel"] = {}
+        for i in range(5):
+            nm = names_k[i]
+            at = float(fam[nm] * E / max(kms[i], 1e-9) / 1e9)
+            roofline["per_kernel"][nm] = {"ms_per_step": float(kms[i]), "algorithmic_tflops": at, "frac_of_bf16_peak": at / peaks["bf16_sustained"],
+                                          "executed_tensor_tflops": float(gemmf[nm] * passes * E / max(kms[i], 1e-9) / 1e9),
+                                          "ncu_tensor_pipe_active_pct": tj.get(nm, {}).get("tensor_pipe_active_pct"),
+                                          "ncu_issue_active_pct": tj.get(nm, {}).get("issue_active_pct"),
+                                          "ncu_dram_bytes_per_edge": tj.get(nm, {}).get("dram_bytes_per_edge")}
 
     # ---- e2e: the literal plugin call (alg_compute_host) from HOST arrays; the neighbour list is re-uploaded every NEIGH_EVERY
     #      steps (LAMMPS passes neighbor->ago), x / type / f cross PCIe inside the call every step
