@@ -622,6 +622,44 @@ def run_ours(args):
     extra["e2e_device_entry"] = {"value": total_atoms * K / (ms_e2e_dev * 1e-3) / 1e6, "unit": "Matom-steps/s",
                                  "note": "pinned host x -> device, NCCL halo, alg_compute_device (scalars read back), local forces -> pinned host, every step"}
 
+    # a whole neighbour cycle with the list built on the device too (alg_neigh_*): Verlet check + cell-list build on the
+    # first step, then NEIGH_EVERY force evaluations on that list -- nothing of the cycle touches the host
+    nbld = capi.NeighborBuilder(local_rank)
+    d_nb2, d_num2 = torch.zeros_like(d_nb), torch.zeros_like(d_num)
+    blo, bhi = atoms.x.min(0) - 1e-9, atoms.x.max(0) + 1e-9
+    rneigh = cfg["r_max"] + SKIN
+
+    def neigh_cycle():
+        nbld.needs_rebuild(ntot, d_x.data_ptr(), SKIN, stream=cs)
+        nbld.build(nl, ng, d_x.data_ptr(), blo, bhi, rneigh, maxn, d_nb2.data_ptr(), d_num2.data_ptr(), want_max=False, stream=cs)
+        for _ in range(NEIGH_EVERY):
+            d_f.zero_()
+            comm.forward(d_x.data_ptr(), cs)
+            h.compute_device(nl, ng, d_x.data_ptr(), d_type.data_ptr(), d_ilist.data_ptr(), d_num2.data_ptr(), d_nb2.data_ptr(),
+                             maxn, 1, d_f.data_ptr(), 0, want_scalars=False, vflag=vflag, stream=cs)
+            comm.reverse(d_f.data_ptr(), cs)
+
+    neigh_cycle()
+    torch.cuda.synchronize()
+    if not torch.equal(d_num2, d_num):
+        raise RuntimeError("alg_neigh_build: neighbour counts differ from the list the bench was set up with")
+    f_ref = d_f.clone()
+    step_device()
+    torch.cuda.synchronize()
+    if float((d_f - f_ref).abs().max()) > 1e-4:
+        raise RuntimeError("forces on the device-built neighbour list differ from those on the set-up list")
+    t0e, t1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0e.record()
+    nbld.build(nl, ng, d_x.data_ptr(), blo, bhi, rneigh, maxn, d_nb2.data_ptr(), d_num2.data_ptr(), want_max=False, stream=cs)
+    t1e.record()
+    torch.cuda.synchronize()
+    ms_build = t0e.elapsed_time(t1e)
+    ms_cycle = timed(neigh_cycle, 1)
+    extra["device_neighbor_cycle"] = {"value": total_atoms * NEIGH_EVERY / (ms_cycle * 1e-3) / 1e6, "unit": "Matom-steps/s", "steps": NEIGH_EVERY,
+                                      "neigh_build_ms": ms_build,
+                                      "note": "alg_neigh_check + alg_neigh_build (cell list on the device) then %d x (halo, alg_compute_device); forces checked against the set-up list" % NEIGH_EVERY}
+    nbld.close()
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         # separate process: libtorch must not see the GPU (CPU path), and its threads must not fight ours

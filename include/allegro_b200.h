@@ -209,6 +209,23 @@ ALG_API int alg_comm_allreduce_sum(alg_comm* c, double* values, int n, void* str
 /* [bytes sent to other ranks per forward, per reverse, packed entries, distinct owner atoms] */
 ALG_API int alg_comm_stats(const alg_comm* c, double* out4);
 
+/* ---- neighbour-list build on the device (the step on the CALLER's side of the path) ------------------------------------
+ * What LAMMPS' Neighbor class builds before Pair::compute reads list->ilist / numneigh / firstneigh
+ * (pair_nequip_allegro.cpp:340-350, 469-480; requested with neighbor->add_request(this, REQ_FULL), :142-147): for every
+ * LOCAL atom i all atoms j != i (locals + ghosts) with |x_i - x_j|^2 <= rneigh^2 (rneigh = r_max + skin), as the 2-D view
+ * d_neighbors[i*stride_i + jj*stride_jj] + d_numneigh that alg_compute_device consumes.  Cell list (cells of rneigh inside
+ * the bounding box lo..hi of ALL atoms incl. ghosts), atoms sorted by (cell, index) with a stable radix sort, one warp per
+ * atom: the same positions always give the same list in the same order.  `max_count` (may be NULL) returns the largest
+ * neighbour count (one small synchronisation); a count above max_neigh truncates the rows and returns ALG_ESTATE.
+ * alg_neigh_check: Verlet-skin criterion -- *rebuild = 1 when some atom moved further than skin/2 since the last build. */
+typedef struct alg_neigh alg_neigh;
+ALG_API int alg_neigh_create(int cuda_device, alg_neigh** out);
+ALG_API void alg_neigh_destroy(alg_neigh* n);
+ALG_API const char* alg_neigh_last_error(const alg_neigh* n);
+ALG_API int alg_neigh_build(alg_neigh* n, int nlocal, int nghost, const double* d_x, const double* lo, const double* hi, double rneigh,
+                    int max_neigh, int64_t stride_i, int64_t stride_jj, int* d_neighbors, int* d_numneigh, int* max_count, void* stream);
+ALG_API int alg_neigh_check(alg_neigh* n, int ntot, const double* d_x, double skin, int* rebuild, void* stream);
+
 /* Building blocks of the above for callers that bring their own transport (LAMMPS pack/unpack_forward/reverse_comm):
  *   pack:        buf[k][0..2] = x[list[k]][0..2] + shift[k][0..2]   (d_shift may be NULL)
  *   unpack_add:  f[list[k]][0..2] += buf[k][0..2]   (fp64 atomics: list entries may repeat, and then the summation

@@ -17,7 +17,8 @@ EXPORTS = ["alg_create", "alg_destroy", "alg_last_error", "alg_metadata", "alg_s
            "alg_compute_host", "alg_compute_device", "alg_get_edges", "alg_get_output", "alg_get_timings", "alg_get_stats",
            "alg_halo_pack", "alg_halo_unpack_add", "alg_version", "alg_device_count",
            "alg_comm_unique_id", "alg_comm_create", "alg_comm_destroy", "alg_comm_last_error", "alg_comm_set_plan", "alg_comm_forward",
-           "alg_comm_reverse", "alg_comm_allreduce_sum", "alg_comm_stats"]
+           "alg_comm_reverse", "alg_comm_allreduce_sum", "alg_comm_stats",
+           "alg_neigh_create", "alg_neigh_destroy", "alg_neigh_last_error", "alg_neigh_build", "alg_neigh_check"]
 
 _lib = None
 
@@ -87,6 +88,16 @@ def load_library(path=None):
     lib.alg_comm_allreduce_sum.restype = C.c_int
     lib.alg_comm_stats.argtypes = [vp, dp]
     lib.alg_comm_stats.restype = C.c_int
+    lib.alg_neigh_create.argtypes = [C.c_int, C.POINTER(vp)]
+    lib.alg_neigh_create.restype = C.c_int
+    lib.alg_neigh_destroy.argtypes = [vp]
+    lib.alg_neigh_destroy.restype = None
+    lib.alg_neigh_last_error.argtypes = [vp]
+    lib.alg_neigh_last_error.restype = C.c_char_p
+    lib.alg_neigh_build.argtypes = [vp, C.c_int, C.c_int, vp, dp, dp, C.c_double, C.c_int, C.c_int64, C.c_int64, vp, vp, ip, vp]
+    lib.alg_neigh_build.restype = C.c_int
+    lib.alg_neigh_check.argtypes = [vp, C.c_int, vp, C.c_double, ip, vp]
+    lib.alg_neigh_check.restype = C.c_int
     lib.alg_device_count.argtypes = []
     lib.alg_device_count.restype = C.c_int
     lib.alg_version.argtypes = []
@@ -293,6 +304,48 @@ class Comm:
         if getattr(self, "c", None):
             self.lib.alg_comm_destroy(self.c)
             self.c = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class NeighborBuilder:
+    """binned FULL neighbour list on the device (alg_neigh_*): the product-side stand-in for LAMMPS' Neighbor class"""
+
+    def __init__(self, device=0):
+        self.lib = load_library()
+        self.n = C.c_void_p()
+        rc = self.lib.alg_neigh_create(int(device), C.byref(self.n))
+        if rc != 0:
+            self.n = None
+            raise AllegroError(rc, "alg_neigh_create failed")
+
+    def _check(self, rc):
+        if rc != 0:
+            raise AllegroError(rc, self.lib.alg_neigh_last_error(self.n).decode())
+
+    def build(self, nlocal, nghost, d_x, lo, hi, rneigh, max_neigh, d_neighbors, d_numneigh, stride_i=None, stride_jj=1, want_max=True, stream=0):
+        """d_* raw device addresses; the view is LayoutRight [nlocal][max_neigh] unless strides are given.  returns the largest count"""
+        lo = np.ascontiguousarray(lo, dtype=np.float64)
+        hi = np.ascontiguousarray(hi, dtype=np.float64)
+        mx = C.c_int(0)
+        self._check(self.lib.alg_neigh_build(self.n, int(nlocal), int(nghost), d_x, _dptr(lo), _dptr(hi), float(rneigh), int(max_neigh),
+                                              int(max_neigh if stride_i is None else stride_i), int(stride_jj), d_neighbors, d_numneigh,
+                                              C.byref(mx) if want_max else None, stream or None))
+        return mx.value
+
+    def needs_rebuild(self, ntot, d_x, skin, stream=0):
+        r = C.c_int(1)
+        self._check(self.lib.alg_neigh_check(self.n, int(ntot), d_x, float(skin), C.byref(r), stream or None))
+        return bool(r.value)
+
+    def close(self):
+        if getattr(self, "n", None):
+            self.lib.alg_neigh_destroy(self.n)
+            self.n = None
 
     def __del__(self):
         try:
