@@ -49,6 +49,11 @@ CONFIGS = {
     "c5": dict(name="C5", l_max=3, num_layers=3, type_names=["Li", "P", "O", "X"], r_max=5.0, avg_nn=47.0, seed=5, scaling="strong",
                natoms=int(os.environ.get("ALG_BENCH_NATOMS", "8000000")), ref_natoms=int(os.environ.get("ALG_BENCH_REF_NATOMS", "3000")),
                what="Li3PO4-like 4-species jittered lattice (0.09 atoms/A^3), r_max=5.0, Allegro l_max=3 3 layers"),
+    # the "high-capacity" C5 architecture (BASELINE.json configs[4]): widths outside the specialised tiled kernels -> width-generic pipeline
+    "c5h": dict(name="C5 high-capacity", l_max=3, num_layers=3, type_names=["Li", "P", "O", "X"], r_max=5.0, avg_nn=47.0, seed=5, scaling="strong",
+                widths=dict(num_scalar_features=128, num_tensor_features=64, mlp_width=128, mlp_depth=2, readout_width=32),
+                natoms=int(os.environ.get("ALG_BENCH_NATOMS", "250000")), ref_natoms=int(os.environ.get("ALG_BENCH_REF_NATOMS", "1500")),
+                what="Li3PO4-like 4-species jittered lattice (0.09 atoms/A^3), r_max=5.0, Allegro l_max=3 3 layers, S=128 U=64 MLP 2x128"),
 }
 
 
@@ -59,14 +64,15 @@ def log(*a):
 def model_config(cfg):
     from pair_allegro_b200 import modelgen
     return modelgen.default_config(type_names=cfg["type_names"], r_max=cfg["r_max"], avg_num_neighbors=float(cfg["avg_nn"]), seed=cfg["seed"],
-                                   l_max=cfg["l_max"], num_layers=cfg["num_layers"])
+                                   l_max=cfg["l_max"], num_layers=cfg["num_layers"], **cfg.get("widths", {}))
 
 
-def flop_model(L, nl, B=8, T=1):
+def flop_model(L, nl, B=8, T=1, widths=None):
     """ALGORITHMIC flops per edge of each phase (DESIGN.md "Roofline"): GEMM 2*K*N,
     tensor product 3 flops per CG non-zero per channel (+2 per mixed output component), forward
     + input-gradient backward; recomputation inside the backward phases is NOT counted."""
-    S, H, U, R = 64, 64, 32, 32
+    w = widths or {}
+    S, H, U, R = w.get("num_scalar_features", 64), w.get("mlp_width", 64), w.get("num_tensor_features", 32), w.get("readout_width", 32)
     tables = json.load(open(os.path.join(ROOT, "tables", "allegro_tables.json")))["L"][str(L)]
     kinds = {1: ["A"], 2: ["B", "A"], 3: ["C", "D", "A"]}[nl]
     ENVW, SIN, NSH = (L + 1) * U, S + (L + 1) * U, (L + 1) ** 2
@@ -392,6 +398,8 @@ def run_ours(args):
     alg = os.path.join(d, "m.alg")
     modelgen.random_alg(model_config(cfg), alg)          # numpy random init, same seed on every rank (no oracle involved)
 
+    generic = "widths" in cfg or args.gemm == "generic"
+
     def make_pair(pin):
         pr = PairAllegroB200(device=local_rank, debug_mode=False, pin_host=pin)
         pr.settings([])
@@ -400,6 +408,9 @@ def run_ours(args):
         hh = pr.handle
         if args.chunk_edges:
             hh.set_option("chunk_edges", str(args.chunk_edges))
+        if generic:
+            hh.set_option("gemm", "generic")      # widths outside the tiled kernels select it anyway
+            return pr
         if cfg["l_max"] <= 2 or args.gemm == "ffma":
             hh.set_option("gemm", args.gemm)      # tc: tcgen05 tensor cores | ffma: FP32 pipe
         if args.gemm == "tc":
@@ -522,7 +533,7 @@ def run_ours(args):
     h.set_option("profile", "0")
     kms /= PS
     kn /= PS
-    fam, gemmf = flop_model(cfg["l_max"], cfg["num_layers"], T=len(cfg["type_names"]))
+    fam, gemmf = flop_model(cfg["l_max"], cfg["num_layers"], T=len(cfg["type_names"]), widths=cfg.get("widths"))
     names_k = capi.KERNEL_FAMILIES
     peaks = measured_peaks()
     tf32_peak = tf32_dense_peak(dev) if rank == 0 else None
@@ -530,7 +541,11 @@ def run_ours(args):
     fused = bool(pipe[0])
     alg_flops_edge = float(sum(fam.values()))
     gemm_flops_edge = float(sum(gemmf.values()))
-    if fused:
+    if generic:
+        # width-generic pipeline: ~100 small per-operation kernels per chunk; the roofline line is the whole network phase
+        dom, dom_name, nlaunch, dur = 0, "width-generic pipeline (all k_gen_* kernels of the step)", 1.0, last_ms[1] * 1e-3
+        flops_per_launch, gemm_per_launch, passes = alg_flops_edge * E, 0.0, 0
+    elif fused:
         dom_name, dur, nlaunch = "k_fused_tc", kms[6] * 1e-3, max(kn[6], 1)
         flops_per_launch = alg_flops_edge * E / nlaunch
         gemm_per_launch = gemm_flops_edge * E / nlaunch
@@ -569,7 +584,10 @@ def run_ours(args):
                 "algorithmic_flops_per_edge_by_phase": {k: float(v) for k, v in fam.items()}}
     if fused and "fused_c2" in tj:
         roofline["ncu"] = {k: tj["fused_c2"].get(k) for k in ("tensor_pipe_active_pct", "issue_active_pct", "dram_bytes_per_edge", "source")}
-    if not fused:
+    if generic:
+        roofline["note"] = ("width-generic pipeline (csrc/alg_generic.cu): FP32 FFMA GEMMs and per-operation kernels, no tensor cores; achieved = ALGORITHMIC "
+                            "fp32 flops of the whole network / its CUDA-event time; the contract's peak is the measured dense bf16 figure")
+    if not fused and not generic:
         roofline["per_kernel"] = {}
         for i in range(5):
             nm = names_k[i]
@@ -675,12 +693,13 @@ def run_ours(args):
         cst = comm.stats()
         line = {"metric": "Matom-steps/s force eval", "value": value, "unit": "Matom-steps/s", "n_gpus": world, "steps": K, "warmup": W,
                 "ms_per_step": ms / K, "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": "%s: %s; %d atoms in total (%d on rank 0, %d edges on rank 0), S=64 U=32 MLP 2x64 readout 32, random-init seed %d, strict fp32"
-                                       % (cfg["name"], cfg["what"], total_atoms, nl, E, cfg["seed"]),
+                "config": {"workload": "%s: %s; %d atoms in total (%d on rank 0, %d edges on rank 0), %s, random-init seed %d, strict fp32"
+                                       % (cfg["name"], cfg["what"], total_atoms, nl, E,
+                                          "widths as named (width-generic pipeline)" if "widths" in cfg else "S=64 U=32 MLP 2x64 readout 32", cfg["seed"]),
                            "domains": grid, "atoms_total": total_atoms, "ghosts_rank0": ng,
                            "l2_policy": "inputs larger than L2 (neighbour list + per-edge state >> 126 MB); no explicit flush",
                            "halo": "alg_comm_* (product code): grouped ncclSend/ncclRecv forward x / reverse f every step" if world > 1 else "periodic self-image halo on the device every step (alg_comm_*, no NCCL)",
-                           "pipeline": "fused" if fused else "tiled", "fused_batch": int(args.fused_batch or 8), "gemm": args.gemm if cfg["l_max"] <= 2 or args.gemm == "ffma" else "tc", "precision": args.precision},
+                           "pipeline": "generic" if generic else ("fused" if fused else "tiled"), "fused_batch": int(args.fused_batch or 8), "gemm": "generic" if generic else (args.gemm if cfg["l_max"] <= 2 or args.gemm == "ffma" else "tc"), "precision": args.precision},
                 "clocks": clocks, "gpu_launches": launches_per_step * K,
                 "phase_ms_last_step": {"edge_build": last_ms[0], "network": last_ms[1], "store": last_ms[2]},
                 "e2e": {"value": e2e_val, "unit": "Matom-steps/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
@@ -711,7 +730,7 @@ def main():
     ap.add_argument("--no-pin", action="store_true", help="e2e leg: do not let the library pin (cudaHostRegister) the caller's x / f / type arrays")
     ap.add_argument("--no-energy-check", action="store_true", help="N>1 weak scaling: skip the N x single-box energy assertion")
     ap.add_argument("--e2e-short", action="store_true", help="e2e leg: time exactly --steps steps instead of whole neighbour-list cycles (10 steps)")
-    ap.add_argument("--gemm", default="tc", choices=["tc", "ffma"])
+    ap.add_argument("--gemm", default="tc", choices=["tc", "ffma", "generic"])
     ap.add_argument("--pipeline", default="auto", choices=["auto", "fused", "tiled"])
     ap.add_argument("--fused-batch", type=int, default=0)
     ap.add_argument("--precision", default="strict", choices=["strict", "tf32"], help="strict = 3xTF32 (fp32-level), tf32 = fast mode")

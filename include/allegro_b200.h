@@ -105,7 +105,11 @@ ALG_API int alg_set_type_map(alg_handle* h, int ntypes, const int* lammps_type_t
  *   "keep_edges"   "1": materialise the int64 [2,E] edge_index for alg_get_edges
  *   "debug"        "1": keep per-edge gradients / intermediates for alg_get_output
  *   "profile"      "1": time every pipeline kernel with CUDA events (alg_get_stats)
- *   "gemm"         "tc": dense contractions on the tcgen05 tensor cores (l_max = 1) | "ffma": FP32 pipe
+ *   "gemm"         "tc": dense contractions on the tcgen05 tensor cores (default; l_max = 1..3) | "ffma": the same tiled
+ *                  kernels on the FP32 pipe | "generic": width-generic per-operation kernels (csrc/alg_generic.cu).  "tc" and
+ *                  "ffma" exist for num_scalar_features=64, num_tensor_features=32, MLP 2x64, readout 32; a model of any
+ *                  other widths (mlp_depth 1..4) loads and runs on "generic" automatically (slower: no tensor cores, every
+ *                  intermediate through HBM, one host synchronisation per step)
  *   "precision"    "strict": fp32-level accuracy (3xTF32 split on the tensor cores) | "tf32": one
  *                  TF32 pass (fast mode, ~1e-3 relative accuracy; tensor-core path only)
  *   "neigh_ago"    LAMMPS' neighbor->ago (steps since the last neighbour-list rebuild), set before

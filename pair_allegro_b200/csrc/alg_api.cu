@@ -21,6 +21,7 @@
 
 #include "../../include/allegro_b200.h"
 #include "alg_pipeline.cuh"
+#include "alg_generic.cuh"
 
 namespace alg {
 const Pipeline* get_pipeline(int L) {
@@ -101,6 +102,12 @@ struct alg_handle {
   const Pipeline* pipe_ffma = nullptr;
   const Pipeline* pipe_tc = nullptr;
   bool use_tc = false;
+  // width-generic pipeline (alg_generic.cuh): the only one for models outside the specialised widths; option gemm=generic otherwise
+  bool generic = false, std_widths = true;
+  GenModel gm{};
+  GenTables gtb{};
+  DevBuf gen_weights, gen_work;
+  long gen_chunk_edges = 65536;
   // fused persistent pipeline (centre-aligned tiles, allegro_kernels_tc.cuh: k_fused_tc)
   int pipeline_mode = 0;                   // option pipeline: 0 = auto, 1 = fused, 2 = tiled
   bool force_tiled = false;                // sticky: a centre with more than 128 edges was seen -> chunked edge-tile pipeline
@@ -497,6 +504,83 @@ __global__ void k_halo_unpack_add(double* __restrict__ f, const int* __restrict_
   atomicAdd(f + 3 * (size_t)i + 2, buf[3 * (size_t)k + 2]);
 }
 
+// width-generic pipeline: plain row-major fp32 matrices (+ transposes) of any width, omega channel-major
+static int setup_generic(alg_handle* h, int gS, int gH, int gU, int gR, int gD) {
+  const int L = h->L, T = h->T, B = h->B, nl = h->nl, ENVW = (L + 1) * gU;
+  std::string err;
+  struct Item { const float* src; long k, n; bool transpose; size_t off; };
+  std::vector<Item> items;
+  std::vector<std::pair<const float**, long>> fix;
+  size_t total = 0;
+  auto add = [&](const std::string& name, long k, long n, bool tr, const float** dst) -> bool {
+    const float* p = tf32(h, name, k, n, err);
+    if (!p) return false;
+    items.push_back({p, k, n, tr, total});
+    fix.push_back({dst, (long)items.size() - 1});
+    total += ((size_t)k * n + 63) / 64 * 64;
+    return true;
+  };
+  auto both = [&](const std::string& name, long k, long n, const float** w, const float** wt) { return add(name, k, n, false, w) && add(name, k, n, true, wt); };
+  GenModel& gm = h->gm;
+  gm = GenModel{};
+  gm.S = gS; gm.H = gH; gm.U = gU; gm.R = gR; gm.L = L; gm.nl = nl; gm.T = T; gm.B = B; gm.depth = gD;
+  auto mlp = [&](const std::string& pre, int din, GenMLP& m) -> bool {
+    m.nlin = gD + 1;
+    m.dims[0] = din;
+    for (int i = 1; i <= gD; ++i) m.dims[i] = gH;
+    m.dims[gD + 1] = gS;
+    for (int i = 0; i < m.nlin; ++i)
+      if (!both(pre + std::to_string(i), m.dims[i], m.dims[i + 1], &m.w[i], &m.wt[i])) return false;
+    return true;
+  };
+  bool ok = mlp("twobody.w", 2 * T + B, gm.two) && both("embed_linear", gS, ENVW, &gm.emb, &gm.emb_t);
+  static const char kinds[4][4] = {"", "A", "BA", "CDA"};
+  for (int k = 0; k < nl && ok; ++k) {
+    const std::string pre = "layer" + std::to_string(k) + ".";
+    GenLayer& gl = gm.layer[k];
+    gl.kind = kinds[nl][k];
+    const GenTpDims td = gen_tp_dims(L, gl.kind);
+    ok = ok && both(pre + "env_linear", gS, ENVW, &gl.env, &gl.env_t);
+    ok = ok && add(pre + "omega", td.npath, gU, true, &gl.omega_t);          // [npath][U] -> [U][npath]
+    ok = ok && mlp(pre + "mlp.w", gS + td.n0 * gU, gl.mlp);
+    const float* al = ok ? tf32(h, pre + "alpha", 1, 1, err) : nullptr;
+    if (!al) { ok = false; break; }
+    const double alpha = al[0];
+    gl.a = (float)(1.0 / std::sqrt(1.0 + alpha * alpha));
+    gl.b = (float)(alpha / std::sqrt(1.0 + alpha * alpha));
+  }
+  ok = ok && both("readout.w0", gS, gR, &gm.ro0, &gm.ro0_t) && add("readout.w1", gR, 1, false, &gm.ro1);
+  if (!ok) return fail(h, ALG_EIO, err);
+  std::vector<float> blob(total, 0.f);
+  for (const Item& it : items) {
+    float* dst = blob.data() + it.off;
+    if (!it.transpose) memcpy(dst, it.src, sizeof(float) * it.k * it.n);
+    else for (long r = 0; r < it.k; ++r) for (long c = 0; c < it.n; ++c) dst[c * it.k + r] = it.src[r * it.n + c];
+  }
+  CK(h->gen_weights.ensure(total * sizeof(float)));
+  CK(cudaMemcpy(h->gen_weights.p, blob.data(), total * sizeof(float), cudaMemcpyHostToDevice));
+  for (auto& fx : fix) *fx.first = h->gen_weights.as<float>() + items[fx.second].off;
+  // per-type tables and scalars (also needed when the tiled pipelines are not set up)
+  auto getf64 = [&](const char* name, long n, std::vector<double>& out) -> bool {
+    auto it = h->tensors.find(name);
+    if (it == h->tensors.end() || it->second.dtype != "f64" || (long)it->second.count() != n) { err = std::string("bad tensor ") + name; return false; }
+    out.assign(reinterpret_cast<const double*>(it->second.data.data()), reinterpret_cast<const double*>(it->second.data.data()) + n);
+    return true;
+  };
+  if (!getf64("scales", T, h->scales) || !getf64("shifts", T, h->shifts) || !getf64("cutoff_table", (long)T * T, h->cut_table))
+    return fail(h, ALG_EIO, err);
+  const double inv = 1.0 / std::sqrt(h->avg_n);
+  for (int i = 0; i < MAXT * MAXT; ++i) h->gtb.rc[i] = (float)h->r_max;
+  for (int i = 0; i < T; ++i) for (int j = 0; j < T; ++j) h->gtb.rc[i * MAXT + j] = (float)h->cut_table[i * T + j];
+  for (int i = 0; i < MAXT; ++i) h->gtb.gscale[i] = i < T ? (float)(inv * h->scales[i]) : 0.f;
+  gm.p = (float)h->p; gm.inv_sqrt_n = (float)inv;
+  CK(h->d_scale.ensure(sizeof(double) * MAXT));
+  CK(h->d_shift.ensure(sizeof(double) * MAXT));
+  CK(cudaMemcpy(h->d_scale.p, h->scales.data(), sizeof(double) * T, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(h->d_shift.p, h->shifts.data(), sizeof(double) * T, cudaMemcpyHostToDevice));
+  return ALG_OK;
+}
+
 // ------------------------------------------------------------------------------------------
 // model setup
 // ------------------------------------------------------------------------------------------
@@ -514,16 +598,29 @@ static int setup_model(alg_handle* h) {
   if (h->nl < 1 || h->nl > 3) return fail(h, ALG_EINVAL, "unsupported num_layers (supported: 1..3)");
   if (h->T < 1 || h->T > MAXT) return fail(h, ALG_EINVAL, "unsupported num_types (supported: 1..8)");
   if (h->B < 1 || h->B > MAXB) return fail(h, ALG_EINVAL, "unsupported num_bessels (supported: 1..16)");
-  if (geti("num_scalar_features", 0) != S || geti("num_tensor_features", 0) != U || geti("mlp_width", 0) != H ||
-      geti("mlp_depth", 0) != 2 || geti("readout_width", 0) != R)
-    return fail(h, ALG_EINVAL, "unsupported widths: this build supports num_scalar_features=64, num_tensor_features=32, "
-                               "mlp 2x64, readout 1x32");
+  const int gS = geti("num_scalar_features", 0), gU = geti("num_tensor_features", 0), gH = geti("mlp_width", 0), gD = geti("mlp_depth", 0),
+            gR = geti("readout_width", 0);
+  if (gS < 1 || gU < 1 || gH < 1 || gR < 1 || gD < 1 || gD + 1 > GEN_MAXLIN || gS > 4096 || gU > 1024 || gH > 4096 || gR > 4096)
+    return fail(h, ALG_EINVAL, "unsupported widths: num_scalar_features / num_tensor_features / mlp_width / readout_width must be positive, "
+                               "mlp_depth in 1..4");
+  // the tiled tensor-core / FP32-pipe kernels are specialised for these widths; every other model runs on the width-generic pipeline
+  h->std_widths = gS == S && gU == U && gH == H && gD == 2 && gR == R;
   {
     std::istringstream ss(hd.count("per_edge_type_cutoff") ? hd["per_edge_type_cutoff"] : "");
     double v;
     while (ss >> v) h->per_edge_cut.push_back(v);
     if (!h->per_edge_cut.empty() && (int)h->per_edge_cut.size() != h->T * h->T)
       return fail(h, ALG_EIO, "per_edge_type_cutoff must hold num_types^2 values");
+  }
+  {
+    int rc = setup_generic(h, gS, gH, gU, gR, gD);
+    if (rc != ALG_OK) return rc;
+  }
+  if (!h->std_widths) {
+    h->generic = true; h->use_tc = false; h->pipe = nullptr; h->fused_grid = 0;
+    cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, h->device);
+    h->tensors.clear();
+    return ALG_OK;
   }
   h->pipe = get_pipeline(h->L);
   h->pinfo = h->pipe->info(h->nl);
@@ -740,7 +837,7 @@ extern "C" void alg_destroy(alg_handle* h) {
                     &h->d_esum, &h->d_facc, &h->d_vacc, &h->d_forces, &h->d_eall, &h->d_red, &h->d_edge_index, &h->d_edge_energy,
                     &h->d_edge_grad, &h->d_eatom_out, &h->tc_weights, &h->c_ZD[0], &h->c_ZD[1], &h->c_ZD[2], &h->c_ZD[3], &h->c_W0, &h->c_dX, &h->c_dY, &h->c_du, &h->c_carry, &h->c_ecarry,
                     &h->c_X[0], &h->c_X[1], &h->c_X[2], &h->c_V[0], &h->c_V[1], &h->c_V[2], &h->c_dV[0], &h->c_dV[1],
-                    &h->c_gamma[0], &h->c_gamma[1], &h->c_gamma[2], &h->c_dgamma[0], &h->c_dgamma[1], &h->c_dgamma[2]};
+                    &h->c_gamma[0], &h->c_gamma[1], &h->c_gamma[2], &h->c_dgamma[0], &h->c_dgamma[1], &h->c_dgamma[2], &h->gen_weights, &h->gen_work};
   for (DevBuf* b : bufs) b->release();
   h->h_stage.release(); h->h_rowptr.release(); h->h_out.release(); h->h_first.release();
   for (int i = 0; i < 4; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
@@ -789,16 +886,19 @@ extern "C" int alg_set_option(alg_handle* h, const char* key, const char* value)
   else if (k == "debug") h->debug = v == "1";
   else if (k == "profile") h->prof.on = v == "1";
   else if (k == "gemm") {
-    if (v == "ffma") { h->use_tc = false; h->pipe = h->pipe_ffma; }
+    if (v == "generic") { h->generic = true; h->use_tc = false; }
+    else if (!h->std_widths) return fail(h, ALG_EINVAL, "gemm=" + v + ": the tiled kernels are specialised for num_scalar_features=64, num_tensor_features=32, "
+                                                          "mlp 2x64, readout 32; this model runs on gemm=generic");
+    else if (v == "ffma") { h->generic = false; h->use_tc = false; h->pipe = h->pipe_ffma; }
     else if (v == "tc") {
       if (!h->pipe_tc) return fail(h, ALG_EINVAL, "gemm=tc: no tensor-core pipeline for this model");
-      h->use_tc = true; h->pipe = h->pipe_tc;
-    } else return fail(h, ALG_EINVAL, "gemm must be ffma or tc");
-    h->pinfo = h->pipe->info(h->nl);
+      h->generic = false; h->use_tc = true; h->pipe = h->pipe_tc;
+    } else return fail(h, ALG_EINVAL, "gemm must be tc, ffma or generic");
+    if (h->pipe) h->pinfo = h->pipe->info(h->nl);
   } else if (k == "pipeline") {
     if (v == "auto") h->pipeline_mode = 0;
     else if (v == "fused") {
-      if (!h->pipe_tc || !h->pipe_tc->run_fused || h->fused_grid <= 0) return fail(h, ALG_EINVAL, "pipeline=fused needs the tensor-core pipeline of this model");
+      if (h->generic || !h->pipe_tc || !h->pipe_tc->run_fused || h->fused_grid <= 0) return fail(h, ALG_EINVAL, "pipeline=fused needs the tensor-core pipeline of this model");
       h->pipeline_mode = 1;
     } else if (v == "tiled") h->pipeline_mode = 2;
     else return fail(h, ALG_EINVAL, "pipeline must be auto, fused or tiled");
@@ -921,7 +1021,7 @@ static int step_tiled(alg_handle* h, const StepIO& io) {
   cudaStream_t st = h->stream;
   const int nlocal = io.nlocal;
   const PipelineInfo& pi = h->pinfo;
-  const int TM = pi.TM;
+  const int TM = h->generic ? 128 : pi.TM;
   CK(h->h_rowptr.ensure(sizeof(int) * (nlocal + 1)));
   CK(cudaMemcpyAsync(h->h_rowptr.p, h->d_rowptr.p, sizeof(int) * (nlocal + 1), cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
@@ -936,7 +1036,7 @@ static int step_tiled(alg_handle* h, const StepIO& io) {
   // chunk plan (centre aligned)
   struct Chunk { int c0, c1, e0, e1; };
   std::vector<Chunk> chunks;
-  const long CE = std::max<long>(h->chunk_edges, TM);
+  const long CE = std::max<long>(h->generic ? std::min<long>(h->chunk_edges, h->gen_chunk_edges) : h->chunk_edges, TM);
   const long CC = CE;   // centres per chunk bound
   long max_tiles = 1, max_cent = 1;
   for (int c0 = 0; c0 < nlocal;) {
@@ -955,6 +1055,18 @@ static int step_tiled(alg_handle* h, const StepIO& io) {
       max_cent = std::max<long>(max_cent, c1 - c0);
     }
     c0 = c1;
+  }
+  if (h->generic) {                                   // width-generic pipeline: own workspace, one chunk after the other
+    long nmax = 1, cmax = 1;
+    for (const Chunk& c : chunks) { nmax = std::max<long>(nmax, c.e1 - c.e0); cmax = std::max<long>(cmax, c.c1 - c.c0); }
+    CK(h->gen_work.ensure(sizeof(float) * gen_work_floats(h->gm, nmax, cmax)));
+    ChunkArgs a;
+    fill_args(h, io, a);
+    GenEdges ge{a.rvec, a.edge_j, a.edge_c, a.rowptr, a.ilist, a.esum, a.edge_energy, a.edge_grad, a.facc, a.vacc};
+    for (const Chunk& c : chunks) CK(gen_run_chunk(h->gm, h->gtb, ge, c.c0, c.c1, c.e0, c.e1, h->gen_work.as<float>(), st, &h->prof.launches));
+    h->step_stats[1] = (double)E; h->step_stats[2] = (double)chunks.size(); h->step_stats[3] = 0;
+    h->dbg_ntiles = 0; h->dbg_c0 = 0; h->dbg_ncent = 0;
+    return ALG_OK;
   }
   rc = ensure_chunk_buffers(h, max_tiles, max_cent);
   if (rc != ALG_OK) return rc;
@@ -1086,7 +1198,7 @@ static int resolve_pending(alg_handle* h, bool block = true, unsigned keep = 0) 
 }
 
 static bool fused_selected(const alg_handle* h) {
-  if (h->pipeline_mode == 2 || !h->use_tc || !h->pipe || !h->pipe->run_fused || h->fused_grid <= 0) return false;
+  if (h->pipeline_mode == 2 || h->generic || !h->use_tc || !h->pipe || !h->pipe->run_fused || h->fused_grid <= 0) return false;
   if (h->pipeline_mode == 1) return true;
   // auto: the faster pipeline as measured on the B200 (bench.py, strict fp32) -- the chunked per-phase kernels: 4 % faster
   // for l_max = 1, 1.25x for l_max = 2, 1.5x for l_max = 3 (the persistent kernel streams the code of all phases through
@@ -1138,7 +1250,7 @@ static int run_step(alg_handle* h, const StepIO& io, double* eng, double* virial
   long cap = 0;
   // chunked pipeline: device-built chunk plan (no host synchronisation) unless intermediates are wanted (debug=1 needs the
   // host-side chunk bookkeeping) or an earlier step showed that the plan does not fit the buffers
-  auto tiled_async = [&] { return !fused && !h->debug && !h->tiled_sync && h->tiled_plan_device; };
+  auto tiled_async = [&] { return !fused && !h->generic && !h->debug && !h->tiled_sync && h->tiled_plan_device; };
   for (int attempt = 0;; ++attempt) {
     CK(cudaMemsetAsync(h->d_esum.p, 0, sizeof(double) * nlocal, st));
     CK(cudaMemsetAsync(h->d_facc.p, 0, sizeof(unsigned long long) * 3 * ntot, st));

@@ -1,0 +1,5 @@
+// width-generic pipeline: tensor-product kernels for l_max = 2
+#include "alg_generic_tp.cuh"
+namespace alg {
+ALG_DEFINE_GENERIC_TP(2)
+}

@@ -27,6 +27,9 @@ def main():
     lst = H.build_full_list(atoms, 6.0)
     print("atoms %d ghosts %d cand %d  (harness %.1fs)" % (atoms.nlocal, atoms.nghost, lst.numneigh.sum(), time.time() - t0))
     cfg = modelgen.default_config(type_names=["Ag"], r_max=5.0, l_max=L, num_layers=nl, avg_num_neighbors=28.0, seed=2)
+    if os.environ.get("ALG_WIDTHS"):                      # S,U,H,depth,R (other than 64,32,64,2,32 -> width-generic pipeline)
+        S, U, Hh, D, R = (int(v) for v in os.environ["ALG_WIDTHS"].split(","))
+        cfg.update(num_scalar_features=S, num_tensor_features=U, mlp_width=Hh, mlp_depth=D, readout_width=R)
     os.makedirs("/tmp/qb", exist_ok=True)
     modelgen.random_alg(cfg, "/tmp/qb/m.alg")
     pair = PairAllegroB200(device=0, debug_mode=False)
