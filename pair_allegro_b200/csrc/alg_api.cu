@@ -574,6 +574,10 @@ static int setup_generic(alg_handle* h, int gS, int gH, int gU, int gR, int gD) 
   for (int i = 0; i < T; ++i) for (int j = 0; j < T; ++j) h->gtb.rc[i * MAXT + j] = (float)h->cut_table[i * T + j];
   for (int i = 0; i < MAXT; ++i) h->gtb.gscale[i] = i < T ? (float)(inv * h->scales[i]) : 0.f;
   gm.p = (float)h->p; gm.inv_sqrt_n = (float)inv;
+  {  // chunk size of the width-generic pipeline: about 8 GB of workspace, 16 k .. 1 M edges
+    const double bytes_per_edge = 4.0 * (double)gen_work_floats(gm, 65536, 2048) / 65536.0;
+    h->gen_chunk_edges = std::min<long>(1048576, std::max<long>(16384, (long)(8.0e9 / bytes_per_edge)));
+  }
   CK(h->d_scale.ensure(sizeof(double) * MAXT));
   CK(h->d_shift.ensure(sizeof(double) * MAXT));
   CK(cudaMemcpy(h->d_scale.p, h->scales.data(), sizeof(double) * T, cudaMemcpyHostToDevice));
