@@ -1,6 +1,8 @@
 // Width-generic pipeline (see alg_generic.cuh): host orchestration + the non-tensor-product kernels.
 // Chain rule as stated (and checked against autograd) in oracle/analytic_numpy.py.
 #include <algorithm>
+#include <cstdlib>
+#include <string>
 
 #include "alg_generic.cuh"
 
@@ -51,10 +53,21 @@ __global__ void k_gen_geom(int n, int e0, const float4* __restrict__ rvec, const
   for (int b = 0; b < B; ++b) in[2 * T + b] = pref * sinf((float)(b + 1) * (3.14159265358979323846f * xr)) / g.r * g.u;
 }
 
+// GEMM epilogues: what happens to an accumulator v of element (row gm, column gj) of C[n][N]
+enum { EPI_STORE = 0, EPI_ADD = 1, EPI_SILU = 2, EPI_MUL = 3 };
+// EPI_SILU: C = c*silu(v), D[gm][gj] = its derivative (D dense, leading dimension N);  EPI_MUL: C = v * D[gm][gj]
+__device__ __forceinline__ void gemm_epilogue(int mode, float* __restrict__ C, int ldc, float* __restrict__ D, int N, int gm, int gj, float v) {
+  float* dst = C + (size_t)gm * ldc + gj;
+  if (mode == EPI_STORE) *dst = v;
+  else if (mode == EPI_ADD) *dst += v;
+  else if (mode == EPI_SILU) { float dd; *dst = silu_act(v, dd); D[(size_t)gm * N + gj] = dd; }
+  else *dst = v * D[(size_t)gm * N + gj];
+}
+
 // C[n][N] (+)= A[n][K] . W[K][N]   (row-major, leading dimensions lda / ldw / ldc); k ascending -> deterministic
 constexpr int GB = 64, GK = 16;
 __global__ void __launch_bounds__(256) k_gen_gemm(const float* __restrict__ A, int lda, const float* __restrict__ W, int ldw,
-                                                  float* __restrict__ C, int ldc, int n, int K, int N, int accumulate) {
+                                                  float* __restrict__ C, int ldc, int n, int K, int N, int mode, float* __restrict__ D) {
   __shared__ float As[GK][GB + 1];
   __shared__ float Ws[GK][GB];
   const int m0 = blockIdx.x * GB, j0 = blockIdx.y * GB;
@@ -96,44 +109,115 @@ __global__ void __launch_bounds__(256) k_gen_gemm(const float* __restrict__ A, i
     for (int j = 0; j < 4; ++j) {
       const int gj = j0 + tx * 4 + j;
       if (gj >= N) continue;
-      float* dst = C + (size_t)gm * ldc + gj;
-      *dst = accumulate ? *dst + c[i][j] : c[i][j];
+      gemm_epilogue(mode, C, ldc, D, N, gm, gj, c[i][j]);
     }
   }
 }
 
-// z -> c*silu(z) in place, derivative kept
-__global__ void k_gen_silu(long total, float* __restrict__ z, float* __restrict__ d) {
-  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= total) return;
-  float dd;
-  z[i] = silu_act(z[i], dd);
-  d[i] = dd;
+// The same GEMM on the tensor cores: warp-level mma.sync m16n8k8 TF32 with the 3xTF32 split (hi*hi + hi*lo + lo*hi, small
+// terms first) for fp32-level accuracy -- the split the tcgen05 pipeline uses (umma.cuh), here with operands of any shape
+// staged through shared memory.  Block 128 x 64, 8 warps of 32 x 32.  Fixed summation order -> deterministic.
+constexpr int MB = 128, NB = 64, KB = 16;
+__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(x));
+  const float r = x - __uint_as_float(hi);
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo) : "f"(r));
 }
-__global__ void k_gen_mul(long total, float* __restrict__ x, const float* __restrict__ d) {
-  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < total) x[i] *= d[i];
+__device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
 }
+__global__ void __launch_bounds__(256) k_gen_gemm_mma(const float* __restrict__ A, int lda, const float* __restrict__ W, int ldw,
+                                                      float* __restrict__ C, int ldc, int n, int K, int N, int mode, float* __restrict__ D) {
+  __shared__ float As[MB][KB + 4];
+  __shared__ float Bs[KB][NB + 8];
+  const int m0 = blockIdx.x * MB, j0 = blockIdx.y * NB;
+  const int t = threadIdx.x, warp = t >> 5, lane = t & 31, g = lane >> 2, tig = lane & 3;
+  const int wm = warp >> 1, wn = warp & 1;
+  float acc[2][4][4];
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) acc[i][j][q] = 0.f;
+  float pa[8], pb[4];                                 // next K-slab, fetched while the current one is multiplied
+  auto fetch = [&](int k0) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int idx = t + 256 * i;
+      const int gm = m0 + (idx >> 4), gk = k0 + (idx & 15);
+      pa[i] = (gm < n && gk < K) ? A[(size_t)gm * lda + gk] : 0.f;
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int idx = t + 256 * i;
+      const int gk = k0 + (idx >> 6), gj = j0 + (idx & 63);
+      pb[i] = (gk < K && gj < N) ? W[(size_t)gk * ldw + gj] : 0.f;
+    }
+  };
+  fetch(0);
+  for (int k0 = 0; k0 < K; k0 += KB) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { const int idx = t + 256 * i; As[idx >> 4][idx & 15] = pa[i]; }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { const int idx = t + 256 * i; Bs[idx >> 6][idx & 63] = pb[i]; }
+    __syncthreads();
+    if (k0 + KB < K) fetch(k0 + KB);
+#pragma unroll
+    for (int ks = 0; ks < KB; ks += 8) {
+      uint32_t ah[2][4], al[2][4], bh[4][2], bl[4][2];
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) {
+        const int r = wm * 32 + mt * 16 + g;
+        split_tf32(As[r][ks + tig], ah[mt][0], al[mt][0]);
+        split_tf32(As[r + 8][ks + tig], ah[mt][1], al[mt][1]);
+        split_tf32(As[r][ks + tig + 4], ah[mt][2], al[mt][2]);
+        split_tf32(As[r + 8][ks + tig + 4], ah[mt][3], al[mt][3]);
+      }
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        const int c = wn * 32 + nt * 8 + g;
+        split_tf32(Bs[ks + tig][c], bh[nt][0], bl[nt][0]);
+        split_tf32(Bs[ks + tig + 4][c], bh[nt][1], bl[nt][1]);
+      }
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+          mma_tf32(acc[mt][nt], al[mt], bh[nt]);
+          mma_tf32(acc[mt][nt], ah[mt], bl[nt]);
+          mma_tf32(acc[mt][nt], ah[mt], bh[nt]);
+        }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int gm = m0 + wm * 32 + mt * 16 + g + (q >> 1) * 8;
+        const int gj = j0 + wn * 32 + nt * 8 + 2 * tig + (q & 1);
+        if (gm < n && gj < N) gemm_epilogue(mode, C, ldc, D, N, gm, gj, acc[mt][nt][q]);
+      }
+}
+
 __global__ void k_gen_zero(long total, float* __restrict__ x) {
   const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < total) x[i] = 0.f;
 }
 // out[q][s] = a * base[q][s] + b * m[q][s] * u[q]   (base may be null)
 __global__ void k_gen_mix(int n, int S, const float* __restrict__ base, const float* __restrict__ m, const float* __restrict__ u,
-                          float a, float b, float* __restrict__ out) {
+                          float a, float b, float* __restrict__ out, float* __restrict__ out2, int ld2) {
   const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (long)n * S) return;
   const int q = (int)(i / S);
-  out[i] = (base ? a * base[i] : 0.f) + b * m[i] * u[q];
-}
-// dst[q][c0 + s] (op)= src[q][s], s < N
-__global__ void k_gen_cols(int n, int N, const float* __restrict__ src, int lds, float* __restrict__ dst, int ldd, int add) {
-  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= (long)n * N) return;
-  const int q = (int)(i / N), s = (int)(i % N);
-  float* d = dst + (size_t)q * ldd + s;
-  const float v = src[(size_t)q * lds + s];
-  *d = add ? *d + v : v;
+  const float v = (base ? a * base[i] : 0.f) + b * m[i] * u[q];
+  out[i] = v;
+  if (out2) out2[(size_t)q * ld2 + (i - (long)q * S)] = v;
 }
 // backward of out = a*x + b*m*u:  dm = b*dout*u, du += sum_s b*dout*m, dx(in place) = a*dout.   One warp per edge.
 __global__ void k_gen_mix_bwd(int n, int S, float* __restrict__ dX, const float* __restrict__ m, const float* __restrict__ u,
@@ -167,8 +251,8 @@ __global__ void k_gen_gamma(int c0, int e0, const int* __restrict__ rowptr, int 
     gamma[(size_t)blockIdx.x * F + f] = acc * inv;
   }
 }
-// dGamma_c[lm*U+u] = sum_{e in N(c)} dG_e[u][lm]
-__global__ void k_gen_dgamma(int c0, int e0, const int* __restrict__ rowptr, int U, int NSH, const float* __restrict__ dge,
+// dGamma_c[lm*U+u] = sum_{e in N(c)} dG_e[lm][e][u]
+__global__ void k_gen_dgamma(int c0, int e0, const int* __restrict__ rowptr, int U, int NSH, size_t NU, const float* __restrict__ dge,
                              float* __restrict__ dgamma) {
   const int c = c0 + blockIdx.x;
   const int q0 = rowptr[c] - e0, q1 = rowptr[c + 1] - e0;
@@ -176,55 +260,49 @@ __global__ void k_gen_dgamma(int c0, int e0, const int* __restrict__ rowptr, int
   for (int f = threadIdx.x; f < F; f += blockDim.x) {
     const int lm = f / U, uu = f % U;
     float acc = 0.f;
-    for (int q = q0; q < q1; ++q) acc += dge[((size_t)q * U + uu) * NSH + lm];
+    for (int q = q0; q < q1; ++q) acc += dge[(size_t)lm * NU + (size_t)q * U + uu];
     dgamma[(size_t)blockIdx.x * F + f] = acc;
   }
 }
-// Gamma = inv * sum w (x) Y backward: dw[e][l*U+u] = inv * sum_{m in l} dGamma_c[lm*U+u] * Y[e][lm]
-__global__ void k_gen_env_bwd_w(int n, int e0, int c0, const int* __restrict__ edge_c, int U, int L, const float* __restrict__ dgamma,
-                                const float* __restrict__ Y, float inv, float* __restrict__ dw) {
-  const int NSH = (L + 1) * (L + 1), ENVW = (L + 1) * U;
-  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= (long)n * ENVW) return;
-  const int q = (int)(i / ENVW), col = (int)(i % ENVW), l = col / U, uu = col % U;
-  const float* dg = dgamma + (size_t)(edge_c[e0 + q] - c0) * NSH * U;
-  float acc = 0.f;
-  for (int lm = l * l; lm < (l + 1) * (l + 1); ++lm) acc += dg[lm * U + uu] * Y[(size_t)q * NSH + lm];
-  dw[i] = acc * inv;
-}
-// ... and dY[e][lm] += inv * sum_u dGamma_c[lm*U+u] * w[e][l*U+u]
-__global__ void k_gen_env_bwd_y(int n, int e0, int c0, const int* __restrict__ edge_c, int U, int L, const float* __restrict__ dgamma,
-                                const float* __restrict__ w, float inv, float* __restrict__ dY) {
-  const int NSH = (L + 1) * (L + 1), ENVW = (L + 1) * U;
-  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= (long)n * NSH) return;
-  const int q = (int)(i / NSH), lm = (int)(i % NSH), l = lsel(lm);
-  const float* dg = dgamma + (size_t)(edge_c[e0 + q] - c0) * NSH * U + (size_t)lm * U;
-  const float* wr = w + (size_t)q * ENVW + l * U;
-  float acc = 0.f;
-  for (int uu = 0; uu < U; ++uu) acc += dg[uu] * wr[uu];
-  dY[i] += acc * inv;
-}
-// V^0 = w0 (x) Y backward: dw0[e][l*U+u] = sum_{m in l} dV[e][u][lm] * Y[e][lm];  dY[e][lm] += sum_u dV[e][u][lm] * w0[e][l*U+u]
-__global__ void k_gen_v0_bwd_w(int n, int U, int L, const float* __restrict__ dv, const float* __restrict__ Y, float* __restrict__ dw0) {
-  const int NSH = (L + 1) * (L + 1), ENVW = (L + 1) * U;
-  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= (long)n * ENVW) return;
-  const int q = (int)(i / ENVW), col = (int)(i % ENVW), l = col / U, uu = col % U;
-  const float* d = dv + ((size_t)q * U + uu) * NSH;
-  float acc = 0.f;
-  for (int lm = l * l; lm < (l + 1) * (l + 1); ++lm) acc += d[lm] * Y[(size_t)q * NSH + lm];
-  dw0[i] = acc;
-}
-__global__ void k_gen_v0_bwd_y(int n, int U, int L, const float* __restrict__ dv, const float* __restrict__ w0, float* __restrict__ dY) {
-  const int NSH = (L + 1) * (L + 1), ENVW = (L + 1) * U;
-  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= (long)n * NSH) return;
-  const int q = (int)(i / NSH), lm = (int)(i % NSH), l = lsel(lm);
-  const float* wr = w0 + (size_t)q * ENVW + l * U;
-  float acc = 0.f;
-  for (int uu = 0; uu < U; ++uu) acc += dv[((size_t)q * U + uu) * NSH + lm] * wr[uu];
-  dY[i] += acc;
+// Backward of an outer product with the spherical harmonics, one warp per edge (lanes over channels, everything coalesced):
+//   dw[e][l*U+u] = inv * sum_{m in l} dT[lm][u] * Y[e][lm]        dY[e][lm] += inv * sum_u dT[lm][u] * w[e][l*U+u]
+// MODE 0: Gamma = inv * sum_e w (x) Y  -> dT = dGamma of the edge's centre ([lm*U+u]);
+// MODE 1: V^0 = w0 (x) Y               -> dT = dV^0 of the edge itself (component-major [lm][e][u]), inv = 1.
+template <int L, int MODE>
+__global__ void k_gen_outer_bwd(int n, int e0, int c0, const int* __restrict__ edge_c, int U, const float* __restrict__ dsrc,
+                                const float* __restrict__ Y, const float* __restrict__ w, float inv, float* __restrict__ dw,
+                                float* __restrict__ dY) {
+  constexpr int NSH = (L + 1) * (L + 1);
+  const int q = (int)(((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+  if (q >= n) return;
+  const int ENVW = (L + 1) * U;
+  const size_t NU = (size_t)n * U;
+  const float* dT = MODE == 0 ? dsrc + (size_t)(edge_c[e0 + q] - c0) * NSH * U : dsrc + (size_t)q * U;
+  const size_t cs = MODE == 0 ? (size_t)U : NU;               // stride between components lm
+  float y[NSH], dyp[NSH];
+#pragma unroll
+  for (int lm = 0; lm < NSH; ++lm) { y[lm] = Y[(size_t)q * NSH + lm]; dyp[lm] = 0.f; }
+  for (int u = lane; u < U; u += 32) {
+#pragma unroll
+    for (int l = 0; l <= L; ++l) {
+      const float wv = w[(size_t)q * ENVW + l * U + u];
+      float acc = 0.f;
+#pragma unroll
+      for (int lm = l * l; lm < (l + 1) * (l + 1); ++lm) {
+        const float d = dT[(size_t)lm * cs + u];
+        acc += d * y[lm];
+        dyp[lm] += d * wv;
+      }
+      dw[(size_t)q * ENVW + l * U + u] = acc * inv;
+    }
+  }
+#pragma unroll
+  for (int lm = 0; lm < NSH; ++lm) {
+    float v = dyp[lm];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) dY[(size_t)q * NSH + lm] += v * inv;
+  }
 }
 // readout second layer: E_e = ro1 . a ;  dz (in place over act') = gscale[Z_i] * ro1 * act'
 __global__ void k_gen_readout(int n, int e0, int R, const float* __restrict__ ar, float* __restrict__ dr, const float* __restrict__ ro1,
@@ -350,9 +428,11 @@ struct Runner {
   int n;
   unsigned blocks(long total, int tpb = 256) const { return (unsigned)((total + tpb - 1) / tpb); }
   void check() { if (err == cudaSuccess) err = cudaGetLastError(); ++launches; }
-  void gemm(const float* A, int lda, const float* W, int ldw, float* C, int ldc, int K, int N, bool acc) {
-    if (n == 0) return;
-    k_gen_gemm<<<dim3((n + GB - 1) / GB, (N + GB - 1) / GB), 256, 0, st>>>(A, lda, W, ldw, C, ldc, n, K, N, acc ? 1 : 0);
+  void gemm(const float* A, int lda, const float* W, int ldw, float* C, int ldc, int K, int N, int mode, float* D = nullptr) {
+    if (n == 0 || N <= 0) return;
+    static const bool ffma = [] { const char* e = getenv("ALG_GENERIC_GEMM"); return e && std::string(e) == "ffma"; }();   // debugging aid
+    if (ffma) k_gen_gemm<<<dim3((n + GB - 1) / GB, (N + GB - 1) / GB), 256, 0, st>>>(A, lda, W, ldw, C, ldc, n, K, N, mode, D);
+    else k_gen_gemm_mma<<<dim3((n + MB - 1) / MB, (N + NB - 1) / NB), 256, 0, st>>>(A, lda, W, ldw, C, ldc, n, K, N, mode, D);
     check();
   }
   // keeps act' of hidden layer i of stage `stage` in D[stage][i]; result (last linear, no activation) -> out [n][dims[nlin]]
@@ -361,27 +441,25 @@ struct Runner {
     for (int i = 0; i < mlp.nlin; ++i) {
       const bool last = i == mlp.nlin - 1;
       float* z = last ? out : ws + p.SC[i & 1];
-      gemm(cur, ld, mlp.w[i], mlp.dims[i + 1], z, mlp.dims[i + 1], mlp.dims[i], mlp.dims[i + 1], false);
-      if (!last) {
-        const long tot = (long)n * mlp.dims[i + 1];
-        k_gen_silu<<<blocks(tot), 256, 0, st>>>(tot, z, ws + p.D[stage][i]);
-        check();
-      }
+      gemm(cur, ld, mlp.w[i], mlp.dims[i + 1], z, mlp.dims[i + 1], mlp.dims[i], mlp.dims[i + 1], last ? EPI_STORE : EPI_SILU,
+           last ? nullptr : ws + p.D[stage][i]);
       cur = z; ld = mlp.dims[i + 1];
     }
   }
-  // dout [n][dims[nlin]] (in SC[2]) -> din [n][dims[0]]
-  void mlp_bwd(const GenMLP& mlp, const float* dout, int stage, float* din) {
+  // dout [n][dims[nlin]] (in SC[2]) -> din [n][dims[0]].  With dx != nullptr the first `split` input columns are ADDED to
+  // dx [n][split] instead (the latent part of a layer's MLP input), the rest goes to din at the same column offset.
+  void mlp_bwd(const GenMLP& mlp, const float* dout, int stage, float* din, float* dx = nullptr, int split = 0) {
     const float* cur = dout;
     int flip = 0;
     for (int i = mlp.nlin - 1; i >= 0; --i) {
       float* o = i == 0 ? din : ws + p.SC[flip];
       flip ^= 1;
-      gemm(cur, mlp.dims[i + 1], mlp.wt[i], mlp.dims[i], o, mlp.dims[i], mlp.dims[i + 1], mlp.dims[i], false);
-      if (i > 0) {
-        const long tot = (long)n * mlp.dims[i];
-        k_gen_mul<<<blocks(tot), 256, 0, st>>>(tot, o, ws + p.D[stage][i - 1]);
-        check();
+      const int K = mlp.dims[i + 1], N = mlp.dims[i];
+      if (i == 0 && dx) {
+        gemm(cur, K, mlp.wt[0], N, dx, split, K, split, EPI_ADD);
+        gemm(cur, K, mlp.wt[0] + split, N, o + split, N, K, N - split, EPI_STORE);
+      } else {
+        gemm(cur, K, mlp.wt[i], N, o, N, K, N, i > 0 ? EPI_MUL : EPI_STORE, i > 0 ? ws + p.D[stage][i - 1] : nullptr);
       }
       cur = o;
     }
@@ -395,6 +473,18 @@ template <int L> void launch_geom(Runner& r, const GenTables& tb, const GenEdges
 template <int L> void launch_force(Runner& r, const GenTables& tb, const GenEdges& g, int e0, const float* dIN0) {
   k_gen_force<L><<<r.blocks(r.n, 128), 128, 0, r.st>>>(r.n, e0, g.rvec, tb, r.m.p, r.m.T, r.m.B, r.ws + r.p.du, dIN0, r.ws + r.p.dY,
                                                          g.edge_j, g.edge_c, g.ilist, g.facc, g.vacc, g.edge_grad);
+  r.check();
+}
+
+void launch_outer_bwd(Runner& r, int L, int mode, int e0, int c0, const int* edge_c, const float* dsrc, const float* w, float inv, float* dw) {
+  const unsigned b = r.blocks((long)r.n * 32, 256);
+  const float* Y = r.ws + r.p.Y;
+  float* dY = r.ws + r.p.dY;
+  const int U = r.m.U;
+#define ALG_OB(LV, MV) k_gen_outer_bwd<LV, MV><<<b, 256, 0, r.st>>>(r.n, e0, c0, edge_c, U, dsrc, Y, w, inv, dw, dY)
+  if (mode == 0) { if (L == 1) ALG_OB(1, 0); else if (L == 2) ALG_OB(2, 0); else ALG_OB(3, 0); }
+  else { if (L == 1) ALG_OB(1, 1); else if (L == 2) ALG_OB(2, 1); else ALG_OB(3, 1); }
+#undef ALG_OB
   r.check();
 }
 
@@ -416,53 +506,49 @@ cudaError_t gen_run_chunk(const GenModel& m, const GenTables& tb, const GenEdges
   k_gen_zero<<<r.blocks(n), 256, 0, st>>>(n, W(p.du)); r.check();
   k_gen_zero<<<r.blocks((long)n * p.NSH), 256, 0, st>>>((long)n * p.NSH, W(p.dY)); r.check();
   r.mlp_fwd(m.two, W(p.IN0), p.K0, 0, W(p.M[0]));
-  k_gen_mix<<<r.blocks((long)n * S), 256, 0, st>>>(n, S, nullptr, W(p.M[0]), W(p.u), 0.f, 1.f, W(p.X[0])); r.check();
-  r.gemm(W(p.X[0]), S, m.emb, p.ENVW, W(p.W0e), p.ENVW, S, p.ENVW, false);
+  k_gen_mix<<<r.blocks((long)n * S), 256, 0, st>>>(n, S, nullptr, W(p.M[0]), W(p.u), 0.f, 1.f, W(p.X[0]), W(p.IN), p.SIN); r.check();
+  r.gemm(W(p.X[0]), S, m.emb, p.ENVW, W(p.W0e), p.ENVW, S, p.ENVW, EPI_STORE);
   GenTp tp{};
   tp.n = n; tp.U = U; tp.S = S; tp.e0 = e0; tp.c0 = c0; tp.ldin = p.SIN; tp.envw = p.ENVW; tp.edge_c = g.edge_c; tp.Y = W(p.Y);
   for (int k = 0; k < nl; ++k) {
     const GenLayer& lw = m.layer[k];
-    r.gemm(W(p.X[k]), S, lw.env, p.ENVW, W(p.Wk[k]), p.ENVW, S, p.ENVW, false);
+    r.gemm(W(p.X[k]), S, lw.env, p.ENVW, W(p.Wk[k]), p.ENVW, S, p.ENVW, EPI_STORE);
     k_gen_gamma<<<nc, 256, 0, st>>>(c0, e0, g.rowptr, U, p.NSH, p.ENVW, W(p.Wk[k]), W(p.Y), m.inv_sqrt_n, W(p.gamma[k])); r.check();
-    k_gen_cols<<<r.blocks((long)n * S), 256, 0, st>>>(n, S, W(p.X[k]), S, W(p.IN), p.SIN, 0); r.check();
     GenTp a = tp;
     a.vin = k == 0 ? W(p.W0e) : W(p.V[k]); a.gamma = W(p.gamma[k]); a.omega_t = lw.omega_t;
     a.vout = k < nl - 1 ? W(p.V[k + 1]) : nullptr; a.IN = W(p.IN);
     if (r.err == cudaSuccess) r.err = gen_tp_launch(L, lw.kind, k == 0, false, a, st);
     ++r.launches;
     r.mlp_fwd(lw.mlp, W(p.IN), p.SIN, k + 1, W(p.M[k + 1]));
-    k_gen_mix<<<r.blocks((long)n * S), 256, 0, st>>>(n, S, W(p.X[k]), W(p.M[k + 1]), W(p.u), lw.a, lw.b, W(p.X[k + 1])); r.check();
+    k_gen_mix<<<r.blocks((long)n * S), 256, 0, st>>>(n, S, W(p.X[k]), W(p.M[k + 1]), W(p.u), lw.a, lw.b, W(p.X[k + 1]),
+                                                     k < nl - 1 ? W(p.IN) : nullptr, p.SIN); r.check();   // x^{k+1} is also the head of the next MLP input
   }
   // ---- readout, energies
   float* ar = W(p.SC[0]);
-  r.gemm(W(p.X[nl]), S, m.ro0, m.R, ar, m.R, S, m.R, false);
-  k_gen_silu<<<r.blocks((long)n * m.R), 256, 0, st>>>((long)n * m.R, ar, W(p.Dr)); r.check();
+  r.gemm(W(p.X[nl]), S, m.ro0, m.R, ar, m.R, S, m.R, EPI_SILU, W(p.Dr));
   k_gen_readout<<<r.blocks(n, 128), 128, 0, st>>>(n, e0, m.R, ar, W(p.Dr), m.ro1, g.rvec, tb, W(p.Ee), g.edge_energy); r.check();
   k_gen_esum<<<r.blocks(nc, 128), 128, 0, st>>>(c0, nc, e0, g.rowptr, W(p.Ee), g.esum); r.check();
   // ---- backward
-  r.gemm(W(p.Dr), m.R, m.ro0_t, S, W(p.dX), S, m.R, S, false);
+  r.gemm(W(p.Dr), m.R, m.ro0_t, S, W(p.dX), S, m.R, S, EPI_STORE);
   int cur = 0;                                       // dV[cur] = dE/dV^{k+1} (valid for k < nl-1)
   for (int k = nl - 1; k >= 0; --k) {
     const GenLayer& lw = m.layer[k];
     float* dM = W(p.SC[2]);
     k_gen_mix_bwd<<<r.blocks((long)n * 32), 256, 0, st>>>(n, S, W(p.dX), W(p.M[k + 1]), W(p.u), lw.a, lw.b, dM, W(p.du)); r.check();
-    r.mlp_bwd(lw.mlp, dM, k + 1, W(p.IN));          // dIN = (dx | ds)
-    k_gen_cols<<<r.blocks((long)n * S), 256, 0, st>>>(n, S, W(p.IN), p.SIN, W(p.dX), S, 1); r.check();
+    r.mlp_bwd(lw.mlp, dM, k + 1, W(p.IN), W(p.dX), S);   // dIN = (dx | ds): dx added to dX, ds -> columns S.. of IN
     GenTp a = tp;
     a.vin = k == 0 ? W(p.W0e) : W(p.V[k]); a.gamma = W(p.gamma[k]); a.omega_t = lw.omega_t; a.IN = W(p.IN);
     a.dvout = k < nl - 1 ? W(p.dV[cur]) : nullptr; a.dvin = W(p.dV[cur ^ 1]); a.dge = W(p.dGe);
     if (r.err == cudaSuccess) r.err = gen_tp_launch(L, lw.kind, k == 0, true, a, st);
     ++r.launches;
     cur ^= 1;                                        // dV[cur] = dE/dV^k
-    k_gen_dgamma<<<nc, 256, 0, st>>>(c0, e0, g.rowptr, U, p.NSH, W(p.dGe), W(p.dgamma)); r.check();
+    k_gen_dgamma<<<nc, 256, 0, st>>>(c0, e0, g.rowptr, U, p.NSH, (size_t)n * U, W(p.dGe), W(p.dgamma)); r.check();
     float* dw = W(p.SC[2]);
-    k_gen_env_bwd_w<<<r.blocks((long)n * p.ENVW), 256, 0, st>>>(n, e0, c0, g.edge_c, U, L, W(p.dgamma), W(p.Y), m.inv_sqrt_n, dw); r.check();
-    k_gen_env_bwd_y<<<r.blocks((long)n * p.NSH), 256, 0, st>>>(n, e0, c0, g.edge_c, U, L, W(p.dgamma), W(p.Wk[k]), m.inv_sqrt_n, W(p.dY)); r.check();
-    r.gemm(dw, p.ENVW, lw.env_t, S, W(p.dX), S, p.ENVW, S, true);
+    launch_outer_bwd(r, L, 0, e0, c0, g.edge_c, W(p.dgamma), W(p.Wk[k]), m.inv_sqrt_n, dw);
+    r.gemm(dw, p.ENVW, lw.env_t, S, W(p.dX), S, p.ENVW, S, EPI_ADD);
     if (k == 0) {
-      k_gen_v0_bwd_w<<<r.blocks((long)n * p.ENVW), 256, 0, st>>>(n, U, L, W(p.dV[cur]), W(p.Y), dw); r.check();
-      k_gen_v0_bwd_y<<<r.blocks((long)n * p.NSH), 256, 0, st>>>(n, U, L, W(p.dV[cur]), W(p.W0e), W(p.dY)); r.check();
-      r.gemm(dw, p.ENVW, m.emb_t, S, W(p.dX), S, p.ENVW, S, true);
+      launch_outer_bwd(r, L, 1, e0, c0, g.edge_c, W(p.dV[cur]), W(p.W0e), 1.f, dw);
+      r.gemm(dw, p.ENVW, m.emb_t, S, W(p.dX), S, p.ENVW, S, EPI_ADD);
     }
   }
   // two-body: x0 = m0 * u

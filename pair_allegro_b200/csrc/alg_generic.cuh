@@ -56,15 +56,15 @@ cudaError_t gen_run_chunk(const GenModel& m, const GenTables& tb, const GenEdges
 struct GenTp {
   int n, U, S, e0, c0, ldin, envw;
   const int* edge_c;
-  const float* vin;        // first layer: w0 [n][ENVW]; else V^k [n][U][DIN]
+  const float* vin;        // first layer: w0 [n][ENVW]; else V^k [DIN][n][U] (component-major)
   const float* Y;          // [n][NSH]
   const float* gamma;      // [nc][NSH*U]
   const float* omega_t;
-  float* vout;             // forward: V^{k+1} [n][U][DOUT] or nullptr
+  float* vout;             // forward: V^{k+1} [DOUT][n][U] or nullptr
   float* IN;               // forward: s written to columns S.. of [n][ldin]; backward: ds read from there
   const float* dvout;      // backward: dV^{k+1} or nullptr
-  float* dvin;             // backward: [n][U][DIN]
-  float* dge;              // backward: per-edge dGamma [n][U][NSH]
+  float* dvin;             // backward: [DIN][n][U]
+  float* dge;              // backward: per-edge dGamma [NSH][n][U]
 };
 struct GenTpDims { int din, dout, npath, n0; };
 GenTpDims gen_tp_dims(int L, char kind);

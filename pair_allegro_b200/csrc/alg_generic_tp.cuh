@@ -14,13 +14,14 @@ __global__ void __launch_bounds__(128) k_gen_tp_fwd(const GenTp a) {
   const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (long)a.n * a.U) return;
   const int q = (int)(idx / a.U), u = (int)(idx % a.U);
+  const size_t NU = (size_t)a.n * a.U;                  // V / dV / dG_e are component-major: [component][edge][channel] (coalesced)
   float Vin[TP::DIN], G[NSH], Vout[TP::DOUT], s[TP::N0];
   if (FIRST) {
 #pragma unroll
     for (int lm = 0; lm < NSH; ++lm) Vin[lm < TP::DIN ? lm : 0] = a.vin[(size_t)q * a.envw + lsel(lm) * a.U + u] * a.Y[(size_t)q * NSH + lm];
   } else {
 #pragma unroll
-    for (int c = 0; c < TP::DIN; ++c) Vin[c] = a.vin[((size_t)q * a.U + u) * TP::DIN + c];
+    for (int c = 0; c < TP::DIN; ++c) Vin[c] = a.vin[(size_t)c * NU + idx];
   }
   const float* gam = a.gamma + (size_t)(a.edge_c[a.e0 + q] - a.c0) * NSH * a.U;
 #pragma unroll
@@ -30,7 +31,7 @@ __global__ void __launch_bounds__(128) k_gen_tp_fwd(const GenTp a) {
   TP::template fwd<1>(Vin, G, a.omega_t + (size_t)u * TP::NPATH, Vout, s);
   if (a.vout) {
 #pragma unroll
-    for (int c = 0; c < TP::DOUT; ++c) a.vout[((size_t)q * a.U + u) * TP::DOUT + c] = Vout[c];
+    for (int c = 0; c < TP::DOUT; ++c) a.vout[(size_t)c * NU + idx] = Vout[c];
   }
 #pragma unroll
   for (int i = 0; i < TP::N0; ++i) a.IN[(size_t)q * a.ldin + a.S + i * a.U + u] = s[i];
@@ -43,26 +44,27 @@ __global__ void __launch_bounds__(128) k_gen_tp_bwd(const GenTp a) {
   const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (long)a.n * a.U) return;
   const int q = (int)(idx / a.U), u = (int)(idx % a.U);
+  const size_t NU = (size_t)a.n * a.U;
   float Vin[TP::DIN], G[NSH], dVout[TP::DOUT], ds[TP::N0], dVin[TP::DIN], dG[NSH];
   if (FIRST) {
 #pragma unroll
     for (int lm = 0; lm < NSH; ++lm) Vin[lm < TP::DIN ? lm : 0] = a.vin[(size_t)q * a.envw + lsel(lm) * a.U + u] * a.Y[(size_t)q * NSH + lm];
   } else {
 #pragma unroll
-    for (int c = 0; c < TP::DIN; ++c) Vin[c] = a.vin[((size_t)q * a.U + u) * TP::DIN + c];
+    for (int c = 0; c < TP::DIN; ++c) Vin[c] = a.vin[(size_t)c * NU + idx];
   }
   const float* gam = a.gamma + (size_t)(a.edge_c[a.e0 + q] - a.c0) * NSH * a.U;
 #pragma unroll
   for (int lm = 0; lm < NSH; ++lm) G[lm] = gam[lm * a.U + u];
 #pragma unroll
-  for (int c = 0; c < TP::DOUT; ++c) dVout[c] = a.dvout ? a.dvout[((size_t)q * a.U + u) * TP::DOUT + c] : 0.f;
+  for (int c = 0; c < TP::DOUT; ++c) dVout[c] = a.dvout ? a.dvout[(size_t)c * NU + idx] : 0.f;
 #pragma unroll
   for (int i = 0; i < TP::N0; ++i) ds[i] = a.IN[(size_t)q * a.ldin + a.S + i * a.U + u];
   TP::template bwd<1>(Vin, G, a.omega_t + (size_t)u * TP::NPATH, dVout, ds, dVin, dG);
 #pragma unroll
-  for (int c = 0; c < TP::DIN; ++c) a.dvin[((size_t)q * a.U + u) * TP::DIN + c] = dVin[c];
+  for (int c = 0; c < TP::DIN; ++c) a.dvin[(size_t)c * NU + idx] = dVin[c];
 #pragma unroll
-  for (int lm = 0; lm < NSH; ++lm) a.dge[((size_t)q * a.U + u) * NSH + lm] = dG[lm];
+  for (int lm = 0; lm < NSH; ++lm) a.dge[(size_t)lm * NU + idx] = dG[lm];
 }
 
 template <int L, char KIND, bool FIRST>
