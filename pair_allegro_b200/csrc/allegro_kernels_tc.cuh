@@ -24,6 +24,15 @@
 #include "tp_gen.cuh"
 #include "umma.cuh"
 
+#ifndef ALG_TP_DBUF_L3
+#define ALG_TP_DBUF_L3 0
+#endif
+#ifndef ALG_TP_FWD_DBUF_L3
+#define ALG_TP_FWD_DBUF_L3 1
+#endif
+#ifndef ALG_TP_DBUF_BELOW
+#define ALG_TP_DBUF_BELOW 3
+#endif
 namespace alg {
 
 // the large building blocks: inlined.  (Measured on the B200: as real functions -- __noinline__, one copy each -- the
@@ -650,18 +659,27 @@ __device__ ALG_NI void tc_tp_forward(const ChunkArgs& a, const LayerW& lw, const
       }
     }
   };
-  In ra[TB], rb[TB];
-  issue(0, ra);
+  constexpr bool DBUF = ALG_TP_FWD_DBUF_L3 || L < 3;
+  In ra[TB], rb[DBUF ? TB : 1];
+  if (DBUF) issue(0, ra);
   if (b == 0) {
 #pragma unroll 1
-    for (int i = TB; i < D::CPT; ++i) Raw::prefetch(a, tile, k, e, uh * D::CPT + i);
+    for (int i = DBUF ? TB : 0; i < D::CPT; ++i) Raw::prefetch(a, tile, k, e, uh * D::CPT + i);
   }
+  if constexpr (DBUF) {
 #pragma unroll 1
-  for (int s = 0; s < NS; s += 2) {
-    issue(s + 1, rb);
-    eval(s, ra);
-    if (s + 2 < NS) issue(s + 2, ra);
-    eval(s + 1, rb);
+    for (int s = 0; s < NS; s += 2) {
+      issue(s + 1, rb);
+      eval(s, ra);
+      if (s + 2 < NS) issue(s + 2, ra);
+      eval(s + 1, rb);
+    }
+  } else {
+#pragma unroll 1
+    for (int s = 0; s < NS; ++s) {
+      issue(s, ra);
+      eval(s, ra);
+    }
   }
 }
 
@@ -727,10 +745,14 @@ __device__ ALG_NI void tc_tp_backward(const ChunkArgs& a, const LayerW& lw, cons
       for (int lm = 0; lm < D::NSH; ++lm) DG[e * D::DGS + lm * D::CHU + ul] = dG[lm];
     }
   };
-  In ra[TB], rb[TB];
-  issue(0, 0, ra);
+  // l_max = 3: one channel of a full-parity product already needs ~100 live registers (Vin, dVin, G, dG, dVout); a second
+  // set of prefetched inputs pushes the arrays into local memory, so the loads are issued right before their evaluation
+  // (the lines were pulled into L2 by the prefetch loop below)
+  constexpr bool DBUF = ALG_TP_DBUF_L3 || L < ALG_TP_DBUF_BELOW;
+  In ra[TB], rb[DBUF ? TB : 1];
+  if (DBUF) issue(0, 0, ra);
 #pragma unroll 1
-  for (int i = TB; i < U / D::CPH; ++i) {               // all remaining channels of this thread -> L2
+  for (int i = DBUF ? TB : 0; i < U / D::CPH; ++i) {    // all remaining channels of this thread -> L2
     const int u = chan(i / CPP, i % CPP);
     Raw::prefetch(a, tile, k, e, u);
     if (HAS_DVOUT) {
@@ -739,13 +761,21 @@ __device__ ALG_NI void tc_tp_backward(const ChunkArgs& a, const LayerW& lw, cons
   }
 #pragma unroll 1
   for (int pass = 0; pass < NPASS; ++pass) {
+    if constexpr (DBUF) {
 #pragma unroll 1
-    for (int jb = 0; jb < BPP; jb += 2) {
-      issue(pass, jb + 1, rb);
-      eval(pass, jb, ra);
-      if (jb + 2 < BPP) issue(pass, jb + 2, ra);
-      else if (pass + 1 < NPASS) issue(pass + 1, 0, ra);
-      eval(pass, jb + 1, rb);
+      for (int jb = 0; jb < BPP; jb += 2) {
+        issue(pass, jb + 1, rb);
+        eval(pass, jb, ra);
+        if (jb + 2 < BPP) issue(pass, jb + 2, ra);
+        else if (pass + 1 < NPASS) issue(pass + 1, 0, ra);
+        eval(pass, jb + 1, rb);
+      }
+    } else {
+#pragma unroll 1
+      for (int jb = 0; jb < BPP; ++jb) {
+        issue(pass, jb, ra);
+        eval(pass, jb, ra);
+      }
     }
     __syncthreads();
     {
