@@ -647,10 +647,12 @@ def run_ours(args):
     blo, bhi = atoms.x.min(0) - 1e-9, atoms.x.max(0) + 1e-9
     rneigh = cfg["r_max"] + SKIN
 
+    cyc_steps = NEIGH_EVERY if ms / K <= 500.0 else 2        # steps of half a second and more: a short cycle keeps the bench bounded
+
     def neigh_cycle():
         nbld.needs_rebuild(ntot, d_x.data_ptr(), SKIN, stream=cs)
         nbld.build(nl, ng, d_x.data_ptr(), blo, bhi, rneigh, maxn, d_nb2.data_ptr(), d_num2.data_ptr(), want_max=False, stream=cs)
-        for _ in range(NEIGH_EVERY):
+        for _ in range(cyc_steps):
             d_f.zero_()
             comm.forward(d_x.data_ptr(), cs)
             h.compute_device(nl, ng, d_x.data_ptr(), d_type.data_ptr(), d_ilist.data_ptr(), d_num2.data_ptr(), d_nb2.data_ptr(),
@@ -673,9 +675,9 @@ def run_ours(args):
     torch.cuda.synchronize()
     ms_build = t0e.elapsed_time(t1e)
     ms_cycle = timed(neigh_cycle, 1)
-    extra["device_neighbor_cycle"] = {"value": total_atoms * NEIGH_EVERY / (ms_cycle * 1e-3) / 1e6, "unit": "Matom-steps/s", "steps": NEIGH_EVERY,
+    extra["device_neighbor_cycle"] = {"value": total_atoms * cyc_steps / (ms_cycle * 1e-3) / 1e6, "unit": "Matom-steps/s", "steps": cyc_steps,
                                       "neigh_build_ms": ms_build,
-                                      "note": "alg_neigh_check + alg_neigh_build (cell list on the device) then %d x (halo, alg_compute_device); forces checked against the set-up list" % NEIGH_EVERY}
+                                      "note": "alg_neigh_check + alg_neigh_build (cell list on the device) then %d x (halo, alg_compute_device); forces checked against the set-up list" % cyc_steps}
     nbld.close()
 
     cpu = None
