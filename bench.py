@@ -635,50 +635,51 @@ def run_ours(args):
         h_f.copy_(d_f[:nl], non_blocking=True)
         torch.cuda.current_stream().synchronize()
 
-    step_e2e_dev()
-    ms_e2e_dev = timed(step_e2e_dev, K)
-    extra["e2e_device_entry"] = {"value": total_atoms * K / (ms_e2e_dev * 1e-3) / 1e6, "unit": "Matom-steps/s",
-                                 "note": "pinned host x -> device, NCCL halo, alg_compute_device (scalars read back), local forces -> pinned host, every step"}
+    if not args.lean:
+        step_e2e_dev()
+        ms_e2e_dev = timed(step_e2e_dev, K)
+        extra["e2e_device_entry"] = {"value": total_atoms * K / (ms_e2e_dev * 1e-3) / 1e6, "unit": "Matom-steps/s",
+                                     "note": "pinned host x -> device, NCCL halo, alg_compute_device (scalars read back), local forces -> pinned host, every step"}
 
-    # a whole neighbour cycle with the list built on the device too (alg_neigh_*): Verlet check + cell-list build on the
-    # first step, then NEIGH_EVERY force evaluations on that list -- nothing of the cycle touches the host
-    nbld = capi.NeighborBuilder(local_rank)
-    d_nb2, d_num2 = torch.zeros_like(d_nb), torch.zeros_like(d_num)
-    blo, bhi = atoms.x.min(0) - 1e-9, atoms.x.max(0) + 1e-9
-    rneigh = cfg["r_max"] + SKIN
+        # a whole neighbour cycle with the list built on the device too (alg_neigh_*): Verlet check + cell-list build on the
+        # first step, then NEIGH_EVERY force evaluations on that list -- nothing of the cycle touches the host
+        nbld = capi.NeighborBuilder(local_rank)
+        d_nb2, d_num2 = torch.zeros_like(d_nb), torch.zeros_like(d_num)
+        blo, bhi = atoms.x.min(0) - 1e-9, atoms.x.max(0) + 1e-9
+        rneigh = cfg["r_max"] + SKIN
 
-    cyc_steps = NEIGH_EVERY if ms / K <= 500.0 else 2        # steps of half a second and more: a short cycle keeps the bench bounded
+        cyc_steps = NEIGH_EVERY if ms / K <= 500.0 else 2        # steps of half a second and more: a short cycle keeps the bench bounded
 
-    def neigh_cycle():
-        nbld.needs_rebuild(ntot, d_x.data_ptr(), SKIN, stream=cs)
+        def neigh_cycle():
+            nbld.needs_rebuild(ntot, d_x.data_ptr(), SKIN, stream=cs)
+            nbld.build(nl, ng, d_x.data_ptr(), blo, bhi, rneigh, maxn, d_nb2.data_ptr(), d_num2.data_ptr(), want_max=False, stream=cs)
+            for _ in range(cyc_steps):
+                d_f.zero_()
+                comm.forward(d_x.data_ptr(), cs)
+                h.compute_device(nl, ng, d_x.data_ptr(), d_type.data_ptr(), d_ilist.data_ptr(), d_num2.data_ptr(), d_nb2.data_ptr(),
+                                 maxn, 1, d_f.data_ptr(), 0, want_scalars=False, vflag=vflag, stream=cs)
+                comm.reverse(d_f.data_ptr(), cs)
+
+        neigh_cycle()
+        torch.cuda.synchronize()
+        if not torch.equal(d_num2, d_num):
+            raise RuntimeError("alg_neigh_build: neighbour counts differ from the list the bench was set up with")
+        f_ref = d_f.clone()
+        step_device()
+        torch.cuda.synchronize()
+        if float((d_f - f_ref).abs().max()) > 1e-4:
+            raise RuntimeError("forces on the device-built neighbour list differ from those on the set-up list")
+        t0e, t1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0e.record()
         nbld.build(nl, ng, d_x.data_ptr(), blo, bhi, rneigh, maxn, d_nb2.data_ptr(), d_num2.data_ptr(), want_max=False, stream=cs)
-        for _ in range(cyc_steps):
-            d_f.zero_()
-            comm.forward(d_x.data_ptr(), cs)
-            h.compute_device(nl, ng, d_x.data_ptr(), d_type.data_ptr(), d_ilist.data_ptr(), d_num2.data_ptr(), d_nb2.data_ptr(),
-                             maxn, 1, d_f.data_ptr(), 0, want_scalars=False, vflag=vflag, stream=cs)
-            comm.reverse(d_f.data_ptr(), cs)
-
-    neigh_cycle()
-    torch.cuda.synchronize()
-    if not torch.equal(d_num2, d_num):
-        raise RuntimeError("alg_neigh_build: neighbour counts differ from the list the bench was set up with")
-    f_ref = d_f.clone()
-    step_device()
-    torch.cuda.synchronize()
-    if float((d_f - f_ref).abs().max()) > 1e-4:
-        raise RuntimeError("forces on the device-built neighbour list differ from those on the set-up list")
-    t0e, t1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    t0e.record()
-    nbld.build(nl, ng, d_x.data_ptr(), blo, bhi, rneigh, maxn, d_nb2.data_ptr(), d_num2.data_ptr(), want_max=False, stream=cs)
-    t1e.record()
-    torch.cuda.synchronize()
-    ms_build = t0e.elapsed_time(t1e)
-    ms_cycle = timed(neigh_cycle, 1)
-    extra["device_neighbor_cycle"] = {"value": total_atoms * cyc_steps / (ms_cycle * 1e-3) / 1e6, "unit": "Matom-steps/s", "steps": cyc_steps,
-                                      "neigh_build_ms": ms_build,
-                                      "note": "alg_neigh_check + alg_neigh_build (cell list on the device) then %d x (halo, alg_compute_device); forces checked against the set-up list" % cyc_steps}
-    nbld.close()
+        t1e.record()
+        torch.cuda.synchronize()
+        ms_build = t0e.elapsed_time(t1e)
+        ms_cycle = timed(neigh_cycle, 1)
+        extra["device_neighbor_cycle"] = {"value": total_atoms * cyc_steps / (ms_cycle * 1e-3) / 1e6, "unit": "Matom-steps/s", "steps": cyc_steps,
+                                          "neigh_build_ms": ms_build,
+                                          "note": "alg_neigh_check + alg_neigh_build (cell list on the device) then %d x (halo, alg_compute_device); forces checked against the set-up list" % cyc_steps}
+        nbld.close()
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -731,6 +732,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-pin", action="store_true", help="e2e leg: do not let the library pin (cudaHostRegister) the caller's x / f / type arrays")
     ap.add_argument("--no-energy-check", action="store_true", help="N>1 weak scaling: skip the N x single-box energy assertion")
+    ap.add_argument("--lean", action="store_true", help="skip the two extra legs (e2e_device_entry, device_neighbor_cycle); for expensive multi-GPU runs")
     ap.add_argument("--e2e-short", action="store_true", help="e2e leg: time exactly --steps steps instead of whole neighbour-list cycles (10 steps)")
     ap.add_argument("--gemm", default="tc", choices=["tc", "ffma", "generic"])
     ap.add_argument("--pipeline", default="auto", choices=["auto", "fused", "tiled"])

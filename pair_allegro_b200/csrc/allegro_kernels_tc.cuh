@@ -30,6 +30,9 @@
 #ifndef ALG_TP_FWD_DBUF_L3
 #define ALG_TP_FWD_DBUF_L3 1
 #endif
+#ifndef ALG_TP_L1_PREFETCH
+#define ALG_TP_L1_PREFETCH 0
+#endif
 #ifndef ALG_TP_DBUF_BELOW
 #define ALG_TP_DBUF_BELOW 3
 #endif
@@ -408,6 +411,8 @@ template <int L> __device__ ALG_NI RowSrc tc_stage_rows(const TcCtx& c, const fl
 // the first global loads of every kernel (edge vector, centre slot), issued before the TMEM allocation /
 // barrier of tc_begin so that their DRAM latency overlaps the CTA start-up
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+template <bool L1> __device__ __forceinline__ void prefetch_lx(const void* p) { if (L1) prefetch_l1(p); else prefetch_l2(p); }
 struct GeomIn { float4 rv; int centre; };
 __device__ __forceinline__ GeomIn tc_geom_load(const ChunkArgs& a, int es, int nvalid) {
   const int e = es + min((int)(threadIdx.x & 127), nvalid - 1);
@@ -552,14 +557,14 @@ template <int N> __device__ __forceinline__ void vec_store(float* g, int e, cons
     for (int cc = 0; cc < N; ++cc) g[cc * 128 + e] = v[cc];
   }
 }
-template <int N> __device__ __forceinline__ void vec_prefetch(const float* g, int e) {
+template <int N, bool L1 = false> __device__ __forceinline__ void vec_prefetch(const float* g, int e) {
   constexpr int NP = vpad(N);
   if constexpr (NP % 4 == 0) {
 #pragma unroll
-    for (int q = 0; q < NP / 4; ++q) prefetch_l2(g + ((q * 128 + e) << 2));
+    for (int q = 0; q < NP / 4; ++q) prefetch_lx<L1>(g + ((q * 128 + e) << 2));
   } else {
 #pragma unroll
-    for (int cc = 0; cc < N; ++cc) prefetch_l2(g + cc * 128 + e);
+    for (int cc = 0; cc < N; ++cc) prefetch_lx<L1>(g + cc * 128 + e);
   }
 }
 // raw global inputs of one tensor-product channel: FIRST layers read the L+1 embed weights w0[l][u]
@@ -568,14 +573,15 @@ template <int L, bool FIRST, int DIN> struct VinRaw {
   static constexpr int N = FIRST ? (L + 1) : DIN;
   float v[N];
   // pull the lines a later issue() will read into L2 (no registers held)
+  template <bool L1 = false>
   __device__ __forceinline__ static void prefetch(const ChunkArgs& a, int tile, int k, int e, int u) {
     using D = DimsTC<L>; constexpr int TM = 128;
     if (FIRST) {
       const float* W0g = a.W0 + (size_t)tile * D::ENVW * TM;
 #pragma unroll
-      for (int l = 0; l <= L; ++l) prefetch_l2(W0g + (l * U + u) * TM + e);
+      for (int l = 0; l <= L; ++l) prefetch_lx<L1>(W0g + (l * U + u) * TM + e);
     } else {
-      vec_prefetch<DIN>(a.V[k] + ((size_t)tile * U + u) * vpad(DIN) * TM, e);
+      vec_prefetch<DIN, L1>(a.V[k] + ((size_t)tile * U + u) * vpad(DIN) * TM, e);
     }
   }
   __device__ __forceinline__ void issue(const ChunkArgs& a, int tile, int k, int e, int u) {
@@ -774,6 +780,14 @@ __device__ ALG_NI void tc_tp_backward(const ChunkArgs& a, const LayerW& lw, cons
 #pragma unroll 1
       for (int jb = 0; jb < BPP; ++jb) {
         issue(pass, jb, ra);
+        if (ALG_TP_L1_PREFETCH && (jb + 1 < BPP || pass + 1 < NPASS)) {      // next channel: L2 -> L1 while this one is evaluated
+          const int un = jb + 1 < BPP ? chan(pass, (jb + 1) * TB) : chan(pass + 1, 0);
+#pragma unroll
+          for (int bb = 0; bb < TB; ++bb) {
+            Raw::template prefetch<true>(a, tile, k, e, un + bb);
+            if (HAS_DVOUT) vec_prefetch<TP::DOUT, true>(dVnext + ((size_t)tile * U + un + bb) * vpad(TP::DOUT) * TM, e);
+          }
+        }
         eval(pass, jb, ra);
       }
     }
