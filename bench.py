@@ -662,13 +662,17 @@ def run_ours(args):
 
         neigh_cycle()
         torch.cuda.synchronize()
-        if not torch.equal(d_num2, d_num):
-            raise RuntimeError("alg_neigh_build: neighbour counts differ from the list the bench was set up with")
+        # a pair within an ulp of r_max + skin may fall on either side in the two builders (harmless: the pair style filters at
+        # r_max); what must agree are the forces.  The verdict is taken collectively so that no rank leaves the others in a barrier.
+        n_mismatch = int((d_num2 != d_num).sum().item())
         f_ref = d_f.clone()
         step_device()
         torch.cuda.synchronize()
-        if float((d_f - f_ref).abs().max()) > 1e-4:
-            raise RuntimeError("forces on the device-built neighbour list differ from those on the set-up list")
+        bad = torch.tensor([1.0 if (float((d_f - f_ref).abs().max()) > 1e-4 or n_mismatch > 8) else 0.0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(bad, op=dist.ReduceOp.MAX)
+        if float(bad.item()) > 0:
+            raise RuntimeError("forces on the device-built neighbour list differ from those on the set-up list (%d atoms with different counts on rank %d)" % (n_mismatch, rank))
         t0e, t1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0e.record()
         nbld.build(nl, ng, d_x.data_ptr(), blo, bhi, rneigh, maxn, d_nb2.data_ptr(), d_num2.data_ptr(), want_max=False, stream=cs)
