@@ -41,6 +41,27 @@ def test_no_cpu_fallback(ensure_built):
     assert ei.value.code == -3 and "no CPU fallback" in str(ei.value)
 
 
+def test_neighbor_builder_and_comm_fail_loudly_without_gpu(ensure_built):
+    """the helper objects of the C-ABI (device neighbour list, NCCL halo) have no CPU path either"""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from pair_allegro_b200 import capi
+    with pytest.raises(capi.AllegroError):
+        capi.NeighborBuilder(0)
+    with pytest.raises(capi.AllegroError):
+        capi.Comm(0, 1, 0, None)
+
+
+def test_sass_carries_tensor_core_and_tma_instructions(ensure_built):
+    """the hot kernels are what DESIGN.md says they are: tcgen05 MMAs (UTCHMMA), TMEM stores/loads (STTM / LDTM), bulk copies
+    (UBLKCP) in the tile kernels, warp-level HMMA in the width-generic GEMM"""
+    import subprocess
+    sass = subprocess.run(["cuobjdump", "-sass", ensure_built], capture_output=True, text=True).stdout
+    for mnemonic in ("UTCHMMA", "STTM", "LDTM", "UBLKCP", "HMMA"):
+        assert mnemonic in sass, mnemonic
+
+
 def test_create_rejects_bad_file(ensure_built, tmp_path):
     """argument validation happens before any device work only for null args; a malformed file on a
     GPU-less box still reports the missing device first -- both are loud errors"""
