@@ -144,9 +144,10 @@ ALG_API int alg_compute_host(alg_handle* h, int nlocal, int nghost, const double
  * d_eatom (may be NULL) assigned for locals (:311-313).  `eng` and `virial6` are HOST
  * pointers written before return (the call synchronises the stream once for them, like
  * the reference's parallel_reduce result :318 and virial .cpu() :329); pass NULL for both
- * to keep the call fully asynchronous: nothing in the call then waits for the device (the tile plan of the fused
- * pipeline is built on the device; the reference blocks on its edge count every step,
- * pair_nequip_allegro_kokkos.cpp:203-206).  Such a step is verified lazily: if it met an atom with more than fused_batch*128
+ * to keep the call fully asynchronous: nothing in the call then waits for the device (the chunk plan of the default
+ * chunked pipeline and the tile plan of the fused pipeline are built on the device; the reference blocks on its edge count
+ * every step, pair_nequip_allegro_kokkos.cpp:203-206; models on the width-generic pipeline, option gemm=generic, build their
+ * chunk plan on the host and synchronise once inside the call).  Such a step is verified lazily: if it met an atom with more than fused_batch*128
  * neighbours, or overflowed edge arrays sized without max_neighbors, it wrote no forces and the NEXT call on the handle
  * returns ALG_ESTATE (then switches to the tiled pipeline / larger arrays).  Calls that pass `eng` or `virial6` are
  * verified before they return and such steps are repeated transparently.  `stream` is a cudaStream_t (0 = legacy default). */
